@@ -1,0 +1,293 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates the golden fixtures under ``tests/golden/``.
+
+Run in the build container (needs /root/reference; it cannot run on the GPU box):
+
+    python -m oracle.make_golden
+
+Every fixture is produced by executing the *reference source itself*, unmodified,
+over ``oracle/tf_standin.py`` (torch-CPU eager; TensorFlow is not installable here):
+  * ``Code/model.py``  custom_conv2d / variants / pooling / upsampling / lrelu /
+    custom_lin / get_model_reg_multi_scale
+  * ``Code/utils.py``  normalizeTensor, getFacesLargeAdj, getEdgeMap, getVerticesFaces
+  * ``Code/train.py``  update_position2, update_position_MS, faceNormalsLoss
+  * ``Code/dataClasses.py`` InferenceMesh preprocessing (real pyramids, permutations)
+Gradients come from torch autograd through the same reference code.
+All inputs, injected weights (RandomState draws in variable-creation order) and
+outputs are stored as float32/int32 ``.npz`` so the oracle port and the CUDA path
+can be checked against them anywhere.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_runner as rr  # noqa: E402
+from facet_graph_convolution_b200 import mesh  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t if dtype is None else t.to(dtype)
+
+
+def random_adj(rs, B, N, K, p_zero_row=0.05, p_pad=0.3, dup=True):
+    """1-indexed adjacency with self in column 0, random neighbours, zero padding at the tail,
+    a few all-zero rows (cnt = 0) and duplicate neighbours."""
+    adj = rs.randint(1, N + 1, size=(B, N, K)).astype(np.int32)
+    adj[:, :, 0] = np.arange(1, N + 1)
+    valid = rs.randint(1, K + 1, size=(B, N))
+    mask = np.arange(K)[None, None, :] < valid[:, :, None]
+    if p_pad > 0:
+        adj = np.where(mask, adj, 0)
+    if dup and K > 3:
+        adj[:, ::7, 2] = adj[:, ::7, 1]
+    zero_rows = rs.rand(B, N) < p_zero_row
+    adj[zero_rows] = 0
+    # a padding hole in the middle of a row must also work (count_nonzero semantics)
+    if K > 4:
+        adj[:, 5::11, 3] = 0
+    return adj.astype(np.int32)
+
+
+def conv_case(ref, name, B, N, Cin, Cout, M, K, seed, bias_mask=True, translation=False):
+    rs = np.random.RandomState(seed)
+    x = rs.randn(B, N, Cin).astype(np.float32)
+    adj = random_adj(rs, B, N, K)
+    gy = rs.randn(B, N, Cout).astype(np.float32)
+    xt = T(x).requires_grad_(True)
+
+    # weights as leaf tensors so autograd reaches them
+    holder = []
+    prov = rr.rng_provider(seed + 1000)
+
+    def provider(shape, stddev, nm):
+        t = T(prov(shape, stddev, nm)).requires_grad_(True)
+        holder.append(t)
+        return t
+
+    ref.tf.variables.reset(provider)
+    # Variable() clones the provided tensor (non-leaf but connected), gradients flow to holder
+    with contextlib.redirect_stdout(io.StringIO()):
+        y, _ = ref.model.custom_conv2d(xt, T(adj), Cout, M, biasMask=bias_mask,
+                                        translation_invariance=translation)
+    (y * T(gy)).sum().backward()
+    names = ["W0", "b", "u", "c"] + ([] if translation else ["v"])
+    d = dict(x=x, adj=adj, gy=gy, y=y.detach().numpy(), gx=xt.grad.numpy(),
+             bias_mask=np.int32(bias_mask), translation=np.int32(translation))
+    for nm, t in zip(names, holder):
+        d[nm] = t.detach().numpy()
+        d["g" + nm] = t.grad.numpy() if t.grad is not None else np.zeros_like(t.detach().numpy())
+    # bit-exact gather fixture (reference get_patches on x itself)
+    d["xg"] = ref.model.get_patches(T(x), T(adj)).numpy()
+    d["q"] = (ref.model.get_weight_assigments_translation_invariance(T(x), T(adj), holder[2].detach(), holder[3].detach())
+              if translation else
+              ref.model.get_weight_assigments(T(x).permute(0, 2, 1), T(adj), holder[2].detach(), holder[4].detach(),
+                                              holder[3].detach())).numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, y.shape)
+
+
+def variant_cases(ref):
+    rs = np.random.RandomState(77)
+    B, N, Cw, Cout, M, K = 1, 60, 5, 8, 4, 6
+    x = rs.randn(B, N, Cw + 3).astype(np.float32)
+    adj = random_adj(rs, B, N, K)
+    d = dict(x=x, adj=adj)
+    for trans in (False, True):
+        (y, _), vs = rr.run(ref.model.custom_conv2d_pos_for_assignment, T(x), T(adj), Cout, M,
+                            translation_invariance=trans, provider=rr.rng_provider(5 + trans))
+        tag = "posassign_t%d_" % trans
+        d[tag + "y"] = rr.to_np(y)
+        for nm, v in zip(["W0", "b", "u", "c"] + ([] if trans else ["vn"]), vs):
+            d[tag + nm] = v
+        (y, _), vs = rr.run(ref.model.custom_conv2d_only_pos_for_assignment, T(x), T(adj), Cout, M,
+                            translation_invariance=trans, provider=rr.rng_provider(9 + trans))
+        tag = "onlypos_t%d_" % trans
+        d[tag + "y"] = rr.to_np(y)
+        for nm, v in zip(["W0", "b", "u", "c"] + ([] if trans else ["v"]), vs):
+            d[tag + nm] = v
+    np.savez_compressed(os.path.join(OUT, "conv_variants.npz"), **d)
+    print("wrote conv_variants")
+
+
+def small_ops(ref):
+    rs = np.random.RandomState(3)
+    x = rs.randn(2, 64, 5).astype(np.float32)
+    xz = x.copy()
+    xz[:, ::3] = 0  # all-zero rows for avg_ignore_zeros
+    xz[:, 4:8] = 0
+    d = dict(x=x, xz=xz)
+    d["pool_max2"] = rr.to_np(ref.model.custom_binary_tree_pooling(T(x), steps=2, pooltype="max"))
+    d["pool_max1"] = rr.to_np(ref.model.custom_binary_tree_pooling(T(x), steps=1, pooltype="max"))
+    d["pool_aiz2"] = rr.to_np(ref.model.custom_binary_tree_pooling(T(xz), steps=2, pooltype="avg_ignore_zeros"))
+    d["up2"] = rr.to_np(ref.model.custom_upsampling(T(x), steps=2))
+    d["lrelu"] = rr.to_np(ref.model.lrelu(T(x), 0.1))
+    y, vs = rr.run(ref.model.custom_lin, T(x), 7, provider=rr.rng_provider(4))
+    d["lin_y"], d["lin_W"], d["lin_b"] = rr.to_np(y), vs[0], vs[1]
+    n = rs.randn(1, 50, 3).astype(np.float32) * 0.02
+    n[0, 7] = 0
+    d["norm_in"] = n
+    d["norm_out"] = rr.to_np(ref.utils.normalizeTensor(T(n)))
+    gt = n.copy() + rs.randn(1, 50, 3).astype(np.float32) * 0.005
+    gt /= np.maximum(np.linalg.norm(gt, axis=-1, keepdims=True), 1e-9)
+    gt[0, 11] = 0
+    gt = gt.astype(np.float32)
+    fn = rr.to_np(ref.utils.normalizeTensor(T(n)))
+    d["loss_fn"], d["loss_gt"] = fn, gt
+    d["loss"] = np.float32(rr.to_np(ref.train.faceNormalsLoss(T(fn), T(gt))))
+    # gradient of loss(normalizeTensor(n)) w.r.t. n through the reference code
+    nt = T(n).requires_grad_(True)
+    ref.train.faceNormalsLoss(ref.utils.normalizeTensor(nt), T(gt)).backward()
+    d["loss_norm_grad"] = nt.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "small_ops.npz"), **d)
+    print("wrote small_ops")
+
+
+def preprocess(ref, V, F, K, multi=False, seed=0, max_patch=25000):
+    """Runs the reference's own preprocessing (dataClasses.py) on arrays."""
+    np.random.seed(seed)
+    ref.dataClasses.K_faces = K
+    im = ref.dataClasses.InferenceMesh(max_patch, 2, 3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if multi:
+            im.fNum, im.vNum = F.shape[0], V.shape[0]
+            ref.dataClasses.PreprocessedData.addMeshWithVertices(im, V, F)
+        else:
+            im.addMesh_TimeEfficient(V, F)
+    return im
+
+
+def net_and_vertex_cases(ref):
+    # ---- C1-shaped single-scale pipeline on icosphere-3 (1280 faces), reference preprocessing
+    V, F = mesh.icosphere(3)
+    Vn = mesh.add_vertex_noise(V, F, 0.3, 0)
+    K = 16
+    im = preprocess(ref, Vn, F, K)
+    x = im.in_list[0].astype(np.float32)
+    adjs = [a.astype(np.int32) for a in im.adj_list[0]]
+    perm = np.asarray(im.permutations[0]).astype(np.int32)
+    nreal = int(im.num_faces[0])
+    y, vs = rr.run(ref.model.get_model_reg_multi_scale, T(x), [T(a) for a in adjs], 1.0,
+                   provider=rr.rng_provider(1234))
+    yn = ref.utils.normalizeTensor(y)
+    outN = rr.to_np(yn)[0][perm][:nreal]
+    pred = ref.utils.normalize(outN)
+    e_map = im.edge_map.astype(np.int32)
+    v_e_map = im.v_e_map.astype(np.int32)
+    verts = Vn[None].astype(np.float32)
+    xo = ref.train.update_position2(T(verts), T(pred[None].astype(np.float32)), T(e_map), T(v_e_map),
+                                    iter_num=60, max_edges=20)
+    d = dict(V=Vn, F=F, x=x, adj0=adjs[0], adj1=adjs[1], adj2=adjs[2], perm=perm, nreal=np.int32(nreal),
+             y_raw=rr.to_np(y), y_norm=rr.to_np(yn), pred_normals=pred, e_map=e_map, v_e_map=v_e_map,
+             verts_in=verts, verts_out=rr.to_np(xo), nparams=np.int32(len(vs)))
+    for i, v in enumerate(vs):
+        d["p%02d" % i] = v
+    np.savez_compressed(os.path.join(OUT, "net_icosphere3.npz"), **d)
+    print("wrote net_icosphere3", x.shape, [a.shape for a in adjs])
+
+    # gradient of the training loss through the whole reference network (small pyramid)
+    rs = np.random.RandomState(21)
+    N0, Kt = 96 * 16 // 16, 8
+    N0 = 96
+    xs = rs.randn(1, N0, 6).astype(np.float32)
+    a0 = random_adj(rs, 1, N0, Kt, p_zero_row=0.0)
+    a1 = random_adj(rs, 1, N0 // 4, Kt, p_zero_row=0.0)
+    a2 = random_adj(rs, 1, N0 // 16, Kt, p_zero_row=0.0)
+    gt = rs.randn(1, N0, 3).astype(np.float32)
+    gt /= np.linalg.norm(gt, axis=-1, keepdims=True)
+    gt[0, 5] = 0
+    holder = []
+    prov = rr.rng_provider(99)
+
+    def provider(shape, stddev, nm):
+        t = T(prov(shape, stddev, nm)).requires_grad_(True)
+        holder.append(t)
+        return t
+
+    ref.tf.variables.reset(provider)
+    with contextlib.redirect_stdout(io.StringIO()):
+        yt = ref.model.get_model_reg_multi_scale(T(xs), [T(a0), T(a1), T(a2)], 1.0)
+    loss = ref.train.faceNormalsLoss(ref.utils.normalizeTensor(yt), T(gt))
+    loss.backward()
+    d = dict(x=xs, adj0=a0, adj1=a1, adj2=a2, gt=gt, y=yt.detach().numpy(), loss=np.float32(loss.item()),
+             nparams=np.int32(len(holder)))
+    for i, t in enumerate(holder):
+        d["p%02d" % i] = t.detach().numpy()
+        d["g%02d" % i] = t.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "net_train_small.npz"), **d)
+    print("wrote net_train_small loss", loss.item())
+
+    # ---- multi-scale pipeline on icosphere-2 (320 faces) via addMeshWithVertices
+    V, F = mesh.icosphere(2)
+    Vn = mesh.add_vertex_noise(V, F, 0.3, 1)
+    im = preprocess(ref, Vn, F, K, multi=True, seed=1)
+    x = im.in_list[0].astype(np.float32)
+    adjs = [a.astype(np.int32) for a in im.adj_list[0]]
+    faces_p = np.asarray(im.faces_list[0]).astype(np.int32)
+    v_faces = np.asarray(im.v_faces_list[0]).astype(np.int32)
+    vpos = np.asarray(im.v_list[0]).astype(np.float32)
+    ys, vs = rr.run(ref.model.get_model_reg_multi_scale, T(x), [T(a) for a in adjs], 1.0, multiScale=True,
+                    provider=rr.rng_provider(4321))
+    n0, n1, n2 = (ref.utils.normalizeTensor(t) for t in ys)
+    xo, dxl = ref.train.update_position_MS(T(vpos), [n0, n1, n2], T(faces_p), T(v_faces), 2,
+                                           iter_num_list=[8, 4, 4])
+    d = dict(V=Vn, F=F, x=x, adj0=adjs[0], adj1=adjs[1], adj2=adjs[2], faces=faces_p, v_faces=v_faces,
+             verts_in=vpos, y0=rr.to_np(ys[0]), y1=rr.to_np(ys[1]), y2=rr.to_np(ys[2]),
+             n0=rr.to_np(n0), n1=rr.to_np(n1), n2=rr.to_np(n2), verts_out=rr.to_np(xo),
+             iters=np.array([8, 4, 4], np.int32), nparams=np.int32(len(vs)))
+    fc = ref.train.updateFacesCenter(T(vpos), T(faces_p), 2)
+    d["fc0"], d["fc1"], d["fc2"] = (rr.to_np(t) for t in fc)
+    for i, v in enumerate(vs):
+        d["p%02d" % i] = v
+    np.savez_compressed(os.path.join(OUT, "net_ms_icosphere2.npz"), **d)
+    print("wrote net_ms_icosphere2", x.shape, faces_p.shape, v_faces.shape, vpos.shape)
+
+
+def index_cases(ref):
+    """Index layouts of the reference's host builders on small meshes (bit-exact targets)."""
+    d = {}
+    for tag, (V, F) in (("ico2", mesh.icosphere(2)), ("torus", mesh.grid_mesh(12, 10, True)),
+                        ("open", mesh.grid_mesh(7, 5, False))):
+        with contextlib.redirect_stdout(io.StringIO()):
+            d[tag + "_F"] = F
+            d[tag + "_adj16"] = ref.utils.getFacesLargeAdj(F, 16)
+            d[tag + "_adj10"] = ref.utils.getFacesLargeAdj(F, 10)
+            e, v = ref.utils.getEdgeMap(F, maxEdges=20)
+            d[tag + "_emap"], d[tag + "_vemap"] = e, v
+            d[tag + "_vf"] = ref.utils.getVerticesFaces(F, 25)
+    # the reference's only known-answer test (Code/lib/coarsening.py:243-244)
+    d["compute_perm_out"] = np.array(
+        [np.asarray(p) for p in ref.coarsening.compute_perm([np.array([4, 1, 1, 2, 2, 3, 0, 0, 3]),
+                                                            np.array([2, 1, 0, 1, 0])])], dtype=object)[0]
+    np.savez_compressed(os.path.join(OUT, "index_layouts.npz"), **d)
+    print("wrote index_layouts")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = rr.load()
+    torch.manual_seed(0)
+    conv_case(ref, "conv_6_32_M9_K23_B2", 2, 300, 6, 32, 9, 23, seed=1)
+    conv_case(ref, "conv_64_32_M9_K23", 1, 200, 64, 32, 9, 23, seed=2)
+    conv_case(ref, "conv_64_64_M8_K16_B2", 2, 256, 64, 64, 8, 16, seed=3)
+    conv_case(ref, "conv_128_128_M9_K23", 1, 96, 128, 128, 9, 23, seed=4)
+    conv_case(ref, "conv_32_64_M9_K16_nomask", 1, 130, 32, 64, 9, 16, seed=5, bias_mask=False)
+    conv_case(ref, "conv_12_20_M5_K7_trans", 2, 90, 12, 20, 5, 7, seed=6, translation=True)
+    variant_cases(ref)
+    small_ops(ref)
+    net_and_vertex_cases(ref)
+    index_cases(ref)
+
+
+if __name__ == "__main__":
+    main()
