@@ -1,0 +1,134 @@
+"""torch.autograd glue: each Function's forward/backward is one or two C-ABI calls.
+
+The reverse adjacency needed by the convolution backward is cached per adjacency tensor
+(keyed by storage pointer + shape + version) so it is built once per patch, not per layer.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+_REV_CACHE = {}
+_REV_CACHE_MAX = 64
+
+
+def reverse_adjacency(adj: torch.Tensor) -> ops.ReverseAdjacency:
+    key = (adj.data_ptr(), tuple(adj.shape), adj._version, str(adj.device), adj.dtype)
+    hit = _REV_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    rev = ops.ReverseAdjacency(adj)
+    if len(_REV_CACHE) >= _REV_CACHE_MAX:
+        _REV_CACHE.pop(next(iter(_REV_CACHE)))
+    _REV_CACHE[key] = (rev, adj)  # keep adj alive so the pointer cannot be recycled
+    return rev
+
+
+def clear_reverse_cache():
+    _REV_CACHE.clear()
+
+
+class FacetConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, adj, W0, b, u, v, c, bias_mask, cw, ca0, ca, rev):
+        y = ops.conv_fwd(x, adj, W0, b, u, v, c, bias_mask, ops.ACT_NONE, 0.0, cw, ca0, ca)
+        ctx.save_for_backward(x, adj, W0, u, v, c)
+        ctx.cfg = (bias_mask, cw, ca0, ca, rev)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, adj, W0, u, v, c = ctx.saved_tensors
+        bias_mask, cw, ca0, ca, rev = ctx.cfg
+        if rev is None:
+            rev = reverse_adjacency(adj)
+        gx, gW0, gb, gu, gv, gc = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, bias_mask, cw, ca0, ca)
+        return gx, None, gW0, gb, gu, gv, gc, None, None, None, None, None
+
+
+class PoolMaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        y = ops.pool_max(x, group)
+        ctx.save_for_backward(x, y)
+        ctx.group = group
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y = ctx.saved_tensors
+        return ops.pool_max_bwd(gy, x, y, ctx.group), None
+
+
+class UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return ops.upsample(x, group)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return ops.upsample_bwd(gy, ctx.group), None
+
+
+class LReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, alpha):
+        ctx.save_for_backward(x)
+        ctx.alpha = alpha
+        return ops.lrelu(x, alpha)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return ops.lrelu_bwd(gy, x, ctx.alpha), None
+
+
+class Concat2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.ca = a.shape[-1]
+        return ops.concat2(a, b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return ops.split2(gy, ctx.ca)
+
+
+class LinFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b):
+        ctx.save_for_backward(x, W)
+        return ops.lin_fwd(x, W, b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        gx, gW, gb = ops.lin_bwd(gy, x, W, need_gx=ctx.needs_input_grad[0])
+        return gx, gW, gb
+
+
+class NormalizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.normalize_rows(x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return ops.normalize_rows_bwd(gy, x)
+
+
+class FaceNormalsLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fn, gt):
+        loss, gfn = ops.face_normals_loss(fn, gt, need_grad=True, gscale=1.0)
+        ctx.save_for_backward(gfn)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (gfn,) = ctx.saved_tensors
+        return gfn * g, None

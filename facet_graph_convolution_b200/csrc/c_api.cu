@@ -1,0 +1,364 @@
+// extern "C" boundary of libfacetconv_b200.so (declared in include/facetconv_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "conv_launch.cuh"
+
+namespace fgc {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------ opt-in kernel profiler
+bool g_prof_on = false;
+namespace {
+struct ProfMark {
+  const char* name;
+  cudaEvent_t ev;
+};
+std::vector<ProfMark> g_marks;
+std::vector<cudaEvent_t> g_pool;
+size_t g_pool_next = 0;
+cudaStream_t g_prof_stream = nullptr;
+cudaEvent_t prof_event() {
+  if (g_pool_next == g_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    g_pool.push_back(e);
+  }
+  return g_pool[g_pool_next++];
+}
+}  // namespace
+void prof_set_stream(cudaStream_t st) { g_prof_stream = st; }
+void prof_mark(const char* name) {
+  cudaEvent_t e = prof_event();
+  if (!e) return;
+  cudaEventRecord(e, g_prof_stream);
+  g_marks.push_back({name, e});
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static int check_shape(const fgc_conv_shape* s, const char* who) {
+  FGC_REQUIRE(s != nullptr, "%s: shape is NULL", who);
+  FGC_REQUIRE(s->B > 0 && s->N > 0, "%s: B and N must be positive (B=%d N=%d)", who, s->B, s->N);
+  FGC_REQUIRE(s->K > 0 && s->K <= FGC_MAX_K, "%s: K=%d outside 1..%d", who, s->K, FGC_MAX_K);
+  FGC_REQUIRE(s->M > 0 && s->M <= FGC_MAX_M, "%s: M=%d outside 1..%d", who, s->M, FGC_MAX_M);
+  FGC_REQUIRE(s->Cin > 0 && s->Cin <= FGC_MAX_C, "%s: Cin=%d outside 1..%d", who, s->Cin, FGC_MAX_C);
+  FGC_REQUIRE(s->Cout > 0 && s->Cout <= FGC_MAX_C, "%s: Cout=%d outside 1..%d", who, s->Cout, FGC_MAX_C);
+  FGC_REQUIRE(s->Cw > 0 && s->Cw <= s->Cin, "%s: Cw=%d outside 1..Cin", who, s->Cw);
+  FGC_REQUIRE(s->Ca > 0 && s->Ca0 >= 0 && s->Ca0 + s->Ca <= s->Cin,
+              "%s: logit window [%d,%d) outside the row", who, s->Ca0, s->Ca0 + s->Ca);
+  FGC_REQUIRE(static_cast<int64_t>(s->B) * s->N * s->K < (1ll << 31), "%s: B*N*K must be < 2^31", who);
+  return FGC_OK;
+}
+
+static size_t conv_fwd_workspace(const fgc_conv_shape* s) {
+  const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  return ws_bytes(rows * 2 * s->M, 4) + ws_bytes(static_cast<size_t>(s->M) * s->Cout * s->Cw, 4) + 512;
+}
+
+static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0,
+                    const float* b, const float* u, const float* v, const float* c, float* y,
+                    int bias_mask, int act, float alpha, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st) {
+  const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  Workspace ws(workspace, workspace_bytes);
+  float* uvx = ws.take<float>(rows * 2 * s->M);
+  float* Wt = ws.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);
+  FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              conv_fwd_workspace(s));
+  int rc = launch_assign_logits(s, x, u, v, c, uvx, st);
+  if (rc) return rc;
+  rc = launch_transpose_w(W0, Wt, s->M, s->Cout, s->Cw, st);
+  if (rc) return rc;
+  ConvFwdParams p{x, adj, uvx, Wt, b, y, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M,
+                  bias_mask, act, alpha};
+  return launch_conv_fwd(p, st);
+}
+
+// ------------------------------------------------------------------ host-buffer path
+struct HostCache {
+  int device = -1;
+  char* dev = nullptr;
+  size_t cap = 0;
+  cudaStream_t stream = nullptr;
+};
+static thread_local HostCache g_hc;
+
+static int host_reserve(int device, size_t bytes) {
+  if (g_hc.device != device) {
+    if (g_hc.dev) {
+      cudaSetDevice(g_hc.device);
+      cudaFree(g_hc.dev);
+      if (g_hc.stream) cudaStreamDestroy(g_hc.stream);
+    }
+    g_hc = HostCache();
+  }
+  FGC_CUDA(cudaSetDevice(device));
+  g_hc.device = device;
+  if (!g_hc.stream) FGC_CUDA(cudaStreamCreateWithFlags(&g_hc.stream, cudaStreamNonBlocking));
+  if (bytes > g_hc.cap) {
+    if (g_hc.dev) FGC_CUDA(cudaFree(g_hc.dev));
+    g_hc.dev = nullptr;
+    g_hc.cap = 0;
+    FGC_CUDA(cudaMalloc(&g_hc.dev, bytes));
+    g_hc.cap = bytes;
+  }
+  return FGC_OK;
+}
+
+}  // namespace fgc
+
+using namespace fgc;
+
+extern "C" {
+
+int fgc_version(void) { return 100; }
+const char* fgc_last_error(void) { return g_err; }
+uint64_t fgc_launch_count(void) { return g_launches.load(); }
+
+int fgc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int fgc_profile_begin(void* stream) {
+  g_marks.clear();
+  g_pool_next = 0;
+  g_prof_on = true;
+  prof_set_stream(reinterpret_cast<cudaStream_t>(stream));
+  prof_mark("<begin>");
+  return FGC_OK;
+}
+
+int fgc_profile_end(char* buf, size_t buf_bytes) {
+  g_prof_on = false;
+  if (g_marks.empty()) return FGC_OK;
+  FGC_CUDA(cudaEventSynchronize(g_marks.back().ev));
+  std::map<std::string, std::pair<double, int>> acc;
+  std::vector<std::string> order;
+  for (size_t i = 1; i < g_marks.size(); ++i) {
+    float ms = 0.f;
+    if (g_marks[i].name[0] == '<') continue;  // a re-begin marker
+    FGC_CUDA(cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev));
+    auto it = acc.find(g_marks[i].name);
+    if (it == acc.end()) {
+      order.push_back(g_marks[i].name);
+      acc[g_marks[i].name] = {ms, 1};
+    } else {
+      it->second.first += ms;
+      it->second.second += 1;
+    }
+  }
+  size_t off = 0;
+  if (buf && buf_bytes) buf[0] = 0;
+  for (const auto& nm : order) {
+    char line[256];
+    const int n = snprintf(line, sizeof(line), "%s %.6f %d\n", nm.c_str(), acc[nm].first, acc[nm].second);
+    if (buf && off + n + 1 < buf_bytes) {
+      memcpy(buf + off, line, n + 1);
+      off += n;
+    }
+  }
+  g_marks.clear();
+  g_pool_next = 0;
+  return FGC_OK;
+}
+
+size_t fgc_conv_fwd_workspace(const fgc_conv_shape* s) {
+  if (check_shape(s, "conv_fwd_workspace")) return 0;
+  return conv_fwd_workspace(s);
+}
+
+size_t fgc_conv_bwd_workspace(const fgc_conv_shape* s) {
+  if (check_shape(s, "conv_bwd_workspace")) return 0;
+  return conv_bwd_workspace(s);
+}
+
+int fgc_conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0,
+                 const float* b, const float* u, const float* v, const float* c, float* y,
+                 int bias_mask, int act, float alpha, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  int rc = check_shape(s, "conv_fwd");
+  if (rc) return rc;
+  FGC_REQUIRE(x && adj && W0 && b && u && v && c && y, "conv_fwd: NULL tensor pointer");
+  FGC_REQUIRE(act == FGC_ACT_NONE || act == FGC_ACT_LRELU, "conv_fwd: unknown activation %d", act);
+  return conv_fwd(s, x, adj, W0, b, u, v, c, y, bias_mask, act, alpha, workspace, workspace_bytes,
+                  as_stream(stream));
+}
+
+size_t fgc_reverse_adj_workspace(int B, int N, int K) {
+  return reverse_adj_workspace(static_cast<int64_t>(B) * N);
+}
+
+int fgc_build_reverse_adj(const int32_t* adj, int B, int N, int K, int32_t* rev_ptr, int32_t* rev_edge,
+                          int64_t* nnz_out, void* workspace, size_t workspace_bytes, void* stream) {
+  FGC_REQUIRE(adj && rev_ptr && rev_edge && B > 0 && N > 0 && K > 0, "build_reverse_adj: bad arguments");
+  return build_reverse_adj(adj, B, N, K, rev_ptr, rev_edge, nnz_out, workspace, workspace_bytes,
+                           as_stream(stream));
+}
+
+int fgc_conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
+                 const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
+                 const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu, float* gv,
+                 float* gc, int bias_mask, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_shape(s, "conv_bwd");
+  if (rc) return rc;
+  FGC_REQUIRE(gy && x && adj && rev_ptr && rev_edge && W0 && u && v && c && gx && gW0 && gb && gu &&
+                  gv && gc,
+              "conv_bwd: NULL tensor pointer");
+  return conv_bwd(s, gy, x, adj, rev_ptr, rev_edge, W0, u, v, c, gx, gW0, gb, gu, gv, gc, bias_mask,
+                  workspace, workspace_bytes, as_stream(stream));
+}
+
+int fgc_gather_rows(const float* x, const int32_t* adj, float* out, int B, int N, int K, int C,
+                    void* stream) {
+  FGC_REQUIRE(x && adj && out && B > 0 && N > 0 && K > 0 && C > 0, "gather_rows: bad arguments");
+  return launch_gather_rows(x, adj, out, static_cast<int64_t>(B) * N, N, K, C, as_stream(stream));
+}
+
+int fgc_assignments(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* u,
+                    const float* v, const float* c, float* q, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  int rc = check_shape(s, "assignments");
+  if (rc) return rc;
+  FGC_REQUIRE(x && adj && u && v && c && q, "assignments: NULL tensor pointer");
+  const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  Workspace ws(workspace, workspace_bytes);
+  float* uvx = ws.take<float>(rows * 2 * s->M);
+  FGC_REQUIRE(ws.ok(), "assignments: workspace too small");
+  rc = launch_assign_logits(s, x, u, v, c, uvx, as_stream(stream));
+  if (rc) return rc;
+  return launch_assignments(adj, uvx, q, rows, s->N, s->K, s->M, as_stream(stream));
+}
+
+// ------------------------------------------------------------------ host-buffer entry points
+int fgc_conv_fwd_host(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0,
+                      const float* b, const float* u, const float* v, const float* c, float* y,
+                      int bias_mask, int act, float alpha, int device) {
+  int rc = check_shape(s, "conv_fwd_host");
+  if (rc) return rc;
+  FGC_REQUIRE(x && adj && W0 && b && u && v && c && y, "conv_fwd_host: NULL pointer");
+  const size_t rows = static_cast<size_t>(s->B) * s->N;
+  const size_t nx = rows * s->Cin, nadj = rows * s->K, ny = rows * s->Cout;
+  const size_t nW = static_cast<size_t>(s->M) * s->Cout * s->Cw, nu = static_cast<size_t>(s->M) * s->Ca;
+  const size_t wsb = conv_fwd_workspace(s);
+  size_t total = 0;
+  auto place = [&](size_t bytes) { size_t o = total; total = align_up(total + bytes, 256); return o; };
+  const size_t ox = place(nx * 4), oadj = place(nadj * 4), oy = place(ny * 4), oW = place(nW * 4),
+               ob = place(s->Cout * 4), ou = place(nu * 4), ov = place(nu * 4), oc = place(s->M * 4),
+               ows = place(wsb);
+  rc = host_reserve(device, total);
+  if (rc) return rc;
+  char* d = g_hc.dev;
+  cudaStream_t st = g_hc.stream;
+  FGC_CUDA(cudaMemcpyAsync(d + ox, x, nx * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + oadj, adj, nadj * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + oW, W0, nW * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + ob, b, s->Cout * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + ou, u, nu * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + ov, v, nu * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + oc, c, s->M * 4, cudaMemcpyHostToDevice, st));
+  rc = conv_fwd(s, (float*)(d + ox), (int32_t*)(d + oadj), (float*)(d + oW), (float*)(d + ob),
+                (float*)(d + ou), (float*)(d + ov), (float*)(d + oc), (float*)(d + oy), bias_mask, act,
+                alpha, d + ows, wsb, st);
+  if (rc) return rc;
+  FGC_CUDA(cudaMemcpyAsync(y, d + oy, ny * 4, cudaMemcpyDeviceToHost, st));
+  FGC_CUDA(cudaStreamSynchronize(st));
+  return FGC_OK;
+}
+
+int fgc_conv_fwd_bwd_host(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* gy,
+                          const float* W0, const float* b, const float* u, const float* v,
+                          const float* c, float* y, float* gx, float* gW0, float* gb, float* gu,
+                          float* gv, float* gc, int bias_mask, int device) {
+  int rc = check_shape(s, "conv_fwd_bwd_host");
+  if (rc) return rc;
+  FGC_REQUIRE(x && adj && gy && W0 && b && u && v && c && y && gx && gW0 && gb && gu && gv && gc,
+              "conv_fwd_bwd_host: NULL pointer");
+  const size_t rows = static_cast<size_t>(s->B) * s->N;
+  const size_t nx = rows * s->Cin, nadj = rows * s->K, ny = rows * s->Cout;
+  const size_t nW = static_cast<size_t>(s->M) * s->Cout * s->Cw, nu = static_cast<size_t>(s->M) * s->Ca;
+  const size_t wsf = conv_fwd_workspace(s), wsb = conv_bwd_workspace(s);
+  const size_t wsr = reverse_adj_workspace(rows);
+  size_t wsmax = wsf > wsb ? wsf : wsb;
+  if (wsr > wsmax) wsmax = wsr;
+  size_t total = 0;
+  auto place = [&](size_t bytes) { size_t o = total; total = align_up(total + bytes, 256); return o; };
+  const size_t ox = place(nx * 4), oadj = place(nadj * 4), ogy = place(ny * 4), oy = place(ny * 4),
+               ogx = place(nx * 4), oW = place(nW * 4), ob = place(s->Cout * 4), ou = place(nu * 4),
+               ov = place(nu * 4), oc = place(s->M * 4), ogW = place(nW * 4), ogb = place(s->Cout * 4),
+               ogu = place(nu * 4), ogv = place(nu * 4), ogc = place(s->M * 4),
+               orp = place((rows + 1) * 4), ore = place(nadj * 4), ows = place(wsmax);
+  rc = host_reserve(device, total);
+  if (rc) return rc;
+  char* d = g_hc.dev;
+  cudaStream_t st = g_hc.stream;
+  FGC_CUDA(cudaMemcpyAsync(d + ox, x, nx * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + oadj, adj, nadj * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + oW, W0, nW * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + ob, b, s->Cout * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + ou, u, nu * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + ov, v, nu * 4, cudaMemcpyHostToDevice, st));
+  FGC_CUDA(cudaMemcpyAsync(d + oc, c, s->M * 4, cudaMemcpyHostToDevice, st));
+  rc = conv_fwd(s, (float*)(d + ox), (int32_t*)(d + oadj), (float*)(d + oW), (float*)(d + ob),
+                (float*)(d + ou), (float*)(d + ov), (float*)(d + oc), (float*)(d + oy), bias_mask,
+                FGC_ACT_NONE, 0.f, d + ows, wsmax, st);
+  if (rc) return rc;
+  FGC_CUDA(cudaMemcpyAsync(y, d + oy, ny * 4, cudaMemcpyDeviceToHost, st));
+  FGC_CUDA(cudaMemcpyAsync(d + ogy, gy, ny * 4, cudaMemcpyHostToDevice, st));
+  rc = build_reverse_adj((int32_t*)(d + oadj), s->B, s->N, s->K, (int32_t*)(d + orp),
+                         (int32_t*)(d + ore), nullptr, d + ows, wsmax, st);
+  if (rc) return rc;
+  rc = conv_bwd(s, (float*)(d + ogy), (float*)(d + ox), (int32_t*)(d + oadj), (int32_t*)(d + orp),
+                (int32_t*)(d + ore), (float*)(d + oW), (float*)(d + ou), (float*)(d + ov),
+                (float*)(d + oc), (float*)(d + ogx), (float*)(d + ogW), (float*)(d + ogb),
+                (float*)(d + ogu), (float*)(d + ogv), (float*)(d + ogc), bias_mask, d + ows, wsmax, st);
+  if (rc) return rc;
+  FGC_CUDA(cudaMemcpyAsync(gx, d + ogx, nx * 4, cudaMemcpyDeviceToHost, st));
+  FGC_CUDA(cudaMemcpyAsync(gW0, d + ogW, nW * 4, cudaMemcpyDeviceToHost, st));
+  FGC_CUDA(cudaMemcpyAsync(gb, d + ogb, s->Cout * 4, cudaMemcpyDeviceToHost, st));
+  FGC_CUDA(cudaMemcpyAsync(gu, d + ogu, nu * 4, cudaMemcpyDeviceToHost, st));
+  FGC_CUDA(cudaMemcpyAsync(gv, d + ogv, nu * 4, cudaMemcpyDeviceToHost, st));
+  FGC_CUDA(cudaMemcpyAsync(gc, d + ogc, s->M * 4, cudaMemcpyDeviceToHost, st));
+  FGC_CUDA(cudaStreamSynchronize(st));
+  return FGC_OK;
+}
+
+void fgc_host_release(void) {
+  if (g_hc.dev) {
+    cudaSetDevice(g_hc.device);
+    cudaFree(g_hc.dev);
+  }
+  if (g_hc.stream) cudaStreamDestroy(g_hc.stream);
+  g_hc = HostCache();
+}
+
+}  // extern "C"

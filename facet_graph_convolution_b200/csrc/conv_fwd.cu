@@ -1,0 +1,276 @@
+// Forward facet-graph convolution (replaces reference Code/model.py:427-504, :74-95, :380-405).
+//
+// Pipeline per call (all on the caller's stream):
+//   1. assign_logits_kernel : uvx[r, 0:M] = u.x_r + c,  uvx[r, M:2M] = v.x_r          (one pass over x)
+//   2. transpose_w_kernel   : Wt[(m,c)][o] = W0[m][o][c]                              (tiny)
+//   3. conv_fwd_kernel      : per tile of 32 facets
+//        phase 1  warp-per-facet: soft assignments (lane per neighbour slot), then the
+//                 q-weighted aggregation s[m][c] = sum_k q[k][m] x_{j_k}[c] with coalesced
+//                 row loads (lanes over channels); s goes to shared memory
+//        phase 2  tile GEMM y = s . Wt streamed through shared memory in 32-row chunks,
+//                 fused epilogue (1/cnt, masked bias, leaky ReLU)
+// The [B,N,K,M*Cout] tensor the reference materialises never exists.
+#include "conv_common.cuh"
+#include "conv_launch.cuh"
+
+namespace fgc {
+
+// ------------------------------------------------------------------ assignment logits pre-pass
+__global__ void __launch_bounds__(kThreads)
+assign_logits_kernel(const float* __restrict__ x, const float* __restrict__ u,
+                     const float* __restrict__ v, const float* __restrict__ c,
+                     float* __restrict__ uvx, int64_t rows, int Cin, int Ca0, int Ca, int M) {
+  extern __shared__ float sm[];
+  const int O = 2 * M;
+  const int RB = kThreads / O;       // rows per block iteration
+  float* uv = sm;                    // [O][Ca+1]
+  float* xs = uv + O * (Ca + 1);     // [RB][Ca]
+  for (int e = threadIdx.x; e < O * Ca; e += kThreads) {
+    const int o = e / Ca, cc = e % Ca;
+    uv[o * (Ca + 1) + cc] = (o < M) ? u[o * Ca + cc] : v[(o - M) * Ca + cc];
+  }
+  const int rl = threadIdx.x / O, o = threadIdx.x % O;
+  const float cadd = (o < M) ? c[o] : 0.f;
+  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * RB; r0 < rows;
+       r0 += static_cast<int64_t>(gridDim.x) * RB) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < RB * Ca; e += kThreads) {
+      const int rr = e / Ca, cc = e % Ca;
+      xs[e] = (r0 + rr < rows) ? __ldg(x + (r0 + rr) * Cin + Ca0 + cc) : 0.f;
+    }
+    __syncthreads();
+    if (rl < RB && r0 + rl < rows) {
+      float acc = 0.f;
+      const float* xr = xs + rl * Ca;
+      const float* w = uv + o * (Ca + 1);
+      for (int cc = 0; cc < Ca; ++cc) acc = fmaf(xr[cc], w[cc], acc);
+      uvx[(r0 + rl) * O + o] = acc + cadd;
+    }
+  }
+}
+
+int launch_assign_logits(const fgc_conv_shape* s, const float* x, const float* u, const float* v,
+                         const float* c, float* uvx, cudaStream_t st) {
+  const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  const int O = 2 * s->M;
+  const int RB = kThreads / O;
+  const size_t smem = (static_cast<size_t>(O) * (s->Ca + 1) + static_cast<size_t>(RB) * s->Ca) * 4;
+  int64_t blocks = (rows + RB - 1) / RB;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  assign_logits_kernel<<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(
+      x, u, v, c, uvx, rows, s->Cin, s->Ca0, s->Ca, s->M);
+  FGC_LAUNCHED("assign_logits_kernel");
+  return FGC_OK;
+}
+
+// ------------------------------------------------------------------ weight transpose
+__global__ void transpose_w_kernel(const float* __restrict__ W0, float* __restrict__ Wt, int M,
+                                   int Cout, int Cw) {
+  const int total = M * Cout * Cw;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int o = e % Cout;
+    const int mc = e / Cout;
+    const int m = mc / Cw, cc = mc % Cw;
+    Wt[e] = W0[(static_cast<int64_t>(m) * Cout + o) * Cw + cc];
+  }
+}
+
+int launch_transpose_w(const float* W0, float* Wt, int M, int Cout, int Cw, cudaStream_t st) {
+  const int total = M * Cout * Cw;
+  transpose_w_kernel<<<(total + 255) / 256, 256, 0, st>>>(W0, Wt, M, Cout, Cw);
+  FGC_LAUNCHED("transpose_w_kernel");
+  return FGC_OK;
+}
+
+// ------------------------------------------------------------------ forward kernel
+template <int MP>
+__host__ __device__ constexpr int q_stride() { return QStride<MP>::value; }
+
+// dynamic shared memory carve-up (floats): S | Bs | qs | nbr | inv | flag
+__host__ __device__ inline int fwd_lda(int M, int Cw) { return ((M * Cw + 3) & ~3); }
+
+template <int MP, int NC>
+__global__ void __launch_bounds__(kThreads)
+conv_fwd_kernel(const ConvFwdParams p) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int QS = QStride<MP>::value;
+  const int KK = p.M * p.Cw;
+  const int lda = fwd_lda(p.M, p.Cw);
+  float* S = sm;                                   // [32][lda]
+  float* Bs = S + kTileFacets * lda;               // [32][128]
+  float* qs_all = Bs + kChunkK * 128;              // [8][32][QS]
+  int* nbr_all = reinterpret_cast<int*>(qs_all + kWarps * 32 * QS);  // [8][32]
+  float* inv = reinterpret_cast<float*>(nbr_all + kWarps * 32);      // [32]
+  float* flag = inv + kTileFacets;                                   // [32]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qs = qs_all + warp * 32 * QS;
+  int* nbr = nbr_all + warp * 32;
+  const int64_t ntiles = (p.rows + kTileFacets - 1) / kTileFacets;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kTileFacets;
+    // ---------------- phase 1: assignments + aggregation, warp per facet
+    for (int f = warp; f < kTileFacets; f += kWarps) {
+      const int64_t r = r0 + f;
+      float acc[MP][NC];
+#pragma unroll
+      for (int m = 0; m < MP; ++m)
+#pragma unroll
+        for (int i = 0; i < NC; ++i) acc[m][i] = 0.f;
+      int cnt = 0;
+      if (r < p.rows) {
+        const int64_t base = (r / p.N) * p.N;
+        cnt = facet_assign<MP>(p.adj, p.uvx, r, base, p.N, p.K, p.M, qs, nbr, lane);
+        aggregate_rows<MP, NC>(p.x, p.Cin, p.Cw, p.K, qs, nbr, lane, acc);
+      }
+      float* Sr = S + f * lda;
+#pragma unroll
+      for (int m = 0; m < MP; ++m) {
+        if (m < p.M) {
+#pragma unroll
+          for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < p.Cw) Sr[m * p.Cw + c] = acc[m][i];
+          }
+        }
+      }
+      if (lane < lda - KK) Sr[KK + lane] = 0.f;
+      if (lane == 0) {
+        inv[f] = cnt ? 1.f / static_cast<float>(cnt) : 0.f;
+        flag[f] = (cnt > 0 || !p.bias_mask) ? 1.f : 0.f;
+      }
+      __syncwarp();
+    }
+    // ---------------- phase 2: contraction y = S . Wt, 128 output columns at a time
+    for (int o0 = 0; o0 < p.Cout; o0 += 128) {
+      const int ncols = min(128, p.Cout - o0);
+      const TileGemmMap mp(ncols);
+      float acc[4][4];
+      tile_gemm(S, lda, KK, p.Wt, p.Cout, o0, ncols, Bs, mp, acc);  // syncs inside
+      if (mp.ty < mp.TY) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int f = mp.ty + mp.TY * i;
+          const int64_t r = r0 + f;
+          if (i < mp.RF && f < kTileFacets && r < p.rows) {
+            const float sc = inv[f], fl = flag[f];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int o = o0 + 4 * mp.tx + j;
+              if (o < p.Cout) {
+                float yv = fmaf(sc, acc[i][j], fl * __ldg(p.b + o));
+                if (p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
+                p.y[r * p.Cout + o] = yv;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // S / inv reused by the next tile
+  }
+}
+
+template <int MP>
+static size_t fwd_smem_bytes(int M, int Cw) {
+  constexpr int QS = QStride<MP>::value;
+  return (static_cast<size_t>(kTileFacets) * fwd_lda(M, Cw) + kChunkK * 128 + kWarps * 32 * QS +
+          kWarps * 32 + 2 * kTileFacets) * 4;
+}
+
+template <int MP, int NC>
+static int launch_conv_fwd_t(const ConvFwdParams& p, cudaStream_t st) {
+  const size_t smem = fwd_smem_bytes<MP>(p.M, p.Cw);
+  if (smem > 227 * 1024) {
+    set_error("conv_fwd: M*Cw = %d needs %zu bytes of shared memory (> 227 KB)", p.M * p.Cw, smem);
+    return FGC_ERR_UNSUPPORTED;
+  }
+  FGC_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<MP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  int occ = 1;
+  FGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_fwd_kernel<MP, NC>, kThreads, smem));
+  if (occ < 1) occ = 1;
+  const int64_t ntiles = (p.rows + kTileFacets - 1) / kTileFacets;
+  int64_t grid = static_cast<int64_t>(num_sms()) * occ;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  conv_fwd_kernel<MP, NC><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(p);
+  FGC_LAUNCHED("conv_fwd_kernel");
+  return FGC_OK;
+}
+
+int launch_conv_fwd(const ConvFwdParams& p, cudaStream_t st) {
+#define FGC_CALL(MPV, NCV) return launch_conv_fwd_t<MPV, NCV>(p, st)
+  FGC_DISPATCH_MP_NC(pick_mp(p.M), pick_nc(p.Cw), FGC_CALL);
+#undef FGC_CALL
+  return FGC_OK;
+}
+
+// ------------------------------------------------------------------ debug / parity helpers
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ adj,
+                                   float* __restrict__ out, int64_t rows, int N, int K, int C) {
+  // one warp per (row, slot); pure copy => bit-exact
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = rows * K;
+  for (int64_t e = w; e < total; e += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) {
+    const int64_t r = e / K;
+    const int id = adj[e];
+    const int64_t base = (r / N) * N;
+    const bool valid = id > 0 && id <= N;
+    for (int c = lane; c < C; c += 32)
+      out[e * C + c] = valid ? x[(base + id - 1) * C + c] : 0.f;
+  }
+}
+
+template <int MP>
+__global__ void __launch_bounds__(kThreads)
+assignments_kernel(const int32_t* __restrict__ adj, const float* __restrict__ uvx,
+                   float* __restrict__ q, int64_t rows, int N, int K, int M) {
+  constexpr int QS = QStride<MP>::value;
+  __shared__ __align__(16) float qs_all[kWarps * 32 * QS];
+  __shared__ int nbr_all[kWarps * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qs = qs_all + warp * 32 * QS;
+  int* nbr = nbr_all + warp * 32;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kWarps + warp; r < rows;
+       r += static_cast<int64_t>(gridDim.x) * kWarps) {
+    const int64_t base = (r / N) * N;
+    facet_assign<MP>(adj, uvx, r, base, N, K, M, qs, nbr, lane);
+    for (int e = lane; e < K * M; e += 32) q[r * K * M + e] = qs[(e / M) * QS + e % M];
+    __syncwarp();
+  }
+}
+
+int launch_assignments(const int32_t* adj, const float* uvx, float* q, int64_t rows, int N, int K,
+                       int M, cudaStream_t st) {
+  int64_t blocks = (rows + kWarps - 1) / kWarps;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  switch (pick_mp(M)) {
+    case 4: assignments_kernel<4><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(adj, uvx, q, rows, N, K, M); break;
+    case 8: assignments_kernel<8><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(adj, uvx, q, rows, N, K, M); break;
+    case 9: assignments_kernel<9><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(adj, uvx, q, rows, N, K, M); break;
+    default: assignments_kernel<16><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(adj, uvx, q, rows, N, K, M); break;
+  }
+  FGC_LAUNCHED("assignments_kernel");
+  return FGC_OK;
+}
+
+int launch_gather_rows(const float* x, const int32_t* adj, float* out, int64_t rows, int N, int K,
+                       int C, cudaStream_t st) {
+  int64_t warps = rows * K;
+  int64_t blocks = (warps + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  gather_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, adj, out, rows, N, K, C);
+  FGC_LAUNCHED("gather_rows_kernel");
+  return FGC_OK;
+}
+
+}  // namespace fgc

@@ -1,0 +1,40 @@
+// Host-side launch interfaces shared between the convolution translation units and c_api.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace fgc {
+
+struct ConvFwdParams {
+  const float* x;
+  const int32_t* adj;
+  const float* uvx;
+  const float* Wt;  // [M*Cw][Cout]
+  const float* b;
+  float* y;
+  int64_t rows;
+  int N, K, Cin, Cw, Cout, M;
+  int bias_mask, act;
+  float alpha;
+};
+
+int launch_assign_logits(const fgc_conv_shape* s, const float* x, const float* u, const float* v,
+                         const float* c, float* uvx, cudaStream_t st);
+int launch_transpose_w(const float* W0, float* Wt, int M, int Cout, int Cw, cudaStream_t st);
+int launch_conv_fwd(const ConvFwdParams& p, cudaStream_t st);
+int launch_assignments(const int32_t* adj, const float* uvx, float* q, int64_t rows, int N, int K,
+                       int M, cudaStream_t st);
+int launch_gather_rows(const float* x, const int32_t* adj, float* out, int64_t rows, int N, int K,
+                       int C, cudaStream_t st);
+size_t conv_bwd_workspace(const fgc_conv_shape* s);
+int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
+             const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
+             const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu, float* gv,
+             float* gc, int bias_mask, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t reverse_adj_workspace(int64_t rows);
+int build_reverse_adj(const int32_t* adj, int B, int N, int K, int32_t* rev_ptr, int32_t* rev_edge,
+                      int64_t* nnz_out, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_reduce_partials(const float* part, float* out, int64_t n, int P, int64_t stride,
+                           cudaStream_t st);
+
+}  // namespace fgc

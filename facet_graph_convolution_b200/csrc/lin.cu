@@ -1,0 +1,355 @@
+// Per-facet linear layers (reference Code/model.py:763-769 custom_lin) and the fused regression
+// head lrelu(x@W1+b1)@W2+b2 (reference Code/model.py:936-941) that never materialises the
+// 1024-wide hidden activation.
+#include "conv_common.cuh"
+#include "conv_launch.cuh"
+
+namespace fgc {
+
+// ------------------------------------------------------------------ y = act(x @ W + b)
+__global__ void __launch_bounds__(kThreads)
+lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+               float* __restrict__ y, int64_t rows, int Cin, int Cout, int act, float alpha) {
+  extern __shared__ __align__(16) float sm[];
+  const int lda = (Cin + 3) & ~3;
+  float* A = sm;                       // [32][lda]
+  float* Bs = A + kTileFacets * lda;   // [32][128]
+  const int64_t ntiles = (rows + kTileFacets - 1) / kTileFacets;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kTileFacets;
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTileFacets * lda; e += kThreads) {
+      const int f = e / lda, c = e % lda;
+      A[e] = (r0 + f < rows && c < Cin) ? __ldg(x + (r0 + f) * Cin + c) : 0.f;
+    }
+    for (int o0 = 0; o0 < Cout; o0 += 128) {
+      const int ncols = min(128, Cout - o0);
+      const TileGemmMap mp(ncols);
+      float acc[4][4];
+      tile_gemm(A, lda, Cin, W, Cout, o0, ncols, Bs, mp, acc);
+      if (mp.ty < mp.TY) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int f = mp.ty + mp.TY * i;
+          const int64_t r = r0 + f;
+          if (i < mp.RF && f < kTileFacets && r < rows) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int o = o0 + 4 * mp.tx + j;
+              if (o < Cout) {
+                float v = acc[i][j] + __ldg(b + o);
+                if (act == FGC_ACT_LRELU) v = lrelu_f(v, alpha);
+                y[r * Cout + o] = v;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fused head
+constexpr int kHeadMaxOut = 4;
+__global__ void __launch_bounds__(kThreads)
+mlp_head_kernel(const float* __restrict__ x, const float* __restrict__ W1,
+                const float* __restrict__ b1, const float* __restrict__ W2,
+                const float* __restrict__ b2, float* __restrict__ y, int64_t rows, int Cin, int H,
+                int Cout, float alpha) {
+  extern __shared__ __align__(16) float sm[];
+  const int lda = (Cin + 3) & ~3;
+  float* A = sm;                                 // [32][lda]
+  float* Bs = A + kTileFacets * lda;             // [32][128]
+  float* part = Bs + kChunkK * 128;              // [32 facets][32 tx][4]
+  const int64_t ntiles = (rows + kTileFacets - 1) / kTileFacets;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kTileFacets;
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTileFacets * lda; e += kThreads) {
+      const int f = e / lda, c = e % lda;
+      A[e] = (r0 + f < rows && c < Cin) ? __ldg(x + (r0 + f) * Cin + c) : 0.f;
+    }
+    float yacc[4][kHeadMaxOut];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < kHeadMaxOut; ++j) yacc[i][j] = 0.f;
+    // hidden columns are always processed in full 128-wide blocks => fixed thread map (TX=32,TY=8,RF=4)
+    const TileGemmMap mp(128);
+    for (int h0 = 0; h0 < H; h0 += 128) {
+      const int ncols = min(128, H - h0);
+      float acc[4][4];
+      tile_gemm(A, lda, Cin, W1, H, h0, ncols, Bs, mp, acc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int h = h0 + 4 * mp.tx + j;
+        if (h < H) {
+          const float bb = __ldg(b1 + h);
+          float w2[kHeadMaxOut];
+#pragma unroll
+          for (int o = 0; o < kHeadMaxOut; ++o) w2[o] = (o < Cout) ? __ldg(W2 + h * Cout + o) : 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float hv = lrelu_f(acc[i][j] + bb, alpha);
+#pragma unroll
+            for (int o = 0; o < kHeadMaxOut; ++o) yacc[i][o] = fmaf(hv, w2[o], yacc[i][o]);
+          }
+        }
+      }
+    }
+    // fixed-order reduction over the 32 column groups of every facet
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = mp.ty + mp.TY * i;
+#pragma unroll
+      for (int o = 0; o < kHeadMaxOut; ++o) part[(f * 32 + mp.tx) * kHeadMaxOut + o] = yacc[i][o];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTileFacets * Cout; e += kThreads) {
+      const int f = e / Cout, o = e % Cout;
+      if (r0 + f < rows) {
+        float a = 0.f;
+        for (int t = 0; t < 32; ++t) a += part[(f * 32 + t) * kHeadMaxOut + o];
+        y[(r0 + f) * Cout + o] = a + __ldg(b2 + o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward
+__global__ void transpose2d_kernel(const float* __restrict__ W, float* __restrict__ Wt, int R, int C) {
+  const int total = R * C;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int r = e / C, c = e % C;
+    Wt[static_cast<int64_t>(c) * R + r] = W[e];
+  }
+}
+
+// gx = gy @ W^T   (A = gy tile, B = Wt[Cout][Cin])
+__global__ void __launch_bounds__(kThreads)
+lin_bwd_x_kernel(const float* __restrict__ gy, const float* __restrict__ Wt, float* __restrict__ gx,
+                 int64_t rows, int Cin, int Cout) {
+  extern __shared__ __align__(16) float sm[];
+  const int lda = (Cout + 3) & ~3;
+  float* A = sm;
+  float* Bs = A + kTileFacets * lda;
+  const int64_t ntiles = (rows + kTileFacets - 1) / kTileFacets;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kTileFacets;
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTileFacets * lda; e += kThreads) {
+      const int f = e / lda, c = e % lda;
+      A[e] = (r0 + f < rows && c < Cout) ? __ldg(gy + (r0 + f) * Cout + c) : 0.f;
+    }
+    for (int c0 = 0; c0 < Cin; c0 += 128) {
+      const int ncols = min(128, Cin - c0);
+      const TileGemmMap mp(ncols);
+      float acc[4][4];
+      tile_gemm(A, lda, Cout, Wt, Cin, c0, ncols, Bs, mp, acc);
+      if (mp.ty < mp.TY) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int f = mp.ty + mp.TY * i;
+          const int64_t r = r0 + f;
+          if (i < mp.RF && f < kTileFacets && r < rows) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = c0 + 4 * mp.tx + j;
+              if (c < Cin) gx[r * Cin + c] = acc[i][j];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// gW[c][o] = sum_r x[r][c] gy[r][o], gb[o] = sum_r gy[r][o]; CTA (chunk, slice) accumulates the
+// o-slice [o0, o0+os) over its chunk of rows in shared memory and writes a partial.
+__global__ void __launch_bounds__(kThreads)
+lin_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partW,
+                 float* __restrict__ partB, int64_t rows, int Cin, int Cout, int os,
+                 int64_t tiles_per_chunk) {
+  extern __shared__ __align__(16) float sm[];
+  const int ldc = (Cin + 3) & ~3;
+  float* ACC = sm;                        // [ldc][os]   (c-major rows, o contiguous)
+  float* X = ACC + ldc * os;              // [32][ldc]
+  float* G = X + kTileFacets * ldc;       // [32][os]
+  const int chunk = blockIdx.x, slice = blockIdx.y;
+  const int o0 = slice * os;
+  const int on = min(os, Cout - o0);
+  const int64_t ntiles = (rows + kTileFacets - 1) / kTileFacets;
+  const int64_t t_begin = chunk * tiles_per_chunk;
+  const int64_t t_end = min(ntiles, t_begin + tiles_per_chunk);
+  for (int e = threadIdx.x; e < ldc * os; e += kThreads) ACC[e] = 0.f;
+  float gb_acc = 0.f;
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    const int64_t r0 = tile * kTileFacets;
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTileFacets * ldc; e += kThreads) {
+      const int f = e / ldc, c = e % ldc;
+      X[e] = (r0 + f < rows && c < Cin) ? __ldg(x + (r0 + f) * Cin + c) : 0.f;
+    }
+    for (int e = threadIdx.x; e < kTileFacets * os; e += kThreads) {
+      const int f = e / os, o = e % os;
+      G[e] = (r0 + f < rows && o < on) ? __ldg(gy + (r0 + f) * Cout + o0 + o) : 0.f;
+    }
+    __syncthreads();
+    const int nbc = ldc / 4, nbo = os / 4;
+    for (int blk = threadIdx.x; blk < nbc * nbo; blk += kThreads) {
+      const int bc = blk / nbo, bo = blk % nbo;
+      float a[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+#pragma unroll 4
+      for (int f = 0; f < kTileFacets; ++f) {
+        const float4 xv = *reinterpret_cast<const float4*>(X + f * ldc + 4 * bc);
+        const float4 g = *reinterpret_cast<const float4*>(G + f * os + 4 * bo);
+        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i][0] = fmaf(xa[i], g.x, a[i][0]);
+          a[i][1] = fmaf(xa[i], g.y, a[i][1]);
+          a[i][2] = fmaf(xa[i], g.z, a[i][2]);
+          a[i][3] = fmaf(xa[i], g.w, a[i][3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4* dst = reinterpret_cast<float4*>(ACC + (4 * bc + i) * os + 4 * bo);
+        float4 cur = *dst;
+        cur.x += a[i][0], cur.y += a[i][1], cur.z += a[i][2], cur.w += a[i][3];
+        *dst = cur;
+      }
+    }
+    if (threadIdx.x < on) {
+      for (int f = 0; f < kTileFacets; ++f) gb_acc += G[f * os + threadIdx.x];
+    }
+  }
+  __syncthreads();
+  float* pw = partW + static_cast<int64_t>(chunk) * Cin * Cout;
+  for (int e = threadIdx.x; e < Cin * on; e += kThreads) {
+    const int c = e / on, o = e % on;
+    pw[static_cast<int64_t>(c) * Cout + o0 + o] = ACC[c * os + o];
+  }
+  if (threadIdx.x < on) partB[static_cast<int64_t>(chunk) * Cout + o0 + threadIdx.x] = gb_acc;
+}
+
+
+struct LinPlan {
+  int os, nslices, chunks;
+  int64_t tiles_per_chunk;
+};
+
+static void lin_plan(int64_t rows, int Cin, int Cout, LinPlan* pl) {
+  const size_t ldc = (Cin + 3) & ~3;
+  int os = (Cout + 3) & ~3;
+  if (os > 128) os = 128;
+  auto smem = [&](int o) { return (ldc * o + kTileFacets * ldc + kTileFacets * o) * 4; };
+  while (os > 4 && smem(os) > 200 * 1024) os -= 4;
+  pl->os = os;
+  pl->nslices = (Cout + os - 1) / os;
+  const int64_t ntiles = (rows + kTileFacets - 1) / kTileFacets;
+  int64_t chunks = (2 * num_sms()) / pl->nslices;
+  if (chunks < 1) chunks = 1;
+  if (chunks > ntiles) chunks = ntiles;
+  if (chunks < 1) chunks = 1;
+  pl->tiles_per_chunk = (ntiles + chunks - 1) / chunks;
+  if (pl->tiles_per_chunk < 1) pl->tiles_per_chunk = 1;
+  pl->chunks = static_cast<int>((ntiles + pl->tiles_per_chunk - 1) / pl->tiles_per_chunk);
+  if (pl->chunks < 1) pl->chunks = 1;
+}
+
+}  // namespace fgc
+
+using namespace fgc;
+
+extern "C" {
+
+int fgc_lin_fwd(const float* x, const float* W, const float* b, float* y, int64_t rows, int Cin,
+                int Cout, int act, float alpha, void* stream) {
+  FGC_REQUIRE(x && W && b && y && rows >= 0 && Cin > 0 && Cout > 0, "lin_fwd: bad arguments");
+  if (rows == 0) return FGC_OK;
+  const size_t smem = (static_cast<size_t>(kTileFacets) * ((Cin + 3) & ~3) + kChunkK * 128) * 4;
+  FGC_UNSUPPORTED(smem > 227 * 1024, "lin_fwd: Cin = %d too large", Cin);
+  FGC_CUDA(cudaFuncSetAttribute(lin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (rows + kTileFacets - 1) / kTileFacets;
+  int64_t grid = static_cast<int64_t>(num_sms()) * 2;
+  if (grid > ntiles) grid = ntiles;
+  lin_fwd_kernel<<<static_cast<unsigned>(grid), kThreads, smem, as_stream(stream)>>>(
+      x, W, b, y, rows, Cin, Cout, act, alpha);
+  FGC_LAUNCHED("lin_fwd_kernel");
+  return FGC_OK;
+}
+
+int fgc_mlp_head_fwd(const float* x, const float* W1, const float* b1, const float* W2,
+                     const float* b2, float* y, int64_t rows, int Cin, int H, int Cout, float alpha,
+                     void* stream) {
+  FGC_REQUIRE(x && W1 && b1 && W2 && b2 && y && rows >= 0 && Cin > 0 && H > 0 && Cout > 0,
+              "mlp_head_fwd: bad arguments");
+  FGC_UNSUPPORTED(Cout > kHeadMaxOut, "mlp_head_fwd: Cout <= %d supported", kHeadMaxOut);
+  if (rows == 0) return FGC_OK;
+  const size_t smem = (static_cast<size_t>(kTileFacets) * ((Cin + 3) & ~3) + kChunkK * 128 +
+                       kTileFacets * 32 * kHeadMaxOut) * 4;
+  FGC_UNSUPPORTED(smem > 227 * 1024, "mlp_head_fwd: Cin = %d too large", Cin);
+  FGC_CUDA(cudaFuncSetAttribute(mlp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (rows + kTileFacets - 1) / kTileFacets;
+  int64_t grid = static_cast<int64_t>(num_sms()) * 2;
+  if (grid > ntiles) grid = ntiles;
+  mlp_head_kernel<<<static_cast<unsigned>(grid), kThreads, smem, as_stream(stream)>>>(
+      x, W1, b1, W2, b2, y, rows, Cin, H, Cout, alpha);
+  FGC_LAUNCHED("mlp_head_kernel");
+  return FGC_OK;
+}
+
+size_t fgc_lin_bwd_workspace(int64_t rows, int Cin, int Cout) {
+  LinPlan pl;
+  lin_plan(rows, Cin, Cout, &pl);
+  const size_t nW = static_cast<size_t>(Cin) * Cout;
+  return ws_bytes(nW, 4) + ws_bytes(static_cast<size_t>(pl.chunks) * nW, 4) +
+         ws_bytes(static_cast<size_t>(pl.chunks) * Cout, 4) + 1024;
+}
+
+int fgc_lin_bwd(const float* gy, const float* x, const float* W, float* gx, float* gW, float* gb,
+                int64_t rows, int Cin, int Cout, void* workspace, size_t workspace_bytes,
+                void* stream) {
+  FGC_REQUIRE(gy && x && W && gW && gb && rows > 0 && Cin > 0 && Cout > 0, "lin_bwd: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  LinPlan pl;
+  lin_plan(rows, Cin, Cout, &pl);
+  const size_t nW = static_cast<size_t>(Cin) * Cout;
+  Workspace ws(workspace, workspace_bytes);
+  float* Wt = ws.take<float>(nW);
+  float* partW = ws.take<float>(static_cast<size_t>(pl.chunks) * nW);
+  float* partB = ws.take<float>(static_cast<size_t>(pl.chunks) * Cout);
+  FGC_REQUIRE(ws.ok(), "lin_bwd: workspace too small");
+  const int64_t ntiles = (rows + kTileFacets - 1) / kTileFacets;
+  if (gx) {
+    transpose2d_kernel<<<static_cast<unsigned>((nW + 255) / 256), 256, 0, st>>>(W, Wt, Cin, Cout);
+    FGC_LAUNCHED("transpose2d_kernel");
+    const size_t smem = (static_cast<size_t>(kTileFacets) * ((Cout + 3) & ~3) + kChunkK * 128) * 4;
+    FGC_UNSUPPORTED(smem > 227 * 1024, "lin_bwd: Cout = %d too large", Cout);
+    FGC_CUDA(cudaFuncSetAttribute(lin_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = static_cast<int64_t>(num_sms()) * 2;
+    if (grid > ntiles) grid = ntiles;
+    lin_bwd_x_kernel<<<static_cast<unsigned>(grid), kThreads, smem, st>>>(gy, Wt, gx, rows, Cin, Cout);
+    FGC_LAUNCHED("lin_bwd_x_kernel");
+  }
+  {
+    const size_t ldc = (Cin + 3) & ~3;
+    const size_t smem = (ldc * pl.os + kTileFacets * ldc + kTileFacets * pl.os) * 4;
+    FGC_UNSUPPORTED(smem > 227 * 1024, "lin_bwd: Cin = %d too large", Cin);
+    FGC_CUDA(cudaFuncSetAttribute(lin_bwd_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(pl.chunks, pl.nslices);
+    lin_bwd_w_kernel<<<grid, kThreads, smem, st>>>(x, gy, partW, partB, rows, Cin, Cout, pl.os,
+                                                   pl.tiles_per_chunk);
+    FGC_LAUNCHED("lin_bwd_w_kernel");
+  }
+  int rc = launch_reduce_partials(partW, gW, nW, pl.chunks, nW, st);
+  if (rc) return rc;
+  return launch_reduce_partials(partB, gb, Cout, pl.chunks, Cout, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+"""Tensor-level wrappers over the C ABI (device tensors in, device tensors out).
+
+PyTorch is used only for device memory, streams and autograd bookkeeping; all arithmetic
+runs in libfacetconv_b200.so.  Every function requires CUDA tensors and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ConvShape, check
+
+ACT_NONE, ACT_LRELU = 0, 1
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.FacetConvError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _i32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.FacetConvError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != torch.int32:
+        # the reference's preprocessing emits int64 and relies on placeholder casting
+        # (reference Code/train.py:52-56)
+        t = t.to(torch.int32)
+    return t.contiguous()
+
+
+def _ws(nbytes: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+
+
+def conv_shape(x, adj, W0, u, cw=None, ca0=0, ca=None) -> ConvShape:
+    B, N, Cin = x.shape
+    if adj.dim() != 3 or adj.shape[0] != B or adj.shape[1] != N:
+        raise _lib.FacetConvError("adj must be [B,N,K] matching x[B,N,Cin]; got %s vs %s"
+                                  % (tuple(adj.shape), tuple(x.shape)))
+    M, Cout, Cw = W0.shape
+    cw = Cin if cw is None else cw
+    ca = (Cin - ca0) if ca is None else ca
+    if Cw != cw:
+        raise _lib.FacetConvError("W0 must be [M,Cout,%d], got %s" % (cw, tuple(W0.shape)))
+    if tuple(u.shape) != (M, ca):
+        raise _lib.FacetConvError("u must be [M,%d], got %s" % (ca, tuple(u.shape)))
+    return ConvShape(B, N, adj.shape[2], Cin, cw, ca0, ca, Cout, M)
+
+
+# ----------------------------------------------------------------------------- convolution
+def conv_fwd(x, adj, W0, b, u, v, c, bias_mask=True, act=ACT_NONE, alpha=0.1, cw=None, ca0=0, ca=None):
+    """y[B,N,Cout] of the facet-graph convolution (reference Code/model.py:427-504)."""
+    L = _lib.lib()
+    x, W0, b, u, v, c = (_f32(t, n) for t, n in ((x, "x"), (W0, "W0"), (b, "b"), (u, "u"), (v, "v"), (c, "c")))
+    adj = _i32(adj, "adj")
+    s = conv_shape(x, adj, W0, u, cw, ca0, ca)
+    y = torch.empty((s.B, s.N, s.Cout), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        nws = L.fgc_conv_fwd_workspace(C.byref(s))
+        ws = _ws(nws, x)
+        check(L.fgc_conv_fwd(C.byref(s), _p(x), _p(adj), _p(W0), _p(b), _p(u), _p(v), _p(c), _p(y),
+                             int(bool(bias_mask)), int(act), float(alpha), _p(ws), ws.numel(), _stream(x)),
+              "fgc_conv_fwd")
+    return y
+
+
+class ReverseAdjacency:
+    """Caller-owned reverse adjacency (built once per adjacency tensor, reused by every backward
+    through a layer that uses it).  Replaces the scatter of TF's gather gradient."""
+
+    def __init__(self, adj: torch.Tensor):
+        L = _lib.lib()
+        adj = _i32(adj, "adj")
+        B, N, K = adj.shape
+        self.shape = (B, N, K)
+        self.ptr = torch.empty(B * N + 1, dtype=torch.int32, device=adj.device)
+        self.edge = torch.empty(B * N * K, dtype=torch.int32, device=adj.device)
+        nnz = C.c_int64(0)
+        with torch.cuda.device(adj.device):
+            ws = _ws(L.fgc_reverse_adj_workspace(B, N, K), adj)
+            check(L.fgc_build_reverse_adj(_p(adj), B, N, K, _p(self.ptr), _p(self.edge), C.byref(nnz),
+                                          _p(ws), ws.numel(), _stream(adj)), "fgc_build_reverse_adj")
+        self.nnz = int(nnz.value)
+
+
+def conv_bwd(gy, x, adj, rev: ReverseAdjacency, W0, u, v, c, bias_mask=True, cw=None, ca0=0, ca=None):
+    """(gx, gW0, gb, gu, gv, gc) -- deterministic backward of conv_fwd."""
+    L = _lib.lib()
+    gy, x, W0, u, v, c = (_f32(t, n) for t, n in ((gy, "gy"), (x, "x"), (W0, "W0"), (u, "u"), (v, "v"), (c, "c")))
+    adj = _i32(adj, "adj")
+    s = conv_shape(x, adj, W0, u, cw, ca0, ca)
+    if rev.shape != (s.B, s.N, s.K):
+        raise _lib.FacetConvError("reverse adjacency built for %s, layer is %s" % (rev.shape, (s.B, s.N, s.K)))
+    dev = x.device
+    gx = torch.empty_like(x)
+    gW0 = torch.empty_like(W0)
+    gb = torch.empty(s.Cout, dtype=torch.float32, device=dev)
+    gu = torch.empty_like(u)
+    gv = torch.empty_like(v)
+    gc = torch.empty_like(c)
+    with torch.cuda.device(dev):
+        ws = _ws(L.fgc_conv_bwd_workspace(C.byref(s)), x)
+        check(L.fgc_conv_bwd(C.byref(s), _p(gy), _p(x), _p(adj), _p(rev.ptr), _p(rev.edge), _p(W0), _p(u),
+                             _p(v), _p(c), _p(gx), _p(gW0), _p(gb), _p(gu), _p(gv), _p(gc),
+                             int(bool(bias_mask)), _p(ws), ws.numel(), _stream(x)), "fgc_conv_bwd")
+    return gx, gW0, gb, gu, gv, gc
+
+
+def gather_rows(x, adj):
+    """concat([0],x)[adj] -> [B,N,K,C], bit-exact (reference Code/model.py:380-399)."""
+    L = _lib.lib()
+    x = _f32(x, "x")
+    adj = _i32(adj, "adj")
+    B, N, Cc = x.shape
+    K = adj.shape[2]
+    out = torch.empty((B, N, K, Cc), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.fgc_gather_rows(_p(x), _p(adj), _p(out), B, N, K, Cc, _stream(x)), "fgc_gather_rows")
+    return out
+
+
+def assignments(x, adj, u, v, c, ca0=0, ca=None):
+    """q[B,N,K,M] (reference Code/model.py:74-95)."""
+    L = _lib.lib()
+    x, u, v, c = (_f32(t, n) for t, n in ((x, "x"), (u, "u"), (v, "v"), (c, "c")))
+    adj = _i32(adj, "adj")
+    B, N, Cin = x.shape
+    M = u.shape[0]
+    ca = (Cin - ca0) if ca is None else ca
+    s = ConvShape(B, N, adj.shape[2], Cin, Cin, ca0, ca, 1, M)
+    q = torch.empty((B, N, adj.shape[2], M), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = _ws(B * N * 2 * M * 4 + 1024, x)
+        check(L.fgc_assignments(C.byref(s), _p(x), _p(adj), _p(u), _p(v), _p(c), _p(q), _p(ws), ws.numel(),
+                                _stream(x)), "fgc_assignments")
+    return q
+
+
+# ----------------------------------------------------------------------------- pooling / pointwise
+def pool_max(x, group=4):
+    L = _lib.lib()
+    x = _f32(x, "x")
+    B, N, Cc = x.shape
+    if N % group:
+        raise _lib.FacetConvError("pool_max: N=%d not divisible by %d" % (N, group))
+    y = torch.empty((B, N // group, Cc), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.fgc_pool_max(_p(x), _p(y), B * (N // group), Cc, group, _stream(x)), "fgc_pool_max")
+    return y
+
+
+def pool_max_bwd(gy, x, y, group=4):
+    L = _lib.lib()
+    gy, x, y = _f32(gy, "gy"), _f32(x, "x"), _f32(y, "y")
+    gx = torch.empty_like(x)
+    B, No, Cc = y.shape
+    with torch.cuda.device(x.device):
+        check(L.fgc_pool_max_bwd(_p(gy), _p(x), _p(y), _p(gx), B * No, Cc, group, _stream(x)), "fgc_pool_max_bwd")
+    return gx
+
+
+def pool_avg_ignore_zeros(x, steps=2):
+    L = _lib.lib()
+    x = _f32(x, "x")
+    B, N, Cc = x.shape
+    y = torch.empty((B, N >> steps, Cc), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.fgc_pool_avg_ignore_zeros(_p(x), _p(y), B, N, Cc, steps, _stream(x)), "fgc_pool_avg_ignore_zeros")
+    return y
+
+
+def upsample(x, group=4):
+    L = _lib.lib()
+    x = _f32(x, "x")
+    B, N, Cc = x.shape
+    y = torch.empty((B, N * group, Cc), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.fgc_upsample(_p(x), _p(y), B * N, Cc, group, _stream(x)), "fgc_upsample")
+    return y
+
+
+def upsample_bwd(gy, group=4):
+    L = _lib.lib()
+    gy = _f32(gy, "gy")
+    B, Ng, Cc = gy.shape
+    gx = torch.empty((B, Ng // group, Cc), dtype=torch.float32, device=gy.device)
+    with torch.cuda.device(gy.device):
+        check(L.fgc_upsample_bwd(_p(gy), _p(gx), B * (Ng // group), Cc, group, _stream(gy)), "fgc_upsample_bwd")
+    return gx
+
+
+def lrelu(x, alpha=0.1):
+    L = _lib.lib()
+    x = _f32(x, "x")
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(L.fgc_lrelu(_p(x), _p(y), x.numel(), float(alpha), _stream(x)), "fgc_lrelu")
+    return y
+
+
+def lrelu_bwd(gy, x_pre, alpha=0.1):
+    L = _lib.lib()
+    gy, x_pre = _f32(gy, "gy"), _f32(x_pre, "x_pre")
+    gx = torch.empty_like(x_pre)
+    with torch.cuda.device(gy.device):
+        check(L.fgc_lrelu_bwd(_p(gy), _p(x_pre), _p(gx), gy.numel(), float(alpha), _stream(gy)), "fgc_lrelu_bwd")
+    return gx
+
+
+def concat2(a, b):
+    L = _lib.lib()
+    a, b = _f32(a, "a"), _f32(b, "b")
+    B, N, Ca = a.shape
+    Cb = b.shape[2]
+    y = torch.empty((B, N, Ca + Cb), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(L.fgc_concat2(_p(a), _p(b), _p(y), B * N, Ca, Cb, _stream(a)), "fgc_concat2")
+    return y
+
+
+def split2(gy, Ca):
+    L = _lib.lib()
+    gy = _f32(gy, "gy")
+    B, N, Cc = gy.shape
+    ga = torch.empty((B, N, Ca), dtype=torch.float32, device=gy.device)
+    gb = torch.empty((B, N, Cc - Ca), dtype=torch.float32, device=gy.device)
+    with torch.cuda.device(gy.device):
+        check(L.fgc_split2(_p(gy), _p(ga), _p(gb), B * N, Ca, Cc - Ca, _stream(gy)), "fgc_split2")
+    return ga, gb
+
+
+def gather_perm(x, idx):
+    """y[r] = x[idx[r]] on a [rows, C] tensor."""
+    L = _lib.lib()
+    x = _f32(x, "x")
+    idx = _i32(idx, "idx")
+    y = torch.empty((idx.numel(), x.shape[-1]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.fgc_gather_perm(_p(x), _p(idx), _p(y), idx.numel(), x.shape[-1], _stream(x)), "fgc_gather_perm")
+    return y
+
+
+# ----------------------------------------------------------------------------- linear layers
+def lin_fwd(x, W, b, act=ACT_NONE, alpha=0.1):
+    L = _lib.lib()
+    x, W, b = _f32(x, "x"), _f32(W, "W"), _f32(b, "b")
+    Cin, Cout = W.shape
+    rows = x.numel() // Cin
+    y = torch.empty(tuple(x.shape[:-1]) + (Cout,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.fgc_lin_fwd(_p(x), _p(W), _p(b), _p(y), rows, Cin, Cout, int(act), float(alpha), _stream(x)),
+              "fgc_lin_fwd")
+    return y
+
+
+def lin_bwd(gy, x, W, need_gx=True):
+    L = _lib.lib()
+    gy, x, W = _f32(gy, "gy"), _f32(x, "x"), _f32(W, "W")
+    Cin, Cout = W.shape
+    rows = x.numel() // Cin
+    gx = torch.empty_like(x) if need_gx else None
+    gW = torch.empty_like(W)
+    gb = torch.empty(Cout, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = _ws(L.fgc_lin_bwd_workspace(rows, Cin, Cout), x)
+        check(L.fgc_lin_bwd(_p(gy), _p(x), _p(W), _p(gx), _p(gW), _p(gb), rows, Cin, Cout, _p(ws), ws.numel(),
+                            _stream(x)), "fgc_lin_bwd")
+    return gx, gW, gb
+
+
+def mlp_head(x, W1, b1, W2, b2, alpha=0.1):
+    """lrelu(x@W1+b1)@W2+b2 without materialising the hidden activation (inference)."""
+    L = _lib.lib()
+    x, W1, b1, W2, b2 = (_f32(t, n) for t, n in ((x, "x"), (W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2")))
+    Cin, H = W1.shape
+    Cout = W2.shape[1]
+    rows = x.numel() // Cin
+    y = torch.empty(tuple(x.shape[:-1]) + (Cout,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.fgc_mlp_head_fwd(_p(x), _p(W1), _p(b1), _p(W2), _p(b2), _p(y), rows, Cin, H, Cout, float(alpha),
+                                 _stream(x)), "fgc_mlp_head_fwd")
+    return y
+
+
+# ----------------------------------------------------------------------------- normalisation / loss
+def normalize_rows(x):
+    """reference Code/utils.py:1700-1715 (normalizeTensor) on ONE patch x[1,N,3] / [N,3]."""
+    L = _lib.lib()
+    x = _f32(x, "x")
+    rows = x.numel() // 3
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        ws = _ws(L.fgc_normalize_workspace(rows), x)
+        check(L.fgc_normalize_rows(_p(x), _p(y), rows, _p(ws), ws.numel(), _stream(x)), "fgc_normalize_rows")
+    return y
+
+
+def normalize_rows_bwd(gy, x):
+    L = _lib.lib()
+    gy, x = _f32(gy, "gy"), _f32(x, "x")
+    rows = x.numel() // 3
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        ws = _ws(L.fgc_normalize_workspace(rows), x)
+        check(L.fgc_normalize_rows_bwd(_p(gy), _p(x), _p(gx), rows, _p(ws), ws.numel(), _stream(x)),
+              "fgc_normalize_rows_bwd")
+    return gx
+
+
+def face_normals_loss(fn, gt, need_grad=False, gscale=1.0):
+    """reference Code/train.py:1272-1294.  Returns (loss[1], gfn or None)."""
+    L = _lib.lib()
+    fn, gt = _f32(fn, "fn"), _f32(gt, "gt")
+    rows = fn.numel() // 3
+    loss = torch.empty(1, dtype=torch.float32, device=fn.device)
+    gfn = torch.empty_like(fn) if need_grad else None
+    with torch.cuda.device(fn.device):
+        ws = _ws(L.fgc_normalize_workspace(rows), fn)
+        check(L.fgc_face_normals_loss(_p(fn), _p(gt), _p(loss), _p(gfn), rows, float(gscale), _p(ws), ws.numel(),
+                                      _stream(fn)), "fgc_face_normals_loss")
+    return loss, gfn
+
+
+# ----------------------------------------------------------------------------- vertex updates
+def vertex_update_edges(x, normals, edge_map, v_edges, iters=60, lam=1.0 / 18):
+    """reference Code/train.py:1467-1557 (update_position2).  x[V,3] -> x[V,3]."""
+    L = _lib.lib()
+    x, normals = _f32(x, "x"), _f32(normals, "normals")
+    edge_map, v_edges = _i32(edge_map, "edge_map"), _i32(v_edges, "v_edges")
+    V = x.numel() // 3
+    F = normals.numel() // 3
+    E = edge_map.numel() // 4
+    max_edges = v_edges.numel() // V
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        ws = _ws(L.fgc_vertex_update_workspace(V), x)
+        check(L.fgc_vertex_update_edges(_p(x), _p(out), _p(normals), _p(edge_map), _p(v_edges), V, F, E,
+                                        max_edges, int(iters), float(lam), _p(ws), ws.numel(), _stream(x)),
+              "fgc_vertex_update_edges")
+    return out
+
+
+def vertex_update_ms(x, normals, faces, v_faces, scale, steps=2, iters=20):
+    """One scale of reference Code/train.py:1668-1798 (update_position_MS)."""
+    L = _lib.lib()
+    x, normals = _f32(x, "x"), _f32(normals, "normals")
+    faces, v_faces = _i32(faces, "faces"), _i32(v_faces, "v_faces")
+    V = x.numel() // 3
+    N0 = faces.numel() // 3
+    max_faces = v_faces.numel() // V
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        ws = _ws(L.fgc_vertex_update_ms_workspace(V, N0), x)
+        check(L.fgc_vertex_update_ms(_p(x), _p(out), _p(normals), _p(faces), _p(v_faces), V, N0, max_faces,
+                                     int(scale), int(steps), int(iters), _p(ws), ws.numel(), _stream(x)),
+              "fgc_vertex_update_ms")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.lib().fgc_launch_count())

@@ -1,0 +1,216 @@
+/*
+ * facetconv_b200.h -- C ABI of the B200-native facet-graph convolution hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference
+ * tree Elensil/Facet_Graph_Convolution).  The reference is Python/TensorFlow and has no
+ * FFI of its own; INTEGRATION.md shows the ctypes stub a maintainer would add to
+ * Code/model.py to route custom_conv2d & friends through this library.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers (cudaMalloc / torch CUDA storage), fp32
+ *     row-major contiguous, indices int32, unless the function name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls only enqueue work, they never synchronise (the _host variants do);
+ *   - inputs are borrowed and never written; outputs must not alias inputs;
+ *   - return value 0 = success, non-zero = error; fgc_last_error() gives the message
+ *     (thread-local).  No CPU fallback exists: without a CUDA device every compute
+ *     entry point fails with FGC_ERR_CUDA.
+ *   - adjacency layout: adj[B,N,K] int32, 1-indexed neighbour ids, 0 = padding,
+ *     column 0 = the facet itself (reference Code/utils.py:243-295, 1799-1827).
+ */
+#ifndef FACETCONV_B200_H_
+#define FACETCONV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FGC_API __attribute__((visibility("default")))
+#else
+#define FGC_API
+#endif
+
+#define FGC_OK 0
+#define FGC_ERR_ARG 1
+#define FGC_ERR_CUDA 2
+#define FGC_ERR_UNSUPPORTED 3
+
+#define FGC_ACT_NONE 0
+#define FGC_ACT_LRELU 1 /* relu(x) - alpha*relu(-x), reference Code/model.py:828-830 */
+
+#define FGC_MAX_K 32  /* neighbour slots per facet (reference default K_faces = 23) */
+#define FGC_MAX_M 16  /* weight matrices per layer (reference network: 9)          */
+#define FGC_MAX_C 256 /* channels per row                                           */
+
+FGC_API int fgc_version(void);
+FGC_API const char* fgc_last_error(void);
+/* number of CUDA devices visible (0 when there is no driver/GPU); never fails */
+FGC_API int fgc_device_count(void);
+/* kernels launched by this library in the calling process since load (all threads) */
+FGC_API uint64_t fgc_launch_count(void);
+
+/* Opt-in per-kernel timing for the bench harness (not thread-safe; one stream at a time):
+ * between _begin and _end every kernel this library launches on `stream` is bracketed by CUDA
+ * events; _end synchronises on the last one and writes lines "kernel_name total_ms launches\n". */
+FGC_API int fgc_profile_begin(void* stream);
+FGC_API int fgc_profile_end(char* buf, size_t buf_bytes);
+
+/* ---------------------------------------------------------------- facet-graph convolution
+ *
+ * Replaces reference Code/model.py:427-504 (custom_conv2d) together with :74-95
+ * (get_weight_assigments) and :380-405 (get_slices/get_patches); with the channel
+ * windows below it also covers the variants at :97-124, :610-696 and :699-760.
+ *
+ *   uvx[r, 0:M]  = u . x_r[ca0:ca0+ca] + c        (own-row logit part)
+ *   uvx[r, M:2M] = v . x_r[ca0:ca0+ca]            (neighbour logit part)
+ *   q[n,k,:]     = softmax_m( uvx[n,0:M] + (adj[n,k] ? uvx[adj[n,k]-1, M:2M] : 0) )
+ *   s[n,m,:]     = sum_k q[n,k,m] * x_{adj[n,k]-1}[0:cw]          (padding adds 0)
+ *   y[n,:]       = act( inv_cnt[n] * sum_m W0[m] s[n,m,:] + (cnt[n]>0 || !bias_mask) * b )
+ *
+ * Translation-invariant assignments (model.py:97-124) are the same formula with
+ * v = -u.  "position for assignment" (model.py:610-696): ca0 = 0, ca = Cin, cw = Cin-3.
+ * "only position" (model.py:699-760): ca0 = Cin-3, ca = 3, cw = Cin-3, bias_mask = 0.
+ */
+typedef struct fgc_conv_shape {
+  int32_t B;    /* batch (patches); rows of different batch elements never mix */
+  int32_t N;    /* facets per batch element */
+  int32_t K;    /* neighbour slots, <= FGC_MAX_K */
+  int32_t Cin;  /* row width of x */
+  int32_t Cw;   /* channels [0,Cw) enter the aggregation / contraction; W0 is [M,Cout,Cw] */
+  int32_t Ca0;  /* channels [Ca0,Ca0+Ca) enter the assignment logits; u,v are [M,Ca] */
+  int32_t Ca;
+  int32_t Cout;
+  int32_t M;    /* <= FGC_MAX_M */
+} fgc_conv_shape;
+
+/* bytes of device scratch fgc_conv_fwd / fgc_conv_bwd need for this shape (upper bound) */
+FGC_API size_t fgc_conv_fwd_workspace(const fgc_conv_shape* s);
+FGC_API size_t fgc_conv_bwd_workspace(const fgc_conv_shape* s);
+
+/* forward; y[B,N,Cout].  v may not be NULL (pass -u for translation invariance). */
+FGC_API int fgc_conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0,
+                 const float* b, const float* u, const float* v, const float* c, float* y,
+                 int bias_mask, int act, float alpha, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* Reverse adjacency (caller-owned cache, built once per adjacency; replaces the scatter of
+ * TF's gather gradient, UnsortedSegmentSum): for every target row t = b*N + j the list of
+ * edge ids e = (b*N + n)*K + k with adj[b,n,k] == j+1, ascending.  rev_ptr[B*N+1],
+ * rev_edge[nnz] with nnz <= B*N*K (allocate B*N*K).  *nnz_out (host) receives nnz; this
+ * call synchronises the stream. */
+FGC_API size_t fgc_reverse_adj_workspace(int B, int N, int K);
+FGC_API int fgc_build_reverse_adj(const int32_t* adj, int B, int N, int K, int32_t* rev_ptr,
+                          int32_t* rev_edge, int64_t* nnz_out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* backward of fgc_conv_fwd (act = NONE; the activation gradient is applied by the caller or by
+ * fgc_lrelu_bwd).  Deterministic: no floating-point atomics, fixed summation order.
+ * Outputs: gx[B,N,Cin], gW0[M,Cout,Cw], gb[Cout], gu[M,Ca], gv[M,Ca], gc[M] (all overwritten). */
+FGC_API int fgc_conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
+                 const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
+                 const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu,
+                 float* gv, float* gc, int bias_mask, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* debug/parity helper: the gathered-neighbour tensor concat([0],x)[adj] -> out[B,N,K,C]
+ * (reference Code/model.py:380-399).  Bit-exact by construction. */
+FGC_API int fgc_gather_rows(const float* x, const int32_t* adj, float* out, int B, int N, int K, int C,
+                    void* stream);
+/* debug/parity helper: assignments q[B,N,K,M] (reference Code/model.py:74-95) */
+FGC_API int fgc_assignments(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* u,
+                    const float* v, const float* c, float* q, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- pooling / unpooling / pointwise
+ * reference Code/model.py:779-825 (custom_binary_tree_pooling, custom_upsampling), :828-830 */
+FGC_API int fgc_pool_max(const float* x, float* y, int64_t rows_out, int C, int group,
+                 void* stream); /* y[r] = max over x[group*r .. group*r+group-1] */
+/* gradient of reduce_max as TF defines it: split equally among tied maxima */
+FGC_API int fgc_pool_max_bwd(const float* gy, const float* x, const float* y, float* gx, int64_t rows_out,
+                     int C, int group, void* stream);
+FGC_API int fgc_pool_avg_ignore_zeros(const float* x, float* y, int B, int64_t rows_in, int C, int steps,
+                              void* stream);
+FGC_API int fgc_upsample(const float* x, float* y, int64_t rows_in, int C, int group, void* stream);
+FGC_API int fgc_upsample_bwd(const float* gy, float* gx, int64_t rows_in, int C, int group, void* stream);
+FGC_API int fgc_lrelu(const float* x, float* y, int64_t n, float alpha, void* stream);
+FGC_API int fgc_lrelu_bwd(const float* gy, const float* x_pre, float* gx, int64_t n, float alpha,
+                  void* stream);
+/* concat along channels: y[r] = [a[r,0:Ca] | b[r,0:Cb]]  (tf.concat at model.py:909,929) */
+FGC_API int fgc_concat2(const float* a, const float* b, float* y, int64_t rows, int Ca, int Cb,
+                void* stream);
+FGC_API int fgc_split2(const float* gy, float* ga, float* gb, int64_t rows, int Ca, int Cb, void* stream);
+/* rows permutation gather: y[r] = x[idx[r]] (host fancy indexing at dataClasses.py:142,
+ * train.py:117-121) */
+FGC_API int fgc_gather_perm(const float* x, const int32_t* idx, float* y, int64_t rows_out, int C,
+                    void* stream);
+
+/* ---------------------------------------------------------------- per-facet linear layers
+ * reference Code/model.py:763-769 (custom_lin): y = x @ W + b, W[Cin,Cout] */
+FGC_API int fgc_lin_fwd(const float* x, const float* W, const float* b, float* y, int64_t rows, int Cin,
+                int Cout, int act, float alpha, void* stream);
+FGC_API int fgc_lin_bwd(const float* gy, const float* x, const float* W, float* gx, float* gW, float* gb,
+                int64_t rows, int Cin, int Cout, void* workspace, size_t workspace_bytes,
+                void* stream);
+FGC_API size_t fgc_lin_bwd_workspace(int64_t rows, int Cin, int Cout);
+/* fused regression head (model.py:936-941): y = lrelu(x@W1+b1) @ W2 + b2 without materialising
+ * the hidden activation.  W1[Cin,H], W2[H,Cout], Cout <= 4. */
+FGC_API int fgc_mlp_head_fwd(const float* x, const float* W1, const float* b1, const float* W2,
+                     const float* b2, float* y, int64_t rows, int Cin, int H, int Cout, float alpha,
+                     void* stream);
+
+/* ---------------------------------------------------------------- output normalisation & loss
+ * reference Code/utils.py:1700-1715 (normalizeTensor) over x[rows,3] of ONE patch: global
+ * mean-abs rescale, then row L2 normalisation with the three 1e-5 epsilons. */
+FGC_API size_t fgc_normalize_workspace(int64_t rows);
+FGC_API int fgc_normalize_rows(const float* x, float* y, int64_t rows, void* workspace,
+                       size_t workspace_bytes, void* stream);
+FGC_API int fgc_normalize_rows_bwd(const float* gy, const float* x, float* gx, int64_t rows, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* reference Code/train.py:1272-1294 (faceNormalsLoss): loss[0] = mean angle in degrees over real
+ * rows; optional gradient w.r.t. fn scaled by gscale. */
+FGC_API int fgc_face_normals_loss(const float* fn, const float* gt, float* loss, float* gfn /*nullable*/,
+                          int64_t rows, float gscale, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---------------------------------------------------------------- vertex position updates
+ * reference Code/train.py:1467-1557 (update_position2): `iters` Jacobi sweeps,
+ *   x_i += (1/18) sum_{e in v_edges[i]} sum_{w in (v1,v2)(e)} sum_{f in (f1,f2)(e)} n_f (n_f.(x_w - x_i))
+ * x_in/x_out[V,3], normals[F,3], edge_map[E,4] = (v1,v2,f1,f2 | -1), v_edges[V,max_edges] | -1.
+ * workspace holds the ping-pong buffer. */
+FGC_API size_t fgc_vertex_update_workspace(int64_t V);
+FGC_API int fgc_vertex_update_edges(const float* x_in, float* x_out, const float* normals,
+                            const int32_t* edge_map, const int32_t* v_edges, int64_t V, int64_t F,
+                            int64_t E, int max_edges, int iters, float lambda, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* reference Code/train.py:1668-1798 (update_position_MS + updateFacesCenter) for ONE scale:
+ * `iters` sweeps of  x_v += (1/#faces_v) sum_{f in v_faces[v]} n_F (n_F.(c_F - x_v)),
+ * F = f >> (2*scale) (floor, -1 stays padding), c = face centres pooled `scale` times with
+ * avg_ignore_zeros.  faces[N0,3] vertex ids (-1 rows = fake nodes), normals[N0 >> 2*scale, 3]. */
+FGC_API size_t fgc_vertex_update_ms_workspace(int64_t V, int64_t N0);
+FGC_API int fgc_vertex_update_ms(const float* x_in, float* x_out, const float* normals,
+                         const int32_t* faces, const int32_t* v_faces, int64_t V, int64_t N0,
+                         int max_faces, int scale, int steps, int iters, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- host-buffer entry points
+ * What a non-torch FFI binding calls: pinned or pageable HOST pointers in, HOST pointers out;
+ * the call allocates device buffers (cached per thread), copies H2D, runs the kernels on
+ * `device`, copies D2H and synchronises.  Used for the end-to-end (`e2e`) measurement. */
+FGC_API int fgc_conv_fwd_host(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0,
+                      const float* b, const float* u, const float* v, const float* c, float* y,
+                      int bias_mask, int act, float alpha, int device);
+FGC_API int fgc_conv_fwd_bwd_host(const fgc_conv_shape* s, const float* x, const int32_t* adj,
+                          const float* gy, const float* W0, const float* b, const float* u,
+                          const float* v, const float* c, float* y, float* gx, float* gW0, float* gb,
+                          float* gu, float* gv, float* gc, int bias_mask, int device);
+FGC_API void fgc_host_release(void); /* frees the per-thread device cache of the _host entry points */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACETCONV_B200_H_ */

@@ -1,0 +1,58 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads without a GPU, exports every
+symbol include/facetconv_b200.h declares, and refuses to compute without a device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "facetconv_b200.h")).read()
+    return sorted(set(re.findall(r"FGC_API\s+[\w\s\*]+?\b(fgc_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    syms = _declared_symbols()
+    assert len(syms) >= 35
+    for must in ("fgc_conv_fwd", "fgc_conv_bwd", "fgc_build_reverse_adj", "fgc_pool_max", "fgc_upsample",
+                 "fgc_mlp_head_fwd", "fgc_normalize_rows", "fgc_vertex_update_edges", "fgc_vertex_update_ms",
+                 "fgc_conv_fwd_host", "fgc_conv_fwd_bwd_host"):
+        assert must in syms
+
+
+def test_library_builds_loads_and_exports_every_symbol():
+    from facet_graph_convolution_b200.build import build
+    from facet_graph_convolution_b200 import _lib
+    path = build()
+    h = ctypes.CDLL(path)
+    for s in _declared_symbols():
+        assert hasattr(h, s), "missing export %s" % s
+    # the ctypes signature table covers the whole header too
+    assert set(_declared_symbols()) == set(_lib.SIGNATURES)
+    assert _lib.lib().fgc_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    from facet_graph_convolution_b200 import _lib, ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert _lib.lib().fgc_device_count() == 0
+    x = torch.zeros(1, 4, 6)
+    adj = torch.zeros(1, 4, 3, dtype=torch.int32)
+    with pytest.raises(_lib.FacetConvError):
+        ops.conv_fwd(x, adj, torch.zeros(2, 5, 6), torch.zeros(5), torch.zeros(2, 6), torch.zeros(2, 6), torch.zeros(2))
+    with pytest.raises(_lib.FacetConvError):
+        _lib.require_device()
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "facet_graph_convolution_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

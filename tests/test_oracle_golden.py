@@ -113,3 +113,17 @@ def test_index_layouts():
         assert np.array_equal(mesh.vertex_faces(F, 25), g[tag + "_vf"])
     # the reference's only known-answer vector (Code/lib/coarsening.py:243-244)
     assert list(g["compute_perm_out"]) == [3, 4, 0, 9, 1, 2, 5, 8, 6, 7, 10, 11]
+
+
+@pytest.mark.parametrize("name", ["conv_64_64_M8_K16_B2", "conv_6_32_M9_K23_B2", "conv_32_64_M9_K16_nomask"])
+def test_ref_order_port(name):
+    """The reference-order torch-CPU port (timed as the CPU baseline) against the golden vectors."""
+    import torch
+    from oracle import ref_order
+    g = golden(name)
+    t = lambda k: torch.from_numpy(g[k])
+    out = ref_order.conv_fwd_bwd(t("x"), t("adj"), t("gy"), t("W0"), t("b"), t("u"), t("v"), t("c"),
+                                 bool(int(g["bias_mask"])))
+    for got, key in zip(out, ("y", "gx", "gW0", "gb", "gu", "gv", "gc")):
+        ref = g[key]
+        assert np.abs(got.numpy() - ref).max() / max(1.0, np.abs(ref).max()) < 1e-5, key
