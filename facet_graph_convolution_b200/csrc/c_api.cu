@@ -1,5 +1,6 @@
 // extern "C" boundary of libfacetconv_b200.so (declared in include/facetconv_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -75,9 +76,15 @@ static int check_shape(const fgc_conv_shape* s, const char* who) {
   return FGC_OK;
 }
 
+static bool use_tc(const fgc_conv_shape* s) {
+  static const bool disabled = getenv("FGC_DISABLE_TC") != nullptr;
+  return !disabled && s->Cin % 4 == 0 && conv_fwd_tc_supported(s->Cw, s->Cout, s->M, s->K);
+}
+
 static size_t conv_fwd_workspace(const fgc_conv_shape* s) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
-  return ws_bytes(rows * 2 * s->M, 4) + ws_bytes(static_cast<size_t>(s->M) * s->Cout * s->Cw, 4) + 512;
+  return ws_bytes(rows * 2 * s->M, 4) + ws_bytes(static_cast<size_t>(s->M) * s->Cout * s->Cw, 4) +
+         ws_bytes(conv_fwd_tc_workspace(s->Cout, s->M), 1) + 512;
 }
 
 static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0,
@@ -92,10 +99,15 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
               conv_fwd_workspace(s));
   int rc = launch_assign_logits(s, x, u, v, c, uvx, st);
   if (rc) return rc;
-  rc = launch_transpose_w(W0, Wt, s->M, s->Cout, s->Cw, st);
-  if (rc) return rc;
   ConvFwdParams p{x, adj, uvx, Wt, b, y, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M,
                   bias_mask, act, alpha};
+  if (use_tc(s)) {
+    char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M));
+    FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the tensor-core path");
+    return launch_conv_fwd_tc(p, W0, wimg, st);
+  }
+  rc = launch_transpose_w(W0, Wt, s->M, s->Cout, s->Cw, st);
+  if (rc) return rc;
   return launch_conv_fwd(p, st);
 }
 

@@ -1,0 +1,437 @@
+// Tensor-core forward facet-graph convolution for the dense layers (Cw = 64 aggregation channels).
+// Replaces reference Code/model.py:427-504 for shapes where M*Cw*Cout is a dense contraction.
+//
+// One persistent CTA per SM, 13 warps, tiles of 64 facets:
+//   warps 0-7   aggregators.  8 lanes per facet (lane owns 8 channels = two float4 of the row),
+//               4 facets per warp and pass, 2 passes per tile.  Soft assignments are evaluated
+//               lane-per-(facet,slot) into shared memory, then s[m][c] = sum_k q[k][m] x_{j_k}[c]
+//               is accumulated with packed fp32x2 FMAs over coalesced 16-byte row loads.
+//               Each finished row (M*64 fp32) is scaled by a power of two to [0.5,1), split into
+//               fp16 hi + fp16 lo*2^11 (22 significant bits) and written to a 32-row staging buffer.
+//   warps 8-11  movers + epilogue.  Thread-per-row copy staging -> TMEM (tcgen05.st): the tile's
+//               A operand is A' = [s_hi ; s_lo] stacked on the 128 TMEM lanes, M*32 columns.
+//               After the MMA they read D' (tcgen05.ld) and combine
+//                   y = scale * (hi.Wh + 2^-11 (hi.Wl + lo.Wh) + 2^-22 lo.Wl) * inv_cnt + flag * b.
+//   warp 12     MMA issuer: D'[128 x 2Cout] = A'[128 x M*64] . [Wh | Wl]  with tcgen05.mma
+//               kind::f16 (A from TMEM, B = resident 128B-swizzled K-major smem image of W).
+// fp16 hi/lo planes with exact power-of-two scaling carry ~2^-22 relative precision per element,
+// i.e. fp32-class results (parity tests: max-abs <= 1e-5 vs the oracle).
+#include "conv_common.cuh"
+#include "conv_launch.cuh"
+#include "tc_common.cuh"
+
+namespace fgc {
+
+namespace {
+
+constexpr int kCw = 64;            // aggregation channels handled by this kernel
+constexpr int kTile = 64;          // facets per tile
+constexpr int kPass = 32;          // rows per staging pass
+constexpr int kAggWarps = 8;
+constexpr int kMoverWarps = 4;
+constexpr int kTcThreads = (kAggWarps + kMoverWarps + 1) * 32;  // 416
+constexpr int kQK = 16;            // neighbour slots per assignment round
+
+template <int M, int COUT>
+struct TcCfg {
+  static constexpr int KK = M * kCw;                 // contraction length
+  static constexpr int NB = 2 * COUT;                // MMA N: [Wh | Wl]
+  static constexpr int A_COLS = KK / 2;              // TMEM columns of A' (2 halves per column)
+  static constexpr int D_COL0 = (A_COLS + 31) & ~31; // first column of D'
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int MQ = (M + 3) & ~3;            // q row stride in floats
+  static constexpr int STG_PITCH = A_COLS + 4;       // words per staged row (pitch % 32 == 4)
+  static constexpr int W_BYTES = M * NB * 128;       // M chunks of [NB rows][64 halves]
+  static constexpr int EXW = 32;                     // epilogue exchange width (columns per round)
+  static_assert(D_COL0 + NB <= TMEM_COLS, "TMEM overflow");
+  static_assert(NB % 16 == 0 && NB <= 256, "invalid UMMA N");
+  static_assert(STG_PITCH % 32 == 4, "staging pitch must be 4 mod 32 words");
+  // shared memory carve-up (bytes)
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_STG_H = OFF_W + W_BYTES;
+  static constexpr int OFF_STG_L = OFF_STG_H + kPass * STG_PITCH * 4;
+  static constexpr int OFF_Q = OFF_STG_L + kPass * STG_PITCH * 4;
+  static constexpr int OFF_NBR = OFF_Q + kAggWarps * 4 * kQK * MQ * 4;
+  static constexpr int OFF_EX = OFF_NBR + kAggWarps * 4 * kQK * 4;
+  static constexpr int OFF_ROW = OFF_EX + kTile * (EXW + 1) * 4;   // rowscale[2][64], rowflag[2][64]
+  static constexpr int OFF_BAR = OFF_ROW + 2 * 2 * kTile * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+};
+
+struct TcParams {
+  const float* x;
+  const int32_t* adj;
+  const float* uvx;
+  const uint4* wimg;     // swizzled fp16 smem image of [Wh | Wl], W_BYTES
+  const float* wunscale; // 2^-aw
+  const float* b;
+  float* y;
+  int64_t rows;
+  int N, K, Cin;
+  int bias_mask, act;
+  float alpha;
+};
+
+// barrier indices
+enum { B_STG_FULL = 0, B_STG_EMPTY, B_A_READY, B_A_FREE, B_MMA_DONE, B_D_FREE, B_COUNT };
+
+template <int M, int COUT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_fwd_tc_kernel(const TcParams p) {
+  using Cfg = TcCfg<M, COUT>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint32_t* stg_h = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_STG_H);
+  uint32_t* stg_l = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_STG_L);
+  float* qs_all = reinterpret_cast<float*>(smem + Cfg::OFF_Q);
+  int* nbr_all = reinterpret_cast<int*>(smem + Cfg::OFF_NBR);
+  float* ex = reinterpret_cast<float*>(smem + Cfg::OFF_EX);
+  float* rowscale = reinterpret_cast<float*>(smem + Cfg::OFF_ROW);
+  float* rowflag = rowscale + 2 * kTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (p.rows + kTile - 1) / kTile;
+
+  // ---------------- one-time setup
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bars[B_STG_FULL], kAggWarps);
+    tc::mbar_init(&bars[B_STG_EMPTY], 2);
+    tc::mbar_init(&bars[B_A_READY], 4);
+    tc::mbar_init(&bars[B_A_FREE], 1);
+    tc::mbar_init(&bars[B_MMA_DONE], 1);
+    tc::mbar_init(&bars[B_D_FREE], kMoverWarps);
+    tc::mbar_fence_init();
+  }
+  if (warp == kAggWarps + kMoverWarps) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  {
+    // resident weight image: plain 16-byte copies (the global image is already swizzled)
+    uint4* wdst = reinterpret_cast<uint4*>(smem + Cfg::OFF_W);
+    for (int i = threadIdx.x; i < Cfg::W_BYTES / 16; i += kTcThreads) wdst[i] = __ldg(p.wimg + i);
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < kAggWarps) {
+    // =========================================================== aggregators
+    float* qs = qs_all + warp * 4 * kQK * Cfg::MQ;
+    int* nbr = nbr_all + warp * 4 * kQK;
+    const int grp = lane >> 3;       // facet within the warp's 4
+    const int gl = lane & 7;         // lane within the 8-lane group
+    uint32_t empty_parity = 1;       // producer convention: the first wait falls through
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int pass = 0; pass < 2; ++pass) {
+        const int prow = warp * 4 + grp;                       // row within the pass (0..31)
+        const int trow = pass * kPass + prow;                  // row within the tile
+        const int64_t r = tile * kTile + trow;                 // global row of this lane's facet
+        float2 acc[M][4];
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[m][i] = make_float2(0.f, 0.f);
+        int cnt = 0;
+        for (int kb = 0; kb < p.K; kb += kQK) {
+          const int nk = min(kQK, p.K - kb);
+          __syncwarp();
+          // ---- soft assignments: lane per (facet, slot) pair
+          for (int pr = lane; pr < 4 * nk; pr += 32) {
+            const int f = pr / nk, k = pr % nk;
+            const int64_t rf = tile * kTile + pass * kPass + warp * 4 + f;
+            int row = -1;
+            float a[M];
+            if (rf < p.rows) {
+              const int id = __ldg(p.adj + rf * p.K + kb + k);
+              const int64_t base = (rf / p.N) * p.N;
+              const bool valid = id > 0 && id <= p.N;
+              row = valid ? static_cast<int>(base + id - 1) : (id != 0 ? -2 : -1);
+              const float* ux = p.uvx + rf * (2 * M);
+              const float* vx = p.uvx + (valid ? static_cast<int64_t>(row) : rf) * (2 * M) + M;
+              float mx = -INFINITY;
+#pragma unroll
+              for (int m = 0; m < M; ++m) {
+                a[m] = __ldg(ux + m) + (valid ? __ldg(vx + m) : 0.f);
+                mx = fmaxf(mx, a[m]);
+              }
+              float sum = 0.f;
+#pragma unroll
+              for (int m = 0; m < M; ++m) {
+                a[m] = expf(a[m] - mx);
+                sum += a[m];
+              }
+              const float rs = 1.f / sum;
+#pragma unroll
+              for (int m = 0; m < M; ++m) a[m] *= rs;
+            } else {
+#pragma unroll
+              for (int m = 0; m < M; ++m) a[m] = 0.f;
+            }
+            float* qd = qs + (f * kQK + k) * Cfg::MQ;
+#pragma unroll
+            for (int m = 0; m < Cfg::MQ; ++m) qd[m] = (m < M) ? a[m < M ? m : 0] : 0.f;
+            nbr[f * kQK + k] = row;
+          }
+          __syncwarp();
+          // ---- q-weighted aggregation, 8 lanes per facet, packed FMAs
+#pragma unroll 4
+          for (int k = 0; k < nk; ++k) {
+            const int j = nbr[grp * kQK + k];
+            cnt += (j != -1);
+            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+            if (j >= 0) {
+              const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(j) * p.Cin);
+              x0 = __ldg(xr + gl);
+              x1 = __ldg(xr + 8 + gl);
+            }
+            const float2 xp[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w),
+                                  make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
+            const float* qk = qs + (grp * kQK + k) * Cfg::MQ;
+            float q[Cfg::MQ];
+#pragma unroll
+            for (int m4 = 0; m4 < Cfg::MQ; m4 += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(qk + m4);
+              q[m4] = t.x, q[m4 + 1] = t.y, q[m4 + 2] = t.z, q[m4 + 3] = t.w;
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+              const float2 qq = make_float2(q[m], q[m]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) tc::ffma2(acc[m][i], qq, xp[i]);
+            }
+          }
+        }
+        // ---- row scale: largest magnitude of the facet's M*64 values -> [0.5, 1)
+        float mx = 0.f;
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(acc[m][i].x), fabsf(acc[m][i].y)));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+        int E = (__float_as_int(mx) >> 23) & 0xFF;
+        E = min(max(E, 16), 240);                                  // keep both scales normal
+        const float sc = __int_as_float((253 - E) << 23);          // 2^(126-E)
+        const float unsc = __int_as_float((E + 1) << 23);          // 2^(E-126)
+        // ---- wait until the movers drained the previous pass, then stage hi / lo planes
+        tc::mbar_wait(&bars[B_STG_EMPTY], empty_parity);
+        empty_parity ^= 1;
+        uint32_t* rh = stg_h + prow * Cfg::STG_PITCH;
+        uint32_t* rl = stg_l + prow * Cfg::STG_PITCH;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float v0 = acc[m][i].x * sc, v1 = acc[m][i].y * sc;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const __half l0 = __float2half_rn((v0 - __half2float(h0)) * 2048.f);
+            const __half l1 = __float2half_rn((v1 - __half2float(h1)) * 2048.f);
+            h[i] = tc::pack_half2(h0, h1);
+            l[i] = tc::pack_half2(l0, l1);
+          }
+          // channels 4gl..4gl+3 -> words m*32 + 2gl, +1 ; channels 32+4gl.. -> words m*32 + 16 + 2gl, +1
+          *reinterpret_cast<uint2*>(rh + m * 32 + 2 * gl) = make_uint2(h[0], h[1]);
+          *reinterpret_cast<uint2*>(rh + m * 32 + 16 + 2 * gl) = make_uint2(h[2], h[3]);
+          *reinterpret_cast<uint2*>(rl + m * 32 + 2 * gl) = make_uint2(l[0], l[1]);
+          *reinterpret_cast<uint2*>(rl + m * 32 + 16 + 2 * gl) = make_uint2(l[2], l[3]);
+        }
+        if (gl == 0) {
+          const float inv = cnt ? 1.f / static_cast<float>(cnt) : 0.f;
+          rowscale[(it & 1) * kTile + trow] = inv * unsc;
+          rowflag[(it & 1) * kTile + trow] = (cnt > 0 || !p.bias_mask) ? 1.f : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[B_STG_FULL]);
+      }
+    }
+  } else if (warp < kAggWarps + kMoverWarps) {
+    // =========================================================== movers + epilogue
+    const int quad = warp - kAggWarps;                 // == warp % 4: TMEM lane quadrant
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    uint32_t full_parity = 0, afree_parity = 1, done_parity = 0;
+    const float wun = __ldg(p.wunscale);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      // A' of the previous tile must have been consumed by the MMA
+      tc::mbar_wait(&bars[B_A_FREE], afree_parity);
+      afree_parity ^= 1;
+      tc::tc_fence_after_sync();
+      for (int pass = 0; pass < 2; ++pass) {
+        tc::mbar_wait(&bars[B_STG_FULL], full_parity);
+        full_parity ^= 1;
+        const bool is_hi = (quad == pass), is_lo = (quad == 2 + pass);
+        if (is_hi || is_lo) {
+          const uint32_t* src = (is_hi ? stg_h : stg_l) + lane * Cfg::STG_PITCH;
+#pragma unroll 1
+          for (int c0 = 0; c0 < Cfg::A_COLS; c0 += 32) {
+            uint32_t r[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 t = *reinterpret_cast<const uint4*>(src + c0 + 4 * i);
+              r[4 * i] = t.x, r[4 * i + 1] = t.y, r[4 * i + 2] = t.z, r[4 * i + 3] = t.w;
+            }
+            tc::tmem_st32(tmem + lane_base + c0, r);
+          }
+          tc::tc_wait_st();
+          tc::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            tc::mbar_arrive(&bars[B_STG_EMPTY]);
+            tc::mbar_arrive(&bars[B_A_READY]);
+          }
+        }
+      }
+      // ---------------- epilogue of this tile
+      tc::mbar_wait(&bars[B_MMA_DONE], done_parity);
+      done_parity ^= 1;
+      tc::tc_fence_after_sync();
+      const int frow = (quad & 1) * 32 + lane;          // facet row within the tile
+      const int64_t r = tile * kTile + frow;
+      const float* rs = rowscale + (it & 1) * kTile;
+      const float* rf = rowflag + (it & 1) * kTile;
+      for (int c0 = 0; c0 < COUT; c0 += Cfg::EXW) {
+        uint32_t d0[32], d1[32];
+        tc::tmem_ld32(tmem + lane_base + Cfg::D_COL0 + c0, d0);          // (.)Wh columns
+        tc::tmem_ld32(tmem + lane_base + Cfg::D_COL0 + COUT + c0, d1);   // (.)Wl columns
+        tc::tc_wait_ld();
+        if (quad >= 2) {   // lo rows: 2^-11 lo.Wh + 2^-22 lo.Wl
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            ex[frow * (Cfg::EXW + 1) + i] =
+                __uint_as_float(d0[i]) * (1.f / 2048.f) + __uint_as_float(d1[i]) * (1.f / 4194304.f);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (quad < 2 && r < p.rows) {
+          const float sc = rs[frow] * wun, fl = rf[frow];
+          float* yr = p.y + r * COUT + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float v = __uint_as_float(d0[i + j]) + __uint_as_float(d1[i + j]) * (1.f / 2048.f) +
+                              ex[frow * (Cfg::EXW + 1) + i + j];
+              float yv = fmaf(sc, v, fl * __ldg(p.b + c0 + i + j));
+              if (p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
+              o[j] = yv;
+            }
+            *reinterpret_cast<float4*>(yr + i) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[B_D_FREE]);
+    }
+  } else {
+    // =========================================================== MMA issuer
+    uint32_t ready_parity = 0, dfree_parity = 1;
+    const uint32_t idesc = tc::idesc_f16(128, Cfg::NB);
+    const uint32_t wbase = tc::smem_u32(smem + Cfg::OFF_W);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      tc::mbar_wait(&bars[B_A_READY], ready_parity);
+      ready_parity ^= 1;
+      tc::mbar_wait(&bars[B_D_FREE], dfree_parity);
+      dfree_parity ^= 1;
+      tc::tc_fence_after_sync();
+      if (lane == 0) {
+#pragma unroll 1
+        for (int kc = 0; kc < M; ++kc) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bdesc = tc::smem_desc_k_sw128(wbase + kc * (Cfg::NB * 128) + ks * 32);
+            tc::mma_f16_ts(tmem + Cfg::D_COL0, tmem + kc * 32 + ks * 8, bdesc, idesc, (kc | ks) ? 1u : 0u);
+          }
+        }
+        tc::tc_commit(&bars[B_A_FREE]);
+        tc::tc_commit(&bars[B_MMA_DONE]);
+      }
+      __syncwarp();
+    }
+  }
+  // ---------------- teardown
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kAggWarps + kMoverWarps) tc::tmem_dealloc(tmem, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ weight image preparation
+// wimg: M chunks of [NB rows][64 halves] (128 B per row, 16-byte units XOR-swizzled by row & 7):
+//   row n < COUT : fp16(W0[m][n][c] * 2^aw)                      (hi)
+//   row n >= COUT: fp16((W*2^aw - hi) * 2^11)                    (lo)
+// One block: max|W| -> power-of-two scale so that |W*2^aw| < 1.
+__global__ void __launch_bounds__(1024)
+prep_w_image_kernel(const float* __restrict__ W0, uint16_t* __restrict__ wimg, float* __restrict__ wunscale,
+                    int M, int COUT) {
+  __shared__ float red[32];
+  const int total = M * COUT * kCw;
+  float mx = 0.f;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) mx = fmaxf(mx, fabsf(W0[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  int E = (__float_as_int(mx) >> 23) & 0xFF;
+  E = min(max(E, 16), 240);
+  const float sc = __int_as_float((253 - E) << 23);
+  if (threadIdx.x == 0) wunscale[0] = __int_as_float((E + 1) << 23);
+  const int NB = 2 * COUT;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c = e % kCw;
+    const int o = (e / kCw) % COUT;
+    const int m = e / (kCw * COUT);
+    const float v = W0[e] * sc;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
+    const int unit = c >> 3, within = c & 7;
+    const size_t chunk = static_cast<size_t>(m) * NB * 64;  // halves
+    const int nh = o, nl = COUT + o;
+    wimg[chunk + nh * 64 + ((unit ^ (nh & 7)) << 3) + within] = __half_as_ushort(h);
+    wimg[chunk + nl * 64 + ((unit ^ (nl & 7)) << 3) + within] = __half_as_ushort(l);
+  }
+}
+
+template <int M, int COUT>
+int launch_tc(const ConvFwdParams& p, void* wimg, float* wunscale, const float* W0, cudaStream_t st) {
+  using Cfg = TcCfg<M, COUT>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+  prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg), wunscale, M, COUT);
+  FGC_LAUNCHED("prep_w_image_kernel");
+  TcParams tp{p.x, p.adj, p.uvx, static_cast<const uint4*>(wimg), wunscale, p.b, p.y, p.rows,
+              p.N, p.K, p.Cin, p.bias_mask, p.act, p.alpha};
+  FGC_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel<M, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg::SMEM_BYTES));
+  const int64_t ntiles = (p.rows + kTile - 1) / kTile;
+  int64_t grid = num_sms();
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  conv_fwd_tc_kernel<M, COUT><<<static_cast<unsigned>(grid), kTcThreads, Cfg::SMEM_BYTES, st>>>(tp);
+  FGC_LAUNCHED("conv_fwd_tc_kernel");
+  return FGC_OK;
+}
+
+}  // namespace
+
+bool conv_fwd_tc_supported(int Cw, int Cout, int M, int K) {
+  return Cw == kCw && Cout == 64 && M == 8 && K <= 32;
+}
+
+size_t conv_fwd_tc_workspace(int Cout, int M) { return static_cast<size_t>(M) * 2 * Cout * 128 + 512; }
+
+// wimg_ws: conv_fwd_tc_workspace bytes (16-byte aligned); its tail holds the scalar un-scale
+int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st) {
+  const size_t img = static_cast<size_t>(p.M) * 2 * p.Cout * 128;
+  float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
+  if (p.M == 8 && p.Cout == 64) return launch_tc<8, 64>(p, wimg_ws, wunscale, W0, st);
+  set_error("conv_fwd_tc: unsupported shape");
+  return FGC_ERR_UNSUPPORTED;
+}
+
+}  // namespace fgc

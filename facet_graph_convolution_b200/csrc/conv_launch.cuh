@@ -26,6 +26,10 @@ int launch_assignments(const int32_t* adj, const float* uvx, float* q, int64_t r
                        int M, cudaStream_t st);
 int launch_gather_rows(const float* x, const int32_t* adj, float* out, int64_t rows, int N, int K,
                        int C, cudaStream_t st);
+// tensor-core (tcgen05) forward for the dense shapes
+bool conv_fwd_tc_supported(int Cw, int Cout, int M, int K);
+size_t conv_fwd_tc_workspace(int Cout, int M);
+int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st);
 size_t conv_bwd_workspace(const fgc_conv_shape* s);
 int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
