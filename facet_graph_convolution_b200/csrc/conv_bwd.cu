@@ -16,6 +16,8 @@
 //   logits_bwd_kernel  d_uvx -> gu, gv, gc partials and the logit-window part of gx
 //   reduce_partials_kernel  fixed-order sum of the per-CTA partials
 // Every summation order is fixed by the launch geometry => bit-reproducible run to run.
+#include <stdlib.h>
+
 #include <cub/device/device_scan.cuh>
 
 #include "conv_common.cuh"
@@ -753,6 +755,7 @@ size_t conv_bwd_workspace(const fgc_conv_shape* s) {
   b += ws_bytes(static_cast<size_t>(pl.chunks) * nW, 4);        // partW
   b += ws_bytes(static_cast<size_t>(pl.chunks) * s->Cout, 4);   // partB
   b += ws_bytes(static_cast<size_t>(pl.lchunks) * (2 * s->M * s->Ca + s->M), 4);  // logits partials
+  b += ws_bytes(conv_fwd_tc_workspace(s->Cw > s->Cout ? s->Cw : s->Cout, s->M), 1);   // TC weight image
   return b + 1024;
 }
 
@@ -827,7 +830,9 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   float* partW = ws.take<float>(static_cast<size_t>(pl.chunks) * nW);
   float* partB = ws.take<float>(static_cast<size_t>(pl.chunks) * s->Cout);
   float* partL = ws.take<float>(static_cast<size_t>(pl.lchunks) * nL);
+  char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cw > s->Cout ? s->Cw : s->Cout, s->M));
   FGC_REQUIRE(ws.ok(), "conv_bwd: workspace too small (%zu bytes given)", workspace_bytes);
+  static const bool tc_disabled = getenv("FGC_DISABLE_TC") != nullptr;
 
   int rc = launch_assign_logits(s, x, u, v, c, uvx, st);
   if (rc) return rc;
@@ -844,7 +849,12 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
 #undef FGC_CALL
     if (rc) return rc;
   }
-  {
+  if (!tc_disabled && s->Cout % 4 == 0 && bwd_tgt_tc_supported(s->Cw, s->Cout, s->M)) {
+    if (s->Cin > s->Cw) FGC_CUDA(cudaMemsetAsync(gx, 0, rows * s->Cin * sizeof(float), st));
+    rc = launch_bwd_tgt_tc(gy, uvx, W0, da_edge, inv, rev_ptr, rev_edge, gx, d_uvx, rows, s->N, s->K,
+                           s->Cin, s->Cw, s->Cout, s->M, wimg, st);
+    if (rc) return rc;
+  } else {
     BwdTgtParams p{gy, uvx, W0, da_edge, inv, rev_ptr, rev_edge, gx, d_uvx, rows,
                    s->N, s->K, s->Cin, s->Cw, s->Cout, s->M};
 #define FGC_CALL(MPV, NCV) rc = run_tgt<MPV, NCV>(p, st)

@@ -58,24 +58,37 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
 };
 
+// MODE_FWD: rows gathered through the adjacency (source-centric forward).
+// MODE_TGT: rows gathered through the reversed adjacency (target-centric backward: t = sum q*gz,
+//           gx = t . W^T), see conv_bwd.cu.
+constexpr int MODE_FWD = 0;
+constexpr int MODE_TGT = 1;
+
 struct TcParams {
-  const float* x;
-  const int32_t* adj;
+  const float* x;        // gathered rows: x (FWD) or gy (TGT); row stride `Cin`
+  const int32_t* adj;    // FWD: adj[rows][K]
   const float* uvx;
   const uint4* wimg;     // swizzled fp16 smem image of [Wh | Wl], W_BYTES
   const float* wunscale; // 2^-aw
   const float* b;
-  float* y;
+  float* y;              // output rows, row stride `ldy`
   int64_t rows;
   int N, K, Cin;
   int bias_mask, act;
   float alpha;
+  int ldy;
+  // TGT only
+  const int32_t* rev_ptr;
+  const int32_t* rev_edge;
+  const float* inv;      // inv_cnt of every source row
+  const float* da_edge;  // [rows*K][M]
+  float* d_uvx;          // [rows][2M], columns M..2M-1 written here
 };
 
 // barrier indices
 enum { B_STG_FULL = 0, B_STG_EMPTY, B_A_READY, B_A_FREE, B_MMA_DONE, B_D_FREE, B_COUNT };
 
-template <int M, int COUT>
+template <int M, int COUT, int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_fwd_tc_kernel(const TcParams p) {
   using Cfg = TcCfg<M, COUT>;
@@ -134,44 +147,86 @@ conv_fwd_tc_kernel(const TcParams p) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[m][i] = make_float2(0.f, 0.f);
         int cnt = 0;
-        for (int kb = 0; kb < p.K; kb += kQK) {
-          const int nk = min(kQK, p.K - kb);
+        // neighbour list of this lane's facet: the K adjacency slots (FWD) or the in-edge segment of
+        // the reversed adjacency (TGT); processed in rounds of kQK entries, warp-uniform trip count
+        int lst0 = 0, lst1 = 0;
+        float dv[2][M];           // TGT: per-lane partial sums of da_edge -> d_uvx[:, M:2M]
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int m = 0; m < M; ++m) dv[h][m] = 0.f;
+        if constexpr (MODE == MODE_FWD) {
+          lst1 = p.K;
+        } else {
+          if (r < p.rows) {
+            lst0 = __ldg(p.rev_ptr + r);
+            lst1 = __ldg(p.rev_ptr + r + 1);
+          }
+        }
+        int nround = lst1 - lst0;
+        nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, 8));
+        nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, 16));
+        for (int kb = 0; kb < nround; kb += kQK) {
+          const int nk = min(kQK, nround - kb);
           __syncwarp();
-          // ---- soft assignments: lane per (facet, slot) pair
-          for (int pr = lane; pr < 4 * nk; pr += 32) {
-            const int f = pr / nk, k = pr % nk;
+          // ---- soft assignments: lane per (facet, slot) pair; pair = lane + 32h, facet = pair / 16
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int f = (lane >> 4) + 2 * h, k = lane & 15;
             const int64_t rf = tile * kTile + pass * kPass + warp * 4 + f;
+            // list bounds of facet f live in the lane group that owns it
+            const int f0 = __shfl_sync(0xffffffffu, lst0, f * 8);
+            const int f1 = __shfl_sync(0xffffffffu, lst1, f * 8);
             int row = -1;
             float a[M];
-            if (rf < p.rows) {
-              const int id = __ldg(p.adj + rf * p.K + kb + k);
-              const int64_t base = (rf / p.N) * p.N;
-              const bool valid = id > 0 && id <= p.N;
-              row = valid ? static_cast<int>(base + id - 1) : (id != 0 ? -2 : -1);
-              const float* ux = p.uvx + rf * (2 * M);
-              const float* vx = p.uvx + (valid ? static_cast<int64_t>(row) : rf) * (2 * M) + M;
-              float mx = -INFINITY;
+            bool have = false;
+            if (k < nk && rf < p.rows && f0 + kb + k < f1) {
+              have = true;
+              const float* ux;
+              const float* vx;
+              bool vvalid = true;
+              if constexpr (MODE == MODE_FWD) {
+                const int id = __ldg(p.adj + rf * p.K + kb + k);
+                const int64_t base = (rf / p.N) * p.N;
+                vvalid = id > 0 && id <= p.N;
+                row = vvalid ? static_cast<int>(base + id - 1) : (id != 0 ? -2 : -1);
+                ux = p.uvx + rf * (2 * M);
+                vx = p.uvx + (vvalid ? static_cast<int64_t>(row) : rf) * (2 * M) + M;
+              } else {
+                const int e = __ldg(p.rev_edge + f0 + kb + k);
+                row = e / p.K;                                  // source facet of the in-edge
+                ux = p.uvx + static_cast<int64_t>(row) * (2 * M);
+                vx = p.uvx + rf * (2 * M) + M;
+                const float* de = p.da_edge + static_cast<int64_t>(e) * M;
 #pragma unroll
-              for (int m = 0; m < M; ++m) {
-                a[m] = __ldg(ux + m) + (valid ? __ldg(vx + m) : 0.f);
-                mx = fmaxf(mx, a[m]);
+                for (int m = 0; m < M; ++m) dv[h][m] += __ldg(de + m);
               }
+#pragma unroll
+              for (int m = 0; m < M; ++m) a[m] = __ldg(ux + m) + (vvalid ? __ldg(vx + m) : 0.f);
+              float mx = a[0];
+#pragma unroll
+              for (int m = 1; m < M; ++m) mx = fmaxf(mx, a[m]);
               float sum = 0.f;
 #pragma unroll
               for (int m = 0; m < M; ++m) {
-                a[m] = expf(a[m] - mx);
+                a[m] = __expf(a[m] - mx);
                 sum += a[m];
               }
-              const float rs = 1.f / sum;
+              float rs = 1.f / sum;
+              if constexpr (MODE == MODE_TGT) rs *= __ldg(p.inv + row);   // gy rows weighted as gz
 #pragma unroll
               for (int m = 0; m < M; ++m) a[m] *= rs;
-            } else {
+            }
+            if (!have) {
 #pragma unroll
               for (int m = 0; m < M; ++m) a[m] = 0.f;
             }
             float* qd = qs + (f * kQK + k) * Cfg::MQ;
 #pragma unroll
-            for (int m = 0; m < Cfg::MQ; ++m) qd[m] = (m < M) ? a[m < M ? m : 0] : 0.f;
+            for (int m4 = 0; m4 < Cfg::MQ; m4 += 4)
+              *reinterpret_cast<float4*>(qd + m4) =
+                  make_float4(m4 < M ? a[m4 < M ? m4 : 0] : 0.f, m4 + 1 < M ? a[m4 + 1 < M ? m4 + 1 : 0] : 0.f,
+                              m4 + 2 < M ? a[m4 + 2 < M ? m4 + 2 : 0] : 0.f, m4 + 3 < M ? a[m4 + 3 < M ? m4 + 3 : 0] : 0.f);
             nbr[f * kQK + k] = row;
           }
           __syncwarp();
@@ -200,6 +255,22 @@ conv_fwd_tc_kernel(const TcParams p) {
               const float2 qq = make_float2(q[m], q[m]);
 #pragma unroll
               for (int i = 0; i < 4; ++i) tc::ffma2(acc[m][i], qq, xp[i]);
+            }
+          }
+        }
+        if constexpr (MODE == MODE_TGT) {
+          // d_uvx[t, M + m] = sum of da_edge over the in-edges of t: reduce the 16 lanes of a facet
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int64_t rf = tile * kTile + pass * kPass + warp * 4 + (lane >> 4) + 2 * h;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+              float t = dv[h][m];
+              t += __shfl_xor_sync(0xffffffffu, t, 1);
+              t += __shfl_xor_sync(0xffffffffu, t, 2);
+              t += __shfl_xor_sync(0xffffffffu, t, 4);
+              t += __shfl_xor_sync(0xffffffffu, t, 8);
+              if ((lane & 15) == 0 && rf < p.rows) p.d_uvx[rf * (2 * M) + M + m] = t;
             }
           }
         }
@@ -240,7 +311,7 @@ conv_fwd_tc_kernel(const TcParams p) {
           *reinterpret_cast<uint2*>(rl + m * 32 + 16 + 2 * gl) = make_uint2(l[2], l[3]);
         }
         if (gl == 0) {
-          const float inv = cnt ? 1.f / static_cast<float>(cnt) : 0.f;
+          const float inv = (MODE == MODE_TGT) ? 1.f : (cnt ? 1.f / static_cast<float>(cnt) : 0.f);
           rowscale[(it & 1) * kTile + trow] = inv * unsc;
           rowflag[(it & 1) * kTile + trow] = (cnt > 0 || !p.bias_mask) ? 1.f : 0.f;
         }
@@ -307,7 +378,7 @@ conv_fwd_tc_kernel(const TcParams p) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (quad < 2 && r < p.rows) {
           const float sc = rs[frow] * wun, fl = rf[frow];
-          float* yr = p.y + r * COUT + c0;
+          float* yr = p.y + r * p.ldy + c0;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float o[4];
@@ -315,8 +386,13 @@ conv_fwd_tc_kernel(const TcParams p) {
             for (int j = 0; j < 4; ++j) {
               const float v = __uint_as_float(d0[i + j]) + __uint_as_float(d1[i + j]) * (1.f / 2048.f) +
                               ex[frow * (Cfg::EXW + 1) + i + j];
-              float yv = fmaf(sc, v, fl * __ldg(p.b + c0 + i + j));
-              if (p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
+              float yv;
+              if constexpr (MODE == MODE_FWD) {
+                yv = fmaf(sc, v, fl * __ldg(p.b + c0 + i + j));
+                if (p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
+              } else {
+                yv = sc * v;
+              }
               o[j] = yv;
             }
             *reinterpret_cast<float4*>(yr + i) = make_float4(o[0], o[1], o[2], o[3]);
@@ -367,7 +443,7 @@ conv_fwd_tc_kernel(const TcParams p) {
 // One block: max|W| -> power-of-two scale so that |W*2^aw| < 1.
 __global__ void __launch_bounds__(1024)
 prep_w_image_kernel(const float* __restrict__ W0, uint16_t* __restrict__ wimg, float* __restrict__ wunscale,
-                    int M, int COUT) {
+                    int M, int COUT, int transposed) {
   __shared__ float red[32];
   const int total = M * COUT * kCw;
   float mx = 0.f;
@@ -384,10 +460,11 @@ prep_w_image_kernel(const float* __restrict__ W0, uint16_t* __restrict__ wimg, f
   if (threadIdx.x == 0) wunscale[0] = __int_as_float((E + 1) << 23);
   const int NB = 2 * COUT;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    // image element (m, n = o, k = c); transposed: n = c of W0, k = o of W0 (B for gx = t . W^T)
     const int c = e % kCw;
     const int o = (e / kCw) % COUT;
     const int m = e / (kCw * COUT);
-    const float v = W0[e] * sc;
+    const float v = (transposed ? W0[(static_cast<size_t>(m) * kCw + c) * COUT + o] : W0[e]) * sc;
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
     const int unit = c >> 3, within = c & 7;
@@ -398,22 +475,24 @@ prep_w_image_kernel(const float* __restrict__ W0, uint16_t* __restrict__ wimg, f
   }
 }
 
-template <int M, int COUT>
-int launch_tc(const ConvFwdParams& p, void* wimg, float* wunscale, const float* W0, cudaStream_t st) {
+template <int M, int COUT, int MODE>
+int launch_tc(const TcParams& tp_in, void* wimg, float* wunscale, const float* W0, cudaStream_t st) {
   using Cfg = TcCfg<M, COUT>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
-  prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg), wunscale, M, COUT);
+  prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg), wunscale, M, COUT,
+                                           MODE == MODE_TGT ? 1 : 0);
   FGC_LAUNCHED("prep_w_image_kernel");
-  TcParams tp{p.x, p.adj, p.uvx, static_cast<const uint4*>(wimg), wunscale, p.b, p.y, p.rows,
-              p.N, p.K, p.Cin, p.bias_mask, p.act, p.alpha};
-  FGC_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel<M, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg::SMEM_BYTES));
-  const int64_t ntiles = (p.rows + kTile - 1) / kTile;
+  TcParams tp = tp_in;
+  tp.wimg = static_cast<const uint4*>(wimg);
+  tp.wunscale = wunscale;
+  auto kern = conv_fwd_tc_kernel<M, COUT, MODE>;
+  FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int64_t ntiles = (tp.rows + kTile - 1) / kTile;
   int64_t grid = num_sms();
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
-  conv_fwd_tc_kernel<M, COUT><<<static_cast<unsigned>(grid), kTcThreads, Cfg::SMEM_BYTES, st>>>(tp);
-  FGC_LAUNCHED("conv_fwd_tc_kernel");
+  kern<<<static_cast<unsigned>(grid), kTcThreads, Cfg::SMEM_BYTES, st>>>(tp);
+  FGC_LAUNCHED(MODE == MODE_TGT ? "bwd_tgt_tc_kernel" : "conv_fwd_tc_kernel");
   return FGC_OK;
 }
 
@@ -429,8 +508,31 @@ size_t conv_fwd_tc_workspace(int Cout, int M) { return static_cast<size_t>(M) * 
 int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st) {
   const size_t img = static_cast<size_t>(p.M) * 2 * p.Cout * 128;
   float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
-  if (p.M == 8 && p.Cout == 64) return launch_tc<8, 64>(p, wimg_ws, wunscale, W0, st);
+  TcParams tp{};
+  tp.x = p.x, tp.adj = p.adj, tp.uvx = p.uvx, tp.b = p.b, tp.y = p.y, tp.rows = p.rows;
+  tp.N = p.N, tp.K = p.K, tp.Cin = p.Cin, tp.bias_mask = p.bias_mask, tp.act = p.act, tp.alpha = p.alpha;
+  tp.ldy = p.Cout;
+  if (p.M == 8 && p.Cout == 64) return launch_tc<8, 64, MODE_FWD>(tp, wimg_ws, wunscale, W0, st);
   set_error("conv_fwd_tc: unsupported shape");
+  return FGC_ERR_UNSUPPORTED;
+}
+
+// Target-centric backward pass on the same skeleton: gx[:, 0:Cw] = sum_m t[.,m,:] W0[m] with
+// t[j,m,:] = sum over in-edges (n->j) of q[n->j,m] * inv_cnt[n] * gy[n,:], plus d_uvx[:, M:2M].
+bool bwd_tgt_tc_supported(int Cw, int Cout, int M) { return Cw == 64 && Cout == kCw && M == 8; }
+
+int launch_bwd_tgt_tc(const float* gy, const float* uvx, const float* W0, const float* da_edge,
+                      const float* inv, const int32_t* rev_ptr, const int32_t* rev_edge, float* gx,
+                      float* d_uvx, int64_t rows, int N, int K, int Cin, int Cw, int Cout, int M,
+                      void* wimg_ws, cudaStream_t st) {
+  const size_t img = static_cast<size_t>(M) * 2 * Cw * 128;
+  float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
+  TcParams tp{};
+  tp.x = gy, tp.uvx = uvx, tp.y = gx, tp.rows = rows, tp.N = N, tp.K = K, tp.Cin = Cout;  // gy row stride
+  tp.ldy = Cin;
+  tp.rev_ptr = rev_ptr, tp.rev_edge = rev_edge, tp.inv = inv, tp.da_edge = da_edge, tp.d_uvx = d_uvx;
+  if (M == 8 && Cw == 64) return launch_tc<8, 64, MODE_TGT>(tp, wimg_ws, wunscale, W0, st);
+  set_error("bwd_tgt_tc: unsupported shape");
   return FGC_ERR_UNSUPPORTED;
 }
 

@@ -30,6 +30,11 @@ int launch_gather_rows(const float* x, const int32_t* adj, float* out, int64_t r
 bool conv_fwd_tc_supported(int Cw, int Cout, int M, int K);
 size_t conv_fwd_tc_workspace(int Cout, int M);
 int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st);
+bool bwd_tgt_tc_supported(int Cw, int Cout, int M);
+int launch_bwd_tgt_tc(const float* gy, const float* uvx, const float* W0, const float* da_edge,
+                      const float* inv, const int32_t* rev_ptr, const int32_t* rev_edge, float* gx,
+                      float* d_uvx, int64_t rows, int N, int K, int Cin, int Cw, int Cout, int M,
+                      void* wimg_ws, cudaStream_t st);
 size_t conv_bwd_workspace(const fgc_conv_shape* s);
 int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
