@@ -18,6 +18,8 @@
 // Every summation order is fixed by the launch geometry => bit-reproducible run to run.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include <cub/device/device_scan.cuh>
 
 #include "conv_common.cuh"
@@ -752,8 +754,10 @@ size_t conv_bwd_workspace(const fgc_conv_shape* s) {
   b += ws_bytes(nW, 4);                            // Wd
   b += ws_bytes(rows * s->K * s->M, 4);            // da_edge
   b += ws_bytes(rows, 4);                          // inv
-  b += ws_bytes(static_cast<size_t>(pl.chunks) * nW, 4);        // partW
-  b += ws_bytes(static_cast<size_t>(pl.chunks) * s->Cout, 4);   // partB
+  const size_t wparts = std::max<size_t>(pl.chunks, bwd_w_tc_grid(rows));
+  b += ws_bytes(wparts * nW, 4);        // partW
+  b += ws_bytes(wparts * s->Cout, 4);   // partB
+  b += ws_bytes(4, 4);                  // absmax scratch
   b += ws_bytes(static_cast<size_t>(pl.lchunks) * (2 * s->M * s->Ca + s->M), 4);  // logits partials
   b += ws_bytes(conv_fwd_tc_workspace(s->Cw > s->Cout ? s->Cw : s->Cout, s->M), 1);   // TC weight image
   return b + 1024;
@@ -827,8 +831,10 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   float* Wd = ws.take<float>(nW);
   float* da_edge = ws.take<float>(rows * s->K * s->M);
   float* inv = ws.take<float>(rows);
-  float* partW = ws.take<float>(static_cast<size_t>(pl.chunks) * nW);
-  float* partB = ws.take<float>(static_cast<size_t>(pl.chunks) * s->Cout);
+  const size_t wparts = std::max<size_t>(pl.chunks, bwd_w_tc_grid(rows));
+  float* partW = ws.take<float>(wparts * nW);
+  float* partB = ws.take<float>(wparts * s->Cout);
+  unsigned* maxbits = ws.take<unsigned>(4);
   float* partL = ws.take<float>(static_cast<size_t>(pl.lchunks) * nL);
   char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cw > s->Cout ? s->Cw : s->Cout, s->M));
   FGC_REQUIRE(ws.ok(), "conv_bwd: workspace too small (%zu bytes given)", workspace_bytes);
@@ -862,7 +868,12 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
 #undef FGC_CALL
     if (rc) return rc;
   }
-  {
+  int wchunks = pl.chunks;
+  if (!tc_disabled && bwd_w_tc_supported(s->Cw, s->Cout, s->M, s->Cin)) {
+    rc = launch_bwd_w_tc(gy, x, adj, uvx, partW, partB, maxbits, rows, s->N, s->K, s->Cin, s->M, bias_mask, st);
+    if (rc) return rc;
+    wchunks = bwd_w_tc_grid(rows);
+  } else {
     BwdWParams p{gy, x, adj, uvx, partW, partB, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M,
                  bias_mask, pl.os, pl.nslices, pl.tiles_per_chunk};
 #define FGC_CALL(MPV, NCV) rc = run_w<MPV, NCV>(p, pl.chunks, st)
@@ -877,9 +888,9 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
     logits_bwd_kernel<<<pl.lchunks, kThreads, smem, st>>>(p);
     FGC_LAUNCHED("logits_bwd_kernel");
   }
-  rc = launch_reduce_partials(partW, gW0, nW, pl.chunks, nW, st);
+  rc = launch_reduce_partials(partW, gW0, nW, wchunks, nW, st);
   if (rc) return rc;
-  rc = launch_reduce_partials(partB, gb, s->Cout, pl.chunks, s->Cout, st);
+  rc = launch_reduce_partials(partB, gb, s->Cout, wchunks, s->Cout, st);
   if (rc) return rc;
   const int nUV = s->M * s->Ca;
   rc = launch_reduce_partials(partL, gu, nUV, pl.lchunks, nL, st);

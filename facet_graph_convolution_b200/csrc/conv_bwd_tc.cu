@@ -1,0 +1,301 @@
+// Tensor-core weight-gradient pass of the facet-graph convolution backward (dense 64-channel
+// layers):  gW0[m][o][c] = sum_n gz[n][o] * s[n][m][c],   gb[o] = sum_n flag[n] * gy[n][o]
+// with s recomputed by the shared aggregation stage (tc_agg.cuh).
+//
+// Persistent CTA, 13 warps, passes of 32 facets, two shared-memory stages:
+//   warps 0-7  aggregate s for 4 facets each, scale by a global power of two, split into fp16
+//              hi / lo*2^11 planes and write them as the UMMA A operand  A = s^T  (M = (m,c), K = facet)
+//              in the canonical MN-major 128B-swizzled layout; gz goes to the B operand (N = o).
+//   warp 12    issues tcgen05.mma kind::f16 (SS mode, both operands MN-major):
+//                 D_hh[(m,c)][o] += s_hi^T gz_hi ;  D_x += s_hi^T gz_lo + s_lo^T gz_hi
+//              the 4 x (64 + 64) accumulator columns fill the whole TMEM and stay resident for
+//              the lifetime of the CTA -- no shared-memory accumulators, no atomics.
+//   warps 8-11 read the accumulators once at the end and write this CTA's partial; a fixed-order
+//              reduction over CTAs (reduce_partials_kernel) finishes gW0 / gb deterministically.
+#include "conv_common.cuh"
+#include "conv_launch.cuh"
+#include "tc_agg.cuh"
+#include "tc_common.cuh"
+
+namespace fgc {
+
+namespace {
+
+constexpr int kAggWarpsW = 8;
+constexpr int kEpiWarpsW = 4;
+constexpr int kThreadsW = (kAggWarpsW + kEpiWarpsW + 1) * 32;  // 416
+constexpr int kPassW = 32;
+
+// |x| max as ordered uint bits (non-negative floats order like unsigned ints)
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// power-of-two scale s with |v| * s < 2^15 for every |v| <= bound * 2^extra_log2 ; returns 1/s too
+__device__ __forceinline__ void pow2_scale(unsigned maxbits, int extra_log2, float& scale, float& unscale) {
+  int E = static_cast<int>((maxbits >> 23) & 0xFF) + extra_log2;
+  E = min(max(E, 20), 250);
+  scale = __int_as_float((268 - E) << 23);    // 2^(141-E)
+  unscale = __int_as_float((E - 14) << 23);   // 2^(E-141)
+}
+
+template <int M>
+struct WCfg {
+  static constexpr int MQ = AggQ<M>::MQ;
+  static constexpr int A_PLANE = 4 * M * 1024;                 // [4 k-groups][M blocks][8 rows][128 B]
+  static constexpr int B_PLANE = 4 * 1024;                     // [4 k-groups][8 rows][128 B]
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int OFF_Q = 2 * STAGE;
+  static constexpr int OFF_NBR = OFF_Q + kAggWarpsW * AggQ<M>::QS_FLOATS * 4;
+  static constexpr int OFF_BAR = OFF_NBR + kAggWarpsW * AggQ<M>::NBR_INTS * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static constexpr int NBLK = M / 2;                           // M-blocks of 128 (m,c) rows
+  static_assert(M % 2 == 0, "M must be even");
+  static_assert(NBLK * 128 <= 512, "TMEM overflow");
+  static_assert(STAGE % 1024 == 0, "stage must keep 1024-byte alignment");
+};
+
+struct WParams {
+  AggSrc src;
+  const float* gy;
+  const unsigned* maxbits;   // [0] = max|x| bits, [1] = max|gy| bits
+  float* partW;              // [grid][M][64][64]
+  float* partB;              // [grid][64]
+  int bias_mask;
+  int64_t npasses;
+};
+
+enum { WB_FULL0 = 0, WB_FULL1, WB_EMPTY0, WB_EMPTY1, WB_DONE, WB_COUNT };
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreadsW, 1)
+bwd_w_tc_kernel(const WParams p) {
+  using Cfg = WCfg<M>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* qs_all = reinterpret_cast<float*>(smem + Cfg::OFF_Q);
+  int* nbr_all = reinterpret_cast<int*>(smem + Cfg::OFF_NBR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + WB_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bars[WB_FULL0], kAggWarpsW);
+    tc::mbar_init(&bars[WB_FULL1], kAggWarpsW);
+    tc::mbar_init(&bars[WB_EMPTY0], 1);
+    tc::mbar_init(&bars[WB_EMPTY1], 1);
+    tc::mbar_init(&bars[WB_DONE], 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == kAggWarpsW + kEpiWarpsW) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  float ss, s_un, sg, g_un;
+  pow2_scale(__ldg(p.maxbits), 5, ss, s_un);      // |s| <= K * max|x|, K <= 32
+  pow2_scale(__ldg(p.maxbits + 1), 0, sg, g_un);  // |gz| <= max|gy|
+
+  if (warp < kAggWarpsW) {
+    // =========================================================== aggregators
+    float* qs = qs_all + warp * AggQ<M>::QS_FLOATS;
+    int* nbr = nbr_all + warp * AggQ<M>::NBR_INTS;
+    const int grp = lane >> 3, gl = lane & 7;
+    const int j = warp * 4 + grp;            // row within the pass
+    const int kg = j >> 3, jr = j & 7;
+    float gb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gb[i] = 0.f;
+    int it = 0;
+    for (int64_t pass = blockIdx.x; pass < p.npasses; pass += gridDim.x, ++it) {
+      const int64_t r = pass * kPassW + j;
+      float2 acc[M][4];
+#pragma unroll
+      for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[m][i] = make_float2(0.f, 0.f);
+      int cnt = 0;
+      float dv[2][M];
+      tc_aggregate<M, MODE_FWD>(p.src, pass * kPassW + warp * 4, qs, nbr, lane, acc, cnt, dv);
+      // gz row of this facet (channels 4gl..4gl+3 and 32+4gl..32+4gl+3)
+      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+      if (r < p.src.rows) {
+        const float4* gr = reinterpret_cast<const float4*>(p.gy + r * 64);
+        g0 = __ldg(gr + gl);
+        g1 = __ldg(gr + 8 + gl);
+      }
+      const float fl = (r < p.src.rows && (cnt > 0 || !p.bias_mask)) ? 1.f : 0.f;
+      gb[0] = fmaf(fl, g0.x, gb[0]), gb[1] = fmaf(fl, g0.y, gb[1]), gb[2] = fmaf(fl, g0.z, gb[2]);
+      gb[3] = fmaf(fl, g0.w, gb[3]), gb[4] = fmaf(fl, g1.x, gb[4]), gb[5] = fmaf(fl, g1.y, gb[5]);
+      gb[6] = fmaf(fl, g1.z, gb[6]), gb[7] = fmaf(fl, g1.w, gb[7]);
+      const float gsc = (cnt ? 1.f / static_cast<float>(cnt) : 0.f) * sg;
+
+      const int st = it & 1;
+      tc::mbar_wait(&bars[WB_EMPTY0 + st], ((it >> 1) & 1) ^ 1);
+      uint8_t* base = smem + st * Cfg::STAGE;
+      uint8_t* ah = base;
+      uint8_t* al = base + Cfg::A_PLANE;
+      uint8_t* bh = base + 2 * Cfg::A_PLANE;
+      uint8_t* bl = bh + Cfg::B_PLANE;
+      // element (row j, block m, channel c): ((kg*M + m)*8 + jr)*128 + ((c/8 ^ jr)*16) + (c%8)*2
+      const int u0 = ((gl >> 1) ^ jr) * 16 + (gl & 1) * 8;        // channels 4gl..4gl+3
+      const int u1 = (((4 + (gl >> 1))) ^ jr) * 16 + (gl & 1) * 8;  // channels 32+4gl..
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_pair(acc[m][i].x * ss, acc[m][i].y * ss, h[i], l[i]);
+        const int rowoff = ((kg * M + m) * 8 + jr) * 128;
+        *reinterpret_cast<uint2*>(ah + rowoff + u0) = make_uint2(h[0], h[1]);
+        *reinterpret_cast<uint2*>(ah + rowoff + u1) = make_uint2(h[2], h[3]);
+        *reinterpret_cast<uint2*>(al + rowoff + u0) = make_uint2(l[0], l[1]);
+        *reinterpret_cast<uint2*>(al + rowoff + u1) = make_uint2(l[2], l[3]);
+      }
+      {
+        uint32_t h[4], l[4];
+        split_pair(g0.x * gsc, g0.y * gsc, h[0], l[0]);
+        split_pair(g0.z * gsc, g0.w * gsc, h[1], l[1]);
+        split_pair(g1.x * gsc, g1.y * gsc, h[2], l[2]);
+        split_pair(g1.z * gsc, g1.w * gsc, h[3], l[3]);
+        const int rowoff = (kg * 8 + jr) * 128;
+        *reinterpret_cast<uint2*>(bh + rowoff + u0) = make_uint2(h[0], h[1]);
+        *reinterpret_cast<uint2*>(bh + rowoff + u1) = make_uint2(h[2], h[3]);
+        *reinterpret_cast<uint2*>(bl + rowoff + u0) = make_uint2(l[0], l[1]);
+        *reinterpret_cast<uint2*>(bl + rowoff + u1) = make_uint2(l[2], l[3]);
+      }
+      tc::fence_proxy_async_smem();   // generic-proxy writes -> UMMA (async proxy) reads
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[WB_FULL0 + st]);
+    }
+    // ---- bias gradient: fixed-order reduction over the 32 facet slots of the CTA
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    float* red = qs_all;  // [32 slots][64 channels]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      red[j * 64 + 4 * gl + i] = gb[i];
+      red[j * 64 + 32 + 4 * gl + i] = gb[4 + i];
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (threadIdx.x < 64) {
+      float a = 0.f;
+      for (int s = 0; s < 32; ++s) a += red[s * 64 + threadIdx.x];
+      p.partB[static_cast<int64_t>(blockIdx.x) * 64 + threadIdx.x] = a;
+    }
+  } else if (warp < kAggWarpsW + kEpiWarpsW) {
+    // =========================================================== final read-out
+    const int quad = warp - kAggWarpsW;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    tc::mbar_wait(&bars[WB_DONE], 0);
+    tc::tc_fence_after_sync();
+    const float un = s_un * g_un;
+    float* pw = p.partW + static_cast<int64_t>(blockIdx.x) * M * 64 * 64;
+    for (int mb = 0; mb < Cfg::NBLK; ++mb) {
+      const int idx = mb * 128 + quad * 32 + lane;   // (m,c) row of this thread
+      const int m = idx >> 6, c = idx & 63;
+#pragma unroll 1
+      for (int o0 = 0; o0 < 64; o0 += 32) {
+        uint32_t dh[32], dx[32];
+        tc::tmem_ld32(tmem + lane_base + mb * 128 + o0, dh);
+        tc::tmem_ld32(tmem + lane_base + mb * 128 + 64 + o0, dx);
+        tc::tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = (__uint_as_float(dh[i]) + __uint_as_float(dx[i]) * (1.f / 2048.f)) * un;
+          pw[(static_cast<int64_t>(m) * 64 + o0 + i) * 64 + c] = v;
+        }
+      }
+    }
+    tc::tc_fence_before_sync();
+  } else {
+    // =========================================================== MMA issuer
+    constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t sbase = tc::smem_u32(smem);
+    int it = 0;
+    for (int64_t pass = blockIdx.x; pass < p.npasses; pass += gridDim.x, ++it) {
+      const int st = it & 1;
+      tc::mbar_wait(&bars[WB_FULL0 + st], (it >> 1) & 1);
+      tc::tc_fence_after_sync();
+      if (lane == 0) {
+        const uint32_t ah = sbase + st * Cfg::STAGE, al = ah + Cfg::A_PLANE;
+        const uint32_t bh = ah + 2 * Cfg::A_PLANE, bl = bh + Cfg::B_PLANE;
+#pragma unroll 1
+        for (int mb = 0; mb < Cfg::NBLK; ++mb) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t aoff = (ks * 2 * M + mb * 2) * 1024;   // k-group 2ks, MN-atom 2mb
+            const uint64_t dah = smem_desc_mn_sw128(ah + aoff, 1024, M * 1024);
+            const uint64_t dal = smem_desc_mn_sw128(al + aoff, 1024, M * 1024);
+            const uint64_t dbh = smem_desc_mn_sw128(bh + ks * 2 * 1024, 1024, 1024);
+            const uint64_t dbl = smem_desc_mn_sw128(bl + ks * 2 * 1024, 1024, 1024);
+            const uint32_t first = (it | ks) ? 1u : 0u;
+            tc::mma_f16_ss(tmem + mb * 128, dah, dbh, idesc, first);
+            tc::mma_f16_ss(tmem + mb * 128 + 64, dah, dbl, idesc, first);
+            tc::mma_f16_ss(tmem + mb * 128 + 64, dal, dbh, idesc, 1u);
+          }
+        }
+        tc::tc_commit(&bars[WB_EMPTY0 + st]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) tc::tc_commit(&bars[WB_DONE]);
+    __syncwarp();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kAggWarpsW + kEpiWarpsW) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool bwd_w_tc_supported(int Cw, int Cout, int M, int Cin) { return Cw == 64 && Cout == 64 && M == 8 && Cin % 4 == 0; }
+
+int bwd_w_tc_grid(int64_t rows) {
+  const int64_t npasses = (rows + kPassW - 1) / kPassW;
+  int64_t g = num_sms();
+  if (g > npasses) g = npasses;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+// partW[grid][M*64*64], partB[grid][64]; maxbits: 2 uints of scratch
+int launch_bwd_w_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, float* partW,
+                    float* partB, unsigned* maxbits, int64_t rows, int N, int K, int Cin, int M,
+                    int bias_mask, cudaStream_t st) {
+  FGC_CUDA(cudaMemsetAsync(maxbits, 0, 2 * sizeof(unsigned), st));
+  const int ab = num_sms() * 4;
+  absmax_kernel<<<ab, 256, 0, st>>>(x, rows * Cin, maxbits);
+  FGC_LAUNCHED("absmax_kernel");
+  absmax_kernel<<<ab, 256, 0, st>>>(gy, rows * 64, maxbits + 1);
+  FGC_LAUNCHED("absmax_kernel");
+  WParams p{};
+  p.src = AggSrc{x, Cin, adj, uvx, N, K, rows, nullptr, nullptr, nullptr, nullptr};
+  p.gy = gy, p.maxbits = maxbits, p.partW = partW, p.partB = partB, p.bias_mask = bias_mask;
+  p.npasses = (rows + kPassW - 1) / kPassW;
+  if (M != 8) {
+    set_error("bwd_w_tc: unsupported M");
+    return FGC_ERR_UNSUPPORTED;
+  }
+  using Cfg = WCfg<8>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+  FGC_CUDA(cudaFuncSetAttribute(bwd_w_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  bwd_w_tc_kernel<8><<<bwd_w_tc_grid(rows), kThreadsW, Cfg::SMEM_BYTES, st>>>(p);
+  FGC_LAUNCHED("bwd_w_tc_kernel");
+  return FGC_OK;
+}
+
+}  // namespace fgc

@@ -18,6 +18,7 @@
 // i.e. fp32-class results (parity tests: max-abs <= 1e-5 vs the oracle).
 #include "conv_common.cuh"
 #include "conv_launch.cuh"
+#include "tc_agg.cuh"
 #include "tc_common.cuh"
 
 namespace fgc {
@@ -30,7 +31,6 @@ constexpr int kPass = 32;          // rows per staging pass
 constexpr int kAggWarps = 8;
 constexpr int kMoverWarps = 4;
 constexpr int kTcThreads = (kAggWarps + kMoverWarps + 1) * 32;  // 416
-constexpr int kQK = 16;            // neighbour slots per assignment round
 
 template <int M, int COUT>
 struct TcCfg {
@@ -61,8 +61,6 @@ struct TcCfg {
 // MODE_FWD: rows gathered through the adjacency (source-centric forward).
 // MODE_TGT: rows gathered through the reversed adjacency (target-centric backward: t = sum q*gz,
 //           gx = t . W^T), see conv_bwd.cu.
-constexpr int MODE_FWD = 0;
-constexpr int MODE_TGT = 1;
 
 struct TcParams {
   const float* x;        // gathered rows: x (FWD) or gy (TGT); row stride `Cin`
@@ -136,6 +134,7 @@ conv_fwd_tc_kernel(const TcParams p) {
     const int gl = lane & 7;         // lane within the 8-lane group
     uint32_t empty_parity = 1;       // producer convention: the first wait falls through
     int it = 0;
+    const AggSrc src{p.x, p.Cin, p.adj, p.uvx, p.N, p.K, p.rows, p.rev_ptr, p.rev_edge, p.inv, p.da_edge};
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       for (int pass = 0; pass < 2; ++pass) {
         const int prow = warp * 4 + grp;                       // row within the pass (0..31)
@@ -147,117 +146,12 @@ conv_fwd_tc_kernel(const TcParams p) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[m][i] = make_float2(0.f, 0.f);
         int cnt = 0;
-        // neighbour list of this lane's facet: the K adjacency slots (FWD) or the in-edge segment of
-        // the reversed adjacency (TGT); processed in rounds of kQK entries, warp-uniform trip count
-        int lst0 = 0, lst1 = 0;
         float dv[2][M];           // TGT: per-lane partial sums of da_edge -> d_uvx[:, M:2M]
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int m = 0; m < M; ++m) dv[h][m] = 0.f;
-        if constexpr (MODE == MODE_FWD) {
-          lst1 = p.K;
-        } else {
-          if (r < p.rows) {
-            lst0 = __ldg(p.rev_ptr + r);
-            lst1 = __ldg(p.rev_ptr + r + 1);
-          }
-        }
-        int nround = lst1 - lst0;
-        nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, 8));
-        nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, 16));
-        for (int kb = 0; kb < nround; kb += kQK) {
-          const int nk = min(kQK, nround - kb);
-          __syncwarp();
-          // ---- soft assignments: lane per (facet, slot) pair; pair = lane + 32h, facet = pair / 16
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int f = (lane >> 4) + 2 * h, k = lane & 15;
-            const int64_t rf = tile * kTile + pass * kPass + warp * 4 + f;
-            // list bounds of facet f live in the lane group that owns it
-            const int f0 = __shfl_sync(0xffffffffu, lst0, f * 8);
-            const int f1 = __shfl_sync(0xffffffffu, lst1, f * 8);
-            int row = -1;
-            float a[M];
-            bool have = false;
-            if (k < nk && rf < p.rows && f0 + kb + k < f1) {
-              have = true;
-              const float* ux;
-              const float* vx;
-              bool vvalid = true;
-              if constexpr (MODE == MODE_FWD) {
-                const int id = __ldg(p.adj + rf * p.K + kb + k);
-                const int64_t base = (rf / p.N) * p.N;
-                vvalid = id > 0 && id <= p.N;
-                row = vvalid ? static_cast<int>(base + id - 1) : (id != 0 ? -2 : -1);
-                ux = p.uvx + rf * (2 * M);
-                vx = p.uvx + (vvalid ? static_cast<int64_t>(row) : rf) * (2 * M) + M;
-              } else {
-                const int e = __ldg(p.rev_edge + f0 + kb + k);
-                row = e / p.K;                                  // source facet of the in-edge
-                ux = p.uvx + static_cast<int64_t>(row) * (2 * M);
-                vx = p.uvx + rf * (2 * M) + M;
-                const float* de = p.da_edge + static_cast<int64_t>(e) * M;
-#pragma unroll
-                for (int m = 0; m < M; ++m) dv[h][m] += __ldg(de + m);
-              }
-#pragma unroll
-              for (int m = 0; m < M; ++m) a[m] = __ldg(ux + m) + (vvalid ? __ldg(vx + m) : 0.f);
-              float mx = a[0];
-#pragma unroll
-              for (int m = 1; m < M; ++m) mx = fmaxf(mx, a[m]);
-              float sum = 0.f;
-#pragma unroll
-              for (int m = 0; m < M; ++m) {
-                a[m] = __expf(a[m] - mx);
-                sum += a[m];
-              }
-              float rs = 1.f / sum;
-              if constexpr (MODE == MODE_TGT) rs *= __ldg(p.inv + row);   // gy rows weighted as gz
-#pragma unroll
-              for (int m = 0; m < M; ++m) a[m] *= rs;
-            }
-            if (!have) {
-#pragma unroll
-              for (int m = 0; m < M; ++m) a[m] = 0.f;
-            }
-            float* qd = qs + (f * kQK + k) * Cfg::MQ;
-#pragma unroll
-            for (int m4 = 0; m4 < Cfg::MQ; m4 += 4)
-              *reinterpret_cast<float4*>(qd + m4) =
-                  make_float4(m4 < M ? a[m4 < M ? m4 : 0] : 0.f, m4 + 1 < M ? a[m4 + 1 < M ? m4 + 1 : 0] : 0.f,
-                              m4 + 2 < M ? a[m4 + 2 < M ? m4 + 2 : 0] : 0.f, m4 + 3 < M ? a[m4 + 3 < M ? m4 + 3 : 0] : 0.f);
-            nbr[f * kQK + k] = row;
-          }
-          __syncwarp();
-          // ---- q-weighted aggregation, 8 lanes per facet, packed FMAs
-#pragma unroll 4
-          for (int k = 0; k < nk; ++k) {
-            const int j = nbr[grp * kQK + k];
-            cnt += (j != -1);
-            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-            if (j >= 0) {
-              const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(j) * p.Cin);
-              x0 = __ldg(xr + gl);
-              x1 = __ldg(xr + 8 + gl);
-            }
-            const float2 xp[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w),
-                                  make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
-            const float* qk = qs + (grp * kQK + k) * Cfg::MQ;
-            float q[Cfg::MQ];
-#pragma unroll
-            for (int m4 = 0; m4 < Cfg::MQ; m4 += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(qk + m4);
-              q[m4] = t.x, q[m4 + 1] = t.y, q[m4 + 2] = t.z, q[m4 + 3] = t.w;
-            }
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-              const float2 qq = make_float2(q[m], q[m]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) tc::ffma2(acc[m][i], qq, xp[i]);
-            }
-          }
-        }
+        tc_aggregate<M, MODE>(src, tile * kTile + pass * kPass + warp * 4, qs, nbr, lane, acc, cnt, dv);
         if constexpr (MODE == MODE_TGT) {
           // d_uvx[t, M + m] = sum of da_edge over the in-edges of t: reduce the 16 lanes of a facet
 #pragma unroll
@@ -296,14 +190,7 @@ conv_fwd_tc_kernel(const TcParams p) {
         for (int m = 0; m < M; ++m) {
           uint32_t h[4], l[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float v0 = acc[m][i].x * sc, v1 = acc[m][i].y * sc;
-            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-            const __half l0 = __float2half_rn((v0 - __half2float(h0)) * 2048.f);
-            const __half l1 = __float2half_rn((v1 - __half2float(h1)) * 2048.f);
-            h[i] = tc::pack_half2(h0, h1);
-            l[i] = tc::pack_half2(l0, l1);
-          }
+          for (int i = 0; i < 4; ++i) split_pair(acc[m][i].x * sc, acc[m][i].y * sc, h[i], l[i]);
           // channels 4gl..4gl+3 -> words m*32 + 2gl, +1 ; channels 32+4gl.. -> words m*32 + 16 + 2gl, +1
           *reinterpret_cast<uint2*>(rh + m * 32 + 2 * gl) = make_uint2(h[0], h[1]);
           *reinterpret_cast<uint2*>(rh + m * 32 + 16 + 2 * gl) = make_uint2(h[2], h[3]);

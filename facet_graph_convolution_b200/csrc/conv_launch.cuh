@@ -35,6 +35,11 @@ int launch_bwd_tgt_tc(const float* gy, const float* uvx, const float* W0, const 
                       const float* inv, const int32_t* rev_ptr, const int32_t* rev_edge, float* gx,
                       float* d_uvx, int64_t rows, int N, int K, int Cin, int Cw, int Cout, int M,
                       void* wimg_ws, cudaStream_t st);
+bool bwd_w_tc_supported(int Cw, int Cout, int M, int Cin);
+int bwd_w_tc_grid(int64_t rows);
+int launch_bwd_w_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, float* partW,
+                    float* partB, unsigned* maxbits, int64_t rows, int N, int K, int Cin, int M,
+                    int bias_mask, cudaStream_t st);
 size_t conv_bwd_workspace(const fgc_conv_shape* s);
 int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
