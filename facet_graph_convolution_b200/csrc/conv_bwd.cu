@@ -842,13 +842,19 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
 
   int rc = launch_assign_logits(s, x, u, v, c, uvx, st);
   if (rc) return rc;
-  {
+  const int MP = pick_mp(s->M);
+  const bool tc_all = !tc_disabled && s->Cout % 4 == 0 && bwd_tgt_tc_supported(s->Cw, s->Cout, s->M) &&
+                      bwd_src_tc_supported(s->Cw, s->Cout, s->M, s->Cin);
+  if (tc_all) {
+    rc = launch_prep_w_image_t(W0, wimg, s->M, s->Cw, st);
+    if (rc) return rc;
+    const float* wunscale = reinterpret_cast<const float*>(wimg + static_cast<size_t>(s->M) * 2 * s->Cw * 128);
+    rc = launch_bwd_src_tc(gy, x, adj, uvx, wimg, wunscale, da_edge, d_uvx, inv, rows, s->N, s->K, s->Cin, s->M, st);
+    if (rc) return rc;
+  } else {
     const int total = static_cast<int>(nW);
     permute_w_ds_kernel<<<(total + 255) / 256, 256, 0, st>>>(W0, Wd, s->M, s->Cout, s->Cw);
     FGC_LAUNCHED("permute_w_ds_kernel");
-  }
-  const int MP = pick_mp(s->M);
-  {
     BwdSrcParams p{gy, x, adj, uvx, Wd, da_edge, d_uvx, inv, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M};
 #define FGC_CALL(MPV, NCV) rc = run_src<MPV, NCV>(p, st)
     FGC_DISPATCH_MP_NC(MP, pick_nc(s->Cw), FGC_CALL);
@@ -857,8 +863,8 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   }
   if (!tc_disabled && s->Cout % 4 == 0 && bwd_tgt_tc_supported(s->Cw, s->Cout, s->M)) {
     if (s->Cin > s->Cw) FGC_CUDA(cudaMemsetAsync(gx, 0, rows * s->Cin * sizeof(float), st));
-    rc = launch_bwd_tgt_tc(gy, uvx, W0, da_edge, inv, rev_ptr, rev_edge, gx, d_uvx, rows, s->N, s->K,
-                           s->Cin, s->Cw, s->Cout, s->M, wimg, st);
+    rc = launch_bwd_tgt_tc(gy, uvx, tc_all ? nullptr : W0, da_edge, inv, rev_ptr, rev_edge, gx, d_uvx, rows,
+                           s->N, s->K, s->Cin, s->Cw, s->Cout, s->M, wimg, st);
     if (rc) return rc;
   } else {
     BwdTgtParams p{gy, uvx, W0, da_edge, inv, rev_ptr, rev_edge, gx, d_uvx, rows,

@@ -261,6 +261,285 @@ bwd_w_tc_kernel(const WParams p) {
   if (warp == kAggWarpsW + kEpiWarpsW) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// ====================================================================================================
+// Source-centric backward pass on tensor cores:
+//   ds[n,m,:]  = W0[m]^T gz[n]            tcgen05.mma, A' = [gz_hi ; gz_lo] in TMEM (32-row tiles),
+//                                         B = the transposed weight image shared with bwd_tgt
+//   dq[n,k,m]  = ds[n,m,:] . x_{j_k}      8 lanes per facet, packed FMAs + transpose-reduce shuffles
+//   da         = q (dq - sum_m q dq)  ->  da_edge[n,k,:],  d_uvx[n,0:M] = sum_k da,  inv_cnt[n]
+// Warps 0-7 aggregate, warp 8/9 own TMEM lane quadrants 0/1 (hi / lo rows: A' writer and D' reader),
+// warp 10 issues the MMAs.  ds travels TMEM -> shared (fp32, 32 x 512) -> registers of the owning lanes.
+constexpr int kSrcAggWarps = 8;
+constexpr int kSrcThreads = (kSrcAggWarps + 3) * 32;  // 352
+constexpr int kSrcTile = 32;
+
+template <int M>
+struct SCfg {
+  static constexpr int KK = M * 64;
+  static constexpr int NB = 128;
+  static constexpr int W_BYTES = M * NB * 128;
+  static constexpr int DS_PITCH = KK + 4;                  // floats, == 4 mod 32
+  static constexpr int EX_PITCH = 33;
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_DS = OFF_W + W_BYTES;
+  static constexpr int OFF_EX = OFF_DS + kSrcTile * DS_PITCH * 4;
+  static constexpr int OFF_Q = OFF_EX + kSrcTile * EX_PITCH * 4;
+  static constexpr int OFF_NBR = OFF_Q + kSrcAggWarps * AggQ<M>::QS_FLOATS * 4;
+  static constexpr int OFF_BAR = OFF_NBR + kSrcAggWarps * AggQ<M>::NBR_INTS * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static constexpr int D_COL0 = 64;                        // two D' slots of 128 columns
+  static_assert(DS_PITCH % 32 == 4, "ds pitch must be 4 mod 32 words");
+};
+
+struct SParams {
+  AggSrc src;
+  const float* gy;
+  const uint4* wimg;       // transposed weight image (chunk m: rows c hi|lo, K = o)
+  const float* wunscale;
+  float* da_edge;
+  float* d_uvx;
+  float* inv_out;
+  int64_t ntiles;
+};
+
+enum { SB_A_READY = 0, SB_A_FREE, SB_D_FULL0, SB_D_FULL1, SB_D_FREE0, SB_D_FREE1, SB_DS_FULL, SB_DS_FREE, SB_COUNT };
+
+template <int M>
+__global__ void __launch_bounds__(kSrcThreads, 1)
+bwd_src_tc_kernel(const SParams p) {
+  static_assert(M == 8, "the transpose-reduce below is written for M == 8");
+  using Cfg = SCfg<M>;
+  constexpr int MQ = AggQ<M>::MQ;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* DS = reinterpret_cast<float*>(smem + Cfg::OFF_DS);
+  float* EX = reinterpret_cast<float*>(smem + Cfg::OFF_EX);
+  float* qs_all = reinterpret_cast<float*>(smem + Cfg::OFF_Q);
+  int* nbr_all = reinterpret_cast<int*>(smem + Cfg::OFF_NBR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + SB_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bars[SB_A_READY], 2);
+    tc::mbar_init(&bars[SB_A_FREE], 1);
+    tc::mbar_init(&bars[SB_D_FULL0], 1);
+    tc::mbar_init(&bars[SB_D_FULL1], 1);
+    tc::mbar_init(&bars[SB_D_FREE0], 2);
+    tc::mbar_init(&bars[SB_D_FREE1], 2);
+    tc::mbar_init(&bars[SB_DS_FULL], 1);
+    tc::mbar_init(&bars[SB_DS_FREE], kSrcAggWarps);
+    tc::mbar_fence_init();
+  }
+  if (warp == kSrcAggWarps + 2) tc::tmem_alloc(tmem_slot, 512);
+  {
+    uint4* wdst = reinterpret_cast<uint4*>(smem + Cfg::OFF_W);
+    for (int i = threadIdx.x; i < Cfg::W_BYTES / 16; i += kSrcThreads) wdst[i] = __ldg(p.wimg + i);
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < kSrcAggWarps) {
+    // =========================================================== aggregators
+    float* qs = qs_all + warp * AggQ<M>::QS_FLOATS;
+    int* nbr = nbr_all + warp * AggQ<M>::NBR_INTS;
+    const int grp = lane >> 3, gl = lane & 7;
+    const int j = warp * 4 + grp;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int64_t wrow0 = tile * kSrcTile + warp * 4;
+      const int64_t r = wrow0 + grp;
+      tc::mbar_wait(&bars[SB_DS_FULL], it & 1);
+      float2 ds2[M][4];
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(DS + j * Cfg::DS_PITCH + m * 64 + 4 * gl);
+        const float4 b = *reinterpret_cast<const float4*>(DS + j * Cfg::DS_PITCH + m * 64 + 32 + 4 * gl);
+        ds2[m][0] = make_float2(a.x, a.y), ds2[m][1] = make_float2(a.z, a.w);
+        ds2[m][2] = make_float2(b.x, b.y), ds2[m][3] = make_float2(b.z, b.w);
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[SB_DS_FREE]);
+      int lst0, lst1;
+      const int nround = agg_list_bounds<MODE_FWD>(p.src, r, lst0, lst1);
+      float dv[2][M];
+      float dux = 0.f;
+      for (int kb = 0; kb < nround; kb += kQK) {
+        const int nk = min(kQK, nround - kb);
+        __syncwarp();
+        agg_assign_round<M, MODE_FWD>(p.src, wrow0, kb, nk, lst0, lst1, qs, nbr, lane, dv);
+        __syncwarp();
+#pragma unroll 2
+        for (int k = 0; k < nk; ++k) {
+          const int jn = nbr[grp * kQK + k];
+          float2 xp[4];
+          agg_load_row(p.src, jn, gl, xp);
+          float v[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tc::ffma2(t, ds2[m][i], xp[i]);
+            v[m] = t.x + t.y;
+          }
+          // transpose-reduce over the 8 lanes of the facet: lane gl ends with the total of m == gl
+          {
+            const bool up = (gl & 4) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+          }
+          {
+            const bool up = (gl & 2) != 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+          }
+          float dq;
+          {
+            const bool up = (gl & 1) != 0;
+            const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+            dq = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+          const float qv = qs[(grp * kQK + k) * MQ + gl];
+          float dot = qv * dq;
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+          const float da = qv * (dq - dot);
+          if (r < p.src.rows && kb + k < p.src.K)
+            p.da_edge[(r * p.src.K + kb + k) * M + gl] = da;
+          dux += da;
+        }
+      }
+      if (r < p.src.rows) p.d_uvx[r * (2 * M) + gl] = dux;
+    }
+  } else if (warp < kSrcAggWarps + 2) {
+    // =========================================================== TMEM lane owners (quad 0: hi, quad 1: lo)
+    const int quad = warp - kSrcAggWarps;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const float wun = __ldg(p.wunscale);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int64_t r = tile * kSrcTile + lane;
+      // ---- gz row -> A' (hi or lo plane), scaled by a power of two to [0.5, 1)
+      float g[64];
+      float inv = 0.f;
+      if (r < p.src.rows) {
+        int cnt = 0;
+        for (int k = 0; k < p.src.K; ++k) cnt += (__ldg(p.src.adj + r * p.src.K + k) != 0);
+        inv = cnt ? 1.f / static_cast<float>(cnt) : 0.f;
+        if (quad == 0) p.inv_out[r] = inv;
+        const float4* gr = reinterpret_cast<const float4*>(p.gy + r * 64);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 t = __ldg(gr + i);
+          g[4 * i] = t.x * inv, g[4 * i + 1] = t.y * inv, g[4 * i + 2] = t.z * inv, g[4 * i + 3] = t.w * inv;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) g[i] = 0.f;
+      }
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, fabsf(g[i]));
+      int E = (__float_as_int(mx) >> 23) & 0xFF;
+      E = min(max(E, 16), 240);
+      const float sc = __int_as_float((253 - E) << 23);
+      const float unsc = __int_as_float((E + 1) << 23) * wun;
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        uint32_t h, l;
+        split_pair(g[2 * i] * sc, g[2 * i + 1] * sc, h, l);
+        w[i] = quad == 0 ? h : l;
+      }
+      tc::mbar_wait(&bars[SB_A_FREE], (it & 1) ^ 1);
+      tc::tc_fence_after_sync();
+      tc::tmem_st32(tmem + lane_base, w);
+      tc::tc_wait_st();
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[SB_A_READY]);
+      // ---- D' chunks -> ds (fp32) in shared memory
+      tc::mbar_wait(&bars[SB_DS_FREE], (it & 1) ^ 1);
+      for (int jm = 0; jm < M; ++jm) {
+        const int cj = it * M + jm, slot = cj & 1;
+        tc::mbar_wait(&bars[SB_D_FULL0 + slot], (cj >> 1) & 1);
+        tc::tc_fence_after_sync();
+        const uint32_t dcol = tmem + lane_base + Cfg::D_COL0 + slot * 128;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t d0[32], d1[32];
+          tc::tmem_ld32(dcol + half * 32, d0);        // (.)Wh
+          tc::tmem_ld32(dcol + 64 + half * 32, d1);   // (.)Wl
+          tc::tc_wait_ld();
+          if (quad == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              EX[lane * Cfg::EX_PITCH + i] =
+                  __uint_as_float(d0[i]) * (1.f / 2048.f) + __uint_as_float(d1[i]) * (1.f / 4194304.f);
+          }
+          asm volatile("bar.sync 3, 64;" ::: "memory");
+          if (quad == 0) {
+            float* dst = DS + lane * Cfg::DS_PITCH + jm * 64 + half * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float o[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                o[q] = (__uint_as_float(d0[i + q]) + __uint_as_float(d1[i + q]) * (1.f / 2048.f) +
+                        EX[lane * Cfg::EX_PITCH + i + q]) * unsc;
+              *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          asm volatile("bar.sync 3, 64;" ::: "memory");
+        }
+        tc::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[SB_D_FREE0 + slot]);
+      }
+      if (quad == 0) {
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[SB_DS_FULL]);
+      }
+    }
+  } else {
+    // =========================================================== MMA issuer
+    const uint32_t idesc = tc::idesc_f16(128, Cfg::NB);
+    const uint32_t wbase = tc::smem_u32(smem + Cfg::OFF_W);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      tc::mbar_wait(&bars[SB_A_READY], it & 1);
+      for (int jm = 0; jm < M; ++jm) {
+        const int cj = it * M + jm, slot = cj & 1;
+        tc::mbar_wait(&bars[SB_D_FREE0 + slot], ((cj >> 1) & 1) ^ 1);
+        tc::tc_fence_after_sync();
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bdesc = tc::smem_desc_k_sw128(wbase + jm * (Cfg::NB * 128) + ks * 32);
+            tc::mma_f16_ts(tmem + Cfg::D_COL0 + slot * 128, tmem + ks * 8, bdesc, idesc, ks ? 1u : 0u);
+          }
+          tc::tc_commit(&bars[SB_D_FULL0 + slot]);
+          if (jm == M - 1) tc::tc_commit(&bars[SB_A_FREE]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kSrcAggWarps + 2) tc::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 
 bool bwd_w_tc_supported(int Cw, int Cout, int M, int Cin) { return Cw == 64 && Cout == 64 && M == 8 && Cin % 4 == 0; }
@@ -295,6 +574,36 @@ int launch_bwd_w_tc(const float* gy, const float* x, const int32_t* adj, const f
   FGC_CUDA(cudaFuncSetAttribute(bwd_w_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   bwd_w_tc_kernel<8><<<bwd_w_tc_grid(rows), kThreadsW, Cfg::SMEM_BYTES, st>>>(p);
   FGC_LAUNCHED("bwd_w_tc_kernel");
+  return FGC_OK;
+}
+
+}  // namespace fgc
+
+namespace fgc {
+
+bool bwd_src_tc_supported(int Cw, int Cout, int M, int Cin) { return Cw == 64 && Cout == 64 && M == 8 && Cin % 4 == 0; }
+
+// wimg/wunscale: the transposed weight image prepared for bwd_tgt (prep_w_image_kernel, transposed = 1)
+int launch_bwd_src_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, const void* wimg,
+                      const float* wunscale, float* da_edge, float* d_uvx, float* inv_out, int64_t rows, int N,
+                      int K, int Cin, int M, cudaStream_t st) {
+  if (M != 8) {
+    set_error("bwd_src_tc: unsupported M");
+    return FGC_ERR_UNSUPPORTED;
+  }
+  using Cfg = SCfg<8>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+  SParams p{};
+  p.src = AggSrc{x, Cin, adj, uvx, N, K, rows, nullptr, nullptr, nullptr, nullptr};
+  p.gy = gy, p.wimg = static_cast<const uint4*>(wimg), p.wunscale = wunscale;
+  p.da_edge = da_edge, p.d_uvx = d_uvx, p.inv_out = inv_out;
+  p.ntiles = (rows + kSrcTile - 1) / kSrcTile;
+  FGC_CUDA(cudaFuncSetAttribute(bwd_src_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  int64_t grid = num_sms();
+  if (grid > p.ntiles) grid = p.ntiles;
+  if (grid < 1) grid = 1;
+  bwd_src_tc_kernel<8><<<static_cast<unsigned>(grid), kSrcThreads, Cfg::SMEM_BYTES, st>>>(p);
+  FGC_LAUNCHED("bwd_src_tc_kernel");
   return FGC_OK;
 }
 

@@ -366,9 +366,11 @@ template <int M, int COUT, int MODE>
 int launch_tc(const TcParams& tp_in, void* wimg, float* wunscale, const float* W0, cudaStream_t st) {
   using Cfg = TcCfg<M, COUT>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
-  prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg), wunscale, M, COUT,
-                                           MODE == MODE_TGT ? 1 : 0);
-  FGC_LAUNCHED("prep_w_image_kernel");
+  if (W0 != nullptr) {   // nullptr: the caller already prepared the image
+    prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg), wunscale, M, COUT,
+                                             MODE == MODE_TGT ? 1 : 0);
+    FGC_LAUNCHED("prep_w_image_kernel");
+  }
   TcParams tp = tp_in;
   tp.wimg = static_cast<const uint4*>(wimg);
   tp.wunscale = wunscale;
@@ -402,6 +404,15 @@ int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, c
   if (p.M == 8 && p.Cout == 64) return launch_tc<8, 64, MODE_FWD>(tp, wimg_ws, wunscale, W0, st);
   set_error("conv_fwd_tc: unsupported shape");
   return FGC_ERR_UNSUPPORTED;
+}
+
+// transposed weight image (chunk m: rows c hi|lo, K = o) shared by bwd_src_tc and bwd_tgt_tc
+int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStream_t st) {
+  const size_t img = static_cast<size_t>(M) * 2 * Cw * 128;
+  float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
+  prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cw, 1);
+  FGC_LAUNCHED("prep_w_image_kernel");
+  return FGC_OK;
 }
 
 // Target-centric backward pass on the same skeleton: gx[:, 0:Cw] = sum_m t[.,m,:] W0[m] with

@@ -35,6 +35,11 @@ int launch_bwd_tgt_tc(const float* gy, const float* uvx, const float* W0, const 
                       const float* inv, const int32_t* rev_ptr, const int32_t* rev_edge, float* gx,
                       float* d_uvx, int64_t rows, int N, int K, int Cin, int Cw, int Cout, int M,
                       void* wimg_ws, cudaStream_t st);
+int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStream_t st);
+bool bwd_src_tc_supported(int Cw, int Cout, int M, int Cin);
+int launch_bwd_src_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, const void* wimg,
+                      const float* wunscale, float* da_edge, float* d_uvx, float* inv_out, int64_t rows, int N,
+                      int K, int Cin, int M, cudaStream_t st);
 bool bwd_w_tc_supported(int Cw, int Cout, int M, int Cin);
 int bwd_w_tc_grid(int64_t rows);
 int launch_bwd_w_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, float* partW,
