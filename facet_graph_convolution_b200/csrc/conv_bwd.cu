@@ -502,6 +502,8 @@ bwd_w_kernel(const BwdWParams p) {
 }
 
 // ------------------------------------------------------------------ logits backward
+// d_uvx[rows][2M] -> (a) the logit-window part of gx, thread per row;
+//                    (b) gu, gv, gc partial sums per CTA (fixed order), thread per 4 outputs.
 struct LogitsBwdParams {
   const float* x;
   const float* d_uvx;  // [rows][2M]
@@ -516,64 +518,108 @@ struct LogitsBwdParams {
 
 constexpr int kLogitRows = 32;
 
-__global__ void __launch_bounds__(kThreads)
-logits_bwd_kernel(const LogitsBwdParams p) {
+template <int OP>
+__global__ void __launch_bounds__(128)
+logits_bwd_x_kernel(const LogitsBwdParams p) {
   extern __shared__ __align__(16) float sm[];
   const int O = 2 * p.M;
-  float* uv = sm;                         // [O][Ca]
-  float* xs = uv + O * p.Ca;              // [32][Ca]
-  float* ds = xs + kLogitRows * p.Ca;     // [32][O]
-  for (int e = threadIdx.x; e < O * p.Ca; e += kThreads) {
-    const int o = e / p.Ca, cc = e % p.Ca;
-    uv[e] = (o < p.M) ? p.u[o * p.Ca + cc] : p.v[(o - p.M) * p.Ca + cc];
+  const int Ca4 = (p.Ca + 3) & ~3;
+  float* uv = sm;  // [O][Ca4]
+  for (int e = threadIdx.x; e < O * Ca4; e += blockDim.x) {
+    const int o = e / Ca4, cc = e % Ca4;
+    uv[e] = cc < p.Ca ? ((o < p.M) ? p.u[o * p.Ca + cc] : p.v[(o - p.M) * p.Ca + cc]) : 0.f;
   }
-  constexpr int kMaxOwn = 32;             // O*Ca <= 32*256 = 8192 = 32 per thread
-  float acc[kMaxOwn];
+  __syncthreads();
+  const bool vec = (p.Cin % 4 == 0) && (p.Ca0 % 4 == 0) && (p.Ca % 4 == 0);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.rows;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float d[OP];
 #pragma unroll
-  for (int i = 0; i < kMaxOwn; ++i) acc[i] = 0.f;
+    for (int o = 0; o < OP; ++o) d[o] = (o < O) ? __ldg(p.d_uvx + r * O + o) : 0.f;
+    float* gr = p.gx + r * p.Cin + p.Ca0;
+    for (int c0 = 0; c0 < Ca4; c0 += 4) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < OP; ++o) {
+        if (o < O) {
+          const float4 w = *reinterpret_cast<const float4*>(uv + o * Ca4 + c0);
+          a.x = fmaf(d[o], w.x, a.x), a.y = fmaf(d[o], w.y, a.y), a.z = fmaf(d[o], w.z, a.z), a.w = fmaf(d[o], w.w, a.w);
+        }
+      }
+      if (vec) {
+        float4 cur = *reinterpret_cast<float4*>(gr + c0);
+        cur.x += a.x, cur.y += a.y, cur.z += a.z, cur.w += a.w;
+        *reinterpret_cast<float4*>(gr + c0) = cur;
+      } else {
+        if (c0 < p.Ca) gr[c0] += a.x;
+        if (c0 + 1 < p.Ca) gr[c0 + 1] += a.y;
+        if (c0 + 2 < p.Ca) gr[c0 + 2] += a.z;
+        if (c0 + 3 < p.Ca) gr[c0 + 3] += a.w;
+      }
+    }
+  }
+}
+
+constexpr int kLogitOwn = 8;  // output quads per thread: 2M * ceil(Ca/4) <= 32 * 64 = 8 * 256
+__global__ void __launch_bounds__(kThreads)
+logits_bwd_p_kernel(const LogitsBwdParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int O = 2 * p.M;
+  const int Ca4 = (p.Ca + 3) & ~3, nq = Ca4 / 4;
+  float* xs = sm;                           // [32][Ca4]
+  float* ds = xs + kLogitRows * Ca4;        // [32][O]
+  float4 acc[kLogitOwn];
+  int oo[kLogitOwn], qq[kLogitOwn];
+#pragma unroll
+  for (int i = 0; i < kLogitOwn; ++i) {
+    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int e = threadIdx.x + i * kThreads;
+    oo[i] = e < O * nq ? e / nq : -1;
+    qq[i] = e % nq;
+  }
   float gc_acc = 0.f;
-  const int nout = O * p.Ca;
   const int64_t rb = static_cast<int64_t>(blockIdx.x) * p.rows_per_chunk;
   const int64_t re = min(p.rows, rb + p.rows_per_chunk);
   for (int64_t r0 = rb; r0 < re; r0 += kLogitRows) {
     const int nr = (re - r0 < kLogitRows) ? static_cast<int>(re - r0) : kLogitRows;
     __syncthreads();
-    for (int e = threadIdx.x; e < kLogitRows * p.Ca; e += kThreads) {
-      const int rr = e / p.Ca, cc = e % p.Ca;
-      xs[e] = (rr < nr) ? __ldg(p.x + (r0 + rr) * p.Cin + p.Ca0 + cc) : 0.f;
+    for (int e = threadIdx.x; e < kLogitRows * Ca4; e += kThreads) {
+      const int rr = e / Ca4, cc = e % Ca4;
+      xs[e] = (rr < nr && cc < p.Ca) ? __ldg(p.x + (r0 + rr) * p.Cin + p.Ca0 + cc) : 0.f;
     }
     for (int e = threadIdx.x; e < kLogitRows * O; e += kThreads) {
       const int rr = e / O;
       ds[e] = (rr < nr) ? __ldg(p.d_uvx + (r0 + rr) * O + e % O) : 0.f;
     }
     __syncthreads();
-    // parameter gradients
 #pragma unroll
-    for (int i = 0; i < kMaxOwn; ++i) {
-      const int e = threadIdx.x + i * kThreads;
-      if (e < nout) {
-        const int o = e / p.Ca, cc = e % p.Ca;
-        float a = acc[i];
-        for (int rr = 0; rr < kLogitRows; ++rr) a = fmaf(ds[rr * O + o], xs[rr * p.Ca + cc], a);
+    for (int i = 0; i < kLogitOwn; ++i) {
+      if (oo[i] >= 0) {
+        float4 a = acc[i];
+#pragma unroll 8
+        for (int rr = 0; rr < kLogitRows; ++rr) {
+          const float dv = ds[rr * O + oo[i]];
+          const float4 xv = *reinterpret_cast<const float4*>(xs + rr * Ca4 + 4 * qq[i]);
+          a.x = fmaf(dv, xv.x, a.x), a.y = fmaf(dv, xv.y, a.y), a.z = fmaf(dv, xv.z, a.z), a.w = fmaf(dv, xv.w, a.w);
+        }
         acc[i] = a;
       }
     }
     if (threadIdx.x < p.M) {
       for (int rr = 0; rr < kLogitRows; ++rr) gc_acc += ds[rr * O + threadIdx.x];
     }
-    // input gradient on the logit window
-    for (int e = threadIdx.x; e < nr * p.Ca; e += kThreads) {
-      const int rr = e / p.Ca, cc = e % p.Ca;
-      float a = 0.f;
-      for (int o = 0; o < O; ++o) a = fmaf(ds[rr * O + o], uv[o * p.Ca + cc], a);
-      p.gx[(r0 + rr) * p.Cin + p.Ca0 + cc] += a;
-    }
   }
+  const int nout = O * p.Ca;
   float* out = p.part + static_cast<int64_t>(blockIdx.x) * (nout + p.M);
 #pragma unroll
-  for (int i = 0; i < kMaxOwn; ++i) {
-    const int e = threadIdx.x + i * kThreads;
-    if (e < nout) out[e] = acc[i];
+  for (int i = 0; i < kLogitOwn; ++i) {
+    if (oo[i] >= 0) {
+      const int cc = 4 * qq[i];
+      const float av[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (cc + j < p.Ca) out[oo[i] * p.Ca + cc + j] = av[j];
+    }
   }
   if (threadIdx.x < p.M) out[nout + threadIdx.x] = gc_acc;
 }
@@ -889,10 +935,22 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   }
   {
     LogitsBwdParams p{x, d_uvx, u, v, gx, partL, rows, s->Cin, s->Ca0, s->Ca, s->M, pl.rows_per_lchunk};
-    const size_t smem = (static_cast<size_t>(2 * s->M) * s->Ca + kLogitRows * s->Ca + kLogitRows * 2 * s->M) * 4;
-    FGC_CUDA(cudaFuncSetAttribute(logits_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    logits_bwd_kernel<<<pl.lchunks, kThreads, smem, st>>>(p);
-    FGC_LAUNCHED("logits_bwd_kernel");
+    const int O = 2 * s->M, Ca4 = (s->Ca + 3) & ~3;
+    const size_t smem_x = static_cast<size_t>(O) * Ca4 * 4;
+    int64_t bx = (rows + 127) / 128;
+    const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    const unsigned g = static_cast<unsigned>(bx);
+    if (O <= 8) logits_bwd_x_kernel<8><<<g, 128, smem_x, st>>>(p);
+    else if (O <= 16) logits_bwd_x_kernel<16><<<g, 128, smem_x, st>>>(p);
+    else if (O <= 18) logits_bwd_x_kernel<18><<<g, 128, smem_x, st>>>(p);
+    else logits_bwd_x_kernel<32><<<g, 128, smem_x, st>>>(p);
+    FGC_LAUNCHED("logits_bwd_x_kernel");
+    const size_t smem_p = (static_cast<size_t>(kLogitRows) * Ca4 + kLogitRows * O) * 4;
+    FGC_CUDA(cudaFuncSetAttribute(logits_bwd_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    logits_bwd_p_kernel<<<pl.lchunks, kThreads, smem_p, st>>>(p);
+    FGC_LAUNCHED("logits_bwd_p_kernel");
   }
   rc = launch_reduce_partials(partW, gW0, nW, wchunks, nW, st);
   if (rc) return rc;

@@ -16,36 +16,51 @@
 namespace fgc {
 
 // ------------------------------------------------------------------ assignment logits pre-pass
-__global__ void __launch_bounds__(kThreads)
+// uvx[r, 0:M] = u . x_r[Ca0:Ca0+Ca] + c ; uvx[r, M:2M] = v . x_r[Ca0:Ca0+Ca].  Thread per row: the row
+// streams through registers four channels at a time, u|v are broadcast from shared memory.
+template <int OP>  // OP >= 2M accumulators
+__global__ void __launch_bounds__(128)
 assign_logits_kernel(const float* __restrict__ x, const float* __restrict__ u,
                      const float* __restrict__ v, const float* __restrict__ c,
                      float* __restrict__ uvx, int64_t rows, int Cin, int Ca0, int Ca, int M) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int O = 2 * M;
-  const int RB = kThreads / O;       // rows per block iteration
-  float* uv = sm;                    // [O][Ca+1]
-  float* xs = uv + O * (Ca + 1);     // [RB][Ca]
-  for (int e = threadIdx.x; e < O * Ca; e += kThreads) {
-    const int o = e / Ca, cc = e % Ca;
-    uv[o * (Ca + 1) + cc] = (o < M) ? u[o * Ca + cc] : v[(o - M) * Ca + cc];
+  const int Ca4 = (Ca + 3) & ~3;
+  float* uv = sm;  // [O][Ca4], zero padded
+  for (int e = threadIdx.x; e < O * Ca4; e += blockDim.x) {
+    const int o = e / Ca4, cc = e % Ca4;
+    uv[e] = cc < Ca ? ((o < M) ? u[o * Ca + cc] : v[(o - M) * Ca + cc]) : 0.f;
   }
-  const int rl = threadIdx.x / O, o = threadIdx.x % O;
-  const float cadd = (o < M) ? c[o] : 0.f;
-  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * RB; r0 < rows;
-       r0 += static_cast<int64_t>(gridDim.x) * RB) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < RB * Ca; e += kThreads) {
-      const int rr = e / Ca, cc = e % Ca;
-      xs[e] = (r0 + rr < rows) ? __ldg(x + (r0 + rr) * Cin + Ca0 + cc) : 0.f;
+  __syncthreads();
+  const bool vec = (Cin % 4 == 0) && (Ca0 % 4 == 0) && (Ca % 4 == 0);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float acc[OP];
+#pragma unroll
+    for (int o = 0; o < OP; ++o) acc[o] = 0.f;
+    const float* xr = x + r * Cin + Ca0;
+    for (int c0 = 0; c0 < Ca4; c0 += 4) {
+      float4 xv;
+      if (vec) {
+        xv = __ldg(reinterpret_cast<const float4*>(xr + c0));
+      } else {
+        xv.x = c0 < Ca ? __ldg(xr + c0) : 0.f;
+        xv.y = c0 + 1 < Ca ? __ldg(xr + c0 + 1) : 0.f;
+        xv.z = c0 + 2 < Ca ? __ldg(xr + c0 + 2) : 0.f;
+        xv.w = c0 + 3 < Ca ? __ldg(xr + c0 + 3) : 0.f;
+      }
+#pragma unroll
+      for (int o = 0; o < OP; ++o) {
+        if (o < O) {
+          const float4 w = *reinterpret_cast<const float4*>(uv + o * Ca4 + c0);
+          acc[o] = fmaf(xv.x, w.x, fmaf(xv.y, w.y, fmaf(xv.z, w.z, fmaf(xv.w, w.w, acc[o]))));
+        }
+      }
     }
-    __syncthreads();
-    if (rl < RB && r0 + rl < rows) {
-      float acc = 0.f;
-      const float* xr = xs + rl * Ca;
-      const float* w = uv + o * (Ca + 1);
-      for (int cc = 0; cc < Ca; ++cc) acc = fmaf(xr[cc], w[cc], acc);
-      uvx[(r0 + rl) * O + o] = acc + cadd;
-    }
+    float* dst = uvx + r * O;
+#pragma unroll
+    for (int o = 0; o < OP; ++o)
+      if (o < O) dst[o] = acc[o] + (o < M ? __ldg(c + o) : 0.f);
   }
 }
 
@@ -53,14 +68,16 @@ int launch_assign_logits(const fgc_conv_shape* s, const float* x, const float* u
                          const float* c, float* uvx, cudaStream_t st) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   const int O = 2 * s->M;
-  const int RB = kThreads / O;
-  const size_t smem = (static_cast<size_t>(O) * (s->Ca + 1) + static_cast<size_t>(RB) * s->Ca) * 4;
-  int64_t blocks = (rows + RB - 1) / RB;
+  const size_t smem = static_cast<size_t>(O) * ((s->Ca + 3) & ~3) * 4;
+  int64_t blocks = (rows + 127) / 128;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  assign_logits_kernel<<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(
-      x, u, v, c, uvx, rows, s->Cin, s->Ca0, s->Ca, s->M);
+  const unsigned g = static_cast<unsigned>(blocks);
+  if (O <= 8) assign_logits_kernel<8><<<g, 128, smem, st>>>(x, u, v, c, uvx, rows, s->Cin, s->Ca0, s->Ca, s->M);
+  else if (O <= 16) assign_logits_kernel<16><<<g, 128, smem, st>>>(x, u, v, c, uvx, rows, s->Cin, s->Ca0, s->Ca, s->M);
+  else if (O <= 18) assign_logits_kernel<18><<<g, 128, smem, st>>>(x, u, v, c, uvx, rows, s->Cin, s->Ca0, s->Ca, s->M);
+  else assign_logits_kernel<32><<<g, 128, smem, st>>>(x, u, v, c, uvx, rows, s->Cin, s->Ca0, s->Ca, s->M);
   FGC_LAUNCHED("assign_logits_kernel");
   return FGC_OK;
 }
