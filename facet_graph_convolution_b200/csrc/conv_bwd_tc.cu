@@ -21,9 +21,9 @@ namespace fgc {
 
 namespace {
 
-constexpr int kAggWarpsW = 8;
+constexpr int kAggWarpsW = kAggW;
 constexpr int kEpiWarpsW = 4;
-constexpr int kThreadsW = (kAggWarpsW + kEpiWarpsW + 1) * 32;  // 416
+constexpr int kThreadsW = (kAggWarpsW + kEpiWarpsW + 1) * 32;
 constexpr int kPassW = 32;
 
 // |x| max as ordered uint bits (non-negative floats order like unsigned ints)
@@ -116,34 +116,36 @@ bwd_w_tc_kernel(const WParams p) {
     // =========================================================== aggregators
     float* qs = qs_all + warp * AggQ<M>::QS_FLOATS;
     int* nbr = nbr_all + warp * AggQ<M>::NBR_INTS;
-    const int grp = lane >> 3, gl = lane & 7;
-    const int j = warp * 4 + grp;            // row within the pass
+    const int grp = lane / kLPG, gl = lane % kLPG;
+    const int j = warp * kFPW + grp;         // row within the pass
     const int kg = j >> 3, jr = j & 7;
-    float gb[8];
+    float gb[2 * kCP];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gb[i] = 0.f;
+    for (int i = 0; i < 2 * kCP; ++i) gb[i] = 0.f;
     int it = 0;
     for (int64_t pass = blockIdx.x; pass < p.npasses; pass += gridDim.x, ++it) {
       const int64_t r = pass * kPassW + j;
-      float2 acc[M][4];
+      float2 acc[M][kCP];
 #pragma unroll
       for (int m = 0; m < M; ++m)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[m][i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < kCP; ++i) acc[m][i] = make_float2(0.f, 0.f);
       int cnt = 0;
-      float dv[2][M];
-      tc_aggregate<M, MODE_FWD>(p.src, pass * kPassW + warp * 4, qs, nbr, lane, acc, cnt, dv);
-      // gz row of this facet (channels 4gl..4gl+3 and 32+4gl..32+4gl+3)
-      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-      if (r < p.src.rows) {
-        const float4* gr = reinterpret_cast<const float4*>(p.gy + r * 64);
-        g0 = __ldg(gr + gl);
-        g1 = __ldg(gr + 8 + gl);
+      float dv[kPairIters][M];
+      tc_aggregate<M, MODE_FWD>(p.src, pass * kPassW + warp * kFPW, qs, nbr, lane, acc, cnt, dv);
+      // gz row of this facet: the lane's float4(s) of gy
+      float4 g[kF4];
+#pragma unroll
+      for (int i = 0; i < kF4; ++i) {
+        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < p.src.rows) g[i] = __ldg(reinterpret_cast<const float4*>(p.gy + r * 64) + gl + kLPG * i);
       }
       const float fl = (r < p.src.rows && (cnt > 0 || !p.bias_mask)) ? 1.f : 0.f;
-      gb[0] = fmaf(fl, g0.x, gb[0]), gb[1] = fmaf(fl, g0.y, gb[1]), gb[2] = fmaf(fl, g0.z, gb[2]);
-      gb[3] = fmaf(fl, g0.w, gb[3]), gb[4] = fmaf(fl, g1.x, gb[4]), gb[5] = fmaf(fl, g1.y, gb[5]);
-      gb[6] = fmaf(fl, g1.z, gb[6]), gb[7] = fmaf(fl, g1.w, gb[7]);
+#pragma unroll
+      for (int i = 0; i < kF4; ++i) {
+        gb[4 * i] = fmaf(fl, g[i].x, gb[4 * i]), gb[4 * i + 1] = fmaf(fl, g[i].y, gb[4 * i + 1]);
+        gb[4 * i + 2] = fmaf(fl, g[i].z, gb[4 * i + 2]), gb[4 * i + 3] = fmaf(fl, g[i].w, gb[4 * i + 3]);
+      }
       const float gsc = (cnt ? 1.f / static_cast<float>(cnt) : 0.f) * sg;
 
       const int st = it & 1;
@@ -154,44 +156,47 @@ bwd_w_tc_kernel(const WParams p) {
       uint8_t* bh = base + 2 * Cfg::A_PLANE;
       uint8_t* bl = bh + Cfg::B_PLANE;
       // element (row j, block m, channel c): ((kg*M + m)*8 + jr)*128 + ((c/8 ^ jr)*16) + (c%8)*2
-      const int u0 = ((gl >> 1) ^ jr) * 16 + (gl & 1) * 8;        // channels 4gl..4gl+3
-      const int u1 = (((4 + (gl >> 1))) ^ jr) * 16 + (gl & 1) * 8;  // channels 32+4gl..
+      int uo[kF4];
+#pragma unroll
+      for (int i = 0; i < kF4; ++i) {
+        const int c = 4 * (gl + kLPG * i);
+        uo[i] = ((c >> 3) ^ jr) * 16 + (c & 7) * 2;
+      }
 #pragma unroll
       for (int m = 0; m < M; ++m) {
-        uint32_t h[4], l[4];
+        uint32_t h[kCP], l[kCP];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_pair(acc[m][i].x * ss, acc[m][i].y * ss, h[i], l[i]);
+        for (int i = 0; i < kCP; ++i) split_pair(acc[m][i].x * ss, acc[m][i].y * ss, h[i], l[i]);
         const int rowoff = ((kg * M + m) * 8 + jr) * 128;
-        *reinterpret_cast<uint2*>(ah + rowoff + u0) = make_uint2(h[0], h[1]);
-        *reinterpret_cast<uint2*>(ah + rowoff + u1) = make_uint2(h[2], h[3]);
-        *reinterpret_cast<uint2*>(al + rowoff + u0) = make_uint2(l[0], l[1]);
-        *reinterpret_cast<uint2*>(al + rowoff + u1) = make_uint2(l[2], l[3]);
+#pragma unroll
+        for (int i = 0; i < kF4; ++i) {
+          *reinterpret_cast<uint2*>(ah + rowoff + uo[i]) = make_uint2(h[2 * i], h[2 * i + 1]);
+          *reinterpret_cast<uint2*>(al + rowoff + uo[i]) = make_uint2(l[2 * i], l[2 * i + 1]);
+        }
       }
       {
-        uint32_t h[4], l[4];
-        split_pair(g0.x * gsc, g0.y * gsc, h[0], l[0]);
-        split_pair(g0.z * gsc, g0.w * gsc, h[1], l[1]);
-        split_pair(g1.x * gsc, g1.y * gsc, h[2], l[2]);
-        split_pair(g1.z * gsc, g1.w * gsc, h[3], l[3]);
         const int rowoff = (kg * 8 + jr) * 128;
-        *reinterpret_cast<uint2*>(bh + rowoff + u0) = make_uint2(h[0], h[1]);
-        *reinterpret_cast<uint2*>(bh + rowoff + u1) = make_uint2(h[2], h[3]);
-        *reinterpret_cast<uint2*>(bl + rowoff + u0) = make_uint2(l[0], l[1]);
-        *reinterpret_cast<uint2*>(bl + rowoff + u1) = make_uint2(l[2], l[3]);
+#pragma unroll
+        for (int i = 0; i < kF4; ++i) {
+          uint32_t h0, l0, h1, l1;
+          split_pair(g[i].x * gsc, g[i].y * gsc, h0, l0);
+          split_pair(g[i].z * gsc, g[i].w * gsc, h1, l1);
+          *reinterpret_cast<uint2*>(bh + rowoff + uo[i]) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(bl + rowoff + uo[i]) = make_uint2(l0, l1);
+        }
       }
       tc::fence_proxy_async_smem();   // generic-proxy writes -> UMMA (async proxy) reads
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars[WB_FULL0 + st]);
     }
     // ---- bias gradient: fixed-order reduction over the 32 facet slots of the CTA
-    asm volatile("bar.sync 2, 256;" ::: "memory");
+    asm volatile("bar.sync 2, %0;" ::"n"(kAggWarpsW * 32) : "memory");
     float* red = qs_all;  // [32 slots][64 channels]
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      red[j * 64 + 4 * gl + i] = gb[i];
-      red[j * 64 + 32 + 4 * gl + i] = gb[4 + i];
-    }
-    asm volatile("bar.sync 2, 256;" ::: "memory");
+    for (int i = 0; i < kF4; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red[j * 64 + 4 * (gl + kLPG * i) + q] = gb[4 * i + q];
+    asm volatile("bar.sync 2, %0;" ::"n"(kAggWarpsW * 32) : "memory");
     if (threadIdx.x < 64) {
       float a = 0.f;
       for (int s = 0; s < 32; ++s) a += red[s * 64 + threadIdx.x];
@@ -270,8 +275,8 @@ bwd_w_tc_kernel(const WParams p) {
 //   da         = q (dq - sum_m q dq)  ->  da_edge[n,k,:],  d_uvx[n,0:M] = sum_k da,  inv_cnt[n]
 // Warps 0-7 aggregate, warp 8/9 own TMEM lane quadrants 0/1 (hi / lo rows: A' writer and D' reader),
 // warp 10 issues the MMAs.  ds travels TMEM -> shared (fp32, 32 x 512) -> registers of the owning lanes.
-constexpr int kSrcAggWarps = 8;
-constexpr int kSrcThreads = (kSrcAggWarps + 3) * 32;  // 352
+constexpr int kSrcAggWarps = kAggW;
+constexpr int kSrcThreads = (kSrcAggWarps + 3) * 32;
 constexpr int kSrcTile = 32;
 
 template <int M>
@@ -346,80 +351,122 @@ bwd_src_tc_kernel(const SParams p) {
     // =========================================================== aggregators
     float* qs = qs_all + warp * AggQ<M>::QS_FLOATS;
     int* nbr = nbr_all + warp * AggQ<M>::NBR_INTS;
-    const int grp = lane >> 3, gl = lane & 7;
-    const int j = warp * 4 + grp;
+    const int grp = lane / kLPG, gl = lane % kLPG;
+    const int j = warp * kFPW + grp;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int64_t wrow0 = tile * kSrcTile + warp * 4;
+      const int64_t wrow0 = tile * kSrcTile + warp * kFPW;
       const int64_t r = wrow0 + grp;
       tc::mbar_wait(&bars[SB_DS_FULL], it & 1);
-      float2 ds2[M][4];
+      float2 ds2[M][kCP];
 #pragma unroll
-      for (int m = 0; m < M; ++m) {
-        const float4 a = *reinterpret_cast<const float4*>(DS + j * Cfg::DS_PITCH + m * 64 + 4 * gl);
-        const float4 b = *reinterpret_cast<const float4*>(DS + j * Cfg::DS_PITCH + m * 64 + 32 + 4 * gl);
-        ds2[m][0] = make_float2(a.x, a.y), ds2[m][1] = make_float2(a.z, a.w);
-        ds2[m][2] = make_float2(b.x, b.y), ds2[m][3] = make_float2(b.z, b.w);
-      }
+      for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int i = 0; i < kF4; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(DS + j * Cfg::DS_PITCH + m * 64 + 4 * (gl + kLPG * i));
+          ds2[m][2 * i] = make_float2(a.x, a.y), ds2[m][2 * i + 1] = make_float2(a.z, a.w);
+        }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars[SB_DS_FREE]);
       int lst0, lst1;
       const int nround = agg_list_bounds<MODE_FWD>(p.src, r, lst0, lst1);
-      float dv[2][M];
+      float dv[kPairIters][M];
       float dux = 0.f;
       for (int kb = 0; kb < nround; kb += kQK) {
         const int nk = min(kQK, nround - kb);
         __syncwarp();
         agg_assign_round<M, MODE_FWD>(p.src, wrow0, kb, nk, lst0, lst1, qs, nbr, lane, dv);
         __syncwarp();
-#pragma unroll 2
-        for (int k = 0; k < nk; ++k) {
-          const int jn = nbr[grp * kQK + k];
-          float2 xp[4];
-          agg_load_row(p.src, jn, gl, xp);
-          float v[M];
+        for (int k0 = 0; k0 < nk; k0 += kUnroll) {
+          float2 xp[kUnroll][kCP];
 #pragma unroll
-          for (int m = 0; m < M; ++m) {
-            float2 t = make_float2(0.f, 0.f);
+          for (int t = 0; t < kUnroll; ++t)
+            agg_load_row(p.src, (k0 + t < nk) ? nbr[grp * kQK + k0 + t] : -1, gl, xp[t]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tc::ffma2(t, ds2[m][i], xp[i]);
-            v[m] = t.x + t.y;
-          }
-          // transpose-reduce over the 8 lanes of the facet: lane gl ends with the total of m == gl
-          {
-            const bool up = (gl & 4) != 0;
+          for (int t = 0; t < kUnroll; ++t) {
+            const int k = k0 + t;
+            float v[M];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            for (int m = 0; m < M; ++m) {
+              float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < kCP; ++i) tc::ffma2(s2, ds2[m][i], xp[t][i]);
+              v[m] = s2.x + s2.y;
+            }
+            // transpose-reduce over the lanes of the facet: the 8 partial sums end up one per lane
+            // (lane gl holds m = gl for 8-lane groups, m = gl >> 1 for 16-lane groups)
+            int mine;
+            float dq;
+            if constexpr (kLPG == 16) {
+              {
+                const bool up = (gl & 8) != 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+              }
+              {
+                const bool up = (gl & 4) != 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
+                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+              }
+              {
+                const bool up = (gl & 2) != 0;
+                const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+                dq = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+              }
+              dq += __shfl_xor_sync(0xffffffffu, dq, 1);
+              mine = gl >> 1;
+            } else {
+              {
+                const bool up = (gl & 4) != 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+              }
+              {
+                const bool up = (gl & 2) != 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
+                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+              }
+              {
+                const bool up = (gl & 1) != 0;
+                const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+                dq = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+              }
+              mine = gl;
+            }
+            const float qv = qs[(grp * kQK + (k < nk ? k : 0)) * MQ + mine];
+            float dot = qv * dq;
+            if constexpr (kLPG == 16) {
+              dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+              dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+              dot += __shfl_xor_sync(0xffffffffu, dot, 8);
+            } else {
+              dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+              dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+              dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            }
+            const float da = qv * (dq - dot);
+            const bool writer = (kLPG == 16) ? ((gl & 1) == 0) : true;
+            if (k < nk) {
+              if (writer && r < p.src.rows && kb + k < p.src.K)
+                p.da_edge[(r * p.src.K + kb + k) * M + mine] = da;
+              dux += da;
             }
           }
-          {
-            const bool up = (gl & 2) != 0;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-          }
-          float dq;
-          {
-            const bool up = (gl & 1) != 0;
-            const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
-            dq = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-          }
-          const float qv = qs[(grp * kQK + k) * MQ + gl];
-          float dot = qv * dq;
-          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-          const float da = qv * (dq - dot);
-          if (r < p.src.rows && kb + k < p.src.K)
-            p.da_edge[(r * p.src.K + kb + k) * M + gl] = da;
-          dux += da;
         }
       }
-      if (r < p.src.rows) p.d_uvx[r * (2 * M) + gl] = dux;
+      if (r < p.src.rows && ((kLPG == 16) ? ((gl & 1) == 0) : true)) p.d_uvx[r * (2 * M) + ((kLPG == 16) ? (gl >> 1) : gl)] = dux;
     }
   } else if (warp < kSrcAggWarps + 2) {
     // =========================================================== TMEM lane owners (quad 0: hi, quad 1: lo)
@@ -430,40 +477,41 @@ bwd_src_tc_kernel(const SParams p) {
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int64_t r = tile * kSrcTile + lane;
       // ---- gz row -> A' (hi or lo plane), scaled by a power of two to [0.5, 1)
-      float g[64];
-      float inv = 0.f;
+      float inv = 0.f, mx = 0.f;
+      const float4* gr = reinterpret_cast<const float4*>(p.gy + r * 64);
       if (r < p.src.rows) {
         int cnt = 0;
         for (int k = 0; k < p.src.K; ++k) cnt += (__ldg(p.src.adj + r * p.src.K + k) != 0);
         inv = cnt ? 1.f / static_cast<float>(cnt) : 0.f;
         if (quad == 0) p.inv_out[r] = inv;
-        const float4* gr = reinterpret_cast<const float4*>(p.gy + r * 64);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float4 t = __ldg(gr + i);
-          g[4 * i] = t.x * inv, g[4 * i + 1] = t.y * inv, g[4 * i + 2] = t.z * inv, g[4 * i + 3] = t.w * inv;
+          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) g[i] = 0.f;
+        mx *= inv;
       }
-      float mx = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, fabsf(g[i]));
       int E = (__float_as_int(mx) >> 23) & 0xFF;
       E = min(max(E, 16), 240);
-      const float sc = __int_as_float((253 - E) << 23);
+      const float sc = __int_as_float((253 - E) << 23) * inv;
       const float unsc = __int_as_float((E + 1) << 23) * wun;
-      uint32_t w[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        uint32_t h, l;
-        split_pair(g[2 * i] * sc, g[2 * i + 1] * sc, h, l);
-        w[i] = quad == 0 ? h : l;
-      }
       tc::mbar_wait(&bars[SB_A_FREE], (it & 1) ^ 1);
       tc::tc_fence_after_sync();
-      tc::tmem_st32(tmem + lane_base, w);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < p.src.rows) t = __ldg(gr + half * 8 + i);
+          uint32_t h0, l0, h1, l1;
+          split_pair(t.x * sc, t.y * sc, h0, l0);
+          split_pair(t.z * sc, t.w * sc, h1, l1);
+          w[2 * i] = quad == 0 ? h0 : l0;
+          w[2 * i + 1] = quad == 0 ? h1 : l1;
+        }
+        tc::tmem_st16(tmem + lane_base + half * 16, w);
+      }
       tc::tc_wait_st();
       tc::tc_fence_before_sync();
       __syncwarp();

@@ -28,9 +28,9 @@ namespace {
 constexpr int kCw = 64;            // aggregation channels handled by this kernel
 constexpr int kTile = 64;          // facets per tile
 constexpr int kPass = 32;          // rows per staging pass
-constexpr int kAggWarps = 8;
+constexpr int kAggWarps = kAggW;     // 32 / kFPW warps cover one pass
 constexpr int kMoverWarps = 4;
-constexpr int kTcThreads = (kAggWarps + kMoverWarps + 1) * 32;  // 416
+constexpr int kTcThreads = (kAggWarps + kMoverWarps + 1) * 32;
 
 template <int M, int COUT>
 struct TcCfg {
@@ -51,8 +51,8 @@ struct TcCfg {
   static constexpr int OFF_STG_H = OFF_W + W_BYTES;
   static constexpr int OFF_STG_L = OFF_STG_H + kPass * STG_PITCH * 4;
   static constexpr int OFF_Q = OFF_STG_L + kPass * STG_PITCH * 4;
-  static constexpr int OFF_NBR = OFF_Q + kAggWarps * 4 * kQK * MQ * 4;
-  static constexpr int OFF_EX = OFF_NBR + kAggWarps * 4 * kQK * 4;
+  static constexpr int OFF_NBR = OFF_Q + kAggWarps * AggQ<M>::QS_FLOATS * 4;
+  static constexpr int OFF_EX = OFF_NBR + kAggWarps * AggQ<M>::NBR_INTS * 4;
   static constexpr int OFF_ROW = OFF_EX + kTile * (EXW + 1) * 4;   // rowscale[2][64], rowflag[2][64]
   static constexpr int OFF_BAR = OFF_ROW + 2 * 2 * kTile * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
@@ -128,35 +128,36 @@ conv_fwd_tc_kernel(const TcParams p) {
 
   if (warp < kAggWarps) {
     // =========================================================== aggregators
-    float* qs = qs_all + warp * 4 * kQK * Cfg::MQ;
-    int* nbr = nbr_all + warp * 4 * kQK;
-    const int grp = lane >> 3;       // facet within the warp's 4
-    const int gl = lane & 7;         // lane within the 8-lane group
+    float* qs = qs_all + warp * AggQ<M>::QS_FLOATS;
+    int* nbr = nbr_all + warp * AggQ<M>::NBR_INTS;
+    const int grp = lane / kLPG;     // facet within the warp
+    const int gl = lane % kLPG;      // lane within the facet's group
     uint32_t empty_parity = 1;       // producer convention: the first wait falls through
     int it = 0;
     const AggSrc src{p.x, p.Cin, p.adj, p.uvx, p.N, p.K, p.rows, p.rev_ptr, p.rev_edge, p.inv, p.da_edge};
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       for (int pass = 0; pass < 2; ++pass) {
-        const int prow = warp * 4 + grp;                       // row within the pass (0..31)
+        const int prow = warp * kFPW + grp;                       // row within the pass (0..31)
         const int trow = pass * kPass + prow;                  // row within the tile
         const int64_t r = tile * kTile + trow;                 // global row of this lane's facet
-        float2 acc[M][4];
+        float2 acc[M][kCP];
 #pragma unroll
         for (int m = 0; m < M; ++m)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[m][i] = make_float2(0.f, 0.f);
+          for (int i = 0; i < kCP; ++i) acc[m][i] = make_float2(0.f, 0.f);
         int cnt = 0;
-        float dv[2][M];           // TGT: per-lane partial sums of da_edge -> d_uvx[:, M:2M]
+        float dv[kPairIters][M];  // TGT: per-lane partial sums of da_edge -> d_uvx[:, M:2M]
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < kPairIters; ++h)
 #pragma unroll
           for (int m = 0; m < M; ++m) dv[h][m] = 0.f;
-        tc_aggregate<M, MODE>(src, tile * kTile + pass * kPass + warp * 4, qs, nbr, lane, acc, cnt, dv);
+        const int64_t wrow0 = tile * kTile + pass * kPass + warp * kFPW;
+        tc_aggregate<M, MODE>(src, wrow0, qs, nbr, lane, acc, cnt, dv);
         if constexpr (MODE == MODE_TGT) {
           // d_uvx[t, M + m] = sum of da_edge over the in-edges of t: reduce the 16 lanes of a facet
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int64_t rf = tile * kTile + pass * kPass + warp * 4 + (lane >> 4) + 2 * h;
+          for (int h = 0; h < kPairIters; ++h) {
+            const int64_t rf = wrow0 + (lane >> 4) + 2 * h;
 #pragma unroll
             for (int m = 0; m < M; ++m) {
               float t = dv[h][m];
@@ -173,10 +174,9 @@ conv_fwd_tc_kernel(const TcParams p) {
 #pragma unroll
         for (int m = 0; m < M; ++m)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(acc[m][i].x), fabsf(acc[m][i].y)));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+          for (int i = 0; i < kCP; ++i) mx = fmaxf(mx, fmaxf(fabsf(acc[m][i].x), fabsf(acc[m][i].y)));
+#pragma unroll
+        for (int o = 1; o < kLPG; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         int E = (__float_as_int(mx) >> 23) & 0xFF;
         E = min(max(E, 16), 240);                                  // keep both scales normal
         const float sc = __int_as_float((253 - E) << 23);          // 2^(126-E)
@@ -188,14 +188,14 @@ conv_fwd_tc_kernel(const TcParams p) {
         uint32_t* rl = stg_l + prow * Cfg::STG_PITCH;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-          uint32_t h[4], l[4];
+          uint32_t h[kCP], l[kCP];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) split_pair(acc[m][i].x * sc, acc[m][i].y * sc, h[i], l[i]);
-          // channels 4gl..4gl+3 -> words m*32 + 2gl, +1 ; channels 32+4gl.. -> words m*32 + 16 + 2gl, +1
-          *reinterpret_cast<uint2*>(rh + m * 32 + 2 * gl) = make_uint2(h[0], h[1]);
-          *reinterpret_cast<uint2*>(rh + m * 32 + 16 + 2 * gl) = make_uint2(h[2], h[3]);
-          *reinterpret_cast<uint2*>(rl + m * 32 + 2 * gl) = make_uint2(l[0], l[1]);
-          *reinterpret_cast<uint2*>(rl + m * 32 + 16 + 2 * gl) = make_uint2(l[2], l[3]);
+          for (int i = 0; i < kCP; ++i) split_pair(acc[m][i].x * sc, acc[m][i].y * sc, h[i], l[i]);
+#pragma unroll
+          for (int i = 0; i < kF4; ++i) {   // float4 i of the lane = channels 4(gl + kLPG i) .. +3
+            *reinterpret_cast<uint2*>(rh + agg_word(m, gl, 2 * i)) = make_uint2(h[2 * i], h[2 * i + 1]);
+            *reinterpret_cast<uint2*>(rl + agg_word(m, gl, 2 * i)) = make_uint2(l[2 * i], l[2 * i + 1]);
+          }
         }
         if (gl == 0) {
           const float inv = (MODE == MODE_TGT) ? 1.f : (cnt ? 1.f / static_cast<float>(cnt) : 0.f);

@@ -1,6 +1,8 @@
 // Shared aggregation stage of the tensor-core kernels: soft assignments + q-weighted sum of gathered
-// rows for the 4 facets of a warp (8 lanes per facet, each lane owns channels 4l..4l+3 and
-// 32+4l..32+4l+3 of the 64-wide rows), packed fp32x2 FMAs.
+// rows.  A group of kLPG lanes serves one facet (lane l of the group owns the float4 number l of the
+// 64-channel row, plus l + kLPG, ... when kLPG < 16), a warp serves kFPW = 32 / kLPG facets and
+// 32 / kFPW warps cover one 32-row pass.  Row loads are 16-byte, fully coalesced per group, issued
+// kUnroll rows ahead of the packed fp32x2 FMAs to keep many L2 requests in flight.
 #pragma once
 
 #include "common.cuh"
@@ -11,6 +13,14 @@ namespace fgc {
 constexpr int MODE_FWD = 0;  // rows gathered through the adjacency (source-centric)
 constexpr int MODE_TGT = 1;  // rows gathered through the reversed adjacency (target-centric)
 constexpr int kQK = 16;      // neighbour slots per assignment round
+
+constexpr int kLPG = 16;                 // lanes per facet
+constexpr int kFPW = 32 / kLPG;          // facets per warp
+constexpr int kF4 = 16 / kLPG;           // float4 per lane and row
+constexpr int kCP = 2 * kF4;             // channel pairs per lane
+constexpr int kAggW = 32 / kFPW;         // aggregator warps per 32-row pass
+constexpr int kUnroll = (kLPG == 16) ? 8 : 4;
+constexpr int kPairIters = (kFPW * kQK + 31) / 32;  // (facet, slot) pairs per lane and round
 
 struct AggSrc {
   const float* x;        // gathered rows (x for FWD, gy for TGT), row stride ldx, 64 channels used
@@ -29,9 +39,14 @@ struct AggSrc {
 template <int M>
 struct AggQ {
   static constexpr int MQ = (M + 3) & ~3;            // q row stride in floats
-  static constexpr int QS_FLOATS = 4 * kQK * MQ;     // per warp
-  static constexpr int NBR_INTS = 4 * kQK;           // per warp
+  static constexpr int QS_FLOATS = kFPW * kQK * MQ;  // per warp
+  static constexpr int NBR_INTS = kFPW * kQK;        // per warp
 };
+
+// word (two fp16) index inside a staged row of M*32 words for this lane's pair p of weight m
+__device__ __forceinline__ int agg_word(int m, int gl, int p) { return m * 32 + 2 * (gl + kLPG * (p >> 1)) + (p & 1); }
+// first channel of this lane's pair p
+__device__ __forceinline__ int agg_channel(int gl, int p) { return 4 * (gl + kLPG * (p >> 1)) + 2 * (p & 1); }
 
 // list bounds of this lane's facet and the warp-uniform number of list entries to walk
 template <int MODE>
@@ -46,25 +61,27 @@ __device__ __forceinline__ int agg_list_bounds(const AggSrc& p, int64_t r, int& 
     }
   }
   int nround = lst1 - lst0;
-  nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, 8));
-  nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, 16));
+#pragma unroll
+  for (int o = kLPG; o < 32; o <<= 1) nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, o));
   return nround;
 }
 
-// soft assignments of one round (list entries kb..kb+nk-1 of the warp's 4 facets): lane per
+// soft assignments of one round (list entries kb..kb+nk-1 of the warp's facets): lane per
 // (facet, slot) pair, pair = lane + 32h, facet = pair / 16.  qs[f][k][0..M) receives q (already
 // multiplied by inv_cnt[source] in TGT mode), nbr[f][k] the gathered row, -1 = padding,
 // -2 = non-zero id outside the patch (counts as a neighbour, contributes nothing).
 template <int M, int MODE>
 __device__ __forceinline__ void agg_assign_round(const AggSrc& p, int64_t wrow0, int kb, int nk, int lst0,
-                                                 int lst1, float* qs, int* nbr, int lane, float (&dv)[2][M]) {
+                                                 int lst1, float* qs, int* nbr, int lane,
+                                                 float (&dv)[kPairIters][M]) {
   constexpr int MQ = AggQ<M>::MQ;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < kPairIters; ++h) {
     const int f = (lane >> 4) + 2 * h, k = lane & 15;
     const int64_t rf = wrow0 + f;
-    const int f0 = __shfl_sync(0xffffffffu, lst0, f * 8);
-    const int f1 = __shfl_sync(0xffffffffu, lst1, f * 8);
+    const int f0 = __shfl_sync(0xffffffffu, lst0, (f * kLPG) & 31);
+    const int f1 = __shfl_sync(0xffffffffu, lst1, (f * kLPG) & 31);
+    if (f >= kFPW) continue;  // (only when kFPW == 1)
     int row = -1;
     float a[M];
     bool have = false;
@@ -86,11 +103,29 @@ __device__ __forceinline__ void agg_assign_round(const AggSrc& p, int64_t wrow0,
         ux = p.uvx + static_cast<int64_t>(row) * (2 * M);
         vx = p.uvx + rf * (2 * M) + M;
         const float* de = p.da_edge + static_cast<int64_t>(e) * M;
+        if constexpr (M % 4 == 0) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) dv[h][m] += __ldg(de + m);
+          for (int m = 0; m < M; m += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(de + m));
+            dv[h][m] += t.x, dv[h][m + 1] += t.y, dv[h][m + 2] += t.z, dv[h][m + 3] += t.w;
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < M; ++m) dv[h][m] += __ldg(de + m);
+        }
       }
+      if constexpr (M % 4 == 0) {
 #pragma unroll
-      for (int m = 0; m < M; ++m) a[m] = __ldg(ux + m) + (vvalid ? __ldg(vx + m) : 0.f);
+        for (int m = 0; m < M; m += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(ux + m));
+          float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (vvalid) w = __ldg(reinterpret_cast<const float4*>(vx + m));
+          a[m] = t.x + w.x, a[m + 1] = t.y + w.y, a[m + 2] = t.z + w.z, a[m + 3] = t.w + w.w;
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < M; ++m) a[m] = __ldg(ux + m) + (vvalid ? __ldg(vx + m) : 0.f);
+      }
       float mx = a[0];
 #pragma unroll
       for (int m = 1; m < M; ++m) mx = fmaxf(mx, a[m]);
@@ -111,32 +146,47 @@ __device__ __forceinline__ void agg_assign_round(const AggSrc& p, int64_t wrow0,
     }
     float* qd = qs + (f * kQK + k) * MQ;
 #pragma unroll
-    for (int m = 0; m < MQ; ++m) qd[m] = (m < M) ? a[m < M ? m : 0] : 0.f;
+    for (int m4 = 0; m4 < MQ; m4 += 4) {
+      float4 t;
+      t.x = (m4 < M) ? a[m4 < M ? m4 : 0] : 0.f;
+      t.y = (m4 + 1 < M) ? a[m4 + 1 < M ? m4 + 1 : 0] : 0.f;
+      t.z = (m4 + 2 < M) ? a[m4 + 2 < M ? m4 + 2 : 0] : 0.f;
+      t.w = (m4 + 3 < M) ? a[m4 + 3 < M ? m4 + 3 : 0] : 0.f;
+      *reinterpret_cast<float4*>(qd + m4) = t;
+    }
     nbr[f * kQK + k] = row;
   }
 }
 
-// the two float4 of gathered row j this lane owns, as 4 channel pairs (zeros for padding)
-__device__ __forceinline__ void agg_load_row(const AggSrc& p, int j, int gl, float2 (&xp)[4]) {
-  float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-  if (j >= 0) {
-    const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(j) * p.ldx);
-    x0 = __ldg(xr + gl);
-    x1 = __ldg(xr + 8 + gl);
+// this lane's float4(s) of gathered row j as channel pairs (zeros for padding)
+__device__ __forceinline__ void agg_load_row(const AggSrc& p, int j, int gl, float2 (&xp)[kCP]) {
+#pragma unroll
+  for (int i = 0; i < kF4; ++i) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j >= 0) t = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(j) * p.ldx) + gl + kLPG * i);
+    xp[2 * i] = make_float2(t.x, t.y);
+    xp[2 * i + 1] = make_float2(t.z, t.w);
   }
-  xp[0] = make_float2(x0.x, x0.y), xp[1] = make_float2(x0.z, x0.w);
-  xp[2] = make_float2(x1.x, x1.y), xp[3] = make_float2(x1.z, x1.w);
+}
+
+template <int M>
+__device__ __forceinline__ void agg_load_q(const float* qk, float (&q)[AggQ<M>::MQ]) {
+#pragma unroll
+  for (int m4 = 0; m4 < AggQ<M>::MQ; m4 += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(qk + m4);
+    q[m4] = t.x, q[m4 + 1] = t.y, q[m4 + 2] = t.z, q[m4 + 3] = t.w;
+  }
 }
 
 // acc[m][i] += sum over the facet's neighbour list of q[.,m] * row[channel pair i]
-// wrow0 = global row of the warp's first facet; lanes 8g..8g+7 serve facet wrow0 + g.
+// wrow0 = global row of the warp's first facet; lanes kLPG*g .. serve facet wrow0 + g.
 // cnt   = number of non-padding list entries (FWD: non-zero adjacency ids).
 // dv    = TGT: per-lane partial sums of da_edge (pair lane+32h belongs to facet (lane>>4)+2h).
 template <int M, int MODE>
 __device__ __forceinline__ void tc_aggregate(const AggSrc& p, int64_t wrow0, float* qs, int* nbr, int lane,
-                                             float2 (&acc)[M][4], int& cnt, float (&dv)[2][M]) {
+                                             float2 (&acc)[M][kCP], int& cnt, float (&dv)[kPairIters][M]) {
   constexpr int MQ = AggQ<M>::MQ;
-  const int grp = lane >> 3, gl = lane & 7;
+  const int grp = lane / kLPG, gl = lane % kLPG;
   int lst0, lst1;
   const int nround = agg_list_bounds<MODE>(p, wrow0 + grp, lst0, lst1);
   for (int kb = 0; kb < nround; kb += kQK) {
@@ -144,24 +194,26 @@ __device__ __forceinline__ void tc_aggregate(const AggSrc& p, int64_t wrow0, flo
     __syncwarp();
     agg_assign_round<M, MODE>(p, wrow0, kb, nk, lst0, lst1, qs, nbr, lane, dv);
     __syncwarp();
-#pragma unroll 4
-    for (int k = 0; k < nk; ++k) {
-      const int j = nbr[grp * kQK + k];
-      cnt += (j != -1);
-      float2 xp[4];
-      agg_load_row(p, j, gl, xp);
-      const float* qk = qs + (grp * kQK + k) * MQ;
-      float q[MQ];
+    for (int k0 = 0; k0 < nk; k0 += kUnroll) {
+      // issue the row loads of kUnroll neighbours before any of them is consumed
+      float2 xp[kUnroll][kCP];
+      int jj[kUnroll];
 #pragma unroll
-      for (int m4 = 0; m4 < MQ; m4 += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(qk + m4);
-        q[m4] = t.x, q[m4 + 1] = t.y, q[m4 + 2] = t.z, q[m4 + 3] = t.w;
+      for (int t = 0; t < kUnroll; ++t) {
+        jj[t] = (k0 + t < nk) ? nbr[grp * kQK + k0 + t] : -1;
+        agg_load_row(p, jj[t], gl, xp[t]);
       }
 #pragma unroll
-      for (int m = 0; m < M; ++m) {
-        const float2 qq = make_float2(q[m], q[m]);
+      for (int t = 0; t < kUnroll; ++t) {
+        cnt += (jj[t] != -1);
+        float q[MQ];
+        agg_load_q<M>(qs + (grp * kQK + ((k0 + t < nk) ? k0 + t : 0)) * MQ, q);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tc::ffma2(acc[m][i], qq, xp[i]);
+        for (int m = 0; m < M; ++m) {
+          const float2 qq = make_float2(q[m], q[m]);
+#pragma unroll
+          for (int i = 0; i < kCP; ++i) tc::ffma2(acc[m][i], qq, xp[t][i]);
+        }
       }
     }
   }
