@@ -78,8 +78,21 @@ def kernel_bytes(name, n):
         "bwd_tgt_kernel": 4 * n * (C_OUT + C_IN) + p,
         "bwd_w_kernel": 4 * n * (C_IN + K_NEIGH + C_OUT) + p,
         "logits_bwd_kernel": 4 * n * 2 * C_IN,
+        "logits_bwd_x_kernel": 4 * n * 2 * C_IN,
+        "logits_bwd_p_kernel": 4 * n * C_IN,
+        "absmax_kernel": 4 * n * C_IN,
     }
-    return table.get(name)
+    return table.get(name.replace("_tc_kernel", "_kernel"))
+
+
+def measured_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    capture of this workload (profiles/traffic.json, written by profiles/summarize.py), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t["kernels"].get(name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -283,19 +296,22 @@ def main():
         nm, tot, cnt = ln.split()
         kernels[nm] = {"ms_per_launch": float(tot) / int(cnt), "launches_per_step": int(cnt) / args.steps,
                        "ms_per_step": float(tot) / args.steps}
+        kb = kernel_bytes(nm, n)
+        if kb:
+            gbs = kb / (kernels[nm]["ms_per_launch"] * 1e-3) / 1e9
+            kernels[nm].update({"algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak_gbs})
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     roofline = None
     if dom:
         kb = kernel_bytes(dom, n)
         ach = (kb / (kernels[dom]["ms_per_launch"] * 1e-3)) / 1e9 if kb else None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
-                    "frac": (ach / peak_gbs) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (ach / peak_gbs) if ach else None, "traffic": measured_traffic(dom),
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kb, "ms_per_launch": kernels[dom]["ms_per_launch"]}
-        fwd_ms = sum(v["ms_per_step"] for k, v in kernels.items()
-                     if k in ("assign_logits_kernel", "transpose_w_kernel", "conv_fwd_kernel")) / 2.0
     layer = {}
     if kernels:
-        f_ms = kernels.get("conv_fwd_kernel", {}).get("ms_per_step", 0.0)
+        f_ms = kernels.get("conv_fwd_tc_kernel", kernels.get("conv_fwd_kernel", {})).get("ms_per_step", 0.0)
         tot_ms = sum(v["ms_per_step"] for v in kernels.values())
         layer = {"fwd_main_kernel_ms": f_ms, "fwd_main_kernel_frac_of_hbm_roofline":
                  (bytes_fwd(n) / (f_ms * 1e-3) / 1e9 / peak_gbs) if f_ms else None,

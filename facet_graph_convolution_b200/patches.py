@@ -1,0 +1,185 @@
+"""Patch-sharded inference: the multi-GPU axis of the hot path.
+
+The reference cuts a mesh into patches on the host and runs them *sequentially* through one
+session (Code/train.py:100-126): every patch has its own adjacency pyramid, its own
+``normalizeTensor`` global mean and no dependence on any other patch.  Here the same patch list
+is dealt to one process per GPU; each rank runs whole patches with no collective on the data
+path, and the per-facet results are merged exactly as the reference does on the host:
+
+    out  = normals[oldToNew][:num_real]            train.py:117-121
+    acc[patch_indices] += out                      train.py:126
+    pred = normalize(acc)  (two passes, +1e-8, float64)   train.py:136, utils.py:26-35
+
+Patches carry a ``core`` mask when they were cut with a halo (synthetic generators below): halo
+facets give the network its receptive field, are computed redundantly, and are not written back.
+Nothing here touches CUDA directly; the per-patch forward is a callable so the sharding / merge
+logic is testable on CPU with ``gloo`` (tests/test_multi_rank_cpu.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import mesh
+
+
+@dataclass
+class Patch:
+    x: np.ndarray                      # [N0, Cin] float32, node order of the pyramid (fake rows = 0)
+    adjs: List[np.ndarray]             # [N_l, K] int32 per level, reference layout
+    face_ids: np.ndarray               # [num_real] int64: global facet id of every real row (train.py:126)
+    perm: Optional[np.ndarray] = None  # [N0] int32 oldToNew (train.py:117-121); None = identity
+    core: Optional[np.ndarray] = None  # [num_real] bool: rows written back (halo rows dropped)
+
+    @property
+    def num_real(self) -> int:
+        return int(self.face_ids.shape[0])
+
+    @property
+    def cost(self) -> int:
+        return int(self.x.shape[0])
+
+
+def partition(costs: Sequence[int], world: int) -> List[List[int]]:
+    """Greedy longest-processing-time assignment of patches to ranks; deterministic
+    (ties broken by patch index) so every rank derives the same plan without communication."""
+    order = sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i))
+    load = [0] * world
+    plan: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        plan[r].append(i)
+        load[r] += int(costs[i])
+    for p in plan:
+        p.sort()
+    return plan
+
+
+def patch_output(p: Patch, normals: np.ndarray):
+    """Un-permute / trim one patch's network output (train.py:117-121); returns (ids, rows)."""
+    out = np.asarray(normals).reshape(-1, normals.shape[-1])
+    if p.perm is not None:
+        out = out[p.perm]
+    out = out[: p.num_real]
+    ids = p.face_ids
+    if p.core is not None:
+        out, ids = out[p.core], ids[p.core]
+    return ids, out
+
+
+def host_normalize(a: np.ndarray) -> np.ndarray:
+    """reference Code/utils.py:26-35 applied as train.py:136 does: two passes, +1e-8, float64."""
+    a = np.asarray(a, np.float64)
+    for _ in range(2):
+        n = np.sqrt((a * a).sum(axis=1))[:, None] + 0.00000001
+        a = a * (1 / n)
+    return a
+
+
+def merge(num_faces: int, contributions) -> np.ndarray:
+    """Sum overlapping per-facet normals then renormalise (train.py:98,126,136)."""
+    acc = np.zeros((num_faces, 3), np.float64)
+    for ids, rows in contributions:
+        np.add.at(acc, np.asarray(ids, np.int64), np.asarray(rows, np.float64))
+    return host_normalize(acc)
+
+
+def run_local(patches: Sequence[Patch], my: Sequence[int], forward: Callable[[Patch], np.ndarray]):
+    """Runs this rank's patches; returns the concatenated (ids[int64], rows[float32]) it owns."""
+    ids, rows = [np.zeros((0,), np.int64)], [np.zeros((0, 3), np.float32)]
+    for i in my:
+        a, b = patch_output(patches[i], forward(patches[i]))
+        ids.append(np.asarray(a, np.int64))
+        rows.append(np.asarray(b, np.float32))
+    return np.concatenate(ids), np.concatenate(rows)
+
+
+def gather_to_all(ids: np.ndarray, rows: np.ndarray, device=None):
+    """all_gather of ragged per-rank results (no data-path collective happened before this point).
+    Works with gloo (CPU tensors) and nccl (``device`` = the rank's CUDA device)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [(ids, rows)]
+    world = dist.get_world_size()
+    dev = device if device is not None else "cpu"
+    n = torch.tensor([ids.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    cap = max(int(t.item()) for t in ns)
+    pid = torch.zeros(cap, dtype=torch.int64, device=dev)
+    prow = torch.zeros(cap, 3, dtype=torch.float32, device=dev)
+    pid[: ids.shape[0]] = torch.from_numpy(ids).to(dev)
+    prow[: rows.shape[0]] = torch.from_numpy(np.ascontiguousarray(rows, np.float32)).to(dev)
+    gid = [torch.zeros_like(pid) for _ in range(world)]
+    grow = [torch.zeros_like(prow) for _ in range(world)]
+    dist.all_gather(gid, pid)
+    dist.all_gather(grow, prow)
+    out = []
+    for r in range(world):
+        k = int(ns[r].item())
+        out.append((gid[r][:k].cpu().numpy(), grow[r][:k].cpu().numpy()))
+    return out
+
+
+def infer_sharded(patches: Sequence[Patch], num_faces: int, forward: Callable[[Patch], np.ndarray],
+                  rank: int = 0, world: int = 1, device=None) -> np.ndarray:
+    """Patch-parallel inference: partition -> local forwards -> gather -> host merge."""
+    plan = partition([p.cost for p in patches], world)
+    ids, rows = run_local(patches, plan[rank], forward)
+    return merge(num_faces, gather_to_all(ids, rows, device))
+
+
+# ----------------------------------------------------------------------------- synthetic patches (C3 / C5)
+def grid_patches(nx: int, ny: int, block: int = 100, halo: int = 3, K: int = 16, height=None, noise: float = 0.3,
+                 seed: int = 0, only: Optional[Sequence[int]] = None):
+    """Cuts an open nx x ny-quad height field (2*nx*ny triangles) into block x block-quad patches
+    grown by `halo` quads on every side (3 levels x 2 convs of receptive field),
+    each with a Morton-ordered facet list, reference-layout adjacency (getFacesLargeAdj semantics,
+    deduplicated as the reference's sparse round trip leaves it) and the analytic 3-level
+    binary-tree pyramid of mesh.build_pyramid.  Global facet id of quad (i,j), triangle t is
+    2*(j*nx+i)+t.  Returns (patches, num_faces); `only` restricts generation to some patch indices
+    (every rank can generate just its own share)."""
+    bx = (nx + block - 1) // block
+    by = (ny + block - 1) // block
+    out = []
+    rs = np.random.RandomState(seed)
+    h = height or (lambda X, Y: 0.05 * np.sin(6.0 * X) * np.cos(4.0 * Y))
+    todo = range(bx * by) if only is None else only
+    for pi in todo:
+        pj, pi_ = divmod(pi, bx)
+        i0, i1 = pi_ * block, min(nx, (pi_ + 1) * block)
+        j0, j1 = pj * block, min(ny, (pj + 1) * block)
+        a0, a1 = max(0, i0 - halo), min(nx, i1 + halo)
+        b0, b1 = max(0, j0 - halo), min(ny, j1 + halo)
+        lx, ly = a1 - a0, b1 - b0
+        jj, ii = np.meshgrid(np.arange(b0, b1 + 1), np.arange(a0, a1 + 1), indexing="ij")
+        X, Y = ii / nx, jj / ny
+        V = np.stack([X, Y, h(X, Y)], -1).reshape(-1, 3).astype(np.float64)
+        qj, qi = np.meshgrid(np.arange(ly), np.arange(lx), indexing="ij")
+        qi, qj = qi.reshape(-1), qj.reshape(-1)
+        order = np.argsort(mesh._morton2(qi, qj), kind="stable")
+        qi, qj = qi[order], qj[order]
+        vx = lx + 1
+        v00, v10, v01, v11 = qj * vx + qi, qj * vx + qi + 1, (qj + 1) * vx + qi, (qj + 1) * vx + qi + 1
+        F = np.empty((qi.size * 2, 3), np.int32)
+        F[0::2] = np.stack([v00, v10, v11], 1)
+        F[1::2] = np.stack([v00, v11, v01], 1)
+        if noise:
+            e = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]], 0)
+            ml = np.linalg.norm(V[e[:, 0]] - V[e[:, 1]], axis=1).mean()
+            V = V + np.random.RandomState(seed * 7919 + pi).normal(0.0, noise * ml, size=V.shape)
+        feat = mesh.face_features(V, F).astype(np.float32)
+        adj = mesh.dedup_adj(mesh.faces_large_adj(F, K))
+        gi, gj = qi + a0, qj + b0
+        fid = np.empty(F.shape[0], np.int64)
+        fid[0::2] = 2 * (gj * nx + gi)
+        fid[1::2] = 2 * (gj * nx + gi) + 1
+        core_q = (gi >= i0) & (gi < i1) & (gj >= j0) & (gj < j1)
+        core = np.repeat(core_q, 2)
+        featp, adjp = mesh.pad_to_multiple(feat, adj, 16)
+        out.append(Patch(x=featp, adjs=mesh.build_pyramid(adjp, 3, K), face_ids=fid, perm=None, core=core))
+    del rs
+    return out, 2 * nx * ny

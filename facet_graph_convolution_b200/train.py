@@ -1,0 +1,137 @@
+"""Data-parallel training step of the denoising network.
+
+Restates the *step* of reference ``Code/train.py:trainNet`` (:380-632) -- not its TF session
+driver: random rotation of the inputs and of the ground-truth normals (:436-451, matrix from
+``utils.py:2034-2074``), network forward, ``normalizeTensor`` (:503), 4000 facet ids sampled with
+replacement (:561, :509-515), ``faceNormalsLoss`` (:517), Adam with TF defaults (:520).
+
+Multi-GPU: replicas only.  Every rank steps on its own patches; the only exchange is ONE
+all-reduce(sum) per step over a single flat fp32 gradient bucket (474 199 floats = 1.9 MB for the
+default network; latency-bound on NVLink, so no bucketing/overlap machinery), then 1/world.
+The reference has batch size 1 and no data parallelism (train.py:404-405); with B patches per
+rank the loss is the mean over the patches of the step.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+COST_SAMPLES = 4000  # reference Code/train.py:415
+
+
+def rand_rotation_matrix(rng: np.random.RandomState, deflection: float = 1.0) -> np.ndarray:
+    """Uniform random rotation after Arvo's Graphics Gems III method, the construction used by
+    reference Code/utils.py:2034-2074: a rotation about z followed by the Householder reflection
+    (v v^T - I) with |v| = sqrt(2)."""
+    theta, phi, z = rng.uniform(size=3)
+    theta *= 2.0 * deflection * math.pi
+    phi *= 2.0 * math.pi
+    z *= 2.0 * deflection
+    r = math.sqrt(z)
+    v = np.array([math.sin(phi) * r, math.cos(phi) * r, math.sqrt(2.0 - z)])
+    st, ct = math.sin(theta), math.cos(theta)
+    Rz = np.array([[ct, st, 0.0], [-st, ct, 0.0], [0.0, 0.0, 1.0]])
+    return (np.outer(v, v) - np.eye(3)).dot(Rz)
+
+
+def rotate_features(x: torch.Tensor, R: torch.Tensor) -> torch.Tensor:
+    """x[..., 3g] -> every consecutive xyz triple multiplied by R (train.py:444-451, channels % 3 == 0)."""
+    C = x.shape[-1]
+    if C % 3 != 0:
+        raise ValueError("rotation augmentation needs a multiple of 3 channels (normal | position), got %d" % C)
+    xr = x.reshape(*x.shape[:-1], C // 3, 3)
+    return torch.matmul(xr, R.t().to(x)).reshape(x.shape)
+
+
+class GradBucket:
+    """One flat fp32 buffer holding every parameter gradient, in the reference's variable-creation
+    order (W0,b,u,c,v per conv; W,b per linear), so a step needs exactly one all-reduce."""
+
+    def __init__(self, params: Sequence[torch.Tensor]):
+        self.params = list(params)
+        self.sizes = [int(p.numel()) for p in self.params]
+        self.total = sum(self.sizes)
+        dev = self.params[0].device if self.params else "cpu"
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.views: List[torch.Tensor] = []
+        o = 0
+        for p, n in zip(self.params, self.sizes):
+            self.views.append(self.flat[o:o + n].view_as(p))
+            o += n
+
+    def pack(self):
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad)
+        return self.flat
+
+    def all_reduce_mean(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.mul_(1.0 / dist.get_world_size(group))
+        return self.flat
+
+    def unpack(self):
+        for p, v in zip(self.params, self.views):
+            p.grad = v  # the optimizer reads straight from the bucket
+
+
+class Adam:
+    """tf.train.AdamOptimizer() defaults (lr 1e-3, beta 0.9/0.999, eps 1e-8; train.py:520) applied to
+    the flat bucket in one fused pass over a flat copy of the parameters."""
+
+    def __init__(self, bucket: GradBucket, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+        self.b, self.lr, self.b1, self.b2, self.eps, self.t = bucket, lr, b1, b2, eps, 0
+        self.m = torch.zeros_like(bucket.flat)
+        self.v = torch.zeros_like(bucket.flat)
+
+    @torch.no_grad()
+    def step(self):
+        self.t += 1
+        g = self.b.flat
+        self.m.mul_(self.b1).add_(g, alpha=1 - self.b1)
+        self.v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+        # TF's formulation: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  p -= lr_t * m / (sqrt(v) + eps)
+        lr_t = self.lr * math.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+        upd = self.m / (self.v.sqrt() + self.eps)
+        o = 0
+        for p, n in zip(self.b.params, self.b.sizes):
+            p.add_(upd[o:o + n].view_as(p), alpha=-lr_t)
+            o += n
+
+
+def loss_on_patch(forward, x, adjs, gt, rng: np.random.RandomState, samples: int = COST_SAMPLES,
+                  augment: bool = True):
+    """One patch of the training objective.  `forward(x, adjs)` returns the raw network output
+    [1,N0,3]; normalisation, sampling and the loss follow train.py:503-517."""
+    from . import model as fm
+    if augment:
+        R = torch.from_numpy(rand_rotation_matrix(rng).astype(np.float32)).to(x.device)
+        x = rotate_features(x, R)
+        gt = rotate_features(gt, R)
+    n = fm.normalizeTensor(forward(x, adjs))
+    idx = torch.from_numpy(rng.randint(x.shape[1], size=samples)).to(x.device)
+    return fm.faceNormalsLoss(n[:, idx, :].contiguous(), gt[:, idx, :].contiguous())
+
+
+def train_step(net, batch, bucket: GradBucket, opt: Adam, rng: np.random.RandomState, group=None,
+               samples: int = COST_SAMPLES, augment: bool = True) -> float:
+    """forward + backward over this rank's `batch` of (x[1,N0,Cin], adjs, gt[1,N0,3]) patches,
+    one all-reduce of the flat gradient bucket, Adam.  Returns the rank-local mean loss."""
+    for p in bucket.params:
+        p.grad = None
+    total = 0.0
+    for x, adjs, gt in batch:
+        loss = loss_on_patch(net, x, adjs, gt, rng, samples, augment) / len(batch)
+        loss.backward()
+        total += float(loss.detach())
+    bucket.pack()
+    bucket.all_reduce_mean(group)
+    opt.step()
+    return total

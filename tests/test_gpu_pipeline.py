@@ -1,0 +1,83 @@
+"""GPU parity of the patch-sharded inference pipeline (C3-shaped) and of one data-parallel
+training step, against the oracle's closed form on the same patches and weights."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _params(seed=11, multi=False):
+    rs = np.random.RandomState(seed)
+    shapes = []
+    M = 9
+    for cin, cout in [(6, 32), (32, 64), (64, 128), (128, 128), (128, 64), (128, 64), (64, 32), (64, 32)]:
+        shapes += [((M, cout, cin), 0.05), ((cout,), 0.01), ((M, cin), 0.05), ((M,), 0.05), ((M, cin), 0.05)]
+    shapes += [((32, 1024), 0.05), ((1024,), 0.01), ((1024, 3), 0.05), ((3,), 0.01)]
+    return [rs.normal(0, s, sh).astype(np.float32) for sh, s in shapes]
+
+
+def test_patch_sharded_inference_matches_oracle():
+    from facet_graph_convolution_b200 import model as fm
+    from facet_graph_convolution_b200 import patches as P
+    pts, nf = P.grid_patches(16, 12, block=8, halo=3, K=16)
+    params = _params()
+    store = fm.VariableStore(dev(), params=params)
+
+    def fwd_gpu(p):
+        x = torch.from_numpy(p.x[None]).to(dev())
+        adjs = [torch.from_numpy(a[None]).to(dev()) for a in p.adjs]
+        with torch.no_grad(), fm.variable_store(store):
+            y = fm.get_model_reg_multi_scale(x, adjs, 1.0)
+        return fm.normalizeTensor(y).cpu().numpy()
+
+    def fwd_oracle(p):
+        y = cf.net_forward(p.x[None].astype(np.float64), [a[None] for a in p.adjs], params)
+        return cf.normalize_tensor(y)
+
+    got = P.infer_sharded(pts, nf, fwd_gpu, 0, 1)
+    ref = P.infer_sharded(pts, nf, fwd_oracle, 0, 1)
+    assert got.shape == (nf, 3)
+    assert np.abs(got - ref).max() < 1e-4                      # north_star: max-abs <= 1e-4
+    ang = cf.angular_diff_vec(got, ref)
+    assert ang.mean() < 0.01 + np.degrees(np.arccos(0.999999))  # mean angular difference <= 0.01 deg
+    # a two-rank plan run rank by rank in this process gives the same merge
+    plan = P.partition([p.cost for p in pts], 2)
+    parts = [P.run_local(pts, plan[r], fwd_gpu) for r in range(2)]
+    assert np.abs(P.merge(nf, parts) - got).max() < 1e-12
+
+
+def test_training_step_reduces_loss_and_matches_oracle_loss():
+    from facet_graph_convolution_b200 import model as fm
+    from facet_graph_convolution_b200 import patches as P
+    from facet_graph_convolution_b200 import train as T
+    pts, _ = P.grid_patches(16, 16, block=16, halo=0, K=16, noise=0.3)
+    clean, _ = P.grid_patches(16, 16, block=16, halo=0, K=16, noise=0.0)
+    p, pc = pts[0], clean[0]
+    x = torch.from_numpy(p.x[None]).to(dev())
+    gt = torch.from_numpy(np.ascontiguousarray(pc.x[None, :, :3])).to(dev())
+    adjs = [torch.from_numpy(a[None]).to(dev()) for a in p.adjs]
+    params = _params(5)
+    net = fm.DenoisingNet(device=dev(), params=params)
+    with torch.no_grad():
+        y0 = net(x, adjs)
+    ref_loss = cf.face_normals_loss(cf.normalize_tensor(cf.net_forward(p.x[None].astype(np.float64),
+                                                                       [a[None] for a in p.adjs], params)),
+                                    pc.x[None, :, :3].astype(np.float64))
+    with torch.no_grad():
+        l0 = float(fm.faceNormalsLoss(fm.normalizeTensor(y0), gt))
+    assert abs(l0 - float(ref_loss)) < 1e-2
+    plist = list(net.parameters())
+    assert sum(t.numel() for t in plist) == 474199           # one 1.9 MB bucket
+    bucket = T.GradBucket(plist)
+    opt = T.Adam(bucket)
+    rng = np.random.RandomState(0)
+    losses = [T.train_step(net, [(x, adjs, gt)], bucket, opt, rng, samples=2000, augment=False) for _ in range(8)]
+    assert all(np.isfinite(losses))
+    assert min(losses[-3:]) < losses[0]

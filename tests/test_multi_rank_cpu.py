@@ -1,0 +1,145 @@
+"""N>1 host logic on CPU: gloo, world_size 2.  No CUDA kernels run here -- the
+per-patch forward is a stand-in; what is tested is partitioning, the ragged gather, the
+reference's overlap merge, the flat gradient bucket and its single all-reduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from facet_graph_convolution_b200 import patches as P
+from facet_graph_convolution_b200 import train as T
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _fake_forward(p):
+    """Deterministic stand-in for the network: a function of the patch's own rows only."""
+    x = p.x.astype(np.float64)
+    n = x[:, :3] + 0.25 * np.roll(x[:, 3:6], 1, axis=1) + 0.01
+    return n[None].astype(np.float32)
+
+
+def _make_patches():
+    rs = np.random.RandomState(3)
+    num_faces = 500
+    out = []
+    for i, (lo, hi) in enumerate([(0, 200), (150, 360), (300, 500), (0, 60), (440, 500)]):
+        ids = np.arange(lo, hi, dtype=np.int64)
+        n0 = (len(ids) + 15) // 16 * 16
+        x = np.zeros((n0, 6), np.float32)
+        perm = rs.permutation(n0).astype(np.int32)           # oldToNew
+        real = rs.randn(len(ids), 6).astype(np.float32)
+        xo = np.zeros((n0, 6), np.float32)
+        xo[: len(ids)] = real
+        x[perm] = xo                                         # x[new] = padded[old]
+        out.append(P.Patch(x=x, adjs=[], face_ids=ids, perm=perm, core=None))
+    return out, num_faces
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        patches, nf = _make_patches()
+        pred = P.infer_sharded(patches, nf, _fake_forward, rank, world)
+        # gradient bucket: rank r contributes (r+1) * base
+        torch.manual_seed(0)
+        params = [torch.randn(4, 3), torch.randn(7), torch.randn(2, 2, 2)]
+        for p in params:
+            p.requires_grad_(True)
+        b = T.GradBucket(params)
+        opt = T.Adam(b)
+        for i, p in enumerate(params):
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        b.pack()
+        b.all_reduce_mean()
+        opt.step()
+        q.put((rank, pred, b.flat.clone().numpy(), [p.detach().clone().numpy() for p in params]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_is_deterministic_and_balanced():
+    costs = [24512, 2016, 20000, 20000, 8192, 8192, 8192, 512]
+    plan = P.partition(costs, 4)
+    assert sorted(i for r in plan for i in r) == list(range(len(costs)))
+    loads = [sum(costs[i] for i in r) for r in plan]
+    assert max(loads) <= 1.35 * (sum(costs) / 4)
+    assert plan == P.partition(list(costs), 4)
+    assert P.partition([5, 5], 1) == [[0, 1]]
+    assert P.partition([], 2) == [[], []]
+
+
+def test_world2_inference_matches_single_process_and_reference_merge():
+    patches, nf = _make_patches()
+    single = P.infer_sharded(patches, nf, _fake_forward, 0, 1)
+    # the reference's own merge (train.py:117-126,136), restated naively
+    acc = np.zeros((nf, 3))
+    for p in patches:
+        out = _fake_forward(p)[0][p.perm][: p.num_real]
+        acc[p.face_ids] += out
+    for _ in range(2):
+        acc = acc * (1 / (np.sqrt((acc * acc).sum(1))[:, None] + 1e-8))
+    assert np.abs(single - acc).max() < 1e-12
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    for rank, pred, flat, params in res:
+        assert np.abs(pred - single).max() < 1e-6
+    # one all-reduce: mean of (1,2) * (i+1) = 1.5 * (i+1), identical on both ranks
+    f0, f1 = res[0][2], res[1][2]
+    assert np.array_equal(f0, f1)
+    assert np.allclose(f0[:12], 1.5) and np.allclose(f0[12:19], 3.0) and np.allclose(f0[19:], 4.5)
+    for a, b in zip(res[0][3], res[1][3]):
+        assert np.array_equal(a, b)          # replicas stay bit-identical after the step
+    # first Adam step moves every parameter by lr (TF formulation)
+    torch.manual_seed(0)
+    ref = [torch.randn(4, 3), torch.randn(7), torch.randn(2, 2, 2)]
+    for a, r in zip(res[0][3], ref):
+        assert np.allclose(a, r.numpy() - 1e-3, atol=1e-6)
+
+
+def test_grid_patches_cover_every_facet_once_with_halo():
+    pts, nf = P.grid_patches(20, 12, block=8, halo=3, K=16)
+    assert nf == 480 and len(pts) == 3 * 2
+    seen = np.zeros(nf, int)
+    for p in pts:
+        assert p.x.shape[0] % 16 == 0 and p.x.shape[1] == 6
+        assert [a.shape[0] for a in p.adjs] == [p.x.shape[0], p.x.shape[0] // 4, p.x.shape[0] // 16]
+        a0 = p.adjs[0]
+        assert np.array_equal(a0[:, 0], np.arange(1, a0.shape[0] + 1))
+        assert a0.min() >= 0 and a0.max() <= a0.shape[0]
+        assert p.core.sum() < p.num_real          # a halo exists
+        np.add.at(seen, p.face_ids[p.core], 1)
+    assert np.array_equal(seen, np.ones(nf, int))
+    # generating only a rank's share gives the same patches
+    some, _ = P.grid_patches(20, 12, block=8, halo=3, K=16, only=[4])
+    assert np.array_equal(some[0].x, pts[4].x) and np.array_equal(some[0].adjs[2], pts[4].adjs[2])
+
+
+def test_rotation_matrix_and_feature_rotation():
+    rng = np.random.RandomState(5)
+    R = T.rand_rotation_matrix(rng)
+    assert np.abs(R @ R.T - np.eye(3)).max() < 1e-12 and abs(np.linalg.det(R) - 1) < 1e-12
+    x = torch.randn(1, 10, 6)
+    y = T.rotate_features(x, torch.from_numpy(R.astype(np.float32)))
+    ref = np.concatenate([x[0, :, :3].numpy() @ R.T, x[0, :, 3:].numpy() @ R.T], axis=1)
+    assert np.abs(y[0].numpy() - ref).max() < 1e-5
