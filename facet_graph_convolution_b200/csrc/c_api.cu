@@ -81,16 +81,21 @@ static bool use_tc(const fgc_conv_shape* s) {
   return !disabled && s->Cin % 4 == 0 && conv_fwd_tc_supported(s->Cw, s->Cout, s->M, s->K);
 }
 
+static bool use_mma(const fgc_conv_shape* s) {
+  static const bool disabled = getenv("FGC_DISABLE_MMA") != nullptr || getenv("FGC_DISABLE_TC") != nullptr;
+  return !disabled && conv_mma_supported(s->Cin, s->Cw, s->Cout, s->M, s->K);
+}
+
 static size_t conv_fwd_workspace(const fgc_conv_shape* s) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   return ws_bytes(rows * 2 * s->M, 4) + ws_bytes(static_cast<size_t>(s->M) * s->Cout * s->Cw, 4) +
-         ws_bytes(conv_fwd_tc_workspace(s->Cout, s->M), 1) + 512;
+         ws_bytes(conv_fwd_tc_workspace(s->Cout, s->M), 1) + (use_mma(s) ? conv_mma_workspace(rows) + 256 : 0) + 512;
 }
 
 static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0,
                     const float* b, const float* u, const float* v, const float* c, float* y,
                     int bias_mask, int act, float alpha, void* workspace, size_t workspace_bytes,
-                    cudaStream_t st) {
+                    cudaStream_t st, const void* plan = nullptr) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   Workspace ws(workspace, workspace_bytes);
   float* uvx = ws.take<float>(rows * 2 * s->M);
@@ -101,6 +106,12 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
   if (rc) return rc;
   ConvFwdParams p{x, adj, uvx, Wt, b, y, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M,
                   bias_mask, act, alpha};
+  if (plan != nullptr && use_mma(s)) {
+    char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M));
+    char* img = ws.take<char>(conv_mma_workspace(rows));
+    FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the planned tensor-core path");
+    return launch_conv_mma(p, W0, plan, img, wimg, st);
+  }
   if (use_tc(s)) {
     char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M));
     FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the tensor-core path");
@@ -116,22 +127,38 @@ struct HostCache {
   int device = -1;
   char* dev = nullptr;
   size_t cap = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // compute
+  cudaStream_t s_in = nullptr;        // host -> device copies
+  cudaStream_t s_out = nullptr;       // device -> host copies
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 static thread_local HostCache g_hc;
+
+static void host_destroy_streams() {
+  if (g_hc.stream) cudaStreamDestroy(g_hc.stream);
+  if (g_hc.s_in) cudaStreamDestroy(g_hc.s_in);
+  if (g_hc.s_out) cudaStreamDestroy(g_hc.s_out);
+  for (auto& e : g_hc.ev)
+    if (e) cudaEventDestroy(e);
+}
 
 static int host_reserve(int device, size_t bytes) {
   if (g_hc.device != device) {
     if (g_hc.dev) {
       cudaSetDevice(g_hc.device);
       cudaFree(g_hc.dev);
-      if (g_hc.stream) cudaStreamDestroy(g_hc.stream);
     }
+    host_destroy_streams();
     g_hc = HostCache();
   }
   FGC_CUDA(cudaSetDevice(device));
   g_hc.device = device;
-  if (!g_hc.stream) FGC_CUDA(cudaStreamCreateWithFlags(&g_hc.stream, cudaStreamNonBlocking));
+  if (!g_hc.stream) {
+    FGC_CUDA(cudaStreamCreateWithFlags(&g_hc.stream, cudaStreamNonBlocking));
+    FGC_CUDA(cudaStreamCreateWithFlags(&g_hc.s_in, cudaStreamNonBlocking));
+    FGC_CUDA(cudaStreamCreateWithFlags(&g_hc.s_out, cudaStreamNonBlocking));
+    for (auto& e : g_hc.ev) FGC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   if (bytes > g_hc.cap) {
     if (g_hc.dev) FGC_CUDA(cudaFree(g_hc.dev));
     g_hc.dev = nullptr;
@@ -224,6 +251,31 @@ int fgc_conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, co
   FGC_REQUIRE(act == FGC_ACT_NONE || act == FGC_ACT_LRELU, "conv_fwd: unknown activation %d", act);
   return conv_fwd(s, x, adj, W0, b, u, v, c, y, bias_mask, act, alpha, workspace, workspace_bytes,
                   as_stream(stream));
+}
+
+int fgc_debug_trace(int64_t* out, int n) { return debug_mma_trace(out, n); }
+
+size_t fgc_conv_plan_bytes(int B, int N, int K, int M) {
+  if (B <= 0 || N <= 0 || K <= 0 || K > FGC_MAX_K || M != 8) return 0;
+  return conv_plan_bytes(static_cast<int64_t>(B) * N, K, M);
+}
+
+int fgc_build_conv_plan(const int32_t* adj, int B, int N, int K, int M, void* plan, size_t plan_bytes,
+                        void* stream) {
+  FGC_REQUIRE(adj && plan && B > 0 && N > 0 && K > 0 && K <= FGC_MAX_K, "build_conv_plan: bad arguments");
+  return build_conv_plan(adj, B, N, K, M, plan, plan_bytes, as_stream(stream));
+}
+
+int fgc_conv_fwd_planned(const fgc_conv_shape* s, const float* x, const int32_t* adj, const void* plan,
+                         const float* W0, const float* b, const float* u, const float* v, const float* c,
+                         float* y, int bias_mask, int act, float alpha, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  int rc = check_shape(s, "conv_fwd_planned");
+  if (rc) return rc;
+  FGC_REQUIRE(x && adj && W0 && b && u && v && c && y, "conv_fwd_planned: NULL tensor pointer");
+  FGC_REQUIRE(act == FGC_ACT_NONE || act == FGC_ACT_LRELU, "conv_fwd_planned: unknown activation %d", act);
+  return conv_fwd(s, x, adj, W0, b, u, v, c, y, bias_mask, act, alpha, workspace, workspace_bytes,
+                  as_stream(stream), plan);
 }
 
 size_t fgc_reverse_adj_workspace(int B, int N, int K) {
@@ -328,39 +380,60 @@ int fgc_conv_fwd_bwd_host(const fgc_conv_shape* s, const float* x, const int32_t
                ogx = place(nx * 4), oW = place(nW * 4), ob = place(s->Cout * 4), ou = place(nu * 4),
                ov = place(nu * 4), oc = place(s->M * 4), ogW = place(nW * 4), ogb = place(s->Cout * 4),
                ogu = place(nu * 4), ogv = place(nu * 4), ogc = place(s->M * 4),
-               orp = place((rows + 1) * 4), ore = place(nadj * 4), ows = place(wsmax);
+               orp = place((rows + 1) * 4), ore = place(nadj * 4), orw = place(wsr), ows = place(wsmax);
   rc = host_reserve(device, total);
   if (rc) return rc;
+  // Three streams: copies in, kernels, copies out.  The adjacency goes first (the reverse adjacency
+  // is built while x is still arriving), gy arrives under the forward, y leaves under the backward
+  // and gx leaves as soon as it is final (before the weight-gradient passes).
   char* d = g_hc.dev;
-  cudaStream_t st = g_hc.stream;
-  FGC_CUDA(cudaMemcpyAsync(d + ox, x, nx * 4, cudaMemcpyHostToDevice, st));
-  FGC_CUDA(cudaMemcpyAsync(d + oadj, adj, nadj * 4, cudaMemcpyHostToDevice, st));
-  FGC_CUDA(cudaMemcpyAsync(d + oW, W0, nW * 4, cudaMemcpyHostToDevice, st));
-  FGC_CUDA(cudaMemcpyAsync(d + ob, b, s->Cout * 4, cudaMemcpyHostToDevice, st));
-  FGC_CUDA(cudaMemcpyAsync(d + ou, u, nu * 4, cudaMemcpyHostToDevice, st));
-  FGC_CUDA(cudaMemcpyAsync(d + ov, v, nu * 4, cudaMemcpyHostToDevice, st));
-  FGC_CUDA(cudaMemcpyAsync(d + oc, c, s->M * 4, cudaMemcpyHostToDevice, st));
+  cudaStream_t st = g_hc.stream, si = g_hc.s_in, so = g_hc.s_out;
+  cudaEvent_t e_adj = g_hc.ev[0], e_x = g_hc.ev[1], e_gy = g_hc.ev[2], e_y = g_hc.ev[3], e_gx = g_hc.ev[4],
+              e_done = g_hc.ev[5];
+  FGC_CUDA(cudaMemcpyAsync(d + oadj, adj, nadj * 4, cudaMemcpyHostToDevice, si));
+  FGC_CUDA(cudaEventRecord(e_adj, si));
+  FGC_CUDA(cudaMemcpyAsync(d + oW, W0, nW * 4, cudaMemcpyHostToDevice, si));
+  FGC_CUDA(cudaMemcpyAsync(d + ob, b, s->Cout * 4, cudaMemcpyHostToDevice, si));
+  FGC_CUDA(cudaMemcpyAsync(d + ou, u, nu * 4, cudaMemcpyHostToDevice, si));
+  FGC_CUDA(cudaMemcpyAsync(d + ov, v, nu * 4, cudaMemcpyHostToDevice, si));
+  FGC_CUDA(cudaMemcpyAsync(d + oc, c, s->M * 4, cudaMemcpyHostToDevice, si));
+  FGC_CUDA(cudaMemcpyAsync(d + ox, x, nx * 4, cudaMemcpyHostToDevice, si));
+  FGC_CUDA(cudaEventRecord(e_x, si));
+  FGC_CUDA(cudaMemcpyAsync(d + ogy, gy, ny * 4, cudaMemcpyHostToDevice, si));
+  FGC_CUDA(cudaEventRecord(e_gy, si));
+  FGC_CUDA(cudaStreamWaitEvent(st, e_adj, 0));
+  // the reverse adjacency has its own scratch (orw) so that it can run before the forward
+  rc = build_reverse_adj((int32_t*)(d + oadj), s->B, s->N, s->K, (int32_t*)(d + orp),
+                         (int32_t*)(d + ore), nullptr, d + orw, wsr, st);
+  if (rc) return rc;
+  FGC_CUDA(cudaStreamWaitEvent(st, e_x, 0));
   rc = conv_fwd(s, (float*)(d + ox), (int32_t*)(d + oadj), (float*)(d + oW), (float*)(d + ob),
                 (float*)(d + ou), (float*)(d + ov), (float*)(d + oc), (float*)(d + oy), bias_mask,
                 FGC_ACT_NONE, 0.f, d + ows, wsmax, st);
   if (rc) return rc;
-  FGC_CUDA(cudaMemcpyAsync(y, d + oy, ny * 4, cudaMemcpyDeviceToHost, st));
-  FGC_CUDA(cudaMemcpyAsync(d + ogy, gy, ny * 4, cudaMemcpyHostToDevice, st));
-  rc = build_reverse_adj((int32_t*)(d + oadj), s->B, s->N, s->K, (int32_t*)(d + orp),
-                         (int32_t*)(d + ore), nullptr, d + ows, wsmax, st);
-  if (rc) return rc;
+  FGC_CUDA(cudaEventRecord(e_y, st));
+  FGC_CUDA(cudaStreamWaitEvent(so, e_y, 0));
+  FGC_CUDA(cudaMemcpyAsync(y, d + oy, ny * 4, cudaMemcpyDeviceToHost, so));
+  FGC_CUDA(cudaStreamWaitEvent(st, e_gy, 0));
+  g_gx_ready_event = e_gx;
   rc = conv_bwd(s, (float*)(d + ogy), (float*)(d + ox), (int32_t*)(d + oadj), (int32_t*)(d + orp),
                 (int32_t*)(d + ore), (float*)(d + oW), (float*)(d + ou), (float*)(d + ov),
                 (float*)(d + oc), (float*)(d + ogx), (float*)(d + ogW), (float*)(d + ogb),
                 (float*)(d + ogu), (float*)(d + ogv), (float*)(d + ogc), bias_mask, d + ows, wsmax, st);
+  g_gx_ready_event = nullptr;
   if (rc) return rc;
-  FGC_CUDA(cudaMemcpyAsync(gx, d + ogx, nx * 4, cudaMemcpyDeviceToHost, st));
-  FGC_CUDA(cudaMemcpyAsync(gW0, d + ogW, nW * 4, cudaMemcpyDeviceToHost, st));
-  FGC_CUDA(cudaMemcpyAsync(gb, d + ogb, s->Cout * 4, cudaMemcpyDeviceToHost, st));
-  FGC_CUDA(cudaMemcpyAsync(gu, d + ogu, nu * 4, cudaMemcpyDeviceToHost, st));
-  FGC_CUDA(cudaMemcpyAsync(gv, d + ogv, nu * 4, cudaMemcpyDeviceToHost, st));
-  FGC_CUDA(cudaMemcpyAsync(gc, d + ogc, s->M * 4, cudaMemcpyDeviceToHost, st));
+  FGC_CUDA(cudaStreamWaitEvent(so, e_gx, 0));
+  FGC_CUDA(cudaMemcpyAsync(gx, d + ogx, nx * 4, cudaMemcpyDeviceToHost, so));
+  FGC_CUDA(cudaEventRecord(e_done, st));
+  FGC_CUDA(cudaStreamWaitEvent(so, e_done, 0));
+  FGC_CUDA(cudaMemcpyAsync(gW0, d + ogW, nW * 4, cudaMemcpyDeviceToHost, so));
+  FGC_CUDA(cudaMemcpyAsync(gb, d + ogb, s->Cout * 4, cudaMemcpyDeviceToHost, so));
+  FGC_CUDA(cudaMemcpyAsync(gu, d + ogu, nu * 4, cudaMemcpyDeviceToHost, so));
+  FGC_CUDA(cudaMemcpyAsync(gv, d + ogv, nu * 4, cudaMemcpyDeviceToHost, so));
+  FGC_CUDA(cudaMemcpyAsync(gc, d + ogc, s->M * 4, cudaMemcpyDeviceToHost, so));
+  FGC_CUDA(cudaStreamSynchronize(so));
   FGC_CUDA(cudaStreamSynchronize(st));
+  FGC_CUDA(cudaStreamSynchronize(si));
   return FGC_OK;
 }
 
@@ -369,7 +442,7 @@ void fgc_host_release(void) {
     cudaSetDevice(g_hc.device);
     cudaFree(g_hc.dev);
   }
-  if (g_hc.stream) cudaStreamDestroy(g_hc.stream);
+  host_destroy_streams();
   g_hc = HostCache();
 }
 

@@ -859,6 +859,9 @@ static int run_w(const BwdWParams& p, int chunks, cudaStream_t st) {
   return FGC_OK;
 }
 
+// set by the host-buffer entry point (c_api.cu): recorded on the stream as soon as gx is final
+thread_local cudaEvent_t g_gx_ready_event = nullptr;
+
 int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
              const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu, float* gv,
@@ -920,6 +923,29 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
 #undef FGC_CALL
     if (rc) return rc;
   }
+  // ---- logit-window part of gx first: gx is final after this kernel (the host-buffer entry point
+  //      starts its device->host copy here, overlapping the weight-gradient passes below)
+  static const bool slow_logits = getenv("FGC_DISABLE_FAST_LOGITS") != nullptr;
+  const bool fast_logits = !slow_logits && logits_fast_supported(s->Cin, s->Ca0, s->Ca, s->M);
+  LogitsBwdParams lp{x, d_uvx, u, v, gx, partL, rows, s->Cin, s->Ca0, s->Ca, s->M, pl.rows_per_lchunk};
+  const int O2 = 2 * s->M, Ca4 = (s->Ca + 3) & ~3;
+  if (fast_logits) {
+    rc = launch_logits_bwd_x_fast(d_uvx, u, v, gx, rows, s->Cin, s->Ca0, s->Ca, s->M, st);
+    if (rc) return rc;
+  } else {
+    const size_t smem_x = static_cast<size_t>(O2) * Ca4 * 4;
+    int64_t bx = (rows + 127) / 128;
+    const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    const unsigned g = static_cast<unsigned>(bx);
+    if (O2 <= 8) logits_bwd_x_kernel<8><<<g, 128, smem_x, st>>>(lp);
+    else if (O2 <= 16) logits_bwd_x_kernel<16><<<g, 128, smem_x, st>>>(lp);
+    else if (O2 <= 18) logits_bwd_x_kernel<18><<<g, 128, smem_x, st>>>(lp);
+    else logits_bwd_x_kernel<32><<<g, 128, smem_x, st>>>(lp);
+    FGC_LAUNCHED("logits_bwd_x_kernel");
+  }
+  if (g_gx_ready_event != nullptr) FGC_CUDA(cudaEventRecord(g_gx_ready_event, st));
   int wchunks = pl.chunks;
   if (!tc_disabled && bwd_w_tc_supported(s->Cw, s->Cout, s->M, s->Cin)) {
     rc = launch_bwd_w_tc(gy, x, adj, uvx, partW, partB, maxbits, rows, s->N, s->K, s->Cin, s->M, bias_mask, st);
@@ -933,23 +959,14 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
 #undef FGC_CALL
     if (rc) return rc;
   }
-  {
-    LogitsBwdParams p{x, d_uvx, u, v, gx, partL, rows, s->Cin, s->Ca0, s->Ca, s->M, pl.rows_per_lchunk};
-    const int O = 2 * s->M, Ca4 = (s->Ca + 3) & ~3;
-    const size_t smem_x = static_cast<size_t>(O) * Ca4 * 4;
-    int64_t bx = (rows + 127) / 128;
-    const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
-    if (bx > cap) bx = cap;
-    if (bx < 1) bx = 1;
-    const unsigned g = static_cast<unsigned>(bx);
-    if (O <= 8) logits_bwd_x_kernel<8><<<g, 128, smem_x, st>>>(p);
-    else if (O <= 16) logits_bwd_x_kernel<16><<<g, 128, smem_x, st>>>(p);
-    else if (O <= 18) logits_bwd_x_kernel<18><<<g, 128, smem_x, st>>>(p);
-    else logits_bwd_x_kernel<32><<<g, 128, smem_x, st>>>(p);
-    FGC_LAUNCHED("logits_bwd_x_kernel");
-    const size_t smem_p = (static_cast<size_t>(kLogitRows) * Ca4 + kLogitRows * O) * 4;
+  if (fast_logits) {
+    rc = launch_logits_bwd_p_fast(x, d_uvx, partL, rows, pl.rows_per_lchunk, pl.lchunks, s->Cin, s->Ca0, s->Ca, s->M,
+                                  st);
+    if (rc) return rc;
+  } else {
+    const size_t smem_p = (static_cast<size_t>(kLogitRows) * Ca4 + kLogitRows * O2) * 4;
     FGC_CUDA(cudaFuncSetAttribute(logits_bwd_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-    logits_bwd_p_kernel<<<pl.lchunks, kThreads, smem_p, st>>>(p);
+    logits_bwd_p_kernel<<<pl.lchunks, kThreads, smem_p, st>>>(lp);
     FGC_LAUNCHED("logits_bwd_p_kernel");
   }
   rc = launch_reduce_partials(partW, gW0, nW, wchunks, nW, st);

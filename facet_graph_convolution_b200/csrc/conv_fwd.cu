@@ -10,6 +10,8 @@
 //        phase 2  tile GEMM y = s . Wt streamed through shared memory in 32-row chunks,
 //                 fused epilogue (1/cnt, masked bias, leaky ReLU)
 // The [B,N,K,M*Cout] tensor the reference materialises never exists.
+#include <stdlib.h>
+
 #include "conv_common.cuh"
 #include "conv_launch.cuh"
 
@@ -67,6 +69,9 @@ assign_logits_kernel(const float* __restrict__ x, const float* __restrict__ u,
 int launch_assign_logits(const fgc_conv_shape* s, const float* x, const float* u, const float* v,
                          const float* c, float* uvx, cudaStream_t st) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  static const bool slow = getenv("FGC_DISABLE_FAST_LOGITS") != nullptr;
+  if (!slow && logits_fast_supported(s->Cin, s->Ca0, s->Ca, s->M))
+    return launch_assign_logits_fast(x, u, v, c, uvx, rows, s->Cin, s->Ca0, s->Ca, s->M, st);
   const int O = 2 * s->M;
   const size_t smem = static_cast<size_t>(O) * ((s->Ca + 3) & ~3) * 4;
   int64_t blocks = (rows + 127) / 128;

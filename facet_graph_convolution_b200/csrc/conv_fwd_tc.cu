@@ -415,6 +415,15 @@ int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStr
   return FGC_OK;
 }
 
+// weight image in forward orientation (chunk m: rows o hi|lo, K = c), shared with conv_mma.cu
+int launch_prep_w_image(const float* W0, void* wimg_ws, int M, int Cout, cudaStream_t st) {
+  const size_t img = static_cast<size_t>(M) * 2 * Cout * 128;
+  float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
+  prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cout, 0);
+  FGC_LAUNCHED("prep_w_image_kernel");
+  return FGC_OK;
+}
+
 // Target-centric backward pass on the same skeleton: gx[:, 0:Cw] = sum_m t[.,m,:] W0[m] with
 // t[j,m,:] = sum over in-edges (n->j) of q[n->j,m] * inv_cnt[n] * gy[n,:], plus d_uvx[:, M:2M].
 bool bwd_tgt_tc_supported(int Cw, int Cout, int M) { return Cw == 64 && Cout == kCw && M == 8; }

@@ -20,6 +20,14 @@ struct ConvFwdParams {
 
 int launch_assign_logits(const fgc_conv_shape* s, const float* x, const float* u, const float* v,
                          const float* c, float* uvx, cudaStream_t st);
+// warp-cooperative fast paths of the logit kernels (logits.cu)
+bool logits_fast_supported(int Cin, int Ca0, int Ca, int M);
+int launch_assign_logits_fast(const float* x, const float* u, const float* v, const float* c, float* uvx,
+                              int64_t rows, int Cin, int Ca0, int Ca, int M, cudaStream_t st);
+int launch_logits_bwd_x_fast(const float* d_uvx, const float* u, const float* v, float* gx, int64_t rows, int Cin,
+                             int Ca0, int Ca, int M, cudaStream_t st);
+int launch_logits_bwd_p_fast(const float* x, const float* d_uvx, float* part, int64_t rows, int64_t rows_per_chunk,
+                             int chunks, int Cin, int Ca0, int Ca, int M, cudaStream_t st);
 int launch_transpose_w(const float* W0, float* Wt, int M, int Cout, int Cw, cudaStream_t st);
 int launch_conv_fwd(const ConvFwdParams& p, cudaStream_t st);
 int launch_assignments(const int32_t* adj, const float* uvx, float* q, int64_t rows, int N, int K,
@@ -35,6 +43,15 @@ int launch_bwd_tgt_tc(const float* gy, const float* uvx, const float* W0, const 
                       const float* inv, const int32_t* rev_ptr, const int32_t* rev_edge, float* gx,
                       float* d_uvx, int64_t rows, int N, int K, int Cin, int Cw, int Cout, int M,
                       void* wimg_ws, cudaStream_t st);
+int launch_prep_w_image(const float* W0, void* wimg_ws, int M, int Cout, cudaStream_t st);
+// dense-assignment tcgen05 path (conv_mma.cu): tile plan + forward
+bool conv_mma_supported(int Cin, int Cw, int Cout, int M, int K);
+size_t conv_plan_bytes(int64_t rows, int K, int M);
+int build_conv_plan(const int32_t* adj, int B, int N, int K, int M, void* plan, size_t plan_bytes, cudaStream_t st);
+size_t conv_mma_workspace(int64_t rows);
+int debug_mma_trace(int64_t* out, int n);
+int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, void* img_ws, void* wimg_ws,
+                    cudaStream_t st);
 int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStream_t st);
 bool bwd_src_tc_supported(int Cw, int Cout, int M, int Cin);
 int launch_bwd_src_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, const void* wimg,
@@ -45,6 +62,7 @@ int bwd_w_tc_grid(int64_t rows);
 int launch_bwd_w_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, float* partW,
                     float* partB, unsigned* maxbits, int64_t rows, int N, int K, int Cin, int M,
                     int bias_mask, cudaStream_t st);
+extern thread_local cudaEvent_t g_gx_ready_event;
 size_t conv_bwd_workspace(const fgc_conv_shape* s);
 int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,

@@ -1,0 +1,807 @@
+// "Dense-assignment" tensor-core facet-graph convolution (second-generation dense path).
+// Replaces reference Code/model.py:427-504 for 64-channel dense layers; same math as conv_fwd_tc.cu
+// but BOTH contractions run on tcgen05 and every neighbour row is fetched once per tile:
+//
+//   tile = TF = 128/M facets.  A caller-owned *tile plan* (built once per adjacency, like the
+//   reversed adjacency) lists the R distinct neighbour rows a tile touches and, per (facet,slot),
+//   the local index of its row and the multiplicity of duplicates.
+//
+//   stage 1   S[(f,m), c] = sum_r Q[(f,m), r] * X[r, c]          tcgen05.mma  M=128 N=64 K=R
+//             Q = soft assignments scattered into a dense [128 x R] fp16 hi/lo tile (K-major,
+//             128B swizzle) by CUDA cores; X = the R distinct rows of a pre-split fp16 hi|lo image
+//             of x, copied global->shared with cp.async straight into the UMMA MN-major layout.
+//             hi.hi + lo.hi + hi.lo accumulate in one fp32 TMEM accumulator.
+//   drain     S (TMEM) -> registers -> fp16 hi/lo -> shared, laid out as the B operand of stage 2
+//   stage 2   Y^T[o, f] = sum_{m,c} [Wh;Wl][o,(m,c)] * [Sh|Sl][(m,c), f]   tcgen05.mma M=128 N=32 K=M*64
+//             A = the resident swizzled weight image shared with conv_fwd_tc.cu.
+//   epilogue  y = act( scale_f * (Wh.Sh + Wh.Sl + 2^-11 Wl.Sh) + flag_f * b )
+//
+// Warp roles (one persistent CTA per SM, 16 warps): 0-3 drain + epilogue (TMEM lane quadrants),
+// 4-7 / 8-11 two assignment groups (softmax, Q scatter; alternate chunks, one Q buffer each),
+// 12-13 row loaders (cp.async, alternate chunks), 14 stage-1 MMA issuer, 15 stage-2 MMA issuer.
+#include "conv_common.cuh"
+#include "conv_launch.cuh"
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "tc_common.cuh"
+
+namespace fgc {
+
+namespace {
+
+constexpr int kC = 64;              // aggregation channels
+constexpr int kRC = 64;             // distinct rows per chunk (one K atom of Q)
+constexpr int kMmaThreads = 16 * 32;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when all cp.async of this thread so far have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// MN-major, 128-byte-swizzled operand descriptor (rows of 64 MN elements = 128 B, 8-row K groups)
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int M, int COUT>
+struct MCfg {
+  static_assert(M == 8 && COUT == 64, "first instantiation: M = 8, Cout = 64");
+  static constexpr int TF = 128 / M;                 // facets per tile; tile row = m * TF + f
+  static constexpr int NB3 = 2 * TF;                 // stage-2 N: [Sh | Sl]
+  static constexpr int NX = 4;                       // row-chunk ring depth
+  static constexpr int X_PLANE = kRC * 128;          // one plane (hi or lo) of a row chunk
+  // ring slot: X hi | X lo | neighbour logits of the chunk's rows | tile header + pair records | own logits
+  static constexpr int SL_VL = 2 * X_PLANE;          // [kRC][M] fp32
+  static constexpr int SL_PR = SL_VL + kRC * M * 4;  // 16-byte header (R) + TF*K uint16
+  static constexpr int SL_UO = SL_PR + 16 + TF * 32 * 2;
+  static constexpr int X_BUF = ((SL_UO + TF * M * 4) + 1023) / 1024 * 1024;
+  static constexpr int Q_PLANE = 128 * 128;          // [128 rows][64 K] halves
+  static constexpr int Q_BUF = 2 * Q_PLANE;          // hi | lo
+  static constexpr int B3_ATOM = NB3 * 128;          // [NB3 rows][64 K] halves
+  static constexpr int B3_BUF = M * B3_ATOM;
+  static constexpr int EX_BYTES = 2 * TF * COUT * 4; // epilogue exchange: two [TF][COUT] fp32 planes
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_Q = OFF_X + NX * X_BUF;
+  static constexpr int OFF_B3 = OFF_Q + 2 * Q_BUF;
+  static constexpr int OFF_EX = OFF_B3 + 2 * B3_BUF;
+  static constexpr int OFF_BAR = OFF_EX + EX_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512;
+  // TMEM: the weight operand [Wh;Wl] lives here for the CTA's lifetime (A of stage 2, 2 halves/column)
+  static constexpr int W_COL = 0;
+  static constexpr int W_COLS = M * kC / 2;          // 256
+  static constexpr int D1_COL = W_COL + W_COLS;      // two stage-1 accumulators of 64 columns
+  static constexpr int D3_COL = D1_COL + 2 * 64;     // two stage-2 accumulators of NB3 columns
+  static constexpr int TMEM_COLS = 512;
+  static_assert(D3_COL + 2 * NB3 <= TMEM_COLS, "TMEM overflow");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+};
+
+struct MmaParams {
+  const uint4* img;        // [rows][16]: 8 x 16 B hi | 8 x 16 B lo (fp16, scaled by 2^-ex)
+  const float* xunscale;   // 2^ex
+  const float* uvx;        // [rows][2M]
+  const int32_t* adj;      // [rows][K]
+  const uint8_t* ppair;    // [ntiles][16 + TF*K*2]: header {R} + (local row index | multiplicity << 10)
+  const int32_t* prow;     // [ntiles][TF*K]: distinct rows of the tile (global row ids)
+  const int32_t* pR;       // [ntiles]
+  const float* pinv;       // [rows]: 1/cnt or 0
+  const uint4* wimg;       // swizzled fp16 image of [Wh | Wl] (prep_w_image_kernel)
+  const float* wunscale;
+  const float* b;
+  float* y;
+  int64_t rows, ntiles;
+  int N, K, ldy, bias_mask, act;
+  float alpha;
+  int trace;
+};
+
+enum {
+  B_X_FULL = 0,            // NX
+  B_X_FREE = 4,            // NX
+  B_Q_FULL = 8,            // 2
+  B_Q_FREE = 10,           // 2
+  B_D1_FULL = 12,          // 2
+  B_D1_FREE = 14,          // 2
+  B_B3_FULL = 16,          // 2
+  B_B3_FREE = 18,          // 2
+  B_D3_FULL = 20,          // 2
+  B_D3_FREE = 22,          // 2
+  B_NUM = 24
+};
+
+// optional pipeline trace (FGC_MMA_TRACE=1): clock64 stamps of CTA 0, first 32 tiles, 4 roles x 8 events
+__device__ long long g_mma_trace[4 * 32 * 8];
+#define FGC_TR(role, t, ev)                                                        \
+  do {                                                                             \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (t) < 32)                       \
+      g_mma_trace[((role) * 32 + (t)) * 8 + (ev)] = clock64();                     \
+  } while (0)
+
+__device__ __forceinline__ int chunks_of(int R) { return R <= kRC ? 1 : (R + kRC - 1) / kRC; }
+
+template <int M, int COUT, int KP>
+__global__ void __launch_bounds__(kMmaThreads, 1)
+conv_mma_kernel(const MmaParams p) {
+  using Cfg = MCfg<M, COUT>;
+  constexpr int TF = Cfg::TF;
+  constexpr int NX = Cfg::NX;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_NUM);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = TF * p.K;  // (facet, slot) pairs per tile
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NX; ++i) tc::mbar_init(&bars[B_X_FULL + i], 32), tc::mbar_init(&bars[B_X_FREE + i], 5);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bars[B_Q_FULL + i], 4), tc::mbar_init(&bars[B_Q_FREE + i], 1);
+      tc::mbar_init(&bars[B_D1_FULL + i], 1), tc::mbar_init(&bars[B_D1_FREE + i], 4);
+      tc::mbar_init(&bars[B_B3_FULL + i], 4), tc::mbar_init(&bars[B_B3_FREE + i], 1);
+      tc::mbar_init(&bars[B_D3_FULL + i], 1), tc::mbar_init(&bars[B_D3_FREE + i], 4);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 14) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  {
+    // stale shared memory may hold NaN bit patterns: rows beyond R are multiplied by zero columns of Q
+    uint4* z = reinterpret_cast<uint4*>(smem + Cfg::OFF_X);
+    for (int i = threadIdx.x; i < (Cfg::OFF_EX - Cfg::OFF_X) / 16; i += kMmaThreads) z[i] = make_uint4(0, 0, 0, 0);
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // weight operand -> TMEM: lane = row of [Wh;Wl] (o | COUT + o), column = K pair; un-swizzle the
+    // shared-memory image (16-byte units XOR row & 7) on the way
+    {
+      const int row = warp * 32 + lane;
+#pragma unroll 1
+      for (int mm = 0; mm < M; ++mm) {
+        const uint4* src = p.wimg + (static_cast<size_t>(mm) * 2 * COUT + row) * 8;
+        uint32_t r[32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint4 tq = __ldg(src + (u ^ (row & 7)));
+          r[4 * u] = tq.x, r[4 * u + 1] = tq.y, r[4 * u + 2] = tq.z, r[4 * u + 3] = tq.w;
+        }
+        tc::tmem_st32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + Cfg::W_COL + mm * 32, r);
+      }
+      tc::tc_wait_st();
+      tc::tc_fence_before_sync();
+    }
+  }
+  __syncthreads();
+  tc::tc_fence_after_sync();
+
+  if (warp < 4) {
+    // =========================================================== drain + epilogue (quadrant = warp)
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const int trow = warp * 32 + lane;           // tile row m * TF + f for the drain; [Wh;Wl] row for D3
+    const int m = trow / TF, f = trow % TF;
+    const float wun = __ldg(p.wunscale), xun = __ldg(p.xunscale);
+    float* ex = reinterpret_cast<float*>(smem + Cfg::OFF_EX);
+    const int nh = f, nl = TF + f;               // B3 rows of the hi / lo value of facet f
+    const int b3h_off = m * Cfg::B3_ATOM + (nh >> 3) * 1024 + (nh & 7) * 128;
+    const int b3l_off = m * Cfg::B3_ATOM + (nl >> 3) * 1024 + (nl & 7) * 128;
+
+    float inv_cur[1], inv_nxt[1];   // 1/cnt of the facet this thread finalises in the epilogue
+    auto load_inv = [&](int64_t tile, float (&iv)[1]) {
+      const int64_t r = tile * TF + ((warp * 32 + lane) >> 3);
+      iv[0] = (r < p.rows) ? __ldg(p.pinv + r) : 0.f;
+    };
+    auto epilogue = [&](int t, int64_t tile) {
+      const int buf = t & 1;
+      tc::mbar_wait(&bars[B_D3_FULL + buf], (t >> 1) & 1);
+      if (warp == 0) FGC_TR(0, t + 1, 4);
+      tc::tc_fence_after_sync();
+      uint32_t d[32];
+      tc::tmem_ld32(tmem + lane_base + Cfg::D3_COL + buf * Cfg::NB3, d);
+      tc::tc_wait_ld();
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[B_D3_FREE + buf]);
+      // plane 0: Wh.(Sh + Sl) from the hi rows, plane 1: 2^-11 Wl.Sh from the lo rows; [f][o] fp32
+      const int o = (warp & 1) * 32 + lane;
+      float* pl = ex + (warp >> 1) * (TF * COUT);
+#pragma unroll
+      for (int i = 0; i < TF; ++i)
+        pl[i * COUT + o] = (warp < 2) ? (__uint_as_float(d[i]) + __uint_as_float(d[TF + i]))
+                                      : __uint_as_float(d[i]) * (1.f / 2048.f);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // thread -> (facet ff, 8 consecutive channels): coalesced 16-byte loads and stores
+      const int tid = warp * 32 + lane;
+      const int ff = tid >> 3, oc = (tid & 7) * 8;
+      const int64_t r = tile * TF + ff;
+      const float4 a0 = *reinterpret_cast<const float4*>(ex + ff * COUT + oc);
+      const float4 a1 = *reinterpret_cast<const float4*>(ex + ff * COUT + oc + 4);
+      const float4 c0 = *reinterpret_cast<const float4*>(ex + TF * COUT + ff * COUT + oc);
+      const float4 c1 = *reinterpret_cast<const float4*>(ex + TF * COUT + ff * COUT + oc + 4);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (r < p.rows) {
+        const float inv = inv_cur[0];
+        const float fl = (inv > 0.f || !p.bias_mask) ? 1.f : 0.f;
+        const float sc = inv * xun * wun;
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b + oc));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b + oc + 4));
+        float yv[8] = {fmaf(sc, a0.x + c0.x, fl * b0.x), fmaf(sc, a0.y + c0.y, fl * b0.y),
+                       fmaf(sc, a0.z + c0.z, fl * b0.z), fmaf(sc, a0.w + c0.w, fl * b0.w),
+                       fmaf(sc, a1.x + c1.x, fl * b1.x), fmaf(sc, a1.y + c1.y, fl * b1.y),
+                       fmaf(sc, a1.z + c1.z, fl * b1.z), fmaf(sc, a1.w + c1.w, fl * b1.w)};
+        if (p.act == FGC_ACT_LRELU) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) yv[i] = lrelu_f(yv[i], p.alpha);
+        }
+        float* yr = p.y + r * p.ldy + oc;
+        *reinterpret_cast<float4*>(yr) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+        *reinterpret_cast<float4*>(yr + 4) = make_float4(yv[4], yv[5], yv[6], yv[7]);
+      }
+    };
+
+    int t = 0;
+    int64_t prev_tile = -1;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+      const int buf = t & 1;
+      tc::mbar_wait(&bars[B_D1_FULL + buf], (t >> 1) & 1);
+      if (warp == 0) FGC_TR(0, t, 0);
+      tc::tc_fence_after_sync();
+      uint32_t v0[32], v1[32];
+      tc::tmem_ld32(tmem + lane_base + Cfg::D1_COL + buf * 64, v0);
+      tc::tmem_ld32(tmem + lane_base + Cfg::D1_COL + buf * 64 + 32, v1);
+      tc::tc_wait_ld();
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[B_D1_FREE + buf]);
+      // fp16 hi (truncated to 11 significant bits, exactly representable) + fp16 residual
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const uint32_t* v = (i < 16) ? v0 : v1;
+        const int c = (i & 15) * 2;
+        const float a0 = __uint_as_float(v[c]), a1 = __uint_as_float(v[c + 1]);
+        const float h0 = __uint_as_float(v[c] & 0xFFFFE000u), h1 = __uint_as_float(v[c + 1] & 0xFFFFE000u);
+        const __half2 hh = __floats2half2_rn(h0, h1);
+        const __half2 ll = __floats2half2_rn(a0 - h0, a1 - h1);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      if (warp == 0) FGC_TR(0, t, 1);
+      tc::mbar_wait(&bars[B_B3_FREE + buf], ((t >> 1) & 1) ^ 1);
+      if (warp == 0) FGC_TR(0, t, 2);
+      uint8_t* b3 = smem + Cfg::OFF_B3 + buf * Cfg::B3_BUF;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<uint4*>(b3 + b3h_off + ((j ^ (nh & 7)) << 4)) =
+            make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        *reinterpret_cast<uint4*>(b3 + b3l_off + ((j ^ (nl & 7)) << 4)) =
+            make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[B_B3_FULL + buf]);
+      if (warp == 0) FGC_TR(0, t, 3);
+      load_inv(tile, inv_nxt);   // after the fence: a MEMBAR would wait for it
+      if (t > 0) epilogue(t - 1, prev_tile);
+      if (warp == 0) FGC_TR(0, t, 5);
+      prev_tile = tile;
+      inv_cur[0] = inv_nxt[0];
+    }
+    if (t > 0) epilogue(t - 1, prev_tile);
+  } else if (warp < 12) {
+    // =========================================================== assignments: softmax + Q scatter
+    // Everything these warps read (pair records, own logits, neighbour logits of the chunk's distinct
+    // rows) is staged in the ring slot by the loader: no global load -- and so no load latency and
+    // no MEMBAR stall -- sits between two Q tiles.
+    const int grp = (warp - 4) >> 2;             // group g handles items with it % 2 == g, Q buffer g
+    const int qt = (threadIdx.x - 128) & 127;    // 0..127 within the group
+    const int f = qt >> 3, s = qt & 7;           // facet of the tile, slot lane: slots s, s+8, ...
+    const bool tracer = (warp == 4);
+    int it = 0;
+    int Rn = (blockIdx.x < p.ntiles) ? __ldg(p.pR + blockIdx.x) : 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const bool rv = tile * TF + f < p.rows;
+      uint32_t rec[KP];
+      float uo[M];
+      const int nch = chunks_of(Rn);
+      if (tile + gridDim.x < p.ntiles) Rn = __ldg(p.pR + tile + gridDim.x);
+      bool have = false;
+      for (int c = 0; c < nch; ++c, ++it) {
+        if ((it & 1) != grp) continue;
+        const int xbuf = it % NX, qb = grp;
+        const int itg = it >> 1;                 // this group's item counter
+        const uint8_t* slot = smem + Cfg::OFF_X + xbuf * Cfg::X_BUF;
+        if (tracer) FGC_TR(1, itg, 3);
+        tc::mbar_wait(&bars[B_X_FULL + xbuf], (it / NX) & 1);
+        if (tracer) FGC_TR(1, itg, 4);
+        if (!have) {
+          // pair records and own logits are staged with chunk 0 only; a group that first meets the
+          // tile at a later chunk reads them from global memory (rare: tiles with > 64 distinct rows)
+          have = true;
+          if (c == 0) {
+            const uint16_t* pr = reinterpret_cast<const uint16_t*>(slot + Cfg::SL_PR + 16);
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+              const int k = s + 8 * j;
+              rec[j] = (rv && k < p.K) ? pr[f * p.K + k] : 0u;
+            }
+            const float4* up = reinterpret_cast<const float4*>(slot + Cfg::SL_UO + f * (M * 4));
+#pragma unroll
+            for (int i = 0; i < M; i += 4) {
+              const float4 tq = up[i / 4];
+              uo[i] = tq.x, uo[i + 1] = tq.y, uo[i + 2] = tq.z, uo[i + 3] = tq.w;
+            }
+          } else {
+            const uint16_t* pr = reinterpret_cast<const uint16_t*>(p.ppair + tile * (16 + P * 2) + 16);
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+              const int k = s + 8 * j;
+              rec[j] = (rv && k < p.K) ? __ldg(pr + f * p.K + k) : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < M; i += 4) {
+              float4 tq = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rv) tq = __ldg(reinterpret_cast<const float4*>(p.uvx + (tile * TF + f) * (2 * M) + i));
+              uo[i] = tq.x, uo[i + 1] = tq.y, uo[i + 2] = tq.z, uo[i + 3] = tq.w;
+            }
+          }
+        }
+        if (tracer) FGC_TR(1, itg, 5);
+        uint32_t qhp[KP][M / 2], qlp[KP][M / 2];
+        int col[KP];
+        // branch-free: every lane evaluates all KP pairs (clamped row for the inactive ones), so
+        // the KP softmax chains interleave; inactive pairs are dropped at the scatter
+        float a[KP][M];
+        float rs[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          const int mult = rec[j] >> 10, lidx = rec[j] & 1023;
+          col[j] = (mult && (lidx >> 6) == c) ? (lidx & 63) : -1;
+          const float4* vp = reinterpret_cast<const float4*>(slot + Cfg::SL_VL + (lidx & 63) * (M * 4));
+#pragma unroll
+          for (int i = 0; i < M; i += 4) {
+            const float4 tq = vp[i / 4];
+            a[j][i] = uo[i] + tq.x, a[j][i + 1] = uo[i + 1] + tq.y, a[j][i + 2] = uo[i + 2] + tq.z, a[j][i + 3] = uo[i + 3] + tq.w;
+          }
+          rs[j] = static_cast<float>(mult);
+        }
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          float mx = a[j][0];
+#pragma unroll
+          for (int i = 1; i < M; ++i) mx = fmaxf(mx, a[j][i]);
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < M; ++i) {
+            a[j][i] = exp2f((a[j][i] - mx) * 1.4426950408889634f);
+            sum += a[j][i];
+          }
+          rs[j] = __fdividef(rs[j], sum);
+        }
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+#pragma unroll
+          for (int i = 0; i < M; i += 2) {
+            const float q0 = a[j][i] * rs[j], q1 = a[j][i + 1] * rs[j];
+            const __half2 hh = __floats2half2_rn(q0, q1);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(q0 - hf.x, q1 - hf.y);
+            qhp[j][i / 2] = *reinterpret_cast<const uint32_t*>(&hh);
+            qlp[j][i / 2] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+        }
+        // the staged data of this slot is consumed
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[B_X_FREE + xbuf]);
+        if (tracer) FGC_TR(1, itg, 0);
+        tc::mbar_wait(&bars[B_Q_FREE + qb], (itg & 1) ^ 1);
+        if (tracer) FGC_TR(1, itg, 1);
+        uint8_t* qh = smem + Cfg::OFF_Q + qb * Cfg::Q_BUF;
+        uint8_t* ql = qh + Cfg::Q_PLANE;
+        // zero both planes (consecutive threads, consecutive 16-byte units), then scatter
+        {
+          uint4* z = reinterpret_cast<uint4*>(qh);
+#pragma unroll
+          for (int j = 0; j < Cfg::Q_BUF / 16 / 128; ++j) z[qt + 128 * j] = make_uint4(0, 0, 0, 0);
+        }
+        if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+        else asm volatile("bar.sync 3, 128;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          if (col[j] >= 0) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+              const int row = i * TF + f;    // tile row of (facet f, weight i)
+              const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((col[j] >> 3) ^ (row & 7)) << 4) + (col[j] & 7) * 2;
+              const uint32_t wh = qhp[j][i / 2], wl = qlp[j][i / 2];
+              *reinterpret_cast<uint16_t*>(qh + off) = static_cast<uint16_t>((i & 1) ? (wh >> 16) : (wh & 0xFFFF));
+              *reinterpret_cast<uint16_t*>(ql + off) = static_cast<uint16_t>((i & 1) ? (wl >> 16) : (wl & 0xFFFF));
+            }
+          }
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[B_Q_FULL + qb]);
+        if (tracer) FGC_TR(1, itg, 2);
+      }
+    }
+  } else if (warp == 12 || warp == 13) {
+    // =========================================================== row loaders (cp.async)
+    // Per (tile, chunk): the chunk's distinct rows (fp16 hi|lo image) into the UMMA layout, their
+    // neighbour logits, and for chunk 0 the tile's pair records and own logits.  Completion is
+    // signalled by cp.async.mbarrier.arrive.noinc (no wait, no fence: the loader never blocks on its
+    // own copies); row ids of the next chunk are fetched while the current copies are issued.
+    const int h = lane >> 4, ch = lane & 15;     // lane copies 16-byte chunk `ch` of rows 2i + h
+    const int plane = ch >> 3, cc = ch & 7;
+    const uint32_t xbase = tc::smem_u32(smem + Cfg::OFF_X);
+    const int64_t step = gridDim.x;
+    const int pr_bytes = 16 + P * 2;
+    struct Ids {
+      int rid[kRC / 2];    // rows 2i + h
+      int vid[kRC / 16];   // rows (lane >> 1) + 16 i
+    };
+    auto load_ids = [&](int64_t tile, int c, int R, Ids& d) {
+      const int rc = (tile < p.ntiles) ? min(kRC, R - c * kRC) : 0;
+      const int32_t* rl = p.prow + tile * P + c * kRC;
+#pragma unroll
+      for (int i = 0; i < kRC / 2; ++i) d.rid[i] = (2 * i + h < rc) ? __ldg(rl + 2 * i + h) : -1;
+#pragma unroll
+      for (int i = 0; i < kRC / 16; ++i) d.vid[i] = ((lane >> 1) + 16 * i < rc) ? __ldg(rl + (lane >> 1) + 16 * i) : -1;
+    };
+    // Two loader warps take alternate items (it % 2); each walks the whole (tile, chunk) sequence.
+    // Row ids are double-buffered in registers with compile-time roles (a copy would stall on the
+    // loads just issued).
+    const int me = warp - 12;
+    int it = 0;
+    int64_t tile = blockIdx.x;
+    int c = 0;
+    int R = (tile < p.ntiles) ? __ldg(p.pR + tile) : 0;
+    int Rn = (tile + step < p.ntiles) ? __ldg(p.pR + tile + step) : 0;
+    auto advance = [&]() {   // next item of the sequence
+      ++c;
+      if (c >= chunks_of(R)) {
+        tile += step, c = 0, R = Rn;
+        Rn = (tile + step < p.ntiles) ? __ldg(p.pR + tile + step) : 0;
+      }
+      ++it;
+    };
+    if (me == 1 && tile < p.ntiles) advance();
+    Ids ids[2];
+    if (tile < p.ntiles) load_ids(tile, c, R, ids[0]);
+    auto issue = [&](const Ids& cur, Ids& nxt) {
+      // my next item is two steps ahead
+      const int64_t tile0 = tile;
+      const int c0 = c, it0 = it;
+      advance();
+      if (tile < p.ntiles) advance();
+      load_ids(tile, c, R, nxt);
+      const int buf = it0 % NX;
+      if (me == 0) FGC_TR(2, it0 >> 1, 0);
+      tc::mbar_wait(&bars[B_X_FREE + buf], ((it0 / NX) & 1) ^ 1);
+      if (me == 0) FGC_TR(2, it0 >> 1, 1);
+      const uint32_t sl = xbase + buf * Cfg::X_BUF;
+      const uint32_t xb = sl + plane * Cfg::X_PLANE;
+#pragma unroll
+      for (int i = 0; i < kRC / 2; ++i) {
+        const int row = 2 * i + h;
+        if (cur.rid[i] >= 0)
+          cp_async16(xb + (row >> 3) * 1024 + (row & 7) * 128 + ((cc ^ (row & 7)) << 4),
+                     p.img + static_cast<int64_t>(cur.rid[i]) * 16 + ch);
+      }
+#pragma unroll
+      for (int i = 0; i < kRC / 16; ++i) {
+        const int row = (lane >> 1) + 16 * i;
+        if (cur.vid[i] >= 0)
+          cp_async16(sl + Cfg::SL_VL + row * (M * 4) + (lane & 1) * 16,
+                     p.uvx + static_cast<int64_t>(cur.vid[i]) * (2 * M) + M + (lane & 1) * 4);
+      }
+      if (c0 == 0) {
+        const uint8_t* src = p.ppair + tile0 * pr_bytes;
+        for (int q = lane * 16; q < pr_bytes; q += 512) cp_async16(sl + Cfg::SL_PR + q, src + q);
+        const int64_t r = tile0 * TF + (lane >> 1);
+        if ((lane >> 1) < TF && r < p.rows)
+          cp_async16(sl + Cfg::SL_UO + (lane >> 1) * (M * 4) + (lane & 1) * 16, p.uvx + r * (2 * M) + (lane & 1) * 4);
+      }
+      cp_async_arrive_noinc(&bars[B_X_FULL + buf]);
+      if (me == 0) FGC_TR(2, it0 >> 1, 2);
+    };
+    while (tile < p.ntiles) {
+      issue(ids[0], ids[1]);
+      if (tile >= p.ntiles) break;
+      issue(ids[1], ids[0]);
+    }
+  } else if (warp == 14) {
+    // =========================================================== stage-1 MMA issuer
+    // A = Q (smem, K-major), B = X rows (smem, MN-major)
+    constexpr uint32_t idesc1 = (1u << 4) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t sb = tc::smem_u32(smem);
+    int t = 0, it = 0;
+    int Rn = (blockIdx.x < p.ntiles) ? __ldg(p.pR + blockIdx.x) : 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+      const int R = Rn;
+      if (tile + gridDim.x < p.ntiles) Rn = __ldg(p.pR + tile + gridDim.x);
+      const int nch = chunks_of(R);
+      const int dbuf = t & 1;
+      FGC_TR(3, t, 0);
+      tc::mbar_wait(&bars[B_D1_FREE + dbuf], ((t >> 1) & 1) ^ 1);
+      FGC_TR(3, t, 1);
+      for (int c = 0; c < nch; ++c, ++it) {
+        const int xbuf = it % NX, qb = it & 1;
+        const int rc = min(kRC, R - c * kRC);
+        const int nks = max(1, (rc + 15) >> 4);
+        tc::mbar_wait(&bars[B_X_FULL + xbuf], (it / NX) & 1);
+        FGC_TR(3, t, 7);
+        tc::mbar_wait(&bars[B_Q_FULL + qb], (it >> 1) & 1);
+        FGC_TR(3, t, 2);
+        tc::tc_fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t xh = sb + Cfg::OFF_X + xbuf * Cfg::X_BUF, xl = xh + Cfg::X_PLANE;
+          const uint32_t qh = sb + Cfg::OFF_Q + qb * Cfg::Q_BUF, ql = qh + Cfg::Q_PLANE;
+          const uint32_t d1 = tmem + Cfg::D1_COL + dbuf * 64;
+#pragma unroll 1
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t aqh = tc::smem_desc_k_sw128(qh + ks * 32);
+            const uint64_t aql = tc::smem_desc_k_sw128(ql + ks * 32);
+            const uint64_t bxh = desc_mn_sw128(xh + ks * 2048, 1024, 1024);
+            const uint64_t bxl = desc_mn_sw128(xl + ks * 2048, 1024, 1024);
+            tc::mma_f16_ss(d1, aqh, bxh, idesc1, (c | ks) ? 1u : 0u);
+            tc::mma_f16_ss(d1, aql, bxh, idesc1, 1u);
+            tc::mma_f16_ss(d1, aqh, bxl, idesc1, 1u);
+          }
+          tc::tc_commit(&bars[B_X_FREE + xbuf]);
+          tc::tc_commit(&bars[B_Q_FREE + qb]);
+          if (c == nch - 1) tc::tc_commit(&bars[B_D1_FULL + dbuf]);
+        }
+        __syncwarp();
+      }
+      FGC_TR(3, t, 3);
+    }
+  } else {
+    // =========================================================== stage-2 MMA issuer
+    // A = [Wh;Wl] (TMEM), B = S (smem, K-major)
+    constexpr uint32_t idesc3 = (1u << 4) | ((static_cast<uint32_t>(Cfg::NB3) >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t sb = tc::smem_u32(smem);
+    int t = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+      const int buf = t & 1;
+      FGC_TR(3, t, 4);
+      tc::mbar_wait(&bars[B_B3_FULL + buf], (t >> 1) & 1);
+      tc::mbar_wait(&bars[B_D3_FREE + buf], ((t >> 1) & 1) ^ 1);
+      FGC_TR(3, t, 5);
+      tc::tc_fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t b3 = sb + Cfg::OFF_B3 + buf * Cfg::B3_BUF;
+#pragma unroll 1
+        for (int mm = 0; mm < M; ++mm) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bd = tc::smem_desc_k_sw128(b3 + mm * Cfg::B3_ATOM + ks * 32);
+            tc::mma_f16_ts(tmem + Cfg::D3_COL + buf * Cfg::NB3, tmem + Cfg::W_COL + mm * 32 + ks * 8, bd, idesc3,
+                           (mm | ks) ? 1u : 0u);
+          }
+        }
+        tc::tc_commit(&bars[B_B3_FREE + buf]);
+        tc::tc_commit(&bars[B_D3_FULL + buf]);
+      }
+      __syncwarp();
+      FGC_TR(3, t, 6);
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 14) tc::tmem_dealloc(tmem, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ fp16 hi|lo image of x
+// img[r] = [fp16(x_r * s) (64) | fp16(x_r * s - hi) (64)], s = 2^(126-E) with E the exponent of max|x|
+__global__ void __launch_bounds__(256)
+prep_x_image_kernel(const float* __restrict__ x, int ldx, int64_t rows, const unsigned* __restrict__ maxbits,
+                    uint4* __restrict__ img, float* __restrict__ xunscale) {
+  int E = static_cast<int>((__ldg(maxbits) >> 23) & 0xFF);
+  E = min(max(E, 16), 240);
+  const float sc = __int_as_float((253 - E) << 23);
+  if (blockIdx.x == 0 && threadIdx.x == 0) xunscale[0] = __int_as_float((E + 1) << 23);
+  const int64_t total = rows * 8;  // one thread per 8 channels
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i >> 3;
+    const int j = static_cast<int>(i & 7);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + 2 * j);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + 2 * j + 1);
+    const float v[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, b.x * sc, b.y * sc, b.z * sc, b.w * sc};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __half2 hh = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(v[2 * q] - hf.x, v[2 * q + 1] - hf.y);
+      hi[q] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[q] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    img[r * 16 + j] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    img[r * 16 + 8 + j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+__global__ void absmax2_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(x) + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// ------------------------------------------------------------------ tile plan
+// One block per tile, one thread per (facet, slot) pair.  Distinct rows are numbered in ascending
+// row order; duplicates inside a facet's list collapse onto the first occurrence with a multiplicity
+// (q depends only on the (facet, row) pair, so k equal ids contribute k * q).
+__global__ void __launch_bounds__(512)
+build_conv_plan_kernel(const int32_t* __restrict__ adj, int64_t rows, int N, int K, int TF,
+                       uint8_t* __restrict__ ppair, int32_t* __restrict__ prow, int32_t* __restrict__ pR,
+                       float* __restrict__ pinv) {
+  extern __shared__ int32_t sm[];
+  const int P = TF * K;
+  int32_t* ids = sm;          // [P] global row or -1
+  int32_t* first = sm + P;    // [P] first occurrence in the tile
+  int32_t* cnt = sm + 2 * P;  // [TF]
+  const int pidx = threadIdx.x;
+  const int64_t tile = blockIdx.x;
+  const int f = pidx / K, k = pidx % K;
+  const int64_t r = tile * TF + f;
+  if (pidx < TF) cnt[pidx] = 0;
+  __syncthreads();
+  int32_t g = -1;
+  if (pidx < P && r < rows) {
+    const int id = __ldg(adj + r * K + k);
+    if (id != 0) atomicAdd(&cnt[f], 1);
+    if (id > 0 && id <= N) g = static_cast<int32_t>((r / N) * N + id - 1);
+  }
+  if (pidx < P) ids[pidx] = g;
+  __syncthreads();
+  bool first_tile = g >= 0, first_facet = g >= 0;
+  int mult = 0;
+  if (g >= 0) {
+    for (int q = 0; q < pidx; ++q)
+      if (ids[q] == g) {
+        first_tile = false;
+        if (q >= f * K) first_facet = false;
+      }
+    for (int q = f * K; q < (f + 1) * K; ++q) mult += (ids[q] == g);
+  }
+  if (pidx < P) first[pidx] = first_tile ? 1 : 0;
+  const int R = __syncthreads_count(first_tile);
+  int lidx = 0;
+  if (g >= 0) {
+    for (int q = 0; q < P; ++q) lidx += (first[q] && ids[q] < g);
+  }
+  if (first_tile) prow[tile * P + lidx] = g;
+  uint8_t* blk = ppair + tile * (16 + 2 * P);   // header {R, 0, 0, 0} + P pair records
+  if (pidx < P)
+    reinterpret_cast<uint16_t*>(blk + 16)[pidx] = (g >= 0) ? static_cast<uint16_t>(lidx | ((first_facet ? mult : 0) << 10)) : 0;
+  if (pidx < 4) reinterpret_cast<int32_t*>(blk)[pidx] = (pidx == 0) ? R : 0;
+  if (pidx == 0) pR[tile] = R;
+  if (pidx < TF && tile * TF + pidx < rows) pinv[tile * TF + pidx] = cnt[pidx] ? 1.f / static_cast<float>(cnt[pidx]) : 0.f;
+}
+
+struct PlanLayout {
+  int64_t rows, ntiles;
+  int K, TF;
+  size_t off_R, off_inv, off_row, off_pair, total;
+  PlanLayout(int64_t rows_, int K_, int M) : rows(rows_), K(K_), TF(128 / M) {
+    ntiles = (rows + TF - 1) / TF;
+    size_t o = 256;  // header
+    off_R = o, o = align_up(o + static_cast<size_t>(ntiles) * 4, 256);
+    off_inv = o, o = align_up(o + static_cast<size_t>(rows) * 4, 256);
+    off_row = o, o = align_up(o + static_cast<size_t>(ntiles) * TF * K * 4, 256);
+    off_pair = o, o = align_up(o + static_cast<size_t>(ntiles) * (16 + TF * K * 2), 256);
+    total = o;
+  }
+};
+
+}  // namespace
+
+bool conv_mma_supported(int Cin, int Cw, int Cout, int M, int K) {
+  return Cw == 64 && Cout == 64 && M == 8 && K <= 32 && Cin % 4 == 0;
+}
+
+size_t conv_plan_bytes(int64_t rows, int K, int M) {
+  if (M < 1 || 128 / M < 1) return 0;
+  return PlanLayout(rows, K, M).total;
+}
+
+int build_conv_plan(const int32_t* adj, int B, int N, int K, int M, void* plan, size_t plan_bytes, cudaStream_t st) {
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  FGC_UNSUPPORTED(M != 8, "conv plan: only M = 8 tiles are implemented (M=%d)", M);
+  const PlanLayout L(rows, K, M);
+  FGC_REQUIRE(plan_bytes >= L.total, "conv plan: buffer too small (%zu given, %zu needed)", plan_bytes, L.total);
+  FGC_REQUIRE(L.TF * K <= 512, "conv plan: TF*K = %d exceeds 512", L.TF * K);
+  char* base = static_cast<char*>(plan);
+  const int P = L.TF * K;
+  const int threads = ((P + 31) / 32) * 32;
+  build_conv_plan_kernel<<<static_cast<unsigned>(L.ntiles), threads, (2 * P + L.TF) * 4, st>>>(
+      adj, rows, N, K, L.TF, reinterpret_cast<uint8_t*>(base + L.off_pair), reinterpret_cast<int32_t*>(base + L.off_row),
+      reinterpret_cast<int32_t*>(base + L.off_R), reinterpret_cast<float*>(base + L.off_inv));
+  FGC_LAUNCHED("build_conv_plan_kernel");
+  return FGC_OK;
+}
+
+size_t conv_mma_workspace(int64_t rows) {
+  return ws_bytes(static_cast<size_t>(rows) * 256, 1) + ws_bytes(64, 4);
+}
+
+// img_ws: conv_mma_workspace(rows) bytes; wimg_ws: the weight image workspace of conv_fwd_tc
+int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, void* img_ws, void* wimg_ws,
+                    cudaStream_t st) {
+  using Cfg = MCfg<8, 64>;
+  const PlanLayout L(p.rows, p.K, p.M);
+  const char* pb = static_cast<const char*>(plan);
+  Workspace ws(img_ws, conv_mma_workspace(p.rows));
+  uint4* img = reinterpret_cast<uint4*>(ws.take<char>(static_cast<size_t>(p.rows) * 256));
+  unsigned* scal = ws.take<unsigned>(16);  // [0] max bits, [1] x unscale
+  FGC_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(unsigned), st));
+  const int ab = num_sms() * 8;
+  // the row stride may exceed Cw (concat tails): only the first 64 channels of every row are used
+  if (p.Cin == kC) {
+    absmax2_kernel<<<ab, 256, 0, st>>>(p.x, p.rows * (kC / 4), scal);
+  } else {
+    // strided rows: scan the whole tensor (a superset bound is still a valid scale)
+    absmax2_kernel<<<ab, 256, 0, st>>>(p.x, p.rows * (p.Cin / 4), scal);
+  }
+  FGC_LAUNCHED("absmax_kernel");
+  prep_x_image_kernel<<<ab, 256, 0, st>>>(p.x, p.Cin, p.rows, scal, img, reinterpret_cast<float*>(scal + 1));
+  FGC_LAUNCHED("prep_x_image_kernel");
+  const size_t wbytes = static_cast<size_t>(p.M) * 2 * p.Cout * 128;
+  float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + wbytes);
+  int rc = launch_prep_w_image(W0, wimg_ws, p.M, p.Cout, st);
+  if (rc) return rc;
+  MmaParams mp{};
+  mp.img = img, mp.xunscale = reinterpret_cast<const float*>(scal + 1), mp.uvx = p.uvx, mp.adj = p.adj;
+  mp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), mp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
+  mp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), mp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
+  mp.wimg = static_cast<const uint4*>(wimg_ws), mp.wunscale = wunscale, mp.b = p.b, mp.y = p.y;
+  mp.rows = p.rows, mp.ntiles = L.ntiles, mp.N = p.N, mp.K = p.K, mp.ldy = p.Cout, mp.bias_mask = p.bias_mask;
+  mp.act = p.act, mp.alpha = p.alpha;
+  static const bool trace = getenv("FGC_MMA_TRACE") != nullptr;
+  mp.trace = trace ? 1 : 0;
+  void (*kern)(const MmaParams) = conv_mma_kernel<8, 64, 4>;
+  if (p.K <= 16) kern = conv_mma_kernel<8, 64, 2>;
+  else if (p.K <= 24) kern = conv_mma_kernel<8, 64, 3>;
+  FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  int64_t grid = num_sms();
+  if (grid > L.ntiles) grid = L.ntiles;
+  if (grid < 1) grid = 1;
+  kern<<<static_cast<unsigned>(grid), kMmaThreads, Cfg::SMEM_BYTES, st>>>(mp);
+  FGC_LAUNCHED("conv_mma_kernel");
+  return FGC_OK;
+}
+
+int debug_mma_trace(int64_t* out, int n) {
+  long long host[4 * 32 * 8];
+  FGC_CUDA(cudaDeviceSynchronize());
+  FGC_CUDA(cudaMemcpyFromSymbol(host, g_mma_trace, sizeof(host)));
+  for (int i = 0; i < n && i < 4 * 32 * 8; ++i) out[i] = host[i];
+  return FGC_OK;
+}
+
+}  // namespace fgc

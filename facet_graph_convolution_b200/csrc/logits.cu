@@ -1,0 +1,284 @@
+// Warp-cooperative fast paths of the three logit kernels (bandwidth-bound passes over x):
+//   assign_logits   uvx[r] = [u;v] . x_r[window] + [c;0]            reference Code/model.py:74-95
+//   logits_bwd_x    gx[r, window] += d_uvx[r] . [u;v]
+//   logits_bwd_p    gu, gv, gc = sum_r d_uvx[r] (x) x_r[window]      (fixed-order partial sums)
+// LPR lanes share a row (lane owns 4 consecutive channels -> every row access is one coalesced
+// 16-byte load per lane), the [u;v] coefficients of the lane's channels live in registers, and the
+// per-row reduction over channels is a transpose-reduce over the LPR lanes.  The generic
+// thread-per-row kernels in conv_fwd.cu / conv_bwd.cu remain for every other shape.
+#include "conv_common.cuh"
+#include "conv_launch.cuh"
+
+namespace fgc {
+
+namespace {
+
+// v[0..OP) per lane, LPR lanes of a row -> each lane ends with OP/LPR sums: outputs gl*(OP/LPR)+i
+template <int OP, int LPR>
+__device__ __forceinline__ void transpose_reduce(float (&v)[OP], int gl) {
+  int h = OP / 2;
+#pragma unroll
+  for (int bit = LPR / 2; bit >= 1; bit >>= 1, h >>= 1) {
+    const bool up = (gl & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < OP / 2; ++i) {
+      if (i < h) {
+        const float keep = up ? v[i + h] : v[i], send = up ? v[i] : v[i + h];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      }
+    }
+  }
+}
+
+struct LgParams {
+  const float* x;
+  const float* u;
+  const float* v;
+  const float* c;
+  float* uvx;          // fwd: out; bwd: d_uvx in
+  float* gx;
+  float* part;
+  int64_t rows, rows_per_chunk;
+  int Cin, Ca0, Ca, M;
+};
+
+// coefficients of this lane's 4 channels: w[o][0..3], o < 2M (zero beyond Ca / 2M)
+template <int OP>
+__device__ __forceinline__ void load_coeffs(const LgParams& p, int gl, float (&w)[OP][4]) {
+#pragma unroll
+  for (int o = 0; o < OP; ++o)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = 4 * gl + j;
+      float t = 0.f;
+      if (o < 2 * p.M && cc < p.Ca) t = (o < p.M) ? __ldg(p.u + o * p.Ca + cc) : __ldg(p.v + (o - p.M) * p.Ca + cc);
+      w[o][j] = t;
+    }
+}
+
+template <int OP, int LPR>
+__global__ void __launch_bounds__(256)
+assign_logits_warp_kernel(const LgParams p) {
+  constexpr int RPW = 32 / LPR, OPL = OP / LPR;
+  const int lane = threadIdx.x & 31, gl = lane % LPR, sub = lane / LPR;
+  const int O = 2 * p.M;
+  float w[OP][4];
+  load_coeffs<OP>(p, gl, w);
+  float cb[OPL];
+#pragma unroll
+  for (int i = 0; i < OPL; ++i) {
+    const int o = gl * OPL + i;
+    cb[i] = (o < p.M) ? __ldg(p.c + o) : 0.f;
+  }
+  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const bool act = 4 * gl < p.Ca;
+  for (int64_t r0 = wid * RPW; r0 < p.rows; r0 += 2 * nw * RPW) {
+    // two row groups per iteration: both loads are in flight before the first is consumed
+    const int64_t ra = r0 + sub, rb = r0 + nw * RPW + sub;
+    float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+    if (ra < p.rows && act) xa = __ldg(reinterpret_cast<const float4*>(p.x + ra * p.Cin + p.Ca0) + gl);
+    if (rb < p.rows && act) xb = __ldg(reinterpret_cast<const float4*>(p.x + rb * p.Cin + p.Ca0) + gl);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const float4 xv = half ? xb : xa;
+      const int64_t r = half ? rb : ra;
+      float a[OP];
+#pragma unroll
+      for (int o = 0; o < OP; ++o) a[o] = fmaf(xv.x, w[o][0], fmaf(xv.y, w[o][1], fmaf(xv.z, w[o][2], xv.w * w[o][3])));
+      transpose_reduce<OP, LPR>(a, gl);
+      if (r < p.rows) {
+#pragma unroll
+        for (int i = 0; i < OPL; ++i) {
+          const int o = gl * OPL + i;
+          if (o < O) p.uvx[r * O + o] = a[i] + cb[i];
+        }
+      }
+    }
+  }
+}
+
+template <int OP, int LPR>
+__global__ void __launch_bounds__(256)
+logits_bwd_x_warp_kernel(const LgParams p) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, gl = lane % LPR, sub = lane / LPR;
+  const int O = 2 * p.M;
+  float w[OP][4];
+  load_coeffs<OP>(p, gl, w);
+  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const bool act = 4 * gl < p.Ca;
+  for (int64_t r0 = wid * RPW; r0 < p.rows; r0 += nw * RPW) {
+    const int64_t r = r0 + sub;
+    if (r >= p.rows || !act) continue;
+    float d[OP];
+    if ((O & 3) == 0) {
+#pragma unroll
+      for (int o = 0; o < OP; o += 4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < O) t = __ldg(reinterpret_cast<const float4*>(p.uvx + r * O + o));
+        d[o] = t.x, d[o + 1] = t.y, d[o + 2] = t.z, d[o + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < OP; ++o) d[o] = (o < O) ? __ldg(p.uvx + r * O + o) : 0.f;
+    }
+    float4* gp = reinterpret_cast<float4*>(p.gx + r * p.Cin + p.Ca0) + gl;
+    float4 g = *gp;
+#pragma unroll
+    for (int o = 0; o < OP; ++o) {
+      g.x = fmaf(d[o], w[o][0], g.x), g.y = fmaf(d[o], w[o][1], g.y);
+      g.z = fmaf(d[o], w[o][2], g.z), g.w = fmaf(d[o], w[o][3], g.w);
+    }
+    *gp = g;
+  }
+}
+
+// one CTA per chunk of rows; warps stride the chunk's rows, fixed-order reduction over the warps
+template <int OP, int LPR>
+__global__ void __launch_bounds__(256)
+logits_bwd_p_warp_kernel(const LgParams p) {
+  constexpr int RPW = 32 / LPR;
+  extern __shared__ float red[];   // [warps * RPW][OP * LPR * 4 + OP]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % LPR, sub = lane / LPR;
+  const int nwarp = blockDim.x >> 5;
+  const int O = 2 * p.M;
+  float acc[OP][4];
+  float gc[OP];
+#pragma unroll
+  for (int o = 0; o < OP; ++o) {
+    acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f;
+    gc[o] = 0.f;
+  }
+  const int64_t rb = static_cast<int64_t>(blockIdx.x) * p.rows_per_chunk;
+  const int64_t re = min(p.rows, rb + p.rows_per_chunk);
+  const bool act = 4 * gl < p.Ca;
+  for (int64_t r0 = rb + warp * RPW; r0 < re; r0 += nwarp * RPW) {
+    const int64_t r = r0 + sub;
+    if (r >= re) continue;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) xv = __ldg(reinterpret_cast<const float4*>(p.x + r * p.Cin + p.Ca0) + gl);
+    float d[OP];
+    if ((O & 3) == 0) {
+#pragma unroll
+      for (int o = 0; o < OP; o += 4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < O) t = __ldg(reinterpret_cast<const float4*>(p.uvx + r * O + o));
+        d[o] = t.x, d[o + 1] = t.y, d[o + 2] = t.z, d[o + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < OP; ++o) d[o] = (o < O) ? __ldg(p.uvx + r * O + o) : 0.f;
+    }
+#pragma unroll
+    for (int o = 0; o < OP; ++o) {
+      acc[o][0] = fmaf(d[o], xv.x, acc[o][0]), acc[o][1] = fmaf(d[o], xv.y, acc[o][1]);
+      acc[o][2] = fmaf(d[o], xv.z, acc[o][2]), acc[o][3] = fmaf(d[o], xv.w, acc[o][3]);
+      if (gl == 0) gc[o] += d[o];
+    }
+  }
+  // slot s = warp * RPW + sub holds this lane group's partials: [o][c] then gc[o]
+  const int slot_floats = OP * LPR * 4 + OP;
+  float* my = red + (warp * RPW + sub) * slot_floats;
+#pragma unroll
+  for (int o = 0; o < OP; ++o) {
+    *reinterpret_cast<float4*>(my + (o * LPR + gl) * 4) = make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
+    if (gl == 0) my[OP * LPR * 4 + o] = gc[o];
+  }
+  __syncthreads();
+  const int nslot = nwarp * RPW;
+  const int nout = O * p.Ca;
+  float* out = p.part + static_cast<int64_t>(blockIdx.x) * (nout + p.M);
+  for (int e = threadIdx.x; e < nout + p.M; e += blockDim.x) {
+    int idx;
+    if (e < nout) {
+      const int o = e / p.Ca, cc = e % p.Ca;
+      idx = (o * LPR + (cc >> 2)) * 4 + (cc & 3);
+    } else {
+      idx = OP * LPR * 4 + (e - nout);
+    }
+    float a = 0.f;
+    for (int s = 0; s < nslot; ++s) a += red[s * slot_floats + idx];
+    out[e] = a;
+  }
+}
+
+template <int OP, int LPR>
+int run_assign(const LgParams& p, cudaStream_t st) {
+  const int64_t rows_per_block = 8 * (32 / LPR);
+  int64_t blocks = (p.rows + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  assign_logits_warp_kernel<OP, LPR><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
+  FGC_LAUNCHED("assign_logits_kernel");
+  return FGC_OK;
+}
+
+template <int OP, int LPR>
+int run_bwd_x(const LgParams& p, cudaStream_t st) {
+  const int64_t rows_per_block = 8 * (32 / LPR);
+  int64_t blocks = (p.rows + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  logits_bwd_x_warp_kernel<OP, LPR><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
+  FGC_LAUNCHED("logits_bwd_x_kernel");
+  return FGC_OK;
+}
+
+template <int OP, int LPR>
+int run_bwd_p(const LgParams& p, int chunks, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(8 * (32 / LPR)) * (OP * LPR * 4 + OP) * 4;
+  FGC_CUDA(cudaFuncSetAttribute(logits_bwd_p_warp_kernel<OP, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  logits_bwd_p_warp_kernel<OP, LPR><<<chunks, 256, smem, st>>>(p);
+  FGC_LAUNCHED("logits_bwd_p_kernel");
+  return FGC_OK;
+}
+
+// 0 = no fast path; otherwise lanes per row
+int fast_lpr(int Cin, int Ca0, int Ca, int M) {
+  if (Cin % 4 || Ca0 % 4 || Ca % 4 || M > 16) return 0;
+  if (Ca <= 64) return 16;
+  if (Ca <= 128) return 32;
+  return 0;
+}
+
+}  // namespace
+
+#define FGC_LG_DISPATCH(FN, ...)                                              \
+  do {                                                                        \
+    const int O = 2 * M;                                                      \
+    if (lpr == 16) {                                                          \
+      if (O <= 16) return FN<16, 16>(__VA_ARGS__);                            \
+      return FN<32, 16>(__VA_ARGS__);                                         \
+    }                                                                         \
+    return FN<32, 32>(__VA_ARGS__);                                           \
+  } while (0)
+
+bool logits_fast_supported(int Cin, int Ca0, int Ca, int M) { return fast_lpr(Cin, Ca0, Ca, M) != 0; }
+
+int launch_assign_logits_fast(const float* x, const float* u, const float* v, const float* c, float* uvx,
+                              int64_t rows, int Cin, int Ca0, int Ca, int M, cudaStream_t st) {
+  const int lpr = fast_lpr(Cin, Ca0, Ca, M);
+  LgParams p{x, u, v, c, uvx, nullptr, nullptr, rows, 0, Cin, Ca0, Ca, M};
+  FGC_LG_DISPATCH(run_assign, p, st);
+}
+
+int launch_logits_bwd_x_fast(const float* d_uvx, const float* u, const float* v, float* gx, int64_t rows, int Cin,
+                             int Ca0, int Ca, int M, cudaStream_t st) {
+  const int lpr = fast_lpr(Cin, Ca0, Ca, M);
+  LgParams p{nullptr, u, v, nullptr, const_cast<float*>(d_uvx), gx, nullptr, rows, 0, Cin, Ca0, Ca, M};
+  FGC_LG_DISPATCH(run_bwd_x, p, st);
+}
+
+int launch_logits_bwd_p_fast(const float* x, const float* d_uvx, float* part, int64_t rows, int64_t rows_per_chunk,
+                             int chunks, int Cin, int Ca0, int Ca, int M, cudaStream_t st) {
+  const int lpr = fast_lpr(Cin, Ca0, Ca, M);
+  LgParams p{x, nullptr, nullptr, nullptr, const_cast<float*>(d_uvx), nullptr, part, rows, rows_per_chunk, Cin, Ca0, Ca, M};
+  FGC_LG_DISPATCH(run_bwd_p, p, chunks, st);
+}
+
+}  // namespace fgc

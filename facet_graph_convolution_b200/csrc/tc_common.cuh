@@ -42,6 +42,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of the (converged) warp, chosen by hardware.  Unlike `lane == 0`, ptxas knows the branch
+// is taken by exactly one thread, so uniform-datapath instructions (tcgen05.mma / commit) inside it
+// are not wrapped in a per-active-thread election loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

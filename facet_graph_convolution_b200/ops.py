@@ -62,7 +62,27 @@ def conv_shape(x, adj, W0, u, cw=None, ca0=0, ca=None) -> ConvShape:
 
 
 # ----------------------------------------------------------------------------- convolution
-def conv_fwd(x, adj, W0, b, u, v, c, bias_mask=True, act=ACT_NONE, alpha=0.1, cw=None, ca0=0, ca=None):
+class ConvPlan:
+    """Caller-owned tile plan of an adjacency (built once, reused by every dense layer that runs on
+    it): distinct neighbour rows per tile of 128/M facets + per-slot local indices.  ``nbytes == 0``
+    means the shape has no planned path and conv_fwd ignores the plan."""
+
+    def __init__(self, adj: torch.Tensor, M: int):
+        L = _lib.lib()
+        adj = _i32(adj, "adj")
+        B, N, K = adj.shape
+        self.shape, self.M = (B, N, K), int(M)
+        self.nbytes = int(L.fgc_conv_plan_bytes(B, N, K, int(M)))
+        self.buf = None
+        if self.nbytes:
+            self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=adj.device)
+            with torch.cuda.device(adj.device):
+                check(L.fgc_build_conv_plan(_p(adj), B, N, K, int(M), _p(self.buf), self.nbytes, _stream(adj)),
+                      "fgc_build_conv_plan")
+
+
+def conv_fwd(x, adj, W0, b, u, v, c, bias_mask=True, act=ACT_NONE, alpha=0.1, cw=None, ca0=0, ca=None,
+             plan: Optional[ConvPlan] = None):
     """y[B,N,Cout] of the facet-graph convolution (reference Code/model.py:427-504)."""
     L = _lib.lib()
     x, W0, b, u, v, c = (_f32(t, n) for t, n in ((x, "x"), (W0, "W0"), (b, "b"), (u, "u"), (v, "v"), (c, "c")))
@@ -72,9 +92,17 @@ def conv_fwd(x, adj, W0, b, u, v, c, bias_mask=True, act=ACT_NONE, alpha=0.1, cw
     with torch.cuda.device(x.device):
         nws = L.fgc_conv_fwd_workspace(C.byref(s))
         ws = _ws(nws, x)
-        check(L.fgc_conv_fwd(C.byref(s), _p(x), _p(adj), _p(W0), _p(b), _p(u), _p(v), _p(c), _p(y),
-                             int(bool(bias_mask)), int(act), float(alpha), _p(ws), ws.numel(), _stream(x)),
-              "fgc_conv_fwd")
+        if plan is not None and plan.buf is not None:
+            if plan.shape != (s.B, s.N, s.K) or plan.M != s.M:
+                raise _lib.FacetConvError("conv plan built for %s/M=%d, layer is %s/M=%d"
+                                          % (plan.shape, plan.M, (s.B, s.N, s.K), s.M))
+            check(L.fgc_conv_fwd_planned(C.byref(s), _p(x), _p(adj), _p(plan.buf), _p(W0), _p(b), _p(u), _p(v),
+                                         _p(c), _p(y), int(bool(bias_mask)), int(act), float(alpha), _p(ws),
+                                         ws.numel(), _stream(x)), "fgc_conv_fwd_planned")
+        else:
+            check(L.fgc_conv_fwd(C.byref(s), _p(x), _p(adj), _p(W0), _p(b), _p(u), _p(v), _p(c), _p(y),
+                                 int(bool(bias_mask)), int(act), float(alpha), _p(ws), ws.numel(), _stream(x)),
+                  "fgc_conv_fwd")
     return y
 
 

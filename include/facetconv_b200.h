@@ -98,6 +98,25 @@ FGC_API int fgc_conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t*
                  int bias_mask, int act, float alpha, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* Tile plan (caller-owned cache, built once per adjacency like the reverse adjacency below; pure
+ * index work on adj, bit-exact): for every tile of 128/M consecutive facets the list of distinct
+ * neighbour rows it touches and, per (facet, slot), the row's local index and the multiplicity of
+ * repeated ids.  With a plan the dense layers run the dense-assignment tcgen05 path, in which each
+ * neighbour row is fetched once per tile.  fgc_conv_plan_bytes returns 0 for shapes without a
+ * planned path (then pass plan = NULL / use fgc_conv_fwd).  fgc_conv_fwd_planned computes exactly
+ * what fgc_conv_fwd computes (same reference lines, Code/model.py:427-504). */
+FGC_API size_t fgc_conv_plan_bytes(int B, int N, int K, int M);
+FGC_API int fgc_build_conv_plan(const int32_t* adj, int B, int N, int K, int M, void* plan,
+                        size_t plan_bytes, void* stream);
+FGC_API int fgc_conv_fwd_planned(const fgc_conv_shape* s, const float* x, const int32_t* adj,
+                         const void* plan, const float* W0, const float* b, const float* u,
+                         const float* v, const float* c, float* y, int bias_mask, int act,
+                         float alpha, void* workspace, size_t workspace_bytes, void* stream);
+
+/* diagnostics: with FGC_MMA_TRACE set in the environment the planned kernel records clock64 stamps of
+ * its pipeline roles for CTA 0 (4 roles x 32 tiles x 8 events); this copies them out (synchronises). */
+FGC_API int fgc_debug_trace(int64_t* out, int n);
+
 /* Reverse adjacency (caller-owned cache, built once per adjacency; replaces the scatter of
  * TF's gather gradient, UnsortedSegmentSum): for every target row t = b*N + j the list of
  * edge ids e = (b*N + n)*K + k with adj[b,n,k] == j+1, ascending.  rev_ptr[B*N+1],

@@ -38,7 +38,7 @@ def test_patch_sharded_inference_matches_oracle():
         return fm.normalizeTensor(y).cpu().numpy()
 
     def fwd_oracle(p):
-        y = cf.net_forward(p.x[None].astype(np.float64), [a[None] for a in p.adjs], params)
+        y = cf.net_forward(p.x[None].astype(np.float64), [a[None] for a in p.adjs], cf.split_net_params(params))
         return cf.normalize_tensor(y)
 
     got = P.infer_sharded(pts, nf, fwd_gpu, 0, 1)
@@ -68,7 +68,8 @@ def test_training_step_reduces_loss_and_matches_oracle_loss():
     with torch.no_grad():
         y0 = net(x, adjs)
     ref_loss = cf.face_normals_loss(cf.normalize_tensor(cf.net_forward(p.x[None].astype(np.float64),
-                                                                       [a[None] for a in p.adjs], params)),
+                                                                       [a[None] for a in p.adjs],
+                                                                       cf.split_net_params(params))),
                                     pc.x[None, :, :3].astype(np.float64))
     with torch.no_grad():
         l0 = float(fm.faceNormalsLoss(fm.normalizeTensor(y0), gt))
