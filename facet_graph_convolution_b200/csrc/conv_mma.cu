@@ -16,9 +16,11 @@
 //             A = the resident swizzled weight image shared with conv_fwd_tc.cu.
 //   epilogue  y = act( scale_f * (Wh.Sh + Wh.Sl + 2^-11 Wl.Sh) + flag_f * b )
 //
-// Warp roles (one persistent CTA per SM, 16 warps): 0-3 drain + epilogue (TMEM lane quadrants),
-// 4-7 / 8-11 two assignment groups (softmax, Q scatter; alternate chunks, one Q buffer each),
-// 12-13 row loaders (cp.async, alternate chunks), 14 stage-1 MMA issuer, 15 stage-2 MMA issuer.
+// Warp roles (one persistent CTA per SM, 20 warps): 0-3 drain (S: TMEM -> fp16 hi/lo -> smem),
+// 4-7 epilogue (Y: TMEM -> global) -- both sets aligned to the TMEM lane quadrants; the drain warps
+// never touch global memory, so their proxy fence (a MEMBAR) only waits for their own shared stores --
+// 8-11 / 12-15 two assignment groups (softmax, Q scatter; alternate chunks, one Q buffer each),
+// 16-17 row loaders (cp.async, alternate chunks), 18 stage-1 MMA issuer, 19 stage-2 MMA issuer.
 #include "conv_common.cuh"
 #include "conv_launch.cuh"
 #include <stdlib.h>
@@ -33,7 +35,7 @@ namespace {
 
 constexpr int kC = 64;              // aggregation channels
 constexpr int kRC = 64;             // distinct rows per chunk (one K atom of Q)
-constexpr int kMmaThreads = 16 * 32;
+constexpr int kMmaThreads = 20 * 32;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -75,7 +77,7 @@ struct MCfg {
   static constexpr int Q_BUF = 2 * Q_PLANE;          // hi | lo
   static constexpr int B3_ATOM = NB3 * 128;          // [NB3 rows][64 K] halves
   static constexpr int B3_BUF = M * B3_ATOM;
-  static constexpr int EX_BYTES = 2 * TF * COUT * 4; // epilogue exchange: two [TF][COUT] fp32 planes
+  static constexpr int EX_BYTES = 0;
   static constexpr int OFF_X = 0;
   static constexpr int OFF_Q = OFF_X + NX * X_BUF;
   static constexpr int OFF_B3 = OFF_Q + 2 * Q_BUF;
@@ -157,7 +159,7 @@ conv_mma_kernel(const MmaParams p) {
     }
     tc::mbar_fence_init();
   }
-  if (warp == 14) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 18) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   {
     // stale shared memory may hold NaN bit patterns: rows beyond R are multiplied by zero columns of Q
     uint4* z = reinterpret_cast<uint4*>(smem + Cfg::OFF_X);
@@ -170,10 +172,11 @@ conv_mma_kernel(const MmaParams p) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 4) {
-    // weight operand -> TMEM: lane = row of [Wh;Wl] (o | COUT + o), column = K pair; un-swizzle the
-    // shared-memory image (16-byte units XOR row & 7) on the way
+    // weight operand -> TMEM, column = K pair; un-swizzle the shared-memory image (16-byte units XOR
+    // row & 7) on the way.  Lane 32q + 16h + i holds row h*COUT + 16q + i of [Wh;Wl]: the hi and lo
+    // rows of output channel 16q + i sit in the same warp, so the epilogue combines them by shuffle.
     {
-      const int row = warp * 32 + lane;
+      const int row = ((lane >> 4) & 1) * COUT + warp * 16 + (lane & 15);
 #pragma unroll 1
       for (int mm = 0; mm < M; ++mm) {
         const uint4* src = p.wimg + (static_cast<size_t>(mm) * 2 * COUT + row) * 8;
@@ -193,25 +196,80 @@ conv_mma_kernel(const MmaParams p) {
   tc::tc_fence_after_sync();
 
   if (warp < 4) {
-    // =========================================================== drain + epilogue (quadrant = warp)
+    // =========================================================== drain: S (TMEM) -> fp16 hi/lo -> B3
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    const int trow = warp * 32 + lane;           // tile row m * TF + f for the drain; [Wh;Wl] row for D3
+    const int trow = warp * 32 + lane;           // tile row m * TF + f
     const int m = trow / TF, f = trow % TF;
-    const float wun = __ldg(p.wunscale), xun = __ldg(p.xunscale);
-    float* ex = reinterpret_cast<float*>(smem + Cfg::OFF_EX);
     const int nh = f, nl = TF + f;               // B3 rows of the hi / lo value of facet f
     const int b3h_off = m * Cfg::B3_ATOM + (nh >> 3) * 1024 + (nh & 7) * 128;
     const int b3l_off = m * Cfg::B3_ATOM + (nl >> 3) * 1024 + (nl & 7) * 128;
-
-    float inv_cur[1], inv_nxt[1];   // 1/cnt of the facet this thread finalises in the epilogue
-    auto load_inv = [&](int64_t tile, float (&iv)[1]) {
-      const int64_t r = tile * TF + ((warp * 32 + lane) >> 3);
-      iv[0] = (r < p.rows) ? __ldg(p.pinv + r) : 0.f;
-    };
-    auto epilogue = [&](int t, int64_t tile) {
+    int t = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
       const int buf = t & 1;
+      tc::mbar_wait(&bars[B_D1_FULL + buf], (t >> 1) & 1);
+      if (warp == 0) FGC_TR(0, t, 0);
+      tc::tc_fence_after_sync();
+      uint8_t* b3 = smem + Cfg::OFF_B3 + buf * Cfg::B3_BUF;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem + lane_base + Cfg::D1_COL + buf * 64 + half * 32, v);
+        tc::tc_wait_ld();
+        if (half == 1) {
+          tc::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bars[B_D1_FREE + buf]);
+        }
+        // fp16 hi (truncated to 11 significant bits, exactly representable) + fp16 residual
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a0 = __uint_as_float(v[2 * i]), a1 = __uint_as_float(v[2 * i + 1]);
+          const float h0 = __uint_as_float(v[2 * i] & 0xFFFFE000u), h1 = __uint_as_float(v[2 * i + 1] & 0xFFFFE000u);
+          const __half2 hh = __floats2half2_rn(h0, h1);
+          const __half2 ll = __floats2half2_rn(a0 - h0, a1 - h1);
+          hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+          lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        if (half == 0) {
+          if (warp == 0) FGC_TR(0, t, 1);
+          tc::mbar_wait(&bars[B_B3_FREE + buf], ((t >> 1) & 1) ^ 1);
+          if (warp == 0) FGC_TR(0, t, 2);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int jj = half * 4 + j;
+          *reinterpret_cast<uint4*>(b3 + b3h_off + ((jj ^ (nh & 7)) << 4)) =
+              make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<uint4*>(b3 + b3l_off + ((jj ^ (nl & 7)) << 4)) =
+              make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[B_B3_FULL + buf]);
+      if (warp == 0) FGC_TR(0, t, 3);
+    }
+  } else if (warp < 8) {
+    // =========================================================== epilogue: Y (TMEM) -> global
+    const int q = warp - 4;                      // TMEM lane quadrant
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const float wun = __ldg(p.wunscale), xun = __ldg(p.xunscale);
+    static_assert(TF == 16, "epilogue written for 16-facet tiles");
+    // lane 16h + i of quadrant q: h = 0 holds Wh.(Sh|Sl) of channel o = 16q + i, h = 1 holds Wl.Sh.
+    // After one shuffle round lane (h, i) owns facets 8h .. 8h+7 of channel o.
+    const int hh = lane >> 4, o = q * 16 + (lane & 15);
+    const float bo = __ldg(p.b + o);
+    const float sc0 = xun * wun;
+    int t = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+      const int buf = t & 1;
+      const int64_t r0 = tile * TF + 8 * hh;
+      float inv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) inv[j] = (r0 + j < p.rows) ? __ldg(p.pinv + r0 + j) : 0.f;
       tc::mbar_wait(&bars[B_D3_FULL + buf], (t >> 1) & 1);
-      if (warp == 0) FGC_TR(0, t + 1, 4);
+      if (q == 0) FGC_TR(0, t, 4);
       tc::tc_fence_after_sync();
       uint32_t d[32];
       tc::tmem_ld32(tmem + lane_base + Cfg::D3_COL + buf * Cfg::NB3, d);
@@ -219,101 +277,33 @@ conv_mma_kernel(const MmaParams p) {
       tc::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars[B_D3_FREE + buf]);
-      // plane 0: Wh.(Sh + Sl) from the hi rows, plane 1: 2^-11 Wl.Sh from the lo rows; [f][o] fp32
-      const int o = (warp & 1) * 32 + lane;
-      float* pl = ex + (warp >> 1) * (TF * COUT);
-#pragma unroll
-      for (int i = 0; i < TF; ++i)
-        pl[i * COUT + o] = (warp < 2) ? (__uint_as_float(d[i]) + __uint_as_float(d[TF + i]))
-                                      : __uint_as_float(d[i]) * (1.f / 2048.f);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // thread -> (facet ff, 8 consecutive channels): coalesced 16-byte loads and stores
-      const int tid = warp * 32 + lane;
-      const int ff = tid >> 3, oc = (tid & 7) * 8;
-      const int64_t r = tile * TF + ff;
-      const float4 a0 = *reinterpret_cast<const float4*>(ex + ff * COUT + oc);
-      const float4 a1 = *reinterpret_cast<const float4*>(ex + ff * COUT + oc + 4);
-      const float4 c0 = *reinterpret_cast<const float4*>(ex + TF * COUT + ff * COUT + oc);
-      const float4 c1 = *reinterpret_cast<const float4*>(ex + TF * COUT + ff * COUT + oc + 4);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (r < p.rows) {
-        const float inv = inv_cur[0];
-        const float fl = (inv > 0.f || !p.bias_mask) ? 1.f : 0.f;
-        const float sc = inv * xun * wun;
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b + oc));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b + oc + 4));
-        float yv[8] = {fmaf(sc, a0.x + c0.x, fl * b0.x), fmaf(sc, a0.y + c0.y, fl * b0.y),
-                       fmaf(sc, a0.z + c0.z, fl * b0.z), fmaf(sc, a0.w + c0.w, fl * b0.w),
-                       fmaf(sc, a1.x + c1.x, fl * b1.x), fmaf(sc, a1.y + c1.y, fl * b1.y),
-                       fmaf(sc, a1.z + c1.z, fl * b1.z), fmaf(sc, a1.w + c1.w, fl * b1.w)};
-        if (p.act == FGC_ACT_LRELU) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) yv[i] = lrelu_f(yv[i], p.alpha);
-        }
-        float* yr = p.y + r * p.ldy + oc;
-        *reinterpret_cast<float4*>(yr) = make_float4(yv[0], yv[1], yv[2], yv[3]);
-        *reinterpret_cast<float4*>(yr + 4) = make_float4(yv[4], yv[5], yv[6], yv[7]);
-      }
-    };
-
-    int t = 0;
-    int64_t prev_tile = -1;
-    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
-      const int buf = t & 1;
-      tc::mbar_wait(&bars[B_D1_FULL + buf], (t >> 1) & 1);
-      if (warp == 0) FGC_TR(0, t, 0);
-      tc::tc_fence_after_sync();
-      uint32_t v0[32], v1[32];
-      tc::tmem_ld32(tmem + lane_base + Cfg::D1_COL + buf * 64, v0);
-      tc::tmem_ld32(tmem + lane_base + Cfg::D1_COL + buf * 64 + 32, v1);
-      tc::tc_wait_ld();
-      tc::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars[B_D1_FREE + buf]);
-      // fp16 hi (truncated to 11 significant bits, exactly representable) + fp16 residual
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const uint32_t* v = (i < 16) ? v0 : v1;
-        const int c = (i & 15) * 2;
-        const float a0 = __uint_as_float(v[c]), a1 = __uint_as_float(v[c + 1]);
-        const float h0 = __uint_as_float(v[c] & 0xFFFFE000u), h1 = __uint_as_float(v[c + 1] & 0xFFFFE000u);
-        const __half2 hh = __floats2half2_rn(h0, h1);
-        const __half2 ll = __floats2half2_rn(a0 - h0, a1 - h1);
-        hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
-        lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
-      }
-      if (warp == 0) FGC_TR(0, t, 1);
-      tc::mbar_wait(&bars[B_B3_FREE + buf], ((t >> 1) & 1) ^ 1);
-      if (warp == 0) FGC_TR(0, t, 2);
-      uint8_t* b3 = smem + Cfg::OFF_B3 + buf * Cfg::B3_BUF;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        *reinterpret_cast<uint4*>(b3 + b3h_off + ((j ^ (nh & 7)) << 4)) =
-            make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        *reinterpret_cast<uint4*>(b3 + b3l_off + ((j ^ (nl & 7)) << 4)) =
-            make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        const float hi_lo = __uint_as_float(d[j]) + __uint_as_float(d[TF + j]);         // facets 0..7  (hi lanes)
+        const float hi_up = __uint_as_float(d[8 + j]) + __uint_as_float(d[TF + 8 + j]); // facets 8..15 (hi lanes)
+        const float lo_lo = __uint_as_float(d[j]) * (1.f / 2048.f);                     // facets 0..7  (lo lanes)
+        const float lo_up = __uint_as_float(d[8 + j]) * (1.f / 2048.f);                 // facets 8..15 (lo lanes)
+        const float send = hh ? lo_lo : hi_up;
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        const float acc = hh ? (recv + lo_up) : (hi_lo + recv);
+        if (r0 + j < p.rows) {
+          const float fl = (inv[j] > 0.f || !p.bias_mask) ? 1.f : 0.f;
+          float yv = fmaf(inv[j] * sc0, acc, fl * bo);
+          if (p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
+          p.y[(r0 + j) * p.ldy + o] = yv;
+        }
       }
-      tc::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars[B_B3_FULL + buf]);
-      if (warp == 0) FGC_TR(0, t, 3);
-      load_inv(tile, inv_nxt);   // after the fence: a MEMBAR would wait for it
-      if (t > 0) epilogue(t - 1, prev_tile);
-      if (warp == 0) FGC_TR(0, t, 5);
-      prev_tile = tile;
-      inv_cur[0] = inv_nxt[0];
+      if (q == 0) FGC_TR(0, t, 5);
     }
-    if (t > 0) epilogue(t - 1, prev_tile);
-  } else if (warp < 12) {
+  } else if (warp < 16) {
     // =========================================================== assignments: softmax + Q scatter
     // Everything these warps read (pair records, own logits, neighbour logits of the chunk's distinct
     // rows) is staged in the ring slot by the loader: no global load -- and so no load latency and
     // no MEMBAR stall -- sits between two Q tiles.
-    const int grp = (warp - 4) >> 2;             // group g handles items with it % 2 == g, Q buffer g
-    const int qt = (threadIdx.x - 128) & 127;    // 0..127 within the group
+    const int grp = (warp - 8) >> 2;             // group g handles items with it % 2 == g, Q buffer g
+    const int qt = threadIdx.x & 127;            // 0..127 within the group
     const int f = qt >> 3, s = qt & 7;           // facet of the tile, slot lane: slots s, s+8, ...
-    const bool tracer = (warp == 4);
+    const bool tracer = (warp == 8);
     int it = 0;
     int Rn = (blockIdx.x < p.ntiles) ? __ldg(p.pR + blockIdx.x) : 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -442,33 +432,26 @@ conv_mma_kernel(const MmaParams p) {
         if (tracer) FGC_TR(1, itg, 2);
       }
     }
-  } else if (warp == 12 || warp == 13) {
+  } else if (warp == 16 || warp == 17) {
     // =========================================================== row loaders (cp.async)
     // Per (tile, chunk): the chunk's distinct rows (fp16 hi|lo image) into the UMMA layout, their
     // neighbour logits, and for chunk 0 the tile's pair records and own logits.  Completion is
     // signalled by cp.async.mbarrier.arrive.noinc (no wait, no fence: the loader never blocks on its
     // own copies); row ids of the next chunk are fetched while the current copies are issued.
-    const int h = lane >> 4, ch = lane & 15;     // lane copies 16-byte chunk `ch` of rows 2i + h
-    const int plane = ch >> 3, cc = ch & 7;
+    // Lane l owns rows l and l + 32 of the chunk (two row ids in registers, all 16-byte units of the
+    // row copied by the same lane: the per-copy address arithmetic is a constant offset).
     const uint32_t xbase = tc::smem_u32(smem + Cfg::OFF_X);
     const int64_t step = gridDim.x;
     const int pr_bytes = 16 + P * 2;
-    struct Ids {
-      int rid[kRC / 2];    // rows 2i + h
-      int vid[kRC / 16];   // rows (lane >> 1) + 16 i
-    };
-    auto load_ids = [&](int64_t tile, int c, int R, Ids& d) {
+    const uint32_t row_off = (lane >> 3) * 1024 + (lane & 7) * 128;   // row l inside a plane; row l+32: +4096
+    auto load_ids = [&](int64_t tile, int c, int R, int (&rid)[2]) {
       const int rc = (tile < p.ntiles) ? min(kRC, R - c * kRC) : 0;
       const int32_t* rl = p.prow + tile * P + c * kRC;
-#pragma unroll
-      for (int i = 0; i < kRC / 2; ++i) d.rid[i] = (2 * i + h < rc) ? __ldg(rl + 2 * i + h) : -1;
-#pragma unroll
-      for (int i = 0; i < kRC / 16; ++i) d.vid[i] = ((lane >> 1) + 16 * i < rc) ? __ldg(rl + (lane >> 1) + 16 * i) : -1;
+      rid[0] = (lane < rc) ? __ldg(rl + lane) : -1;
+      rid[1] = (lane + 32 < rc) ? __ldg(rl + lane + 32) : -1;
     };
     // Two loader warps take alternate items (it % 2); each walks the whole (tile, chunk) sequence.
-    // Row ids are double-buffered in registers with compile-time roles (a copy would stall on the
-    // loads just issued).
-    const int me = warp - 12;
+    const int me = warp - 16;
     int it = 0;
     int64_t tile = blockIdx.x;
     int c = 0;
@@ -483,9 +466,9 @@ conv_mma_kernel(const MmaParams p) {
       ++it;
     };
     if (me == 1 && tile < p.ntiles) advance();
-    Ids ids[2];
+    int ids[2][2];
     if (tile < p.ntiles) load_ids(tile, c, R, ids[0]);
-    auto issue = [&](const Ids& cur, Ids& nxt) {
+    auto issue = [&](const int (&cur)[2], int (&nxt)[2]) {
       // my next item is two steps ahead
       const int64_t tile0 = tile;
       const int c0 = c, it0 = it;
@@ -497,20 +480,21 @@ conv_mma_kernel(const MmaParams p) {
       tc::mbar_wait(&bars[B_X_FREE + buf], ((it0 / NX) & 1) ^ 1);
       if (me == 0) FGC_TR(2, it0 >> 1, 1);
       const uint32_t sl = xbase + buf * Cfg::X_BUF;
-      const uint32_t xb = sl + plane * Cfg::X_PLANE;
 #pragma unroll
-      for (int i = 0; i < kRC / 2; ++i) {
-        const int row = 2 * i + h;
-        if (cur.rid[i] >= 0)
-          cp_async16(xb + (row >> 3) * 1024 + (row & 7) * 128 + ((cc ^ (row & 7)) << 4),
-                     p.img + static_cast<int64_t>(cur.rid[i]) * 16 + ch);
-      }
+      for (int rr = 0; rr < 2; ++rr) {
+        if (cur[rr] >= 0) {
+          const uint4* src = p.img + static_cast<int64_t>(cur[rr]) * 16;
+          const uint32_t dst = sl + row_off + rr * 4096;
 #pragma unroll
-      for (int i = 0; i < kRC / 16; ++i) {
-        const int row = (lane >> 1) + 16 * i;
-        if (cur.vid[i] >= 0)
-          cp_async16(sl + Cfg::SL_VL + row * (M * 4) + (lane & 1) * 16,
-                     p.uvx + static_cast<int64_t>(cur.vid[i]) * (2 * M) + M + (lane & 1) * 4);
+          for (int cc = 0; cc < 8; ++cc) {
+            cp_async16(dst + ((cc ^ (lane & 7)) << 4), src + cc);
+            cp_async16(dst + Cfg::X_PLANE + ((cc ^ (lane & 7)) << 4), src + 8 + cc);
+          }
+          const float* vsrc = p.uvx + static_cast<int64_t>(cur[rr]) * (2 * M) + M;
+          const uint32_t vdst = sl + Cfg::SL_VL + (lane + 32 * rr) * (M * 4);
+#pragma unroll
+          for (int q = 0; q < M / 4; ++q) cp_async16(vdst + q * 16, vsrc + q * 4);
+        }
       }
       if (c0 == 0) {
         const uint8_t* src = p.ppair + tile0 * pr_bytes;
@@ -527,7 +511,7 @@ conv_mma_kernel(const MmaParams p) {
       if (tile >= p.ntiles) break;
       issue(ids[1], ids[0]);
     }
-  } else if (warp == 14) {
+  } else if (warp == 18) {
     // =========================================================== stage-1 MMA issuer
     // A = Q (smem, K-major), B = X rows (smem, MN-major)
     constexpr uint32_t idesc1 = (1u << 4) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
@@ -606,7 +590,7 @@ conv_mma_kernel(const MmaParams p) {
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 14) tc::tmem_dealloc(tmem, Cfg::TMEM_COLS);
+  if (warp == 18) tc::tmem_dealloc(tmem, Cfg::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ fp16 hi|lo image of x
@@ -659,7 +643,7 @@ __global__ void absmax2_kernel(const float* __restrict__ x, int64_t n4, unsigned
 __global__ void __launch_bounds__(512)
 build_conv_plan_kernel(const int32_t* __restrict__ adj, int64_t rows, int N, int K, int TF,
                        uint8_t* __restrict__ ppair, int32_t* __restrict__ prow, int32_t* __restrict__ pR,
-                       float* __restrict__ pinv) {
+                       float* __restrict__ pinv, unsigned long long* __restrict__ total_rows) {
   extern __shared__ int32_t sm[];
   const int P = TF * K;
   int32_t* ids = sm;          // [P] global row or -1
@@ -700,7 +684,10 @@ build_conv_plan_kernel(const int32_t* __restrict__ adj, int64_t rows, int N, int
   if (pidx < P)
     reinterpret_cast<uint16_t*>(blk + 16)[pidx] = (g >= 0) ? static_cast<uint16_t>(lidx | ((first_facet ? mult : 0) << 10)) : 0;
   if (pidx < 4) reinterpret_cast<int32_t*>(blk)[pidx] = (pidx == 0) ? R : 0;
-  if (pidx == 0) pR[tile] = R;
+  if (pidx == 0) {
+    pR[tile] = R;
+    atomicAdd(total_rows, static_cast<unsigned long long>(R));   // integer: order-independent
+  }
   if (pidx < TF && tile * TF + pidx < rows) pinv[tile * TF + pidx] = cnt[pidx] ? 1.f / static_cast<float>(cnt[pidx]) : 0.f;
 }
 
@@ -737,11 +724,16 @@ int build_conv_plan(const int32_t* adj, int B, int N, int K, int M, void* plan, 
   FGC_REQUIRE(plan_bytes >= L.total, "conv plan: buffer too small (%zu given, %zu needed)", plan_bytes, L.total);
   FGC_REQUIRE(L.TF * K <= 512, "conv plan: TF*K = %d exceeds 512", L.TF * K);
   char* base = static_cast<char*>(plan);
+  // header: [0] sum over tiles of the distinct-row counts (int64), [1] number of tiles
+  FGC_CUDA(cudaMemsetAsync(base, 0, 256, st));
+  const long long nt = L.ntiles;
+  FGC_CUDA(cudaMemcpyAsync(base + 8, &nt, sizeof(nt), cudaMemcpyHostToDevice, st));
   const int P = L.TF * K;
   const int threads = ((P + 31) / 32) * 32;
   build_conv_plan_kernel<<<static_cast<unsigned>(L.ntiles), threads, (2 * P + L.TF) * 4, st>>>(
       adj, rows, N, K, L.TF, reinterpret_cast<uint8_t*>(base + L.off_pair), reinterpret_cast<int32_t*>(base + L.off_row),
-      reinterpret_cast<int32_t*>(base + L.off_R), reinterpret_cast<float*>(base + L.off_inv));
+      reinterpret_cast<int32_t*>(base + L.off_R), reinterpret_cast<float*>(base + L.off_inv),
+      reinterpret_cast<unsigned long long*>(base));
   FGC_LAUNCHED("build_conv_plan_kernel");
   return FGC_OK;
 }

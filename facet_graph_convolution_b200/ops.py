@@ -67,6 +67,8 @@ class ConvPlan:
     it): distinct neighbour rows per tile of 128/M facets + per-slot local indices.  ``nbytes == 0``
     means the shape has no planned path and conv_fwd ignores the plan."""
 
+    MAX_MEAN_ROWS = 112.0
+
     def __init__(self, adj: torch.Tensor, M: int):
         L = _lib.lib()
         adj = _i32(adj, "adj")
@@ -74,11 +76,19 @@ class ConvPlan:
         self.shape, self.M = (B, N, K), int(M)
         self.nbytes = int(L.fgc_conv_plan_bytes(B, N, K, int(M)))
         self.buf = None
+        self.mean_rows = None
         if self.nbytes:
-            self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=adj.device)
+            buf = torch.empty(self.nbytes, dtype=torch.uint8, device=adj.device)
             with torch.cuda.device(adj.device):
-                check(L.fgc_build_conv_plan(_p(adj), B, N, K, int(M), _p(self.buf), self.nbytes, _stream(adj)),
+                check(L.fgc_build_conv_plan(_p(adj), B, N, K, int(M), _p(buf), self.nbytes, _stream(adj)),
                       "fgc_build_conv_plan")
+            # plan header: sum of distinct rows over tiles, number of tiles (one-time host read)
+            tot, nt = (int(v) for v in buf[:16].view(torch.int64).tolist())
+            self.mean_rows = tot / max(nt, 1)
+            # the dense-assignment path pays per distinct row: with little neighbour sharing between
+            # the facets of a tile (random adjacency) the per-facet gather path is the faster one
+            if self.mean_rows <= self.MAX_MEAN_ROWS:
+                self.buf = buf
 
 
 def conv_fwd(x, adj, W0, b, u, v, c, bias_mask=True, act=ACT_NONE, alpha=0.1, cw=None, ca0=0, ca=None,

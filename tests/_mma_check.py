@@ -45,6 +45,7 @@ def plan_ref(adj, M=8):
 
 def check(name, x, adj, P, bias_mask=True, act=0):
     W0, b, u, v, c = P
+    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
     plan = ops.ConvPlan(T(adj), W0.shape[0])
     assert plan.buf is not None
     torch.cuda.synchronize()
@@ -64,6 +65,7 @@ def main():
     B, N, K = 2, 100, 16
     adj = rs.randint(0, N + 1, size=(B, N, K)).astype(np.int32); adj[:, :, 0] = np.arange(1, N + 1); adj[0, 7] = 0
     adj[1, 3, 5] = adj[1, 3, 2]
+    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
     plan = ops.ConvPlan(T(adj), 8); torch.cuda.synchronize()
     buf = plan.buf.cpu().numpy()
     rows = B * N; TF = 16; nt = (rows + TF - 1) // TF

@@ -34,7 +34,7 @@ if os.environ.get("FGC_MMA_TRACE"):
     L.fgc_debug_trace(out, 1024)
     tr = np.array(list(out), dtype=np.int64).reshape(4, 32, 8)
     t0 = tr[tr > 0].min()
-    names = ["drain: D1full cvt B3free B3full_arr D3full(prev) epi_done", "q: ready Qfree Qfull_arr top Xfull staged_read", "loader: top Xfree issued arrived",
+    names = ["drain: D1full cvt B3free B3full_arr | epilogue: D3full done", "q: ready Qfree Qfull_arr top Xfull staged_read", "loader: top Xfree issued arrived",
              "mma: top D1free Q+Xfull S1done B3wait B3full S3done Xfull"]
     for role in range(4):
         print(names[role])
