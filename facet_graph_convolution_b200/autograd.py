@@ -25,14 +25,35 @@ def reverse_adjacency(adj: torch.Tensor) -> ops.ReverseAdjacency:
     return rev
 
 
+_PLAN_CACHE = {}
+
+
+def conv_plan(adj: torch.Tensor, M: int):
+    """Tile plan of an adjacency for the dense-assignment forward, cached like the reverse adjacency.
+    Returns None when the shape has no planned path (the plan costs nothing to ask for then)."""
+    if not ops.ConvPlan.supported(adj, M):
+        return None
+    key = (adj.data_ptr(), tuple(adj.shape), adj._version, str(adj.device), adj.dtype, int(M))
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    plan = ops.ConvPlan(adj, M)
+    if len(_PLAN_CACHE) >= _REV_CACHE_MAX:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    _PLAN_CACHE[key] = (plan, adj)
+    return plan
+
+
 def clear_reverse_cache():
     _REV_CACHE.clear()
+    _PLAN_CACHE.clear()
 
 
 class FacetConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, adj, W0, b, u, v, c, bias_mask, cw, ca0, ca, rev):
-        y = ops.conv_fwd(x, adj, W0, b, u, v, c, bias_mask, ops.ACT_NONE, 0.0, cw, ca0, ca)
+        plan = conv_plan(adj, W0.shape[0]) if ops.planned_shape(x, W0, cw) else None
+        y = ops.conv_fwd(x, adj, W0, b, u, v, c, bias_mask, ops.ACT_NONE, 0.0, cw, ca0, ca, plan=plan)
         ctx.save_for_backward(x, adj, W0, u, v, c)
         ctx.cfg = (bias_mask, cw, ca0, ca, rev)
         return y

@@ -302,6 +302,27 @@ int fgc_conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const
                   workspace, workspace_bytes, as_stream(stream));
 }
 
+int fgc_build_reverse_padded(const int32_t* rev_ptr, const int32_t* rev_edge, int B, int N, int K, int Kr,
+                             int32_t* radj, void* stream) {
+  FGC_REQUIRE(rev_ptr && rev_edge && radj && B > 0 && N > 0 && K > 0 && Kr > 0 && Kr <= FGC_MAX_K,
+              "build_reverse_padded: bad arguments");
+  return launch_build_radj(rev_ptr, rev_edge, B, N, K, Kr, radj, as_stream(stream));
+}
+
+int fgc_conv_bwd_planned(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
+                         const int32_t* rev_ptr, const int32_t* rev_edge, const int32_t* radj, int Kr,
+                         const void* rplan, const float* W0, const float* u, const float* v, const float* c,
+                         float* gx, float* gW0, float* gb, float* gu, float* gv, float* gc, int bias_mask,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_shape(s, "conv_bwd_planned");
+  if (rc) return rc;
+  FGC_REQUIRE(gy && x && adj && rev_ptr && rev_edge && W0 && u && v && c && gx && gW0 && gb && gu && gv && gc,
+              "conv_bwd_planned: NULL tensor pointer");
+  FGC_REQUIRE((radj == nullptr) == (rplan == nullptr), "conv_bwd_planned: radj and rplan go together");
+  return conv_bwd(s, gy, x, adj, rev_ptr, rev_edge, W0, u, v, c, gx, gW0, gb, gu, gv, gc, bias_mask, workspace,
+                  workspace_bytes, as_stream(stream), radj, Kr, rplan);
+}
+
 int fgc_gather_rows(const float* x, const int32_t* adj, float* out, int B, int N, int K, int C,
                     void* stream) {
   FGC_REQUIRE(x && adj && out && B > 0 && N > 0 && K > 0 && C > 0, "gather_rows: bad arguments");

@@ -806,6 +806,7 @@ size_t conv_bwd_workspace(const fgc_conv_shape* s) {
   b += ws_bytes(4, 4);                  // absmax scratch
   b += ws_bytes(static_cast<size_t>(pl.lchunks) * (2 * s->M * s->Ca + s->M), 4);  // logits partials
   b += ws_bytes(conv_fwd_tc_workspace(s->Cw > s->Cout ? s->Cw : s->Cout, s->M), 1);   // TC weight image
+  if (conv_mma_supported(s->Cin, s->Cw, s->Cout, s->M, s->K)) b += conv_mma_workspace(rows) + 256;  // gy image
   return b + 1024;
 }
 
@@ -865,7 +866,8 @@ thread_local cudaEvent_t g_gx_ready_event = nullptr;
 int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
              const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu, float* gv,
-             float* gc, int bias_mask, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+             float* gc, int bias_mask, void* workspace, size_t workspace_bytes, cudaStream_t st,
+             const int32_t* radj, int Kr, const void* rplan) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   BwdPlan pl;
   if (make_plan(s, &pl) != FGC_OK) {
@@ -886,6 +888,10 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   unsigned* maxbits = ws.take<unsigned>(4);
   float* partL = ws.take<float>(static_cast<size_t>(pl.lchunks) * nL);
   char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cw > s->Cout ? s->Cw : s->Cout, s->M));
+  static const bool mma_disabled = getenv("FGC_DISABLE_MMA") != nullptr || getenv("FGC_DISABLE_TC") != nullptr;
+  const bool tgt_mma = !mma_disabled && rplan != nullptr && radj != nullptr &&
+                       bwd_tgt_mma_supported(s->Cin, s->Cw, s->Cout, s->M, Kr);
+  char* gyimg = tgt_mma ? ws.take<char>(conv_mma_workspace(rows)) : nullptr;
   FGC_REQUIRE(ws.ok(), "conv_bwd: workspace too small (%zu bytes given)", workspace_bytes);
   static const bool tc_disabled = getenv("FGC_DISABLE_TC") != nullptr;
 
@@ -910,7 +916,12 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
 #undef FGC_CALL
     if (rc) return rc;
   }
-  if (!tc_disabled && s->Cout % 4 == 0 && bwd_tgt_tc_supported(s->Cw, s->Cout, s->M)) {
+  if (tgt_mma && tc_all) {
+    if (s->Cin > s->Cw) FGC_CUDA(cudaMemsetAsync(gx, 0, rows * s->Cin * sizeof(float), st));
+    rc = launch_bwd_tgt_mma(gy, uvx, da_edge, inv, rev_ptr, rev_edge, radj, Kr, rplan, gx, d_uvx, rows, s->N, s->Cin,
+                            s->Cout, s->M, wimg, gyimg, st);
+    if (rc) return rc;
+  } else if (!tc_disabled && s->Cout % 4 == 0 && bwd_tgt_tc_supported(s->Cw, s->Cout, s->M)) {
     if (s->Cin > s->Cw) FGC_CUDA(cudaMemsetAsync(gx, 0, rows * s->Cin * sizeof(float), st));
     rc = launch_bwd_tgt_tc(gy, uvx, tc_all ? nullptr : W0, da_edge, inv, rev_ptr, rev_edge, gx, d_uvx, rows,
                            s->N, s->K, s->Cin, s->Cw, s->Cout, s->M, wimg, st);

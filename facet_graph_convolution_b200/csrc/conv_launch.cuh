@@ -50,6 +50,13 @@ size_t conv_plan_bytes(int64_t rows, int K, int M);
 int build_conv_plan(const int32_t* adj, int B, int N, int K, int M, void* plan, size_t plan_bytes, cudaStream_t st);
 size_t conv_mma_workspace(int64_t rows);
 int debug_mma_trace(int64_t* out, int n);
+int launch_build_radj(const int32_t* rev_ptr, const int32_t* rev_edge, int B, int N, int K, int Kr, int32_t* radj,
+                      cudaStream_t st);
+bool bwd_tgt_mma_supported(int Cin, int Cw, int Cout, int M, int Kr);
+int launch_bwd_tgt_mma(const float* gy, const float* uvx, const float* da_edge, const float* inv,
+                       const int32_t* rev_ptr, const int32_t* rev_edge, const int32_t* radj, int Kr, const void* rplan,
+                       float* gx, float* d_uvx, int64_t rows, int N, int Cin, int Cout, int M, const void* wimg,
+                       void* img_ws, cudaStream_t st);
 int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, void* img_ws, void* wimg_ws,
                     cudaStream_t st);
 int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStream_t st);
@@ -67,7 +74,8 @@ size_t conv_bwd_workspace(const fgc_conv_shape* s);
 int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
              const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu, float* gv,
-             float* gc, int bias_mask, void* workspace, size_t workspace_bytes, cudaStream_t st);
+             float* gc, int bias_mask, void* workspace, size_t workspace_bytes, cudaStream_t st,
+             const int32_t* radj = nullptr, int Kr = 0, const void* rplan = nullptr);
 size_t reverse_adj_workspace(int64_t rows);
 int build_reverse_adj(const int32_t* adj, int B, int N, int K, int32_t* rev_ptr, int32_t* rev_edge,
                       int64_t* nnz_out, void* workspace, size_t workspace_bytes, cudaStream_t st);

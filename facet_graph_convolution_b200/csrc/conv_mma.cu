@@ -40,6 +40,9 @@ constexpr int kMmaThreads = 20 * 32;
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -72,7 +75,8 @@ struct MCfg {
   static constexpr int SL_VL = 2 * X_PLANE;          // [kRC][M] fp32
   static constexpr int SL_PR = SL_VL + kRC * M * 4;  // 16-byte header (R) + TF*K uint16
   static constexpr int SL_UO = SL_PR + 16 + TF * 32 * 2;
-  static constexpr int X_BUF = ((SL_UO + TF * M * 4) + 1023) / 1024 * 1024;
+  static constexpr int SL_VI = SL_UO + TF * M * 4;   // [kRC] fp32: 1/cnt of the chunk's rows (target-centric mode)
+  static constexpr int X_BUF = ((SL_VI + kRC * 4) + 1023) / 1024 * 1024;
   static constexpr int Q_PLANE = 128 * 128;          // [128 rows][64 K] halves
   static constexpr int Q_BUF = 2 * Q_PLANE;          // hi | lo
   static constexpr int B3_ATOM = NB3 * 128;          // [NB3 rows][64 K] halves
@@ -111,6 +115,12 @@ struct MmaParams {
   int N, K, ldy, bias_mask, act;
   float alpha;
   int trace;
+  // logits: a = uvx[centre][uo_off : uo_off+M] + uvx[other][vl_off : vl_off+M]
+  //   forward         centre = facet, other = neighbour:  uo_off = 0, vl_off = M
+  //   target-centric  centre = target, other = source:    uo_off = M, vl_off = 0, q *= inv_src[other]
+  int uo_off, vl_off;
+  const float* inv_src;    // nullptr in forward mode
+  int mode;                // 0: y = act(inv*scale*acc + flag*b)   1: y = scale*acc (gx of the target pass)
 };
 
 enum {
@@ -259,7 +269,7 @@ conv_mma_kernel(const MmaParams p) {
     // lane 16h + i of quadrant q: h = 0 holds Wh.(Sh|Sl) of channel o = 16q + i, h = 1 holds Wl.Sh.
     // After one shuffle round lane (h, i) owns facets 8h .. 8h+7 of channel o.
     const int hh = lane >> 4, o = q * 16 + (lane & 15);
-    const float bo = __ldg(p.b + o);
+    const float bo = (p.mode == 0) ? __ldg(p.b + o) : 0.f;
     const float sc0 = xun * wun;
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
@@ -287,9 +297,14 @@ conv_mma_kernel(const MmaParams p) {
         const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
         const float acc = hh ? (recv + lo_up) : (hi_lo + recv);
         if (r0 + j < p.rows) {
-          const float fl = (inv[j] > 0.f || !p.bias_mask) ? 1.f : 0.f;
-          float yv = fmaf(inv[j] * sc0, acc, fl * bo);
-          if (p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
+          float yv;
+          if (p.mode == 0) {
+            const float fl = (inv[j] > 0.f || !p.bias_mask) ? 1.f : 0.f;
+            yv = fmaf(inv[j] * sc0, acc, fl * bo);
+            if (p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
+          } else {
+            yv = sc0 * acc;
+          }
           p.y[(r0 + j) * p.ldy + o] = yv;
         }
       }
@@ -348,7 +363,7 @@ conv_mma_kernel(const MmaParams p) {
 #pragma unroll
             for (int i = 0; i < M; i += 4) {
               float4 tq = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (rv) tq = __ldg(reinterpret_cast<const float4*>(p.uvx + (tile * TF + f) * (2 * M) + i));
+              if (rv) tq = __ldg(reinterpret_cast<const float4*>(p.uvx + (tile * TF + f) * (2 * M) + p.uo_off + i));
               uo[i] = tq.x, uo[i + 1] = tq.y, uo[i + 2] = tq.z, uo[i + 3] = tq.w;
             }
           }
@@ -371,6 +386,7 @@ conv_mma_kernel(const MmaParams p) {
             a[j][i] = uo[i] + tq.x, a[j][i + 1] = uo[i + 1] + tq.y, a[j][i + 2] = uo[i + 2] + tq.z, a[j][i + 3] = uo[i + 3] + tq.w;
           }
           rs[j] = static_cast<float>(mult);
+          if (p.inv_src != nullptr) rs[j] *= *reinterpret_cast<const float*>(slot + Cfg::SL_VI + (lidx & 63) * 4);
         }
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
@@ -490,10 +506,11 @@ conv_mma_kernel(const MmaParams p) {
             cp_async16(dst + ((cc ^ (lane & 7)) << 4), src + cc);
             cp_async16(dst + Cfg::X_PLANE + ((cc ^ (lane & 7)) << 4), src + 8 + cc);
           }
-          const float* vsrc = p.uvx + static_cast<int64_t>(cur[rr]) * (2 * M) + M;
+          const float* vsrc = p.uvx + static_cast<int64_t>(cur[rr]) * (2 * M) + p.vl_off;
           const uint32_t vdst = sl + Cfg::SL_VL + (lane + 32 * rr) * (M * 4);
 #pragma unroll
           for (int q = 0; q < M / 4; ++q) cp_async16(vdst + q * 16, vsrc + q * 4);
+          if (p.inv_src != nullptr) cp_async4(sl + Cfg::SL_VI + (lane + 32 * rr) * 4, p.inv_src + cur[rr]);
         }
       }
       if (c0 == 0) {
@@ -501,7 +518,8 @@ conv_mma_kernel(const MmaParams p) {
         for (int q = lane * 16; q < pr_bytes; q += 512) cp_async16(sl + Cfg::SL_PR + q, src + q);
         const int64_t r = tile0 * TF + (lane >> 1);
         if ((lane >> 1) < TF && r < p.rows)
-          cp_async16(sl + Cfg::SL_UO + (lane >> 1) * (M * 4) + (lane & 1) * 16, p.uvx + r * (2 * M) + (lane & 1) * 4);
+          cp_async16(sl + Cfg::SL_UO + (lane >> 1) * (M * 4) + (lane & 1) * 16,
+                     p.uvx + r * (2 * M) + p.uo_off + (lane & 1) * 4);
       }
       cp_async_arrive_noinc(&bars[B_X_FULL + buf]);
       if (me == 0) FGC_TR(2, it0 >> 1, 2);
@@ -774,6 +792,7 @@ int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, v
   mp.wimg = static_cast<const uint4*>(wimg_ws), mp.wunscale = wunscale, mp.b = p.b, mp.y = p.y;
   mp.rows = p.rows, mp.ntiles = L.ntiles, mp.N = p.N, mp.K = p.K, mp.ldy = p.Cout, mp.bias_mask = p.bias_mask;
   mp.act = p.act, mp.alpha = p.alpha;
+  mp.uo_off = 0, mp.vl_off = p.M, mp.inv_src = nullptr, mp.mode = 0;
   static const bool trace = getenv("FGC_MMA_TRACE") != nullptr;
   mp.trace = trace ? 1 : 0;
   void (*kern)(const MmaParams) = conv_mma_kernel<8, 64, 4>;
@@ -785,6 +804,107 @@ int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, v
   if (grid < 1) grid = 1;
   kern<<<static_cast<unsigned>(grid), kMmaThreads, Cfg::SMEM_BYTES, st>>>(mp);
   FGC_LAUNCHED("conv_mma_kernel");
+  return FGC_OK;
+}
+
+
+// ------------------------------------------------------------------ target-centric pass on the same kernel
+// radj[t][0..Kr): 1-indexed (within the batch element) source facets of the in-edges of target t, in
+// rev_edge order, 0 padded -- the reversed adjacency in the forward layout, so that the same tile
+// plan builder and the same kernel serve the target-centric backward pass.
+__global__ void build_radj_kernel(const int32_t* __restrict__ rev_ptr, const int32_t* __restrict__ rev_edge,
+                                  int64_t rows, int N, int K, int Kr, int32_t* __restrict__ radj) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * Kr;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / Kr;
+    const int k = static_cast<int>(i % Kr);
+    const int e0 = __ldg(rev_ptr + t), e1 = __ldg(rev_ptr + t + 1);
+    int32_t v = 0;
+    if (e0 + k < e1) {
+      const int64_t src = __ldg(rev_edge + e0 + k) / K;   // global source row
+      v = static_cast<int32_t>(src - (t / N) * N) + 1;
+    }
+    radj[i] = v;
+  }
+}
+
+// d_uvx[t, M:2M] = sum over the in-edges e of t of da_edge[e, 0:M]   (list order: deterministic)
+template <int M>
+__global__ void __launch_bounds__(256)
+tgt_dv_kernel(const int32_t* __restrict__ rev_ptr, const int32_t* __restrict__ rev_edge,
+              const float* __restrict__ da_edge, float* __restrict__ d_uvx, int64_t rows) {
+  constexpr int LP = M / 4;   // lanes per target, one float4 each
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t t = gid / LP;
+  const int part = static_cast<int>(gid % LP);
+  if (t >= rows) return;
+  const int e0 = __ldg(rev_ptr + t), e1 = __ldg(rev_ptr + t + 1);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = e0; e < e1; ++e) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(da_edge + static_cast<int64_t>(__ldg(rev_edge + e)) * M) + part);
+    a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+  }
+  *reinterpret_cast<float4*>(d_uvx + t * (2 * M) + M + 4 * part) = a;
+}
+
+int launch_build_radj(const int32_t* rev_ptr, const int32_t* rev_edge, int B, int N, int K, int Kr, int32_t* radj,
+                      cudaStream_t st) {
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  int64_t blocks = (rows * Kr + 255) / 256;
+  if (blocks > static_cast<int64_t>(num_sms()) * 32) blocks = static_cast<int64_t>(num_sms()) * 32;
+  if (blocks < 1) blocks = 1;
+  build_radj_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(rev_ptr, rev_edge, rows, N, K, Kr, radj);
+  FGC_LAUNCHED("build_radj_kernel");
+  return FGC_OK;
+}
+
+bool bwd_tgt_mma_supported(int Cin, int Cw, int Cout, int M, int Kr) {
+  return Cw == 64 && Cout == 64 && M == 8 && Kr <= 32 && Cin % 4 == 0;
+}
+
+// gx[:, 0:Cw] = sum_m t[., m, :] W0[m] with t[j, m, :] = sum over in-edges (n -> j) of q[n->j, m] inv_cnt[n] gy[n, :]
+// and d_uvx[:, M:2M]; radj / rplan: reversed adjacency in forward layout and its tile plan.
+// wimg: transposed weight image (launch_prep_w_image_t); img_ws: conv_mma_workspace(rows) bytes.
+int launch_bwd_tgt_mma(const float* gy, const float* uvx, const float* da_edge, const float* inv,
+                       const int32_t* rev_ptr, const int32_t* rev_edge, const int32_t* radj, int Kr, const void* rplan,
+                       float* gx, float* d_uvx, int64_t rows, int N, int Cin, int Cout, int M, const void* wimg,
+                       void* img_ws, cudaStream_t st) {
+  using Cfg = MCfg<8, 64>;
+  const PlanLayout L(rows, Kr, M);
+  const char* pb = static_cast<const char*>(rplan);
+  Workspace ws(img_ws, conv_mma_workspace(rows));
+  uint4* img = reinterpret_cast<uint4*>(ws.take<char>(static_cast<size_t>(rows) * 256));
+  unsigned* scal = ws.take<unsigned>(16);
+  FGC_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(unsigned), st));
+  const int ab = num_sms() * 8;
+  absmax2_kernel<<<ab, 256, 0, st>>>(gy, rows * (Cout / 4), scal);
+  FGC_LAUNCHED("absmax_kernel");
+  prep_x_image_kernel<<<ab, 256, 0, st>>>(gy, Cout, rows, scal, img, reinterpret_cast<float*>(scal + 1));
+  FGC_LAUNCHED("prep_x_image_kernel");
+  const size_t wbytes = static_cast<size_t>(M) * 2 * 64 * 128;
+  MmaParams mp{};
+  mp.img = img, mp.xunscale = reinterpret_cast<const float*>(scal + 1), mp.uvx = uvx, mp.adj = radj;
+  mp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), mp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
+  mp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), mp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
+  mp.wimg = static_cast<const uint4*>(wimg);
+  mp.wunscale = reinterpret_cast<const float*>(static_cast<const char*>(wimg) + wbytes);
+  mp.b = nullptr, mp.y = gx, mp.rows = rows, mp.ntiles = L.ntiles, mp.N = N, mp.K = Kr, mp.ldy = Cin;
+  mp.bias_mask = 0, mp.act = FGC_ACT_NONE, mp.alpha = 0.f;
+  mp.uo_off = M, mp.vl_off = 0, mp.inv_src = inv, mp.mode = 1;
+  static const bool trace = getenv("FGC_MMA_TRACE") != nullptr;
+  mp.trace = trace ? 1 : 0;
+  void (*kern)(const MmaParams) = conv_mma_kernel<8, 64, 4>;
+  if (Kr <= 16) kern = conv_mma_kernel<8, 64, 2>;
+  else if (Kr <= 24) kern = conv_mma_kernel<8, 64, 3>;
+  FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  int64_t grid = num_sms();
+  if (grid > L.ntiles) grid = L.ntiles;
+  if (grid < 1) grid = 1;
+  kern<<<static_cast<unsigned>(grid), kMmaThreads, Cfg::SMEM_BYTES, st>>>(mp);
+  FGC_LAUNCHED("bwd_tgt_mma_kernel");
+  const int64_t threads = rows * (8 / 4);
+  tgt_dv_kernel<8><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(rev_ptr, rev_edge, da_edge, d_uvx, rows);
+  FGC_LAUNCHED("tgt_dv_kernel");
   return FGC_OK;
 }
 

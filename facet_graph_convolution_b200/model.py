@@ -110,7 +110,8 @@ def _conv(x, adj, W0, b, u, v, c, bias_mask, cw=None, ca0=0, ca=None, act=ops.AC
     if _needs_grad(x, W0, b, u, v, c):
         y = ag.FacetConvFn.apply(x, adj, W0, b, u, v, c, bias_mask, cw, ca0, ca, rev)
         return ag.LReluFn.apply(y, alpha) if act == ops.ACT_LRELU else y
-    return ops.conv_fwd(x, adj, W0, b, u, v, c, bias_mask, act, alpha, cw, ca0, ca)
+    plan = ag.conv_plan(adj, W0.shape[0]) if ops.planned_shape(x, W0, cw) else None
+    return ops.conv_fwd(x, adj, W0, b, u, v, c, bias_mask, act, alpha, cw, ca0, ca, plan=plan)
 
 
 # ----------------------------------------------------------------------------- operators

@@ -62,12 +62,23 @@ def conv_shape(x, adj, W0, u, cw=None, ca0=0, ca=None) -> ConvShape:
 
 
 # ----------------------------------------------------------------------------- convolution
+def planned_shape(x, W0, cw=None) -> bool:
+    """Layer shapes served by the dense-assignment tensor-core kernels (conv_mma.cu)."""
+    M, Cout, Cw = W0.shape
+    return M == 8 and Cout == 64 and Cw == 64 and x.shape[2] % 4 == 0 and (cw is None or cw == 64)
+
+
 class ConvPlan:
     """Caller-owned tile plan of an adjacency (built once, reused by every dense layer that runs on
     it): distinct neighbour rows per tile of 128/M facets + per-slot local indices.  ``nbytes == 0``
     means the shape has no planned path and conv_fwd ignores the plan."""
 
     MAX_MEAN_ROWS = 112.0
+
+    @staticmethod
+    def supported(adj: torch.Tensor, M: int) -> bool:
+        B, N, K = adj.shape
+        return adj.is_cuda and int(_lib.lib().fgc_conv_plan_bytes(B, N, K, int(M))) > 0
 
     def __init__(self, adj: torch.Tensor, M: int):
         L = _lib.lib()
@@ -133,9 +144,34 @@ class ReverseAdjacency:
             check(L.fgc_build_reverse_adj(_p(adj), B, N, K, _p(self.ptr), _p(self.edge), C.byref(nnz),
                                           _p(ws), ws.numel(), _stream(adj)), "fgc_build_reverse_adj")
         self.nnz = int(nnz.value)
+        self._adj_dev = adj.device
+        self._tgt = {}   # M -> (radj, Kr, ConvPlan) or None
+
+    def target_plan(self, M: int):
+        """Reversed adjacency in forward layout + its tile plan (built on first use, cached): lets the
+        gx pass of conv_bwd run on the dense-assignment kernel.  None when the in-degree exceeds the
+        kernel's slot limit or the shape has no planned path."""
+        if M in self._tgt:
+            return self._tgt[M]
+        L = _lib.lib()
+        B, N, K = self.shape
+        res = None
+        deg = int((self.ptr[1:] - self.ptr[:-1]).max().item()) if B * N > 0 else 0
+        Kr = max(8, (deg + 7) // 8 * 8)
+        if Kr <= 32 and L.fgc_conv_plan_bytes(B, N, Kr, int(M)) > 0:
+            radj = torch.empty((B, N, Kr), dtype=torch.int32, device=self._adj_dev)
+            with torch.cuda.device(self._adj_dev):
+                check(L.fgc_build_reverse_padded(_p(self.ptr), _p(self.edge), B, N, K, Kr, _p(radj), _stream(radj)),
+                      "fgc_build_reverse_padded")
+            plan = ConvPlan(radj, M)
+            if plan.buf is not None:
+                res = (radj, Kr, plan)
+        self._tgt[M] = res
+        return res
 
 
-def conv_bwd(gy, x, adj, rev: ReverseAdjacency, W0, u, v, c, bias_mask=True, cw=None, ca0=0, ca=None):
+def conv_bwd(gy, x, adj, rev: ReverseAdjacency, W0, u, v, c, bias_mask=True, cw=None, ca0=0, ca=None,
+             planned: bool = True):
     """(gx, gW0, gb, gu, gv, gc) -- deterministic backward of conv_fwd."""
     L = _lib.lib()
     gy, x, W0, u, v, c = (_f32(t, n) for t, n in ((gy, "gy"), (x, "x"), (W0, "W0"), (u, "u"), (v, "v"), (c, "c")))
@@ -150,11 +186,19 @@ def conv_bwd(gy, x, adj, rev: ReverseAdjacency, W0, u, v, c, bias_mask=True, cw=
     gu = torch.empty_like(u)
     gv = torch.empty_like(v)
     gc = torch.empty_like(c)
+    tp = rev.target_plan(s.M) if planned else None
     with torch.cuda.device(dev):
         ws = _ws(L.fgc_conv_bwd_workspace(C.byref(s)), x)
-        check(L.fgc_conv_bwd(C.byref(s), _p(gy), _p(x), _p(adj), _p(rev.ptr), _p(rev.edge), _p(W0), _p(u),
-                             _p(v), _p(c), _p(gx), _p(gW0), _p(gb), _p(gu), _p(gv), _p(gc),
-                             int(bool(bias_mask)), _p(ws), ws.numel(), _stream(x)), "fgc_conv_bwd")
+        if tp is not None:
+            radj, Kr, rplan = tp
+            check(L.fgc_conv_bwd_planned(C.byref(s), _p(gy), _p(x), _p(adj), _p(rev.ptr), _p(rev.edge), _p(radj), Kr,
+                                         _p(rplan.buf), _p(W0), _p(u), _p(v), _p(c), _p(gx), _p(gW0), _p(gb), _p(gu),
+                                         _p(gv), _p(gc), int(bool(bias_mask)), _p(ws), ws.numel(), _stream(x)),
+                  "fgc_conv_bwd_planned")
+        else:
+            check(L.fgc_conv_bwd(C.byref(s), _p(gy), _p(x), _p(adj), _p(rev.ptr), _p(rev.edge), _p(W0), _p(u),
+                                 _p(v), _p(c), _p(gx), _p(gW0), _p(gb), _p(gu), _p(gv), _p(gc),
+                                 int(bool(bias_mask)), _p(ws), ws.numel(), _stream(x)), "fgc_conv_bwd")
     return gx, gW0, gb, gu, gv, gc
 
 

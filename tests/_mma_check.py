@@ -122,5 +122,59 @@ def main():
     print("OK")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def check_bwd(name, x, adj, P):
+    W0, b, u, v, c = P
+    rs = np.random.RandomState(7)
+    gy = rs.randn(*x.shape[:2], W0.shape[1]).astype(np.float32)
+    rev = ops.ReverseAdjacency(T(adj))
+    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
+    tp = rev.target_plan(W0.shape[0])
+    g1 = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), planned=True)
+    g0 = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), planned=False)
+    ref = cf.conv_bwd(gy, x, adj, W0, b, u, v, c)
+    keys = ["gx", "gW0", "gb", "gu", "gv", "gc"]
+    out = []
+    for k, a1, a0 in zip(keys, g1, g0):
+        r = ref[k]; sc = max(1.0, np.abs(r).max())
+        out.append("%s %.2g/%.2g" % (k, np.abs(a1.cpu().numpy() - r).max() / sc, np.abs(a0.cpu().numpy() - r).max() / sc))
+    print("%-26s Kr=%s planned/old rel err: %s" % (name, None if tp is None else tp[1], "  ".join(out)), flush=True)
+    worst = max(np.abs(a1.cpu().numpy() - ref[k]).max() / max(1.0, np.abs(ref[k]).max()) for k, a1 in zip(keys, g1))
+    assert tp is not None and worst < 2e-5, worst
+
+
+def main_bwd():
+    rs = np.random.RandomState(3)
+    _, F = mesh.grid_mesh(16, 8, torus=True, morton=True)
+    a = mesh.faces_large_adj(F, 16)[None]
+    x = rs.randn(1, a.shape[1], 64).astype(np.float32)
+    check_bwd("torus mesh adj", x, a, params(rs))
+    check_bwd("torus dedup", x, mesh.dedup_adj(a[0])[None], params(rs))
+    B, N, K = 2, 300, 12
+    adj = rs.randint(0, N + 1, size=(B, N, K)).astype(np.int32); adj[:, :, 0] = np.arange(1, N + 1); adj[0, 7] = 0
+    x = rs.randn(B, N, 64).astype(np.float32)
+    check_bwd("random N=300 B=2 K=12", x, adj, params(rs))
+    # timing at scale
+    n = 1_000_000
+    _, F = mesh.grid_mesh(1000, 500, torus=True, morton=True)
+    a = T(mesh.faces_large_adj(F, 16)[None])
+    P = [T(t) for t in params(rs)]
+    W0, b, u, v, c = P
+    x = torch.randn(1, n, 64, device=dev); gy = torch.randn(1, n, 64, device=dev)
+    rev = ops.ReverseAdjacency(a)
+    for planned in (True, False):
+        for _ in range(2): ops.conv_bwd(gy, x, a, rev, W0, u, v, c, planned=planned)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): ops.conv_bwd(gy, x, a, rev, W0, u, v, c, planned=planned)
+        e1.record(); torch.cuda.synchronize()
+        print("bwd %s: %.3f ms" % ("planned" if planned else "old    ", e0.elapsed_time(e1) / 5), flush=True)
+    print("BWD OK")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bwd":
+    main_bwd()
