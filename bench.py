@@ -80,6 +80,7 @@ def kernel_bytes(name, n):
         "logits_bwd_kernel": 4 * n * 2 * C_IN,
         "conv_mma_kernel": bytes_fwd(n),
         "bwd_tgt_mma_kernel": 4 * n * (C_OUT + C_IN) + p,
+        "bwd_src_mma_kernel": 4 * n * (C_IN + K_NEIGH + C_OUT) + p,
         "prep_x_image_kernel": 4 * n * C_IN,
         "logits_bwd_x_kernel": 4 * n * 2 * C_IN,
         "logits_bwd_p_kernel": 4 * n * C_IN,
@@ -238,7 +239,7 @@ def main():
 
     def step():
         y = ops.conv_fwd(x, adj, W0, b, u, v, c, plan=plan)
-        grads = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c)
+        grads = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, plan=plan)
         if world > 1:
             flat = torch.cat([t.reshape(-1) for t in grads[1:]])
             dist.all_reduce(flat)
@@ -281,7 +282,7 @@ def main():
         L.fgc_profile_begin(C.c_void_p(stream.cuda_stream))
         for _ in range(args.steps):
             ops.conv_fwd(x, adj, W0, b, u, v, c, plan=plan)
-            ops.conv_bwd(gy, x, adj, rev, W0, u, v, c)
+            ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, plan=plan)
         buf = C.create_string_buffer(1 << 16)
         L.fgc_profile_end(buf, len(buf))
         prof_txt = buf.value.decode()

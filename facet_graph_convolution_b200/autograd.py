@@ -64,7 +64,8 @@ class FacetConvFn(torch.autograd.Function):
         bias_mask, cw, ca0, ca, rev = ctx.cfg
         if rev is None:
             rev = reverse_adjacency(adj)
-        gx, gW0, gb, gu, gv, gc = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, bias_mask, cw, ca0, ca)
+        plan = conv_plan(adj, W0.shape[0]) if ops.planned_shape(x, W0, cw) else None
+        gx, gW0, gb, gu, gv, gc = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, bias_mask, cw, ca0, ca, plan=plan)
         return gx, None, gW0, gb, gu, gv, gc, None, None, None, None, None
 
 

@@ -310,8 +310,8 @@ int fgc_build_reverse_padded(const int32_t* rev_ptr, const int32_t* rev_edge, in
 }
 
 int fgc_conv_bwd_planned(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
-                         const int32_t* rev_ptr, const int32_t* rev_edge, const int32_t* radj, int Kr,
-                         const void* rplan, const float* W0, const float* u, const float* v, const float* c,
+                         const void* plan, const int32_t* rev_ptr, const int32_t* rev_edge, const int32_t* radj,
+                         int Kr, const void* rplan, const float* W0, const float* u, const float* v, const float* c,
                          float* gx, float* gW0, float* gb, float* gu, float* gv, float* gc, int bias_mask,
                          void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_shape(s, "conv_bwd_planned");
@@ -320,7 +320,7 @@ int fgc_conv_bwd_planned(const fgc_conv_shape* s, const float* gy, const float* 
               "conv_bwd_planned: NULL tensor pointer");
   FGC_REQUIRE((radj == nullptr) == (rplan == nullptr), "conv_bwd_planned: radj and rplan go together");
   return conv_bwd(s, gy, x, adj, rev_ptr, rev_edge, W0, u, v, c, gx, gW0, gb, gu, gv, gc, bias_mask, workspace,
-                  workspace_bytes, as_stream(stream), radj, Kr, rplan);
+                  workspace_bytes, as_stream(stream), radj, Kr, rplan, plan);
 }
 
 int fgc_gather_rows(const float* x, const int32_t* adj, float* out, int B, int N, int K, int C,

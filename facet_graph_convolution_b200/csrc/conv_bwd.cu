@@ -806,7 +806,7 @@ size_t conv_bwd_workspace(const fgc_conv_shape* s) {
   b += ws_bytes(4, 4);                  // absmax scratch
   b += ws_bytes(static_cast<size_t>(pl.lchunks) * (2 * s->M * s->Ca + s->M), 4);  // logits partials
   b += ws_bytes(conv_fwd_tc_workspace(s->Cw > s->Cout ? s->Cw : s->Cout, s->M), 1);   // TC weight image
-  if (conv_mma_supported(s->Cin, s->Cw, s->Cout, s->M, s->K)) b += conv_mma_workspace(rows) + 256;  // gy image
+  if (conv_mma_supported(s->Cin, s->Cw, s->Cout, s->M, s->K)) b += 2 * (conv_mma_workspace(rows) + 256);  // gy, x images
   return b + 1024;
 }
 
@@ -867,7 +867,7 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
              const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu, float* gv,
              float* gc, int bias_mask, void* workspace, size_t workspace_bytes, cudaStream_t st,
-             const int32_t* radj, int Kr, const void* rplan) {
+             const int32_t* radj, int Kr, const void* rplan, const void* fplan) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   BwdPlan pl;
   if (make_plan(s, &pl) != FGC_OK) {
@@ -891,7 +891,9 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   static const bool mma_disabled = getenv("FGC_DISABLE_MMA") != nullptr || getenv("FGC_DISABLE_TC") != nullptr;
   const bool tgt_mma = !mma_disabled && rplan != nullptr && radj != nullptr &&
                        bwd_tgt_mma_supported(s->Cin, s->Cw, s->Cout, s->M, Kr);
-  char* gyimg = tgt_mma ? ws.take<char>(conv_mma_workspace(rows)) : nullptr;
+  const bool src_mma = !mma_disabled && fplan != nullptr && bwd_src_mma_supported(s->Cin, s->Cw, s->Cout, s->M, s->K);
+  char* gyimg = (tgt_mma || src_mma) ? ws.take<char>(conv_mma_workspace(rows)) : nullptr;
+  char* ximg = src_mma ? ws.take<char>(conv_mma_workspace(rows)) : nullptr;
   FGC_REQUIRE(ws.ok(), "conv_bwd: workspace too small (%zu bytes given)", workspace_bytes);
   static const bool tc_disabled = getenv("FGC_DISABLE_TC") != nullptr;
 
@@ -904,8 +906,21 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
     rc = launch_prep_w_image_t(W0, wimg, s->M, s->Cw, st);
     if (rc) return rc;
     const float* wunscale = reinterpret_cast<const float*>(wimg + static_cast<size_t>(s->M) * 2 * s->Cw * 128);
-    rc = launch_bwd_src_tc(gy, x, adj, uvx, wimg, wunscale, da_edge, d_uvx, inv, rows, s->N, s->K, s->Cin, s->M, st);
-    if (rc) return rc;
+    if (gyimg != nullptr) {   // the gy image serves the gz scale of the source pass and the rows of the target pass
+      rc = launch_prep_image(gy, s->Cout, rows, gyimg, st);
+      if (rc) return rc;
+    }
+    if (src_mma) {
+      rc = launch_prep_image(x, s->Cin, rows, ximg, st);
+      if (rc) return rc;
+      rc = launch_bwd_src_mma(gy, uvx, adj, fplan, ximg, gyimg, wimg, da_edge, d_uvx, rows, s->N, s->K, s->M, st);
+      if (rc) return rc;
+      FGC_CUDA(cudaMemcpyAsync(inv, conv_plan_inv(fplan, rows, s->K, s->M), rows * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    } else {
+      rc = launch_bwd_src_tc(gy, x, adj, uvx, wimg, wunscale, da_edge, d_uvx, inv, rows, s->N, s->K, s->Cin, s->M, st);
+      if (rc) return rc;
+    }
   } else {
     const int total = static_cast<int>(nW);
     permute_w_ds_kernel<<<(total + 255) / 256, 256, 0, st>>>(W0, Wd, s->M, s->Cout, s->Cw);

@@ -206,7 +206,7 @@ bwd_w_tc_kernel(const WParams p) {
     // =========================================================== final read-out
     const int quad = warp - kAggWarpsW;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    tc::mbar_wait(&bars[WB_DONE], 0);
+    tc::mbar_wait_relaxed(&bars[WB_DONE], 0);
     tc::tc_fence_after_sync();
     const float un = s_un * g_un;
     float* pw = p.partW + static_cast<int64_t>(blockIdx.x) * M * 64 * 64;
@@ -234,9 +234,9 @@ bwd_w_tc_kernel(const WParams p) {
     int it = 0;
     for (int64_t pass = blockIdx.x; pass < p.npasses; pass += gridDim.x, ++it) {
       const int st = it & 1;
-      tc::mbar_wait(&bars[WB_FULL0 + st], (it >> 1) & 1);
+      tc::mbar_wait_relaxed(&bars[WB_FULL0 + st], (it >> 1) & 1);
       tc::tc_fence_after_sync();
-      if (lane == 0) {
+      if (tc::elect_one()) {
         const uint32_t ah = sbase + st * Cfg::STAGE, al = ah + Cfg::A_PLANE;
         const uint32_t bh = ah + 2 * Cfg::A_PLANE, bl = bh + Cfg::B_PLANE;
 #pragma unroll 1
@@ -258,7 +258,7 @@ bwd_w_tc_kernel(const WParams p) {
       }
       __syncwarp();
     }
-    if (lane == 0) tc::tc_commit(&bars[WB_DONE]);
+    if (tc::elect_one()) tc::tc_commit(&bars[WB_DONE]);
     __syncwarp();
   }
   tc::tc_fence_before_sync();
@@ -377,6 +377,11 @@ bwd_src_tc_kernel(const SParams p) {
         __syncwarp();
         agg_assign_round<M, MODE_FWD>(p.src, wrow0, kb, nk, lst0, lst1, qs, nbr, lane, dv);
         __syncwarp();
+        // loop-invariant addressing of this lane's output slot and assignment column
+        const bool wr_lane = ((kLPG == 16) ? ((gl & 1) == 0) : true) && r < p.src.rows;
+        const int mine_c = (kLPG == 16) ? (gl >> 1) : gl;
+        float* de_base = p.da_edge + (r * p.src.K + kb) * M + mine_c;
+        const float* q_base = qs + grp * kQK * MQ + mine_c;
         for (int k0 = 0; k0 < nk; k0 += kUnroll) {
           float2 xp[kUnroll][kCP];
 #pragma unroll
@@ -445,7 +450,8 @@ bwd_src_tc_kernel(const SParams p) {
               }
               mine = gl;
             }
-            const float qv = qs[(grp * kQK + (k < nk ? k : 0)) * MQ + mine];
+            (void)mine;
+            const float qv = q_base[(k < nk ? k : 0) * MQ];
             float dot = qv * dq;
             if constexpr (kLPG == 16) {
               dot += __shfl_xor_sync(0xffffffffu, dot, 2);
@@ -457,10 +463,8 @@ bwd_src_tc_kernel(const SParams p) {
               dot += __shfl_xor_sync(0xffffffffu, dot, 4);
             }
             const float da = qv * (dq - dot);
-            const bool writer = (kLPG == 16) ? ((gl & 1) == 0) : true;
-            if (k < nk) {
-              if (writer && r < p.src.rows && kb + k < p.src.K)
-                p.da_edge[(r * p.src.K + kb + k) * M + mine] = da;
+            if (k < nk) {          // kb + k < K always holds here (nk <= K - kb)
+              if (wr_lane) de_base[k * M] = da;
               dux += da;
             }
           }
@@ -517,7 +521,7 @@ bwd_src_tc_kernel(const SParams p) {
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars[SB_A_READY]);
       // ---- D' chunks -> ds (fp32) in shared memory
-      tc::mbar_wait(&bars[SB_DS_FREE], (it & 1) ^ 1);
+      tc::mbar_wait_relaxed(&bars[SB_DS_FREE], (it & 1) ^ 1);
       for (int jm = 0; jm < M; ++jm) {
         const int cj = it * M + jm, slot = cj & 1;
         tc::mbar_wait(&bars[SB_D_FULL0 + slot], (cj >> 1) & 1);
@@ -565,12 +569,12 @@ bwd_src_tc_kernel(const SParams p) {
     const uint32_t wbase = tc::smem_u32(smem + Cfg::OFF_W);
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      tc::mbar_wait(&bars[SB_A_READY], it & 1);
+      tc::mbar_wait_relaxed(&bars[SB_A_READY], it & 1);
       for (int jm = 0; jm < M; ++jm) {
         const int cj = it * M + jm, slot = cj & 1;
         tc::mbar_wait(&bars[SB_D_FREE0 + slot], ((cj >> 1) & 1) ^ 1);
         tc::tc_fence_after_sync();
-        if (lane == 0) {
+        if (tc::elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t bdesc = tc::smem_desc_k_sw128(wbase + jm * (Cfg::NB * 128) + ks * 32);

@@ -50,6 +50,12 @@ size_t conv_plan_bytes(int64_t rows, int K, int M);
 int build_conv_plan(const int32_t* adj, int B, int N, int K, int M, void* plan, size_t plan_bytes, cudaStream_t st);
 size_t conv_mma_workspace(int64_t rows);
 int debug_mma_trace(int64_t* out, int n);
+int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st);
+bool bwd_src_mma_supported(int Cin, int Cw, int Cout, int M, int K);
+const float* conv_plan_inv(const void* plan, int64_t rows, int K, int M);
+int launch_bwd_src_mma(const float* gy, const float* uvx, const int32_t* adj, const void* plan, void* ximg_ws,
+                       void* gyimg_ws, const void* wimg, float* da_edge, float* d_uvx, int64_t rows, int N, int K,
+                       int M, cudaStream_t st);
 int launch_build_radj(const int32_t* rev_ptr, const int32_t* rev_edge, int B, int N, int K, int Kr, int32_t* radj,
                       cudaStream_t st);
 bool bwd_tgt_mma_supported(int Cin, int Cw, int Cout, int M, int Kr);
@@ -75,7 +81,7 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
              const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu, float* gv,
              float* gc, int bias_mask, void* workspace, size_t workspace_bytes, cudaStream_t st,
-             const int32_t* radj = nullptr, int Kr = 0, const void* rplan = nullptr);
+             const int32_t* radj = nullptr, int Kr = 0, const void* rplan = nullptr, const void* fplan = nullptr);
 size_t reverse_adj_workspace(int64_t rows);
 int build_reverse_adj(const int32_t* adj, int B, int N, int K, int32_t* rev_ptr, int32_t* rev_edge,
                       int64_t* nnz_out, void* workspace, size_t workspace_bytes, cudaStream_t st);

@@ -103,7 +103,8 @@ struct MmaParams {
   const float* xunscale;   // 2^ex
   const float* uvx;        // [rows][2M]
   const int32_t* adj;      // [rows][K]
-  const uint8_t* ppair;    // [ntiles][16 + TF*K*2]: header {R} + (local row index | multiplicity << 10)
+  const uint8_t* ppair;    // [ntiles][16 + TF*K*2]: header {R} + records: local row index (bits 0-8) |
+                           // multiplicity << 9 (bits 9-14; 0 for repeated ids) | valid id << 15
   const int32_t* prow;     // [ntiles][TF*K]: distinct rows of the tile (global row ids)
   const int32_t* pR;       // [ntiles]
   const float* pinv;       // [rows]: 1/cnt or 0
@@ -377,7 +378,7 @@ conv_mma_kernel(const MmaParams p) {
         float rs[KP];
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
-          const int mult = rec[j] >> 10, lidx = rec[j] & 1023;
+          const int mult = (rec[j] >> 9) & 63, lidx = rec[j] & 511;
           col[j] = (mult && (lidx >> 6) == c) ? (lidx & 63) : -1;
           const float4* vp = reinterpret_cast<const float4*>(slot + Cfg::SL_VL + (lidx & 63) * (M * 4));
 #pragma unroll
@@ -700,7 +701,7 @@ build_conv_plan_kernel(const int32_t* __restrict__ adj, int64_t rows, int N, int
   if (first_tile) prow[tile * P + lidx] = g;
   uint8_t* blk = ppair + tile * (16 + 2 * P);   // header {R, 0, 0, 0} + P pair records
   if (pidx < P)
-    reinterpret_cast<uint16_t*>(blk + 16)[pidx] = (g >= 0) ? static_cast<uint16_t>(lidx | ((first_facet ? mult : 0) << 10)) : 0;
+    reinterpret_cast<uint16_t*>(blk + 16)[pidx] = (g >= 0) ? static_cast<uint16_t>(lidx | ((first_facet ? mult : 0) << 9) | 0x8000) : 0;
   if (pidx < 4) reinterpret_cast<int32_t*>(blk)[pidx] = (pidx == 0) ? R : 0;
   if (pidx == 0) {
     pR[tile] = R;
@@ -725,6 +726,11 @@ struct PlanLayout {
 };
 
 }  // namespace
+}  // namespace fgc
+
+#include "conv_mma_src.cuh"
+
+namespace fgc {
 
 bool conv_mma_supported(int Cin, int Cw, int Cout, int M, int K) {
   return Cw == 64 && Cout == 64 && M == 8 && K <= 32 && Cin % 4 == 0;
@@ -760,27 +766,43 @@ size_t conv_mma_workspace(int64_t rows) {
   return ws_bytes(static_cast<size_t>(rows) * 256, 1) + ws_bytes(64, 4);
 }
 
+// fp16 hi|lo image of the first 64 channels of x (row stride ld floats) into img_ws
+// (conv_mma_workspace(rows) bytes): image at offset 0, then 16 words of scalars
+// ([0] max|x| bits, [1] 2^ex un-scale).
+struct ImgWs {
+  uint4* img;
+  unsigned* scal;
+};
+static ImgWs img_ws_views(void* img_ws, int64_t rows) {
+  Workspace ws(img_ws, conv_mma_workspace(rows));
+  ImgWs v;
+  v.img = reinterpret_cast<uint4*>(ws.take<char>(static_cast<size_t>(rows) * 256));
+  v.scal = ws.take<unsigned>(16);
+  return v;
+}
+int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st) {
+  const ImgWs v = img_ws_views(img_ws, rows);
+  FGC_CUDA(cudaMemsetAsync(v.scal, 0, 16 * sizeof(unsigned), st));
+  const int ab = num_sms() * 8;
+  // a row stride above 64 (concat tails): scan the whole tensor, a superset bound is still a valid scale
+  absmax2_kernel<<<ab, 256, 0, st>>>(x, rows * (ld / 4), v.scal);
+  FGC_LAUNCHED("absmax_kernel");
+  prep_x_image_kernel<<<ab, 256, 0, st>>>(x, ld, rows, v.scal, v.img, reinterpret_cast<float*>(v.scal + 1));
+  FGC_LAUNCHED("prep_x_image_kernel");
+  return FGC_OK;
+}
+
 // img_ws: conv_mma_workspace(rows) bytes; wimg_ws: the weight image workspace of conv_fwd_tc
 int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, void* img_ws, void* wimg_ws,
                     cudaStream_t st) {
   using Cfg = MCfg<8, 64>;
   const PlanLayout L(p.rows, p.K, p.M);
   const char* pb = static_cast<const char*>(plan);
-  Workspace ws(img_ws, conv_mma_workspace(p.rows));
-  uint4* img = reinterpret_cast<uint4*>(ws.take<char>(static_cast<size_t>(p.rows) * 256));
-  unsigned* scal = ws.take<unsigned>(16);  // [0] max bits, [1] x unscale
-  FGC_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(unsigned), st));
-  const int ab = num_sms() * 8;
-  // the row stride may exceed Cw (concat tails): only the first 64 channels of every row are used
-  if (p.Cin == kC) {
-    absmax2_kernel<<<ab, 256, 0, st>>>(p.x, p.rows * (kC / 4), scal);
-  } else {
-    // strided rows: scan the whole tensor (a superset bound is still a valid scale)
-    absmax2_kernel<<<ab, 256, 0, st>>>(p.x, p.rows * (p.Cin / 4), scal);
-  }
-  FGC_LAUNCHED("absmax_kernel");
-  prep_x_image_kernel<<<ab, 256, 0, st>>>(p.x, p.Cin, p.rows, scal, img, reinterpret_cast<float*>(scal + 1));
-  FGC_LAUNCHED("prep_x_image_kernel");
+  int rc0 = launch_prep_image(p.x, p.Cin, p.rows, img_ws, st);
+  if (rc0) return rc0;
+  const ImgWs iv = img_ws_views(img_ws, p.rows);
+  uint4* img = iv.img;
+  unsigned* scal = iv.scal;
   const size_t wbytes = static_cast<size_t>(p.M) * 2 * p.Cout * 128;
   float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + wbytes);
   int rc = launch_prep_w_image(W0, wimg_ws, p.M, p.Cout, st);
@@ -872,15 +894,12 @@ int launch_bwd_tgt_mma(const float* gy, const float* uvx, const float* da_edge, 
   using Cfg = MCfg<8, 64>;
   const PlanLayout L(rows, Kr, M);
   const char* pb = static_cast<const char*>(rplan);
-  Workspace ws(img_ws, conv_mma_workspace(rows));
-  uint4* img = reinterpret_cast<uint4*>(ws.take<char>(static_cast<size_t>(rows) * 256));
-  unsigned* scal = ws.take<unsigned>(16);
-  FGC_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(unsigned), st));
-  const int ab = num_sms() * 8;
-  absmax2_kernel<<<ab, 256, 0, st>>>(gy, rows * (Cout / 4), scal);
-  FGC_LAUNCHED("absmax_kernel");
-  prep_x_image_kernel<<<ab, 256, 0, st>>>(gy, Cout, rows, scal, img, reinterpret_cast<float*>(scal + 1));
-  FGC_LAUNCHED("prep_x_image_kernel");
+  // img_ws holds the gy image prepared by launch_prep_image(gy, Cout, rows, img_ws)
+  (void)gy;
+  (void)Cout;
+  const ImgWs iv = img_ws_views(img_ws, rows);
+  uint4* img = iv.img;
+  unsigned* scal = iv.scal;
   const size_t wbytes = static_cast<size_t>(M) * 2 * 64 * 128;
   MmaParams mp{};
   mp.img = img, mp.xunscale = reinterpret_cast<const float*>(scal + 1), mp.uvx = uvx, mp.adj = radj;
@@ -905,6 +924,47 @@ int launch_bwd_tgt_mma(const float* gy, const float* uvx, const float* da_edge, 
   const int64_t threads = rows * (8 / 4);
   tgt_dv_kernel<8><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(rev_ptr, rev_edge, da_edge, d_uvx, rows);
   FGC_LAUNCHED("tgt_dv_kernel");
+  return FGC_OK;
+}
+
+
+bool bwd_src_mma_supported(int Cin, int Cw, int Cout, int M, int K) { return conv_mma_supported(Cin, Cw, Cout, M, K); }
+
+const float* conv_plan_inv(const void* plan, int64_t rows, int K, int M) {
+  return reinterpret_cast<const float*>(static_cast<const char*>(plan) + PlanLayout(rows, K, M).off_inv);
+}
+
+// ds / dq / da of the source-centric pass (conv_mma_src.cuh).  ximg_ws / gyimg_ws: images prepared by
+// launch_prep_image; plan: the forward tile plan; wimg: transposed weight image.
+int launch_bwd_src_mma(const float* gy, const float* uvx, const int32_t* adj, const void* plan, void* ximg_ws,
+                       void* gyimg_ws, const void* wimg, float* da_edge, float* d_uvx, int64_t rows, int N, int K,
+                       int M, cudaStream_t st) {
+  using Cfg = SrcCfg<8>;
+  const PlanLayout L(rows, K, M);
+  const char* pb = static_cast<const char*>(plan);
+  const ImgWs xi = img_ws_views(ximg_ws, rows), gi = img_ws_views(gyimg_ws, rows);
+  const size_t wbytes = static_cast<size_t>(M) * 2 * 64 * 128;
+  SrcParams sp{};
+  sp.img = xi.img, sp.xunscale = reinterpret_cast<const float*>(xi.scal + 1);
+  sp.gy = gy, sp.gunscale = reinterpret_cast<const float*>(gi.scal + 1), sp.gmaxbits = gi.scal;
+  sp.uvx = uvx;
+  sp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), sp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
+  sp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), sp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
+  sp.wimg = static_cast<const uint4*>(wimg);
+  sp.wunscale = reinterpret_cast<const float*>(static_cast<const char*>(wimg) + wbytes);
+  sp.da_edge = da_edge, sp.d_uvx = d_uvx, sp.rows = rows, sp.ntiles = L.ntiles, sp.N = N, sp.K = K;
+  void (*kern)(const SrcParams) = bwd_src_mma_kernel<8, 4>;
+  if (K <= 16) kern = bwd_src_mma_kernel<8, 2>;
+  else if (K <= 24) kern = bwd_src_mma_kernel<8, 3>;
+  FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  int64_t grid = num_sms();
+  if (grid > L.ntiles) grid = L.ntiles;
+  if (grid < 1) grid = 1;
+  kern<<<static_cast<unsigned>(grid), kMmaThreads, Cfg::SMEM_BYTES, st>>>(sp);
+  FGC_LAUNCHED("bwd_src_mma_kernel");
+  src_dux_fix_kernel<8><<<static_cast<unsigned>((rows + 255) / 256), 256, 0, st>>>(sp.pR, adj, da_edge, d_uvx, rows, N,
+                                                                                  K, L.TF);
+  FGC_LAUNCHED("src_dux_fix_kernel");
   return FGC_OK;
 }
 

@@ -41,6 +41,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for waits that are expected to be long (a whole tile of someone else's work): after a few polls
+// the warp sleeps between polls instead of occupying issue slots of its SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  int polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls > 4) __nanosleep(64);
+  }
+}
 
 // One lane of the (converged) warp, chosen by hardware.  Unlike `lane == 0`, ptxas knows the branch
 // is taken by exactly one thread, so uniform-datapath instructions (tcgen05.mma / commit) inside it

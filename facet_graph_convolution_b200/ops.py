@@ -171,7 +171,7 @@ class ReverseAdjacency:
 
 
 def conv_bwd(gy, x, adj, rev: ReverseAdjacency, W0, u, v, c, bias_mask=True, cw=None, ca0=0, ca=None,
-             planned: bool = True):
+             planned: bool = True, plan: Optional["ConvPlan"] = None):
     """(gx, gW0, gb, gu, gv, gc) -- deterministic backward of conv_fwd."""
     L = _lib.lib()
     gy, x, W0, u, v, c = (_f32(t, n) for t, n in ((gy, "gy"), (x, "x"), (W0, "W0"), (u, "u"), (v, "v"), (c, "c")))
@@ -187,14 +187,16 @@ def conv_bwd(gy, x, adj, rev: ReverseAdjacency, W0, u, v, c, bias_mask=True, cw=
     gv = torch.empty_like(v)
     gc = torch.empty_like(c)
     tp = rev.target_plan(s.M) if planned else None
+    fplan = plan if (planned and plan is not None and plan.buf is not None) else None
     with torch.cuda.device(dev):
         ws = _ws(L.fgc_conv_bwd_workspace(C.byref(s)), x)
-        if tp is not None:
-            radj, Kr, rplan = tp
-            check(L.fgc_conv_bwd_planned(C.byref(s), _p(gy), _p(x), _p(adj), _p(rev.ptr), _p(rev.edge), _p(radj), Kr,
-                                         _p(rplan.buf), _p(W0), _p(u), _p(v), _p(c), _p(gx), _p(gW0), _p(gb), _p(gu),
-                                         _p(gv), _p(gc), int(bool(bias_mask)), _p(ws), ws.numel(), _stream(x)),
-                  "fgc_conv_bwd_planned")
+        if tp is not None or fplan is not None:
+            radj, Kr, rplan = tp if tp is not None else (None, 0, None)
+            check(L.fgc_conv_bwd_planned(C.byref(s), _p(gy), _p(x), _p(adj), _p(fplan.buf) if fplan else None,
+                                         _p(rev.ptr), _p(rev.edge), _p(radj), Kr,
+                                         _p(rplan.buf) if rplan is not None else None, _p(W0), _p(u), _p(v), _p(c),
+                                         _p(gx), _p(gW0), _p(gb), _p(gu), _p(gv), _p(gc), int(bool(bias_mask)),
+                                         _p(ws), ws.numel(), _stream(x)), "fgc_conv_bwd_planned")
         else:
             check(L.fgc_conv_bwd(C.byref(s), _p(gy), _p(x), _p(adj), _p(rev.ptr), _p(rev.edge), _p(W0), _p(u),
                                  _p(v), _p(c), _p(gx), _p(gW0), _p(gb), _p(gu), _p(gv), _p(gc),

@@ -140,12 +140,15 @@ FGC_API int fgc_conv_bwd(const fgc_conv_shape* s, const float* gy, const float* 
  * in the forward layout: radj[B,N,Kr], 1-indexed source facets of every target's in-edges in
  * rev_edge order, 0 padded (Kr >= the largest in-degree, <= FGC_MAX_K).  A tile plan built on radj
  * (fgc_build_conv_plan(radj, B, N, Kr, M, ...)) lets fgc_conv_bwd_planned run the gx pass on the
- * dense-assignment tensor-core kernel; with radj = rplan = NULL it equals fgc_conv_bwd. */
+ * dense-assignment tensor-core kernel, and the forward plan of adj lets it run the source-centric
+ * pass (ds, dq, da) on the staged tcgen05 pipeline; with plan = radj = rplan = NULL it equals
+ * fgc_conv_bwd. */
 FGC_API int fgc_build_reverse_padded(const int32_t* rev_ptr, const int32_t* rev_edge, int B, int N, int K,
                              int Kr, int32_t* radj, void* stream);
 FGC_API int fgc_conv_bwd_planned(const fgc_conv_shape* s, const float* gy, const float* x,
-                         const int32_t* adj, const int32_t* rev_ptr, const int32_t* rev_edge,
-                         const int32_t* radj, int Kr, const void* rplan, const float* W0,
+                         const int32_t* adj, const void* plan /* forward tile plan or NULL */,
+                         const int32_t* rev_ptr, const int32_t* rev_edge, const int32_t* radj,
+                         int Kr, const void* rplan, const float* W0,
                          const float* u, const float* v, const float* c, float* gx, float* gW0,
                          float* gb, float* gu, float* gv, float* gc, int bias_mask, void* workspace,
                          size_t workspace_bytes, void* stream);

@@ -39,7 +39,7 @@ def plan_ref(adj, M=8):
                 li = int(np.searchsorted(d, v))
                 mult = 0 if v in seen else int((g[r - r0] == v).sum())
                 seen.add(v)
-                pair[r, k] = li | (mult << 10)
+                pair[r, k] = li | (mult << 9) | 0x8000
     return R, pair, prow
 
 
@@ -133,7 +133,8 @@ def check_bwd(name, x, adj, P):
     rev = ops.ReverseAdjacency(T(adj))
     ops.ConvPlan.MAX_MEAN_ROWS = 1e9
     tp = rev.target_plan(W0.shape[0])
-    g1 = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), planned=True)
+    fp = ops.ConvPlan(T(adj), W0.shape[0])
+    g1 = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), planned=True, plan=fp)
     g0 = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), planned=False)
     ref = cf.conv_bwd(gy, x, adj, W0, b, u, v, c)
     keys = ["gx", "gW0", "gb", "gu", "gv", "gc"]
@@ -165,12 +166,13 @@ def main_bwd():
     W0, b, u, v, c = P
     x = torch.randn(1, n, 64, device=dev); gy = torch.randn(1, n, 64, device=dev)
     rev = ops.ReverseAdjacency(a)
+    fp = ops.ConvPlan(a, 8)
     for planned in (True, False):
-        for _ in range(2): ops.conv_bwd(gy, x, a, rev, W0, u, v, c, planned=planned)
+        for _ in range(2): ops.conv_bwd(gy, x, a, rev, W0, u, v, c, planned=planned, plan=fp)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5): ops.conv_bwd(gy, x, a, rev, W0, u, v, c, planned=planned)
+        for _ in range(5): ops.conv_bwd(gy, x, a, rev, W0, u, v, c, planned=planned, plan=fp)
         e1.record(); torch.cuda.synchronize()
         print("bwd %s: %.3f ms" % ("planned" if planned else "old    ", e0.elapsed_time(e1) / 5), flush=True)
     print("BWD OK")

@@ -26,7 +26,7 @@ def _params(rs, M=8, Cin=64, Cout=64):
 
 
 def _plan_ref(adj, M=8):
-    """distinct rows per tile (ascending), per-slot local index | multiplicity << 10, 1/cnt."""
+    """distinct rows per tile (ascending), per-slot local index | multiplicity << 9 | valid << 15, 1/cnt."""
     B, N, K = adj.shape
     TF = 128 // M
     rows = B * N
@@ -52,7 +52,7 @@ def _plan_ref(adj, M=8):
                     continue
                 mult = 0 if v in seen else int((g[r - r0] == v).sum())
                 seen.add(v)
-                pair[r, k] = int(np.searchsorted(d, v)) | (mult << 10)
+                pair[r, k] = int(np.searchsorted(d, v)) | (mult << 9) | 0x8000
     cnt = (a != 0).sum(1)
     inv = np.where(cnt > 0, 1.0 / np.maximum(cnt, 1), 0).astype(np.float32)
     return R, pair, prow, inv
@@ -134,13 +134,16 @@ def test_planned_backward_matches_oracle_and_is_reproducible():
     from facet_graph_convolution_b200 import ops
     ops.ConvPlan.MAX_MEAN_ROWS = 1e9
     rs = np.random.RandomState(2)
-    for name, x, adj in _cases()[:3]:
+    for name, x, adj in _cases():
         W0, b, u, v, c = _params(rs)
         gy = rs.randn(*x.shape[:2], 64).astype(np.float32)
         rev = ops.ReverseAdjacency(T(adj))
-        assert rev.target_plan(8) is not None, name
-        g1 = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), planned=True)
-        g2 = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), planned=True)
+        if rev.target_plan(8) is None:   # in-degree above the kernel's slot limit: gx pass falls back
+            assert name == 'ragged_K23'
+        fp = ops.ConvPlan(T(adj), 8)
+        assert fp.buf is not None
+        g1 = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), planned=True, plan=fp)
+        g2 = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), planned=True, plan=fp)
         ref = cf.conv_bwd(gy, x, adj, W0, b, u, v, c)
         for k, a1, a2 in zip(["gx", "gW0", "gb", "gu", "gv", "gc"], g1, g2):
             sc = max(1.0, float(np.abs(ref[k]).max()))
