@@ -40,6 +40,10 @@ constexpr int kMmaThreads = 20 * 32;
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// copies 16 bytes when ok, writes 16 zero bytes otherwise (src-size 0: the source is not read)
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool ok) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -946,7 +950,8 @@ int launch_bwd_src_mma(const float* gy, const float* uvx, const int32_t* adj, co
   const size_t wbytes = static_cast<size_t>(M) * 2 * 64 * 128;
   SrcParams sp{};
   sp.img = xi.img, sp.xunscale = reinterpret_cast<const float*>(xi.scal + 1);
-  sp.gy = gy, sp.gunscale = reinterpret_cast<const float*>(gi.scal + 1), sp.gmaxbits = gi.scal;
+  (void)gy;   // the stage-A operand is the gy image prepared by launch_prep_image(gy, ...) in gyimg_ws
+  sp.gimg = gi.img, sp.gunscale = reinterpret_cast<const float*>(gi.scal + 1);
   sp.uvx = uvx;
   sp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), sp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
   sp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), sp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);

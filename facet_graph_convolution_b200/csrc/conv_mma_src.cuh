@@ -1,15 +1,17 @@
 // Source-centric backward pass on the staged tcgen05 pipeline (included by conv_mma.cu).
 // Replaces the bwd_src pass of conv_bwd_tc.cu for the dense 64-channel, M = 8 layers:
 //
-//   gz[n]       = inv_cnt[n] gy[n]
-//   ds[n,m,:]   = W0[m]^T gz[n]                    stage A   tcgen05.mma  A = [Wt_h;Wt_l] (TMEM), B = gz
-//   dq[n,k,m]   = ds[n,m,:] . x_{j_k}              stage B   tcgen05.mma  A = X rows (smem), B = ds
+//   ds'[n,m,:]  = W0[m]^T gy[n]                    stage A   tcgen05.mma  A = [Wt_h;Wt_l] (TMEM), B = gy image
+//   dq[n,k,m]   = inv_cnt[n] ds'[n,m,:] . x_{j_k}  stage B   tcgen05.mma  A = X rows (smem), B = ds'
+//                                                  (1/cnt is a per-facet scalar: applied by the pair threads)
 //   da[n,k,m]   = q (dq - sum_m' q dq)             CUDA cores (softmax recomputed from staged logits)
 //   outputs     da_edge[n,k,:], d_uvx[n,0:M] = sum_k da[n,k,:]
 //
 // Tile = 16 source facets, the forward tile plan gives its R distinct neighbour rows.  Per item
 // (tile, chunk of <= 64 distinct rows) and per half h of the weight matrices (m = 4h .. 4h+3):
-//   A_h   D_A[c (hi|lo lanes), (m', f hi | f lo)] = Wt[:, m-slice] . gz^T            16 MMAs, N = 32
+//   A_h   D_A[c (hi|lo lanes), (m', f hi | f lo)] = Wt[:, m-slice] . gy^T            16 MMAs, N = 32
+//         (B operand = the tile's rows of the fp16 hi|lo image of gy, copied by the loaders with
+//         cp.async straight into the K-major swizzled layout: no conversion, no fence in the pair warps)
 //   dr_A  TMEM -> registers, hi/lo lanes of a channel combined by shuffle, fp16 hi/lo
 //         -> shared DS_h[c][(m', f)]   (MN-major B operand of stage B, 128 B per channel row)
 //   B_h   D_B[row (hi|lo lanes), (m', f)] = [Xh;Xl] . DS_h                           8 MMAs, N = 64
@@ -18,7 +20,7 @@
 // TMEM: weights 256 + D_A 128 + D_B 2 x 64 columns.
 //
 // Warp roles (20 warps): 0-3 drain A, 4-7 drain B (both aligned to the TMEM lane quadrants),
-// 8-11 / 12-15 two pair groups (alternate items: gz operand, softmax, da), 16-17 loaders,
+// 8-11 / 12-15 two pair groups (alternate items: softmax, da, outputs), 16-17 loaders,
 // 18 stage-A issuer, 19 stage-B issuer.
 #pragma once
 
@@ -31,20 +33,21 @@ struct SrcCfg {
   static constexpr int TF = 128 / M;
   static constexpr int NX = 4;
   // ring slot: 128 operand rows of 128 B (lane-permuted hi/lo planes of the chunk's distinct rows) |
-  // neighbour logits | header + pair records | own logits | 1/cnt of the tile's facets | gy rows (fp32)
+  // gy operand of the tile's own facets [32 rows: f hi | f lo][64 K = o] halves | neighbour logits |
+  // header + pair records | own logits | 1/cnt of the tile's facets
   static constexpr int SL_X = 0;
-  static constexpr int SL_VL = 2 * kRC * 128;
+  static constexpr int SL_GZ = 2 * kRC * 128;
+  static constexpr int GZ_BYTES = 2 * TF * 128;
+  static constexpr int SL_VL = SL_GZ + GZ_BYTES;
   static constexpr int SL_PR = SL_VL + kRC * M * 4;
   static constexpr int SL_UO = SL_PR + 16 + TF * 32 * 2;
   static constexpr int SL_INV = SL_UO + TF * M * 4;
-  static constexpr int SL_GY = SL_INV + TF * 4;
-  static constexpr int X_BUF = ((SL_GY + TF * kC * 4) + 1023) / 1024 * 1024;
-  static constexpr int GZ_BYTES = 2 * TF * 128;          // [32 rows: f hi | f lo][64 K = o] halves
+  static constexpr int X_BUF = ((SL_INV + TF * 4) + 1023) / 1024 * 1024;
   static constexpr int DS_BYTES = 2 * kC * 128;          // hi | lo planes of [64 K rows = c][64 N = (m', f)]
-  static constexpr int DQ_BYTES = kRC * 64 * 4;          // [64 rows][64 (m', f)] fp32
+  static constexpr int DQ_LD = 68;                       // fp32 row stride of DQ (padded: conflict-free drain stores)
+  static constexpr int DQ_BYTES = kRC * DQ_LD * 4;       // [64 rows][64 (m', f)] fp32
   static constexpr int OFF_X = 0;
-  static constexpr int OFF_GZ = OFF_X + NX * X_BUF;
-  static constexpr int OFF_DS = OFF_GZ + 2 * GZ_BYTES;   // gz: one buffer per pair group; ds: two halves
+  static constexpr int OFF_DS = OFF_X + NX * X_BUF;      // ds: two halves
   static constexpr int OFF_DQ = OFF_DS + 2 * DS_BYTES;   // dq: [pair group][half]
   static constexpr int OFF_BAR = OFF_DQ + 4 * DQ_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 512;
@@ -59,9 +62,8 @@ struct SrcCfg {
 struct SrcParams {
   const uint4* img;        // fp16 hi|lo image of x
   const float* xunscale;
-  const float* gy;         // [rows][64] fp32
-  const float* gunscale;   // 2^eg: the gz operand is gy * inv * 2^-eg
-  const unsigned* gmaxbits;
+  const uint4* gimg;       // fp16 hi|lo image of gy (scaled by 2^-eg)
+  const float* gunscale;   // 2^eg
   const float* uvx;
   const uint8_t* ppair;
   const int32_t* prow;
@@ -78,8 +80,6 @@ struct SrcParams {
 enum {
   S_X_FULL = 0,    // NX (32 cp.async arrivals)
   S_X_FREE = 4,    // NX (4 pair warps + stage-B commit)
-  S_GZ_FULL = 8,   // [pair group] (4)
-  S_GZ_FREE = 10,  // [pair group] (1, stage-A commit)
   S_DA_FULL = 12,  // 1
   S_DA_FREE = 13,  // 4
   S_DS_FULL = 14,  // [half] (4)
@@ -109,7 +109,6 @@ bwd_src_mma_kernel(const SrcParams p) {
     for (int i = 0; i < NX; ++i) tc::mbar_init(&bars[S_X_FULL + i], 32), tc::mbar_init(&bars[S_X_FREE + i], 5);
     tc::mbar_init(&bars[S_DA_FULL], 1), tc::mbar_init(&bars[S_DA_FREE], 4);
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&bars[S_GZ_FULL + i], 4), tc::mbar_init(&bars[S_GZ_FREE + i], 1);
       tc::mbar_init(&bars[S_DS_FULL + i], 4), tc::mbar_init(&bars[S_DS_FREE + i], 1);
       tc::mbar_init(&bars[S_DB_FULL + i], 1), tc::mbar_init(&bars[S_DB_FREE + i], 4);
     }
@@ -251,7 +250,7 @@ bwd_src_mma_kernel(const SrcParams p) {
           const int g = nb & 1, ng = nb >> 1;   // pair group of the item and its per-group use counter
           tc::mbar_wait(&bars[S_DQ_FREE + 2 * g + h], (ng & 1) ^ 1);
           float4* dst =
-              reinterpret_cast<float4*>(smem + Cfg::OFF_DQ + (2 * g + h) * Cfg::DQ_BYTES + row * 256 + hh * 128);
+              reinterpret_cast<float4*>(smem + Cfg::OFF_DQ + (2 * g + h) * Cfg::DQ_BYTES + row * (Cfg::DQ_LD * 4) + hh * 128);
 #pragma unroll
           for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           __syncwarp();
@@ -265,12 +264,6 @@ bwd_src_mma_kernel(const SrcParams p) {
     const int qt = threadIdx.x & 127;
     const int f = qt >> 3, s = qt & 7;
     const float unsc = __ldg(p.xunscale) * __ldg(p.wunscale) * __ldg(p.gunscale);
-    float gsc;   // gz scale 2^-eg as applied by the image convention of prep_x_image_kernel
-    {
-      int E = static_cast<int>((__ldg(p.gmaxbits) >> 23) & 0xFF);
-      E = min(max(E, 16), 240);
-      gsc = __int_as_float((253 - E) << 23);
-    }
     int it = 0;
     int Rn = (blockIdx.x < p.ntiles) ? __ldg(p.pR + blockIdx.x) : 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += step) {
@@ -283,34 +276,7 @@ bwd_src_mma_kernel(const SrcParams p) {
         const uint8_t* slot = smem + Cfg::OFF_X + xbuf * Cfg::X_BUF;
         if ((it & 1) != grp) continue;
         tc::mbar_wait(&bars[S_X_FULL + xbuf], (it / NX) & 1);
-        // ---- gz operand of stage A: thread (f, s) converts 8 channels of gy[f]
-        {
-          const float inv = *reinterpret_cast<const float*>(slot + Cfg::SL_INV + f * 4);
-          const float4* gp = reinterpret_cast<const float4*>(slot + Cfg::SL_GY + f * (kC * 4) + s * 32);
-          const float4 g0 = gp[0], g1 = gp[1];
-          const float sc = rv ? inv * gsc : 0.f;
-          const float v[8] = {g0.x * sc, g0.y * sc, g0.z * sc, g0.w * sc, g1.x * sc, g1.y * sc, g1.z * sc, g1.w * sc};
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-            hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
-            lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
-          }
-          tc::mbar_wait(&bars[S_GZ_FREE + grp], ((it >> 1) & 1) ^ 1);
-          // K-major rows n = f (hi) and TF + f (lo), 16-byte unit s
-          uint8_t* gz = smem + Cfg::OFF_GZ + grp * Cfg::GZ_BYTES;
-          const int nh = f, nl = TF + f;
-          *reinterpret_cast<uint4*>(gz + (nh >> 3) * 1024 + (nh & 7) * 128 + ((s ^ (nh & 7)) << 4)) =
-              make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(gz + (nl >> 3) * 1024 + (nl & 7) * 128 + ((s ^ (nl & 7)) << 4)) =
-              make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          tc::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&bars[S_GZ_FULL + grp]);
-        }
+        const float dsc = unsc * *reinterpret_cast<const float*>(slot + Cfg::SL_INV + f * 4);
         // ---- soft assignments of this thread's pairs (every slot on its own: no multiplicity here)
         uint32_t rec[KP];
         float uo[M];
@@ -374,7 +340,7 @@ bwd_src_mma_kernel(const SrcParams p) {
           for (int j = 0; j < KP; ++j)
 #pragma unroll
             for (int mq = 0; mq < 4; ++mq)
-              dq[j][4 * h + mq] = (col[j] >= 0) ? dqs[col[j] * 64 + mq * TF + f] * unsc : 0.f;
+              dq[j][4 * h + mq] = (col[j] >= 0) ? dqs[col[j] * Cfg::DQ_LD + mq * TF + f] * dsc : 0.f;
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&bars[S_DQ_FREE + 2 * grp + h]);
         }
@@ -471,11 +437,16 @@ bwd_src_mma_kernel(const SrcParams p) {
         }
       }
       {
-        // per item: gy rows and 1/cnt of the tile's own facets (every chunk rebuilds the gz operand)
+        // per item: gy image rows (stage-A B operand, K-major rows n = f (hi) | TF + f (lo), 128B swizzle)
+        // and 1/cnt of the tile's own facets; rows past the end are zero-filled
         const int64_t r0 = tile0 * TF;
-        for (int q = lane; q < TF * 16; q += 32) {      // 16 x 16 B per gy row
-          const int ff = q >> 4;
-          if (r0 + ff < p.rows) cp_async16(sl + Cfg::SL_GY + q * 16, p.gy + (r0 + ff) * kC + (q & 15) * 4);
+#pragma unroll
+        for (int q = lane; q < TF * 16; q += 32) {      // 16 x 16 B per image row
+          const int ff = q >> 4, u16 = q & 15;
+          const int nrow = (u16 >> 3) * TF + ff, cc = u16 & 7;
+          const uint32_t dst = sl + Cfg::SL_GZ + (nrow >> 3) * 1024 + (nrow & 7) * 128 + ((cc ^ (nrow & 7)) << 4);
+          const bool ok = r0 + ff < p.rows;
+          cp_async16_zfill(dst, p.gimg + (ok ? (r0 + ff) * 16 + u16 : 0), ok);
         }
         if (lane < TF && r0 + lane < p.rows) cp_async4(sl + Cfg::SL_INV + lane * 4, p.pinv + r0 + lane);
       }
@@ -496,15 +467,16 @@ bwd_src_mma_kernel(const SrcParams p) {
   } else if (warp == 18) {
     // =========================================================== stage-A issuer: D_A = Wt[:, m-slice] . gz^T
     constexpr uint32_t idescA = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t gzb = tc::smem_u32(smem + Cfg::OFF_GZ);
+    const uint32_t sb = tc::smem_u32(smem);
     int it = 0, n = 0;
     int Rn = (blockIdx.x < p.ntiles) ? __ldg(p.pR + blockIdx.x) : 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += step) {
       const int nch = chunks_of(Rn);
       if (tile + step < p.ntiles) Rn = __ldg(p.pR + tile + step);
       for (int c = 0; c < nch; ++c, ++it) {
-        const int g = it & 1;
-        tc::mbar_wait(&bars[S_GZ_FULL + g], (it >> 1) & 1);
+        const int xbuf = it % NX;
+        const uint32_t gzb = sb + Cfg::OFF_X + xbuf * Cfg::X_BUF + Cfg::SL_GZ;
+        tc::mbar_wait(&bars[S_X_FULL + xbuf], (it / NX) & 1);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h, ++n) {
           tc::mbar_wait(&bars[S_DA_FREE], (n & 1) ^ 1);
@@ -515,13 +487,12 @@ bwd_src_mma_kernel(const SrcParams p) {
               const int mm = 4 * h + mq;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t bd = tc::smem_desc_k_sw128(gzb + g * Cfg::GZ_BYTES + ks * 32);
+                const uint64_t bd = tc::smem_desc_k_sw128(gzb + ks * 32);
                 tc::mma_f16_ts(tmem + Cfg::DA_COL + mq * 32, tmem + Cfg::W_COL + mm * 32 + ks * 8, bd, idescA,
                                ks ? 1u : 0u);
               }
             }
             tc::tc_commit(&bars[S_DA_FULL]);
-            if (h == 1) tc::tc_commit(&bars[S_GZ_FREE + g]);
           }
           __syncwarp();
         }
