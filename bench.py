@@ -238,8 +238,10 @@ def main():
     rev.target_plan(M_W)
 
     def step():
-        y = ops.conv_fwd(x, adj, W0, b, u, v, c, plan=plan)
-        grads = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, plan=plan)
+        # as in a training step, the backward reuses what the forward saved (logits, fp16 image of x)
+        saved = ops.ConvSaved()
+        y = ops.conv_fwd(x, adj, W0, b, u, v, c, plan=plan, save=saved)
+        grads = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, plan=plan, saved=saved)
         if world > 1:
             flat = torch.cat([t.reshape(-1) for t in grads[1:]])
             dist.all_reduce(flat)
@@ -281,8 +283,9 @@ def main():
     if not profile:  # separate profiled pass (keeps the all-reduce out of the kernel brackets)
         L.fgc_profile_begin(C.c_void_p(stream.cuda_stream))
         for _ in range(args.steps):
-            ops.conv_fwd(x, adj, W0, b, u, v, c, plan=plan)
-            ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, plan=plan)
+            step_saved = ops.ConvSaved()
+            ops.conv_fwd(x, adj, W0, b, u, v, c, plan=plan, save=step_saved)
+            ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, plan=plan, saved=step_saved)
         buf = C.create_string_buffer(1 << 16)
         L.fgc_profile_end(buf, len(buf))
         prof_txt = buf.value.decode()

@@ -50,7 +50,7 @@ SIGNATURES = {
     "fgc_build_reverse_adj": (i32, [p, i32, i32, i32, p, p, C.POINTER(i64), p, sz, p]),
     "fgc_conv_bwd": (i32, [PS, p, p, p, p, p, p, p, p, p, p, p, p, p, p, p, i32, p, sz, p]),
     "fgc_build_reverse_padded": (i32, [p, p, i32, i32, i32, i32, p, p]),
-    "fgc_conv_bwd_planned": (i32, [PS, p, p, p, p, p, p, p, i32, p, p, p, p, p, p, p, p, p, p, p, i32, p, sz, p]),
+    "fgc_conv_bwd_planned": (i32, [PS, p, p, p, p, p, p, p, i32, p, p, p, p, p, p, p, p, p, p, p, i32, p, sz, p, sz, p]),
     "fgc_gather_rows": (i32, [p, p, p, i32, i32, i32, i32, p]),
     "fgc_assignments": (i32, [PS, p, p, p, p, p, p, p, sz, p]),
     "fgc_pool_max": (i32, [p, p, i64, i32, i32, p]),

@@ -53,9 +53,13 @@ class FacetConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, adj, W0, b, u, v, c, bias_mask, cw, ca0, ca, rev):
         plan = conv_plan(adj, W0.shape[0]) if ops.planned_shape(x, W0, cw) else None
-        y = ops.conv_fwd(x, adj, W0, b, u, v, c, bias_mask, ops.ACT_NONE, 0.0, cw, ca0, ca, plan=plan)
+        # planned layers keep the forward's logits and x image for the backward (the parameters are
+        # only updated after backward, so they are still the ones the logits were computed with)
+        saved = ops.ConvSaved() if plan is not None else None
+        y = ops.conv_fwd(x, adj, W0, b, u, v, c, bias_mask, ops.ACT_NONE, 0.0, cw, ca0, ca, plan=plan, save=saved)
         ctx.save_for_backward(x, adj, W0, u, v, c)
         ctx.cfg = (bias_mask, cw, ca0, ca, rev)
+        ctx.fwd_saved = saved
         return y
 
     @staticmethod
@@ -65,7 +69,9 @@ class FacetConvFn(torch.autograd.Function):
         if rev is None:
             rev = reverse_adjacency(adj)
         plan = conv_plan(adj, W0.shape[0]) if ops.planned_shape(x, W0, cw) else None
-        gx, gW0, gb, gu, gv, gc = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, bias_mask, cw, ca0, ca, plan=plan)
+        gx, gW0, gb, gu, gv, gc = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, bias_mask, cw, ca0, ca, plan=plan,
+                                               saved=ctx.fwd_saved)
+        ctx.fwd_saved = None
         return gx, None, gW0, gb, gu, gv, gc, None, None, None, None, None
 
 

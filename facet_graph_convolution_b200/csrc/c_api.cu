@@ -122,6 +122,21 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
   return launch_conv_fwd(p, st);
 }
 
+// shared with conv_bwd.cu
+int conv_fwd_saved_views(const fgc_conv_shape* s, const void* fwd_ws, size_t fwd_ws_bytes, FwdSaved* out) {
+  // mirrors the take() order of conv_fwd's planned branch
+  const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  FGC_REQUIRE(use_mma(s), "conv_bwd: a saved forward workspace needs the planned tensor-core path");
+  Workspace ws(const_cast<void*>(fwd_ws), fwd_ws_bytes);
+  out->uvx = ws.take<float>(rows * 2 * s->M);
+  ws.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);
+  ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M));
+  out->ximg = ws.take<char>(conv_mma_workspace(rows));
+  FGC_REQUIRE(ws.ok(), "conv_bwd: saved forward workspace too small (%zu bytes given, %zu needed)", fwd_ws_bytes,
+              conv_fwd_workspace(s));
+  return FGC_OK;
+}
+
 // ------------------------------------------------------------------ host-buffer path
 struct HostCache {
   int device = -1;
@@ -313,14 +328,16 @@ int fgc_conv_bwd_planned(const fgc_conv_shape* s, const float* gy, const float* 
                          const void* plan, const int32_t* rev_ptr, const int32_t* rev_edge, const int32_t* radj,
                          int Kr, const void* rplan, const float* W0, const float* u, const float* v, const float* c,
                          float* gx, float* gW0, float* gb, float* gu, float* gv, float* gc, int bias_mask,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+                         const void* fwd_workspace, size_t fwd_workspace_bytes, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   int rc = check_shape(s, "conv_bwd_planned");
   if (rc) return rc;
   FGC_REQUIRE(gy && x && adj && rev_ptr && rev_edge && W0 && u && v && c && gx && gW0 && gb && gu && gv && gc,
               "conv_bwd_planned: NULL tensor pointer");
   FGC_REQUIRE((radj == nullptr) == (rplan == nullptr), "conv_bwd_planned: radj and rplan go together");
+  FGC_REQUIRE(fwd_workspace == nullptr || plan != nullptr, "conv_bwd_planned: a saved forward workspace needs the plan");
   return conv_bwd(s, gy, x, adj, rev_ptr, rev_edge, W0, u, v, c, gx, gW0, gb, gu, gv, gc, bias_mask, workspace,
-                  workspace_bytes, as_stream(stream), radj, Kr, rplan, plan);
+                  workspace_bytes, as_stream(stream), radj, Kr, rplan, plan, fwd_workspace, fwd_workspace_bytes);
 }
 
 int fgc_gather_rows(const float* x, const int32_t* adj, float* out, int B, int N, int K, int C,

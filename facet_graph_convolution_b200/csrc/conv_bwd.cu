@@ -867,7 +867,8 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
              const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu, float* gv,
              float* gc, int bias_mask, void* workspace, size_t workspace_bytes, cudaStream_t st,
-             const int32_t* radj, int Kr, const void* rplan, const void* fplan) {
+             const int32_t* radj, int Kr, const void* rplan, const void* fplan, const void* fwd_ws,
+             size_t fwd_ws_bytes) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   BwdPlan pl;
   if (make_plan(s, &pl) != FGC_OK) {
@@ -877,7 +878,7 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   const size_t nW = static_cast<size_t>(s->M) * s->Cout * s->Cw;
   const int nL = 2 * s->M * s->Ca + s->M;
   Workspace ws(workspace, workspace_bytes);
-  float* uvx = ws.take<float>(rows * 2 * s->M);
+  float* uvx_own = ws.take<float>(rows * 2 * s->M);
   float* d_uvx = ws.take<float>(rows * 2 * s->M);
   float* Wd = ws.take<float>(nW);
   float* da_edge = ws.take<float>(rows * s->K * s->M);
@@ -897,8 +898,20 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   FGC_REQUIRE(ws.ok(), "conv_bwd: workspace too small (%zu bytes given)", workspace_bytes);
   static const bool tc_disabled = getenv("FGC_DISABLE_TC") != nullptr;
 
-  int rc = launch_assign_logits(s, x, u, v, c, uvx, st);
-  if (rc) return rc;
+  // Products of the planned forward (logits uvx, fp16 image of x and its scale) are reused when the
+  // caller hands back the forward's workspace untouched (what an autograd context saves).
+  const float* uvx = uvx_own;
+  bool ximg_saved = false;
+  int rc = FGC_OK;
+  if (fwd_ws != nullptr && src_mma) {
+    FwdSaved sv;
+    rc = conv_fwd_saved_views(s, fwd_ws, fwd_ws_bytes, &sv);
+    if (rc) return rc;
+    uvx = sv.uvx, ximg = const_cast<char*>(sv.ximg), ximg_saved = true;
+  } else {
+    rc = launch_assign_logits(s, x, u, v, c, uvx_own, st);
+    if (rc) return rc;
+  }
   const int MP = pick_mp(s->M);
   const bool tc_all = !tc_disabled && s->Cout % 4 == 0 && bwd_tgt_tc_supported(s->Cw, s->Cout, s->M) &&
                       bwd_src_tc_supported(s->Cw, s->Cout, s->M, s->Cin);
@@ -911,8 +924,10 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
       if (rc) return rc;
     }
     if (src_mma) {
-      rc = launch_prep_image(x, s->Cin, rows, ximg, st);
-      if (rc) return rc;
+      if (!ximg_saved) {
+        rc = launch_prep_image(x, s->Cin, rows, ximg, st);
+        if (rc) return rc;
+      }
       rc = launch_bwd_src_mma(gy, uvx, adj, fplan, ximg, gyimg, wimg, da_edge, d_uvx, rows, s->N, s->K, s->M, st);
       if (rc) return rc;
       FGC_CUDA(cudaMemcpyAsync(inv, conv_plan_inv(fplan, rows, s->K, s->M), rows * sizeof(float),
@@ -974,7 +989,11 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   if (g_gx_ready_event != nullptr) FGC_CUDA(cudaEventRecord(g_gx_ready_event, st));
   int wchunks = pl.chunks;
   if (!tc_disabled && bwd_w_tc_supported(s->Cw, s->Cout, s->M, s->Cin)) {
-    rc = launch_bwd_w_tc(gy, x, adj, uvx, partW, partB, maxbits, rows, s->N, s->K, s->Cin, s->M, bias_mask, st);
+    // max|x| and max|gy| were already reduced for the fp16 images of the planned passes
+    const unsigned* xmax = src_mma ? conv_mma_image_maxbits(ximg, rows) : nullptr;
+    const unsigned* gmax = gyimg != nullptr && tc_all ? conv_mma_image_maxbits(gyimg, rows) : nullptr;
+    rc = launch_bwd_w_tc(gy, x, adj, uvx, partW, partB, maxbits, xmax, gmax, rows, s->N, s->K, s->Cin, s->M, bias_mask,
+                         st);
     if (rc) return rc;
     wchunks = bwd_w_tc_grid(rows);
   } else {

@@ -604,15 +604,26 @@ int bwd_w_tc_grid(int64_t rows) {
 }
 
 // partW[grid][M*64*64], partB[grid][64]; maxbits: 2 uints of scratch
+// xmax / gmax: device words holding the float bits of max|x| / max|gy| when a previous pass already
+// reduced them (nullptr: reduce here)
 int launch_bwd_w_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, float* partW,
-                    float* partB, unsigned* maxbits, int64_t rows, int N, int K, int Cin, int M,
-                    int bias_mask, cudaStream_t st) {
-  FGC_CUDA(cudaMemsetAsync(maxbits, 0, 2 * sizeof(unsigned), st));
+                    float* partB, unsigned* maxbits, const unsigned* xmax, const unsigned* gmax, int64_t rows, int N,
+                    int K, int Cin, int M, int bias_mask, cudaStream_t st) {
   const int ab = num_sms() * 4;
-  absmax_kernel<<<ab, 256, 0, st>>>(x, rows * Cin, maxbits);
-  FGC_LAUNCHED("absmax_kernel");
-  absmax_kernel<<<ab, 256, 0, st>>>(gy, rows * 64, maxbits + 1);
-  FGC_LAUNCHED("absmax_kernel");
+  if (xmax != nullptr) {
+    FGC_CUDA(cudaMemcpyAsync(maxbits, xmax, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+  } else {
+    FGC_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(unsigned), st));
+    absmax_kernel<<<ab, 256, 0, st>>>(x, rows * Cin, maxbits);
+    FGC_LAUNCHED("absmax_kernel");
+  }
+  if (gmax != nullptr) {
+    FGC_CUDA(cudaMemcpyAsync(maxbits + 1, gmax, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+  } else {
+    FGC_CUDA(cudaMemsetAsync(maxbits + 1, 0, sizeof(unsigned), st));
+    absmax_kernel<<<ab, 256, 0, st>>>(gy, rows * 64, maxbits + 1);
+    FGC_LAUNCHED("absmax_kernel");
+  }
   WParams p{};
   p.src = AggSrc{x, Cin, adj, uvx, N, K, rows, nullptr, nullptr, nullptr, nullptr};
   p.gy = gy, p.maxbits = maxbits, p.partW = partW, p.partB = partB, p.bias_mask = bias_mask;

@@ -73,15 +73,23 @@ int launch_bwd_src_tc(const float* gy, const float* x, const int32_t* adj, const
 bool bwd_w_tc_supported(int Cw, int Cout, int M, int Cin);
 int bwd_w_tc_grid(int64_t rows);
 int launch_bwd_w_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, float* partW,
-                    float* partB, unsigned* maxbits, int64_t rows, int N, int K, int Cin, int M,
-                    int bias_mask, cudaStream_t st);
+                    float* partB, unsigned* maxbits, const unsigned* xmax, const unsigned* gmax, int64_t rows, int N,
+                    int K, int Cin, int M, int bias_mask, cudaStream_t st);
+const unsigned* conv_mma_image_maxbits(const void* img_ws, int64_t rows);
+// products the planned forward leaves in its workspace (c_api.cu: conv_fwd), reusable by the backward
+struct FwdSaved {
+  const float* uvx;   // [rows][2M] assignment logits
+  const char* ximg;   // conv_mma_workspace(rows) bytes: fp16 hi|lo image of x + its scale words
+};
+int conv_fwd_saved_views(const fgc_conv_shape* s, const void* fwd_ws, size_t fwd_ws_bytes, FwdSaved* out);
 extern thread_local cudaEvent_t g_gx_ready_event;
 size_t conv_bwd_workspace(const fgc_conv_shape* s);
 int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int32_t* adj,
              const int32_t* rev_ptr, const int32_t* rev_edge, const float* W0, const float* u,
              const float* v, const float* c, float* gx, float* gW0, float* gb, float* gu, float* gv,
              float* gc, int bias_mask, void* workspace, size_t workspace_bytes, cudaStream_t st,
-             const int32_t* radj = nullptr, int Kr = 0, const void* rplan = nullptr, const void* fplan = nullptr);
+             const int32_t* radj = nullptr, int Kr = 0, const void* rplan = nullptr, const void* fplan = nullptr,
+             const void* fwd_ws = nullptr, size_t fwd_ws_bytes = 0);
 size_t reverse_adj_workspace(int64_t rows);
 int build_reverse_adj(const int32_t* adj, int B, int N, int K, int32_t* rev_ptr, int32_t* rev_edge,
                       int64_t* nnz_out, void* workspace, size_t workspace_bytes, cudaStream_t st);

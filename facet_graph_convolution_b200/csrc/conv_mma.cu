@@ -276,13 +276,26 @@ conv_mma_kernel(const MmaParams p) {
     const int hh = lane >> 4, o = q * 16 + (lane & 15);
     const float bo = (p.mode == 0) ? __ldg(p.b + o) : 0.f;
     const float sc0 = xun * wun;
+    float* const ybase = p.y + o;
+    const int64_t ldy = p.ldy;
+    const bool unmasked = !p.bias_mask;
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
       const int buf = t & 1;
       const int64_t r0 = tile * TF + 8 * hh;
+      const int nv = (p.rows - r0 >= 8) ? 8 : static_cast<int>(p.rows - r0);   // valid facets of this lane's 8 (<= 0: none)
       float inv[8];
+      if (p.mode == 0) {
+        if (nv == 8) {   // r0 is a multiple of 8: two aligned 16-byte loads
+          const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.pinv + r0));
+          const float4 i1 = __ldg(reinterpret_cast<const float4*>(p.pinv + r0) + 1);
+          inv[0] = i0.x, inv[1] = i0.y, inv[2] = i0.z, inv[3] = i0.w;
+          inv[4] = i1.x, inv[5] = i1.y, inv[6] = i1.z, inv[7] = i1.w;
+        } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) inv[j] = (r0 + j < p.rows) ? __ldg(p.pinv + r0 + j) : 0.f;
+          for (int j = 0; j < 8; ++j) inv[j] = (j < nv) ? __ldg(p.pinv + r0 + j) : 0.f;
+        }
+      }
       tc::mbar_wait(&bars[B_D3_FULL + buf], (t >> 1) & 1);
       if (q == 0) FGC_TR(0, t, 4);
       tc::tc_fence_after_sync();
@@ -292,26 +305,44 @@ conv_mma_kernel(const MmaParams p) {
       tc::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars[B_D3_FREE + buf]);
+      // all eight exchanges are issued before the first is consumed
+      float keep[8], recv[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float hi_lo = __uint_as_float(d[j]) + __uint_as_float(d[TF + j]);         // facets 0..7  (hi lanes)
         const float hi_up = __uint_as_float(d[8 + j]) + __uint_as_float(d[TF + 8 + j]); // facets 8..15 (hi lanes)
         const float lo_lo = __uint_as_float(d[j]) * (1.f / 2048.f);                     // facets 0..7  (lo lanes)
         const float lo_up = __uint_as_float(d[8 + j]) * (1.f / 2048.f);                 // facets 8..15 (lo lanes)
-        const float send = hh ? lo_lo : hi_up;
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-        const float acc = hh ? (recv + lo_up) : (hi_lo + recv);
-        if (r0 + j < p.rows) {
-          float yv;
-          if (p.mode == 0) {
-            const float fl = (inv[j] > 0.f || !p.bias_mask) ? 1.f : 0.f;
-            yv = fmaf(inv[j] * sc0, acc, fl * bo);
-            if (p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
-          } else {
-            yv = sc0 * acc;
-          }
-          p.y[(r0 + j) * p.ldy + o] = yv;
+        keep[j] = hh ? lo_up : hi_lo;
+        recv[j] = hh ? lo_lo : hi_up;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) recv[j] = __shfl_xor_sync(0xffffffffu, recv[j], 16);
+      float yv[8];
+      if (p.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // hi lanes: (Wh.Sh + Wh.Sl) + Wl.Sh/2048; lo lanes: the same sum in the same order
+          const float acc = hh ? (recv[j] + keep[j]) : (keep[j] + recv[j]);
+          const float fl = (inv[j] > 0.f || unmasked) ? bo : 0.f;
+          yv[j] = fmaf(inv[j] * sc0, acc, fl);
         }
+        if (p.act == FGC_ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) yv[j] = lrelu_f(yv[j], p.alpha);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yv[j] = sc0 * (hh ? (recv[j] + keep[j]) : (keep[j] + recv[j]));
+      }
+      float* yp = ybase + r0 * ldy;
+      if (nv == 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yp[j * ldy] = yv[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nv) yp[j * ldy] = yv[j];
       }
       if (q == 0) FGC_TR(0, t, 5);
     }
@@ -783,6 +814,9 @@ static ImgWs img_ws_views(void* img_ws, int64_t rows) {
   v.img = reinterpret_cast<uint4*>(ws.take<char>(static_cast<size_t>(rows) * 256));
   v.scal = ws.take<unsigned>(16);
   return v;
+}
+const unsigned* conv_mma_image_maxbits(const void* img_ws, int64_t rows) {
+  return img_ws_views(const_cast<void*>(img_ws), rows).scal;
 }
 int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st) {
   const ImgWs v = img_ws_views(img_ws, rows);

@@ -102,8 +102,17 @@ class ConvPlan:
                 self.buf = buf
 
 
+class ConvSaved:
+    """What a planned forward leaves behind for its backward (an autograd context keeps it alive):
+    the forward's workspace with the assignment logits and the fp16 image of x.  ``ws is None`` when
+    the forward ran on a path that has nothing to reuse."""
+
+    def __init__(self):
+        self.ws = None
+
+
 def conv_fwd(x, adj, W0, b, u, v, c, bias_mask=True, act=ACT_NONE, alpha=0.1, cw=None, ca0=0, ca=None,
-             plan: Optional[ConvPlan] = None):
+             plan: Optional[ConvPlan] = None, save: Optional[ConvSaved] = None):
     """y[B,N,Cout] of the facet-graph convolution (reference Code/model.py:427-504)."""
     L = _lib.lib()
     x, W0, b, u, v, c = (_f32(t, n) for t, n in ((x, "x"), (W0, "W0"), (b, "b"), (u, "u"), (v, "v"), (c, "c")))
@@ -120,7 +129,11 @@ def conv_fwd(x, adj, W0, b, u, v, c, bias_mask=True, act=ACT_NONE, alpha=0.1, cw
             check(L.fgc_conv_fwd_planned(C.byref(s), _p(x), _p(adj), _p(plan.buf), _p(W0), _p(b), _p(u), _p(v),
                                          _p(c), _p(y), int(bool(bias_mask)), int(act), float(alpha), _p(ws),
                                          ws.numel(), _stream(x)), "fgc_conv_fwd_planned")
+            if save is not None:
+                save.ws = ws
         else:
+            if save is not None:
+                save.ws = None
             check(L.fgc_conv_fwd(C.byref(s), _p(x), _p(adj), _p(W0), _p(b), _p(u), _p(v), _p(c), _p(y),
                                  int(bool(bias_mask)), int(act), float(alpha), _p(ws), ws.numel(), _stream(x)),
                   "fgc_conv_fwd")
@@ -171,8 +184,9 @@ class ReverseAdjacency:
 
 
 def conv_bwd(gy, x, adj, rev: ReverseAdjacency, W0, u, v, c, bias_mask=True, cw=None, ca0=0, ca=None,
-             planned: bool = True, plan: Optional["ConvPlan"] = None):
-    """(gx, gW0, gb, gu, gv, gc) -- deterministic backward of conv_fwd."""
+             planned: bool = True, plan: Optional["ConvPlan"] = None, saved: Optional["ConvSaved"] = None):
+    """(gx, gW0, gb, gu, gv, gc) -- deterministic backward of conv_fwd.  ``saved``: the ConvSaved a
+    planned conv_fwd of the same x, u, v, c filled (its logits and x image are reused)."""
     L = _lib.lib()
     gy, x, W0, u, v, c = (_f32(t, n) for t, n in ((gy, "gy"), (x, "x"), (W0, "W0"), (u, "u"), (v, "v"), (c, "c")))
     adj = _i32(adj, "adj")
@@ -192,10 +206,12 @@ def conv_bwd(gy, x, adj, rev: ReverseAdjacency, W0, u, v, c, bias_mask=True, cw=
         ws = _ws(L.fgc_conv_bwd_workspace(C.byref(s)), x)
         if tp is not None or fplan is not None:
             radj, Kr, rplan = tp if tp is not None else (None, 0, None)
+            fws = saved.ws if (saved is not None and fplan is not None) else None
             check(L.fgc_conv_bwd_planned(C.byref(s), _p(gy), _p(x), _p(adj), _p(fplan.buf) if fplan else None,
                                          _p(rev.ptr), _p(rev.edge), _p(radj), Kr,
                                          _p(rplan.buf) if rplan is not None else None, _p(W0), _p(u), _p(v), _p(c),
                                          _p(gx), _p(gW0), _p(gb), _p(gu), _p(gv), _p(gc), int(bool(bias_mask)),
+                                         _p(fws) if fws is not None else None, fws.numel() if fws is not None else 0,
                                          _p(ws), ws.numel(), _stream(x)), "fgc_conv_bwd_planned")
         else:
             check(L.fgc_conv_bwd(C.byref(s), _p(gy), _p(x), _p(adj), _p(rev.ptr), _p(rev.edge), _p(W0), _p(u),

@@ -142,7 +142,11 @@ FGC_API int fgc_conv_bwd(const fgc_conv_shape* s, const float* gy, const float* 
  * (fgc_build_conv_plan(radj, B, N, Kr, M, ...)) lets fgc_conv_bwd_planned run the gx pass on the
  * dense-assignment tensor-core kernel, and the forward plan of adj lets it run the source-centric
  * pass (ds, dq, da) on the staged tcgen05 pipeline; with plan = radj = rplan = NULL it equals
- * fgc_conv_bwd. */
+ * fgc_conv_bwd.
+ * fwd_workspace (optional, needs plan): the workspace buffer fgc_conv_fwd_planned ran in for the same
+ * shape, x, u, v, c, untouched since -- what an autograd context saves for backward.  The backward then
+ * reuses the forward's assignment logits and fp16 image of x instead of recomputing them (same bits,
+ * three kernels fewer).  NULL: everything is recomputed from x. */
 FGC_API int fgc_build_reverse_padded(const int32_t* rev_ptr, const int32_t* rev_edge, int B, int N, int K,
                              int Kr, int32_t* radj, void* stream);
 FGC_API int fgc_conv_bwd_planned(const fgc_conv_shape* s, const float* gy, const float* x,
@@ -150,7 +154,8 @@ FGC_API int fgc_conv_bwd_planned(const fgc_conv_shape* s, const float* gy, const
                          const int32_t* rev_ptr, const int32_t* rev_edge, const int32_t* radj,
                          int Kr, const void* rplan, const float* W0,
                          const float* u, const float* v, const float* c, float* gx, float* gW0,
-                         float* gb, float* gu, float* gv, float* gc, int bias_mask, void* workspace,
+                         float* gb, float* gu, float* gv, float* gc, int bias_mask,
+                         const void* fwd_workspace, size_t fwd_workspace_bytes, void* workspace,
                          size_t workspace_bytes, void* stream);
 
 /* debug/parity helper: the gathered-neighbour tensor concat([0],x)[adj] -> out[B,N,K,C]

@@ -151,6 +151,33 @@ def test_planned_backward_matches_oracle_and_is_reproducible():
             assert torch.equal(a1, a2), (name, k)       # deterministic: no atomics on floats
 
 
+def test_backward_with_saved_forward_products_is_bit_identical():
+    """conv_bwd(saved=...) reuses the forward's logits and fp16 image of x: same bits as recomputing."""
+    from facet_graph_convolution_b200 import ops
+    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
+    rs = np.random.RandomState(3)
+    for name, x, adj in _cases():
+        W0, b, u, v, c = _params(rs)
+        gy = rs.randn(*x.shape[:2], 64).astype(np.float32)
+        rev = ops.ReverseAdjacency(T(adj))
+        fp = ops.ConvPlan(T(adj), 8)
+        saved = ops.ConvSaved()
+        xd, ad = T(x), T(adj)
+        ops.conv_fwd(xd, ad, T(W0), T(b), T(u), T(v), T(c), plan=fp, save=saved)
+        assert saved.ws is not None
+        # scribble over freshly freed allocator blocks: the saved workspace must be what is read
+        junk = torch.full((saved.ws.numel() // 4,), float("nan"), device=dev())
+        del junk
+        g1 = ops.conv_bwd(T(gy), xd, ad, rev, T(W0), T(u), T(v), T(c), plan=fp, saved=saved)
+        g2 = ops.conv_bwd(T(gy), xd, ad, rev, T(W0), T(u), T(v), T(c), plan=fp)
+        for k, a1, a2 in zip(["gx", "gW0", "gb", "gu", "gv", "gc"], g1, g2):
+            assert torch.equal(a1, a2), (name, k)
+    # a forward without a plan has nothing to save, and the backward then recomputes
+    saved = ops.ConvSaved()
+    ops.conv_fwd(xd, ad, T(W0), T(b), T(u), T(v), T(c), save=saved)
+    assert saved.ws is None
+
+
 def test_reverse_padded_adjacency_is_exact():
     from facet_graph_convolution_b200 import ops
     _, x, adj = _cases()[0]
