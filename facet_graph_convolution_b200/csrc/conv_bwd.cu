@@ -800,9 +800,12 @@ size_t conv_bwd_workspace(const fgc_conv_shape* s) {
   b += ws_bytes(nW, 4);                            // Wd
   b += ws_bytes(rows * s->K * s->M, 4);            // da_edge
   b += ws_bytes(rows, 4);                          // inv
-  const size_t wparts = std::max<size_t>(pl.chunks, bwd_w_tc_grid(rows));
+  const bool mma_ok = conv_mma_supported(s->Cin, s->Cw, s->Cout, s->M, s->K);
+  size_t wparts = std::max<size_t>(pl.chunks, bwd_w_tc_grid(rows));
+  if (mma_ok) wparts = std::max<size_t>(wparts, bwd_w_mma_grid(rows, s->M));
+  const size_t bparts = mma_ok ? std::max<size_t>(wparts, prep_image_blocks()) : wparts;
   b += ws_bytes(wparts * nW, 4);        // partW
-  b += ws_bytes(wparts * s->Cout, 4);   // partB
+  b += ws_bytes(bparts * s->Cout, 4);   // partB
   b += ws_bytes(4, 4);                  // absmax scratch
   b += ws_bytes(static_cast<size_t>(pl.lchunks) * (2 * s->M * s->Ca + s->M), 4);  // logits partials
   b += ws_bytes(conv_fwd_tc_workspace(s->Cw > s->Cout ? s->Cw : s->Cout, s->M), 1);   // TC weight image
@@ -883,9 +886,12 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   float* Wd = ws.take<float>(nW);
   float* da_edge = ws.take<float>(rows * s->K * s->M);
   float* inv = ws.take<float>(rows);
-  const size_t wparts = std::max<size_t>(pl.chunks, bwd_w_tc_grid(rows));
+  const bool mma_ok = conv_mma_supported(s->Cin, s->Cw, s->Cout, s->M, s->K);
+  size_t wparts = std::max<size_t>(pl.chunks, bwd_w_tc_grid(rows));
+  if (mma_ok) wparts = std::max<size_t>(wparts, bwd_w_mma_grid(rows, s->M));
+  const size_t bparts = mma_ok ? std::max<size_t>(wparts, prep_image_blocks()) : wparts;
   float* partW = ws.take<float>(wparts * nW);
-  float* partB = ws.take<float>(wparts * s->Cout);
+  float* partB = ws.take<float>(bparts * s->Cout);
   unsigned* maxbits = ws.take<unsigned>(4);
   float* partL = ws.take<float>(static_cast<size_t>(pl.lchunks) * nL);
   char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cw > s->Cout ? s->Cw : s->Cout, s->M));
@@ -919,8 +925,10 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
     rc = launch_prep_w_image_t(W0, wimg, s->M, s->Cw, st);
     if (rc) return rc;
     const float* wunscale = reinterpret_cast<const float*>(wimg + static_cast<size_t>(s->M) * 2 * s->Cw * 128);
-    if (gyimg != nullptr) {   // the gy image serves the gz scale of the source pass and the rows of the target pass
-      rc = launch_prep_image(gy, s->Cout, rows, gyimg, st);
+    if (gyimg != nullptr) {   // the gy image serves the source pass, the target pass and the weight gradient
+      // (with a forward plan the same pass over gy also leaves the bias-gradient partials)
+      if (src_mma) rc = launch_prep_image(gy, s->Cout, rows, gyimg, st, conv_plan_inv(fplan, rows, s->K, s->M), bias_mask, partB);
+      else rc = launch_prep_image(gy, s->Cout, rows, gyimg, st);
       if (rc) return rc;
     }
     if (src_mma) {
@@ -987,8 +995,13 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
     FGC_LAUNCHED("logits_bwd_x_kernel");
   }
   if (g_gx_ready_event != nullptr) FGC_CUDA(cudaEventRecord(g_gx_ready_event, st));
-  int wchunks = pl.chunks;
-  if (!tc_disabled && bwd_w_tc_supported(s->Cw, s->Cout, s->M, s->Cin)) {
+  int wchunks = pl.chunks, bchunks = -1;
+  if (src_mma && tc_all) {
+    rc = launch_bwd_w_mma(uvx, adj, fplan, ximg, gyimg, partW, rows, s->N, s->K, s->M, st);
+    if (rc) return rc;
+    wchunks = bwd_w_mma_grid(rows, s->M);
+    bchunks = prep_image_blocks();
+  } else if (!tc_disabled && bwd_w_tc_supported(s->Cw, s->Cout, s->M, s->Cin)) {
     // max|x| and max|gy| were already reduced for the fp16 images of the planned passes
     const unsigned* xmax = src_mma ? conv_mma_image_maxbits(ximg, rows) : nullptr;
     const unsigned* gmax = gyimg != nullptr && tc_all ? conv_mma_image_maxbits(gyimg, rows) : nullptr;
@@ -1016,7 +1029,7 @@ int conv_bwd(const fgc_conv_shape* s, const float* gy, const float* x, const int
   }
   rc = launch_reduce_partials(partW, gW0, nW, wchunks, nW, st);
   if (rc) return rc;
-  rc = launch_reduce_partials(partB, gb, s->Cout, wchunks, s->Cout, st);
+  rc = launch_reduce_partials(partB, gb, s->Cout, bchunks > 0 ? bchunks : wchunks, s->Cout, st);
   if (rc) return rc;
   const int nUV = s->M * s->Ca;
   rc = launch_reduce_partials(partL, gu, nUV, pl.lchunks, nL, st);

@@ -50,7 +50,12 @@ size_t conv_plan_bytes(int64_t rows, int K, int M);
 int build_conv_plan(const int32_t* adj, int B, int N, int K, int M, void* plan, size_t plan_bytes, cudaStream_t st);
 size_t conv_mma_workspace(int64_t rows);
 int debug_mma_trace(int64_t* out, int n);
-int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st);
+int prep_image_blocks();
+int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st,
+                      const float* pinv = nullptr, int bias_mask = 0, float* partB = nullptr);
+int bwd_w_mma_grid(int64_t rows, int M);
+int launch_bwd_w_mma(const float* uvx, const int32_t* adj, const void* plan, void* ximg_ws, void* gyimg_ws,
+                     float* partW, int64_t rows, int N, int K, int M, cudaStream_t st);
 bool bwd_src_mma_supported(int Cin, int Cw, int Cout, int M, int K);
 const float* conv_plan_inv(const void* plan, int64_t rows, int K, int M);
 int launch_bwd_src_mma(const float* gy, const float* uvx, const int32_t* adj, const void* plan, void* ximg_ws,

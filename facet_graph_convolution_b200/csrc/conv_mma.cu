@@ -85,18 +85,23 @@ struct MCfg {
   static constexpr int Q_BUF = 2 * Q_PLANE;          // hi | lo
   static constexpr int B3_ATOM = NB3 * 128;          // [NB3 rows][64 K] halves
   static constexpr int B3_BUF = M * B3_ATOM;
-  static constexpr int EX_BYTES = 0;
-  static constexpr int OFF_X = 0;
+  static constexpr int GZ_BUF = 2 * TF * 128;        // weight-gradient mode: gy image rows of the tile's facets,
+  static constexpr int OFF_X = 0;                    //   [TF rows hi | TF rows lo][64 o] halves (MN-major B operand);
+                                                     //   buffer b shares the full/free barriers of B3 buffer b
   static constexpr int OFF_Q = OFF_X + NX * X_BUF;
   static constexpr int OFF_B3 = OFF_Q + 2 * Q_BUF;
-  static constexpr int OFF_EX = OFF_B3 + 2 * B3_BUF;
-  static constexpr int OFF_BAR = OFF_EX + EX_BYTES;
+  static constexpr int OFF_GZ = OFF_B3 + 2 * B3_BUF;
+  static constexpr int OFF_EX = OFF_GZ + 2 * GZ_BUF;
+  static constexpr int OFF_BAR = OFF_EX;
   static constexpr int SMEM_BYTES = OFF_BAR + 512;
   // TMEM: the weight operand [Wh;Wl] lives here for the CTA's lifetime (A of stage 2, 2 halves/column)
   static constexpr int W_COL = 0;
   static constexpr int W_COLS = M * kC / 2;          // 256
   static constexpr int D1_COL = W_COL + W_COLS;      // two stage-1 accumulators of 64 columns
   static constexpr int D3_COL = D1_COL + 2 * 64;     // two stage-2 accumulators of NB3 columns
+  // weight-gradient mode: no resident weights; D1 at 0, the M/2 gW accumulators of 64 columns behind it
+  static constexpr int GW_D1_COL = 0;
+  static constexpr int GW_COL = 128;
   static constexpr int TMEM_COLS = 512;
   static_assert(D3_COL + 2 * NB3 <= TMEM_COLS, "TMEM overflow");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
@@ -126,6 +131,10 @@ struct MmaParams {
   int uo_off, vl_off;
   const float* inv_src;    // nullptr in forward mode
   int mode;                // 0: y = act(inv*scale*acc + flag*b)   1: y = scale*acc (gx of the target pass)
+                           // 2: weight gradient -- stage 2 is gW0[m] += (inv S_m)^T gy over the CTA's tiles,
+                           //    y = this CTA's partial gW0 [M][COUT][64] (partW + blockIdx.x * M*COUT*64)
+  const uint4* gimg;       // mode 2: fp16 hi|lo image of gy
+  const float* gunscale;   // mode 2
 };
 
 enum {
@@ -139,7 +148,8 @@ enum {
   B_B3_FREE = 18,          // 2
   B_D3_FULL = 20,          // 2
   B_D3_FREE = 22,          // 2
-  B_NUM = 24
+  B_GW_DONE = 24,          // 1 (mode 2; last stage-2 commit)
+  B_NUM = 25
 };
 
 // optional pipeline trace (FGC_MMA_TRACE=1): clock64 stamps of CTA 0, first 32 tiles, 4 roles x 8 events
@@ -172,6 +182,7 @@ conv_mma_kernel(const MmaParams p) {
       tc::mbar_init(&bars[B_B3_FULL + i], 4), tc::mbar_init(&bars[B_B3_FREE + i], 1);
       tc::mbar_init(&bars[B_D3_FULL + i], 1), tc::mbar_init(&bars[B_D3_FREE + i], 4);
     }
+    tc::mbar_init(&bars[B_GW_DONE], 1);
     tc::mbar_fence_init();
   }
   if (warp == 18) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -186,7 +197,9 @@ conv_mma_kernel(const MmaParams p) {
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  const bool gw_mode = p.mode == 2;
+  const uint32_t d1_col = gw_mode ? Cfg::GW_D1_COL : Cfg::D1_COL;
+  if (warp < 4 && !gw_mode) {
     // weight operand -> TMEM, column = K pair; un-swizzle the shared-memory image (16-byte units XOR
     // row & 7) on the way.  Lane 32q + 16h + i holds row h*COUT + 16q + i of [Wh;Wl]: the hi and lo
     // rows of output channel 16q + i sit in the same warp, so the epilogue combines them by shuffle.
@@ -221,6 +234,19 @@ conv_mma_kernel(const MmaParams p) {
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
       const int buf = t & 1;
+      // weight-gradient mode: S rows are scaled by 1/cnt of their facet (gz = inv gy, folded into S)
+      // and the drain warps also stage the gy image rows of the tile (thread -> facet tid/8, 16-byte unit
+      // tid%8 of the hi and of the lo plane): loaded here, long before the fence below
+      float rsc = 1.f;
+      uint4 gzh = make_uint4(0, 0, 0, 0), gzl = gzh;
+      if (gw_mode) {
+        rsc = (tile * TF + f < p.rows) ? __ldg(p.pinv + tile * TF + f) : 0.f;
+        const int64_t gr = tile * TF + (threadIdx.x >> 3);
+        if (gr < p.rows) {
+          gzh = __ldg(p.gimg + gr * 16 + (threadIdx.x & 7));
+          gzl = __ldg(p.gimg + gr * 16 + 8 + (threadIdx.x & 7));
+        }
+      }
       tc::mbar_wait(&bars[B_D1_FULL + buf], (t >> 1) & 1);
       if (warp == 0) FGC_TR(0, t, 0);
       tc::tc_fence_after_sync();
@@ -228,8 +254,12 @@ conv_mma_kernel(const MmaParams p) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
-        tc::tmem_ld32(tmem + lane_base + Cfg::D1_COL + buf * 64 + half * 32, v);
+        tc::tmem_ld32(tmem + lane_base + d1_col + buf * 64 + half * 32, v);
         tc::tc_wait_ld();
+        if (gw_mode) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * rsc);
+        }
         if (half == 1) {
           tc::tc_fence_before_sync();
           __syncwarp();
@@ -250,6 +280,12 @@ conv_mma_kernel(const MmaParams p) {
           if (warp == 0) FGC_TR(0, t, 1);
           tc::mbar_wait(&bars[B_B3_FREE + buf], ((t >> 1) & 1) ^ 1);
           if (warp == 0) FGC_TR(0, t, 2);
+          if (gw_mode) {
+            uint8_t* gz = smem + Cfg::OFF_GZ + buf * Cfg::GZ_BUF;
+            const int kh = threadIdx.x >> 3, kl = TF + kh, cc = threadIdx.x & 7;
+            *reinterpret_cast<uint4*>(gz + (kh >> 3) * 1024 + (kh & 7) * 128 + ((cc ^ (kh & 7)) << 4)) = gzh;
+            *reinterpret_cast<uint4*>(gz + (kl >> 3) * 1024 + (kl & 7) * 128 + ((cc ^ (kl & 7)) << 4)) = gzl;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -269,7 +305,7 @@ conv_mma_kernel(const MmaParams p) {
     // =========================================================== epilogue: Y (TMEM) -> global
     const int q = warp - 4;                      // TMEM lane quadrant
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const float wun = __ldg(p.wunscale), xun = __ldg(p.xunscale);
+    const float wun = gw_mode ? 1.f : __ldg(p.wunscale), xun = __ldg(p.xunscale);
     static_assert(TF == 16, "epilogue written for 16-facet tiles");
     // lane 16h + i of quadrant q: h = 0 holds Wh.(Sh|Sl) of channel o = 16q + i, h = 1 holds Wl.Sh.
     // After one shuffle round lane (h, i) owns facets 8h .. 8h+7 of channel o.
@@ -280,6 +316,28 @@ conv_mma_kernel(const MmaParams p) {
     const int64_t ldy = p.ldy;
     const bool unmasked = !p.bias_mask;
     int t = 0;
+    if (gw_mode) {
+      // weight-gradient mode: one read-out per CTA.  TMEM lane 64 parity + c, column 64 i + o holds
+      // gW0[2i + parity][o][c] in image units; partial of this CTA -> p.y + blockIdx.x * M*COUT*64
+      const float usc = xun * __ldg(p.gunscale);
+      const int row = q * 32 + lane, par = row >> 6, cch = row & 63;
+      float* out = p.y + static_cast<size_t>(blockIdx.x) * (M * COUT * kC);
+      tc::mbar_wait(&bars[B_GW_DONE], 0);
+      tc::tc_fence_after_sync();
+#pragma unroll 1
+      for (int i = 0; i < M / 2; ++i) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t d[32];
+          tc::tmem_ld32(tmem + lane_base + Cfg::GW_COL + i * 64 + half * 32, d);
+          tc::tc_wait_ld();
+          float* dst = out + (static_cast<size_t>(2 * i + par) * COUT + half * 32) * kC + cch;
+#pragma unroll
+          for (int oo = 0; oo < 32; ++oo) dst[oo * kC] = __uint_as_float(d[oo]) * usc;
+        }
+      }
+      tc::tc_fence_before_sync();
+    } else
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
       const int buf = t & 1;
       const int64_t r0 = tile * TF + 8 * hh;
@@ -592,7 +650,7 @@ conv_mma_kernel(const MmaParams p) {
         if (tc::elect_one()) {
           const uint32_t xh = sb + Cfg::OFF_X + xbuf * Cfg::X_BUF, xl = xh + Cfg::X_PLANE;
           const uint32_t qh = sb + Cfg::OFF_Q + qb * Cfg::Q_BUF, ql = qh + Cfg::Q_PLANE;
-          const uint32_t d1 = tmem + Cfg::D1_COL + dbuf * 64;
+          const uint32_t d1 = tmem + d1_col + dbuf * 64;
 #pragma unroll 1
           for (int ks = 0; ks < nks; ++ks) {
             const uint64_t aqh = tc::smem_desc_k_sw128(qh + ks * 32);
@@ -617,6 +675,36 @@ conv_mma_kernel(const MmaParams p) {
     constexpr uint32_t idesc3 = (1u << 4) | ((static_cast<uint32_t>(Cfg::NB3) >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t sb = tc::smem_u32(smem);
     int t = 0;
+    if (gw_mode) {
+      // weight gradient: D_i[(m parity, c), o] += sum_f (inv S)[f, 2i + parity, c] gy[f, o], i = 0..M/2-1
+      // A = two B3 atoms read MN-major (M = 128: 64 channels of weight 2i, then of 2i+1; K = 16 facets),
+      // B = the gy rows (MN-major, N = 64); hi.hi + lo.hi + hi.lo into one fp32 accumulator that stays
+      // in TMEM for the CTA's lifetime.
+      constexpr uint32_t idescW = (1u << 4) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+        const int buf = t & 1;
+        tc::mbar_wait(&bars[B_B3_FULL + buf], (t >> 1) & 1);
+        tc::tc_fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t b3 = sb + Cfg::OFF_B3 + buf * Cfg::B3_BUF;
+          const uint32_t gz = sb + Cfg::OFF_GZ + buf * Cfg::GZ_BUF;
+          const uint64_t bgh = desc_mn_sw128(gz, 1024, 1024);
+          const uint64_t bgl = desc_mn_sw128(gz + TF * 128, 1024, 1024);
+#pragma unroll
+          for (int i = 0; i < M / 2; ++i) {
+            const uint64_t ash = desc_mn_sw128(b3 + 2 * i * Cfg::B3_ATOM, Cfg::B3_ATOM, 1024);
+            const uint64_t asl = desc_mn_sw128(b3 + 2 * i * Cfg::B3_ATOM + TF * 128, Cfg::B3_ATOM, 1024);
+            const uint32_t dw = tmem + Cfg::GW_COL + i * 64;
+            tc::mma_f16_ss(dw, ash, bgh, idescW, t ? 1u : 0u);
+            tc::mma_f16_ss(dw, asl, bgh, idescW, 1u);
+            tc::mma_f16_ss(dw, ash, bgl, idescW, 1u);
+          }
+          tc::tc_commit(&bars[B_B3_FREE + buf]);
+          if (tile + gridDim.x >= p.ntiles) tc::tc_commit(&bars[B_GW_DONE]);
+        }
+        __syncwarp();
+      }
+    } else
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
       const int buf = t & 1;
       FGC_TR(3, t, 4);
@@ -649,9 +737,15 @@ conv_mma_kernel(const MmaParams p) {
 
 // ------------------------------------------------------------------ fp16 hi|lo image of x
 // img[r] = [fp16(x_r * s) (64) | fp16(x_r * s - hi) (64)], s = 2^(126-E) with E the exponent of max|x|
+// Optionally (partB != nullptr, ldx == 64) also the bias gradient of the layer the rows are the gy of:
+// partB[block][64] = sum over the block's rows of flag_r * x_r, flag_r = (pinv_r > 0 or no bias mask);
+// fixed thread -> row assignment and a fixed-order block reduction: deterministic.
 __global__ void __launch_bounds__(256)
 prep_x_image_kernel(const float* __restrict__ x, int ldx, int64_t rows, const unsigned* __restrict__ maxbits,
-                    uint4* __restrict__ img, float* __restrict__ xunscale) {
+                    uint4* __restrict__ img, float* __restrict__ xunscale, const float* __restrict__ pinv,
+                    int bias_mask, float* __restrict__ partB) {
+  __shared__ float red[256 * 9];
+  float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int E = static_cast<int>((__ldg(maxbits) >> 23) & 0xFF);
   E = min(max(E, 16), 240);
   const float sc = __int_as_float((253 - E) << 23);
@@ -663,6 +757,11 @@ prep_x_image_kernel(const float* __restrict__ x, int ldx, int64_t rows, const un
     const int j = static_cast<int>(i & 7);
     const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + 2 * j);
     const float4 b = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + 2 * j + 1);
+    if (partB != nullptr) {
+      const float fl = (!bias_mask || __ldg(pinv + r) > 0.f) ? 1.f : 0.f;
+      bs[0] += fl * a.x, bs[1] += fl * a.y, bs[2] += fl * a.z, bs[3] += fl * a.w;
+      bs[4] += fl * b.x, bs[5] += fl * b.y, bs[6] += fl * b.z, bs[7] += fl * b.w;
+    }
     const float v[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, b.x * sc, b.y * sc, b.z * sc, b.w * sc};
     uint32_t hi[4], lo[4];
 #pragma unroll
@@ -675,6 +774,18 @@ prep_x_image_kernel(const float* __restrict__ x, int ldx, int64_t rows, const un
     }
     img[r * 16 + j] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     img[r * 16 + 8 + j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (partB != nullptr) {
+    // thread t always works on channels 8 (t % 8) .. 8 (t % 8) + 7 (block and grid strides are multiples of 8)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) red[threadIdx.x * 9 + q] = bs[q];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int jj = threadIdx.x >> 3, q = threadIdx.x & 7;
+      float acc = 0.f;
+      for (int w = 0; w < 32; ++w) acc += red[(w * 8 + jj) * 9 + q];
+      partB[static_cast<size_t>(blockIdx.x) * 64 + threadIdx.x] = acc;
+    }
   }
 }
 
@@ -818,14 +929,18 @@ static ImgWs img_ws_views(void* img_ws, int64_t rows) {
 const unsigned* conv_mma_image_maxbits(const void* img_ws, int64_t rows) {
   return img_ws_views(const_cast<void*>(img_ws), rows).scal;
 }
-int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st) {
+int prep_image_blocks() { return num_sms() * 8; }
+int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st, const float* pinv,
+                      int bias_mask, float* partB) {
   const ImgWs v = img_ws_views(img_ws, rows);
   FGC_CUDA(cudaMemsetAsync(v.scal, 0, 16 * sizeof(unsigned), st));
-  const int ab = num_sms() * 8;
+  const int ab = prep_image_blocks();
+  FGC_REQUIRE(partB == nullptr || (ld == 64 && pinv != nullptr), "prep_image: bias partials need 64-channel rows");
   // a row stride above 64 (concat tails): scan the whole tensor, a superset bound is still a valid scale
   absmax2_kernel<<<ab, 256, 0, st>>>(x, rows * (ld / 4), v.scal);
   FGC_LAUNCHED("absmax_kernel");
-  prep_x_image_kernel<<<ab, 256, 0, st>>>(x, ld, rows, v.scal, v.img, reinterpret_cast<float*>(v.scal + 1));
+  prep_x_image_kernel<<<ab, 256, 0, st>>>(x, ld, rows, v.scal, v.img, reinterpret_cast<float*>(v.scal + 1), pinv,
+                                          bias_mask, partB);
   FGC_LAUNCHED("prep_x_image_kernel");
   return FGC_OK;
 }
@@ -965,6 +1080,40 @@ int launch_bwd_tgt_mma(const float* gy, const float* uvx, const float* da_edge, 
   return FGC_OK;
 }
 
+
+// Weight gradient on the dense-assignment kernel (mode 2): gW0[m] = sum_n gz_n (x) s[n,m,:], with s rebuilt by
+// stage 1 exactly as in the forward.  partW: [grid][M][64][64] per-CTA partials (reduced in fixed order by the
+// caller); returns the grid in *grid_out.  ximg_ws / gyimg_ws: images prepared by launch_prep_image.
+int bwd_w_mma_grid(int64_t rows, int M) {
+  const int64_t ntiles = (rows + 128 / M - 1) / (128 / M);
+  int64_t g = num_sms();
+  if (g > ntiles) g = ntiles;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+int launch_bwd_w_mma(const float* uvx, const int32_t* adj, const void* plan, void* ximg_ws, void* gyimg_ws,
+                     float* partW, int64_t rows, int N, int K, int M, cudaStream_t st) {
+  using Cfg = MCfg<8, 64>;
+  const PlanLayout L(rows, K, M);
+  const char* pb = static_cast<const char*>(plan);
+  const ImgWs xi = img_ws_views(ximg_ws, rows), gi = img_ws_views(gyimg_ws, rows);
+  MmaParams mp{};
+  mp.img = xi.img, mp.xunscale = reinterpret_cast<const float*>(xi.scal + 1), mp.uvx = uvx, mp.adj = adj;
+  mp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), mp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
+  mp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), mp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
+  mp.wimg = nullptr, mp.wunscale = nullptr, mp.b = nullptr, mp.y = partW;
+  mp.rows = rows, mp.ntiles = L.ntiles, mp.N = N, mp.K = K, mp.ldy = 64, mp.bias_mask = 0;
+  mp.act = FGC_ACT_NONE, mp.alpha = 0.f;
+  mp.uo_off = 0, mp.vl_off = M, mp.inv_src = nullptr, mp.mode = 2;
+  mp.gimg = gi.img, mp.gunscale = reinterpret_cast<const float*>(gi.scal + 1);
+  mp.trace = 0;
+  void (*kern)(const MmaParams) = conv_mma_kernel<8, 64, 4>;
+  if (K <= 16) kern = conv_mma_kernel<8, 64, 2>;
+  else if (K <= 24) kern = conv_mma_kernel<8, 64, 3>;
+  FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  kern<<<static_cast<unsigned>(bwd_w_mma_grid(rows, M)), kMmaThreads, Cfg::SMEM_BYTES, st>>>(mp);
+  FGC_LAUNCHED("bwd_w_mma_kernel");
+  return FGC_OK;
+}
 
 bool bwd_src_mma_supported(int Cin, int Cw, int Cout, int M, int K) { return conv_mma_supported(Cin, Cw, Cout, M, K); }
 
