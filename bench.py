@@ -81,6 +81,7 @@ def kernel_bytes(name, n):
         "conv_mma_kernel": bytes_fwd(n),
         "bwd_tgt_mma_kernel": 4 * n * (C_OUT + C_IN) + p,
         "bwd_src_mma_kernel": 4 * n * (C_IN + K_NEIGH + C_OUT) + p,
+        "bwd_w_mma_kernel": 4 * n * (C_IN + K_NEIGH + C_OUT) + p,
         "prep_x_image_kernel": 4 * n * C_IN,
         "logits_bwd_x_kernel": 4 * n * 2 * C_IN,
         "logits_bwd_p_kernel": 4 * n * C_IN,
@@ -363,7 +364,8 @@ def main():
                "h2d_bytes_per_step": 4 * (x_h.numel() + adj_h.numel() + gy_h.numel() + npar),
                "d2h_bytes_per_step": 4 * (y_h.numel() + gx_h.numel() + npar),
                "steps": ksteps, "ms_per_step": dt / ksteps * 1e3,
-               "api": "fgc_conv_fwd_bwd_host (C ABI, pinned host buffers, includes reverse-adjacency build)"}
+               "api": "fgc_conv_fwd_bwd_host (C ABI, pinned host buffers; the reverse adjacency and both tile "
+                      "plans are rebuilt from adj inside every call)"}
         L.fgc_host_release()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)

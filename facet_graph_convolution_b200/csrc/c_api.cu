@@ -410,15 +410,21 @@ int fgc_conv_fwd_bwd_host(const fgc_conv_shape* s, const float* x, const int32_t
   const size_t nW = static_cast<size_t>(s->M) * s->Cout * s->Cw, nu = static_cast<size_t>(s->M) * s->Ca;
   const size_t wsf = conv_fwd_workspace(s), wsb = conv_bwd_workspace(s);
   const size_t wsr = reverse_adj_workspace(rows);
-  size_t wsmax = wsf > wsb ? wsf : wsb;
-  if (wsr > wsmax) wsmax = wsr;
+  // caches of the planned tensor-core path, rebuilt per call from adj (they only depend on adj) while x
+  // is still on the wire: forward tile plan, reversed adjacency in forward layout (<= 32 slots) + its plan
+  const bool mma = use_mma(s);
+  const int kKrMax = 32;
+  const size_t pbf = mma ? conv_plan_bytes(rows, s->K, s->M) : 0;
+  const size_t pbr = mma ? conv_plan_bytes(rows, kKrMax, s->M) : 0;
   size_t total = 0;
   auto place = [&](size_t bytes) { size_t o = total; total = align_up(total + bytes, 256); return o; };
   const size_t ox = place(nx * 4), oadj = place(nadj * 4), ogy = place(ny * 4), oy = place(ny * 4),
                ogx = place(nx * 4), oW = place(nW * 4), ob = place(s->Cout * 4), ou = place(nu * 4),
                ov = place(nu * 4), oc = place(s->M * 4), ogW = place(nW * 4), ogb = place(s->Cout * 4),
                ogu = place(nu * 4), ogv = place(nu * 4), ogc = place(s->M * 4),
-               orp = place((rows + 1) * 4), ore = place(nadj * 4), orw = place(wsr), ows = place(wsmax);
+               orp = place((rows + 1) * 4), ore = place(nadj * 4), orw = place(wsr), owf = place(wsf),
+               owb = place(wsb), opf = place(pbf), opr = place(pbr), ora = place(mma ? rows * kKrMax * 4 : 0),
+               odg = place(256);
   rc = host_reserve(device, total);
   if (rc) return rc;
   // Three streams: copies in, kernels, copies out.  The adjacency goes first (the reverse adjacency
@@ -444,10 +450,42 @@ int fgc_conv_fwd_bwd_host(const fgc_conv_shape* s, const float* x, const int32_t
   rc = build_reverse_adj((int32_t*)(d + oadj), s->B, s->N, s->K, (int32_t*)(d + orp),
                          (int32_t*)(d + ore), nullptr, d + orw, wsr, st);
   if (rc) return rc;
+  const void* fplan = nullptr;
+  const void* rplan = nullptr;
+  const int32_t* radj = nullptr;
+  int Kr = 0;
+  if (mma) {
+    // The plans pay per distinct row of a tile: with little neighbour sharing (random adjacency) the
+    // per-facet gather kernels are faster, so the plan is dropped above kMaxMeanRows rows per tile.
+    const double kMaxMeanRows = 112.0;
+    long long hdr[2] = {0, 0};
+    int deg = 0;
+    rc = build_conv_plan((int32_t*)(d + oadj), s->B, s->N, s->K, s->M, d + opf, pbf, st);
+    if (rc) return rc;
+    rc = launch_max_degree((int32_t*)(d + orp), rows, (int32_t*)(d + odg), st);
+    if (rc) return rc;
+    FGC_CUDA(cudaMemcpyAsync(hdr, d + opf, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+    FGC_CUDA(cudaMemcpyAsync(&deg, d + odg, sizeof(deg), cudaMemcpyDeviceToHost, st));
+    FGC_CUDA(cudaStreamSynchronize(st));   // x is still arriving on the copy stream
+    if (hdr[1] > 0 && static_cast<double>(hdr[0]) / hdr[1] <= kMaxMeanRows) fplan = d + opf;
+    Kr = deg < 8 ? 8 : (deg + 7) / 8 * 8;
+    if (Kr <= kKrMax) {
+      rc = launch_build_radj((int32_t*)(d + orp), (int32_t*)(d + ore), s->B, s->N, s->K, Kr, (int32_t*)(d + ora), st);
+      if (rc) return rc;
+      rc = build_conv_plan((int32_t*)(d + ora), s->B, s->N, Kr, s->M, d + opr, pbr, st);
+      if (rc) return rc;
+      FGC_CUDA(cudaMemcpyAsync(hdr, d + opr, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+      FGC_CUDA(cudaStreamSynchronize(st));
+      if (hdr[1] > 0 && static_cast<double>(hdr[0]) / hdr[1] <= kMaxMeanRows) {
+        rplan = d + opr;
+        radj = (int32_t*)(d + ora);
+      }
+    }
+  }
   FGC_CUDA(cudaStreamWaitEvent(st, e_x, 0));
   rc = conv_fwd(s, (float*)(d + ox), (int32_t*)(d + oadj), (float*)(d + oW), (float*)(d + ob),
                 (float*)(d + ou), (float*)(d + ov), (float*)(d + oc), (float*)(d + oy), bias_mask,
-                FGC_ACT_NONE, 0.f, d + ows, wsmax, st);
+                FGC_ACT_NONE, 0.f, d + owf, wsf, st, fplan);
   if (rc) return rc;
   FGC_CUDA(cudaEventRecord(e_y, st));
   FGC_CUDA(cudaStreamWaitEvent(so, e_y, 0));
@@ -457,7 +495,8 @@ int fgc_conv_fwd_bwd_host(const fgc_conv_shape* s, const float* x, const int32_t
   rc = conv_bwd(s, (float*)(d + ogy), (float*)(d + ox), (int32_t*)(d + oadj), (int32_t*)(d + orp),
                 (int32_t*)(d + ore), (float*)(d + oW), (float*)(d + ou), (float*)(d + ov),
                 (float*)(d + oc), (float*)(d + ogx), (float*)(d + ogW), (float*)(d + ogb),
-                (float*)(d + ogu), (float*)(d + ogv), (float*)(d + ogc), bias_mask, d + ows, wsmax, st);
+                (float*)(d + ogu), (float*)(d + ogv), (float*)(d + ogc), bias_mask, d + owb, wsb, st, radj, Kr,
+                rplan, fplan, fplan != nullptr ? d + owf : nullptr, wsf);
   g_gx_ready_event = nullptr;
   if (rc) return rc;
   FGC_CUDA(cudaStreamWaitEvent(so, e_gx, 0));

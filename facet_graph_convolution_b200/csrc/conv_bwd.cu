@@ -635,9 +635,28 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __
   }
 }
 
+// few outputs, many partials: one warp per output, lane l sums partials l, l+32, ... and the lanes are
+// combined by a butterfly (fixed order: deterministic)
+__global__ void reduce_partials_warp_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                            int64_t n, int P, int64_t stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (e >= n) return;
+  float a = 0.f;
+  for (int q = lane; q < P; q += 32) a += part[q * stride + e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[e] = a;
+}
+
 int launch_reduce_partials(const float* part, float* out, int64_t n, int P, int64_t stride,
                            cudaStream_t st) {
   if (n <= 0) return FGC_OK;
+  if (n <= 4096 && P >= 64) {
+    reduce_partials_warp_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, st>>>(part, out, n, P, stride);
+    FGC_LAUNCHED("reduce_partials_kernel");
+    return FGC_OK;
+  }
   int64_t blocks = (n + 255) / 256;
   if (blocks > 4096) blocks = 4096;
   reduce_partials_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(part, out, n, P, stride);

@@ -61,6 +61,7 @@ const float* conv_plan_inv(const void* plan, int64_t rows, int K, int M);
 int launch_bwd_src_mma(const float* gy, const float* uvx, const int32_t* adj, const void* plan, void* ximg_ws,
                        void* gyimg_ws, const void* wimg, float* da_edge, float* d_uvx, int64_t rows, int N, int K,
                        int M, cudaStream_t st);
+int launch_max_degree(const int32_t* rev_ptr, int64_t rows, int32_t* out, cudaStream_t st);
 int launch_build_radj(const int32_t* rev_ptr, const int32_t* rev_edge, int B, int N, int K, int Kr, int32_t* radj,
                       cudaStream_t st);
 bool bwd_tgt_mma_supported(int Cin, int Cw, int Cout, int M, int Kr);

@@ -1022,6 +1022,24 @@ tgt_dv_kernel(const int32_t* __restrict__ rev_ptr, const int32_t* __restrict__ r
   *reinterpret_cast<float4*>(d_uvx + t * (2 * M) + M + 4 * part) = a;
 }
 
+__global__ void max_degree_kernel(const int32_t* __restrict__ rev_ptr, int64_t rows, int32_t* __restrict__ out) {
+  int m = 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    m = max(m, __ldg(rev_ptr + i + 1) - __ldg(rev_ptr + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// largest in-degree of the reversed adjacency -> *out (device)
+int launch_max_degree(const int32_t* rev_ptr, int64_t rows, int32_t* out, cudaStream_t st) {
+  FGC_CUDA(cudaMemsetAsync(out, 0, sizeof(int32_t), st));
+  max_degree_kernel<<<num_sms() * 4, 256, 0, st>>>(rev_ptr, rows, out);
+  FGC_LAUNCHED("max_degree_kernel");
+  return FGC_OK;
+}
+
 int launch_build_radj(const int32_t* rev_ptr, const int32_t* rev_edge, int B, int N, int K, int Kr, int32_t* radj,
                       cudaStream_t st) {
   const int64_t rows = static_cast<int64_t>(B) * N;

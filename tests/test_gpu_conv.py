@@ -206,3 +206,51 @@ def test_c2_shape_properties_at_scale():
     cnt = (adjs[0, rows] != 0).sum(-1)
     yref = np.einsum("moc,nmc->no", W1.cpu().numpy().astype(np.float64), s) / cnt[:, None] + b.cpu().numpy()
     assert np.abs(y1[0, rows].cpu().numpy() - yref).max() < TOL_Y
+
+
+def _host_fwd_bwd(x, adj, gy, W0, b, u, v, c, bias_mask=True):
+    """One call of the host-buffer C-ABI entry point (what bench.py's e2e arm times)."""
+    import ctypes as C
+    from facet_graph_convolution_b200 import _lib
+    L = _lib.lib()
+    B, N, Cin = x.shape
+    M, Cout, Cw = W0.shape
+    s = _lib.ConvShape(B, N, adj.shape[2], Cin, Cw, 0, u.shape[1], Cout, M)
+    ins = [np.ascontiguousarray(a) for a in (x, adj.astype(np.int32), gy, W0, b, u, v, c)]
+    outs = [np.empty((B, N, Cout), np.float32), np.empty_like(ins[0]), np.empty_like(ins[3]), np.empty_like(ins[4]),
+            np.empty_like(ins[5]), np.empty_like(ins[6]), np.empty_like(ins[7])]
+    P = lambda a: C.c_void_p(a.ctypes.data)
+    _lib.check(L.fgc_conv_fwd_bwd_host(C.byref(s), *[P(a) for a in ins], *[P(a) for a in outs], int(bias_mask), 0),
+               "fgc_conv_fwd_bwd_host")
+    L.fgc_host_release()
+    return outs
+
+
+def test_host_entry_point_matches_oracle():
+    """fgc_conv_fwd_bwd_host (host buffers in, host buffers out) on: a dense 64->64 M=8 layer over a mesh
+    adjacency (planned tensor-core path, caches built inside the call), the same layer over a random
+    adjacency (plan dropped: too many distinct rows per tile), and an M=9 layer (FFMA path)."""
+    from facet_graph_convolution_b200 import mesh
+    rs = np.random.RandomState(5)
+    _, F = mesh.grid_mesh(20, 10, torus=True, morton=True)
+    a_mesh = mesh.faces_large_adj(F, 16)[None]
+    N = 300
+    a_rand = rs.randint(0, N + 1, size=(1, N, 16)).astype(np.int32)
+    a_rand[:, :, 0] = np.arange(1, N + 1)
+    a_rand[0, 11] = 0
+    for name, adj, Cin, Cout, M in (("mesh", a_mesh, 64, 64, 8), ("random", a_rand, 64, 64, 8),
+                                    ("m9", a_rand, 32, 64, 9)):
+        Nn = adj.shape[1]
+        x = rs.randn(1, Nn, Cin).astype(np.float32)
+        gy = rs.randn(1, Nn, Cout).astype(np.float32)
+        W0 = (rs.randn(M, Cout, Cin) * 0.05).astype(np.float32)
+        b = (rs.randn(Cout) * 0.01).astype(np.float32)
+        u = (rs.randn(M, Cin) * 0.05).astype(np.float32)
+        v = (rs.randn(M, Cin) * 0.05).astype(np.float32)
+        c = (rs.randn(M) * 0.05).astype(np.float32)
+        y, gx, gW0, gb, gu, gv, gc = _host_fwd_bwd(x, adj, gy, W0, b, u, v, c)
+        assert np.abs(y - cf.conv_fwd(x, adj, W0, b, u, v, c)).max() < TOL_Y, name
+        ref = cf.conv_bwd(gy, x, adj, W0, b, u, v, c)
+        for k, got in (("gx", gx), ("gW0", gW0), ("gb", gb), ("gu", gu), ("gv", gv), ("gc", gc)):
+            sc = max(1.0, float(np.abs(ref[k]).max()))
+            assert np.abs(got - ref[k]).max() / sc < TOL_G, (name, k)
