@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Network-level measurements of SURVEY.md section 8(d): C1, C3 and C4 (bench.py is C2, the headline).
+
+    python benchmarks/net_bench.py --config c1          # single-mesh denoising: icosphere-5, 20 480 faces
+    python benchmarks/net_bench.py --config c3          # 2M-facet mesh, ~100 patches with halo, sharded by patch
+    python benchmarks/net_bench.py --config c4          # training step on 8 192-node patches (data parallel)
+    python -m torch.distributed.run --nproc-per-node N ... benchmarks/net_bench.py --config c3|c4
+
+Every config prints ONE JSON line (rank 0).  facets/s counts real input faces (C3: core faces, each
+written back once); GPU time is CUDA-event time of the network forward (+ vertex update for C1) with
+the patch tensors resident in HBM; `e2e` adds the pinned-host upload of the patch tensors and the
+read-back of the normals per patch.  The CPU number beside it is the oracle's fp32 NumPy closed form
+(`oracle/closed_form.py`, kind "port": TensorFlow is not installable and the reference sources cannot
+travel to the GPU box) on a bounded sample, with the core count printed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def net_params(rs, multi_scale=False):
+    """Random-init parameters in the reference's creation order (model.py:31-44 stddevs)."""
+    M, cin = 9, 6
+    shapes = []
+    for ci, co in ((cin, 32), (32, 64), (64, 128), (128, 128), (128, 64), (128, 64), (64, 32), (64, 32)):
+        shapes += [((M, co, ci), 0.05), ((co,), 0.01), ((M, ci), 0.05), ((M,), 0.05), ((M, ci), 0.05)]
+    shapes += [((32, 1024), 0.05), ((1024,), 0.01), ((1024, 3), 0.05), ((3,), 0.01)]
+    return [rs.normal(0, sd, sh).astype(np.float32) for sh, sd in shapes]
+
+
+def icosphere_patch(level=5, K=16, seed=0):
+    from facet_graph_convolution_b200 import mesh
+    V, F = mesh.icosphere(level)
+    Vn = mesh.add_vertex_noise(V, F, 0.3, seed)
+    feat = mesh.face_features(Vn, F).astype(np.float32)
+    adj = mesh.dedup_adj(mesh.faces_large_adj(F, K))
+    featp, adjp = mesh.pad_to_multiple(feat, adj, 16)
+    adjs = mesh.build_pyramid(adjp, 3, K)
+    e_map, v_e = mesh.edge_maps(F, 20)
+    return Vn.astype(np.float32), F, featp, adjs, e_map, v_e
+
+
+def clocks_sampler(index):
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(index)
+    s.start()
+    return s
+
+
+def cpu_net_forward(x, adjs, params, repeat=1):
+    """Oracle closed form in fp32 NumPy (all BLAS threads)."""
+    from oracle import closed_form as cf
+    pd = cf.split_net_params(params)
+    t0 = time.perf_counter()
+    for _ in range(repeat):
+        cf.net_forward(x[None].astype(np.float32), [a[None] for a in adjs], pd, dtype=np.float32)
+    return (time.perf_counter() - t0) / repeat
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c1", choices=["c1", "c3", "c4"])
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--grid", type=int, default=1000, help="c3: quads per side (1000 -> 2M facets)")
+    ap.add_argument("--block", type=int, default=100)
+    ap.add_argument("--batch", type=int, default=4, help="c4: patches per rank per step")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="per-kernel CUDA-event times of one forward (library profiler)")
+    args = ap.parse_args()
+
+    import torch
+    from facet_graph_convolution_b200 import _lib, ops, patches, mesh
+    from facet_graph_convolution_b200 import model as fm
+    _lib.require_device()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    L = _lib.lib()
+    rs = np.random.RandomState(1234)
+    params = net_params(rs)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cores = os.cpu_count() or 1
+    line = {"metric": "facets/sec", "unit": "facets/s", "n_gpus": world, "higher_is_better": True, "dtype": "f32",
+            "data": "synthetic", "vs_baseline": None}
+
+    if args.config == "c1":
+        Vn, F, feat, adjs, e_map, v_e = icosphere_patch(5)
+        nreal = F.shape[0]
+        x_d, adjs_d = T(feat[None]), [T(a[None]) for a in adjs]
+        v_d, em_d, ve_d = T(Vn[None]), T(e_map[None]), T(v_e[None])
+        store = fm.VariableStore(dev, params=params)
+
+        def step():
+            with torch.no_grad(), fm.variable_store(store):
+                y = fm.get_model_reg_multi_scale(x_d, adjs_d, 1.0)
+                n = fm.normalizeTensor(y)
+                xo = fm.update_position2(v_d, n[:, :nreal].contiguous(), em_d, ve_d, iter_num=60, max_edges=20)
+            return n, xo
+
+        def fwd_only():
+            with torch.no_grad(), fm.variable_store(store):
+                return fm.normalizeTensor(fm.get_model_reg_multi_scale(x_d, adjs_d, 1.0))
+
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        if args.profile:
+            import ctypes as C
+            L.fgc_profile_begin(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            fwd_only()
+            buf = C.create_string_buffer(1 << 16)
+            L.fgc_profile_end(buf, len(buf))
+            line["kernels_ms"] = {ln.split()[0]: [round(float(ln.split()[1]), 4), int(ln.split()[2])]
+                                  for ln in buf.value.decode().strip().splitlines()}
+        smp = clocks_sampler(local_rank)
+        n0 = L.fgc_launch_count()
+        ts, tf = [], []
+        for _ in range(args.steps):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            fwd_only()
+            e1.record()
+            step()
+            e2.record()
+            torch.cuda.synchronize()
+            tf.append(e0.elapsed_time(e1))
+            ts.append(e1.elapsed_time(e2))
+        launches = (L.fgc_launch_count() - n0) / args.steps
+        clocks = smp.result()
+        ms_net, ms_all = float(np.median(tf)), float(np.median(ts))
+        cpu = None
+        if not args.no_cpu:
+            dt = cpu_net_forward(feat, adjs, params)
+            cpu = {"value": nreal / dt, "unit": "facets/s", "cores": cores, "kind": "port",
+                   "sample": "oracle/closed_form.py net_forward (fp32 NumPy), 1 pass over the same patch, %.2f s" % dt}
+        line.update({"value": nreal / (ms_all * 1e-3), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all,
+                     "scaling": "weak", "clocks": clocks, "gpu_launches": launches,
+                     "config": {"workload": "C1 single-mesh denoising: noisy icosphere-5 (20480 faces, N0=%d nodes), K=16, M=9, "
+                                            "network forward + normalizeTensor + update_position2 (60 sweeps)" % feat.shape[0]},
+                     "network_forward_ms": ms_net, "network_forward_facets_per_s": nreal / (ms_net * 1e-3),
+                     "cpu_baseline": cpu})
+
+    elif args.config == "c3":
+        nx = ny = args.grid
+        bx = (nx + args.block - 1) // args.block
+        npatch = bx * bx
+        costs = [1] * npatch   # equal-sized blocks: the partition only needs relative costs
+        plan = patches.partition(costs, world)
+        t0 = time.perf_counter()
+        mine, num_faces = patches.grid_patches(nx, ny, block=args.block, halo=3, K=16, only=plan[rank])
+        t_gen = time.perf_counter() - t0
+        store = fm.VariableStore(dev, params=params)
+        host = [(torch.from_numpy(p.x[None]).pin_memory(), [torch.from_numpy(a[None]).pin_memory() for a in p.adjs])
+                for p in mine]
+        resident = [(x.to(dev), [a.to(dev) for a in adjs]) for x, adjs in host]
+        core = sum(int(p.core.sum()) for p in mine)
+
+        def fwd(x, adjs):
+            with torch.no_grad(), fm.variable_store(store):
+                return fm.normalizeTensor(fm.get_model_reg_multi_scale(x, adjs, 1.0))
+
+        for x, adjs in resident[: max(2, args.warmup)]:
+            fwd(x, adjs)
+        barrier()
+        smp = clocks_sampler(local_rank)
+        n0 = L.fgc_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for x, adjs in resident:
+            fwd(x, adjs)
+        e1.record()
+        barrier()
+        launches = L.fgc_launch_count() - n0
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        clocks = smp.result()
+        # end to end: pinned-host patch tensors in, normals out, per patch
+        outs = [torch.empty(1, x.shape[1], 3).pin_memory() for x, _ in host]
+        barrier()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for (x, adjs), o in zip(host, outs):
+            xd, ad = x.to(dev, non_blocking=True), [a.to(dev, non_blocking=True) for a in adjs]
+            o.copy_(fwd(xd, ad), non_blocking=True)
+            h2d += x.numel() * 4 + sum(a.numel() * 4 for a in adjs)
+            d2h += o.numel() * 4
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        total_core = core
+        if world > 1:
+            t = torch.tensor([core], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            total_core = int(t.item())
+        cpu = None
+        if rank == 0 and not args.no_cpu:
+            p = mine[0]
+            dtc = cpu_net_forward(p.x, p.adjs, params)
+            cpu = {"value": int(p.core.sum()) / dtc, "unit": "facets/s", "cores": cores, "kind": "port",
+                   "sample": "oracle/closed_form.py net_forward (fp32 NumPy) on 1 of %d patches (%d nodes), %.2f s; "
+                             "per-patch time x patch count" % (npatch, p.x.shape[0], dtc)}
+        line.update({"value": total_core / (ms * 1e-3), "steps": 1, "warmup": max(2, args.warmup), "ms_per_step": ms,
+                     "scaling": "strong", "clocks": clocks, "gpu_launches": int(launches),
+                     "config": {"workload": "C3 multi-scale denoising net inference: %dx%d-quad height field = %d facets, %d patches "
+                                            "of %dx%d quads + 3-quad halo, K=16, M=9, patches dealt to %d GPU(s), no collective"
+                                            % (nx, ny, num_faces, npatch, args.block, args.block, world),
+                                "patches_this_rank": len(mine), "host_patch_generation_s": t_gen},
+                     "e2e": {"value": total_core / dt, "unit": "facets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                             "ms_per_step": dt * 1e3},
+                     "cpu_baseline": cpu})
+
+    else:  # c4
+        from facet_graph_convolution_b200 import train as ftrain
+        nq = 64   # 64x64 quads = 8192 triangles per patch
+        batch = []
+        for bi in range(args.batch):
+            P, _ = patches.grid_patches(nq, nq, block=nq, halo=0, K=16, seed=rank * 100 + bi)
+            p = P[0]
+            Vc, Fc = mesh.grid_mesh(nq, nq, torus=False, morton=True)
+            gt = np.zeros((p.x.shape[0], 3), np.float32)
+            gt[: p.num_real] = p.x[: p.num_real, :3]   # clean-ish target: the patch's own normals (synthetic)
+            batch.append((T(p.x[None]), [T(a[None]) for a in p.adjs], T(gt[None])))
+        net = fm.DenoisingNet(6, device=dev, params=params)
+        net(batch[0][0], batch[0][1])
+        plist = list(net.parameters())
+        bucket = ftrain.GradBucket(plist)
+        opt = ftrain.Adam(bucket)
+        rng = np.random.RandomState(rank)
+        group = dist.group.WORLD if world > 1 else None
+        for _ in range(args.warmup):
+            ftrain.train_step(net, batch, bucket, opt, rng, group)
+        barrier()
+        smp = clocks_sampler(local_rank)
+        n0 = L.fgc_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            ftrain.train_step(net, batch, bucket, opt, rng, group)
+        e1.record()
+        barrier()
+        launches = (L.fgc_launch_count() - n0) / args.steps
+        ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        clocks = smp.result()
+        facets = args.batch * 8192 * world
+        line.update({"value": facets / (ms * 1e-3), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                     "scaling": "weak", "clocks": clocks, "gpu_launches": launches,
+                     "config": {"workload": "C4 training step: %d patches/GPU x 8192 level-0 nodes, Cin=6, K=16, M=9, random "
+                                            "rotation, 4000 sampled facets, faceNormalsLoss, fwd+bwd, one all-reduce of the flat "
+                                            "gradient bucket (%d floats), Adam" % (args.batch, bucket.flat.numel()),
+                                "parallelism": "dp%d" % world}})
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

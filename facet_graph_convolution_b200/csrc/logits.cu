@@ -57,7 +57,7 @@ __device__ __forceinline__ void load_coeffs(const LgParams& p, int gl, float (&w
 }
 
 template <int OP, int LPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (OP <= 16) ? 2 : 1)
 assign_logits_warp_kernel(const LgParams p) {
   constexpr int RPW = 32 / LPR, OPL = OP / LPR;
   const int lane = threadIdx.x & 31, gl = lane % LPR, sub = lane / LPR;
@@ -73,16 +73,20 @@ assign_logits_warp_kernel(const LgParams p) {
   const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const bool act = 4 * gl < p.Ca;
-  for (int64_t r0 = wid * RPW; r0 < p.rows; r0 += 2 * nw * RPW) {
-    // two row groups per iteration: both loads are in flight before the first is consumed
-    const int64_t ra = r0 + sub, rb = r0 + nw * RPW + sub;
-    float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
-    if (ra < p.rows && act) xa = __ldg(reinterpret_cast<const float4*>(p.x + ra * p.Cin + p.Ca0) + gl);
-    if (rb < p.rows && act) xb = __ldg(reinterpret_cast<const float4*>(p.x + rb * p.Cin + p.Ca0) + gl);
+  constexpr int U = 4;   // row groups per iteration: all loads are in flight before the first is consumed
+  for (int64_t r0 = wid * RPW; r0 < p.rows; r0 += U * nw * RPW) {
+    int64_t rr[U];
+    float4 xs[U];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const float4 xv = half ? xb : xa;
-      const int64_t r = half ? rb : ra;
+    for (int t = 0; t < U; ++t) {
+      rr[t] = r0 + t * nw * RPW + sub;
+      xs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rr[t] < p.rows && act) xs[t] = __ldg(reinterpret_cast<const float4*>(p.x + rr[t] * p.Cin + p.Ca0) + gl);
+    }
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const float4 xv = xs[t];
+      const int64_t r = rr[t];
       float a[OP];
 #pragma unroll
       for (int o = 0; o < OP; ++o) a[o] = fmaf(xv.x, w[o][0], fmaf(xv.y, w[o][1], fmaf(xv.z, w[o][2], xv.w * w[o][3])));
@@ -99,7 +103,7 @@ assign_logits_warp_kernel(const LgParams p) {
 }
 
 template <int OP, int LPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (OP <= 16) ? 2 : 1)
 logits_bwd_x_warp_kernel(const LgParams p) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, gl = lane % LPR, sub = lane / LPR;
@@ -109,35 +113,50 @@ logits_bwd_x_warp_kernel(const LgParams p) {
   const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const bool act = 4 * gl < p.Ca;
-  for (int64_t r0 = wid * RPW; r0 < p.rows; r0 += nw * RPW) {
-    const int64_t r = r0 + sub;
-    if (r >= p.rows || !act) continue;
-    float d[OP];
-    if ((O & 3) == 0) {
+  constexpr int U = 2;   // row groups per iteration (loads of both are issued before either is used)
+  for (int64_t r0 = wid * RPW; r0 < p.rows; r0 += U * nw * RPW) {
+    float d[U][OP];
+    float4 g[U];
+    bool ok[U];
 #pragma unroll
-      for (int o = 0; o < OP; o += 4) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < O) t = __ldg(reinterpret_cast<const float4*>(p.uvx + r * O + o));
-        d[o] = t.x, d[o + 1] = t.y, d[o + 2] = t.z, d[o + 3] = t.w;
+    for (int t = 0; t < U; ++t) {
+      const int64_t r = r0 + t * nw * RPW + sub;
+      ok[t] = r < p.rows && act;
+      g[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < OP; ++o) d[t][o] = 0.f;
+      if (!ok[t]) continue;
+      if ((O & 3) == 0) {
+#pragma unroll
+        for (int o = 0; o < OP; o += 4) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (o < O) q = __ldg(reinterpret_cast<const float4*>(p.uvx + r * O + o));
+          d[t][o] = q.x, d[t][o + 1] = q.y, d[t][o + 2] = q.z, d[t][o + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < OP; ++o) d[t][o] = (o < O) ? __ldg(p.uvx + r * O + o) : 0.f;
       }
-    } else {
-#pragma unroll
-      for (int o = 0; o < OP; ++o) d[o] = (o < O) ? __ldg(p.uvx + r * O + o) : 0.f;
+      g[t] = *(reinterpret_cast<const float4*>(p.gx + r * p.Cin + p.Ca0) + gl);
     }
-    float4* gp = reinterpret_cast<float4*>(p.gx + r * p.Cin + p.Ca0) + gl;
-    float4 g = *gp;
 #pragma unroll
-    for (int o = 0; o < OP; ++o) {
-      g.x = fmaf(d[o], w[o][0], g.x), g.y = fmaf(d[o], w[o][1], g.y);
-      g.z = fmaf(d[o], w[o][2], g.z), g.w = fmaf(d[o], w[o][3], g.w);
+    for (int t = 0; t < U; ++t) {
+      if (!ok[t]) continue;
+      const int64_t r = r0 + t * nw * RPW + sub;
+      float4 gg = g[t];
+#pragma unroll
+      for (int o = 0; o < OP; ++o) {
+        gg.x = fmaf(d[t][o], w[o][0], gg.x), gg.y = fmaf(d[t][o], w[o][1], gg.y);
+        gg.z = fmaf(d[t][o], w[o][2], gg.z), gg.w = fmaf(d[t][o], w[o][3], gg.w);
+      }
+      *(reinterpret_cast<float4*>(p.gx + r * p.Cin + p.Ca0) + gl) = gg;
     }
-    *gp = g;
   }
 }
 
 // one CTA per chunk of rows; warps stride the chunk's rows, fixed-order reduction over the warps
 template <int OP, int LPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (OP <= 16) ? 2 : 1)
 logits_bwd_p_warp_kernel(const LgParams p) {
   constexpr int RPW = 32 / LPR;
   extern __shared__ float red[];   // [warps * RPW][OP * LPR * 4 + OP]
@@ -154,28 +173,39 @@ logits_bwd_p_warp_kernel(const LgParams p) {
   const int64_t rb = static_cast<int64_t>(blockIdx.x) * p.rows_per_chunk;
   const int64_t re = min(p.rows, rb + p.rows_per_chunk);
   const bool act = 4 * gl < p.Ca;
-  for (int64_t r0 = rb + warp * RPW; r0 < re; r0 += nwarp * RPW) {
-    const int64_t r = r0 + sub;
-    if (r >= re) continue;
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act) xv = __ldg(reinterpret_cast<const float4*>(p.x + r * p.Cin + p.Ca0) + gl);
-    float d[OP];
-    if ((O & 3) == 0) {
+  constexpr int U = 2;   // rows per iteration per lane group (loads of both issued first; fixed order of use)
+  for (int64_t r0 = rb + warp * RPW; r0 < re; r0 += U * nwarp * RPW) {
+    float4 xs[U];
+    float d[U][OP];
 #pragma unroll
-      for (int o = 0; o < OP; o += 4) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < O) t = __ldg(reinterpret_cast<const float4*>(p.uvx + r * O + o));
-        d[o] = t.x, d[o + 1] = t.y, d[o + 2] = t.z, d[o + 3] = t.w;
+    for (int t = 0; t < U; ++t) {
+      const int64_t r = r0 + t * nwarp * RPW + sub;
+      xs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < OP; ++o) d[t][o] = 0.f;
+      if (r >= re) continue;
+      if (act) xs[t] = __ldg(reinterpret_cast<const float4*>(p.x + r * p.Cin + p.Ca0) + gl);
+      if ((O & 3) == 0) {
+#pragma unroll
+        for (int o = 0; o < OP; o += 4) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (o < O) q = __ldg(reinterpret_cast<const float4*>(p.uvx + r * O + o));
+          d[t][o] = q.x, d[t][o + 1] = q.y, d[t][o + 2] = q.z, d[t][o + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < OP; ++o) d[t][o] = (o < O) ? __ldg(p.uvx + r * O + o) : 0.f;
       }
-    } else {
-#pragma unroll
-      for (int o = 0; o < OP; ++o) d[o] = (o < O) ? __ldg(p.uvx + r * O + o) : 0.f;
     }
 #pragma unroll
-    for (int o = 0; o < OP; ++o) {
-      acc[o][0] = fmaf(d[o], xv.x, acc[o][0]), acc[o][1] = fmaf(d[o], xv.y, acc[o][1]);
-      acc[o][2] = fmaf(d[o], xv.z, acc[o][2]), acc[o][3] = fmaf(d[o], xv.w, acc[o][3]);
-      if (gl == 0) gc[o] += d[o];
+    for (int t = 0; t < U; ++t) {
+      const float4 xv = xs[t];
+#pragma unroll
+      for (int o = 0; o < OP; ++o) {
+        acc[o][0] = fmaf(d[t][o], xv.x, acc[o][0]), acc[o][1] = fmaf(d[t][o], xv.y, acc[o][1]);
+        acc[o][2] = fmaf(d[t][o], xv.z, acc[o][2]), acc[o][3] = fmaf(d[t][o], xv.w, acc[o][3]);
+        if (gl == 0) gc[o] += d[t][o];
+      }
     }
   }
   // slot s = warp * RPW + sub holds this lane group's partials: [o][c] then gc[o]

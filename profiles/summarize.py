@@ -16,12 +16,25 @@ import os
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+TIME_MS = {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 SHORT = ["conv_fwd_tc_kernel", "bwd_src_tc_kernel", "bwd_tgt_tc_kernel", "bwd_w_tc_kernel", "conv_fwd_kernel",
          "bwd_src_kernel", "bwd_tgt_kernel", "bwd_w_kernel", "fconv_fwd_kernel", "fconv_tgt_kernel"]
 
 
+MMA_ORDER = ["conv_mma_kernel", "bwd_tgt_mma_kernel", "bwd_w_mma_kernel"]   # launch order inside one fwd+bwd step
+_mma_seen = [0]
+
+
 def short_name(full):
+    if "conv_mma_kernel" in full:
+        # one kernel template serves the forward, the target-centric pass and the weight gradient
+        # (MmaParams::mode); the launches of a step come in this fixed order
+        nm = MMA_ORDER[_mma_seen[0] % 3]
+        _mma_seen[0] += 1
+        return nm
+    if "bwd_src_mma_kernel" in full:
+        return "bwd_src_mma_kernel"
     if "conv_fwd_tc_kernel" in full and full.rstrip().split(",")[-1].strip().startswith("1"):
         return "bwd_tgt_tc_kernel"      # conv_fwd_tc_kernel<M, COUT, MODE_TGT>
     if "conv_fwd_tc_kernel" in full and "(int)1>" in full:
@@ -58,7 +71,7 @@ def main():
         if name == "conv_fwd_tc_kernel" and name in kernels:
             name = "bwd_tgt_tc_kernel"
         kernels[name] = {
-            "ncu_ms": val(r, "gpu__time_duration.sum"),
+            "ncu_ms": (val(r, "gpu__time_duration.sum") or 0.0) * TIME_MS.get(units[idx["gpu__time_duration.sum"]], 1.0),
             "dram_bytes_per_launch": (val(r, "dram__bytes_read.sum", True) or 0) + (val(r, "dram__bytes_write.sum", True) or 0),
             "dram_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
             "tensor_pipe_pct": val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
@@ -72,6 +85,7 @@ def main():
             "stall_long_scoreboard": val(r, "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
         }
     shares = collections.OrderedDict()
+    _mma_seen[0] = 0
     lpath = os.path.join(HERE, tag + "_launches.csv")
     if os.path.exists(lpath):
         lr = list(csv.reader(open(lpath)))
