@@ -76,6 +76,7 @@ def main():
     ap.add_argument("--grid", type=int, default=1000, help="c3: quads per side (1000 -> 2M facets)")
     ap.add_argument("--block", type=int, default=100)
     ap.add_argument("--batch", type=int, default=4, help="c4: patches per rank per step")
+    ap.add_argument("--patch-batch", type=int, default=10, help="c3: patches per launch (1 = the reference's B=1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile", action="store_true", help="per-kernel CUDA-event times of one forward (library profiler)")
     args = ap.parse_args()
@@ -180,39 +181,54 @@ def main():
         mine, num_faces = patches.grid_patches(nx, ny, block=args.block, halo=3, K=16, only=plan[rank])
         t_gen = time.perf_counter() - t0
         store = fm.VariableStore(dev, params=params)
-        host = [(torch.from_numpy(p.x[None]).pin_memory(), [torch.from_numpy(a[None]).pin_memory() for a in p.adjs])
-                for p in mine]
-        resident = [(x.to(dev), [a.to(dev) for a in adjs]) for x, adjs in host]
+        # patches are stacked `--patch-batch` at a time (padded with fake nodes to a common size): the
+        # layers treat batch elements independently, so the real rows are those of the B=1 run
+        PB = max(1, args.patch_batch)
+        groups = [list(range(i, min(i + PB, len(mine)))) for i in range(0, len(mine), PB)]
+        host = []
+        for g in groups:
+            xb, ab = patches.batch_patches(mine, g)
+            host.append((torch.from_numpy(xb).pin_memory(), [torch.from_numpy(a).pin_memory() for a in ab],
+                         [mine[i].x.shape[0] for i in g]))
+        resident = [(x.to(dev), [a.to(dev) for a in adjs], ns) for x, adjs, ns in host]
         core = sum(int(p.core.sum()) for p in mine)
 
-        def fwd(x, adjs):
+        def fwd(x, adjs, ns):
             with torch.no_grad(), fm.variable_store(store):
-                return fm.normalizeTensor(fm.get_model_reg_multi_scale(x, adjs, 1.0))
+                y = fm.get_model_reg_multi_scale(x, adjs, 1.0)
+                # normalizeTensor's mean is global per patch (utils.py:1700-1715): one call per element
+                return [fm.normalizeTensor(y[b:b + 1, :n]) for b, n in enumerate(ns)]
 
-        for x, adjs in resident[: max(2, args.warmup)]:
-            fwd(x, adjs)
+        if PB > 1 and rank == 0:   # the batched run reproduces the B=1 rows bit for bit
+            p0 = mine[0]
+            one = fwd(torch.from_numpy(p0.x[None]).to(dev), [torch.from_numpy(a[None]).to(dev) for a in p0.adjs],
+                      [p0.x.shape[0]])[0]
+            assert torch.equal(one, fwd(*resident[0])[0]), "batched forward differs from the B=1 forward"
+        for x, adjs, ns in resident[: max(2, args.warmup)]:
+            fwd(x, adjs, ns)
         barrier()
         smp = clocks_sampler(local_rank)
         n0 = L.fgc_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for x, adjs in resident:
-            fwd(x, adjs)
+        for x, adjs, ns in resident:
+            fwd(x, adjs, ns)
         e1.record()
         barrier()
         launches = L.fgc_launch_count() - n0
         ms = max_over_ranks(e0.elapsed_time(e1))
         clocks = smp.result()
-        # end to end: pinned-host patch tensors in, normals out, per patch
-        outs = [torch.empty(1, x.shape[1], 3).pin_memory() for x, _ in host]
+        # end to end: pinned-host patch tensors in, normals out, per batch of patches
+        outs = [[torch.empty(1, n, 3).pin_memory() for n in ns] for _, _, ns in host]
         barrier()
         t0 = time.perf_counter()
         h2d = d2h = 0
-        for (x, adjs), o in zip(host, outs):
+        for (x, adjs, ns), os_ in zip(host, outs):
             xd, ad = x.to(dev, non_blocking=True), [a.to(dev, non_blocking=True) for a in adjs]
-            o.copy_(fwd(xd, ad), non_blocking=True)
+            for o, yn in zip(os_, fwd(xd, ad, ns)):
+                o.copy_(yn, non_blocking=True)
+                d2h += o.numel() * 4
             h2d += x.numel() * 4 + sum(a.numel() * 4 for a in adjs)
-            d2h += o.numel() * 4
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         total_core = core
@@ -230,8 +246,9 @@ def main():
         line.update({"value": total_core / (ms * 1e-3), "steps": 1, "warmup": max(2, args.warmup), "ms_per_step": ms,
                      "scaling": "strong", "clocks": clocks, "gpu_launches": int(launches),
                      "config": {"workload": "C3 multi-scale denoising net inference: %dx%d-quad height field = %d facets, %d patches "
-                                            "of %dx%d quads + 3-quad halo, K=16, M=9, patches dealt to %d GPU(s), no collective"
-                                            % (nx, ny, num_faces, npatch, args.block, args.block, world),
+                                            "of %dx%d quads + 3-quad halo, K=16, M=9, patches dealt to %d GPU(s), no collective, "
+                                            "%d patches per launch"
+                                            % (nx, ny, num_faces, npatch, args.block, args.block, world, PB),
                                 "patches_this_rank": len(mine), "host_patch_generation_s": t_gen},
                      "e2e": {"value": total_core / dt, "unit": "facets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                              "ms_per_step": dt * 1e3},

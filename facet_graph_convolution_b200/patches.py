@@ -132,6 +132,41 @@ def infer_sharded(patches: Sequence[Patch], num_faces: int, forward: Callable[[P
     return merge(num_faces, gather_to_all(ids, rows, device))
 
 
+# ----------------------------------------------------------------------------- batching
+def pad_patch(p: Patch, n0: int):
+    """(x[n0,Cin], [adj_l[n0 >> 2l, K]]) of patch `p` grown to n0 level-0 nodes with fake nodes: zero
+    features and a self-only adjacency row at every level -- the state the reference's coarsening
+    leaves fake nodes in.  Fake rows never appear in a real row's adjacency,
+    so the real rows of every layer are bit-identical to the unpadded run."""
+    N = p.x.shape[0]
+    assert n0 >= N and n0 % 16 == 0
+    x = np.zeros((n0,) + p.x.shape[1:], p.x.dtype)
+    x[:N] = p.x
+    adjs = []
+    for lvl, a in enumerate(p.adjs):
+        nl, tl = a.shape[0], n0 >> (2 * lvl)
+        out = np.zeros((tl, a.shape[1]), a.dtype)
+        out[:nl] = a
+        out[nl:, 0] = np.arange(nl + 1, tl + 1)
+        adjs.append(out)
+    return x, adjs
+
+
+def batch_patches(patches: Sequence[Patch], idx: Sequence[int]):
+    """Stacks the patches `idx` into one batch (x[B,n0,Cin], [adj_l[B,n_l,K]]): the layers treat batch
+    elements independently (adjacency ids are per element), so one launch serves B patches.  The
+    per-patch normalizeTensor (a global mean per patch) is applied to the rows [:N_b] of element b
+    by the caller."""
+    n0 = max(patches[i].x.shape[0] for i in idx)
+    n0 = (n0 + 15) // 16 * 16
+    xs, adjs = [], None
+    for i in idx:
+        x, a = pad_patch(patches[i], n0)
+        xs.append(x)
+        adjs = [[t] for t in a] if adjs is None else [u + [t] for u, t in zip(adjs, a)]
+    return np.stack(xs), [np.stack(u) for u in adjs]
+
+
 # ----------------------------------------------------------------------------- synthetic patches (C3 / C5)
 def grid_patches(nx: int, ny: int, block: int = 100, halo: int = 3, K: int = 16, height=None, noise: float = 0.3,
                  seed: int = 0, only: Optional[Sequence[int]] = None):

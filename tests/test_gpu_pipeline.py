@@ -53,6 +53,27 @@ def test_patch_sharded_inference_matches_oracle():
     assert np.abs(P.merge(nf, parts) - got).max() < 1e-12
 
 
+def test_batched_patches_reproduce_single_patch_rows_bit_for_bit():
+    """Several ragged patches per launch (patches.batch_patches) give every patch the rows of its own
+    B=1 run: batch elements are independent and fake padding rows are never referenced."""
+    from facet_graph_convolution_b200 import model as fm
+    from facet_graph_convolution_b200 import patches as P
+    pts, _ = P.grid_patches(20, 12, block=8, halo=3, K=16)
+    store = fm.VariableStore(dev(), params=_params())
+    idx = [0, 2, 5]
+    xb, ab = P.batch_patches(pts, idx)
+    with torch.no_grad(), fm.variable_store(store):
+        yb = fm.get_model_reg_multi_scale(torch.from_numpy(xb).to(dev()), [torch.from_numpy(a).to(dev()) for a in ab], 1.0)
+    for b, i in enumerate(idx):
+        p = pts[i]
+        with torch.no_grad(), fm.variable_store(store):   # the store's cursor restarts with every forward
+            y1 = fm.get_model_reg_multi_scale(torch.from_numpy(p.x[None]).to(dev()),
+                                              [torch.from_numpy(a[None]).to(dev()) for a in p.adjs], 1.0)
+        n = p.x.shape[0]
+        assert torch.equal(yb[b, :n], y1[0])
+        assert torch.equal(fm.normalizeTensor(yb[b:b + 1, :n]), fm.normalizeTensor(y1))
+
+
 def test_training_step_reduces_loss_and_matches_oracle_loss():
     from facet_graph_convolution_b200 import model as fm
     from facet_graph_convolution_b200 import patches as P

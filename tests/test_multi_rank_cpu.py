@@ -135,6 +135,27 @@ def test_grid_patches_cover_every_facet_once_with_halo():
     assert np.array_equal(some[0].x, pts[4].x) and np.array_equal(some[0].adjs[2], pts[4].adjs[2])
 
 
+def test_batched_patches_pad_with_fake_nodes_only():
+    """batch_patches: ragged patches stacked into one [B,n0,...] batch; the padding is fake nodes (zero
+    features, self-only adjacency at every level), real rows are untouched and never reference padding."""
+    pts, _ = P.grid_patches(20, 12, block=8, halo=3, K=16)
+    idx = [0, 2, 5]
+    xb, ab = P.batch_patches(pts, idx)
+    n0 = xb.shape[1]
+    assert n0 % 16 == 0 and n0 == max(pts[i].x.shape[0] for i in idx)
+    assert [a.shape[1] for a in ab] == [n0, n0 // 4, n0 // 16]
+    for b, i in enumerate(idx):
+        p = pts[i]
+        n = p.x.shape[0]
+        assert np.array_equal(xb[b, :n], p.x) and not xb[b, n:].any()
+        for lvl, a in enumerate(p.adjs):
+            nl = a.shape[0]
+            assert np.array_equal(ab[lvl][b, :nl], a)
+            pad = ab[lvl][b, nl:]
+            assert not pad[:, 1:].any() and np.array_equal(pad[:, 0], np.arange(nl + 1, ab[lvl].shape[1] + 1))
+            assert a.max() <= nl
+
+
 def test_rotation_matrix_and_feature_rotation():
     rng = np.random.RandomState(5)
     R = T.rand_rotation_matrix(rng)
