@@ -387,8 +387,10 @@ int launch_tc(const TcParams& tp_in, void* wimg, float* wunscale, const float* W
 
 }  // namespace
 
+// (M, Cout) pairs whose resident weight image M * 2 Cout * 128 B fits next to the staging buffers:
+// the C2 layer (8, 64) and the network's 64 -> 32 layers (9, 32) (reference Code/model.py:905-932)
 bool conv_fwd_tc_supported(int Cw, int Cout, int M, int K) {
-  return Cw == kCw && Cout == 64 && M == 8 && K <= 32;
+  return Cw == kCw && K <= 32 && ((M == 8 && Cout == 64) || (M == 9 && Cout == 32));
 }
 
 size_t conv_fwd_tc_workspace(int Cout, int M) { return static_cast<size_t>(M) * 2 * Cout * 128 + 512; }
@@ -402,6 +404,7 @@ int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, c
   tp.N = p.N, tp.K = p.K, tp.Cin = p.Cin, tp.bias_mask = p.bias_mask, tp.act = p.act, tp.alpha = p.alpha;
   tp.ldy = p.Cout;
   if (p.M == 8 && p.Cout == 64) return launch_tc<8, 64, MODE_FWD>(tp, wimg_ws, wunscale, W0, st);
+  if (p.M == 9 && p.Cout == 32) return launch_tc<9, 32, MODE_FWD>(tp, wimg_ws, wunscale, W0, st);
   set_error("conv_fwd_tc: unsupported shape");
   return FGC_ERR_UNSUPPORTED;
 }
