@@ -102,16 +102,26 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
   float* Wt = ws.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);
   FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
               conv_fwd_workspace(s));
-  int rc = launch_assign_logits(s, x, u, v, c, uvx, st);
-  if (rc) return rc;
   ConvFwdParams p{x, adj, uvx, Wt, b, y, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M,
                   bias_mask, act, alpha};
+  int rc = FGC_OK;
   if (plan != nullptr && use_mma(s)) {
     char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M));
     char* img = ws.take<char>(conv_mma_workspace(rows));
     FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the planned tensor-core path");
-    return launch_conv_mma(p, W0, plan, img, wimg, st);
+    // max|x| for the image scale rides on the logits pass when that pass reads the whole row
+    const bool fused = assign_logits_absmax_supported(s);
+    if (fused) {
+      rc = prep_image_reset(img, rows, st);
+      if (rc) return rc;
+    }
+    rc = launch_assign_logits(s, x, u, v, c, uvx, st,
+                              fused ? const_cast<unsigned*>(conv_mma_image_maxbits(img, rows)) : nullptr);
+    if (rc) return rc;
+    return launch_conv_mma(p, W0, plan, img, wimg, st, fused);
   }
+  rc = launch_assign_logits(s, x, u, v, c, uvx, st);
+  if (rc) return rc;
   if (use_tc(s)) {
     char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M));
     FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the tensor-core path");

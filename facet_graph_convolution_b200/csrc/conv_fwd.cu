@@ -66,12 +66,19 @@ assign_logits_kernel(const float* __restrict__ x, const float* __restrict__ u,
   }
 }
 
+bool assign_logits_absmax_supported(const fgc_conv_shape* s) {
+  static const bool slow = getenv("FGC_DISABLE_FAST_LOGITS") != nullptr;
+  return !slow && logits_fast_supported(s->Cin, s->Ca0, s->Ca, s->M) && s->Ca0 == 0 && s->Ca == s->Cin;
+}
+
 int launch_assign_logits(const fgc_conv_shape* s, const float* x, const float* u, const float* v,
-                         const float* c, float* uvx, cudaStream_t st) {
+                         const float* c, float* uvx, cudaStream_t st, unsigned* maxbits) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   static const bool slow = getenv("FGC_DISABLE_FAST_LOGITS") != nullptr;
   if (!slow && logits_fast_supported(s->Cin, s->Ca0, s->Ca, s->M))
-    return launch_assign_logits_fast(x, u, v, c, uvx, rows, s->Cin, s->Ca0, s->Ca, s->M, st);
+    return launch_assign_logits_fast(x, u, v, c, uvx, rows, s->Cin, s->Ca0, s->Ca, s->M, st,
+                                     assign_logits_absmax_supported(s) ? maxbits : nullptr);
+  FGC_REQUIRE(maxbits == nullptr, "assign_logits: fused absmax needs the warp-cooperative kernel");
   const int O = 2 * s->M;
   const size_t smem = static_cast<size_t>(O) * ((s->Ca + 3) & ~3) * 4;
   int64_t blocks = (rows + 127) / 128;

@@ -26,6 +26,7 @@ namespace fgc {
 namespace {
 
 constexpr int kCw = 64;            // aggregation channels handled by this kernel
+constexpr int kPrepWBlocks = 16;   // blocks of prep_w_image_kernel
 constexpr int kTile = 64;          // facets per tile
 constexpr int kPass = 32;          // rows per staging pass
 constexpr int kAggWarps = kAggW;     // 32 / kFPW warps cover one pass
@@ -327,7 +328,8 @@ conv_fwd_tc_kernel(const TcParams p) {
 // wimg: M chunks of [NB rows][64 halves] (128 B per row, 16-byte units XOR-swizzled by row & 7):
 //   row n < COUT : fp16(W0[m][n][c] * 2^aw)                      (hi)
 //   row n >= COUT: fp16((W*2^aw - hi) * 2^11)                    (lo)
-// One block: max|W| -> power-of-two scale so that |W*2^aw| < 1.
+// Every block reduces max|W| itself (the weights are a few hundred KB in L2: cheaper than a second launch
+// or a grid barrier) -> power-of-two scale so that |W*2^aw| < 1; then the blocks share the image elements.
 __global__ void __launch_bounds__(1024)
 prep_w_image_kernel(const float* __restrict__ W0, uint16_t* __restrict__ wimg, float* __restrict__ wunscale,
                     int M, int COUT, int transposed) {
@@ -344,9 +346,9 @@ prep_w_image_kernel(const float* __restrict__ W0, uint16_t* __restrict__ wimg, f
   int E = (__float_as_int(mx) >> 23) & 0xFF;
   E = min(max(E, 16), 240);
   const float sc = __int_as_float((253 - E) << 23);
-  if (threadIdx.x == 0) wunscale[0] = __int_as_float((E + 1) << 23);
+  if (threadIdx.x == 0 && blockIdx.x == 0) wunscale[0] = __int_as_float((E + 1) << 23);
   const int NB = 2 * COUT;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     // image element (m, n = o, k = c); transposed: n = c of W0, k = o of W0 (B for gx = t . W^T)
     const int c = e % kCw;
     const int o = (e / kCw) % COUT;
@@ -367,7 +369,7 @@ int launch_tc(const TcParams& tp_in, void* wimg, float* wunscale, const float* W
   using Cfg = TcCfg<M, COUT>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   if (W0 != nullptr) {   // nullptr: the caller already prepared the image
-    prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg), wunscale, M, COUT,
+    prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg), wunscale, M, COUT,
                                              MODE == MODE_TGT ? 1 : 0);
     FGC_LAUNCHED("prep_w_image_kernel");
   }
@@ -413,7 +415,7 @@ int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, c
 int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStream_t st) {
   const size_t img = static_cast<size_t>(M) * 2 * Cw * 128;
   float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
-  prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cw, 1);
+  prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cw, 1);
   FGC_LAUNCHED("prep_w_image_kernel");
   return FGC_OK;
 }
@@ -422,7 +424,7 @@ int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStr
 int launch_prep_w_image(const float* W0, void* wimg_ws, int M, int Cout, cudaStream_t st) {
   const size_t img = static_cast<size_t>(M) * 2 * Cout * 128;
   float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
-  prep_w_image_kernel<<<1, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cout, 0);
+  prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cout, 0);
   FGC_LAUNCHED("prep_w_image_kernel");
   return FGC_OK;
 }

@@ -19,11 +19,11 @@ struct ConvFwdParams {
 };
 
 int launch_assign_logits(const fgc_conv_shape* s, const float* x, const float* u, const float* v,
-                         const float* c, float* uvx, cudaStream_t st);
+                         const float* c, float* uvx, cudaStream_t st, unsigned* maxbits = nullptr);
 // warp-cooperative fast paths of the logit kernels (logits.cu)
 bool logits_fast_supported(int Cin, int Ca0, int Ca, int M);
 int launch_assign_logits_fast(const float* x, const float* u, const float* v, const float* c, float* uvx,
-                              int64_t rows, int Cin, int Ca0, int Ca, int M, cudaStream_t st);
+                              int64_t rows, int Cin, int Ca0, int Ca, int M, cudaStream_t st, unsigned* maxbits = nullptr);
 int launch_logits_bwd_x_fast(const float* d_uvx, const float* u, const float* v, float* gx, int64_t rows, int Cin,
                              int Ca0, int Ca, int M, cudaStream_t st);
 int launch_logits_bwd_p_fast(const float* x, const float* d_uvx, float* part, int64_t rows, int64_t rows_per_chunk,
@@ -52,7 +52,10 @@ size_t conv_mma_workspace(int64_t rows);
 int debug_mma_trace(int64_t* out, int n);
 int prep_image_blocks();
 int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st,
-                      const float* pinv = nullptr, int bias_mask = 0, float* partB = nullptr);
+                      const float* pinv = nullptr, int bias_mask = 0, float* partB = nullptr, bool have_absmax = false);
+// true when launch_assign_logits(..., maxbits) reduces max|x| over exactly the channels the image uses
+bool assign_logits_absmax_supported(const fgc_conv_shape* s);
+int prep_image_reset(void* img_ws, int64_t rows, cudaStream_t st);   // zeroes the scale words; returns them via conv_mma_image_maxbits
 int bwd_w_mma_grid(int64_t rows, int M);
 int launch_bwd_w_mma(const float* uvx, const int32_t* adj, const void* plan, void* ximg_ws, void* gyimg_ws,
                      float* partW, int64_t rows, int N, int K, int M, cudaStream_t st);
@@ -70,7 +73,7 @@ int launch_bwd_tgt_mma(const float* gy, const float* uvx, const float* da_edge, 
                        float* gx, float* d_uvx, int64_t rows, int N, int Cin, int Cout, int M, const void* wimg,
                        void* img_ws, cudaStream_t st);
 int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, void* img_ws, void* wimg_ws,
-                    cudaStream_t st);
+                    cudaStream_t st, bool have_absmax = false);
 int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStream_t st);
 bool bwd_src_tc_supported(int Cw, int Cout, int M, int Cin);
 int launch_bwd_src_tc(const float* gy, const float* x, const int32_t* adj, const float* uvx, const void* wimg,

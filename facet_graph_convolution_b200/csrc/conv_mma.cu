@@ -930,11 +930,22 @@ const unsigned* conv_mma_image_maxbits(const void* img_ws, int64_t rows) {
   return img_ws_views(const_cast<void*>(img_ws), rows).scal;
 }
 int prep_image_blocks() { return num_sms() * 8; }
+int prep_image_reset(void* img_ws, int64_t rows, cudaStream_t st) {
+  FGC_CUDA(cudaMemsetAsync(img_ws_views(img_ws, rows).scal, 0, 16 * sizeof(unsigned), st));
+  return FGC_OK;
+}
 int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st, const float* pinv,
-                      int bias_mask, float* partB) {
+                      int bias_mask, float* partB, bool have_absmax) {
   const ImgWs v = img_ws_views(img_ws, rows);
-  FGC_CUDA(cudaMemsetAsync(v.scal, 0, 16 * sizeof(unsigned), st));
   const int ab = prep_image_blocks();
+  if (have_absmax) {   // scal[0] already holds max|x| (prep_image_reset + the fused reduction of assign_logits)
+    FGC_REQUIRE(partB == nullptr || (ld == 64 && pinv != nullptr), "prep_image: bias partials need 64-channel rows");
+    prep_x_image_kernel<<<ab, 256, 0, st>>>(x, ld, rows, v.scal, v.img, reinterpret_cast<float*>(v.scal + 1), pinv,
+                                            bias_mask, partB);
+    FGC_LAUNCHED("prep_x_image_kernel");
+    return FGC_OK;
+  }
+  FGC_CUDA(cudaMemsetAsync(v.scal, 0, 16 * sizeof(unsigned), st));
   FGC_REQUIRE(partB == nullptr || (ld == 64 && pinv != nullptr), "prep_image: bias partials need 64-channel rows");
   // a row stride above 64 (concat tails): scan the whole tensor, a superset bound is still a valid scale
   absmax2_kernel<<<ab, 256, 0, st>>>(x, rows * (ld / 4), v.scal);
@@ -947,11 +958,11 @@ int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaSt
 
 // img_ws: conv_mma_workspace(rows) bytes; wimg_ws: the weight image workspace of conv_fwd_tc
 int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, void* img_ws, void* wimg_ws,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool have_absmax) {
   using Cfg = MCfg<8, 64>;
   const PlanLayout L(p.rows, p.K, p.M);
   const char* pb = static_cast<const char*>(plan);
-  int rc0 = launch_prep_image(p.x, p.Cin, p.rows, img_ws, st);
+  int rc0 = launch_prep_image(p.x, p.Cin, p.rows, img_ws, st, nullptr, 0, nullptr, have_absmax);
   if (rc0) return rc0;
   const ImgWs iv = img_ws_views(img_ws, p.rows);
   uint4* img = iv.img;

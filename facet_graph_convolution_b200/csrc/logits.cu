@@ -40,6 +40,7 @@ struct LgParams {
   float* part;
   int64_t rows, rows_per_chunk;
   int Cin, Ca0, Ca, M;
+  unsigned* maxbits;   // assign_logits only, optional: atomicMax of the float bits of max|x| over the window
 };
 
 // coefficients of this lane's 4 channels: w[o][0..3], o < 2M (zero beyond Ca / 2M)
@@ -74,6 +75,7 @@ assign_logits_warp_kernel(const LgParams p) {
   const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const bool act = 4 * gl < p.Ca;
   constexpr int U = 4;   // row groups per iteration: all loads are in flight before the first is consumed
+  float amax = 0.f;
   for (int64_t r0 = wid * RPW; r0 < p.rows; r0 += U * nw * RPW) {
     int64_t rr[U];
     float4 xs[U];
@@ -82,6 +84,7 @@ assign_logits_warp_kernel(const LgParams p) {
       rr[t] = r0 + t * nw * RPW + sub;
       xs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (rr[t] < p.rows && act) xs[t] = __ldg(reinterpret_cast<const float4*>(p.x + rr[t] * p.Cin + p.Ca0) + gl);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(xs[t].x), fabsf(xs[t].y)), fmaxf(fabsf(xs[t].z), fabsf(xs[t].w))));
     }
 #pragma unroll
     for (int t = 0; t < U; ++t) {
@@ -99,6 +102,11 @@ assign_logits_warp_kernel(const LgParams p) {
         }
       }
     }
+  }
+  if (p.maxbits != nullptr) {   // max is order-independent: the atomic keeps the result deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) atomicMax(p.maxbits, __float_as_uint(amax));
   }
 }
 
@@ -291,23 +299,23 @@ int fast_lpr(int Cin, int Ca0, int Ca, int M) {
 bool logits_fast_supported(int Cin, int Ca0, int Ca, int M) { return fast_lpr(Cin, Ca0, Ca, M) != 0; }
 
 int launch_assign_logits_fast(const float* x, const float* u, const float* v, const float* c, float* uvx,
-                              int64_t rows, int Cin, int Ca0, int Ca, int M, cudaStream_t st) {
+                              int64_t rows, int Cin, int Ca0, int Ca, int M, cudaStream_t st, unsigned* maxbits) {
   const int lpr = fast_lpr(Cin, Ca0, Ca, M);
-  LgParams p{x, u, v, c, uvx, nullptr, nullptr, rows, 0, Cin, Ca0, Ca, M};
+  LgParams p{x, u, v, c, uvx, nullptr, nullptr, rows, 0, Cin, Ca0, Ca, M, maxbits};
   FGC_LG_DISPATCH(run_assign, p, st);
 }
 
 int launch_logits_bwd_x_fast(const float* d_uvx, const float* u, const float* v, float* gx, int64_t rows, int Cin,
                              int Ca0, int Ca, int M, cudaStream_t st) {
   const int lpr = fast_lpr(Cin, Ca0, Ca, M);
-  LgParams p{nullptr, u, v, nullptr, const_cast<float*>(d_uvx), gx, nullptr, rows, 0, Cin, Ca0, Ca, M};
+  LgParams p{nullptr, u, v, nullptr, const_cast<float*>(d_uvx), gx, nullptr, rows, 0, Cin, Ca0, Ca, M, nullptr};
   FGC_LG_DISPATCH(run_bwd_x, p, st);
 }
 
 int launch_logits_bwd_p_fast(const float* x, const float* d_uvx, float* part, int64_t rows, int64_t rows_per_chunk,
                              int chunks, int Cin, int Ca0, int Ca, int M, cudaStream_t st) {
   const int lpr = fast_lpr(Cin, Ca0, Ca, M);
-  LgParams p{x, nullptr, nullptr, nullptr, const_cast<float*>(d_uvx), nullptr, part, rows, rows_per_chunk, Cin, Ca0, Ca, M};
+  LgParams p{x, nullptr, nullptr, nullptr, const_cast<float*>(d_uvx), nullptr, part, rows, rows_per_chunk, Cin, Ca0, Ca, M, nullptr};
   FGC_LG_DISPATCH(run_bwd_p, p, chunks, st);
 }
 
