@@ -4,6 +4,7 @@
     python benchmarks/net_bench.py --config c1          # single-mesh denoising: icosphere-5, 20 480 faces
     python benchmarks/net_bench.py --config c3          # 2M-facet mesh, ~100 patches with halo, sharded by patch
     python benchmarks/net_bench.py --config c4          # training step on 8 192-node patches (data parallel)
+    python benchmarks/net_bench.py --config c5          # C3 at 3162x3162 quads (20M facets) + whole-mesh vertex update
     python -m torch.distributed.run --nproc-per-node N ... benchmarks/net_bench.py --config c3|c4
 
 Every config prints ONE JSON line (rank 0).  facets/s counts real input faces (C3: core faces, each
@@ -70,7 +71,7 @@ def cpu_net_forward(x, adjs, params, repeat=1):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="c1", choices=["c1", "c3", "c4"])
+    ap.add_argument("--config", default="c1", choices=["c1", "c3", "c4", "c5"])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--grid", type=int, default=1000, help="c3: quads per side (1000 -> 2M facets)")
@@ -171,7 +172,9 @@ def main():
                      "network_forward_ms": ms_net, "network_forward_facets_per_s": nreal / (ms_net * 1e-3),
                      "cpu_baseline": cpu})
 
-    elif args.config == "c3":
+    elif args.config in ("c3", "c5"):
+        if args.config == "c5" and args.grid == 1000:
+            args.grid = 3162
         nx = ny = args.grid
         bx = (nx + args.block - 1) // args.block
         npatch = bx * bx
@@ -243,9 +246,32 @@ def main():
             cpu = {"value": int(p.core.sum()) / dtc, "unit": "facets/s", "cores": cores, "kind": "port",
                    "sample": "oracle/closed_form.py net_forward (fp32 NumPy) on 1 of %d patches (%d nodes), %.2f s; "
                              "per-patch time x patch count" % (npatch, p.x.shape[0], dtc)}
+        vu = None
+        if args.config == "c5" and rank == 0:
+            # whole-mesh update_position2 (60 Jacobi sweeps) on one GPU: ~10M vertices, ~30M edges
+            t0 = time.perf_counter()
+            Vg, Fg = mesh.grid_mesh(nx, ny, torus=False, morton=False)
+            e_map, v_e = mesh.edge_maps(Fg, 20)
+            nrm = mesh.face_normals(Vg, Fg).astype(np.float32)
+            t_idx = time.perf_counter() - t0
+            vd, nd, ed, ved = T(Vg.astype(np.float32)[None]), T(nrm[None]), T(e_map[None]), T(v_e[None])
+            fm.update_position2(vd, nd, ed, ved, iter_num=2, max_edges=20)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            fm.update_position2(vd, nd, ed, ved, iter_num=60, max_edges=20)
+            g1.record()
+            torch.cuda.synchronize()
+            vms = g0.elapsed_time(g1)
+            Vn_, En_, Fn_ = Vg.shape[0], e_map.shape[0], Fg.shape[0]
+            sweep_bytes = 4 * (3 * Vn_ + 3 * Vn_) + 4 * (20 * Vn_ + 4 * En_) + 4 * 3 * Fn_   # SURVEY 8(d) byte model
+            vu = {"ms_60_sweeps": vms, "vertices": Vn_, "edges": En_, "faces": Fn_, "host_index_build_s": t_idx,
+                  "algorithmic_GBps": 60 * sweep_bytes / (vms * 1e-3) / 1e9}
+        if world > 1:
+            dist.barrier()
         line.update({"value": total_core / (ms * 1e-3), "steps": 1, "warmup": max(2, args.warmup), "ms_per_step": ms,
-                     "scaling": "strong", "clocks": clocks, "gpu_launches": int(launches),
-                     "config": {"workload": "C3 multi-scale denoising net inference: %dx%d-quad height field = %d facets, %d patches "
+                     "scaling": "strong", "clocks": clocks, "gpu_launches": int(launches), "vertex_update": vu,
+                     "config": {"workload": args.config.upper() + " multi-scale denoising net inference: %dx%d-quad height field = %d facets, %d patches "
                                             "of %dx%d quads + 3-quad halo, K=16, M=9, patches dealt to %d GPU(s), no collective, "
                                             "%d patches per launch"
                                             % (nx, ny, num_faces, npatch, args.block, args.block, world, PB),
