@@ -78,7 +78,12 @@ static int check_shape(const fgc_conv_shape* s, const char* who) {
 
 static bool use_tc(const fgc_conv_shape* s) {
   static const bool disabled = getenv("FGC_DISABLE_TC") != nullptr;
-  return !disabled && s->Cin % 4 == 0 && conv_fwd_tc_supported(s->Cw, s->Cout, s->M, s->K);
+  if (disabled || s->Cin % 4 != 0 || !conv_fwd_tc_supported(s->Cw, s->Cout, s->M, s->K)) return false;
+  // a layer that needs several channel-block launches only pays off with enough 64-facet tiles to fill
+  // the SMs (measured: 1 250 rows x 8 launches 0.28 ms vs 0.18 ms on the FFMA path; 5 000 rows x 4 launches
+  // 0.16 vs 0.30 ms)
+  const int launches = ((s->Cw + 63) / 64) * ((s->Cout + 31) / 32);
+  return s->M == 8 || launches == 1 || static_cast<int64_t>(s->B) * s->N >= 4096;
 }
 
 static bool use_mma(const fgc_conv_shape* s) {
@@ -89,7 +94,7 @@ static bool use_mma(const fgc_conv_shape* s) {
 static size_t conv_fwd_workspace(const fgc_conv_shape* s) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   return ws_bytes(rows * 2 * s->M, 4) + ws_bytes(static_cast<size_t>(s->M) * s->Cout * s->Cw, 4) +
-         ws_bytes(conv_fwd_tc_workspace(s->Cout, s->M), 1) + (use_mma(s) ? conv_mma_workspace(rows) + 256 : 0) + 512;
+         ws_bytes(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw), 1) + (use_mma(s) ? conv_mma_workspace(rows) + 256 : 0) + 512;
 }
 
 static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0,
@@ -106,7 +111,7 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
                   bias_mask, act, alpha};
   int rc = FGC_OK;
   if (plan != nullptr && use_mma(s)) {
-    char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M));
+    char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw));
     char* img = ws.take<char>(conv_mma_workspace(rows));
     FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the planned tensor-core path");
     // max|x| for the image scale rides on the logits pass when that pass reads the whole row
@@ -123,7 +128,7 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
   rc = launch_assign_logits(s, x, u, v, c, uvx, st);
   if (rc) return rc;
   if (use_tc(s)) {
-    char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M));
+    char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw));
     FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the tensor-core path");
     return launch_conv_fwd_tc(p, W0, wimg, st);
   }
@@ -140,7 +145,7 @@ int conv_fwd_saved_views(const fgc_conv_shape* s, const void* fwd_ws, size_t fwd
   Workspace ws(const_cast<void*>(fwd_ws), fwd_ws_bytes);
   out->uvx = ws.take<float>(rows * 2 * s->M);
   ws.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);
-  ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M));
+  ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw));
   out->ximg = ws.take<char>(conv_mma_workspace(rows));
   FGC_REQUIRE(ws.ok(), "conv_bwd: saved forward workspace too small (%zu bytes given, %zu needed)", fwd_ws_bytes,
               conv_fwd_workspace(s));

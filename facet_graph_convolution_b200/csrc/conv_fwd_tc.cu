@@ -82,6 +82,11 @@ struct TcParams {
   const float* inv;      // inv_cnt of every source row
   const float* da_edge;  // [rows*K][M]
   float* d_uvx;          // [rows][2M], columns M..2M-1 written here
+  // FWD only: a layer wider than one launch covers (64 aggregation channels x COUT outputs) is a sum of
+  // launches over channel blocks -- the first adds the bias, later ones accumulate into y, the last
+  // applies the activation
+  int add_bias, accumulate, apply_act;
+  int cw;                // aggregation channels present in the rows of this launch (0 = 64)
 };
 
 // barrier indices
@@ -135,7 +140,7 @@ conv_fwd_tc_kernel(const TcParams p) {
     const int gl = lane % kLPG;      // lane within the facet's group
     uint32_t empty_parity = 1;       // producer convention: the first wait falls through
     int it = 0;
-    const AggSrc src{p.x, p.Cin, p.adj, p.uvx, p.N, p.K, p.rows, p.rev_ptr, p.rev_edge, p.inv, p.da_edge};
+    const AggSrc src{p.x, p.Cin, p.adj, p.uvx, p.N, p.K, p.rows, p.rev_ptr, p.rev_edge, p.inv, p.da_edge, p.cw};
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       for (int pass = 0; pass < 2; ++pass) {
         const int prow = warp * kFPW + grp;                       // row within the pass (0..31)
@@ -276,8 +281,10 @@ conv_fwd_tc_kernel(const TcParams p) {
                               ex[frow * (Cfg::EXW + 1) + i + j];
               float yv;
               if constexpr (MODE == MODE_FWD) {
-                yv = fmaf(sc, v, fl * __ldg(p.b + c0 + i + j));
-                if (p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
+                yv = sc * v;
+                if (p.add_bias) yv = fmaf(fl, __ldg(p.b + c0 + i + j), yv);
+                if (p.accumulate) yv += yr[i + j];
+                if (p.apply_act && p.act == FGC_ACT_LRELU) yv = lrelu_f(yv, p.alpha);
               } else {
                 yv = sc * v;
               }
@@ -330,13 +337,22 @@ conv_fwd_tc_kernel(const TcParams p) {
 //   row n >= COUT: fp16((W*2^aw - hi) * 2^11)                    (lo)
 // Every block reduces max|W| itself (the weights are a few hundred KB in L2: cheaper than a second launch
 // or a grid barrier) -> power-of-two scale so that |W*2^aw| < 1; then the blocks share the image elements.
+// The image may be a block of a wider layer: outputs o0 .. o0+COUT-1 of ldo, channels c0 .. c0+63 of ldc
+// (ldo = COUT, ldc = 64, o0 = c0 = 0: the whole W0[M][COUT][64]).
+__device__ __forceinline__ size_t w_src_index(int m, int o, int c, int ldo, int ldc, int o0, int c0) {
+  return (static_cast<size_t>(m) * ldo + o0 + o) * ldc + c0 + c;
+}
 __global__ void __launch_bounds__(1024)
 prep_w_image_kernel(const float* __restrict__ W0, uint16_t* __restrict__ wimg, float* __restrict__ wunscale,
-                    int M, int COUT, int transposed) {
+                    int M, int COUT, int transposed, int ldo, int ldc, int o0, int c0) {
   __shared__ float red[32];
   const int total = M * COUT * kCw;
   float mx = 0.f;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) mx = fmaxf(mx, fabsf(W0[e]));
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c = e % kCw, o = (e / kCw) % COUT, m = e / (kCw * COUT);
+    const bool in = transposed || c0 + c < ldc;   // a 32-channel layer fills half of the 64-wide image
+    mx = fmaxf(mx, in ? fabsf(transposed ? W0[e] : W0[w_src_index(m, o, c, ldo, ldc, o0, c0)]) : 0.f);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -353,7 +369,8 @@ prep_w_image_kernel(const float* __restrict__ W0, uint16_t* __restrict__ wimg, f
     const int c = e % kCw;
     const int o = (e / kCw) % COUT;
     const int m = e / (kCw * COUT);
-    const float v = (transposed ? W0[(static_cast<size_t>(m) * kCw + c) * COUT + o] : W0[e]) * sc;
+    const float v = (transposed ? W0[(static_cast<size_t>(m) * kCw + c) * COUT + o]
+                                : (c0 + c < ldc ? W0[w_src_index(m, o, c, ldo, ldc, o0, c0)] : 0.f)) * sc;
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
     const int unit = c >> 3, within = c & 7;
@@ -370,7 +387,7 @@ int launch_tc(const TcParams& tp_in, void* wimg, float* wunscale, const float* W
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   if (W0 != nullptr) {   // nullptr: the caller already prepared the image
     prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg), wunscale, M, COUT,
-                                             MODE == MODE_TGT ? 1 : 0);
+                                                       MODE == MODE_TGT ? 1 : 0, COUT, kCw, 0, 0);
     FGC_LAUNCHED("prep_w_image_kernel");
   }
   TcParams tp = tp_in;
@@ -389,24 +406,54 @@ int launch_tc(const TcParams& tp_in, void* wimg, float* wunscale, const float* W
 
 }  // namespace
 
-// (M, Cout) pairs whose resident weight image M * 2 Cout * 128 B fits next to the staging buffers:
-// the C2 layer (8, 64) and the network's 64 -> 32 layers (9, 32) (reference Code/model.py:905-932)
+// One launch covers 64 aggregation channels x COUT outputs with a resident weight image of
+// M * 2 COUT * 128 B next to the staging buffers: (M, COUT) = (8, 64) -- the C2 layer -- and (9, 32).
+// The network's M = 9 layers (reference Code/model.py:870-932) with 64 / 128 aggregation channels and
+// 32 / 64 / 128 outputs are sums of (Cw / 64) x (Cout / 32) such launches over channel blocks.
 bool conv_fwd_tc_supported(int Cw, int Cout, int M, int K) {
-  return Cw == kCw && K <= 32 && ((M == 8 && Cout == 64) || (M == 9 && Cout == 32));
+  if (K > 32) return false;
+  if (M == 8) return Cw == kCw && Cout == 64;
+  return M == 9 && (Cw == 32 || Cw == 64 || Cw == 128) && (Cout == 32 || Cout == 64 || Cout == 128);
 }
 
-size_t conv_fwd_tc_workspace(int Cout, int M) { return static_cast<size_t>(M) * 2 * Cout * 128 + 512; }
+static size_t tc_image_bytes(int Cout, int M) { return (static_cast<size_t>(M) * 2 * Cout * 128 + 512 + 255) / 256 * 256; }
 
-// wimg_ws: conv_fwd_tc_workspace bytes (16-byte aligned); its tail holds the scalar un-scale
+size_t conv_fwd_tc_workspace(int Cout, int M, int Cw) {
+  if (M == 9) return tc_image_bytes(32, M) * ((Cout + 31) / 32) * ((Cw + 63) / 64);
+  return static_cast<size_t>(M) * 2 * Cout * 128 + 512;
+}
+
+// wimg_ws: conv_fwd_tc_workspace bytes (16-byte aligned); the tail of every image holds its scalar un-scale
 int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st) {
-  const size_t img = static_cast<size_t>(p.M) * 2 * p.Cout * 128;
-  float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
   TcParams tp{};
   tp.x = p.x, tp.adj = p.adj, tp.uvx = p.uvx, tp.b = p.b, tp.y = p.y, tp.rows = p.rows;
   tp.N = p.N, tp.K = p.K, tp.Cin = p.Cin, tp.bias_mask = p.bias_mask, tp.act = p.act, tp.alpha = p.alpha;
   tp.ldy = p.Cout;
-  if (p.M == 8 && p.Cout == 64) return launch_tc<8, 64, MODE_FWD>(tp, wimg_ws, wunscale, W0, st);
-  if (p.M == 9 && p.Cout == 32) return launch_tc<9, 32, MODE_FWD>(tp, wimg_ws, wunscale, W0, st);
+  tp.add_bias = 1, tp.accumulate = 0, tp.apply_act = 1;
+  if (p.M == 8 && p.Cout == 64) {
+    const size_t img = static_cast<size_t>(p.M) * 2 * p.Cout * 128;
+    float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
+    return launch_tc<8, 64, MODE_FWD>(tp, wimg_ws, wunscale, W0, st);
+  }
+  if (p.M == 9) {
+    const int nco = p.Cout / 32, ncc = (p.Cw + 63) / 64;
+    const size_t img = static_cast<size_t>(p.M) * 2 * 32 * 128;
+    for (int oh = 0; oh < nco; ++oh)
+      for (int ch = 0; ch < ncc; ++ch) {
+        char* base = static_cast<char*>(wimg_ws) + tc_image_bytes(32, p.M) * (oh * ncc + ch);
+        float* wunscale = reinterpret_cast<float*>(base + img);
+        prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, reinterpret_cast<uint16_t*>(base), wunscale, p.M, 32, 0,
+                                                           p.Cout, p.Cw, 32 * oh, 64 * ch);
+        FGC_LAUNCHED("prep_w_image_kernel");
+        TcParams t2 = tp;
+        t2.x = p.x + 64 * ch, t2.b = p.b + 32 * oh, t2.y = p.y + 32 * oh;
+        t2.add_bias = ch == 0, t2.accumulate = ch > 0, t2.apply_act = ch == ncc - 1;
+        t2.cw = (p.Cw - 64 * ch >= 64) ? 0 : p.Cw - 64 * ch;
+        const int rc = launch_tc<9, 32, MODE_FWD>(t2, base, wunscale, nullptr, st);
+        if (rc) return rc;
+      }
+    return FGC_OK;
+  }
   set_error("conv_fwd_tc: unsupported shape");
   return FGC_ERR_UNSUPPORTED;
 }
@@ -415,7 +462,7 @@ int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, c
 int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStream_t st) {
   const size_t img = static_cast<size_t>(M) * 2 * Cw * 128;
   float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
-  prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cw, 1);
+  prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cw, 1, Cw, kCw, 0, 0);
   FGC_LAUNCHED("prep_w_image_kernel");
   return FGC_OK;
 }
@@ -424,7 +471,7 @@ int launch_prep_w_image_t(const float* W0, void* wimg_ws, int M, int Cw, cudaStr
 int launch_prep_w_image(const float* W0, void* wimg_ws, int M, int Cout, cudaStream_t st) {
   const size_t img = static_cast<size_t>(M) * 2 * Cout * 128;
   float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img);
-  prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cout, 0);
+  prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, static_cast<uint16_t*>(wimg_ws), wunscale, M, Cout, 0, Cout, kCw, 0, 0);
   FGC_LAUNCHED("prep_w_image_kernel");
   return FGC_OK;
 }

@@ -36,7 +36,7 @@ int launch_gather_rows(const float* x, const int32_t* adj, float* out, int64_t r
                        int C, cudaStream_t st);
 // tensor-core (tcgen05) forward for the dense shapes
 bool conv_fwd_tc_supported(int Cw, int Cout, int M, int K);
-size_t conv_fwd_tc_workspace(int Cout, int M);
+size_t conv_fwd_tc_workspace(int Cout, int M, int Cw = 64);
 int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st);
 bool bwd_tgt_tc_supported(int Cw, int Cout, int M);
 int launch_bwd_tgt_tc(const float* gy, const float* uvx, const float* W0, const float* da_edge,

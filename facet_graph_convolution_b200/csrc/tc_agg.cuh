@@ -34,6 +34,7 @@ struct AggSrc {
   const int32_t* rev_edge;
   const float* inv;      // inv_cnt of every source row
   const float* da_edge;  // [rows*K][M]
+  int cw;                // aggregation channels actually present in a row (0 = all 64); the rest read as zero
 };
 
 template <int M>
@@ -163,7 +164,8 @@ __device__ __forceinline__ void agg_load_row(const AggSrc& p, int j, int gl, flo
 #pragma unroll
   for (int i = 0; i < kF4; ++i) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j >= 0) t = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(j) * p.ldx) + gl + kLPG * i);
+    if (j >= 0 && (p.cw == 0 || 4 * (gl + kLPG * i) < p.cw))
+      t = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(j) * p.ldx) + gl + kLPG * i);
     xp[2 * i] = make_float2(t.x, t.y);
     xp[2 * i + 1] = make_float2(t.z, t.w);
   }
