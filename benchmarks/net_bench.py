@@ -202,11 +202,14 @@ def main():
                 # normalizeTensor's mean is global per patch (utils.py:1700-1715): one call per element
                 return [fm.normalizeTensor(y[b:b + 1, :n]) for b, n in enumerate(ns)]
 
-        if PB > 1 and rank == 0:   # the batched run reproduces the B=1 rows bit for bit
+        if PB > 1 and rank == 0:
+            # the batched run reproduces the B=1 rows (bit for bit when both sizes select the same kernels --
+            # tests/test_gpu_pipeline.py; small coarse levels run on the FFMA family, batched ones on tcgen05)
             p0 = mine[0]
             one = fwd(torch.from_numpy(p0.x[None]).to(dev), [torch.from_numpy(a[None]).to(dev) for a in p0.adjs],
                       [p0.x.shape[0]])[0]
-            assert torch.equal(one, fwd(*resident[0])[0]), "batched forward differs from the B=1 forward"
+            dmax = float((one - fwd(*resident[0])[0]).abs().max())
+            assert dmax < 1e-5, "batched forward differs from the B=1 forward by %g" % dmax
         for x, adjs, ns in resident[: max(2, args.warmup)]:
             fwd(x, adjs, ns)
         barrier()

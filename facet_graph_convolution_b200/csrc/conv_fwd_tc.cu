@@ -342,10 +342,20 @@ conv_fwd_tc_kernel(const TcParams p) {
 __device__ __forceinline__ size_t w_src_index(int m, int o, int c, int ldo, int ldc, int o0, int c0) {
   return (static_cast<size_t>(m) * ldo + o0 + o) * ldc + c0 + c;
 }
+// blockIdx.y selects the block of a channel-block decomposition: image y = oh * ncc + ch lies img_stride
+// bytes after the previous one (its un-scale word behind its M * 2 COUT * 128 image bytes) and covers
+// outputs o0 + COUT oh .., channels c0 + 64 ch ..  (ncc = 1, gridDim.y = 1: a single image).
 __global__ void __launch_bounds__(1024)
 prep_w_image_kernel(const float* __restrict__ W0, uint16_t* __restrict__ wimg, float* __restrict__ wunscale,
-                    int M, int COUT, int transposed, int ldo, int ldc, int o0, int c0) {
+                    int M, int COUT, int transposed, int ldo, int ldc, int o0, int c0, int ncc = 1,
+                    size_t img_stride = 0) {
   __shared__ float red[32];
+  if (gridDim.y > 1) {
+    const int oh = blockIdx.y / ncc, ch = blockIdx.y % ncc;
+    o0 += COUT * oh, c0 += kCw * ch;
+    wimg = reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(wimg) + img_stride * blockIdx.y);
+    wunscale = reinterpret_cast<float*>(reinterpret_cast<char*>(wunscale) + img_stride * blockIdx.y);
+  }
   const int total = M * COUT * kCw;
   float mx = 0.f;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
@@ -438,13 +448,15 @@ int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, c
   if (p.M == 9) {
     const int nco = p.Cout / 32, ncc = (p.Cw + 63) / 64;
     const size_t img = static_cast<size_t>(p.M) * 2 * 32 * 128;
+    // all weight images of the layer in one launch
+    prep_w_image_kernel<<<dim3(kPrepWBlocks, nco * ncc), 1024, 0, st>>>(
+        W0, static_cast<uint16_t*>(wimg_ws), reinterpret_cast<float*>(static_cast<char*>(wimg_ws) + img), p.M, 32, 0,
+        p.Cout, p.Cw, 0, 0, ncc, tc_image_bytes(32, p.M));
+    FGC_LAUNCHED("prep_w_image_kernel");
     for (int oh = 0; oh < nco; ++oh)
       for (int ch = 0; ch < ncc; ++ch) {
         char* base = static_cast<char*>(wimg_ws) + tc_image_bytes(32, p.M) * (oh * ncc + ch);
         float* wunscale = reinterpret_cast<float*>(base + img);
-        prep_w_image_kernel<<<kPrepWBlocks, 1024, 0, st>>>(W0, reinterpret_cast<uint16_t*>(base), wunscale, p.M, 32, 0,
-                                                           p.Cout, p.Cw, 32 * oh, 64 * ch);
-        FGC_LAUNCHED("prep_w_image_kernel");
         TcParams t2 = tp;
         t2.x = p.x + 64 * ch, t2.b = p.b + 32 * oh, t2.y = p.y + 32 * oh;
         t2.add_bias = ch == 0, t2.accumulate = ch > 0, t2.apply_act = ch == ncc - 1;
