@@ -304,6 +304,14 @@ def main():
         for _ in range(args.warmup):
             ftrain.train_step(net, batch, bucket, opt, rng, group)
         barrier()
+        if args.profile:
+            import ctypes as C
+            L.fgc_profile_begin(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            ftrain.train_step(net, batch, bucket, opt, rng, group)
+            buf = C.create_string_buffer(1 << 16)
+            L.fgc_profile_end(buf, len(buf))
+            line["kernels_ms"] = {ln.split()[0]: [round(float(ln.split()[1]), 4), int(ln.split()[2])]
+                                  for ln in buf.value.decode().strip().splitlines()}
         smp = clocks_sampler(local_rank)
         n0 = L.fgc_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

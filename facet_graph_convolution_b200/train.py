@@ -120,17 +120,72 @@ def loss_on_patch(forward, x, adjs, gt, rng: np.random.RandomState, samples: int
     return fm.faceNormalsLoss(n[:, idx, :].contiguous(), gt[:, idx, :].contiguous())
 
 
+_STACK_CACHE = {}
+_STACK_CACHE_MAX = 16
+
+
+def _stacked_adjs(batch):
+    """Adjacency pyramids of the batch concatenated along the batch axis.  Cached per batch composition
+    (the caches of the reverse adjacency and of the tile plans are keyed by tensor identity, so a batch
+    that comes back -- every epoch -- must come back as the same tensors)."""
+    key = tuple((a.data_ptr(), a._version, tuple(a.shape)) for _, adjs, _ in batch for a in adjs)
+    hit = _STACK_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    adjs = [torch.cat([b[1][lvl] for b in batch], dim=0) for lvl in range(len(batch[0][1]))]
+    if len(_STACK_CACHE) >= _STACK_CACHE_MAX:
+        _STACK_CACHE.pop(next(iter(_STACK_CACHE)))
+    _STACK_CACHE[key] = (adjs, [b[1] for b in batch])   # keep the parts alive: their pointers are the key
+    return adjs
+
+
+def _stackable(batch) -> bool:
+    x0, a0, g0 = batch[0]
+    return len(batch) > 1 and all(x.shape == x0.shape and g.shape == g0.shape and len(a) == len(a0) and
+                                  all(u.shape == v.shape for u, v in zip(a, a0)) for x, a, g in batch)
+
+
+def loss_on_stacked_patches(forward, batch, rng: np.random.RandomState, samples: int = COST_SAMPLES,
+                            augment: bool = True):
+    """Mean over the patches of `batch` of the per-patch objective, with ONE network forward over the
+    patches stacked along the batch axis (the layers treat batch elements independently; the
+    per-patch normalizeTensor and sampling follow train.py:503-517 element by element).  Random
+    numbers are drawn in the order of the patch-by-patch loop (rotation, then sample ids)."""
+    from . import model as fm
+    xs, gts, ids = [], [], []
+    for x, _, gt in batch:
+        if augment:
+            R = torch.from_numpy(rand_rotation_matrix(rng).astype(np.float32)).to(x.device)
+            x, gt = rotate_features(x, R), rotate_features(gt, R)
+        xs.append(x)
+        gts.append(gt)
+        ids.append(torch.from_numpy(rng.randint(x.shape[1], size=samples)).to(x.device))
+    y = forward(torch.cat(xs, dim=0), _stacked_adjs(batch))
+    total = None
+    for b, (gt, idx) in enumerate(zip(gts, ids)):
+        n = fm.normalizeTensor(y[b:b + 1].contiguous())
+        lb = fm.faceNormalsLoss(n[:, idx, :].contiguous(), gt[:, idx, :].contiguous()) / len(batch)
+        total = lb if total is None else total + lb
+    return total
+
+
 def train_step(net, batch, bucket: GradBucket, opt: Adam, rng: np.random.RandomState, group=None,
-               samples: int = COST_SAMPLES, augment: bool = True) -> float:
+               samples: int = COST_SAMPLES, augment: bool = True, stack: bool = True) -> float:
     """forward + backward over this rank's `batch` of (x[1,N0,Cin], adjs, gt[1,N0,3]) patches,
-    one all-reduce of the flat gradient bucket, Adam.  Returns the rank-local mean loss."""
+    one all-reduce of the flat gradient bucket, Adam.  Returns the rank-local mean loss.
+    Equal-sized patches are stacked into one forward/backward (`stack`); ragged ones run one by one."""
     for p in bucket.params:
         p.grad = None
     total = 0.0
-    for x, adjs, gt in batch:
-        loss = loss_on_patch(net, x, adjs, gt, rng, samples, augment) / len(batch)
+    if stack and _stackable(batch):
+        loss = loss_on_stacked_patches(net, batch, rng, samples, augment)
         loss.backward()
-        total += float(loss.detach())
+        total = float(loss.detach())
+    else:
+        for x, adjs, gt in batch:
+            loss = loss_on_patch(net, x, adjs, gt, rng, samples, augment) / len(batch)
+            loss.backward()
+            total += float(loss.detach())
     bucket.pack()
     bucket.all_reduce_mean(group)
     opt.step()

@@ -103,3 +103,29 @@ def test_training_step_reduces_loss_and_matches_oracle_loss():
     losses = [T.train_step(net, [(x, adjs, gt)], bucket, opt, rng, samples=2000, augment=False) for _ in range(8)]
     assert all(np.isfinite(losses))
     assert min(losses[-3:]) < losses[0]
+
+
+def test_stacked_training_step_matches_patch_by_patch():
+    """train_step stacks equal-sized patches into one forward/backward; loss and the flat gradient bucket
+    equal the patch-by-patch loop (same random stream: rotation, then sample ids, per patch)."""
+    from facet_graph_convolution_b200 import model as fm
+    from facet_graph_convolution_b200 import patches as P
+    from facet_graph_convolution_b200 import train as T
+    batch = []
+    for seed in (0, 1, 2):
+        pts, _ = P.grid_patches(16, 16, block=16, halo=0, K=16, noise=0.3, seed=seed)
+        clean, _ = P.grid_patches(16, 16, block=16, halo=0, K=16, noise=0.0, seed=seed)
+        p, pc = pts[0], clean[0]
+        batch.append((torch.from_numpy(p.x[None]).to(dev()), [torch.from_numpy(a[None]).to(dev()) for a in p.adjs],
+                      torch.from_numpy(np.ascontiguousarray(pc.x[None, :, :3])).to(dev())))
+    out = []
+    for stack in (False, True):
+        net = fm.DenoisingNet(device=dev(), params=_params(7))
+        net(batch[0][0], batch[0][1])
+        bucket = T.GradBucket(list(net.parameters()))
+        opt = T.Adam(bucket, lr=1e-3)
+        loss = T.train_step(net, batch, bucket, opt, np.random.RandomState(3), samples=1500, augment=True, stack=stack)
+        out.append((loss, bucket.flat.clone()))
+    (l0, g0), (l1, g1) = out
+    assert abs(l0 - l1) < 1e-4 * max(1.0, abs(l0))
+    assert float((g0 - g1).abs().max()) < 1e-4 * max(1.0, float(g0.abs().max()))
