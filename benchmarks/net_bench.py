@@ -5,6 +5,7 @@
     python benchmarks/net_bench.py --config c3          # 2M-facet mesh, ~100 patches with halo, sharded by patch
     python benchmarks/net_bench.py --config c4          # training step on 8 192-node patches (data parallel)
     python benchmarks/net_bench.py --config c5          # C3 at 3162x3162 quads (20M facets) + whole-mesh vertex update
+    python benchmarks/net_bench.py --config index       # GPU index builders (adjacency, vertex-face, edge maps) at 2M faces
     python -m torch.distributed.run --nproc-per-node N ... benchmarks/net_bench.py --config c3|c4
 
 Every config prints ONE JSON line (rank 0).  facets/s counts real input faces (C3: core faces, each
@@ -71,7 +72,7 @@ def cpu_net_forward(x, adjs, params, repeat=1):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="c1", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--config", default="c1", choices=["c1", "c3", "c4", "c5", "index"])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--grid", type=int, default=1000, help="c3: quads per side (1000 -> 2M facets)")
@@ -281,6 +282,56 @@ def main():
                                 "patches_this_rank": len(mine), "host_patch_generation_s": t_gen},
                      "e2e": {"value": total_core / dt, "unit": "facets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                              "ms_per_step": dt * 1e3},
+                     "cpu_baseline": cpu})
+
+    elif args.config == "index":
+        # getFacesLargeAdj + getVerticesFaces + getEdgeMap on the GPU, host faces in,
+        # index tensors resident on the device out; the CPU number is the vectorised NumPy restatement
+        # (the reference's own Python loops take minutes at this size)
+        nx = ny = args.grid
+        _, Fh = mesh.grid_mesh(nx, ny, torus=False, morton=True)
+        Fh = np.ascontiguousarray(Fh, np.int32)
+        nf, nv = Fh.shape[0], int(Fh.max()) + 1
+        Fp = torch.from_numpy(Fh).pin_memory()
+
+        def build_all():
+            Fd = Fp.to(dev, non_blocking=True)
+            adj, vf = ops.build_faces_adj(Fd, K=16, kv=25, nv=nv)
+            e_map, v_e = ops.build_edge_maps(Fd, 20, nv=nv)
+            return adj, vf, e_map, v_e
+
+        for _ in range(3):
+            build_all()
+        barrier()
+        n0 = L.fgc_launch_count()
+        ts = []
+        for _ in range(max(5, args.steps // 2)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = build_all()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        launches = (L.fgc_launch_count() - n0) / len(ts)
+        ms = float(np.median(ts))
+        out_bytes = sum(t.numel() * 4 for t in out)
+        cpu = None
+        if not args.no_cpu:
+            t0 = time.perf_counter()
+            a_ref = mesh.faces_large_adj(Fh, 16)
+            mesh.vertex_faces(Fh, 25)
+            mesh.edge_maps(Fh, 20)
+            dtc = time.perf_counter() - t0
+            assert np.array_equal(out[0].cpu().numpy(), a_ref)
+            cpu = {"value": nf / dtc, "unit": "facets/s", "cores": 1, "kind": "port",
+                   "sample": "NumPy restatement (mesh.faces_large_adj + vertex_faces + edge_maps) of the reference's host "
+                             "loops on the same %d faces, %.2f s" % (nf, dtc)}
+        line.update({"value": nf / (ms * 1e-3), "steps": len(ts), "warmup": 3, "ms_per_step": ms, "scaling": "weak",
+                     "gpu_launches": launches,
+                     "config": {"workload": "index builders: %dx%d-quad grid = %d faces, %d vertices; adjacency K=16, vertex-face "
+                                            "lists (25), edge map + vertex-edge lists (20); faces uploaded from pinned host memory "
+                                            "inside the timed region" % (nx, ny, nf, nv)},
+                     "output_bytes": out_bytes, "algorithmic_GBps": (nf * 12 + out_bytes) / (ms * 1e-3) / 1e9,
                      "cpu_baseline": cpu})
 
     else:  # c4

@@ -473,3 +473,40 @@ def vertex_update_ms(x, normals, faces, v_faces, scale, steps=2, iters=20):
 
 def launch_count() -> int:
     return int(_lib.lib().fgc_launch_count())
+
+
+# ----------------------------------------------------------------------------- index builders
+def build_faces_adj(faces, K=None, nv=None, kv=None):
+    """GPU getFacesLargeAdj / getVerticesFaces (reference Code/utils.py:243-295, 370-395).
+    faces[nf,3] int32 on the GPU -> (adj[nf,K] | None, v_faces[nv,kv] | None), bit-identical to the
+    reference's host loops."""
+    L = _lib.lib()
+    faces = _i32(faces, "faces")
+    if faces.dim() != 2 or faces.shape[1] != 3:
+        raise _lib.FacetConvError("faces must be [nf,3], got %s" % (tuple(faces.shape),))
+    nf = faces.shape[0]
+    nv = int(faces.max().item()) + 1 if nv is None else int(nv)
+    adj = torch.empty((nf, K), dtype=torch.int32, device=faces.device) if K else None
+    vf = torch.empty((nv, kv), dtype=torch.int32, device=faces.device) if kv else None
+    with torch.cuda.device(faces.device):
+        ws = _ws(L.fgc_faces_adj_workspace(nf, nv), faces)
+        check(L.fgc_build_faces_adj(_p(faces), nf, nv, int(K or 0), _p(adj) if adj is not None else None,
+                                    _p(vf) if vf is not None else None, int(kv or 0), _p(ws), ws.numel(),
+                                    _stream(faces)), "fgc_build_faces_adj")
+    return adj, vf
+
+
+def build_edge_maps(faces, max_edges=20, nv=None):
+    """GPU getEdgeMap (reference Code/utils.py:91-183): (e_map[E,4], v_edges[nv,max_edges])."""
+    L = _lib.lib()
+    faces = _i32(faces, "faces")
+    nf = faces.shape[0]
+    nv = int(faces.max().item()) + 1 if nv is None else int(nv)
+    e_map = torch.empty((3 * nf, 4), dtype=torch.int32, device=faces.device)
+    v_e = torch.empty((nv, max_edges), dtype=torch.int32, device=faces.device)
+    ne = C.c_int64(0)
+    with torch.cuda.device(faces.device):
+        ws = _ws(L.fgc_edge_maps_workspace(nf, nv), faces)
+        check(L.fgc_build_edge_maps(_p(faces), nf, nv, int(max_edges), _p(e_map), C.byref(ne), _p(v_e), _p(ws),
+                                    ws.numel(), _stream(faces)), "fgc_build_edge_maps")
+    return e_map[: int(ne.value)], v_e

@@ -238,6 +238,30 @@ FGC_API int fgc_vertex_update_ms(const float* x_in, float* x_out, const float* n
                          int max_faces, int scale, int steps, int iters, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- index builders
+ * GPU versions of the host loops that produce the index tensors above; pure integer work, outputs
+ * bit-identical to the reference's (pinned by tests/golden/index_layouts.npz, which the reference
+ * functions generated).  faces[nf][3] int32 vertex ids (rows of -1 = fake nodes are skipped).
+ *
+ * fgc_build_faces_adj: adj[nf][K] in getFacesLargeAdj layout (reference Code/utils.py:243-295: row f =
+ * f+1, then the other faces around each vertex of f -- vertices in increasing id, faces in increasing id,
+ * edge-adjacent faces therefore twice -- cut after K-1 appends, 0 padded) and/or v_faces[nv][kv] in
+ * getVerticesFaces layout (Code/utils.py:370-395: faces around each vertex, increasing, -1 padded).
+ * Either output may be NULL.  Synchronises the stream (returns an error for vertex ids outside
+ * 0..nv-1 or a vertex with more than kv faces).
+ *
+ * fgc_build_edge_maps: e_map[E][4] = (va, vb, first face, last later face | -1) with edges numbered by
+ * first appearance over faces and slots (v1v2, v1v3, v2v3), va/vb as in that first appearance, and
+ * v_edges[nv][max_edges] = edge ids around each vertex, increasing, -1 padded (getEdgeMap,
+ * Code/utils.py:91-183).  e_map must hold 3*nf rows; *num_edges (host) receives E.  Synchronises. */
+FGC_API size_t fgc_faces_adj_workspace(int64_t nf, int64_t nv);
+FGC_API int fgc_build_faces_adj(const int32_t* faces, int64_t nf, int64_t nv, int K, int32_t* adj,
+                        int32_t* v_faces, int kv, void* workspace, size_t workspace_bytes, void* stream);
+FGC_API size_t fgc_edge_maps_workspace(int64_t nf, int64_t nv);
+FGC_API int fgc_build_edge_maps(const int32_t* faces, int64_t nf, int64_t nv, int max_edges, int32_t* e_map,
+                        int64_t* num_edges, int32_t* v_edges, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* ---------------------------------------------------------------- host-buffer entry points
  * What a non-torch FFI binding calls: pinned or pageable HOST pointers in, HOST pointers out;
  * the call allocates device buffers (cached per thread), copies H2D, runs the kernels on

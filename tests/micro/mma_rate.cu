@@ -60,8 +60,12 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int nacc, int c
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+__global__ void spin(long long cycles) { const long long t0 = clock64(); while (clock64() - t0 < cycles) {} }
+
 int main() {
   long long* d; cudaMalloc(&d, 16);
+  spin<<<148, 128>>>(400000000ll);   // ~0.2 s: let the clocks ramp before the one-CTA measurements
+  cudaDeviceSynchronize();
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   const char* names[] = {"TS  B K-major ", "SS  B K-major ", "SS  B MN-major"};
   for (int mode = 0; mode < 3; ++mode)
