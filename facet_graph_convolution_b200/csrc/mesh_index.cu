@@ -162,6 +162,80 @@ __global__ void ve_fill_kernel(const int32_t* __restrict__ e_map, int64_t E, int
   }
 }
 
+// ---- per-face input features [normal | barycentre / bbox diagonal]  (reference Code/utils.py:63-68 with the
+// two-pass normalize of :26-35, and :1264-1294).  The reference works in float64 NumPy; the arithmetic here is
+// double too, rounded once to fp32 (the dtype the placeholders cast to, train.py:52-56).
+__device__ __forceinline__ unsigned f2ord(float f) {   // order-preserving float -> unsigned
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__global__ void bbox_kernel(const float* __restrict__ verts, int64_t nv, unsigned* __restrict__ mm) {
+  unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nv;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const unsigned o = f2ord(verts[3 * v + j]);
+      lo[j] = min(lo[j], o), hi[j] = max(hi[j], o);
+    }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[j] = min(lo[j], __shfl_xor_sync(0xffffffffu, lo[j], o));
+      hi[j] = max(hi[j], __shfl_xor_sync(0xffffffffu, hi[j], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(mm + j, lo[j]);
+      atomicMax(mm + 3 + j, hi[j]);
+    }
+  }
+}
+
+__global__ void face_features_kernel(const float* __restrict__ verts, const int32_t* __restrict__ faces, int64_t nf,
+                                     int64_t nv, const unsigned* __restrict__ mm, int normalize, float* __restrict__ out) {
+  double diag = 1.0;
+  if (normalize) {
+    double d2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double e = static_cast<double>(ord2f(mm[3 + j])) - static_cast<double>(ord2f(mm[j]));
+      d2 += e * e;
+    }
+    diag = sqrt(d2);
+  }
+  for (int64_t f = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; f < nf;
+       f += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float* o = out + 6 * f;
+    const int a = faces[3 * f], b = faces[3 * f + 1], c = faces[3 * f + 2];
+    if (a < 0 || a >= nv || b < 0 || b >= nv || c < 0 || c >= nv) {   // fake node: zero features
+#pragma unroll
+      for (int j = 0; j < 6; ++j) o[j] = 0.f;
+      continue;
+    }
+    double p[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) p[0][j] = verts[3ll * a + j], p[1][j] = verts[3ll * b + j], p[2][j] = verts[3ll * c + j];
+    const double e1[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
+    const double e2[3] = {p[2][0] - p[0][0], p[2][1] - p[0][1], p[2][2] - p[0][2]};
+    double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {   // normalize(): a * (1 / (|a| + 1e-8)), applied twice
+      const double inv = 1.0 / (sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) + 0.00000001);
+      n[0] *= inv, n[1] *= inv, n[2] *= inv;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      o[j] = static_cast<float>(n[j]);
+      o[3 + j] = static_cast<float>((p[0][j] / diag + p[1][j] / diag + p[2][j] / diag) / 3);
+    }
+  }
+}
+
 unsigned grid_for(int64_t n) {
   int64_t b = (n + 255) / 256;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 32;
@@ -236,6 +310,24 @@ int fgc_build_faces_adj(const int32_t* faces, int64_t nf, int64_t nv, int K, int
     FGC_CUDA(cudaStreamSynchronize(st));
     FGC_REQUIRE(h_flag == 0, "build_faces_adj: a vertex has %d faces, more than kv=%d", h_flag, kv);
   }
+  return FGC_OK;
+}
+
+int fgc_face_features(const float* verts, const int32_t* faces, int64_t nf, int64_t nv, int normalize,
+                      float* features, void* workspace, size_t workspace_bytes, void* stream) {
+  FGC_REQUIRE(verts && faces && features && nf > 0 && nv > 0, "face_features: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Workspace ws(workspace, workspace_bytes);
+  unsigned* mm = ws.take<unsigned>(8);
+  FGC_REQUIRE(ws.ok(), "face_features: workspace too small (needs 1 KB)");
+  FGC_CUDA(cudaMemsetAsync(mm, 0xFF, 3 * sizeof(unsigned), st));
+  FGC_CUDA(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(unsigned), st));
+  if (normalize) {
+    bbox_kernel<<<grid_for(nv), 256, 0, st>>>(verts, nv, mm);
+    FGC_LAUNCHED("bbox_kernel");
+  }
+  face_features_kernel<<<grid_for(nf), 256, 0, st>>>(verts, faces, nf, nv, mm, normalize, features);
+  FGC_LAUNCHED("face_features_kernel");
   return FGC_OK;
 }
 

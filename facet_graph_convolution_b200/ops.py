@@ -510,3 +510,16 @@ def build_edge_maps(faces, max_edges=20, nv=None):
         check(L.fgc_build_edge_maps(_p(faces), nf, nv, int(max_edges), _p(e_map), C.byref(ne), _p(v_e), _p(ws),
                                     ws.numel(), _stream(faces)), "fgc_build_edge_maps")
     return e_map[: int(ne.value)], v_e
+
+
+def face_features(verts, faces, normalize=True):
+    """[unit normal | barycentre / bbox diagonal] per face (reference Code/utils.py:63-68, 1264-1294)."""
+    L = _lib.lib()
+    verts = _f32(verts, "verts")
+    faces = _i32(faces, "faces")
+    out = torch.empty((faces.shape[0], 6), dtype=torch.float32, device=verts.device)
+    with torch.cuda.device(verts.device):
+        ws = _ws(1024, verts)
+        check(L.fgc_face_features(_p(verts), _p(faces), faces.shape[0], verts.shape[0], int(bool(normalize)), _p(out),
+                                  _p(ws), ws.numel(), _stream(verts)), "fgc_face_features")
+    return out

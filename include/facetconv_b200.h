@@ -254,6 +254,12 @@ FGC_API int fgc_vertex_update_ms(const float* x_in, float* x_out, const float* n
  * first appearance over faces and slots (v1v2, v1v3, v2v3), va/vb as in that first appearance, and
  * v_edges[nv][max_edges] = edge ids around each vertex, increasing, -1 padded (getEdgeMap,
  * Code/utils.py:91-183).  e_map must hold 3*nf rows; *num_edges (host) receives E.  Synchronises. */
+/* features[nf][6] = [unit face normal | barycentre of the vertices divided by the bounding-box diagonal]
+ * (reference computeFacesNormals Code/utils.py:63-68 with the two-pass normalize of :26-35, and
+ * getTrianglesBarycenter :1264-1294; double arithmetic like the reference's NumPy, one rounding to fp32);
+ * rows of faces with an id outside 0..nv-1 (fake nodes) get zeros.  workspace: 1 KB. */
+FGC_API int fgc_face_features(const float* verts, const int32_t* faces, int64_t nf, int64_t nv, int normalize,
+                      float* features, void* workspace, size_t workspace_bytes, void* stream);
 FGC_API size_t fgc_faces_adj_workspace(int64_t nf, int64_t nv);
 FGC_API int fgc_build_faces_adj(const int32_t* faces, int64_t nf, int64_t nv, int K, int32_t* adj,
                         int32_t* v_faces, int kv, void* workspace, size_t workspace_bytes, void* stream);

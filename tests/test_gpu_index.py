@@ -56,3 +56,17 @@ def test_fake_rows_and_errors():
         ops.build_faces_adj(T(F), kv=2)                                # a vertex has more than 2 faces
     with pytest.raises(_lib.FacetConvError):
         ops.build_faces_adj(T(F), K=16, nv=5)                          # vertex ids outside 0..nv-1
+
+
+def test_face_features_match_float64_reference_arithmetic():
+    """normal | barycentre/diag rows: the reference computes them in float64 NumPy; tolerance 1e-6 on O(1) values."""
+    from facet_graph_convolution_b200 import mesh, ops
+    V, F = mesh.icosphere(3)
+    V = mesh.add_vertex_noise(V, F, 0.3, 1).astype(np.float32)
+    F = np.asarray(F, np.int32)
+    got = ops.face_features(T(V), T(F)).cpu().numpy()
+    ref = mesh.face_features(V.astype(np.float64), F)
+    assert np.abs(got - ref).max() < 1e-6
+    Fp = np.concatenate([F, np.full((4, 3), -1, np.int32)])
+    gp = ops.face_features(T(V), T(Fp)).cpu().numpy()
+    assert np.array_equal(gp[: F.shape[0]], got) and not gp[F.shape[0]:].any()
