@@ -1,0 +1,276 @@
+// Fused regression head on tcgen05: y = lrelu(x W1 + b1) W2 + b2 with x[rows,32], W1[32,1024], W2[1024,3]
+// (reference Code/model.py:936-941 through custom_lin :763-769; 72 KFLOP per facet, the largest single FLOP
+// item of the network).  The 1024-wide hidden activation never leaves the SM.
+//
+// One persistent CTA per SM, tiles of 128 rows, 9 warps:
+//   warps 4-7  producers: thread = row.  The row is scaled by its own power of two (the scale is a per-lane
+//              factor of the accumulator, undone in the epilogue) and split into fp16 hi + fp16 residual,
+//              written as the K-major 128B-swizzled A operand (K = 32: the first 64 bytes of every row).
+//   warp  8    MMA issuer: per tile and chunk of 256 hidden units  D[128 x 256] = Ah.Bh + Al.Bh + Ah.Bl
+//              (tcgen05.mma kind::f16, M = 128, N = 256, two k-steps each; fp32 accumulation in TMEM).
+//              B = the resident fp16 hi/lo image of W1^T (512 hidden units per launch: 128 KB of shared memory).
+//   warps 0-3  epilogue: tcgen05.ld of the chunk, h = lrelu(scale * d + b1), three FMAs per hidden unit
+//              into the row's outputs; the two chunk accumulators ping-pong, so the MMAs of the next tile run
+//              under the epilogue of this one.
+// The 1024 hidden units are two launches of 512 (the weight image of all 1024 does not fit shared memory):
+// the first writes y = b2 + partial, the second adds its partial.
+#include "conv_common.cuh"
+#include "conv_launch.cuh"
+#include "tc_common.cuh"
+
+namespace fgc {
+
+namespace {
+
+constexpr int kHK = 32;          // input channels (MMA K)
+constexpr int kHH = 1024;        // hidden units
+constexpr int kHPass = 512;      // hidden units per launch
+constexpr int kHChunk = 256;     // hidden units per MMA (N)
+constexpr int kHTile = 128;      // rows per tile
+constexpr int kHThreads = 9 * 32;
+
+struct HeadCfg {
+  static constexpr int B_PLANE = kHPass * 128;             // [512 rows = hidden units][64 K halves], 32 used
+  static constexpr int A_PLANE = kHTile * 128;
+  static constexpr int OFF_B = 0;                          // hi | lo
+  static constexpr int OFF_A = OFF_B + 2 * B_PLANE;        // 2 buffers x (hi | lo)
+  static constexpr int OFF_PRM = OFF_A + 4 * A_PLANE;      // [512] float4 (b1, W2[.,0], W2[.,1], W2[.,2])
+  static constexpr int OFF_RS = OFF_PRM + kHPass * 16;     // [4][128] row un-scales
+  static constexpr int OFF_BAR = OFF_RS + 4 * kHTile * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
+};
+static_assert(HeadCfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+
+enum { H_A_FULL = 0, H_A_FREE = 2, H_D_FULL = 4, H_D_FREE = 6, H_NUM = 8 };
+
+struct HeadParams {
+  const float* x;
+  const uint4* wimg;       // this pass: hi plane then lo plane, B_PLANE bytes each, already swizzled
+  const float* wunscale;
+  const float* b1;         // + pass offset
+  const float* W2;         // [1024][3], + pass offset rows
+  const float* b2;
+  float* y;
+  int64_t rows, ntiles;
+  int accumulate;          // second pass: y += partial
+  float alpha;
+};
+
+__global__ void __launch_bounds__(kHThreads, 1)
+mlp_head_tc_kernel(const HeadParams p) {
+  using Cfg = HeadCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + H_NUM);
+  float4* prm = reinterpret_cast<float4*>(smem + Cfg::OFF_PRM);
+  float* rs = reinterpret_cast<float*>(smem + Cfg::OFF_RS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bars[H_A_FULL + i], 4), tc::mbar_init(&bars[H_A_FREE + i], 1);
+      tc::mbar_init(&bars[H_D_FULL + i], 1), tc::mbar_init(&bars[H_D_FREE + i], 4);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+  {
+    uint4* dst = reinterpret_cast<uint4*>(smem + Cfg::OFF_B);
+    for (int i = threadIdx.x; i < 2 * Cfg::B_PLANE / 16; i += kHThreads) dst[i] = __ldg(p.wimg + i);
+    // rows of A beyond K = 32 are never read; zero them once so that no NaN pattern sits in the operand
+    uint4* az = reinterpret_cast<uint4*>(smem + Cfg::OFF_A);
+    for (int i = threadIdx.x; i < 4 * Cfg::A_PLANE / 16; i += kHThreads) az[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < kHPass; i += kHThreads)
+      prm[i] = make_float4(__ldg(p.b1 + i), __ldg(p.W2 + 3 * i), __ldg(p.W2 + 3 * i + 1), __ldg(p.W2 + 3 * i + 2));
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // =========================================================== epilogue
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const int row = warp * 32 + lane;
+    const float wun = __ldg(p.wunscale);
+    const float b20 = __ldg(p.b2), b21 = __ldg(p.b2 + 1), b22 = __ldg(p.b2 + 2);
+    int t = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      float sc = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        tc::mbar_wait(&bars[H_D_FULL + c], t & 1);
+        tc::tc_fence_after_sync();
+        if (c == 0) sc = rs[(t & 3) * kHTile + row] * wun;
+#pragma unroll 1
+        for (int j = 0; j < kHChunk / 32; ++j) {
+          uint32_t d[32];
+          tc::tmem_ld32(tmem + lane_base + c * kHChunk + j * 32, d);
+          tc::tc_wait_ld();
+          if (j == kHChunk / 32 - 1) {
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bars[H_D_FREE + c]);
+          }
+          const float4* pp = prm + c * kHChunk + j * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 q = pp[i];
+            const float h = lrelu_f(fmaf(__uint_as_float(d[i]), sc, q.x), p.alpha);
+            a0 = fmaf(h, q.y, a0), a1 = fmaf(h, q.z, a1), a2 = fmaf(h, q.w, a2);
+          }
+        }
+      }
+      const int64_t r = tile * kHTile + row;
+      if (r < p.rows) {
+        float* yr = p.y + 3 * r;
+        if (p.accumulate) yr[0] += a0, yr[1] += a1, yr[2] += a2;
+        else yr[0] = a0 + b20, yr[1] = a1 + b21, yr[2] = a2 + b22;
+      }
+    }
+  } else if (warp < 8) {
+    // =========================================================== producers: thread = row
+    const int row = (warp - 4) * 32 + lane;
+    int t = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+      const int b = t & 1;
+      const int64_t r = tile * kHTile + row;
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = (r < p.rows) ? __ldg(reinterpret_cast<const float4*>(p.x + r * kHK) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+      int E = (__float_as_int(mx) >> 23) & 0xFF;
+      E = min(max(E, 16), 240);
+      const float sc = __int_as_float((267 - E) << 23);   // 2^(140-E): |x| sc in [2^13, 2^14)
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float f[4] = {v[i].x * sc, v[i].y * sc, v[i].z * sc, v[i].w * sc};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const __half2 hh = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(f[2 * k] - hf.x, f[2 * k + 1] - hf.y);
+          hi[2 * i + k] = *reinterpret_cast<const uint32_t*>(&hh);
+          lo[2 * i + k] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+      }
+      tc::mbar_wait(&bars[H_A_FREE + b], ((t >> 1) & 1) ^ 1);
+      uint8_t* ah = smem + Cfg::OFF_A + b * 2 * Cfg::A_PLANE + (row >> 3) * 1024 + (row & 7) * 128;
+      uint8_t* al = ah + Cfg::A_PLANE;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        *reinterpret_cast<uint4*>(ah + ((u ^ (row & 7)) << 4)) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+        *reinterpret_cast<uint4*>(al + ((u ^ (row & 7)) << 4)) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+      }
+      rs[(t & 3) * kHTile + row] = __int_as_float((E - 13) << 23);   // 2^(E-140)
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[H_A_FULL + b]);
+    }
+  } else {
+    // =========================================================== MMA issuer
+    constexpr uint32_t idesc = tc::idesc_f16(128, kHChunk);
+    const uint32_t sb = tc::smem_u32(smem);
+    int t = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+      const int b = t & 1;
+      tc::mbar_wait(&bars[H_A_FULL + b], (t >> 1) & 1);
+      const uint32_t ah = sb + Cfg::OFF_A + b * 2 * Cfg::A_PLANE, al = ah + Cfg::A_PLANE;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        tc::mbar_wait(&bars[H_D_FREE + c], (t & 1) ^ 1);
+        tc::tc_fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t bh = sb + Cfg::OFF_B + c * kHChunk * 128, bl = bh + Cfg::B_PLANE;
+          const uint32_t d = tmem + c * kHChunk;
+#pragma unroll
+          for (int ks = 0; ks < kHK / 16; ++ks) {
+            const uint64_t dah = tc::smem_desc_k_sw128(ah + ks * 32), dal = tc::smem_desc_k_sw128(al + ks * 32);
+            const uint64_t dbh = tc::smem_desc_k_sw128(bh + ks * 32), dbl = tc::smem_desc_k_sw128(bl + ks * 32);
+            tc::mma_f16_ss(d, dah, dbh, idesc, ks ? 1u : 0u);
+            tc::mma_f16_ss(d, dal, dbh, idesc, 1u);
+            tc::mma_f16_ss(d, dah, dbl, idesc, 1u);
+          }
+          tc::tc_commit(&bars[H_D_FULL + c]);
+          if (c == 1) tc::tc_commit(&bars[H_A_FREE + b]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+// image of W1^T for both passes: pass p, plane (hi, lo): [512 hidden units][128 B], K-major, 128B swizzle;
+// values W1[k][512 p + n] * 2^(140 - E) with E the exponent of max|W1| (hi < 2^14, residual in the normal range)
+__global__ void __launch_bounds__(1024)
+prep_head_w_kernel(const float* __restrict__ W1, uint16_t* __restrict__ img, float* __restrict__ wunscale) {
+  __shared__ float red[32];
+  float mx = 0.f;
+  for (int e = threadIdx.x; e < kHK * kHH; e += blockDim.x) mx = fmaxf(mx, fabsf(W1[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  int E = (__float_as_int(mx) >> 23) & 0xFF;
+  E = min(max(E, 16), 240);
+  const float sc = __int_as_float((267 - E) << 23);
+  if (threadIdx.x == 0 && blockIdx.x == 0) wunscale[0] = __int_as_float((E - 13) << 23);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kHK * kHH; e += gridDim.x * blockDim.x) {
+    const int k = e / kHH, hcol = e % kHH;           // coalesced read of W1[k][.]
+    const int pass = hcol / kHPass, n = hcol % kHPass;
+    const float v = W1[e] * sc;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const size_t plane_halves = static_cast<size_t>(kHPass) * 64;
+    const size_t off = static_cast<size_t>(pass) * 2 * plane_halves + (n >> 3) * 512 + (n & 7) * 64 +
+                       (((k >> 3) ^ (n & 7)) << 3) + (k & 7);
+    img[off] = __half_as_ushort(h);
+    img[off + plane_halves] = __half_as_ushort(l);
+  }
+}
+
+}  // namespace
+
+bool mlp_head_tc_supported(int64_t rows, int Cin, int H, int Cout) {
+  static const bool disabled = getenv("FGC_DISABLE_TC") != nullptr;
+  return !disabled && Cin == kHK && H == kHH && Cout == 3 && rows >= 2048;
+}
+
+size_t mlp_head_tc_workspace() { return 2 * 2 * static_cast<size_t>(HeadCfg::B_PLANE) + 1024; }
+
+int launch_mlp_head_tc(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* y,
+                       int64_t rows, float alpha, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  Workspace ws(workspace, workspace_bytes);
+  char* img = ws.take<char>(2 * 2 * static_cast<size_t>(HeadCfg::B_PLANE));
+  float* wunscale = ws.take<float>(4);
+  FGC_REQUIRE(ws.ok(), "mlp_head: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              mlp_head_tc_workspace());
+  prep_head_w_kernel<<<16, 1024, 0, st>>>(W1, reinterpret_cast<uint16_t*>(img), wunscale);
+  FGC_LAUNCHED("prep_head_w_kernel");
+  FGC_CUDA(cudaFuncSetAttribute(mlp_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg::SMEM_BYTES));
+  HeadParams p{};
+  p.x = x, p.wunscale = wunscale, p.b2 = b2, p.y = y, p.rows = rows, p.alpha = alpha;
+  p.ntiles = (rows + kHTile - 1) / kHTile;
+  int64_t grid = num_sms();
+  if (grid > p.ntiles) grid = p.ntiles;
+  for (int pass = 0; pass < kHH / kHPass; ++pass) {
+    p.wimg = reinterpret_cast<const uint4*>(img + static_cast<size_t>(pass) * 2 * HeadCfg::B_PLANE);
+    p.b1 = b1 + pass * kHPass, p.W2 = W2 + static_cast<size_t>(pass) * kHPass * 3, p.accumulate = pass > 0;
+    mlp_head_tc_kernel<<<static_cast<unsigned>(grid), kHThreads, HeadCfg::SMEM_BYTES, st>>>(p);
+    FGC_LAUNCHED("mlp_head_tc_kernel");
+  }
+  return FGC_OK;
+}
+
+}  // namespace fgc
