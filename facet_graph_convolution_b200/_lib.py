@@ -71,7 +71,8 @@ SIGNATURES = {
     "fgc_lin_fwd": (i32, [p, p, p, p, i64, i32, i32, i32, f32, p]),
     "fgc_lin_bwd": (i32, [p, p, p, p, p, p, i64, i32, i32, p, sz, p]),
     "fgc_lin_bwd_workspace": (sz, [i64, i32, i32]),
-    "fgc_mlp_head_fwd": (i32, [p, p, p, p, p, p, i64, i32, i32, i32, f32, p]),
+    "fgc_mlp_head_workspace": (sz, [i64, i32, i32, i32]),
+    "fgc_mlp_head_fwd": (i32, [p, p, p, p, p, p, i64, i32, i32, i32, f32, p, sz, p]),
     "fgc_normalize_workspace": (sz, [i64]),
     "fgc_normalize_rows": (i32, [p, p, i64, p, sz, p]),
     "fgc_normalize_rows_bwd": (i32, [p, p, p, i64, p, sz, p]),

@@ -104,5 +104,10 @@ int build_reverse_adj(const int32_t* adj, int B, int N, int K, int32_t* rev_ptr,
                       int64_t* nnz_out, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_reduce_partials(const float* part, float* out, int64_t n, int P, int64_t stride,
                            cudaStream_t st);
+// fused regression head on tcgen05 (lin_tc.cu)
+bool mlp_head_tc_supported(int64_t rows, int Cin, int H, int Cout);
+size_t mlp_head_tc_workspace();
+int launch_mlp_head_tc(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* y,
+                       int64_t rows, float alpha, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace fgc

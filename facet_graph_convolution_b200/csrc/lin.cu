@@ -284,13 +284,19 @@ int fgc_lin_fwd(const float* x, const float* W, const float* b, float* y, int64_
   return FGC_OK;
 }
 
+size_t fgc_mlp_head_workspace(int64_t rows, int Cin, int H, int Cout) {
+  return mlp_head_tc_supported(rows, Cin, H, Cout) ? mlp_head_tc_workspace() : 0;
+}
+
 int fgc_mlp_head_fwd(const float* x, const float* W1, const float* b1, const float* W2,
                      const float* b2, float* y, int64_t rows, int Cin, int H, int Cout, float alpha,
-                     void* stream) {
+                     void* workspace, size_t workspace_bytes, void* stream) {
   FGC_REQUIRE(x && W1 && b1 && W2 && b2 && y && rows >= 0 && Cin > 0 && H > 0 && Cout > 0,
               "mlp_head_fwd: bad arguments");
   FGC_UNSUPPORTED(Cout > kHeadMaxOut, "mlp_head_fwd: Cout <= %d supported", kHeadMaxOut);
   if (rows == 0) return FGC_OK;
+  if (mlp_head_tc_supported(rows, Cin, H, Cout))
+    return launch_mlp_head_tc(x, W1, b1, W2, b2, y, rows, alpha, workspace, workspace_bytes, as_stream(stream));
   const size_t smem = (static_cast<size_t>(kTileFacets) * ((Cin + 3) & ~3) + kChunkK * 128 +
                        kTileFacets * 32 * kHeadMaxOut) * 4;
   FGC_UNSUPPORTED(smem > 227 * 1024, "mlp_head_fwd: Cin = %d too large", Cin);

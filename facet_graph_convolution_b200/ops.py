@@ -391,8 +391,9 @@ def mlp_head(x, W1, b1, W2, b2, alpha=0.1):
     rows = x.numel() // Cin
     y = torch.empty(tuple(x.shape[:-1]) + (Cout,), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
+        ws = _ws(L.fgc_mlp_head_workspace(rows, Cin, H, Cout), x)
         check(L.fgc_mlp_head_fwd(_p(x), _p(W1), _p(b1), _p(W2), _p(b2), _p(y), rows, Cin, H, Cout, float(alpha),
-                                 _stream(x)), "fgc_mlp_head_fwd")
+                                 _p(ws), ws.numel(), _stream(x)), "fgc_mlp_head_fwd")
     return y
 
 

@@ -199,10 +199,13 @@ FGC_API int fgc_lin_bwd(const float* gy, const float* x, const float* W, float* 
                 void* stream);
 FGC_API size_t fgc_lin_bwd_workspace(int64_t rows, int Cin, int Cout);
 /* fused regression head (model.py:936-941): y = lrelu(x@W1+b1) @ W2 + b2 without materialising
- * the hidden activation.  W1[Cin,H], W2[H,Cout], Cout <= 4. */
+ * the hidden activation.  W1[Cin,H], W2[H,Cout], Cout <= 4.  The network's shape (Cin = 32, H = 1024,
+ * Cout = 3) runs on tcgen05 from 2 048 rows on and then needs fgc_mlp_head_workspace() bytes for the
+ * fp16 image of W1; workspace may be NULL otherwise. */
+FGC_API size_t fgc_mlp_head_workspace(int64_t rows, int Cin, int H, int Cout);
 FGC_API int fgc_mlp_head_fwd(const float* x, const float* W1, const float* b1, const float* W2,
                      const float* b2, float* y, int64_t rows, int Cin, int H, int Cout, float alpha,
-                     void* stream);
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- output normalisation & loss
  * reference Code/utils.py:1700-1715 (normalizeTensor) over x[rows,3] of ONE patch: global
