@@ -102,6 +102,8 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
                     int bias_mask, int act, float alpha, void* workspace, size_t workspace_bytes,
                     cudaStream_t st, const void* plan = nullptr) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  if (conv_fwd_small_supported(s))   // the 6 -> 32 input layer: thread per facet, logits inline, no workspace
+    return launch_conv_fwd_small(s, x, adj, W0, b, u, v, c, y, bias_mask, act, alpha, st);
   Workspace ws(workspace, workspace_bytes);
   float* uvx = ws.take<float>(rows * 2 * s->M);
   float* Wt = ws.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);

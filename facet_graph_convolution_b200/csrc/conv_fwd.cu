@@ -238,6 +238,128 @@ int launch_conv_fwd(const ConvFwdParams& p, cudaStream_t st) {
   return FGC_OK;
 }
 
+// ------------------------------------------------------------------ narrow input layer (thread per facet)
+// The network's first layer (6 -> 32, M = 9: reference Code/model.py:858) gathers 24-byte rows: a warp per
+// facet leaves 26 of 32 lanes idle in the aggregation.  Here one thread owns one facet end to end -- own and
+// neighbour logits inline (no uvx pre-pass), softmax, s[M][CIN] in registers, contraction against a
+// transposed weight image in shared memory read by broadcast -- same arithmetic order per facet for every
+// launch geometry.
+template <int M, int CIN, int COUT>
+__global__ void __launch_bounds__(128)
+conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ adj, const float* __restrict__ W0,
+                      const float* __restrict__ b, const float* __restrict__ u, const float* __restrict__ v,
+                      const float* __restrict__ c, float* __restrict__ y, int64_t rows, int N, int K, int bias_mask,
+                      int act, float alpha) {
+  __shared__ __align__(16) float Wt[M * CIN * COUT];   // [(m, c)][o]
+  __shared__ float us[M * CIN], vs[M * CIN], cs[M];
+  for (int e = threadIdx.x; e < M * CIN * COUT; e += blockDim.x) {
+    const int o = e % COUT, mc = e / COUT;
+    Wt[e] = W0[(static_cast<size_t>(mc / CIN) * COUT + o) * CIN + mc % CIN];
+  }
+  for (int e = threadIdx.x; e < M * CIN; e += blockDim.x) us[e] = u[e], vs[e] = v[e];
+  if (threadIdx.x < M) cs[threadIdx.x] = c[threadIdx.x];
+  __syncthreads();
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t base = (r / N) * N;
+    float xn[CIN], own[M], s[M][CIN];
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) xn[i] = __ldg(x + r * CIN + i);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float a = cs[m];
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) a = fmaf(us[m * CIN + i], xn[i], a);
+      own[m] = a;
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) s[m][i] = 0.f;
+    }
+    int cnt = 0;
+    for (int k = 0; k < K; ++k) {
+      const int id = __ldg(adj + r * K + k);
+      if (id == 0) continue;          // padding: contributes nothing and is not counted
+      ++cnt;
+      if (id < 0 || id > N) continue; // id outside the patch: a counted neighbour that contributes zero
+      const float* xr = x + (base + id - 1) * CIN;
+      float xj[CIN];
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) xj[i] = __ldg(xr + i);
+      float q[M];
+      float mx = -3.4e38f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        float a = own[m];
+#pragma unroll
+        for (int i = 0; i < CIN; ++i) a = fmaf(vs[m * CIN + i], xj[i], a);
+        q[m] = a;
+        mx = fmaxf(mx, a);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        q[m] = __expf(q[m] - mx);
+        sum += q[m];
+      }
+      const float rs = 1.f / sum;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float qq = q[m] * rs;
+#pragma unroll
+        for (int i = 0; i < CIN; ++i) s[m][i] = fmaf(qq, xj[i], s[m][i]);
+      }
+    }
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) {
+        const float sv = s[m][i];
+        const float4* wr = reinterpret_cast<const float4*>(Wt + (m * CIN + i) * COUT);
+#pragma unroll
+        for (int o4 = 0; o4 < COUT / 4; ++o4) {
+          const float4 w = wr[o4];
+          acc[4 * o4] = fmaf(sv, w.x, acc[4 * o4]), acc[4 * o4 + 1] = fmaf(sv, w.y, acc[4 * o4 + 1]);
+          acc[4 * o4 + 2] = fmaf(sv, w.z, acc[4 * o4 + 2]), acc[4 * o4 + 3] = fmaf(sv, w.w, acc[4 * o4 + 3]);
+        }
+      }
+    const float inv = cnt ? 1.f / static_cast<float>(cnt) : 0.f;
+    const float fl = (cnt > 0 || !bias_mask) ? 1.f : 0.f;
+    float4* yr = reinterpret_cast<float4*>(y + r * COUT);
+#pragma unroll
+    for (int o4 = 0; o4 < COUT / 4; ++o4) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float yv = fmaf(inv, acc[4 * o4 + j], fl * __ldg(b + 4 * o4 + j));
+        if (act == FGC_ACT_LRELU) yv = lrelu_f(yv, alpha);
+        o[j] = yv;
+      }
+      yr[o4] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+bool conv_fwd_small_supported(const fgc_conv_shape* s) {
+  static const bool disabled = getenv("FGC_DISABLE_SMALL") != nullptr;
+  return !disabled && s->M == 9 && s->Cin == 6 && s->Cw == 6 && s->Ca0 == 0 && s->Ca == 6 && s->Cout == 32;
+}
+
+int launch_conv_fwd_small(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0, const float* b,
+                          const float* u, const float* v, const float* c, float* y, int bias_mask, int act,
+                          float alpha, cudaStream_t st) {
+  const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  int64_t blocks = (rows + 127) / 128;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  conv_fwd_small_kernel<9, 6, 32><<<static_cast<unsigned>(blocks), 128, 0, st>>>(x, adj, W0, b, u, v, c, y, rows, s->N,
+                                                                               s->K, bias_mask, act, alpha);
+  FGC_LAUNCHED("conv_fwd_small_kernel");
+  return FGC_OK;
+}
+
 // ------------------------------------------------------------------ debug / parity helpers
 __global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ adj,
                                    float* __restrict__ out, int64_t rows, int N, int K, int C) {

@@ -37,6 +37,10 @@ int launch_gather_rows(const float* x, const int32_t* adj, float* out, int64_t r
 // tensor-core (tcgen05) forward for the dense shapes
 bool conv_fwd_tc_supported(int Cw, int Cout, int M, int K);
 size_t conv_fwd_tc_workspace(int Cout, int M, int Cw = 64);
+bool conv_fwd_small_supported(const fgc_conv_shape* s);
+int launch_conv_fwd_small(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0, const float* b,
+                          const float* u, const float* v, const float* c, float* y, int bias_mask, int act,
+                          float alpha, cudaStream_t st);
 int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st);
 bool bwd_tgt_tc_supported(int Cw, int Cout, int M);
 int launch_bwd_tgt_tc(const float* gy, const float* uvx, const float* W0, const float* da_edge,
