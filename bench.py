@@ -171,6 +171,17 @@ def cpu_reference_run(steps, warmup, sample_facets, adjacency_kind):
     return n * steps / dt, dt / steps * 1e3, n, cores
 
 
+def cpu_net_reference(x, adjs, params, repeat=1):
+    """cpu_baseline leg of the network-level runs (benchmarks/net_bench.py): seconds per forward of the
+    oracle's closed form of the reference network (Code/model.py:837-946) in fp32 NumPy, all BLAS threads."""
+    from oracle import closed_form as cf
+    pd = cf.split_net_params(params)
+    t0 = time.perf_counter()
+    for _ in range(repeat):
+        cf.net_forward(x[None].astype(np.float32), [a[None] for a in adjs], pd, dtype=np.float32)
+    return (time.perf_counter() - t0) / repeat
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()

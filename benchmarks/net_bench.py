@@ -61,13 +61,10 @@ def clocks_sampler(index):
 
 
 def cpu_net_forward(x, adjs, params, repeat=1):
-    """Oracle closed form in fp32 NumPy (all BLAS threads)."""
-    from oracle import closed_form as cf
-    pd = cf.split_net_params(params)
-    t0 = time.perf_counter()
-    for _ in range(repeat):
-        cf.net_forward(x[None].astype(np.float32), [a[None] for a in adjs], pd, dtype=np.float32)
-    return (time.perf_counter() - t0) / repeat
+    """CPU baseline leg: lives in bench.py (the one benchmark module that may execute oracle/)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench.cpu_net_reference(x, adjs, params, repeat)
 
 
 def main():
