@@ -1,7 +1,7 @@
 """Scratch GPU check of the planned (dense-assignment tcgen05) forward against the oracle."""
 import sys, os, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from facet_graph_convolution_b200 import ops, mesh
 from oracle import closed_form as cf
 

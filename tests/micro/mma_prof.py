@@ -1,7 +1,7 @@
 """Scratch: planned forward at C2 scale, per-kernel times via the library profiler."""
 import sys, os, ctypes as C
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from facet_graph_convolution_b200 import ops, mesh, _lib
 dev = torch.device("cuda:0")
 T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
