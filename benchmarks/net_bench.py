@@ -77,6 +77,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4, help="c4: patches per rank per step")
     ap.add_argument("--patch-batch", type=int, default=10, help="c3: patches per launch (1 = the reference's B=1)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="c1: also time the step replayed from a CUDA graph")
     ap.add_argument("--profile", action="store_true", help="per-kernel CUDA-event times of one forward (library profiler)")
     args = ap.parse_args()
 
@@ -158,6 +159,31 @@ def main():
         launches = (L.fgc_launch_count() - n0) / args.steps
         clocks = smp.result()
         ms_net, ms_all = float(np.median(tf)), float(np.median(ts))
+        if args.graph:
+            # the whole step (all layer launches + 60 vertex sweeps) captured once and replayed: the kernels are
+            # the same, only the launch gaps between ~150 small kernels go away
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                n_g, xo_g = step()
+            n_e, xo_e = step()
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(n_g, n_e) and torch.equal(xo_g, xo_e), "graph replay differs from the eager step"
+            tg = []
+            for _ in range(args.steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                tg.append(e0.elapsed_time(e1))
+            line["cuda_graph_ms_per_step"] = float(np.median(tg))
+            line["cuda_graph_facets_per_s"] = nreal / (float(np.median(tg)) * 1e-3)
         cpu = None
         if not args.no_cpu:
             dt = cpu_net_forward(feat, adjs, params)
