@@ -23,6 +23,7 @@
 // 16-17 row loaders (cp.async, alternate chunks), 18 stage-1 MMA issuer, 19 stage-2 MMA issuer.
 #include "conv_common.cuh"
 #include "conv_launch.cuh"
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
 #include <type_traits>
@@ -55,6 +56,22 @@ __device__ __forceinline__ void cp_async_wait() {
 // the mbarrier receives one (pre-counted) arrival when all cp.async of this thread so far have landed
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// TMA gather of four rows of the fp16 image (2-D tensor map: 128 halves per row = hi plane | lo plane, box
+// 64 x 1, 128-byte swizzle): rows r0..r3 of plane `col` (0 or 64) land as four consecutive swizzled 128-byte
+// rows at dst; 512 bytes are counted on the mbarrier.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int col, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(tc::smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
 // MN-major, 128-byte-swizzled operand descriptor (rows of 64 MN elements = 128 B, 8-row K groups)
@@ -108,6 +125,8 @@ struct MCfg {
 };
 
 struct MmaParams {
+  CUtensorMap tmap;        // 2-D map of img for the TMA row gather (use_tma)
+  int use_tma;
   const uint4* img;        // [rows][16]: 8 x 16 B hi | 8 x 16 B lo (fp16, scaled by 2^-ex)
   const float* xunscale;   // 2^ex
   const float* uvx;        // [rows][2M]
@@ -162,9 +181,9 @@ __device__ long long g_mma_trace[4 * 32 * 8];
 
 __device__ __forceinline__ int chunks_of(int R) { return R <= kRC ? 1 : (R + kRC - 1) / kRC; }
 
-template <int M, int COUT, int KP>
+template <int M, int COUT, int KP, bool TMA>
 __global__ void __launch_bounds__(kMmaThreads, 1)
-conv_mma_kernel(const MmaParams p) {
+conv_mma_kernel(const __grid_constant__ MmaParams p) {
   using Cfg = MCfg<M, COUT>;
   constexpr int TF = Cfg::TF;
   constexpr int NX = Cfg::NX;
@@ -581,7 +600,7 @@ conv_mma_kernel(const MmaParams p) {
     auto issue = [&](const int (&cur)[2], int (&nxt)[2]) {
       // my next item is two steps ahead
       const int64_t tile0 = tile;
-      const int c0 = c, it0 = it;
+      const int c0 = c, it0 = it, R0 = R;
       advance();
       if (tile < p.ntiles) advance();
       load_ids(tile, c, R, nxt);
@@ -590,15 +609,33 @@ conv_mma_kernel(const MmaParams p) {
       tc::mbar_wait(&bars[B_X_FREE + buf], ((it0 / NX) & 1) ^ 1);
       if (me == 0) FGC_TR(2, it0 >> 1, 1);
       const uint32_t sl = xbase + buf * Cfg::X_BUF;
+      if constexpr (TMA) {
+        // row planes by TMA gather: lane j < 16 fetches rows 4j .. 4j+3 of the chunk (their ids are the
+        // L1-hot words load_ids read one item ago), hi plane then lo plane, 512 bytes each
+        const int rc0 = min(kRC, R0 - c0 * kRC);
+        if (lane < 16 && 4 * lane < rc0) {
+          int4 r4 = __ldg(reinterpret_cast<const int4*>(p.prow + tile0 * P + c0 * kRC) + lane);
+          const int nv = rc0 - 4 * lane;           // rows past the end repeat the first one (zero columns of Q)
+          if (nv < 2) r4.y = r4.x;
+          if (nv < 3) r4.z = r4.x;
+          if (nv < 4) r4.w = r4.x;
+          const uint32_t dst = sl + (lane >> 1) * 1024 + (lane & 1) * 512;
+          mbar_expect_tx(&bars[B_X_FULL + buf], 1024);
+          tma_gather4(dst, &p.tmap, &bars[B_X_FULL + buf], 0, r4.x, r4.y, r4.z, r4.w);
+          tma_gather4(dst + Cfg::X_PLANE, &p.tmap, &bars[B_X_FULL + buf], 64, r4.x, r4.y, r4.z, r4.w);
+        }
+      }
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         if (cur[rr] >= 0) {
           const uint4* src = p.img + static_cast<int64_t>(cur[rr]) * 16;
           const uint32_t dst = sl + row_off + rr * 4096;
+          if constexpr (!TMA) {
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            cp_async16(dst + ((cc ^ (lane & 7)) << 4), src + cc);
-            cp_async16(dst + Cfg::X_PLANE + ((cc ^ (lane & 7)) << 4), src + 8 + cc);
+            for (int cc = 0; cc < 8; ++cc) {
+              cp_async16(dst + ((cc ^ (lane & 7)) << 4), src + cc);
+              cp_async16(dst + Cfg::X_PLANE + ((cc ^ (lane & 7)) << 4), src + 8 + cc);
+            }
           }
           const float* vsrc = p.uvx + static_cast<int64_t>(cur[rr]) * (2 * M) + p.vl_off;
           const uint32_t vdst = sl + Cfg::SL_VL + (lane + 32 * rr) * (M * 4);
@@ -934,6 +971,49 @@ int prep_image_reset(void* img_ws, int64_t rows, cudaStream_t st) {
   FGC_CUDA(cudaMemsetAsync(img_ws_views(img_ws, rows).scal, 0, 16 * sizeof(unsigned), st));
   return FGC_OK;
 }
+// ---- tensor map of an image workspace for the TMA row gather
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    if (getenv("FGC_DISABLE_TMA") != nullptr) return nullptr;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+typedef void (*ConvMmaKernel)(const MmaParams);
+static ConvMmaKernel pick_conv_mma_kernel(int K, int tma) {
+  if (tma) return K <= 16 ? conv_mma_kernel<8, 64, 2, true> : (K <= 24 ? conv_mma_kernel<8, 64, 3, true> : conv_mma_kernel<8, 64, 4, true>);
+  return K <= 16 ? conv_mma_kernel<8, 64, 2, false> : (K <= 24 ? conv_mma_kernel<8, 64, 3, false> : conv_mma_kernel<8, 64, 4, false>);
+}
+
+// which passes gather their rows by TMA: bit 0 forward, 1 target pass, 2 weight gradient, 3 source pass
+// (FGC_TMA_MODES overrides the default mask)
+static bool tma_pass_enabled(int bit) {
+  static const int mask = getenv("FGC_TMA_MODES") != nullptr ? atoi(getenv("FGC_TMA_MODES")) : 15;
+  return (mask >> bit) & 1;
+}
+// true when *tm describes img as [rows][128 halves] with a 64 x 1 box and the 128-byte swizzle
+static bool make_img_tmap(CUtensorMap* tm, const void* img, int64_t rows, int pass_bit) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (enc == nullptr || !tma_pass_enabled(pass_bit)) return false;
+  const cuuint64_t gdim[2] = {128, static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstr[1] = {256};
+  const cuuint32_t box[2] = {64, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(img), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st, const float* pinv,
                       int bias_mask, float* partB, bool have_absmax) {
   const ImgWs v = img_ws_views(img_ws, rows);
@@ -973,6 +1053,7 @@ int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, v
   if (rc) return rc;
   MmaParams mp{};
   mp.img = img, mp.xunscale = reinterpret_cast<const float*>(scal + 1), mp.uvx = p.uvx, mp.adj = p.adj;
+  mp.use_tma = make_img_tmap(&mp.tmap, img, p.rows, 0) ? 1 : 0;
   mp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), mp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
   mp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), mp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
   mp.wimg = static_cast<const uint4*>(wimg_ws), mp.wunscale = wunscale, mp.b = p.b, mp.y = p.y;
@@ -981,9 +1062,7 @@ int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, v
   mp.uo_off = 0, mp.vl_off = p.M, mp.inv_src = nullptr, mp.mode = 0;
   static const bool trace = getenv("FGC_MMA_TRACE") != nullptr;
   mp.trace = trace ? 1 : 0;
-  void (*kern)(const MmaParams) = conv_mma_kernel<8, 64, 4>;
-  if (p.K <= 16) kern = conv_mma_kernel<8, 64, 2>;
-  else if (p.K <= 24) kern = conv_mma_kernel<8, 64, 3>;
+  void (*kern)(const MmaParams) = pick_conv_mma_kernel(p.K, mp.use_tma);
   FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   int64_t grid = num_sms();
   if (grid > L.ntiles) grid = L.ntiles;
@@ -1085,6 +1164,7 @@ int launch_bwd_tgt_mma(const float* gy, const float* uvx, const float* da_edge, 
   const size_t wbytes = static_cast<size_t>(M) * 2 * 64 * 128;
   MmaParams mp{};
   mp.img = img, mp.xunscale = reinterpret_cast<const float*>(scal + 1), mp.uvx = uvx, mp.adj = radj;
+  mp.use_tma = make_img_tmap(&mp.tmap, img, rows, 1) ? 1 : 0;
   mp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), mp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
   mp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), mp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
   mp.wimg = static_cast<const uint4*>(wimg);
@@ -1094,9 +1174,7 @@ int launch_bwd_tgt_mma(const float* gy, const float* uvx, const float* da_edge, 
   mp.uo_off = M, mp.vl_off = 0, mp.inv_src = inv, mp.mode = 1;
   static const bool trace = getenv("FGC_MMA_TRACE") != nullptr;
   mp.trace = trace ? 1 : 0;
-  void (*kern)(const MmaParams) = conv_mma_kernel<8, 64, 4>;
-  if (Kr <= 16) kern = conv_mma_kernel<8, 64, 2>;
-  else if (Kr <= 24) kern = conv_mma_kernel<8, 64, 3>;
+  void (*kern)(const MmaParams) = pick_conv_mma_kernel(Kr, mp.use_tma);
   FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   int64_t grid = num_sms();
   if (grid > L.ntiles) grid = L.ntiles;
@@ -1127,6 +1205,7 @@ int launch_bwd_w_mma(const float* uvx, const int32_t* adj, const void* plan, voi
   const ImgWs xi = img_ws_views(ximg_ws, rows), gi = img_ws_views(gyimg_ws, rows);
   MmaParams mp{};
   mp.img = xi.img, mp.xunscale = reinterpret_cast<const float*>(xi.scal + 1), mp.uvx = uvx, mp.adj = adj;
+  mp.use_tma = make_img_tmap(&mp.tmap, xi.img, rows, 2) ? 1 : 0;
   mp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), mp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
   mp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), mp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
   mp.wimg = nullptr, mp.wunscale = nullptr, mp.b = nullptr, mp.y = partW;
@@ -1135,9 +1214,7 @@ int launch_bwd_w_mma(const float* uvx, const int32_t* adj, const void* plan, voi
   mp.uo_off = 0, mp.vl_off = M, mp.inv_src = nullptr, mp.mode = 2;
   mp.gimg = gi.img, mp.gunscale = reinterpret_cast<const float*>(gi.scal + 1);
   mp.trace = 0;
-  void (*kern)(const MmaParams) = conv_mma_kernel<8, 64, 4>;
-  if (K <= 16) kern = conv_mma_kernel<8, 64, 2>;
-  else if (K <= 24) kern = conv_mma_kernel<8, 64, 3>;
+  void (*kern)(const MmaParams) = pick_conv_mma_kernel(K, mp.use_tma);
   FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   kern<<<static_cast<unsigned>(bwd_w_mma_grid(rows, M)), kMmaThreads, Cfg::SMEM_BYTES, st>>>(mp);
   FGC_LAUNCHED("bwd_w_mma_kernel");
@@ -1162,6 +1239,7 @@ int launch_bwd_src_mma(const float* gy, const float* uvx, const int32_t* adj, co
   const size_t wbytes = static_cast<size_t>(M) * 2 * 64 * 128;
   SrcParams sp{};
   sp.img = xi.img, sp.xunscale = reinterpret_cast<const float*>(xi.scal + 1);
+  sp.use_tma = make_img_tmap(&sp.tmap, xi.img, rows, 3) ? 1 : 0;
   (void)gy;   // the stage-A operand is the gy image prepared by launch_prep_image(gy, ...) in gyimg_ws
   sp.gimg = gi.img, sp.gunscale = reinterpret_cast<const float*>(gi.scal + 1);
   sp.uvx = uvx;
@@ -1170,9 +1248,10 @@ int launch_bwd_src_mma(const float* gy, const float* uvx, const int32_t* adj, co
   sp.wimg = static_cast<const uint4*>(wimg);
   sp.wunscale = reinterpret_cast<const float*>(static_cast<const char*>(wimg) + wbytes);
   sp.da_edge = da_edge, sp.d_uvx = d_uvx, sp.rows = rows, sp.ntiles = L.ntiles, sp.N = N, sp.K = K;
-  void (*kern)(const SrcParams) = bwd_src_mma_kernel<8, 4>;
-  if (K <= 16) kern = bwd_src_mma_kernel<8, 2>;
-  else if (K <= 24) kern = bwd_src_mma_kernel<8, 3>;
+  void (*kern)(const SrcParams) = bwd_src_mma_kernel<8, 4, false>;
+  if (sp.use_tma) kern = K <= 16 ? bwd_src_mma_kernel<8, 2, true> : (K <= 24 ? bwd_src_mma_kernel<8, 3, true> : bwd_src_mma_kernel<8, 4, true>);
+  else if (K <= 16) kern = bwd_src_mma_kernel<8, 2, false>;
+  else if (K <= 24) kern = bwd_src_mma_kernel<8, 3, false>;
   FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   int64_t grid = num_sms();
   if (grid > L.ntiles) grid = L.ntiles;

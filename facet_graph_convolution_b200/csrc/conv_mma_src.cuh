@@ -60,6 +60,8 @@ struct SrcCfg {
 };
 
 struct SrcParams {
+  CUtensorMap tmap;        // 2-D map of img for the TMA row gather (use_tma)
+  int use_tma;
   const uint4* img;        // fp16 hi|lo image of x
   const float* xunscale;
   const uint4* gimg;       // fp16 hi|lo image of gy (scaled by 2^-eg)
@@ -94,9 +96,9 @@ enum {
   // still in the previous phase returns at once).
 };
 
-template <int M, int KP>
+template <int M, int KP, bool TMA>
 __global__ void __launch_bounds__(kMmaThreads, 1)
-bwd_src_mma_kernel(const SrcParams p) {
+bwd_src_mma_kernel(const __grid_constant__ SrcParams p) {
   using Cfg = SrcCfg<M>;
   constexpr int TF = Cfg::TF, NX = Cfg::NX;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -411,13 +413,29 @@ bwd_src_mma_kernel(const SrcParams p) {
     if (tile < p.ntiles) load_ids(tile, c, R, ids[0]);
     auto issue = [&](const int (&cur)[2], int (&nxt)[2]) {
       const int64_t tile0 = tile;
-      const int c0 = c, it0 = it;
+      const int c0 = c, it0 = it, R0 = R;
       advance();
       if (tile < p.ntiles) advance();
       load_ids(tile, c, R, nxt);
       const int buf = it0 % NX;
       tc::mbar_wait(&bars[S_X_FREE + buf], ((it0 / NX) & 1) ^ 1);
       const uint32_t sl = xbase + buf * Cfg::X_BUF;
+      if constexpr (TMA) {
+        // row planes by TMA gather (see conv_mma.cu): lane j < 16 fetches rows 4j .. 4j+3 of the chunk
+        const int rc0 = min(kRC, R0 - c0 * kRC);
+        if (lane < 16 && 4 * lane < rc0) {
+          int4 r4 = __ldg(reinterpret_cast<const int4*>(p.prow + tile0 * P + c0 * kRC) + lane);
+          const int nv = rc0 - 4 * lane;
+          if (nv < 2) r4.y = r4.x;
+          if (nv < 3) r4.z = r4.x;
+          if (nv < 4) r4.w = r4.x;
+          const int l = 4 * lane;
+          const uint32_t dh = sl + op_row_off(l);
+          mbar_expect_tx(&bars[S_X_FULL + buf], 1024);
+          tma_gather4(dh, &p.tmap, &bars[S_X_FULL + buf], 0, r4.x, r4.y, r4.z, r4.w);
+          tma_gather4(dh + 2 * 1024, &p.tmap, &bars[S_X_FULL + buf], 64, r4.x, r4.y, r4.z, r4.w);
+        }
+      }
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         if (cur[rr] >= 0) {
@@ -425,10 +443,12 @@ bwd_src_mma_kernel(const SrcParams p) {
           const uint4* src = p.img + static_cast<int64_t>(cur[rr]) * 16;
           const uint32_t dh = sl + op_row_off(l), dl = dh + 2 * 1024;   // lo plane: operand row + 16
           const int sw = (32 * (l >> 4) + (l & 15)) & 7;                 // (row & 7) is the same for row + 16
+          if constexpr (!TMA) {
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            cp_async16(dh + ((cc ^ sw) << 4), src + cc);
-            cp_async16(dl + ((cc ^ sw) << 4), src + 8 + cc);
+            for (int cc = 0; cc < 8; ++cc) {
+              cp_async16(dh + ((cc ^ sw) << 4), src + cc);
+              cp_async16(dl + ((cc ^ sw) << 4), src + 8 + cc);
+            }
           }
           const float* vsrc = p.uvx + static_cast<int64_t>(cur[rr]) * (2 * M) + M;
           const uint32_t vdst = sl + Cfg::SL_VL + l * (M * 4);
