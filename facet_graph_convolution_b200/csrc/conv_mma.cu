@@ -126,7 +126,6 @@ struct MCfg {
 
 struct MmaParams {
   CUtensorMap tmap;        // 2-D map of img for the TMA row gather (use_tma)
-  CUtensorMap tmap_uvx;    // 2-D map of uvx [rows][2M] fp32, box M x 1: logits of four rows per gather
   int use_tma;
   const uint4* img;        // [rows][16]: 8 x 16 B hi | 8 x 16 B lo (fp16, scaled by 2^-ex)
   const float* xunscale;   // 2^ex
@@ -625,24 +624,6 @@ conv_mma_kernel(const __grid_constant__ MmaParams p) {
           tma_gather4(dst, &p.tmap, &bars[B_X_FULL + buf], 0, r4.x, r4.y, r4.z, r4.w);
           tma_gather4(dst + Cfg::X_PLANE, &p.tmap, &bars[B_X_FULL + buf], 64, r4.x, r4.y, r4.z, r4.w);
         }
-        // neighbour logits of the chunk's rows (lanes 16..31, four rows = 128 bytes per gather) and, with chunk
-        // 0, the own logits of the tile's facets (rows past the end of the tensor are zero-filled)
-        static_assert(M == 8 && TF == 16, "logit gathers written for M = 8, 16-facet tiles");
-        if (lane >= 16 && 4 * (lane - 16) < rc0) {
-          const int j = lane - 16;
-          int4 r4 = __ldg(reinterpret_cast<const int4*>(p.prow + tile0 * P + c0 * kRC) + j);
-          const int nv = rc0 - 4 * j;
-          if (nv < 2) r4.y = r4.x;
-          if (nv < 3) r4.z = r4.x;
-          if (nv < 4) r4.w = r4.x;
-          mbar_expect_tx(&bars[B_X_FULL + buf], 128);
-          tma_gather4(sl + Cfg::SL_VL + j * 128, &p.tmap_uvx, &bars[B_X_FULL + buf], p.vl_off, r4.x, r4.y, r4.z, r4.w);
-        }
-        if (c0 == 0 && lane >= 16 && lane < 20) {
-          const int r = static_cast<int>(tile0 * TF) + 4 * (lane - 16);
-          mbar_expect_tx(&bars[B_X_FULL + buf], 128);
-          tma_gather4(sl + Cfg::SL_UO + (lane - 16) * 128, &p.tmap_uvx, &bars[B_X_FULL + buf], p.uo_off, r, r + 1, r + 2, r + 3);
-        }
       }
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
@@ -656,12 +637,10 @@ conv_mma_kernel(const __grid_constant__ MmaParams p) {
               cp_async16(dst + Cfg::X_PLANE + ((cc ^ (lane & 7)) << 4), src + 8 + cc);
             }
           }
-          if constexpr (!TMA) {
-            const float* vsrc = p.uvx + static_cast<int64_t>(cur[rr]) * (2 * M) + p.vl_off;
-            const uint32_t vdst = sl + Cfg::SL_VL + (lane + 32 * rr) * (M * 4);
+          const float* vsrc = p.uvx + static_cast<int64_t>(cur[rr]) * (2 * M) + p.vl_off;
+          const uint32_t vdst = sl + Cfg::SL_VL + (lane + 32 * rr) * (M * 4);
 #pragma unroll
-            for (int q = 0; q < M / 4; ++q) cp_async16(vdst + q * 16, vsrc + q * 4);
-          }
+          for (int q = 0; q < M / 4; ++q) cp_async16(vdst + q * 16, vsrc + q * 4);
           if (p.inv_src != nullptr) cp_async4(sl + Cfg::SL_VI + (lane + 32 * rr) * 4, p.inv_src + cur[rr]);
         }
       }
@@ -669,7 +648,7 @@ conv_mma_kernel(const __grid_constant__ MmaParams p) {
         const uint8_t* src = p.ppair + tile0 * pr_bytes;
         for (int q = lane * 16; q < pr_bytes; q += 512) cp_async16(sl + Cfg::SL_PR + q, src + q);
         const int64_t r = tile0 * TF + (lane >> 1);
-        if (!TMA && (lane >> 1) < TF && r < p.rows)
+        if ((lane >> 1) < TF && r < p.rows)
           cp_async16(sl + Cfg::SL_UO + (lane >> 1) * (M * 4) + (lane & 1) * 16,
                      p.uvx + r * (2 * M) + p.uo_off + (lane & 1) * 4);
       }
@@ -1035,19 +1014,6 @@ static bool make_img_tmap(CUtensorMap* tm, const void* img, int64_t rows, int pa
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// *tm describes uvx as [rows][2M] fp32 with an M x 1 box, no swizzle (four rows of M logits per gather)
-static bool make_uvx_tmap(CUtensorMap* tm, const float* uvx, int64_t rows, int M) {
-  EncodeTiledFn enc = tensor_map_encoder();
-  if (enc == nullptr) return false;
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(2 * M), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(2 * M) * 4};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(M), 1};
-  const cuuint32_t estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(uvx), gdim, gstr, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st, const float* pinv,
                       int bias_mask, float* partB, bool have_absmax) {
   const ImgWs v = img_ws_views(img_ws, rows);
@@ -1087,7 +1053,7 @@ int launch_conv_mma(const ConvFwdParams& p, const float* W0, const void* plan, v
   if (rc) return rc;
   MmaParams mp{};
   mp.img = img, mp.xunscale = reinterpret_cast<const float*>(scal + 1), mp.uvx = p.uvx, mp.adj = p.adj;
-  mp.use_tma = (make_img_tmap(&mp.tmap, img, p.rows, 0) && make_uvx_tmap(&mp.tmap_uvx, p.uvx, p.rows, p.M)) ? 1 : 0;
+  mp.use_tma = make_img_tmap(&mp.tmap, img, p.rows, 0) ? 1 : 0;
   mp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), mp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
   mp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), mp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
   mp.wimg = static_cast<const uint4*>(wimg_ws), mp.wunscale = wunscale, mp.b = p.b, mp.y = p.y;
@@ -1198,7 +1164,7 @@ int launch_bwd_tgt_mma(const float* gy, const float* uvx, const float* da_edge, 
   const size_t wbytes = static_cast<size_t>(M) * 2 * 64 * 128;
   MmaParams mp{};
   mp.img = img, mp.xunscale = reinterpret_cast<const float*>(scal + 1), mp.uvx = uvx, mp.adj = radj;
-  mp.use_tma = (make_img_tmap(&mp.tmap, img, rows, 1) && make_uvx_tmap(&mp.tmap_uvx, uvx, rows, M)) ? 1 : 0;
+  mp.use_tma = make_img_tmap(&mp.tmap, img, rows, 1) ? 1 : 0;
   mp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), mp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
   mp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), mp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
   mp.wimg = static_cast<const uint4*>(wimg);
@@ -1239,7 +1205,7 @@ int launch_bwd_w_mma(const float* uvx, const int32_t* adj, const void* plan, voi
   const ImgWs xi = img_ws_views(ximg_ws, rows), gi = img_ws_views(gyimg_ws, rows);
   MmaParams mp{};
   mp.img = xi.img, mp.xunscale = reinterpret_cast<const float*>(xi.scal + 1), mp.uvx = uvx, mp.adj = adj;
-  mp.use_tma = (make_img_tmap(&mp.tmap, xi.img, rows, 2) && make_uvx_tmap(&mp.tmap_uvx, uvx, rows, M)) ? 1 : 0;
+  mp.use_tma = make_img_tmap(&mp.tmap, xi.img, rows, 2) ? 1 : 0;
   mp.ppair = reinterpret_cast<const uint8_t*>(pb + L.off_pair), mp.prow = reinterpret_cast<const int32_t*>(pb + L.off_row);
   mp.pR = reinterpret_cast<const int32_t*>(pb + L.off_R), mp.pinv = reinterpret_cast<const float*>(pb + L.off_inv);
   mp.wimg = nullptr, mp.wunscale = nullptr, mp.b = nullptr, mp.y = partW;
