@@ -240,3 +240,52 @@ def test_full_size_c2_workload_properties():
     g_again = ops.conv_bwd(gy, x, a, rev, Wd, ud, vd, cd, plan=plan, saved=saved)
     assert all(torch.equal(t1, t2) for t1, t2 in zip(g_p, g_again))     # deterministic
     assert torch.equal(y_p, ops.conv_fwd(x, a, Wd, bd, ud, vd, cd, plan=plan))
+
+
+def test_tma_and_cp_async_loaders_give_identical_bits(tmp_path):
+    """The row gather of the planned kernels has two instantiations -- TMA gather4 through a tensor map of the
+    image, and per-16-byte cp.async (FGC_DISABLE_TMA, or no tensor-map encoder in the driver).  Same operands,
+    same arithmetic: forward and every gradient must agree bit for bit.  The environment switch is read once
+    per process, so the cp.async run happens in a child process."""
+    import os
+    import subprocess
+    import sys
+    from facet_graph_convolution_b200 import ops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "cpasync.npz")
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import test_gpu_planned as tp
+from facet_graph_convolution_b200 import ops
+ops.ConvPlan.MAX_MEAN_ROWS = 1e9
+res = {}
+rs = np.random.RandomState(9)
+for name, x, adj in tp._cases():
+    W0, b, u, v, c = tp._params(rs)
+    gy = rs.randn(*x.shape[:2], 64).astype(np.float32)
+    T = tp.T
+    plan = ops.ConvPlan(T(adj), 8)
+    rev = ops.ReverseAdjacency(T(adj))
+    y = ops.conv_fwd(T(x), T(adj), T(W0), T(b), T(u), T(v), T(c), plan=plan)
+    g = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), plan=plan)
+    res[name + "_y"] = y.cpu().numpy()
+    for k, t in zip(["gx", "gW0", "gb", "gu", "gv", "gc"], g):
+        res[name + "_" + k] = t.cpu().numpy()
+np.savez(%r, **res)
+''' % (root, os.path.join(root, "tests"), out)
+    env = dict(os.environ, FGC_DISABLE_TMA="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    ref = np.load(out)
+    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
+    rs = np.random.RandomState(9)
+    for name, x, adj in _cases():
+        W0, b, u, v, c = _params(rs)
+        gy = rs.randn(*x.shape[:2], 64).astype(np.float32)
+        plan = ops.ConvPlan(T(adj), 8)
+        rev = ops.ReverseAdjacency(T(adj))
+        y = ops.conv_fwd(T(x), T(adj), T(W0), T(b), T(u), T(v), T(c), plan=plan)
+        g = ops.conv_bwd(T(gy), T(x), T(adj), rev, T(W0), T(u), T(v), T(c), plan=plan)
+        assert np.array_equal(y.cpu().numpy(), ref[name + "_y"]), name
+        for k, t in zip(["gx", "gW0", "gb", "gu", "gv", "gc"], g):
+            assert np.array_equal(t.cpu().numpy(), ref[name + "_" + k]), (name, k)
