@@ -255,8 +255,13 @@ def main():
         y = ops.conv_fwd(x, adj, W0, b, u, v, c, plan=plan, save=saved)
         grads = ops.conv_bwd(gy, x, adj, rev, W0, u, v, c, plan=plan, saved=saved)
         if world > 1:
+            # one all-reduce of the layer's parameter gradients, then the 1/world average on the compute stream
+            # (as train.GradBucket.all_reduce_mean does): the next step's kernels are ordered behind the
+            # collective, so an NCCL kernel still waiting for its peers never shares the SMs with the
+            # persistent one-CTA-per-SM kernels (whose static tile split would wait for the displaced CTA)
             flat = torch.cat([t.reshape(-1) for t in grads[1:]])
             dist.all_reduce(flat)
+            flat.mul_(1.0 / world)
         return y, grads
 
     def barrier():
