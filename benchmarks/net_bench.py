@@ -75,7 +75,7 @@ def main():
     ap.add_argument("--grid", type=int, default=1000, help="c3: quads per side (1000 -> 2M facets)")
     ap.add_argument("--block", type=int, default=100)
     ap.add_argument("--batch", type=int, default=4, help="c4: patches per rank per step")
-    ap.add_argument("--patch-batch", type=int, default=10, help="c3: patches per launch (1 = the reference's B=1)")
+    ap.add_argument("--patch-batch", type=int, default=25, help="c3: patches per launch (1 = the reference's B=1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--graph", action="store_true", help="c1: also time the step replayed from a CUDA graph")
     ap.add_argument("--profile", action="store_true", help="per-kernel CUDA-event times of one forward (library profiler)")
