@@ -293,6 +293,46 @@ using namespace fgc;
 
 extern "C" {
 
+// ---- several patches of one batch: segment b = rows [b * stride_rows, b * stride_rows + counts[b])
+constexpr int kSegBlocks = 32;   // partial sums per segment
+
+__global__ void seg_abs_sum_kernel(const float* __restrict__ x, int64_t stride_rows, const int32_t* __restrict__ counts,
+                                   float* __restrict__ part) {
+  __shared__ float sh[32];
+  const int b = blockIdx.y;
+  const int64_t n = static_cast<int64_t>(counts[b]) * 3;
+  const float* xb = x + static_cast<int64_t>(b) * stride_rows * 3;
+  float a = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    a += fabsf(xb[i]);
+  const float r = block_sum(a, sh);
+  if (threadIdx.x == 0) part[b * kSegBlocks + blockIdx.x] = r;
+}
+
+__global__ void seg_normalize_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t stride_rows,
+                                     const int32_t* __restrict__ counts, const float* __restrict__ part) {
+  const float eps = 1e-5f;
+  const int b = blockIdx.y;
+  const int64_t rows = counts[b];
+  float tot = 0.f;
+  for (int i = 0; i < kSegBlocks; ++i) tot += part[b * kSegBlocks + i];   // fixed order, same in every thread
+  const float den = tot / static_cast<float>(rows * 3) + eps;
+  const float* xb = x + static_cast<int64_t>(b) * stride_rows * 3;
+  float* yb = y + static_cast<int64_t>(b) * stride_rows * 3;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < stride_rows;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (r >= rows) {   // padding rows of the batch element
+      yb[3 * r] = 0.f, yb[3 * r + 1] = 0.f, yb[3 * r + 2] = 0.f;
+      continue;
+    }
+    const float a = xb[3 * r] / den, bb = xb[3 * r + 1] / den, c = xb[3 * r + 2] / den;
+    const float nrm = sqrtf(eps + (a * a + bb * bb + c * c));
+    const float inv = nrm > eps ? 1.f / (nrm + eps) : 0.f;
+    yb[3 * r] = a * inv, yb[3 * r + 1] = bb * inv, yb[3 * r + 2] = c * inv;
+  }
+}
+
 size_t fgc_normalize_workspace(int64_t rows) { return ws_bytes(2 * kRedBlocksMax + 8, 4) + 256; }
 
 int fgc_normalize_rows(const float* x, float* y, int64_t rows, void* workspace,
@@ -310,6 +350,23 @@ int fgc_normalize_rows(const float* x, float* y, int64_t rows, void* workspace,
   FGC_LAUNCHED("finalize_sum_kernel");
   normalize_rows_kernel<<<red_blocks(rows), kRedThreads, 0, st>>>(x, y, rows, scal);
   FGC_LAUNCHED("normalize_rows_kernel");
+  return FGC_OK;
+}
+
+int fgc_normalize_rows_segmented(const float* x, float* y, int B, int64_t stride_rows, const int32_t* counts,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  FGC_REQUIRE(x && y && counts && B > 0 && B <= 65535 && stride_rows > 0, "normalize_rows_segmented: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  Workspace ws(workspace, workspace_bytes);
+  float* part = ws.take<float>(static_cast<size_t>(B) * kSegBlocks);
+  FGC_REQUIRE(ws.ok(), "normalize_rows_segmented: workspace too small (%zu bytes needed)",
+              static_cast<size_t>(B) * kSegBlocks * 4 + 512);
+  seg_abs_sum_kernel<<<dim3(kSegBlocks, B), kRedThreads, 0, st>>>(x, stride_rows, counts, part);
+  FGC_LAUNCHED("seg_abs_sum_kernel");
+  int nb = red_blocks(stride_rows);
+  if (nb > 64) nb = 64;
+  seg_normalize_kernel<<<dim3(nb, B), kRedThreads, 0, st>>>(x, y, stride_rows, counts, part);
+  FGC_LAUNCHED("seg_normalize_kernel");
   return FGC_OK;
 }
 

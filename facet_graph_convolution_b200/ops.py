@@ -410,6 +410,21 @@ def normalize_rows(x):
     return y
 
 
+def normalize_rows_segmented(x, counts):
+    """normalizeTensor per element of a batch of padded patches: x[B,Nmax,3], counts[B] int32 (device) = real
+    node count of every element.  Each element gets its own global mean (utils.py:1700-1715); padding rows -> 0."""
+    L = _lib.lib()
+    x = _f32(x, "x")
+    counts = _i32(counts, "counts")
+    B, Nmax = x.shape[0], x.shape[1]
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        ws = _ws(B * 128 + 512, x)
+        check(L.fgc_normalize_rows_segmented(_p(x), _p(y), B, Nmax, _p(counts), _p(ws), ws.numel(), _stream(x)),
+              "fgc_normalize_rows_segmented")
+    return y
+
+
 def normalize_rows_bwd(gy, x):
     L = _lib.lib()
     gy, x = _f32(gy, "gy"), _f32(x, "x")

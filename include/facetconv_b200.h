@@ -213,6 +213,11 @@ FGC_API int fgc_mlp_head_fwd(const float* x, const float* W1, const float* b1, c
 FGC_API size_t fgc_normalize_workspace(int64_t rows);
 FGC_API int fgc_normalize_rows(const float* x, float* y, int64_t rows, void* workspace,
                        size_t workspace_bytes, void* stream);
+/* the same per patch for a batch of padded patches: element b of x[B][stride_rows][3] is normalised over its
+ * first counts[b] rows (device int32) with its own global mean; the padding rows of y are zeroed.
+ * workspace: B * 128 + 512 bytes. */
+FGC_API int fgc_normalize_rows_segmented(const float* x, float* y, int B, int64_t stride_rows, const int32_t* counts,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 FGC_API int fgc_normalize_rows_bwd(const float* gy, const float* x, float* gx, int64_t rows, void* workspace,
                            size_t workspace_bytes, void* stream);
 /* reference Code/train.py:1272-1294 (faceNormalsLoss): loss[0] = mean angle in degrees over real

@@ -129,3 +129,20 @@ def test_stacked_training_step_matches_patch_by_patch():
     (l0, g0), (l1, g1) = out
     assert abs(l0 - l1) < 1e-4 * max(1.0, abs(l0))
     assert float((g0 - g1).abs().max()) < 1e-4 * max(1.0, float(g0.abs().max()))
+
+
+def test_segmented_normalize_matches_per_patch_normalize():
+    """normalizeTensor per element of a padded batch (one launch pair) against the one-patch kernels and the oracle."""
+    from facet_graph_convolution_b200 import ops
+    rs = np.random.RandomState(8)
+    B, Nmax = 5, 700
+    ns = [700, 512, 333, 1, 690]
+    x = (rs.randn(B, Nmax, 3) * np.array([1.0, 5.0, 0.1, 2.0, 1e-3])[:, None, None]).astype(np.float32)
+    x[1, 7] = 0.0
+    xd = torch.from_numpy(x).to(dev())
+    y = ops.normalize_rows_segmented(xd, torch.tensor(ns, dtype=torch.int32, device=dev())).cpu().numpy()
+    for b, n in enumerate(ns):
+        one = ops.normalize_rows(xd[b:b + 1, :n].contiguous()).cpu().numpy()
+        assert np.abs(y[b:b + 1, :n] - one).max() < 1e-6
+        assert np.abs(y[b:b + 1, :n] - cf.normalize_tensor(x[b:b + 1, :n].astype(np.float64))).max() < 1e-5
+        assert not y[b, n:].any()
