@@ -19,7 +19,9 @@ def test_header_declares_expected_surface():
     assert len(syms) >= 35
     for must in ("fgc_conv_fwd", "fgc_conv_bwd", "fgc_build_reverse_adj", "fgc_pool_max", "fgc_upsample",
                  "fgc_mlp_head_fwd", "fgc_normalize_rows", "fgc_vertex_update_edges", "fgc_vertex_update_ms",
-                 "fgc_conv_fwd_host", "fgc_conv_fwd_bwd_host"):
+                 "fgc_conv_fwd_host", "fgc_conv_fwd_bwd_host", "fgc_conv_fwd_planned", "fgc_conv_bwd_planned",
+                 "fgc_build_conv_plan", "fgc_build_faces_adj", "fgc_build_edge_maps", "fgc_face_features",
+                 "fgc_normalize_rows_segmented", "fgc_mlp_head_workspace"):
         assert must in syms
 
 
@@ -56,3 +58,19 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_reference_arm_of_bench_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the B200 arm) needs no GPU: one bounded
+    step of the reference-order port, one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--cpu-sample", "2000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "facets/sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "facets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
