@@ -44,6 +44,8 @@ SIGNATURES = {
     "fgc_conv_fwd": (i32, [PS, p, p, p, p, p, p, p, p, i32, i32, f32, p, sz, p]),
     "fgc_conv_plan_bytes": (sz, [i32, i32, i32, i32]),
     "fgc_build_conv_plan": (i32, [p, i32, i32, i32, i32, p, sz, p]),
+    "fgc_conv_fwd_up_supported": (i32, [PS, i32]),
+    "fgc_conv_fwd_up": (i32, [PS, p, p, p, p, p, p, p, p, i32, i32, f32, i32, p, sz, p]),
     "fgc_conv_fwd_planned": (i32, [PS, p, p, p, p, p, p, p, p, p, i32, i32, f32, p, sz, p]),
     "fgc_debug_trace": (i32, [C.POINTER(i64), i32]),
     "fgc_reverse_adj_workspace": (sz, [i32, i32, i32]),

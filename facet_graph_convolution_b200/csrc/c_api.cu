@@ -100,8 +100,25 @@ static size_t conv_fwd_workspace(const fgc_conv_shape* s) {
 static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0,
                     const float* b, const float* u, const float* v, const float* c, float* y,
                     int bias_mask, int act, float alpha, void* workspace, size_t workspace_bytes,
-                    cudaStream_t st, const void* plan = nullptr) {
+                    cudaStream_t st, const void* plan = nullptr, int upshift = 0) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  if (upshift > 0) {
+    // fused custom_upsampling: x holds (rows >> upshift) rows, row r of the layer reads row r >> upshift.
+    // Only the first-generation tcgen05 forward indexes its gathers this way.
+    FGC_UNSUPPORTED(!(s->M == 9 && use_tc(s)) || plan != nullptr || upshift > 4 || (s->N & ((1 << upshift) - 1)),
+                    "conv_fwd_up: shape has no fused-upsampling path");
+    Workspace wsu(workspace, workspace_bytes);
+    float* uvx_c = wsu.take<float>(rows * 2 * s->M);
+    wsu.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);
+    char* wimg_u = wsu.take<char>(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw));
+    FGC_REQUIRE(wsu.ok(), "conv_fwd_up: workspace too small");
+    fgc_conv_shape sc = *s;
+    sc.B = 1, sc.N = static_cast<int>(rows >> upshift);     // the logits pass runs over the coarse rows
+    int rcu = launch_assign_logits(&sc, x, u, v, c, uvx_c, st);
+    if (rcu) return rcu;
+    ConvFwdParams pu{x, adj, uvx_c, nullptr, b, y, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M, bias_mask, act, alpha};
+    return launch_conv_fwd_tc(pu, W0, wimg_u, st, upshift);
+  }
   if (conv_fwd_small_supported(s))   // the 6 -> 32 input layer: thread per facet, logits inline, no workspace
     return launch_conv_fwd_small(s, x, adj, W0, b, u, v, c, y, bias_mask, act, alpha, st);
   Workspace ws(workspace, workspace_bytes);
@@ -283,6 +300,22 @@ int fgc_conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, co
   FGC_REQUIRE(act == FGC_ACT_NONE || act == FGC_ACT_LRELU, "conv_fwd: unknown activation %d", act);
   return conv_fwd(s, x, adj, W0, b, u, v, c, y, bias_mask, act, alpha, workspace, workspace_bytes,
                   as_stream(stream));
+}
+
+int fgc_conv_fwd_up_supported(const fgc_conv_shape* s, int upshift) {
+  if (check_shape(s, "conv_fwd_up_supported")) return 0;
+  return (s->M == 9 && use_tc(s) && upshift > 0 && upshift <= 4 && (s->N & ((1 << upshift) - 1)) == 0) ? 1 : 0;
+}
+
+int fgc_conv_fwd_up(const fgc_conv_shape* s, const float* x_coarse, const int32_t* adj, const float* W0,
+                    const float* b, const float* u, const float* v, const float* c, float* y, int bias_mask,
+                    int act, float alpha, int upshift, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_shape(s, "conv_fwd_up");
+  if (rc) return rc;
+  FGC_REQUIRE(x_coarse && adj && W0 && b && u && v && c && y && upshift > 0, "conv_fwd_up: bad arguments");
+  FGC_REQUIRE(act == FGC_ACT_NONE || act == FGC_ACT_LRELU, "conv_fwd_up: unknown activation %d", act);
+  return conv_fwd(s, x_coarse, adj, W0, b, u, v, c, y, bias_mask, act, alpha, workspace, workspace_bytes,
+                  as_stream(stream), nullptr, upshift);
 }
 
 int fgc_debug_trace(int64_t* out, int n) { return debug_mma_trace(out, n); }

@@ -87,6 +87,7 @@ struct TcParams {
   // applies the activation
   int add_bias, accumulate, apply_act;
   int cw;                // aggregation channels present in the rows of this launch (0 = 64)
+  int upshift;           // FWD: gathered rows and logits are indexed by (row >> upshift)
 };
 
 // barrier indices
@@ -140,7 +141,7 @@ conv_fwd_tc_kernel(const TcParams p) {
     const int gl = lane % kLPG;      // lane within the facet's group
     uint32_t empty_parity = 1;       // producer convention: the first wait falls through
     int it = 0;
-    const AggSrc src{p.x, p.Cin, p.adj, p.uvx, p.N, p.K, p.rows, p.rev_ptr, p.rev_edge, p.inv, p.da_edge, p.cw};
+    const AggSrc src{p.x, p.Cin, p.adj, p.uvx, p.N, p.K, p.rows, p.rev_ptr, p.rev_edge, p.inv, p.da_edge, p.cw, p.upshift};
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       for (int pass = 0; pass < 2; ++pass) {
         const int prow = warp * kFPW + grp;                       // row within the pass (0..31)
@@ -434,8 +435,9 @@ size_t conv_fwd_tc_workspace(int Cout, int M, int Cw) {
 }
 
 // wimg_ws: conv_fwd_tc_workspace bytes (16-byte aligned); the tail of every image holds its scalar un-scale
-int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st) {
+int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st, int upshift) {
   TcParams tp{};
+  tp.upshift = upshift;
   tp.x = p.x, tp.adj = p.adj, tp.uvx = p.uvx, tp.b = p.b, tp.y = p.y, tp.rows = p.rows;
   tp.N = p.N, tp.K = p.K, tp.Cin = p.Cin, tp.bias_mask = p.bias_mask, tp.act = p.act, tp.alpha = p.alpha;
   tp.ldy = p.Cout;

@@ -35,6 +35,7 @@ struct AggSrc {
   const float* inv;      // inv_cnt of every source row
   const float* da_edge;  // [rows*K][M]
   int cw;                // aggregation channels actually present in a row (0 = all 64); the rest read as zero
+  int upshift;           // FWD: x and uvx have (rows >> upshift) rows -- a fused custom_upsampling (repeat x 2^upshift)
 };
 
 template <int M>
@@ -96,8 +97,8 @@ __device__ __forceinline__ void agg_assign_round(const AggSrc& p, int64_t wrow0,
         const int64_t base = (rf / p.N) * p.N;
         vvalid = id > 0 && id <= p.N;
         row = vvalid ? static_cast<int>(base + id - 1) : (id != 0 ? -2 : -1);
-        ux = p.uvx + rf * (2 * M);
-        vx = p.uvx + (vvalid ? static_cast<int64_t>(row) : rf) * (2 * M) + M;
+        ux = p.uvx + (rf >> p.upshift) * (2 * M);
+        vx = p.uvx + ((vvalid ? static_cast<int64_t>(row) : rf) >> p.upshift) * (2 * M) + M;
       } else {
         const int e = __ldg(p.rev_edge + f0 + kb + k);
         row = e / p.K;  // source facet of the in-edge
@@ -165,7 +166,7 @@ __device__ __forceinline__ void agg_load_row(const AggSrc& p, int j, int gl, flo
   for (int i = 0; i < kF4; ++i) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (j >= 0 && (p.cw == 0 || 4 * (gl + kLPG * i) < p.cw))
-      t = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(j) * p.ldx) + gl + kLPG * i);
+      t = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(j >> p.upshift) * p.ldx) + gl + kLPG * i);
     xp[2 * i] = make_float2(t.x, t.y);
     xp[2 * i + 1] = make_float2(t.z, t.w);
   }

@@ -217,6 +217,23 @@ def faceNormalsLoss(fn, gt_fn):
 
 
 # ----------------------------------------------------------------------------- network
+def _up_conv(h, adj, out_channels, M, steps, fused_ok):
+    """custom_conv2d(custom_upsampling(h, steps), adj, out_channels, M)[0] (reference model.py:902-905, 923-926);
+    variables are created in the reference's order either way."""
+    if fused_ok:
+        Cin = h.shape[2]
+        W0 = weight_variable([M, out_channels, Cin])
+        b = bias_variable([out_channels])
+        u = assignment_variable([M, Cin])
+        c = assignment_variable([M])
+        v = assignment_variable([M, Cin])
+        y = ops.conv_fwd_up(h, adj, W0, b, u, v, c, upshift=steps)
+        if y is None:
+            y = ops.conv_fwd(ops.upsample(h, 1 << steps), adj, W0, b, u, v, c)
+        return y
+    return custom_conv2d(custom_upsampling(h, steps=steps), adj, out_channels, M)[0]
+
+
 def get_model_reg_multi_scale(x, adjs, keep_prob=1.0, coarsening_steps=2, multiScale=False, fuse=True):
     """Drop-in for reference Code/model.py:837-946: the 3-level U-Net of facet-graph convolutions.
 
@@ -257,15 +274,13 @@ def get_model_reg_multi_scale(x, adjs, keep_prob=1.0, coarsening_steps=2, multiS
     h_conv3_act = conv_act(pool2, adjs[2], 128)
     dconv3_act = conv_act(h_conv3_act, adjs[2], 128)
     y_conv2 = head(dconv3_act) if multiScale else None
-    upsamp2 = custom_upsampling(dconv3_act, steps=coarsening_steps)
-    # Level1
-    upconv2, _ = custom_conv2d(upsamp2, adjs[1], 64, M)
+    # Level1 (inference: the repeat x 4 is an index shift inside the layer when its shape has that path)
+    upconv2 = _up_conv(dconv3_act, adjs[1], 64, M, coarsening_steps, infer)
     concat2 = concat_channels(upconv2, h_conv2_act)
     dconv2_act = conv_act(concat2, adjs[1], 64)
     y_conv1 = head(dconv2_act) if multiScale else None
-    upsamp1 = custom_upsampling(dconv2_act, steps=coarsening_steps)
     # Level0
-    upconv1, _ = custom_conv2d(upsamp1, adjs[0], 32, M)
+    upconv1 = _up_conv(dconv2_act, adjs[0], 32, M, coarsening_steps, infer)
     concat1 = concat_channels(upconv1, h_conv1_act)
     dconv1_act = conv_act(concat1, adjs[0], 32)
     y_conv0 = head(dconv1_act)

@@ -140,6 +140,29 @@ def conv_fwd(x, adj, W0, b, u, v, c, bias_mask=True, act=ACT_NONE, alpha=0.1, cw
     return y
 
 
+def conv_fwd_up(x_coarse, adj, W0, b, u, v, c, upshift, bias_mask=True, act=ACT_NONE, alpha=0.1):
+    """conv_fwd(custom_upsampling(x_coarse, steps), adj, ...) without materialising the repeated tensor
+    (2^upshift = 4^steps rows per coarse row).  Returns None when the shape has no fused path."""
+    L = _lib.lib()
+    x_coarse, W0, b, u, v, c = (_f32(t, n) for t, n in ((x_coarse, "x"), (W0, "W0"), (b, "b"), (u, "u"), (v, "v"), (c, "c")))
+    adj = _i32(adj, "adj")
+    B, Nc, Cin = x_coarse.shape
+    N = adj.shape[1]
+    if adj.shape[0] != B or (Nc << upshift) != N:
+        raise _lib.FacetConvError("conv_fwd_up: adj has %d rows, x_coarse %d << %d" % (N, Nc, upshift))
+    M, Cout, Cw = W0.shape
+    s = ConvShape(B, N, adj.shape[2], Cin, Cw, 0, u.shape[1], Cout, M)
+    if not L.fgc_conv_fwd_up_supported(C.byref(s), int(upshift)):
+        return None
+    y = torch.empty((B, N, Cout), dtype=torch.float32, device=x_coarse.device)
+    with torch.cuda.device(x_coarse.device):
+        ws = _ws(L.fgc_conv_fwd_workspace(C.byref(s)), x_coarse)
+        check(L.fgc_conv_fwd_up(C.byref(s), _p(x_coarse), _p(adj), _p(W0), _p(b), _p(u), _p(v), _p(c), _p(y),
+                                int(bool(bias_mask)), int(act), float(alpha), int(upshift), _p(ws), ws.numel(),
+                                _stream(x_coarse)), "fgc_conv_fwd_up")
+    return y
+
+
 class ReverseAdjacency:
     """Caller-owned reverse adjacency (built once per adjacency tensor, reused by every backward
     through a layer that uses it).  Replaces the scatter of TF's gather gradient."""

@@ -98,6 +98,17 @@ FGC_API int fgc_conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t*
                  int bias_mask, int act, float alpha, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* forward with a fused custom_upsampling (reference Code/model.py:817-825 followed by :427-504, as the network
+ * does at :902-905 and :923-926): x_coarse has (B*N) >> upshift rows and row r of the layer reads row
+ * r >> upshift (features and assignment logits), so the repeated tensor is never materialised.  Same values,
+ * bit for bit, as fgc_conv_fwd on the repeated input.  fgc_conv_fwd_up_supported tells whether the shape
+ * has this path (the M = 9 layers on the tcgen05 forward); workspace as fgc_conv_fwd_workspace(s). */
+FGC_API int fgc_conv_fwd_up_supported(const fgc_conv_shape* s, int upshift);
+FGC_API int fgc_conv_fwd_up(const fgc_conv_shape* s, const float* x_coarse, const int32_t* adj, const float* W0,
+                    const float* b, const float* u, const float* v, const float* c, float* y,
+                    int bias_mask, int act, float alpha, int upshift, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* Tile plan (caller-owned cache, built once per adjacency like the reverse adjacency below; pure
  * index work on adj, bit-exact): for every tile of 128/M consecutive facets the list of distinct
  * neighbour rows it touches and, per (facet, slot), the row's local index and the multiplicity of

@@ -172,3 +172,53 @@ def test_network_training_gradients():
         scale = max(float(np.abs(ref).max()), 1e-3)
         assert t.grad is not None, i
         assert np.abs(t.grad.cpu().numpy() - ref).max() / scale < 5e-3, (i, store.names[i])
+
+
+def _rand_adj(rs, B, N, K):
+    adj = rs.randint(0, N + 1, size=(B, N, K)).astype(np.int32)
+    adj[:, :, 0] = np.arange(1, N + 1, dtype=np.int32)[None]
+    adj[:, :, K - 3:] *= (rs.rand(B, N, 3) < 0.5)  # ragged neighbourhoods
+    return adj
+
+
+@pytest.mark.parametrize("B,N,Cin,Cout", [(1, 8192, 128, 64), (3, 4096, 64, 32), (1, 4096 + 64, 64, 32)])
+def test_fused_upsampling_is_bit_identical_to_the_repeated_input(B, N, Cin, Cout):
+    """conv(custom_upsampling(x, 2)) with the repeat folded into the gather (row r reads coarse row r >> 2,
+    model.py:817-825 then :427-504) == the same layer on the materialised tensor, bit for bit; batches and a
+    ragged last tile included."""
+    from facet_graph_convolution_b200 import ops
+    rs = np.random.RandomState(5)
+    M, K = 9, 16
+    xc = rs.randn(B, N // 4, Cin).astype(np.float32)
+    adj = _rand_adj(rs, B, N, K)
+    W0 = (rs.randn(M, Cout, Cin) * 0.05).astype(np.float32)
+    b = (rs.randn(Cout) * 0.05).astype(np.float32)
+    u = (rs.randn(M, Cin) * 0.05).astype(np.float32)
+    v = (rs.randn(M, Cin) * 0.05).astype(np.float32)
+    c = (rs.randn(M) * 0.05).astype(np.float32)
+    args = [T(a) for a in (W0, b, u, v, c)]
+    y_up = ops.conv_fwd_up(T(xc), T(adj), *args, upshift=2)
+    assert y_up is not None, "the M = 9 layers at >= 4096 rows must have the fused path"
+    y_mat = ops.conv_fwd(ops.upsample(T(xc), 4), T(adj), *args)
+    assert torch.equal(y_up, y_mat)
+    ref = cf.conv_fwd(cf.upsample(xc[:1].astype(np.float64), 2), adj[:1], W0, b, u, v, c)
+    assert np.abs(y_up[:1].cpu().numpy() - ref).max() < 1e-5
+    # shapes without the path say so instead of computing something else
+    a8 = [T(a) for a in (W0[:8], b, u[:8], v[:8], c[:8])]
+    assert ops.conv_fwd_up(T(xc), T(adj), *a8, upshift=2) is None
+
+
+def test_network_with_fused_upsampling_matches_unfused_at_size():
+    """The whole network at a size where both upsampling layers take the fused path: identical to fuse=False
+    within the per-layer tolerance (the unfused arm materialises every intermediate)."""
+    from facet_graph_convolution_b200 import model as fm
+    rs = np.random.RandomState(9)
+    N0 = 4096 * 16
+    adjs = [T(_rand_adj(rs, 1, N0 >> (2 * l), 16)) for l in range(3)]
+    x = T(rs.randn(1, N0, 6).astype(np.float32))
+    store = fm.VariableStore(dev(), seed=3)
+    with torch.no_grad(), fm.variable_store(store):
+        y0 = fm.get_model_reg_multi_scale(x, adjs, 1.0, fuse=False)
+    with torch.no_grad(), fm.variable_store(store):
+        y1 = fm.get_model_reg_multi_scale(x, adjs, 1.0, fuse=True)
+    assert (y0 - y1).abs().max().item() < 1e-5
