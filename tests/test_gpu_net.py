@@ -222,3 +222,30 @@ def test_network_with_fused_upsampling_matches_unfused_at_size():
     with torch.no_grad(), fm.variable_store(store):
         y1 = fm.get_model_reg_multi_scale(x, adjs, 1.0, fuse=True)
     assert (y0 - y1).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("gname,multi", [("net_icosphere3", False), ("net_ms_icosphere2", True)])
+def test_saver_checkpoint_names_follow_the_creation_order_and_round_trip(tmp_path, gname, multi):
+    """The variables the network creates (order, leaf names, shapes) are the ones `checkpoint.network_variables`
+    names after the reference's Saver; the golden parameters written as a Saver file and loaded
+    back by name give the golden outputs."""
+    from facet_graph_convolution_b200 import checkpoint as ck
+    from facet_graph_convolution_b200 import model as fm
+    g = golden(gname)
+    adjs = [T(g["adj0"]), T(g["adj1"]), T(g["adj2"])]
+    spec = ck.network_variables(in_channels=g["x"].shape[2], multi_scale=multi)
+    for fuse in (False, True):
+        store = fm.VariableStore(dev(), seed=1)
+        with torch.no_grad(), fm.variable_store(store):
+            fm.get_model_reg_multi_scale(T(g["x"]), adjs, 1.0, multiScale=multi, fuse=fuse)
+        assert [tuple(p.shape) for p in store.params] == [s for _, s in spec]
+        assert store.names == [n.rsplit("/", 1)[1].split("_")[0] for n, _ in spec]
+    prefix = ck.save_network(str(tmp_path / "net"), _params(g), in_channels=g["x"].shape[2], multi_scale=multi,
+                             global_step=7)
+    params = ck.load_network(ck.latest_checkpoint(str(tmp_path)), in_channels=g["x"].shape[2], multi_scale=multi)
+    assert prefix.endswith("net-7")
+    with torch.no_grad(), fm.variable_store(fm.VariableStore(dev(), params=params)):
+        ys = fm.get_model_reg_multi_scale(T(g["x"]), adjs, 1.0, multiScale=multi)
+    ys = ys if multi else (ys,)
+    for y, k in zip(ys, ("y0", "y1", "y2") if multi else ("y_raw",)):
+        assert np.abs(y.cpu().numpy() - g[k]).max() < 1e-5
