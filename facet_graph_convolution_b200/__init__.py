@@ -3,12 +3,12 @@
 Drop-in for the FeaStNet-style layer and the multi-scale normal-denoising network of
 Elensil/Facet_Graph_Convolution (reference Code/model.py), built from scratch as hand-written
 sm_100a CUDA kernels behind a C ABI (include/facetconv_b200.h).  ``mesh`` (host-side synthetic
-generators) and ``checkpoint`` (Saver-file interchange) import without the CUDA library; everything else needs libfacetconv_b200.so and a
+generators), ``mesh_io`` (OBJ files) and ``checkpoint`` (Saver-file interchange) import without the CUDA library; everything else needs libfacetconv_b200.so and a
 CUDA device and fails loudly otherwise.
 """
 from . import mesh  # noqa: F401  (NumPy only)
 
-__all__ = ["mesh", "checkpoint", "ops", "model", "autograd", "build_library"]
+__all__ = ["mesh", "mesh_io", "checkpoint", "ops", "model", "autograd", "build_library"]
 
 
 def build_library(force=False):
@@ -17,7 +17,7 @@ def build_library(force=False):
 
 
 def __getattr__(name):
-    if name in ("ops", "model", "autograd", "patches", "train", "checkpoint"):
+    if name in ("ops", "model", "autograd", "patches", "train", "checkpoint", "mesh_io"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -1,0 +1,76 @@
+"""OBJ reader / writer of the reference's drivers, host side, NumPy only.
+
+`load_mesh` follows reference Code/utils.py:476-641 as every caller uses it (`K = 0`, `bGetAdj = False`:
+dataClasses.py:30,491-523, computeMetrics.py:41,66) and `write_mesh` Code/utils.py:659-699; same return
+tuple, same dtypes, same text.  Pinned by `tests/golden/obj_io.npz`, produced by the reference's own two
+functions (oracle/make_golden.py:obj_cases).
+"""
+import os
+
+import numpy as np
+
+__all__ = ["load_mesh", "write_mesh", "compute_vertex_normals"]
+
+
+def _unit_rows_twice(a):
+    """utils.py:26-35: a / (|a| + 1e-8), applied two times."""
+    for _ in range(2):
+        a = a * (1 / (np.sqrt((a * a).sum(1))[:, np.newaxis] + 0.00000001))
+    return a
+
+
+def compute_vertex_normals(verts, faces):
+    """`computeNormals` (utils.py:44-59), including its indexed `+=`: when a vertex occurs several times in
+    one corner column only the last face of that column contributes."""
+    tri = verts[faces]
+    fn = _unit_rows_twice(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]))
+    normals = np.zeros(verts.shape, dtype=np.float32)
+    for corner in range(3):
+        col = faces[:, corner]
+        normals[col] = normals[col] + fn  # buffered: one write per vertex, the last one wins
+    return _unit_rows_twice(normals)
+
+
+def load_mesh(path, filename, K=0, bGetAdj=False):
+    """Returns (vertices float32 [V,3], adj, free_ind, faces uint16|uint32 [F,3] zero-based, vertex normals).
+    Polygons are fan-triangulated around their first vertex; `v/vt/vn` corners keep the vertex index; `vn`,
+    `vt`, `mtllib`, `usemtl`, comments and blank lines are skipped.  The per-vertex ring adjacency
+    (`bGetAdj`) is not built: no driver of the reference asks for it."""
+    if bGetAdj:
+        raise NotImplementedError("load_mesh(bGetAdj=True): the vertex-ring adjacency is never requested by "
+                                  "the reference's drivers; use build_faces_adj for the facet graph")
+    verts = []
+    corners = []
+    with open(os.path.join(path, filename), "r") as f:
+        for line in f:
+            tok = line.split()
+            if not tok or line.startswith("#"):
+                continue
+            if tok[0] == "v":
+                verts.append((float(tok[1]), float(tok[2]), float(tok[3])))
+            elif tok[0] == "f":
+                ids = [int(t.split("/")[0]) - 1 for t in tok[1:]]
+                for t in range(len(ids) - 2):
+                    corners += (ids[0], ids[t + 1], ids[t + 2])
+    vertices = np.array(verts).astype(np.float32)
+    itype = np.uint16 if vertices.shape[0] < 65536 else np.uint32
+    faces = np.array(corners).reshape(len(corners) // 3, 3).astype(itype)
+    return vertices, [], [], faces, compute_vertex_normals(vertices, faces)
+
+
+def write_mesh(vl, fl, strFileName):
+    """One `v` line per vertex with `%.6f` coordinates (every column of `vl`), then one `f` line per face,
+    one-based; every token is followed by a blank.  Face rows (-1, -1, .) are skipped and the first row
+    (0, 0, .) ends the list (the padding conventions of the patch pipeline)."""
+    vl = np.asarray(vl)
+    fl = np.asarray(fl)
+    lines = ["v " + "".join("%.6f " % x for x in row) for row in vl]
+    one = fl.astype(np.int64) + 1 if fl.size else np.zeros((0, 3), np.int64)
+    for row in one:
+        if row[0] == 1 and row[1] == 1:
+            break
+        if row[0] == 0 and row[1] == 0:
+            continue
+        lines.append("f " + "".join("%d " % i for i in row))
+    with open(strFileName, "w") as f:
+        f.write("\n".join(lines) + ("\n" if lines else ""))

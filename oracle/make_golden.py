@@ -273,6 +273,57 @@ def index_cases(ref):
     print("wrote index_layouts")
 
 
+OBJ_TEXT = """# comment line
+mtllib scene.mtl
+
+v 0 0 0
+v 1.5 0 0.25
+v 1 1 -0.5
+v 0 1 1e-3
+vn 0 0 1
+vt 0.5 0.5
+v -1 0.5 2
+v 0.5 -1 0.125 0.9 0.1 0.2
+usemtl mat0
+f 1 2 3
+f 1/1/1 3/2/1 4/3/1
+f 1//1 4//1 5//1 6//1
+  f 2 6 1 5 3
+f 6 5 4
+"""
+
+
+def obj_cases(ref):
+    """The reference's OBJ reader and writer on a hand-written file (comments, materials, vn/vt records, a
+    vertex with colour columns, v/vt/vn corners, a quad and a pentagon, an indented record) and on meshes
+    with padding faces."""
+    import tempfile
+    d = {"obj_text": np.frombuffer(OBJ_TEXT.encode(), dtype=np.uint8)}
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "in.obj"), "w") as f:
+            f.write(OBJ_TEXT)
+        with contextlib.redirect_stdout(io.StringIO()):
+            V, adj, free_ind, F, N = ref.utils.load_mesh(tmp, "in.obj", 0, False)
+        assert adj == [] and free_ind == []
+        d["V"], d["F"], d["N"] = V, F, N
+        Vi, Fi = mesh.icosphere(1)
+        rs = np.random.RandomState(3)
+        Vn = (Vi + 0.05 * rs.randn(*Vi.shape)).astype(np.float32)
+        Fp = np.concatenate([Fi[:5], -np.ones((2, 3), np.int32), Fi[5:], np.zeros((3, 3), np.int32), Fi[:2]]).astype(np.int32)
+        ref.utils.write_mesh(Vn, Fp, os.path.join(tmp, "out.obj"))
+        d["w_V"], d["w_F"] = Vn, Fp
+        d["w_text"] = np.frombuffer(open(os.path.join(tmp, "out.obj"), "rb").read(), dtype=np.uint8)
+        Vc = np.concatenate([Vn, rs.rand(Vn.shape[0], 3).astype(np.float32)], axis=1)
+        ref.utils.write_mesh(Vc, Fi.astype(np.int32), os.path.join(tmp, "outc.obj"))
+        d["wc_V"], d["wc_F"] = Vc, Fi.astype(np.int32)
+        d["wc_text"] = np.frombuffer(open(os.path.join(tmp, "outc.obj"), "rb").read(), dtype=np.uint8)
+        with contextlib.redirect_stdout(io.StringIO()):
+            V2, _, _, F2, N2 = ref.utils.load_mesh(tmp, "out.obj", 0, False)
+        d["r_V"], d["r_F"], d["r_N"] = V2, F2, N2
+    np.savez_compressed(os.path.join(OUT, "obj_io.npz"), **d)
+    print("wrote obj_io")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rr.load()
@@ -287,6 +338,7 @@ def main():
     small_ops(ref)
     net_and_vertex_cases(ref)
     index_cases(ref)
+    obj_cases(ref)
 
 
 if __name__ == "__main__":
