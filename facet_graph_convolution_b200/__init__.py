@@ -17,7 +17,7 @@ def build_library(force=False):
 
 
 def __getattr__(name):
-    if name in ("ops", "model", "autograd", "patches", "train", "checkpoint", "mesh_io"):
+    if name in ("ops", "model", "autograd", "patches", "train", "checkpoint", "mesh_io", "coarsening"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

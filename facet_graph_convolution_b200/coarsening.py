@@ -1,0 +1,211 @@
+"""Graph pyramid of a facet patch: weighted facet graph, heavy-edge coarsening, binary-tree node order and
+the K-column adjacency lists of every level (host half).
+
+Replaces, for the way `dataClasses.py:108-135` drives them, reference `utils.listToSparseWNormals`
+(Code/utils.py:1753-1797), `lib/coarsening.coarsen` / `metis` / `compute_perm` / `perm_adjacency`
+(Code/lib/coarsening.py:5-32, 35-131, 196-243, 269-296), `utils.sparseToList` (:1799-1828) and `utils.inv_perm`
+(:1830-1836).  Host side: the pairing of a level visits nodes one after the other and every choice depends
+on the earlier ones, so it is the native sequential routine `fgc_greedy_pairing` (O(nnz)); everything else is
+vectorised NumPy / SciPy instead of per-node Python loops (the reference's `compute_perm` scans the whole
+parent vector once per node, quadratic in the patch size).  The sparse assembly goes through the same SciPy
+calls as the reference so that duplicate edges are summed in the same float32 order.
+
+The reference draws its visiting orders from the global NumPy generator (coarsening.py:57, 96); `rng` here
+defaults to that generator and is consumed in the same sequence, so a seeded run gives the reference's
+pyramid exactly (tests/golden/coarsen_*.npz, produced by the reference functions in this container).  Ties
+between equal edge scores are resolved by the column order of the sorted adjacency; this module fixes that
+order (row-major, columns ascending), which is what the reference's unstable `np.argsort` yields in this
+image -- on another NumPy build the reference itself may break ties differently.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse
+
+from . import _lib
+
+__all__ = ["list_to_sparse_w_normals", "coarsen", "compute_perm", "perm_adjacency", "sparse_to_list", "inv_perm",
+           "greedy_pairing", "patch_pyramid"]
+
+
+def list_to_sparse_w_normals(adj, nodes_pos, nodes_normals):
+    """Weighted facet graph of a 1-based, 0-padded adjacency list whose first column is the node itself:
+    w(n, j) = max(<n_n, n_j> * exp(-|p_j - p_n|^2 / (2 * 0.001^2)), 0.001) as float32, a row ending at its
+    first 0 (utils.py:1753-1797)."""
+    adj = np.asarray(adj)
+    N, K = adj.shape
+    nb = adj[:, 1:].astype(np.int64) - 1
+    keep = np.logical_and.accumulate(nb >= 0, axis=1)
+    rows = np.broadcast_to(np.arange(N, dtype=np.int64)[:, None], nb.shape)[keep]
+    cols = nb[keep]
+    pos = np.asarray(nodes_pos)
+    nrm = np.asarray(nodes_normals)
+    dp = (nrm[rows] * nrm[cols]).sum(axis=-1)
+    d = pos[cols] - pos[rows]
+    dist = np.sqrt((d * d).sum(axis=-1))
+    vals = np.maximum(dp * np.exp(-(dist ** 2) * (1.0 / (2 * 0.001 * 0.001))), 0.001).astype(np.float32)
+    return scipy.sparse.coo_matrix((vals, (rows.astype(np.int32), cols.astype(np.int32))), shape=(N, N))
+
+
+def greedy_pairing(rr, cc, vv, rid, weights, precision=32):
+    """One level of pairing (coarsening.py:135-194) on row-sorted entries: (cluster_id[N], total score)."""
+    rr = np.ascontiguousarray(rr, dtype=np.int32)
+    cc = np.ascontiguousarray(cc, dtype=np.int32)
+    vv = np.ascontiguousarray(vv, dtype=np.float32)
+    rid = np.ascontiguousarray(rid, dtype=np.int64)
+    weights = np.ascontiguousarray(weights, dtype=np.float32)
+    if rr.size == 0:
+        raise _lib.FacetConvError("greedy_pairing: graph without edges")
+    n = int(rr[-1]) + 1
+    if weights.size < n:
+        raise _lib.FacetConvError("greedy_pairing: %d weights for %d rows" % (weights.size, n))
+    cluster = np.empty(n, dtype=np.int32)
+    total = C.c_double(0.0)
+    ncl = C.c_int32(0)
+    _lib.check(_lib.lib().fgc_greedy_pairing(
+        rr.ctypes.data, cc.ctypes.data, vv.ctypes.data, rr.size, rid.ctypes.data, rid.size, weights.ctypes.data, n,
+        int(precision), cluster.ctypes.data, C.byref(total), C.byref(ncl)), "fgc_greedy_pairing")
+    return cluster, total.value
+
+
+def _row_major_entries(W):
+    """Non-zero entries of W (duplicates summed) ordered by row, then column."""
+    r, c, v = scipy.sparse.find(W)
+    order = np.lexsort((c, r))
+    return r[order], c[order], v[order]
+
+
+def _pair_levels(W, levels, rng, precision, trials=3):
+    N = W.shape[0]
+    rid = rng.permutation(range(N))
+    degree = W.sum(axis=0) - W.diagonal()
+    graphs, parents = [W], []
+    for _ in range(levels):
+        weights = np.array(degree).squeeze()
+        rr, cc, vv = _row_major_entries(W)
+        best, best_score = None, 0.0
+        for _t in range(trials):
+            cluster, score = greedy_pairing(rr, cc, vv, rid, weights, precision)
+            if score > best_score:
+                best, best_score = cluster, score
+            rid = rng.permutation(range(N))  # drawn after every trial, the last one unused (as the reference)
+        if best is None:
+            raise _lib.FacetConvError("coarsen: no edge with a positive score")
+        parents.append(best)
+        n_new = int(best.max()) + 1
+        W = scipy.sparse.csr_matrix((vv, (best[rr], best[cc])), shape=(n_new, n_new))
+        W.eliminate_zeros()
+        graphs.append(W)
+        N = n_new
+        degree = W.sum(axis=0)  # self loops of merged pairs now count
+        rid = np.argsort(np.array(degree).squeeze())
+    return graphs, parents
+
+
+def compute_perm(parents):
+    """Node orders, finest level first, in which nodes 2i and 2i+1 of a level are the children of node i of
+    the next one; singletons get a fake sibling, fake parents two fake children, fakes numbered after the real
+    nodes in order of appearance (coarsening.py:196-240; known answer at :243-244).  Linear time."""
+    if len(parents) == 0:
+        return []
+    layers = [np.arange(int(np.max(parents[-1])) + 1, dtype=np.int64)]
+    for parent in parents[::-1]:
+        parent = np.asarray(parent, dtype=np.int64)
+        above = layers[-1]
+        n_above = int(above.max()) + 1 if above.size else 0
+        counts = np.bincount(parent, minlength=n_above)
+        if counts.size > n_above or counts.max(initial=0) > 2:
+            raise AssertionError("compute_perm: a cluster has more than two members or an unknown parent")
+        by_parent = np.argsort(parent, kind="stable")
+        first = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        cnt = counts[above]                                   # fake parents index past the real ones: count 0
+        fakes_before = np.concatenate([[0], np.cumsum(2 - cnt)[:-1]]) + parent.size
+        safe = np.minimum(first[above], max(parent.size - 1, 0))
+        c0 = np.where(cnt >= 1, by_parent[safe], fakes_before)
+        c1 = np.where(cnt == 2, by_parent[np.minimum(safe + 1, max(parent.size - 1, 0))],
+                      fakes_before + (cnt == 0))
+        layers.append(np.stack([c0, c1], axis=1).reshape(-1))
+    return [l.tolist() for l in layers[::-1]]
+
+
+def perm_adjacency(A, indices):
+    """A with Mnew - M isolated nodes appended and node j moved to the position of j in `indices`
+    (coarsening.py:269-296)."""
+    if indices is None:
+        return A
+    M = A.shape[0]
+    Mnew = len(indices)
+    assert Mnew >= M
+    A = A.tocoo()
+    where = np.argsort(indices)
+    return scipy.sparse.coo_matrix((A.data, (where[A.row], where[A.col])), shape=(Mnew, Mnew))
+
+
+def coarsen(A, levels, self_connections=False, rng=None, precision=32):
+    """`levels` rounds of pairing; returns (graphs as CSR with every level but the last in binary-tree order
+    and padded with fake nodes, order of the finest level = new-to-old) -- coarsening.py:5-32."""
+    rng = np.random if rng is None else rng
+    graphs, parents = _pair_levels(A, levels, rng, precision)
+    perms = compute_perm(parents)
+    out = []
+    for i, G in enumerate(graphs):
+        G = G.tocoo(copy=True)  # (the reference zeroes the diagonal of the caller's matrix in place)
+        if not self_connections:
+            G.setdiag(0)
+        if i < levels:
+            G = perm_adjacency(G, perms[i])
+        G = G.tocsr()
+        G.eliminate_zeros()
+        out.append(G)
+    return out, (perms[0] if levels > 0 else None)
+
+
+def sparse_to_list(A, K):
+    """[N, K] 1-based adjacency list, column 0 the node itself, then the off-diagonal entries of the row in
+    storage order, 0-padded; (list, saturated) with saturated = some row had more than K - 1 (utils.py:1799-1828)."""
+    N = A.shape[0]
+    cx = A.tocoo()
+    off = cx.row != cx.col
+    r, c = cx.row[off].astype(np.int64), cx.col[off].astype(np.int64)
+    if r.size and np.any(np.diff(r) < 0):  # storage order is row-major for the CSR input; be safe otherwise
+        o = np.argsort(r, kind="stable")
+        r, c = r[o], c[o]
+    counts = np.bincount(r, minlength=N)
+    slot = np.arange(r.size) - np.repeat(np.concatenate([[0], np.cumsum(counts)[:-1]]), counts) + 1
+    out = np.zeros((N, K), dtype=np.int32)
+    out[:, 0] = np.arange(N) + 1
+    ok = slot < K
+    out[r[ok], slot[ok]] = c[ok] + 1
+    return out, bool((~ok).any())
+
+
+def inv_perm(perm):
+    """inverse[p] = position of p in `perm` (utils.py:1830-1836)."""
+    perm = np.asarray(perm, dtype=np.int64)
+    inverse = np.zeros(max(perm.size, int(perm.max()) + 1 if perm.size else 0), dtype=np.int64)
+    inverse[perm] = np.arange(perm.size)
+    return inverse
+
+
+def patch_pyramid(adj, features, K, level_num=3, step_num=2, rng=None, precision=32, max_retries=20):
+    """The network inputs of one patch as `dataClasses.py:108-150` prepares them: the graph is coarsened
+    (level_num - 1) * step_num times (again while some level saturates its K columns), the K-column lists
+    of levels 0, step_num, 2 * step_num, ... are extracted and the feature rows are padded with zero rows for
+    the fake nodes and put in tree order.  `features` = [N, 6] normals | positions.
+    Returns (adjs [1, N_l, K] per level, features [N_0', C], new_to_old, old_to_new)."""
+    features = np.asarray(features)
+    coo = list_to_sparse_w_normals(adj, features[:, -3:], features[:, :3])
+    for _ in range(max_retries):
+        graphs, new_to_old = coarsen(coo, (level_num - 1) * step_num, rng=rng, precision=precision)
+        adjs, saturated = [], False
+        for lvl in range(level_num):
+            a, sat = sparse_to_list(graphs[step_num * lvl], K)
+            adjs.append(a[np.newaxis])
+            saturated = saturated or sat
+        if not saturated:
+            break
+    else:
+        raise _lib.FacetConvError("patch_pyramid: a level still saturates K = %d after %d coarsenings" % (K, max_retries))
+    new_to_old = np.asarray(new_to_old, dtype=np.int64)
+    padded = np.concatenate([features, np.zeros((new_to_old.size - features.shape[0], features.shape[1]))], axis=0)
+    return adjs, padded[new_to_old], new_to_old, inv_perm(new_to_old)

@@ -287,6 +287,17 @@ FGC_API int fgc_build_edge_maps(const int32_t* faces, int64_t nf, int64_t nv, in
                         int64_t* num_edges, int32_t* v_edges, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* Host-only (no device work, HOST pointers): the greedy heavy-edge pairing of one coarsening level, reference
+ * Code/lib/coarsening.py:135-194 `metis_one_level`.  (row, col, val)[nnz] is the weighted adjacency sorted by
+ * row, n = row[nnz-1] + 1 nodes, order[0..n) the visiting order, weights[n] the node degrees.  A node visited
+ * unpaired takes the unpaired neighbour with the largest val * (1/weights[node] + 1/weights[neighbour]) (first
+ * one on ties, none when every score is 0) and both get the next cluster id.  precision 32 evaluates scores
+ * and their sum in float (what the reference's expressions give on float32 inputs under NumPy >= 2), 64 in
+ * double (NumPy 1.x promotion).  cluster_id[n], *total_assoc = sum of the winning scores, *n_clusters. */
+FGC_API int fgc_greedy_pairing(const int32_t* row, const int32_t* col, const float* val, int64_t nnz,
+                       const int64_t* order, int64_t n_order, const float* weights, int32_t n, int precision,
+                       int32_t* cluster_id, double* total_assoc, int32_t* n_clusters);
+
 /* ---------------------------------------------------------------- host-buffer entry points
  * What a non-torch FFI binding calls: pinned or pageable HOST pointers in, HOST pointers out;
  * the call allocates device buffers (cached per thread), copies H2D, runs the kernels on

@@ -324,6 +324,38 @@ def obj_cases(ref):
     print("wrote obj_io")
 
 
+def coarsen_cases(ref):
+    """The reference's weighted graph, coarsening, node orders and adjacency lists on noisy meshes whose
+    positions are scaled so that the Gaussian edge weights really vary (at unit scale they all clamp to
+    0.001), global NumPy generator seeded per case."""
+    d = {}
+    for tag, (V, F), scale, K, seed in (("ico3", mesh.icosphere(3), 0.004, 23, 4),
+                                        ("open", mesh.grid_mesh(23, 17, False), 0.01, 16, 7),
+                                        ("unit", mesh.grid_mesh(16, 16, True), 1.0, 16, 2)):
+        V = mesh.add_vertex_noise(V, F, 0.3, seed=1)
+        adj = mesh.faces_large_adj(F, K)
+        feat = mesh.face_features(V, F).astype(np.float64)
+        feat[:, 3:] *= scale
+        with contextlib.redirect_stdout(io.StringIO()):
+            coo = ref.utils.listToSparseWNormals(adj, feat[:, -3:], feat[:, :3])
+            coo_in = (coo.row.copy(), coo.col.copy(), coo.data.copy())  # coarsen() adds a zero diagonal in place
+            np.random.seed(seed)
+            graphs, perm = ref.coarsening.coarsen(coo, 4)
+            lists = [ref.utils.sparseToList(graphs[2 * l], K) for l in range(3)]
+        d[tag + "_adj"], d[tag + "_feat"], d[tag + "_seed"], d[tag + "_K"] = adj, feat, np.int32(seed), np.int32(K)
+        d[tag + "_coo_row"], d[tag + "_coo_col"], d[tag + "_coo_val"] = coo_in
+        d[tag + "_perm"] = np.asarray(perm, dtype=np.int32)
+        d[tag + "_inv_perm"] = np.asarray(ref.utils.inv_perm(perm), dtype=np.int32)
+        for l, (la, sat) in enumerate(lists):
+            d[tag + "_list%d" % l], d[tag + "_sat%d" % l] = la.astype(np.int32), np.bool_(sat)
+        for l, G in enumerate(graphs):
+            G = G.tocsr()
+            G.sort_indices()
+            d[tag + "_g%d_indptr" % l], d[tag + "_g%d_indices" % l], d[tag + "_g%d_data" % l] = G.indptr, G.indices, G.data
+    np.savez_compressed(os.path.join(OUT, "coarsen_cases.npz"), **d)
+    print("wrote coarsen_cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rr.load()
@@ -339,6 +371,7 @@ def main():
     net_and_vertex_cases(ref)
     index_cases(ref)
     obj_cases(ref)
+    coarsen_cases(ref)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,116 @@
+"""Graph pyramid of a patch (host half) against the reference's own functions: fixtures in
+tests/golden/coarsen_cases.npz (oracle/make_golden.py:coarsen_cases) and the preprocessing outputs of the
+reference driver already held by net_icosphere3.npz.  CPU only (the native pairing routine is host code)."""
+import numpy as np
+import pytest
+import scipy.sparse
+
+from conftest import golden
+from facet_graph_convolution_b200 import _lib, coarsening as co, mesh
+
+
+def test_compute_perm_known_answer():
+    # the reference's only known-answer test, Code/lib/coarsening.py:243-244
+    assert co.compute_perm([np.array([4, 1, 1, 2, 2, 3, 0, 0, 3]), np.array([2, 1, 0, 1, 0])]) == \
+        [[3, 4, 0, 9, 1, 2, 5, 8, 6, 7, 10, 11], [2, 4, 1, 3, 0, 5], [0, 1, 2]]
+    assert co.compute_perm([]) == []
+    with pytest.raises(AssertionError):
+        co.compute_perm([np.array([0, 0, 0])])
+
+
+@pytest.mark.parametrize("tag", ["ico3", "open", "unit"])
+def test_pyramid_equals_the_reference_functions(tag):
+    g = golden("coarsen_cases")
+    adj, feat, K = g[tag + "_adj"], g[tag + "_feat"], int(g[tag + "_K"])
+    coo = co.list_to_sparse_w_normals(adj, feat[:, -3:], feat[:, :3])
+    assert coo.data.dtype == np.float32
+    assert np.array_equal(coo.row, g[tag + "_coo_row"]) and np.array_equal(coo.col, g[tag + "_coo_col"])
+    assert np.array_equal(coo.data, g[tag + "_coo_val"])
+    if tag != "unit":
+        assert np.unique(coo.data).size > 1000  # the weights really vary in these cases
+    graphs, perm = co.coarsen(coo, 4, rng=np.random.RandomState(int(g[tag + "_seed"])))
+    assert np.array_equal(np.asarray(perm), g[tag + "_perm"])
+    assert np.array_equal(co.inv_perm(perm), g[tag + "_inv_perm"])
+    for l, G in enumerate(graphs):
+        G = G.tocsr()
+        G.sort_indices()
+        assert np.array_equal(G.indptr, g[tag + "_g%d_indptr" % l]) and np.array_equal(G.indices, g[tag + "_g%d_indices" % l])
+        assert np.array_equal(G.data, g[tag + "_g%d_data" % l])  # duplicate edges summed in the same order
+    for l in range(3):
+        lst, sat = co.sparse_to_list(graphs[2 * l], K)
+        assert lst.dtype == np.int32 and np.array_equal(lst, g[tag + "_list%d" % l]) and sat == bool(g[tag + "_sat%d" % l])
+
+
+def test_patch_pyramid_reproduces_the_reference_driver():
+    """net_icosphere3.npz holds what `InferenceMesh.addMesh_TimeEfficient` (dataClasses.py) prepared with the
+    global generator seeded to 0: level lists, permuted padded features, old-to-new permutation."""
+    g = golden("net_icosphere3")
+    K = g["adj0"].shape[2]
+    adj = mesh.faces_large_adj(g["F"], K)
+    np.random.seed(0)  # the default generator is the global one, like the reference
+    adjs, x, new_to_old, old_to_new = co.patch_pyramid(adj, mesh.face_features(g["V"], g["F"]), K)
+    for l in range(3):
+        assert np.array_equal(adjs[l], g["adj%d" % l])
+    assert np.array_equal(x[None].astype(np.float32), g["x"])
+    assert np.array_equal(old_to_new, g["perm"]) and int(g["nreal"]) == adj.shape[0]
+    assert np.array_equal(new_to_old[old_to_new[: adj.shape[0]]], np.arange(adj.shape[0]))
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_structure_at_size(precision):
+    V, F = mesh.icosphere(5)
+    V = mesh.add_vertex_noise(V, F, 0.3, seed=3)
+    K = 16
+    adj = mesh.faces_large_adj(F, K)
+    feat = mesh.face_features(V, F).astype(np.float64)
+    feat[:, 3:] *= 0.01
+    coo = co.list_to_sparse_w_normals(adj, feat[:, -3:], feat[:, :3])
+    rr, cc, vv = co._row_major_entries(coo)
+    deg = np.array(coo.sum(axis=0) - coo.diagonal()).squeeze()
+    rid = np.random.RandomState(0).permutation(coo.shape[0])
+    cluster, score = co.greedy_pairing(rr, cc, vv, rid, deg, precision)
+    sizes = np.bincount(cluster)
+    assert sizes.min() >= 1 and sizes.max() <= 2 and cluster.max() + 1 == sizes.size and score > 0
+    nbr = set(zip(rr.tolist(), cc.tolist()))
+    order = np.argsort(cluster, kind="stable")
+    pairs = order[np.repeat(np.cumsum(sizes) - sizes, 1)][sizes == 2], order[(np.cumsum(sizes) - 1)][sizes == 2]
+    assert all((a, b) in nbr for a, b in zip(pairs[0].tolist(), pairs[1].tolist()))  # mates share an edge
+    assert (sizes == 2).sum() > 0.8 * sizes.size  # a mesh graph pairs almost everything
+    graphs, perm = co.coarsen(coo, 4, rng=np.random.RandomState(1), precision=precision)
+    n = [G.shape[0] for G in graphs]
+    assert all(n[i] == 2 * n[i + 1] for i in range(4)) and len(perm) == n[0] and sorted(perm) == list(range(n[0]))
+    real = np.asarray(perm) < coo.shape[0]
+    G0 = graphs[0]
+    assert (G0 != G0.T).nnz == 0 and G0.diagonal().sum() == 0
+    assert np.all(np.diff(G0.indptr)[~real] == 0)  # fake nodes are isolated
+    lst, sat = co.sparse_to_list(G0, K)
+    assert not sat and np.array_equal(lst[:, 0], np.arange(n[0]) + 1)
+    # pooling by four consecutive nodes maps every fine edge into a coarse edge or inside one node
+    G2 = graphs[2].tocoo()
+    coarse = set(zip(G2.row.tolist(), G2.col.tolist()))
+    c0 = G0.tocoo()
+    assert all(a == b or (a, b) in coarse for a, b in zip((c0.row // 4).tolist(), (c0.col // 4).tolist()))
+
+
+def test_sparse_to_list_saturation_and_native_argument_checks():
+    A = scipy.sparse.csr_matrix(np.array([[5, 1, 1, 1], [1, 0, 0, 0], [1, 0, 0, 1], [1, 0, 1, 0]], np.float32))
+    lst, sat = co.sparse_to_list(A, 3)
+    assert sat and np.array_equal(lst, [[1, 2, 3], [2, 1, 0], [3, 1, 4], [4, 1, 3]])
+    lst, sat = co.sparse_to_list(A, 4)
+    assert not sat and np.array_equal(lst[0], [1, 2, 3, 4])
+    r = np.array([0, 0, 1, 2], np.int32)
+    c = np.array([1, 2, 0, 0], np.int32)
+    v = np.ones(4, np.float32)
+    w = np.ones(3, np.float32)
+    cl, score = co.greedy_pairing(r, c, v, np.array([0, 1, 2]), w)
+    assert cl.tolist() == [0, 0, 1] and score == 2.0  # first of two equal scores wins, node 2 stays single
+    cl, _ = co.greedy_pairing(r, c, v, np.array([2, 1, 0]), w)
+    assert cl.tolist() == [0, 1, 0]
+    with pytest.raises(_lib.FacetConvError, match="sorted"):
+        co.greedy_pairing(r[::-1], c, v, np.array([0, 1, 2]), w)
+    with pytest.raises(_lib.FacetConvError, match="precision"):
+        co.greedy_pairing(r, c, v, np.array([0, 1, 2]), w, precision=16)
+    with pytest.raises(_lib.FacetConvError, match="order"):
+        co.greedy_pairing(r, c, v, np.array([0, 1, 7]), w)
+    with pytest.raises(_lib.FacetConvError):
+        co.greedy_pairing(r[:0], c[:0], v[:0], np.array([0]), w)
