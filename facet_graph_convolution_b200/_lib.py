@@ -66,6 +66,7 @@ SIGNATURES = {
     "fgc_split2": (i32, [p, p, p, i64, i32, i32, p]),
     "fgc_gather_perm": (i32, [p, p, p, i64, i32, p]),
     "fgc_greedy_pairing": (i32, [p, p, p, i64, p, i64, p, i32, i32, p, p, p]),
+    "fgc_grow_patch": (i32, [p, i64, i32, i64, i64, p, i64, p, i64, p, p, p]),
     "fgc_face_features": (i32, [p, p, i64, i64, i32, p, p, sz, p]),
     "fgc_faces_adj_workspace": (sz, [i64, i64]),
     "fgc_build_faces_adj": (i32, [p, i64, i64, i32, p, p, i32, p, sz, p]),

@@ -25,7 +25,7 @@ import scipy.sparse
 from . import _lib
 
 __all__ = ["list_to_sparse_w_normals", "coarsen", "compute_perm", "perm_adjacency", "sparse_to_list", "inv_perm",
-           "greedy_pairing", "patch_pyramid"]
+           "greedy_pairing", "patch_pyramid", "get_graph_patch_w_mask", "extract_patches"]
 
 
 def list_to_sparse_w_normals(adj, nodes_pos, nodes_normals):
@@ -209,3 +209,60 @@ def patch_pyramid(adj, features, K, level_num=3, step_num=2, rng=None, precision
     new_to_old = np.asarray(new_to_old, dtype=np.int64)
     padded = np.concatenate([features, np.zeros((new_to_old.size - features.shape[0], features.shape[1]))], axis=0)
     return adjs, padded[new_to_old], new_to_old, inv_perm(new_to_old)
+
+
+def get_graph_patch_w_mask(f_adj, nodes_num, seed, mask, min_patch_size):
+    """One patch grown breadth-first from `seed` (utils.py:1508-1696): (patch adjacency [n_p, K] 1-based in
+    patch-local ids, original id of every patch node, next seed or -1).  Native host routine `fgc_grow_patch`."""
+    f_adj = np.ascontiguousarray(f_adj, dtype=np.int32)
+    n, K = f_adj.shape
+    taken = np.ascontiguousarray(np.asarray(mask) == 1, dtype=np.uint8)
+    if taken.size != n:
+        raise _lib.FacetConvError("get_graph_patch_w_mask: mask has %d entries for %d nodes" % (taken.size, n))
+    cap = max(int(nodes_num), int(min_patch_size)) + K
+    out = np.empty((cap, K), dtype=np.int32)
+    old = np.empty(cap, dtype=np.int64)
+    count, nxt = C.c_int64(0), C.c_int64(-1)
+    _lib.check(_lib.lib().fgc_grow_patch(f_adj.ctypes.data, n, K, int(nodes_num), int(seed), taken.ctypes.data,
+                                         int(min_patch_size), out.ctypes.data, cap, old.ctypes.data,
+                                         C.byref(count), C.byref(nxt)), "fgc_grow_patch")
+    return out[: count.value].astype(np.int64), old[: count.value].copy(), int(nxt.value)
+
+
+def extract_patches(f_adj, features, patch_size, K, min_patch_size=2000, level_num=3, step_num=2, rng=None,
+                    precision=32, min_component=100):
+    """The patch loop of the reference's preprocessing (dataClasses.py:69-150) for a mesh above the size limit:
+    seeds are drawn among the facets no patch owns yet (or taken from the previous patch's border), every
+    patch is grown to `patch_size` (at least `min_patch_size` with context), components under 100 facets are
+    dropped, and each patch gets its pyramid.  Returns `patches.Patch` objects (x, level lists, global facet
+    ids, old-to-new permutation).  `rng` as in `coarsen`: the global NumPy generator by default, consumed in
+    the reference's order (one `randint` per fresh seed, then the coarsening draws)."""
+    from .patches import Patch
+    rng = np.random if rng is None else rng
+    f_adj = np.asarray(f_adj)
+    features = np.asarray(features)
+    n = f_adj.shape[0]
+    owned = np.zeros(n)
+    out = []
+    next_seed = -1
+    while np.any(owned == 0):
+        if next_seed == -1:
+            free = np.flatnonzero(owned == 0)
+            seed = int(free[rng.randint(free.shape[0])])
+        else:
+            seed = next_seed
+            if owned[seed] == 1:
+                raise _lib.FacetConvError("extract_patches: the border seed %d is already owned" % seed)
+        p_adj, old, next_seed = get_graph_patch_w_mask(f_adj, patch_size, seed, owned, min_patch_size)
+        owned[old] = 1
+        if old.shape[0] < min_component:
+            continue
+        feats = features[old]
+        if level_num > 1:
+            adjs, x, _, old_to_new = patch_pyramid(p_adj, feats, K, level_num, step_num, rng, precision)
+            adjs = [a[0].astype(np.int32) for a in adjs]
+        else:
+            adjs, x, old_to_new = [p_adj.astype(np.int32)], feats, None
+        out.append(Patch(x=x.astype(np.float32), adjs=adjs, face_ids=old.astype(np.int64),
+                         perm=None if old_to_new is None else old_to_new.astype(np.int32)))
+    return out

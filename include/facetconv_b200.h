@@ -298,6 +298,17 @@ FGC_API int fgc_greedy_pairing(const int32_t* row, const int32_t* col, const flo
                        const int64_t* order, int64_t n_order, const float* weights, int32_t n, int precision,
                        int32_t* cluster_id, double* total_assoc, int32_t* n_clusters);
 
+/* Host-only: breadth-first growth of one patch, reference Code/utils.py:1508-1696 `getGraphPatch_wMask`.
+ * adj[n][K] 1-based / 0-padded with the node itself in column 0, mask[n] != 0 for nodes earlier patches own.
+ * Grows from `seed` until nodes_num nodes are reached (owned nodes join but wait in a second queue that is
+ * only expanded while the patch is below min_patch), then closes the rows still queued with the neighbours
+ * that are inside.  adj_out[capacity][K] (capacity >= max(nodes_num, min_patch) + K) gets patch-local lists,
+ * old_index[capacity] the original ids in local order, *patch_nodes the size, *next_seed a not-owned node
+ * adjacent to the patch or -1. */
+FGC_API int fgc_grow_patch(const int32_t* adj, int64_t n, int K, int64_t nodes_num, int64_t seed,
+                   const uint8_t* mask, int64_t min_patch, int32_t* adj_out, int64_t capacity,
+                   int64_t* old_index, int64_t* patch_nodes, int64_t* next_seed);
+
 /* ---------------------------------------------------------------- host-buffer entry points
  * What a non-torch FFI binding calls: pinned or pageable HOST pointers in, HOST pointers out;
  * the call allocates device buffers (cached per thread), copies H2D, runs the kernels on

@@ -356,6 +356,45 @@ def coarsen_cases(ref):
     print("wrote coarsen_cases")
 
 
+def patch_cases(ref):
+    """The reference's patch growth (`getGraphPatch_wMask`) on a noisy icosphere-4 with a mask that fills up
+    between calls, and its whole patch loop (`addMesh_TimeEfficient` above the size limit: seeds, growth,
+    small-component rule, pyramid per patch) with the global generator seeded."""
+    V, F = mesh.icosphere(4)
+    V = mesh.add_vertex_noise(V, F, 0.3, seed=2)
+    K = 16
+    adj = mesh.faces_large_adj(F, K)
+    d = {"V": V, "F": F, "K": np.int32(K)}
+    mask = np.zeros(F.shape[0])
+    rs = np.random.RandomState(0)
+    for t in range(6):
+        seed = int(rs.randint(F.shape[0]))
+        nn = int(rs.choice([300, 1000, 2500]))
+        mp = int(rs.choice([100, nn - 50, nn]))
+        with contextlib.redirect_stdout(io.StringIO()):
+            a, o, nxt = ref.utils.getGraphPatch_wMask(adj, nn, seed, mask, mp)
+        d["g%d_args" % t] = np.array([nn, seed, mp, nxt], dtype=np.int64)
+        d["g%d_mask" % t] = mask.astype(np.uint8)
+        d["g%d_adj" % t], d["g%d_old" % t] = a.astype(np.int32), o.astype(np.int64)
+        if t % 2 == 0 and mask[o].min() == 0:
+            mask[o] = 1
+    old_min = ref.dataClasses.MIN_PATCH_SIZE
+    ref.dataClasses.MIN_PATCH_SIZE = 700
+    try:
+        im = preprocess(ref, V, F, K, seed=5, max_patch=1500)
+    finally:
+        ref.dataClasses.MIN_PATCH_SIZE = old_min
+    d["drv_args"] = np.array([1500, 700, 5, len(im.in_list)], dtype=np.int64)  # patch size, min size, seed, patches
+    for i in range(len(im.in_list)):
+        d["drv%d_x" % i] = im.in_list[i][0].astype(np.float32)
+        for l in range(3):
+            d["drv%d_adj%d" % (i, l)] = im.adj_list[i][l][0].astype(np.int32)
+        d["drv%d_ids" % i] = np.asarray(im.patch_indices[i], dtype=np.int64)
+        d["drv%d_perm" % i] = np.asarray(im.permutations[i], dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, "patch_cases.npz"), **d)
+    print("wrote patch_cases", len(im.in_list))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rr.load()
@@ -372,6 +411,7 @@ def main():
     index_cases(ref)
     obj_cases(ref)
     coarsen_cases(ref)
+    patch_cases(ref)
 
 
 if __name__ == "__main__":

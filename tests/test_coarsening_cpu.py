@@ -114,3 +114,51 @@ def test_sparse_to_list_saturation_and_native_argument_checks():
         co.greedy_pairing(r, c, v, np.array([0, 1, 7]), w)
     with pytest.raises(_lib.FacetConvError):
         co.greedy_pairing(r[:0], c[:0], v[:0], np.array([0]), w)
+
+
+def test_patch_growth_equals_the_reference_function():
+    """tests/golden/patch_cases.npz: `getGraphPatch_wMask` (utils.py:1508-1696) called six times on a noisy
+    icosphere-4 while the ownership mask fills up (context nodes, the minimum-size second phase, next seeds)."""
+    g = golden("patch_cases")
+    adj = mesh.faces_large_adj(g["F"], int(g["K"]))
+    for t in range(6):
+        nn, seed, mp, nxt = (int(v) for v in g["g%d_args" % t])
+        a, old, s = co.get_graph_patch_w_mask(adj, nn, seed, g["g%d_mask" % t].astype(np.float64), mp)
+        assert np.array_equal(a, g["g%d_adj" % t]) and np.array_equal(old, g["g%d_old" % t]) and s == nxt, t
+    # structure: local ids are a bijection onto the patch, column 0 is the node, lists stay inside the patch
+    a, old, _ = co.get_graph_patch_w_mask(adj, 800, 17, np.zeros(adj.shape[0]), 100)
+    assert np.unique(old).size == old.size and np.array_equal(a[:, 0], np.arange(a.shape[0]) + 1)
+    assert a.min() >= 0 and a.max() <= a.shape[0]
+    inside = set(old.tolist())
+    for i in (0, 5, a.shape[0] - 1):
+        want = [j - 1 for j in adj[old[i], 1:] if j > 0 and j - 1 in inside]
+        got = [int(old[j - 1]) for j in a[i, 1:] if j > 0]
+        assert got == want
+    with pytest.raises(_lib.FacetConvError, match="seed"):
+        co.get_graph_patch_w_mask(adj, 100, adj.shape[0], np.zeros(adj.shape[0]), 50)
+    with pytest.raises(_lib.FacetConvError, match="mask"):
+        co.get_graph_patch_w_mask(adj, 100, 0, np.zeros(3), 50)
+    bad = adj.copy()
+    bad[3, 2] = adj.shape[0] + 5
+    with pytest.raises(_lib.FacetConvError, match="outside"):
+        co.get_graph_patch_w_mask(bad, 100, 3, np.zeros(adj.shape[0]), 50)
+
+
+def test_patch_loop_equals_the_reference_driver():
+    """The whole preprocessing of a mesh above the size limit (dataClasses.py:69-150) with the generator seeded
+    like the reference run: same patches, same pyramids, same permutations."""
+    g = golden("patch_cases")
+    K = int(g["K"])
+    patch_size, min_size, seed, count = (int(v) for v in g["drv_args"])
+    adj = mesh.faces_large_adj(g["F"], K)
+    feat = mesh.face_features(g["V"], g["F"])
+    ps = co.extract_patches(adj, feat, patch_size, K, min_patch_size=min_size, rng=np.random.RandomState(seed))
+    assert len(ps) == count
+    covered = np.zeros(adj.shape[0], dtype=bool)
+    for i, p in enumerate(ps):
+        assert np.array_equal(p.x, g["drv%d_x" % i]) and np.array_equal(p.face_ids, g["drv%d_ids" % i])
+        assert np.array_equal(p.perm, g["drv%d_perm" % i])
+        for l in range(3):
+            assert p.adjs[l].dtype == np.int32 and np.array_equal(p.adjs[l], g["drv%d_adj%d" % (i, l)])
+        covered[p.face_ids] = True
+    assert covered.all()

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import golden
 from oracle import closed_form as cf
 
 pytestmark = pytest.mark.gpu
@@ -146,3 +147,40 @@ def test_segmented_normalize_matches_per_patch_normalize():
         assert np.abs(y[b:b + 1, :n] - one).max() < 1e-6
         assert np.abs(y[b:b + 1, :n] - cf.normalize_tensor(x[b:b + 1, :n].astype(np.float64))).max() < 1e-5
         assert not y[b, n:].any()
+
+
+def test_from_raw_mesh_to_denoised_vertices_equals_the_reference_pipeline(tmp_path):
+    """Everything between an OBJ file and the denoised vertices with this package only -- OBJ reader, GPU
+    adjacency / edge maps / face features, host patch pyramid (seeded like the reference run), network from a
+    Saver file, normalisation, un-permutation, vertex update -- against the outputs the reference's own driver
+    and graph functions produced for the same mesh (net_icosphere3.npz)."""
+    from facet_graph_convolution_b200 import checkpoint, coarsening, mesh_io, model as fm, ops
+    g = golden("net_icosphere3")
+    K = g["adj0"].shape[2]
+    F = torch.from_numpy(g["F"].astype(np.int32)).cuda()
+    V = torch.from_numpy(g["V"].astype(np.float32)).cuda()
+    adj, _ = ops.build_faces_adj(F, K=K)
+    feat = ops.face_features(V, F)
+    np.random.seed(0)
+    adjs, x, new_to_old, old_to_new = coarsening.patch_pyramid(adj.cpu().numpy(), feat.cpu().numpy(), K)
+    assert all(np.array_equal(a, g["adj%d" % l]) for l, a in enumerate(adjs))
+    assert np.array_equal(x[None].astype(np.float32), g["x"])
+    prefix = checkpoint.save_network(str(tmp_path / "net"), [g["p%02d" % i] for i in range(int(g["nparams"]))])
+    params = checkpoint.load_network(checkpoint.latest_checkpoint(str(tmp_path)))
+    dev = torch.device("cuda:0")
+    with torch.no_grad(), fm.variable_store(fm.VariableStore(dev, params=params)):
+        y = fm.get_model_reg_multi_scale(torch.from_numpy(x[None].astype(np.float32)).cuda(),
+                                         [torch.from_numpy(a).cuda() for a in adjs], 1.0)
+    assert np.abs(y.cpu().numpy() - g["y_raw"]).max() < 1e-5
+    yn = fm.normalizeTensor(y)
+    out = ops.gather_perm(yn.reshape(-1, 3), torch.from_numpy(old_to_new.astype(np.int32)).cuda())[: F.shape[0]]
+    pred = cf.host_normalize(out.cpu().numpy())
+    assert np.abs(pred - g["pred_normals"]).max() < 1e-4
+    e_map, v_e = ops.build_edge_maps(F, max_edges=20, nv=V.shape[0])
+    assert np.array_equal(e_map.cpu().numpy(), g["e_map"]) and np.array_equal(v_e.cpu().numpy(), g["v_e_map"])
+    xo = fm.update_position2(V[None], torch.from_numpy(pred[None].astype(np.float32)).cuda(), e_map, v_e,
+                             iter_num=60, max_edges=20)
+    assert np.abs(xo.cpu().numpy() - g["verts_out"]).max() < 1e-4
+    mesh_io.write_mesh(xo[0].cpu().numpy(), g["F"], str(tmp_path / "out.obj"))
+    V2, _, _, F2, _ = mesh_io.load_mesh(str(tmp_path), "out.obj")
+    assert np.array_equal(F2, g["F"]) and np.abs(V2 - g["verts_out"][0]).max() < 1e-4
