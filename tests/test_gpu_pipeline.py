@@ -160,9 +160,12 @@ def test_from_raw_mesh_to_denoised_vertices_equals_the_reference_pipeline(tmp_pa
     F = torch.from_numpy(g["F"].astype(np.int32)).cuda()
     V = torch.from_numpy(g["V"].astype(np.float32)).cuda()
     adj, _ = ops.build_faces_adj(F, K=K)
-    feat = ops.face_features(V, F)
+    from facet_graph_convolution_b200 import mesh
+    feat = mesh.face_features(g["V"], g["F"])  # the fixture's vertices are float64, like the reference run
+    # the GPU builder sees them rounded to fp32: thin noisy triangles move a unit normal by a few 1e-6
+    assert np.abs(ops.face_features(V, F).cpu().numpy() - feat).max() < 2e-5
     np.random.seed(0)
-    adjs, x, new_to_old, old_to_new = coarsening.patch_pyramid(adj.cpu().numpy(), feat.cpu().numpy(), K)
+    adjs, x, new_to_old, old_to_new = coarsening.patch_pyramid(adj.cpu().numpy(), feat, K)
     assert all(np.array_equal(a, g["adj%d" % l]) for l, a in enumerate(adjs))
     assert np.array_equal(x[None].astype(np.float32), g["x"])
     prefix = checkpoint.save_network(str(tmp_path / "net"), [g["p%02d" % i] for i in range(int(g["nparams"]))])
@@ -177,7 +180,7 @@ def test_from_raw_mesh_to_denoised_vertices_equals_the_reference_pipeline(tmp_pa
     pred = cf.host_normalize(out.cpu().numpy())
     assert np.abs(pred - g["pred_normals"]).max() < 1e-4
     e_map, v_e = ops.build_edge_maps(F, max_edges=20, nv=V.shape[0])
-    assert np.array_equal(e_map.cpu().numpy(), g["e_map"]) and np.array_equal(v_e.cpu().numpy(), g["v_e_map"])
+    assert np.array_equal(e_map.cpu().numpy(), g["e_map"][0]) and np.array_equal(v_e.cpu().numpy(), g["v_e_map"][0])
     xo = fm.update_position2(V[None], torch.from_numpy(pred[None].astype(np.float32)).cuda(), e_map, v_e,
                              iter_num=60, max_edges=20)
     assert np.abs(xo.cpu().numpy() - g["verts_out"]).max() < 1e-4
