@@ -9,6 +9,12 @@ from conftest import golden
 from facet_graph_convolution_b200 import _lib, coarsening as co, mesh
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _library():
+    from facet_graph_convolution_b200.build import build
+    build()  # no-op when libfacetconv_b200.so is up to date; the pairing / growth routines live in it
+
+
 def test_compute_perm_known_answer():
     # the reference's only known-answer test, Code/lib/coarsening.py:243-244
     assert co.compute_perm([np.array([4, 1, 1, 2, 2, 3, 0, 0, 3]), np.array([2, 1, 0, 1, 0])]) == \
