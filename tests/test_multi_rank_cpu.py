@@ -164,3 +164,50 @@ def test_rotation_matrix_and_feature_rotation():
     y = T.rotate_features(x, torch.from_numpy(R.astype(np.float32)))
     ref = np.concatenate([x[0, :, :3].numpy() @ R.T, x[0, :, 3:].numpy() @ R.T], axis=1)
     assert np.abs(y[0].numpy() - ref).max() < 1e-5
+
+
+def _extracted_patches():
+    from facet_graph_convolution_b200 import coarsening, mesh
+    V, F = mesh.icosphere(4)
+    V = mesh.add_vertex_noise(V, F, 0.3, seed=2)
+    adj = mesh.faces_large_adj(F, 16)
+    ps = coarsening.extract_patches(adj, mesh.face_features(V, F), 1500, 16, min_patch_size=700,
+                                    rng=np.random.RandomState(5))
+    return ps, F.shape[0]
+
+
+def _worker_extracted(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        patches, nf = _extracted_patches()  # every rank cuts the same patches from the same seed
+        q.put((rank, P.infer_sharded(patches, nf, _fake_forward, rank, world)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_inference_on_patches_cut_by_the_reference_patch_loop():
+    """Patches produced by `coarsening.extract_patches` (overlapping context facets, tree-order permutation,
+    fake rows) dealt to two ranks: same merged normals as one process and as the reference's merge."""
+    patches, nf = _extracted_patches()
+    assert len(patches) >= 3 and sum(p.num_real for p in patches) > nf  # context facets are computed twice
+    single = P.infer_sharded(patches, nf, _fake_forward, 0, 1)
+    acc = np.zeros((nf, 3))
+    for p in patches:
+        acc[p.face_ids] += _fake_forward(p)[0][p.perm][: p.num_real]
+    for _ in range(2):
+        acc = acc * (1 / (np.sqrt((acc * acc).sum(1))[:, None] + 1e-8))
+    assert np.abs(single - acc).max() < 1e-12
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_extracted, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    for _, pred in res:
+        assert np.abs(pred - single).max() < 1e-6
