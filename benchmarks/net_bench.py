@@ -69,7 +69,7 @@ def cpu_net_forward(x, adjs, params, repeat=1):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="c1", choices=["c1", "c3", "c4", "c5", "index"])
+    ap.add_argument("--config", default="c1", choices=["c1", "c3", "c4", "c5", "index", "mesh"])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--grid", type=int, default=1000, help="c3: quads per side (1000 -> 2M facets)")
@@ -368,6 +368,68 @@ def main():
                                             "inside the timed region" % (nx, ny, nf, nv)},
                      "output_bytes": out_bytes, "algorithmic_GBps": (nf * 12 + out_bytes) / (ms * 1e-3) / 1e9,
                      "cpu_baseline": cpu})
+
+    elif args.config == "mesh":
+        # The reference's `inferNet` from file to file on one GPU (Code/train.py:29-150): OBJ in, adjacency /
+        # edge maps / features (GPU), patch pyramid (host, f-2), network from a Saver file (f-3),
+        # normalizeTensor, un-permutation, host normalize, 60 vertex-update sweeps, OBJ out (f-4).  Wall-clock
+        # per stage (file I/O and host preprocessing are CPU work, so CUDA events alone would miss them).
+        import tempfile
+        from facet_graph_convolution_b200 import checkpoint, coarsening, mesh_io
+        K = 23  # settings.py:23 K_faces
+        V0, F0 = mesh.icosphere(5)
+        V0 = mesh.add_vertex_noise(V0, F0, 0.3, 0)
+        tmp = tempfile.mkdtemp()
+        mesh_io.write_mesh(V0, F0, os.path.join(tmp, "noisy.obj"))
+        prefix = checkpoint.save_network(os.path.join(tmp, "net"), params, global_step=1)
+
+        def run(seed):
+            tm = {}
+            t = time.perf_counter()
+            Vh, _, _, Fh, _ = mesh_io.load_mesh(tmp, "noisy.obj", 0, False)
+            tm["read_obj"] = time.perf_counter() - t
+            t = time.perf_counter()
+            Fd, Vd = T(Fh.astype(np.int32)), T(Vh)
+            adj, _ = ops.build_faces_adj(Fd, K=K, nv=Vh.shape[0])
+            e_map, v_e = ops.build_edge_maps(Fd, 20, nv=Vh.shape[0])
+            feat = ops.face_features(Vd, Fd)
+            adj_h, feat_h = adj.cpu().numpy(), feat.cpu().numpy()
+            tm["gpu_index_and_features"] = time.perf_counter() - t
+            t = time.perf_counter()
+            adjs, x, _, old_to_new = coarsening.patch_pyramid(adj_h, feat_h, K, rng=np.random.RandomState(seed))
+            tm["host_pyramid"] = time.perf_counter() - t
+            t = time.perf_counter()
+            store = fm.VariableStore(dev, params=checkpoint.load_network(checkpoint.latest_checkpoint(tmp), verify=True))
+            tm["read_checkpoint"] = time.perf_counter() - t
+            t = time.perf_counter()
+            with torch.no_grad(), fm.variable_store(store):
+                y = fm.get_model_reg_multi_scale(T(x[None].astype(np.float32)), [T(a) for a in adjs], 1.0)
+                n = fm.normalizeTensor(y)
+                out = ops.gather_perm(n.reshape(-1, 3), T(old_to_new.astype(np.int32)))[: Fh.shape[0]]
+                pred = patches.host_normalize(out.cpu().numpy()).astype(np.float32)
+                xo = fm.update_position2(Vd[None], T(pred[None]), e_map, v_e, iter_num=60, max_edges=20)
+                Vout = xo[0].cpu().numpy()
+            tm["network_and_vertex_update"] = time.perf_counter() - t
+            t = time.perf_counter()
+            mesh_io.write_mesh(Vout, Fh, os.path.join(tmp, "denoised.obj"))
+            tm["write_obj"] = time.perf_counter() - t
+            return tm, Fh.shape[0]
+
+        for i in range(2):
+            run(i)
+        n0 = L.fgc_launch_count()
+        runs = [run(10 + i) for i in range(5)]
+        launches = (L.fgc_launch_count() - n0) / len(runs)
+        nf = runs[0][1]
+        stages = {k: float(np.median([r[0][k] for r in runs])) * 1e3 for k in runs[0][0]}
+        ms = float(np.median([sum(r[0].values()) for r in runs])) * 1e3
+        line.update({"value": nf / (ms * 1e-3), "steps": len(runs), "warmup": 2, "ms_per_step": ms, "scaling": "weak",
+                     "gpu_launches": launches, "stages_ms": stages,
+                     "config": {"workload": "file to file: noisy icosphere-5 OBJ (%d faces) -> adjacency K=%d, edge maps, "
+                                            "features on the GPU -> host patch pyramid (4 coarsenings) -> network from a "
+                                            "Saver checkpoint -> normals -> 60 vertex-update sweeps -> OBJ; wall clock, "
+                                            "median of %d runs" % (nf, K, len(runs))},
+                     "cpu_baseline": None})
 
     else:  # c4
         from facet_graph_convolution_b200 import train as ftrain

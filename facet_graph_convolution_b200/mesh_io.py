@@ -64,13 +64,17 @@ def write_mesh(vl, fl, strFileName):
     (0, 0, .) ends the list (the padding conventions of the patch pipeline)."""
     vl = np.asarray(vl)
     fl = np.asarray(fl)
-    lines = ["v " + "".join("%.6f " % x for x in row) for row in vl]
-    one = fl.astype(np.int64) + 1 if fl.size else np.zeros((0, 3), np.int64)
-    for row in one:
-        if row[0] == 1 and row[1] == 1:
-            break
-        if row[0] == 0 and row[1] == 0:
-            continue
-        lines.append("f " + "".join("%d " % i for i in row))
+    text = ""
+    if vl.size:
+        row = "v " + "%.6f " * vl.shape[1] + "\n"
+        text = (row * vl.shape[0]) % tuple(vl.ravel().tolist())
+    if fl.size:
+        one = fl.astype(np.int64) + 1
+        end = np.flatnonzero((one[:, 0] == 1) & (one[:, 1] == 1))
+        if end.size:
+            one = one[: end[0]]
+        one = one[~((one[:, 0] == 0) & (one[:, 1] == 0))]
+        row = "f " + "%d " * one.shape[1] + "\n"
+        text += (row * one.shape[0]) % tuple(one.ravel().tolist())
     with open(strFileName, "w") as f:
-        f.write("\n".join(lines) + ("\n" if lines else ""))
+        f.write(text)
