@@ -70,7 +70,15 @@ def greedy_pairing(rr, cc, vv, rid, weights, precision=32):
 
 def _row_major_entries(W):
     """Non-zero entries of W (duplicates summed) ordered by row, then column."""
-    r, c, v = scipy.sparse.find(W)
+    if scipy.sparse.issparse(W) and W.format == "csr" and W.has_canonical_format:
+        r = np.repeat(np.arange(W.shape[0], dtype=np.int32), np.diff(W.indptr))
+        nz = W.data != 0
+        return r[nz], W.indices[nz], W.data[nz]
+    r, c, v = scipy.sparse.find(W)  # sums duplicates the way the reference's call does
+    if r.size > 1:
+        dr = np.diff(r)
+        if np.all((dr > 0) | ((dr == 0) & (np.diff(c) > 0))):
+            return r, c, v
     order = np.lexsort((c, r))
     return r[order], c[order], v[order]
 
