@@ -20,9 +20,11 @@ Host-side file handling, no device work: nothing here touches the CUDA library.
 PARITY UNPINNED: `/root/reference` ships no checkpoint file and TensorFlow is not installed in this image, so
 the reader has only been exercised on files produced by the writer below (format restated from the published
 tensor-bundle / table layout), and the names are derived from the scoping rules rather than read from a real
-`.index`.  `tests/test_checkpoint_cpu.py` checks the pieces that have independent known answers (CRC-32C test
-vectors, the masked-CRC definition, varint coding, the uniquified-name sequence worked out by hand from the
-reference source).
+`.index`.  `tests/test_checkpoint_cpu.py` checks the pieces that have independent known answers: CRC-32C test
+vectors, varint coding, the uniquified-name sequence worked out by hand from the reference source, and --
+against the TensorFlow-derived code TensorBoard ships in this image -- the masked CRC, the dtype enum values
+and the TensorShapeProto / VersionDef encodings.  What stays unpinned is the table block layout and the
+BundleEntryProto / BundleHeaderProto field numbers.
 """
 import os
 import re

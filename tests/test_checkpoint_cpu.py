@@ -162,3 +162,35 @@ def test_corruption_and_mismatches_are_reported(tmp_path):
     assert ck.latest_checkpoint(str(tmp_path / "nowhere")) is None
     with pytest.raises(ck.CheckpointError, match="expected"):
         ck.save_network(str(tmp_path / "c" / "net"), params[:-1])
+
+
+def test_crc_and_protobuf_pieces_against_tensorboard_implementations():
+    """TensorBoard ships an independent masked CRC-32C (TFRecord framing uses the same mask as the table and
+    bundle formats) and TensorFlow's generated protobuf classes for shapes, dtypes and versions: the pieces of
+    the bundle encoding they cover must parse / agree."""
+    tb = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    shape_pb2 = pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    types_pb2 = pytest.importorskip("tensorboard.compat.proto.types_pb2")
+    versions_pb2 = pytest.importorskip("tensorboard.compat.proto.versions_pb2")
+    rs = np.random.RandomState(1)
+    for n in (0, 1, 9, 4096, 20000):
+        data = rs.randint(0, 256, n).astype(np.uint8).tobytes()
+        assert ck.crc32c(data) == tb.crc32c(data)
+        assert ck._mask_crc(ck.crc32c(data)) == tb.masked_crc32c(data)
+    assert {types_pb2.DT_FLOAT: "<f4", types_pb2.DT_DOUBLE: "<f8", types_pb2.DT_INT32: "<i4",
+            types_pb2.DT_INT64: "<i8"} == {k: v.str for k, v in ck._DTYPES.items()}
+    arr = np.zeros((9, 64, 128), np.float32)
+    fields = {fn: v for fn, _, v in ck._pb_fields(ck._encode_entry(arr, 1234, 0xDEADBEEF))}
+    shape = shape_pb2.TensorShapeProto()
+    shape.ParseFromString(fields[2])
+    assert [d.size for d in shape.dim] == [9, 64, 128] and not shape.unknown_rank
+    assert fields[1] == types_pb2.DT_FLOAT and fields[4] == 1234 and fields[5] == arr.nbytes and fields[6] == 0xDEADBEEF
+    # and the other way: a shape serialised by the real class is decoded by the reader
+    real = shape_pb2.TensorShapeProto(dim=[shape_pb2.TensorShapeProto.Dim(size=s) for s in (3, 1, 70000)])
+    entry = b"\x08\x01\x12" + ck._put_varint(len(real.SerializeToString())) + real.SerializeToString() + b"\x28\x04"
+    assert ck._decode_entry(entry)["shape"] == [3, 1, 70000]
+    scalar = ck._decode_entry(ck._encode_entry(np.zeros((), np.int64), 0, 1))
+    assert scalar["shape"] == [] and scalar["dtype"] == types_pb2.DT_INT64 and scalar["size"] == 8
+    ver = versions_pb2.VersionDef()
+    ver.ParseFromString(b"\x08\x01")  # the header's version submessage written by write_bundle
+    assert ver.producer == 1
