@@ -34,7 +34,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 __all__ = ["network_variables", "read_bundle", "write_bundle", "latest_checkpoint", "load_network",
-           "save_network", "crc32c", "CheckpointError"]
+           "save_network", "save_training_state", "load_training_state", "crc32c", "CheckpointError"]
 
 
 class CheckpointError(RuntimeError):
@@ -531,3 +531,59 @@ def save_network(prefix: str, params: Sequence, in_channels: int = 6, multi_scal
     with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), "checkpoint"), "w") as f:
         f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))
     return prefix
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+
+
+def save_training_state(prefix: str, params: Sequence, adam_m: Sequence, adam_v: Sequence, step: int,
+                        b1: float = 0.9, b2: float = 0.999, in_channels: int = 6, multi_scale: bool = False,
+                        scope: str = "model", global_step: Optional[int] = None) -> str:
+    """A training checkpoint as the reference's Saver writes it after `step` Adam updates (train.py:429, 520,
+    552): the variables, their Adam slots `<name>/Adam` (first moment) and `<name>/Adam_1` (second moment), the
+    optimiser's `beta1_power` / `beta2_power` (TF keeps beta^(step+1)) and the unnamed step counter
+    `Variable`.  File name and `checkpoint` state file as `save_network`."""
+    spec = network_variables(in_channels, multi_scale, scope)
+    if not (len(params) == len(adam_m) == len(adam_v) == len(spec)):
+        raise CheckpointError("expected %d variables with one first and one second moment each" % len(spec))
+    tensors: Dict[str, np.ndarray] = {}
+    for (name, shape), p, m, v in zip(spec, params, adam_m, adam_v):
+        for suffix, t in (("", p), ("/Adam", m), ("/Adam_1", v)):
+            a = _np(t).astype(np.float32, copy=False)
+            if tuple(a.shape) != tuple(shape):
+                raise CheckpointError("%s%s: shape %s, network expects %s" % (name, suffix, tuple(a.shape), tuple(shape)))
+            tensors[name + suffix] = a
+    tensors["beta1_power"] = np.float32(b1 ** (int(step) + 1)).reshape(())
+    tensors["beta2_power"] = np.float32(b2 ** (int(step) + 1)).reshape(())
+    tensors["Variable"] = np.int32(step).reshape(())
+    if global_step is not None:
+        prefix = "%s-%d" % (prefix, int(global_step))
+    write_bundle(prefix, tensors)
+    base = os.path.basename(prefix)
+    with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), "checkpoint"), "w") as f:
+        f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))
+    return prefix
+
+
+def load_training_state(prefix: str, in_channels: int = 6, multi_scale: bool = False, scope: str = "model",
+                        verify: bool = True) -> dict:
+    """{'params', 'm', 'v': lists in creation order, 'step': Adam updates done} from a training checkpoint.
+    A file without optimiser slots (an inference export) gives zero moments and step 0."""
+    spec = network_variables(in_channels, multi_scale, scope)
+    got = read_bundle(prefix, None, verify)
+    out = {"params": [], "m": [], "v": [], "step": 0}
+    for name, shape in spec:
+        if name not in got:
+            raise CheckpointError("%s: variables not in the checkpoint: %s" % (prefix, name))
+        for key, suffix in (("params", ""), ("m", "/Adam"), ("v", "/Adam_1")):
+            a = got.get(name + suffix)
+            if a is None:
+                a = np.zeros(shape, np.float32)
+            if tuple(a.shape) != tuple(shape):
+                raise CheckpointError("%s%s: checkpoint shape %s, network expects %s"
+                                      % (name, suffix, tuple(a.shape), tuple(shape)))
+            out[key].append(a.astype(np.float32, copy=False))
+    if "Variable" in got and got["Variable"].shape == ():
+        out["step"] = int(got["Variable"])
+    return out

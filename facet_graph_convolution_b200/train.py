@@ -106,6 +106,27 @@ class Adam:
             o += n
 
 
+    def state_lists(self):
+        """(first moments, second moments) per parameter, creation order -- the Saver's `/Adam`, `/Adam_1` slots."""
+        ms, vs, o = [], [], 0
+        for p, n in zip(self.b.params, self.b.sizes):
+            ms.append(self.m[o:o + n].view_as(p))
+            vs.append(self.v[o:o + n].view_as(p))
+            o += n
+        return ms, vs
+
+    @torch.no_grad()
+    def load_state(self, ms, vs, step: int):
+        """Resume from per-parameter moments and the number of updates already done
+        (`checkpoint.load_training_state`)."""
+        o = 0
+        for p, n, m, v in zip(self.b.params, self.b.sizes, ms, vs):
+            self.m[o:o + n].copy_(torch.as_tensor(m, dtype=self.m.dtype).reshape(-1))
+            self.v[o:o + n].copy_(torch.as_tensor(v, dtype=self.v.dtype).reshape(-1))
+            o += n
+        self.t = int(step)
+
+
 def loss_on_patch(forward, x, adjs, gt, rng: np.random.RandomState, samples: int = COST_SAMPLES,
                   augment: bool = True):
     """One patch of the training objective.  `forward(x, adjs)` returns the raw network output

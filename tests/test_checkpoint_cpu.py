@@ -194,3 +194,57 @@ def test_crc_and_protobuf_pieces_against_tensorboard_implementations():
     ver = versions_pb2.VersionDef()
     ver.ParseFromString(b"\x08\x01")  # the header's version submessage written by write_bundle
     assert ver.producer == 1
+
+
+def test_training_state_resumes_adam_exactly(tmp_path):
+    """Saver-style training checkpoint (variables, `/Adam`, `/Adam_1`, beta powers, step counter): five Adam
+    updates, save, restore into fresh objects, five more == ten uninterrupted updates, bit for bit."""
+    import torch
+    from facet_graph_convolution_b200 import train as T
+    spec = ck.network_variables()
+
+    def fresh():
+        g = torch.Generator().manual_seed(0)
+        ps = [(torch.randn(s, generator=g) * 0.05).requires_grad_(True) for _, s in spec]
+        b = T.GradBucket(ps)
+        return ps, b, T.Adam(b)
+
+    def update(ps, b, opt, k):
+        g = torch.Generator().manual_seed(100 + k)
+        for p in ps:
+            p.grad = torch.randn(p.shape, generator=g)
+        b.pack()
+        opt.step()
+
+    ps_a, b_a, opt_a = fresh()
+    for k in range(10):
+        update(ps_a, b_a, opt_a, k)
+    ps_b, b_b, opt_b = fresh()
+    for k in range(5):
+        update(ps_b, b_b, opt_b, k)
+    m, v = opt_b.state_lists()
+    prefix = ck.save_training_state(str(tmp_path / "net"), ps_b, m, v, opt_b.t, global_step=5)
+    assert ck.latest_checkpoint(str(tmp_path)) == prefix and prefix.endswith("net-5")
+    everything = ck.read_bundle(prefix)
+    assert len(everything) == 3 * len(spec) + 3
+    assert np.float32(everything["beta1_power"]) == np.float32(0.9 ** 6) and int(everything["Variable"]) == 5
+    assert "model/Level1_1/Conv_1/assignment_2/Adam_1" in everything
+    st = ck.load_training_state(prefix)
+    assert st["step"] == 5
+    ps_c = [torch.from_numpy(a.copy()).requires_grad_(True) for a in st["params"]]
+    b_c = T.GradBucket(ps_c)
+    opt_c = T.Adam(b_c)
+    opt_c.load_state(st["m"], st["v"], st["step"])
+    for k in range(5, 10):
+        update(ps_c, b_c, opt_c, k)
+    for a, c in zip(ps_a, ps_c):
+        assert torch.equal(a.detach(), c.detach())
+    # the inference loader reads the same file and ignores the optimiser's entries
+    back = ck.load_network(prefix)
+    assert all(np.array_equal(x, p.detach().numpy()) for x, p in zip(back, ps_b))
+    # an inference export resumes with zero moments
+    p2 = ck.save_network(str(tmp_path / "inf" / "net"), ps_b)
+    st2 = ck.load_training_state(p2)
+    assert st2["step"] == 0 and all(not a.any() for a in st2["m"]) and all(not a.any() for a in st2["v"])
+    with pytest.raises(ck.CheckpointError, match="moment"):
+        ck.save_training_state(str(tmp_path / "x"), ps_b, m[:-1], v, 1)
