@@ -16,6 +16,12 @@ pyramid exactly (tests/golden/coarsen_*.npz, produced by the reference functions
 between equal edge scores are resolved by the column order of the sorted adjacency; this module fixes that
 order (row-major, columns ascending), which is what the reference's unstable `np.argsort` yields in this
 image -- on another NumPy build the reference itself may break ties differently.
+
+`precision`: the reference scores an edge as `vv * (1.0/weights[tid] + 1.0/weights[nid])` on float32 arrays.
+Under NumPy >= 2 (this image; the fixtures) Python floats are weak scalars and the whole expression, and the
+running total, stay float32 -- `precision=32`, the default and the pinned behaviour.  Under the NumPy 1.x the
+reference was written for, the same source promotes to float64 -- `precision=64` evaluates that; it has no
+reference run to compare with here (only the structural test), so treat it as unpinned.
 """
 import ctypes as C
 
