@@ -31,7 +31,8 @@ import scipy.sparse
 from . import _lib
 
 __all__ = ["list_to_sparse_w_normals", "coarsen", "compute_perm", "perm_adjacency", "sparse_to_list", "inv_perm",
-           "greedy_pairing", "patch_pyramid", "get_graph_patch_w_mask", "extract_patches"]
+           "greedy_pairing", "patch_pyramid", "get_graph_patch_w_mask", "extract_patches",
+           "mesh_with_vertices"]
 
 
 def list_to_sparse_w_normals(adj, nodes_pos, nodes_normals):
@@ -280,3 +281,32 @@ def extract_patches(f_adj, features, patch_size, K, min_patch_size=2000, level_n
         out.append(Patch(x=x.astype(np.float32), adjs=adjs, face_ids=old.astype(np.int64),
                          perm=None if old_to_new is None else old_to_new.astype(np.int32)))
     return out
+
+
+def mesh_with_vertices(V, F, K, level_num=3, step_num=2, rng=None, precision=32, kv=25, f_adj=None):
+    """Inputs of the multi-scale network *with vertex update* for a mesh below the size limit, as the small-mesh
+    branch of `PreprocessedData.addMeshWithVertices` prepares them (dataClasses.py:236-270, 377-443): vertices
+    divided by their bounding-box diagonal (`normalizePointSets`, utils.py:2077-2107), facet features and
+    pyramid in tree order, the face list padded with (-1,-1,-1) rows for the fake nodes and permuted the same
+    way, and the vertex -> faces lists of that permuted list (`getVerticesFaces(faces, 25, V)`).
+    `f_adj` may carry the adjacency already built on the GPU (`ops.build_faces_adj`).
+    Returns dict(x [N0', 6], adjs [1, N_l, K] per level, faces [N0', 3], v_faces [V, kv], verts [V, 3],
+    new_to_old, old_to_new, num_faces)."""
+    from . import mesh
+    V = np.asarray(V)
+    F = np.asarray(F)
+    fn = mesh.face_normals(V, F)
+    adj = mesh.faces_large_adj(F, K) if f_adj is None else np.asarray(f_adj)
+    pos = mesh.face_barycenters(V, F, normalize=True)
+    feats = np.concatenate((fn, pos), axis=1)
+    span = V.max(axis=0) - V.min(axis=0)
+    verts = V / np.sqrt((span.astype(np.float64) ** 2).sum())
+    coo = list_to_sparse_w_normals(adj, pos, fn)
+    graphs, new_to_old = coarsen(coo, (level_num - 1) * step_num, rng=rng, precision=precision)
+    new_to_old = np.asarray(new_to_old, dtype=np.int64)
+    extra = new_to_old.size - F.shape[0]
+    faces = np.concatenate((F.astype(np.int64), -np.ones((extra, 3), np.int64)), axis=0)[new_to_old]
+    x = np.concatenate((feats, np.zeros((extra, feats.shape[1]))), axis=0)[new_to_old]
+    adjs = [sparse_to_list(graphs[step_num * lvl], K)[0][np.newaxis] for lvl in range(level_num)]
+    return dict(x=x, adjs=adjs, faces=faces, v_faces=mesh.vertex_faces(faces, kv, V.shape[0]), verts=verts,
+                new_to_old=new_to_old, old_to_new=inv_perm(new_to_old), num_faces=F.shape[0])

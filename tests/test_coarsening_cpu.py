@@ -168,3 +168,22 @@ def test_patch_loop_equals_the_reference_driver():
             assert p.adjs[l].dtype == np.int32 and np.array_equal(p.adjs[l], g["drv%d_adj%d" % (i, l)])
         covered[p.face_ids] = True
     assert covered.all()
+
+
+def test_mesh_with_vertices_reproduces_the_reference_driver():
+    """net_ms_icosphere2.npz holds what `PreprocessedData.addMeshWithVertices` (small-mesh branch,
+    dataClasses.py:236-270, 377-443) prepared with the global generator seeded to 1: normalised vertices,
+    permuted features, level lists, the face list with (-1,-1,-1) rows for fake nodes, vertex -> faces lists."""
+    g = golden("net_ms_icosphere2")
+    K = g["adj0"].shape[2]
+    d = co.mesh_with_vertices(g["V"], g["F"], K, rng=np.random.RandomState(1))
+    for l in range(3):
+        assert np.array_equal(d["adjs"][l], g["adj%d" % l])
+    assert np.array_equal(d["x"][None].astype(np.float32), g["x"])
+    assert np.array_equal(d["faces"][None], g["faces"]) and np.array_equal(d["v_faces"][None], g["v_faces"])
+    assert np.array_equal(d["verts"][None].astype(np.float32), g["verts_in"])
+    assert d["num_faces"] == g["F"].shape[0] and (d["faces"][d["new_to_old"] >= d["num_faces"]] == -1).all()
+    assert np.array_equal(d["new_to_old"][d["old_to_new"][: d["num_faces"]]], np.arange(d["num_faces"]))
+    # the adjacency may come from the GPU builder instead: same result
+    d2 = co.mesh_with_vertices(g["V"], g["F"], K, rng=np.random.RandomState(1), f_adj=mesh.faces_large_adj(g["F"], K))
+    assert np.array_equal(d2["x"], d["x"]) and np.array_equal(d2["v_faces"], d["v_faces"])
