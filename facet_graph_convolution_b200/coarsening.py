@@ -32,7 +32,7 @@ from . import _lib
 
 __all__ = ["list_to_sparse_w_normals", "coarsen", "compute_perm", "perm_adjacency", "sparse_to_list", "inv_perm",
            "greedy_pairing", "patch_pyramid", "get_graph_patch_w_mask", "extract_patches",
-           "mesh_with_vertices"]
+           "mesh_with_vertices", "get_mesh_patch", "extract_patches_with_vertices"]
 
 
 def list_to_sparse_w_normals(adj, nodes_pos, nodes_normals):
@@ -310,3 +310,58 @@ def mesh_with_vertices(V, F, K, level_num=3, step_num=2, rng=None, precision=32,
     adjs = [sparse_to_list(graphs[step_num * lvl], K)[0][np.newaxis] for lvl in range(level_num)]
     return dict(x=x, adjs=adjs, faces=faces, v_faces=mesh.vertex_faces(faces, kv, V.shape[0]), verts=verts,
                 new_to_old=new_to_old, old_to_new=inv_perm(new_to_old), num_faces=F.shape[0])
+
+
+def get_mesh_patch(v_in, f_in, f_adj_in, face_num, seed):
+    """A patch of a triangle mesh grown breadth-first over the facet graph (utils.py:1298-1415): faces are
+    numbered in discovery order exactly as `get_graph_patch_w_mask` does without a mask, vertices in order of
+    first use by those faces.  Returns (vertices float32, faces in patch-local vertex ids, patch adjacency,
+    original vertex ids, original face ids)."""
+    v_in = np.asarray(v_in)
+    f_in = np.asarray(f_in).astype(np.int64)
+    adj_p, f_old, _ = get_graph_patch_w_mask(f_adj_in, face_num, seed, np.zeros(f_in.shape[0]), 0)
+    corners = f_in[f_old].reshape(-1)
+    uniq, first = np.unique(corners, return_index=True)
+    v_old = uniq[np.argsort(first, kind="stable")]
+    local = np.full(v_in.shape[0], -1, dtype=np.int64)
+    local[v_old] = np.arange(v_old.size)
+    return v_in[v_old].astype(np.float32), local[f_in[f_old]], adj_p, v_old, f_old
+
+
+def extract_patches_with_vertices(V, F, patch_size, K, level_num=3, step_num=2, rng=None, precision=32, kv=25,
+                                  f_adj=None, min_component=100):
+    """The patch loop of `PreprocessedData.addMeshWithVertices` for a mesh above the size limit
+    (dataClasses.py:236-376, inference case): every patch starts at a random face no patch covers yet and grows
+    to `patch_size` faces whatever the earlier patches took; per patch the vertices (of the mesh divided by its
+    bounding-box diagonal), the features / pyramid in tree order, the permuted face list with (-1,-1,-1)
+    rows and its vertex -> faces lists.  Returns a list of dicts like `mesh_with_vertices` plus
+    `face_ids` / `vertex_ids` (original ids in patch order)."""
+    from . import mesh
+    rng = np.random if rng is None else rng
+    V = np.asarray(V)
+    F = np.asarray(F)
+    adj = mesh.faces_large_adj(F, K) if f_adj is None else np.asarray(f_adj)
+    feats = np.concatenate((mesh.face_normals(V, F), mesh.face_barycenters(V, F, normalize=True)), axis=1)
+    span = V.max(axis=0) - V.min(axis=0)
+    Vn = V / np.sqrt((span.astype(np.float64) ** 2).sum())
+    covered = np.zeros(F.shape[0])
+    out = []
+    while np.any(covered == 0):
+        free = np.flatnonzero(covered == 0)
+        seed = int(free[rng.randint(free.shape[0])])
+        pv, pf, p_adj, v_old, f_old = get_mesh_patch(Vn, F, adj, patch_size, seed)
+        covered[f_old] += 1
+        if f_old.shape[0] < min_component:
+            continue
+        x0 = feats[f_old]
+        graphs, new_to_old = coarsen(list_to_sparse_w_normals(p_adj, x0[:, -3:], x0[:, :3]),
+                                     (level_num - 1) * step_num, rng=rng, precision=precision)
+        new_to_old = np.asarray(new_to_old, dtype=np.int64)
+        extra = new_to_old.size - f_old.shape[0]
+        faces = np.concatenate((pf, -np.ones((extra, 3), np.int64)), axis=0)[new_to_old]
+        x = np.concatenate((x0, np.zeros((extra, x0.shape[1]))), axis=0)[new_to_old]
+        adjs = [sparse_to_list(graphs[step_num * lvl], K)[0][np.newaxis] for lvl in range(level_num)]
+        out.append(dict(x=x, adjs=adjs, faces=faces, v_faces=mesh.vertex_faces(faces, kv, pv.shape[0]), verts=pv,
+                        new_to_old=new_to_old, old_to_new=inv_perm(new_to_old), num_faces=f_old.shape[0],
+                        face_ids=f_old, vertex_ids=v_old))
+    return out

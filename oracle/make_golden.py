@@ -395,6 +395,42 @@ def patch_cases(ref):
     print("wrote patch_cases", len(im.in_list))
 
 
+def _digest(a):
+    import hashlib
+    a = np.ascontiguousarray(a)
+    return np.frombuffer(hashlib.sha1(a.tobytes()).digest(), dtype=np.uint8)
+
+
+def patch_vertex_cases(ref):
+    """`getMeshPatch` and the patch loop of `addMeshWithVertices` (mesh above the size limit) on the noisy
+    icosphere-4 of patch_cases: three single patches in full, and for the eight patches of the driver run the
+    shapes and SHA-1 digests of every output array (int64 / float64 / float32 as the reference leaves them)."""
+    V, F = mesh.icosphere(4)
+    V = mesh.add_vertex_noise(V, F, 0.3, seed=2)
+    K = 16
+    adj = mesh.faces_large_adj(F, K)
+    d = {"K": np.int32(K)}
+    for i, seed in enumerate((3, 700, 4000)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            vO, fO, aO, vOld, fOld = ref.utils.getMeshPatch(V.astype(np.float32), F, adj, 400, seed)
+        d["mp%d_seed" % i] = np.int64(seed)
+        d["mp%d_v" % i], d["mp%d_f" % i], d["mp%d_adj" % i] = vO, fO.astype(np.int32), aO.astype(np.int32)
+        d["mp%d_vold" % i], d["mp%d_fold" % i] = vOld.astype(np.int32), fOld.astype(np.int32)
+    im = preprocess(ref, V, F, K, multi=True, seed=6, max_patch=1500)
+    d["drv_args"] = np.array([1500, 6, len(im.in_list)], dtype=np.int64)
+    for i in range(len(im.in_list)):
+        arrs = dict(x=im.in_list[i][0], adj0=im.adj_list[i][0][0], adj1=im.adj_list[i][1][0], adj2=im.adj_list[i][2][0],
+                    faces=im.faces_list[i][0], v_faces=im.v_faces_list[i][0], verts=im.v_list[i][0],
+                    face_ids=im.fOldInd_list[i], vertex_ids=im.vOldInd_list[i], old_to_new=np.asarray(im.permutations[i]))
+        for k, a in arrs.items():
+            a = np.asarray(a)
+            d["drv%d_%s_shape" % (i, k)] = np.array(a.shape, dtype=np.int64)
+            d["drv%d_%s_dtype" % (i, k)] = np.frombuffer(a.dtype.str.encode(), dtype=np.uint8)
+            d["drv%d_%s_sha1" % (i, k)] = _digest(a)
+    np.savez_compressed(os.path.join(OUT, "patch_vertex_cases.npz"), **d)
+    print("wrote patch_vertex_cases", len(im.in_list))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rr.load()
@@ -412,6 +448,7 @@ def main():
     obj_cases(ref)
     coarsen_cases(ref)
     patch_cases(ref)
+    patch_vertex_cases(ref)
 
 
 if __name__ == "__main__":

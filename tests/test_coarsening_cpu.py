@@ -187,3 +187,32 @@ def test_mesh_with_vertices_reproduces_the_reference_driver():
     # the adjacency may come from the GPU builder instead: same result
     d2 = co.mesh_with_vertices(g["V"], g["F"], K, rng=np.random.RandomState(1), f_adj=mesh.faces_large_adj(g["F"], K))
     assert np.array_equal(d2["x"], d["x"]) and np.array_equal(d2["v_faces"], d["v_faces"])
+
+
+def test_mesh_patches_with_vertices_equal_the_reference():
+    """tests/golden/patch_vertex_cases.npz: `getMeshPatch` (utils.py:1298-1415) in full for three seeds, and the
+    patch loop of `addMeshWithVertices` (dataClasses.py:274-376) by shape, dtype and SHA-1 of every output."""
+    import hashlib
+    g = golden("patch_vertex_cases")
+    V, F = mesh.icosphere(4)
+    V = mesh.add_vertex_noise(V, F, 0.3, seed=2)
+    K = int(g["K"])
+    adj = mesh.faces_large_adj(F, K)
+    for i in range(3):
+        v, f, a, vold, fold = co.get_mesh_patch(V.astype(np.float32), F, adj, 400, int(g["mp%d_seed" % i]))
+        assert v.dtype == np.float32 and np.array_equal(v, g["mp%d_v" % i]) and np.array_equal(f, g["mp%d_f" % i])
+        assert np.array_equal(a, g["mp%d_adj" % i]) and np.array_equal(vold, g["mp%d_vold" % i])
+        assert np.array_equal(fold, g["mp%d_fold" % i])
+        assert np.array_equal(V.astype(np.float32)[vold][f], V.astype(np.float32)[F[fold]])  # same triangles
+    patch_size, seed, count = (int(t) for t in g["drv_args"])
+    ps = co.extract_patches_with_vertices(V, F, patch_size, K, rng=np.random.RandomState(seed))
+    assert len(ps) == count
+    for i, p in enumerate(ps):
+        arrs = dict(x=p["x"], adj0=p["adjs"][0][0], adj1=p["adjs"][1][0], adj2=p["adjs"][2][0], faces=p["faces"],
+                    v_faces=p["v_faces"], verts=p["verts"], face_ids=p["face_ids"], vertex_ids=p["vertex_ids"],
+                    old_to_new=p["old_to_new"])
+        for k, a in arrs.items():
+            want_dtype = np.dtype(bytes(g["drv%d_%s_dtype" % (i, k)]).decode())
+            a = np.ascontiguousarray(np.asarray(a).astype(want_dtype, copy=False))
+            assert tuple(a.shape) == tuple(g["drv%d_%s_shape" % (i, k)]), (i, k)
+            assert hashlib.sha1(a.tobytes()).digest() == bytes(g["drv%d_%s_sha1" % (i, k)]), (i, k)
