@@ -249,3 +249,26 @@ def test_saver_checkpoint_names_follow_the_creation_order_and_round_trip(tmp_pat
     ys = ys if multi else (ys,)
     for y, k in zip(ys, ("y0", "y1", "y2") if multi else ("y_raw",)):
         assert np.abs(y.cpu().numpy() - g[k]).max() < 1e-5
+
+
+def test_multi_scale_pipeline_from_raw_mesh():
+    """Raw vertices and faces -> `coarsening.mesh_with_vertices` (seeded like the reference run) -> multi-scale
+    network -> normals of the three levels -> `update_position_MS`, against what the reference's driver and
+    graph functions produced for the same mesh (net_ms_icosphere2.npz)."""
+    from facet_graph_convolution_b200 import coarsening
+    from facet_graph_convolution_b200 import model as fm
+    g = golden("net_ms_icosphere2")
+    d = coarsening.mesh_with_vertices(g["V"], g["F"], g["adj0"].shape[2], rng=np.random.RandomState(1))
+    adjs = [T(a.astype(np.int32)) for a in d["adjs"]]
+    with torch.no_grad(), fm.variable_store(fm.VariableStore(dev(), params=_params(g))):
+        ys = fm.get_model_reg_multi_scale(T(d["x"][None].astype(np.float32)), adjs, 1.0, multiScale=True)
+    for y, k in zip(ys, ("y0", "y1", "y2")):
+        assert np.abs(y.cpu().numpy() - g[k]).max() < 1e-5
+    ns = [fm.normalizeTensor(y) for y in ys]
+    for n, k in zip(ns, ("n0", "n1", "n2")):
+        assert np.abs(n.cpu().numpy() - g[k]).max() < 1e-4
+    xo, dxl = fm.update_position_MS(T(d["verts"][None].astype(np.float32)), ns, T(d["faces"][None].astype(np.int32)),
+                                    T(d["v_faces"][None].astype(np.int32)), 2,
+                                    iter_num_list=[int(i) for i in g["iters"]])
+    assert len(dxl) == 3
+    assert np.abs(xo.cpu().numpy() - g["verts_out"]).max() < 5e-4
