@@ -216,3 +216,12 @@ def test_mesh_patches_with_vertices_equal_the_reference():
             a = np.ascontiguousarray(np.asarray(a).astype(want_dtype, copy=False))
             assert tuple(a.shape) == tuple(g["drv%d_%s_shape" % (i, k)]), (i, k)
             assert hashlib.sha1(a.tobytes()).digest() == bytes(g["drv%d_%s_sha1" % (i, k)]), (i, k)
+
+
+def test_patch_pyramid_gives_up_when_k_is_too_small():
+    """The reference coarsens again for as long as a level has more neighbours than K - 1 columns
+    (dataClasses.py:116-129) -- forever when K is simply too small; here that is an error after 20 tries."""
+    V, F = mesh.icosphere(2)
+    adj = mesh.faces_large_adj(F, 12)
+    with pytest.raises(_lib.FacetConvError, match="saturates"):
+        co.patch_pyramid(adj, mesh.face_features(V, F), 3, rng=np.random.RandomState(0))
