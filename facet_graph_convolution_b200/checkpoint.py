@@ -139,7 +139,6 @@ def _make_table():
 
 
 _TABLE = _make_table()
-_LANES = 512
 
 
 def _crc_raw_scalar(state: int, data: bytes) -> int:
@@ -157,30 +156,46 @@ def _zero_shift_columns(nbytes: int) -> np.ndarray:
     return cols
 
 
+def _byte_tables(cols: np.ndarray) -> np.ndarray:
+    """tables[k][v] = image of the state v << 8k under the linear register map given by its 32 column images."""
+    tabs = np.zeros((4, 256), dtype=np.uint32)
+    for k in range(4):
+        t = np.zeros(1, dtype=np.uint32)
+        for b in range(8):  # entries with bit b set = entries without it, xor that column
+            t = np.concatenate([t, t ^ cols[8 * k + b]])
+        tabs[k] = t
+    return tabs
+
+
+def _apply_tables(tabs: np.ndarray, x: np.ndarray) -> np.ndarray:
+    return (tabs[0][x & 0xFF] ^ tabs[1][(x >> 8) & 0xFF] ^ tabs[2][(x >> 16) & 0xFF] ^ tabs[3][x >> 24])
+
+
 def crc32c(data, seed: int = 0) -> int:
     """CRC-32C of a bytes-like object (reflected polynomial 0x1EDC6F41, init/final xor 0xFFFFFFFF).
-    Long inputs run the byte-wise table recurrence on 512 equal chunks at once (NumPy lanes) and join the
-    chunk registers through the zero-feed operator."""
+    Inputs from 16 KB on are cut into a power-of-two number of equal chunks that run the byte-wise table
+    recurrence side by side (NumPy lanes); neighbouring chunk registers are then joined pairwise, log2(lanes)
+    times, through the zero-feed operator of the current chunk length (squared after every round)."""
     buf = np.frombuffer(memoryview(data).cast("B"), dtype=np.uint8)
     state = (seed ^ 0xFFFFFFFF) & 0xFFFFFFFF
     n = buf.size
-    L = n // _LANES
-    if L >= 16:
-        body = buf[: L * _LANES].reshape(_LANES, L)
-        st = np.zeros(_LANES, dtype=np.uint32)
+    if n >= 16384:
+        lanes = 512
+        while lanes < (1 << 20) and n // (2 * lanes) >= 32:
+            lanes *= 2
+        L = n // lanes
+        body = np.ascontiguousarray(buf[: L * lanes].reshape(lanes, L).T)
+        st = np.zeros(lanes, dtype=np.uint32)
         st[0] = state
         for i in range(L):
-            st = _TABLE[(st ^ body[:, i]) & 0xFF] ^ (st >> 8)
+            st = _TABLE[(st ^ body[i]) & 0xFF] ^ (st >> 8)
         cols = _zero_shift_columns(L)
-        bits = np.arange(32, dtype=np.uint32)
-        acc = np.uint32(0)
-        for i in range(_LANES):
-            # acc <- shift_L(acc) ^ st[i]
-            sel = ((acc >> bits) & 1).astype(bool)
-            acc = np.bitwise_xor.reduce(cols[sel]) if sel.any() else np.uint32(0)
-            acc = np.uint32(acc) ^ st[i]
-        state = int(acc)
-        buf = buf[L * _LANES:]
+        while st.size > 1:
+            tabs = _byte_tables(cols)
+            st = _apply_tables(tabs, st[0::2]) ^ st[1::2]
+            cols = _apply_tables(tabs, cols)
+        state = int(st[0])
+        buf = buf[L * lanes:]
     state = _crc_raw_scalar(state, buf.tobytes())
     return (state ^ 0xFFFFFFFF) & 0xFFFFFFFF
 

@@ -15,7 +15,7 @@ def test_crc32c_known_answers_and_lane_path():
     assert ck.crc32c(b"\xff" * 32) == 0x62A8AB43
     assert ck.crc32c(b"") == 0
     rs = np.random.RandomState(0)
-    for n in (8191, 8192, 8193, 70001):
+    for n in (8191, 16383, 16384, 16385, 32768 + 17, 70001, 1 << 20):
         data = rs.randint(0, 256, n).astype(np.uint8).tobytes()
         want = ck._crc_raw_scalar(0xFFFFFFFF, data) ^ 0xFFFFFFFF  # byte-at-a-time recurrence
         assert ck.crc32c(data) == want, n
