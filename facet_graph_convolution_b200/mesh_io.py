@@ -31,6 +31,28 @@ def compute_vertex_normals(verts, faces):
     return _unit_rows_twice(normals)
 
 
+def _parse_plain(lines):
+    """Fast path for files made of `v x y z` and `f a b c` records only (what `write_mesh` and most scanners
+    emit): the numbers of all records go through one C-level parse.  None when anything else is present --
+    extra vertex columns, `v/vt/vn` corners, polygons, indented records -- and the general loop takes over."""
+    vrec = [l for l in lines if l.startswith("v ")]
+    frec = [l for l in lines if l.startswith("f ")]
+    rest = [l for l in lines if l and not l.startswith(("v ", "f ", "#"))]
+    if not vrec or any(l.split() and l.split()[0] in ("v", "f") for l in rest):
+        return None
+    ftext = " ".join(l[2:] for l in frec)
+    if "/" in ftext:
+        return None
+    try:
+        v = np.fromstring(" ".join(l[2:] for l in vrec), dtype=np.float64, sep=" ")
+        c = np.fromstring(ftext, dtype=np.int64, sep=" ") if frec else np.zeros(0, np.int64)
+    except (ValueError, DeprecationWarning):
+        return None
+    if v.size != 3 * len(vrec) or c.size != 3 * len(frec):
+        return None
+    return v.reshape(-1, 3), (c - 1)
+
+
 def load_mesh(path, filename, K=0, bGetAdj=False):
     """Returns (vertices float32 [V,3], adj, free_ind, faces uint16|uint32 [F,3] zero-based, vertex normals).
     Polygons are fan-triangulated around their first vertex; `v/vt/vn` corners keep the vertex index; `vn`,
@@ -39,10 +61,15 @@ def load_mesh(path, filename, K=0, bGetAdj=False):
     if bGetAdj:
         raise NotImplementedError("load_mesh(bGetAdj=True): the vertex-ring adjacency is never requested by "
                                   "the reference's drivers; use build_faces_adj for the facet graph")
-    verts = []
-    corners = []
     with open(os.path.join(path, filename), "r") as f:
-        for line in f:
+        lines = f.read().split("\n")
+    parsed = _parse_plain(lines)
+    if parsed is not None:
+        verts, corners = parsed
+    else:
+        verts = []
+        corners = []
+        for line in lines:
             tok = line.split()
             if not tok or line.startswith("#"):
                 continue
@@ -54,7 +81,8 @@ def load_mesh(path, filename, K=0, bGetAdj=False):
                     corners += (ids[0], ids[t + 1], ids[t + 2])
     vertices = np.array(verts).astype(np.float32)
     itype = np.uint16 if vertices.shape[0] < 65536 else np.uint32
-    faces = np.array(corners).reshape(len(corners) // 3, 3).astype(itype)
+    corners = np.asarray(corners)
+    faces = corners.reshape(corners.size // 3, 3).astype(itype)
     return vertices, [], [], faces, compute_vertex_normals(vertices, faces)
 
 
