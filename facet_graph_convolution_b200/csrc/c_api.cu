@@ -91,9 +91,15 @@ static bool use_mma(const fgc_conv_shape* s) {
   return !disabled && conv_mma_supported(s->Cin, s->Cw, s->Cout, s->M, s->K);
 }
 
+// HMMA-aggregation forward (conv_hm.cu): the dense layers without a tile plan, fused upsampling included
+static bool use_hm(const fgc_conv_shape* s) {
+  static const bool disabled = getenv("FGC_DISABLE_HM") != nullptr || getenv("FGC_DISABLE_TC") != nullptr;
+  return !disabled && conv_hm_supported(s->Cin, s->Cw, s->Cout, s->M, s->K) && static_cast<int64_t>(s->B) * s->N >= 64;
+}
+
 static size_t conv_fwd_workspace(const fgc_conv_shape* s) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
-  return ws_bytes(rows * 2 * s->M, 4) + ws_bytes(static_cast<size_t>(s->M) * s->Cout * s->Cw, 4) +
+  return (use_hm(s) ? conv_hm_workspace(rows, s->Cw, s->Cout, s->M) + 256 : 0) + ws_bytes((rows + 1) * 2 * s->M, 4) + ws_bytes(static_cast<size_t>(s->M) * s->Cout * s->Cw, 4) +
          ws_bytes(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw), 1) + (use_mma(s) ? conv_mma_workspace(rows) + 256 : 0) + 512;
 }
 
@@ -104,11 +110,23 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   if (upshift > 0) {
     // fused custom_upsampling: x holds (rows >> upshift) rows, row r of the layer reads row r >> upshift.
-    // Only the first-generation tcgen05 forward indexes its gathers this way.
-    FGC_UNSUPPORTED(!(s->M == 9 && use_tc(s)) || plan != nullptr || upshift > 4 || (s->N & ((1 << upshift) - 1)),
+    // Only the tensor-core forwards without a tile plan index their gathers this way.
+    FGC_UNSUPPORTED(!(use_hm(s) || (s->M == 9 && use_tc(s))) || plan != nullptr || upshift > 4 ||
+                        (s->N & ((1 << upshift) - 1)),
                     "conv_fwd_up: shape has no fused-upsampling path");
     Workspace wsu(workspace, workspace_bytes);
-    float* uvx_c = wsu.take<float>(rows * 2 * s->M);
+    float* uvx_c = wsu.take<float>((rows + 1) * 2 * s->M);
+    if (use_hm(s)) {
+      const size_t hb = conv_hm_workspace(rows >> upshift, s->Cw, s->Cout, s->M);
+      char* hws = wsu.take<char>(hb);
+      FGC_REQUIRE(wsu.ok(), "conv_fwd_up: workspace too small");
+      fgc_conv_shape sc = *s;
+      sc.B = 1, sc.N = static_cast<int>(rows >> upshift);
+      int rch = launch_assign_logits(&sc, x, u, v, c, uvx_c, st);
+      if (rch) return rch;
+      ConvFwdParams ph{x, adj, uvx_c, nullptr, b, y, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M, bias_mask, act, alpha};
+      return launch_conv_hm(ph, W0, hws, hb, st, upshift);
+    }
     wsu.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);
     char* wimg_u = wsu.take<char>(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw));
     FGC_REQUIRE(wsu.ok(), "conv_fwd_up: workspace too small");
@@ -122,7 +140,7 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
   if (conv_fwd_small_supported(s))   // the 6 -> 32 input layer: thread per facet, logits inline, no workspace
     return launch_conv_fwd_small(s, x, adj, W0, b, u, v, c, y, bias_mask, act, alpha, st);
   Workspace ws(workspace, workspace_bytes);
-  float* uvx = ws.take<float>(rows * 2 * s->M);
+  float* uvx = ws.take<float>((rows + 1) * 2 * s->M);   // one spare row: the HMMA path's zero row
   float* Wt = ws.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);
   FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
               conv_fwd_workspace(s));
@@ -146,6 +164,12 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
   }
   rc = launch_assign_logits(s, x, u, v, c, uvx, st);
   if (rc) return rc;
+  if (use_hm(s)) {
+    const size_t hb = conv_hm_workspace(rows, s->Cw, s->Cout, s->M);
+    char* hws = ws.take<char>(hb);
+    FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the HMMA-aggregation path");
+    return launch_conv_hm(p, W0, hws, hb, st);
+  }
   if (use_tc(s)) {
     char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw));
     FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the tensor-core path");
@@ -162,7 +186,7 @@ int conv_fwd_saved_views(const fgc_conv_shape* s, const void* fwd_ws, size_t fwd
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
   FGC_REQUIRE(use_mma(s), "conv_bwd: a saved forward workspace needs the planned tensor-core path");
   Workspace ws(const_cast<void*>(fwd_ws), fwd_ws_bytes);
-  out->uvx = ws.take<float>(rows * 2 * s->M);
+  out->uvx = ws.take<float>((rows + 1) * 2 * s->M);
   ws.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);
   ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw));
   out->ximg = ws.take<char>(conv_mma_workspace(rows));
@@ -304,7 +328,7 @@ int fgc_conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj, co
 
 int fgc_conv_fwd_up_supported(const fgc_conv_shape* s, int upshift) {
   if (check_shape(s, "conv_fwd_up_supported")) return 0;
-  return (s->M == 9 && use_tc(s) && upshift > 0 && upshift <= 4 && (s->N & ((1 << upshift) - 1)) == 0) ? 1 : 0;
+  return ((use_hm(s) || (s->M == 9 && use_tc(s))) && upshift > 0 && upshift <= 4 && (s->N & ((1 << upshift) - 1)) == 0) ? 1 : 0;
 }
 
 int fgc_conv_fwd_up(const fgc_conv_shape* s, const float* x_coarse, const int32_t* adj, const float* W0,

@@ -1,0 +1,655 @@
+// Facet-graph convolution forward for the network's dense layers (reference Code/model.py:427-504, called at
+// :870-932 with M = 9; also the M = 8 benchmark layer): per-facet aggregation on the warp-level tensor path
+// (mma.sync m16n8k16), contraction with W on tcgen05.  No tile plan, no per-tile row dedup: works on any adjacency.
+//
+//   stage 1 (8 aggregator warps, one facet at a time per warp, registers only)
+//       S_n[m, c] = sum_k q[n,k,m] x_{j_k}[c]            A = q  (16 x 16: rows m, columns = neighbour slots)
+//                                                         B = the 16 gathered rows of the fp16 hi|lo image of x
+//       q is computed in the A-fragment layout (lane (g,t) owns row m = g and slots 2t,2t+1,2t+8,2t+9; the
+//       softmax normaliser is a 3-step shuffle sum over the 8 g-lanes), the gathered rows are loaded straight
+//       from global / L1 as 16-byte units (lane (g,t): channels 8g..8g+7 of the rows of its four slots) and
+//       turned into B fragments with byte permutes: n-block nb of the MMA holds channels {8g'+nb}.
+//       q_hi.x_hi + q_lo.x_hi + q_hi.x_lo in fp32 accumulators = fp32-class precision.
+//       M = 9: rows 8..15 of A all carry q[.,8] (every lane then owns a copy of S[8,.] and converts 2 of its 64
+//       values); M = 8: rows 8..15 carry q_lo, so two MMAs per n-block instead of three.
+//   drain   S -> fp16 hi (11 bits, exact) + fp16 residual -> shared memory, directly in the K-major 128B-swizzled
+//       layout of the B operand of stage 2 ([hi rows of the tile's 32 facets | lo rows], one 64-element atom per
+//       (weight pair, unit parity) so that the 16-byte stores of a quarter warp hit 8 different bank groups).
+//   stage 2 (one elected thread)   Y^T[(h,o), f] = sum_{m,c} [Wh;Wl][(h,o),(m,c)] [Sh|Sl][(m,c), f]
+//       tcgen05.mma M = 128, N = 64, K = 64 M, A = the weight image resident in TMEM for the CTA's lifetime.
+//   epilogue (4 warps on the TMEM lane quadrants)  y = act(inv_cnt * scale * (Wh.Sh + Wh.Sl + 2^-11 Wl.Sh) + flag * b),
+//       optional max over groups of 4 rows (custom_binary_tree_pooling, model.py:863,875) and max|y| for the
+//       image scale of the next layer.
+// One launch covers 64 aggregation channels x up to 64 outputs; wider layers are sums of launches over channel
+// blocks (bias in the first, activation / pooling in the last), as in conv_fwd_tc.cu.
+#include "conv_launch.cuh"
+#include "tc_common.cuh"
+
+namespace fgc {
+
+namespace {
+
+constexpr int kHT = 32;                              // facets per tile
+constexpr int kHAgg = 8;                             // aggregator warps
+constexpr int kHFpw = kHT / kHAgg;                   // facets per warp and tile
+constexpr int kHThreads = (4 + kHAgg) * 32;          // 4 epilogue warps + aggregators (3 warps per sub-partition)
+
+template <int M>
+struct HmCfg {
+  static_assert(M == 8 || M == 9, "M = 8 or 9");
+  static constexpr int NATOM = M;                    // K atoms of 64 elements: 8 for the (m < 8, unit) pairs, +1 for m = 8
+  static constexpr int W_COLS = NATOM * 32;          // TMEM columns of the weight operand (2 halves per column)
+  static constexpr int D_COL = 320;                  // two accumulators of ND columns
+  static constexpr int ND = 2 * kHT;                 // stage-2 N: [Sh | Sl]
+  static constexpr int ATOM_BYTES = ND * 128;
+  static constexpr int B3_BUF = NATOM * ATOM_BYTES;
+  static constexpr int OFF_ROW = 2 * B3_BUF;         // inv_cnt of the tile's facets, 4 tiles deep
+  static constexpr int OFF_BAR = OFF_ROW + 4 * kHT * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
+  static_assert(W_COLS <= D_COL && D_COL + 2 * ND <= 512, "TMEM overflow");
+};
+
+enum { HB_B3_FREE = 0, HB_D_FULL = 2, HB_D_FREE = 4, HB_NUM = 6 };
+
+struct HmParams {
+  const uint4* img;        // fp16 image of this launch's 64-channel unit: row r at img + r * img_ld, [0..8) hi, [8..16) lo
+  int img_ld;
+  const float* xunscale;
+  const float* uvx;        // [rows >> upshift][2M]
+  const int32_t* adj;
+  const uint32_t* wt;      // [128 TMEM lanes][W_COLS]
+  const float* wunscale;
+  const float* b;
+  float* y;
+  int ldy;
+  float* ypool;            // optional: max over groups of 4 consecutive rows of the final output
+  int ldp;
+  unsigned* ymax;          // optional: atomicMax of the bits of |final output|
+  int64_t rows, ntiles;
+  int N, K, upshift;
+  int bias_mask, act;
+  float alpha;
+  int add_bias, accumulate, apply_act;
+  int cout;                // outputs of this launch (16 .. 64, multiple of 16)
+  int single;              // B == 1: neighbour ids index the rows directly
+  int zrow;                // index of an all-zero row of the image and of uvx (padding / out-of-range slots read it)
+};
+
+__device__ __forceinline__ void hmma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// fp16 pair of (a, b) and of the residuals
+__device__ __forceinline__ void split_rn(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// hi truncated to 11 significant bits (exactly representable), lo = fp16 of the exact residual
+__device__ __forceinline__ void split_trunc(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  const __half2 h = __floats2half2_rn(h0, h1);
+  const __half2 l = __floats2half2_rn(a - h0, b - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ uint32_t w4(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+// ---- aggregator building blocks.  Work item = (facet, group of 16 neighbour slots); K <= 16: one item per facet.
+// The inputs of item n+1 (and the adjacency ids of item n+2) are in flight while item n is computed.
+struct HmPre {            // prefetched inputs of one item
+  uint4 xh[4], xl[4];     // 16-byte unit g of the hi / lo plane of the rows of this lane's four slots
+  float vg[4], v8[4];     // neighbour logits of weight g / weight 8 of those slots
+  float uo_g, uo_8;       // own logits
+  int okm;                // bit i: slot i holds a valid neighbour
+  int nz;                 // non-zero ids among this lane's four slots
+};
+
+template <bool ZERO_C>
+__device__ __forceinline__ void hm_mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+  if (ZERO_C) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+  } else {
+    hmma16816(d, a0, a1, a2, a3, b0, b1);
+  }
+}
+
+// acc (+)= contribution of the item's 16 slots; returns the number of non-zero ids among them
+template <int M, bool FIRST>
+__device__ __forceinline__ int hm_mma_item(const HmPre& in, float (&acc)[8][4]) {
+  int c = in.nz;
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  constexpr float L2E = 1.4426950408889634f;
+  float qg[4], q8[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float ag = in.uo_g + in.vg[i];
+    const float a8 = (M == 9) ? in.uo_8 + in.v8[i] : 0.f;
+    float mx = (M == 9) ? fmaxf(ag, a8) : ag;
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    const float ms = -mx * L2E;
+    const float eg = ex2_approx(fmaf(ag, L2E, ms));
+    const float e8 = (M == 9) ? ex2_approx(fmaf(a8, L2E, ms)) : 0.f;
+    float z = eg;
+    z += __shfl_xor_sync(0xffffffffu, z, 4);
+    z += __shfl_xor_sync(0xffffffffu, z, 8);
+    z += __shfl_xor_sync(0xffffffffu, z, 16);
+    z += e8;
+    const float rs = ((in.okm >> i) & 1) ? rcp_approx(z) : 0.f;
+    qg[i] = eg * rs;
+    q8[i] = e8 * rs;
+  }
+  uint32_t gh0, gl0, gh1, gl1, eh0 = 0, el0 = 0, eh1 = 0, el1 = 0;
+  split_rn(qg[0], qg[1], gh0, gl0);
+  split_rn(qg[2], qg[3], gh1, gl1);
+  if (M == 9) {
+    split_rn(q8[0], q8[1], eh0, el0);
+    split_rn(q8[2], q8[3], eh1, el1);
+  }
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const uint32_t sel = (nb & 1) ? 0x7632u : 0x5410u;
+    const uint32_t b0 = __byte_perm(w4(in.xh[0], nb >> 1), w4(in.xh[1], nb >> 1), sel);
+    const uint32_t b1 = __byte_perm(w4(in.xh[2], nb >> 1), w4(in.xh[3], nb >> 1), sel);
+    if (M == 9) {
+      hm_mma<FIRST>(acc[nb], gh0, eh0, gh1, eh1, b0, b1);
+      hm_mma<false>(acc[nb], gl0, el0, gl1, el1, b0, b1);
+    } else {
+      hm_mma<FIRST>(acc[nb], gh0, gl0, gh1, gl1, b0, b1);   // rows g: q_hi.x_hi, rows g+8: q_lo.x_hi
+    }
+  }
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const uint32_t sel = (nb & 1) ? 0x7632u : 0x5410u;
+    const uint32_t b0 = __byte_perm(w4(in.xl[0], nb >> 1), w4(in.xl[1], nb >> 1), sel);
+    const uint32_t b1 = __byte_perm(w4(in.xl[2], nb >> 1), w4(in.xl[3], nb >> 1), sel);
+    if (M == 9) hm_mma<false>(acc[nb], gh0, eh0, gh1, eh1, b0, b1);
+    else hm_mma<false>(acc[nb], gh0, 0u, gh1, 0u, b0, b1);
+  }
+  return c;
+}
+
+// S of facet f (C fragments) -> fp16 hi/lo rows of the stage-2 B operand.
+// rows m = g of units 2t (c0) and 2t+1 (c1) -> atoms 2(g>>1) + {0,1}, slot 4(g&1) + t
+template <int M>
+__device__ __forceinline__ void hm_drain(uint8_t* b3, int f, int g, int t, const float (&acc)[8][4]) {
+  using Cfg = HmCfg<M>;
+  const int sw = f & 7;
+  uint8_t* rh = b3 + (f >> 3) * 1024 + sw * 128;              // hi row f of an atom
+  uint8_t* rl = rh + (kHT >> 3) * 1024;                       // lo row 32 + f
+  const int slot = (((g & 1) * 4 + t) ^ sw) << 4;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v0 = acc[2 * j][h], v1 = acc[2 * j + 1][h];
+      if (M == 8) v0 += acc[2 * j][2 + h], v1 += acc[2 * j + 1][2 + h];
+      split_trunc(v0, v1, hi[j], lo[j]);
+    }
+    const int aoff = (2 * (g >> 1) + h) * Cfg::ATOM_BYTES + slot;
+    *reinterpret_cast<uint4*>(rh + aoff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(rl + aoff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (M == 9) {
+    // row m = 8 (every lane holds a copy): lane (g,t) converts channels 16t + 8(g>>2) + 2(g&3), +1
+    const int gq = g & 3;
+    const bool up = g >= 4;
+    const float e0 = gq == 0 ? acc[0][2] : (gq == 1 ? acc[2][2] : (gq == 2 ? acc[4][2] : acc[6][2]));
+    const float e1 = gq == 0 ? acc[1][2] : (gq == 1 ? acc[3][2] : (gq == 2 ? acc[5][2] : acc[7][2]));
+    const float o0 = gq == 0 ? acc[0][3] : (gq == 1 ? acc[2][3] : (gq == 2 ? acc[4][3] : acc[6][3]));
+    const float o1 = gq == 0 ? acc[1][3] : (gq == 1 ? acc[3][3] : (gq == 2 ? acc[5][3] : acc[7][3]));
+    uint32_t hi, lo;
+    split_trunc(up ? o0 : e0, up ? o1 : e1, hi, lo);
+    const int off = 8 * Cfg::ATOM_BYTES + (((2 * t + (g >> 2)) ^ sw) << 4) + gq * 4;
+    *reinterpret_cast<uint32_t*>(rh + off) = hi;
+    *reinterpret_cast<uint32_t*>(rl + off) = lo;
+  }
+}
+
+template <int M, int NG>
+__global__ void __launch_bounds__(kHThreads, 1)
+conv_hm_kernel(const HmParams p) {
+  using Cfg = HmCfg<M>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + HB_NUM);
+  unsigned* arrived = reinterpret_cast<unsigned*>(tmem_slot + 2);   // [2] aggregator warps done with B3 buffer b
+  float* invtab = reinterpret_cast<float*>(arrived + 2);            // [33] 1 / cnt (0 for cnt = 0)
+  float* rowinv = reinterpret_cast<float*>(smem + Cfg::OFF_ROW);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nepi = p.cout >> 4;   // epilogue warps with outputs
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bars[HB_B3_FREE + i], 1);
+      tc::mbar_init(&bars[HB_D_FULL + i], 1), tc::mbar_init(&bars[HB_D_FREE + i], nepi);
+      arrived[i] = 0;
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 5 && lane <= 32 - 1) invtab[lane + 1] = 1.f / static_cast<float>(lane + 1), invtab[0] = 0.f;
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // weight operand -> TMEM: lane 32 warp + l of the image is TMEM lane 32 warp + l, column = K pair
+    const uint32_t* src = p.wt + static_cast<size_t>(warp * 32 + lane) * Cfg::W_COLS;
+#pragma unroll 1
+    for (int c0 = 0; c0 < Cfg::W_COLS; c0 += 32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint4 tq = __ldg(reinterpret_cast<const uint4*>(src + c0) + u);
+        r[4 * u] = tq.x, r[4 * u + 1] = tq.y, r[4 * u + 2] = tq.z, r[4 * u + 3] = tq.w;
+      }
+      tc::tmem_st32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+    }
+    tc::tc_wait_st();
+    tc::tc_fence_before_sync();
+  }
+  __syncthreads();
+  tc::tc_fence_after_sync();
+
+  if (warp < 4) {
+    // =========================================================== epilogue: Y (TMEM) -> global
+    if (warp < nepi) {
+      const int q = warp;
+      const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+      // lane 16h + i of quadrant q: h = 0 holds Wh.(Sh|Sl) of channel o = 16q + i, h = 1 holds Wl.Sh.
+      // After one shuffle round lane (h, i) owns facets 16h .. 16h+15 of channel o.
+      const int hh = lane >> 4, o = q * 16 + (lane & 15);
+      const float bo = p.add_bias ? __ldg(p.b + o) : 0.f;
+      const float sc0 = __ldg(p.xunscale) * __ldg(p.wunscale);
+      const bool unmasked = !p.bias_mask;
+      int it = 0;
+      float amax = 0.f;
+      for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int64_t r0 = tile * kHT + 16 * hh;
+        int64_t left = p.rows - r0;
+        const int nv = left >= 16 ? 16 : (left < 0 ? 0 : static_cast<int>(left));
+        tc::mbar_wait_relaxed(&bars[HB_D_FULL + buf], (it >> 1) & 1);
+        tc::tc_fence_after_sync();
+        uint32_t d0[32], d1[32];
+        tc::tmem_ld32(tmem + lane_base + Cfg::D_COL + buf * Cfg::ND, d0);        // . Sh of facets 0..31
+        tc::tmem_ld32(tmem + lane_base + Cfg::D_COL + buf * Cfg::ND + 32, d1);   // . Sl
+        float inv[16];
+        {
+          const float4* ri = reinterpret_cast<const float4*>(rowinv + (it & 3) * kHT + 16 * hh);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = ri[j];
+            inv[4 * j] = v.x, inv[4 * j + 1] = v.y, inv[4 * j + 2] = v.z, inv[4 * j + 3] = v.w;
+          }
+        }
+        tc::tc_wait_ld();
+        tc::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[HB_D_FREE + buf]);
+        float keep[16], send[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a_lo = __uint_as_float(d0[j]) + __uint_as_float(d1[j]);             // facets 0..15  (hi lanes)
+          const float a_up = __uint_as_float(d0[16 + j]) + __uint_as_float(d1[16 + j]);   // facets 16..31 (hi lanes)
+          const float l_lo = __uint_as_float(d0[j]) * (1.f / 2048.f);                     // facets 0..15  (lo lanes)
+          const float l_up = __uint_as_float(d0[16 + j]) * (1.f / 2048.f);                // facets 16..31 (lo lanes)
+          keep[j] = hh ? l_up : a_lo;
+          send[j] = hh ? l_lo : a_up;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) send[j] = __shfl_xor_sync(0xffffffffu, send[j], 16);
+        float yv[16];
+        float* yp = p.y + r0 * p.ldy + o;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float accv = hh ? (send[j] + keep[j]) : (keep[j] + send[j]);   // (Wh.Sh + Wh.Sl) + Wl.Sh / 2048
+          const float fl = (inv[j] > 0.f || unmasked) ? bo : 0.f;
+          float v = fmaf(inv[j] * sc0, accv, fl);
+          if (p.accumulate && j < nv) v += yp[j * p.ldy];
+          if (p.apply_act && p.act == FGC_ACT_LRELU) v = lrelu_f(v, p.alpha);
+          yv[j] = v;
+        }
+        if (nv == 16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) yp[j * p.ldy] = yv[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nv) yp[j * p.ldy] = yv[j];
+        }
+        if (p.ypool != nullptr) {
+          float* pp = p.ypool + (r0 >> 2) * p.ldp + o;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            if (4 * a < nv) pp[a * p.ldp] = fmaxf(fmaxf(yv[4 * a], yv[4 * a + 1]), fmaxf(yv[4 * a + 2], yv[4 * a + 3]));
+        }
+        if (p.ymax != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nv) amax = fmaxf(amax, fabsf(yv[j]));
+        }
+      }
+      if (p.ymax != nullptr) {   // max is order-independent: the atomic keeps the result deterministic
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
+        if (lane == 0) atomicMax(p.ymax, __float_as_uint(amax));
+      }
+    }
+  } else {
+    // =========================================================== aggregators (+ stage-2 issue by the last to arrive)
+    // Facet n of this warp: tile counter n >> 2, facet n & 3 of the warp's four; item m = n * NG + slot group.
+    const int aw = warp - 4;
+    const int g = lane >> 2, t = lane & 3;
+    const int my_tiles = static_cast<int>((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int nitems = my_tiles * kHFpw * NG;
+    const int rows32 = static_cast<int>(p.rows);
+    constexpr uint32_t idesc = (1u << 4) | ((static_cast<uint32_t>(Cfg::ND) >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t sb = tc::smem_u32(smem);
+    const float* uvx_g = p.uvx + g;
+    const float* uvx_vg = p.uvx + M + g;
+    const uint4* img_g = p.img + g;
+    auto row_of = [&](int m) -> int {   // global row of item m, -1 when there is none
+      const int n = m / NG;
+      const int r = (static_cast<int>(blockIdx.x) + (n >> 2) * static_cast<int>(gridDim.x)) * kHT + aw * kHFpw + (n & 3);
+      return (m < nitems && r < rows32) ? r : -1;
+    };
+    auto load_ids = [&](int m, int (&id)[4]) {
+      const int r = row_of(m);
+      const int32_t* arow = p.adj + static_cast<int64_t>(r < 0 ? 0 : r) * p.K + (m % NG) * 16 + 2 * t;
+      const int kmax = (r < 0) ? 0 : p.K - (m % NG) * 16 - 2 * t;   // slots of this lane: offsets 0, 1, 8, 9
+      id[0] = (0 < kmax) ? __ldg(arow) : 0;
+      id[1] = (1 < kmax) ? __ldg(arow + 1) : 0;
+      id[2] = (8 < kmax) ? __ldg(arow + 8) : 0;
+      id[3] = (9 < kmax) ? __ldg(arow + 9) : 0;
+    };
+    int base_cur = 0, base_next = p.N;     // batch element of the rows the issue stage walks (monotone)
+    auto issue = [&](int m, const int (&id)[4], HmPre& o) {
+      const int r = row_of(m);
+      int base = 0;
+      if (!p.single && r >= 0) {
+        while (r >= base_next) base_cur = base_next, base_next += p.N;
+        base = base_cur;
+      }
+      const int64_t ro = static_cast<int64_t>((r < 0 ? 0 : r) >> p.upshift) * (2 * M);
+      o.uo_g = __ldg(uvx_g + ro);
+      o.uo_8 = (M == 9) ? __ldg(p.uvx + ro + 8) : 0.f;
+      o.okm = 0, o.nz = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = static_cast<unsigned>(id[i] - 1) < static_cast<unsigned>(p.N);
+        const int row = ok ? ((base + id[i] - 1) >> p.upshift) : p.zrow;   // zrow: all-zero image / logit row
+        o.okm |= ok ? (1 << i) : 0;
+        o.nz += (id[i] != 0);
+        const int64_t lo = static_cast<int64_t>(row) * (2 * M);
+        o.vg[i] = __ldg(uvx_vg + lo);
+        o.v8[i] = (M == 9) ? __ldg(p.uvx + lo + (M + 8)) : 0.f;
+        const uint4* src = img_g + static_cast<int64_t>(row) * p.img_ld;
+        o.xh[i] = __ldg(src);
+        o.xl[i] = __ldg(src + 8);
+      }
+    };
+    float acc[8][4];
+    int cnt = 0;
+    auto finish = [&](int m) {   // the facet of item m is aggregated: drain, and after the warp's last facet hand over
+      const int n = m / NG, it = n >> 2, fi = n & 3, buf = it & 1, f = aw * kHFpw + fi;
+      if (fi == 0) tc::mbar_wait(&bars[HB_B3_FREE + buf], ((it >> 1) & 1) ^ 1);
+      hm_drain<M>(smem + buf * Cfg::B3_BUF, f, g, t, acc);
+      if (lane == 0) rowinv[(it & 3) * kHT + f] = invtab[cnt];
+      if (fi != kHFpw - 1) return;
+      // this warp's rows of the tile are in place: the last of the 8 warps to get here issues stage 2
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        last = (atomicAdd(&arrived[buf], 1u) & (kHAgg - 1)) == kHAgg - 1;
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence_block();
+        tc::fence_proxy_async_smem();
+        tc::mbar_wait(&bars[HB_D_FREE + buf], ((it >> 1) & 1) ^ 1);
+        tc::tc_fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t b3 = sb + buf * Cfg::B3_BUF;
+#pragma unroll 1
+          for (int a = 0; a < Cfg::NATOM; ++a) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bd = tc::smem_desc_k_sw128(b3 + a * Cfg::ATOM_BYTES + ks * 32);
+              tc::mma_f16_ts(tmem + Cfg::D_COL + buf * Cfg::ND, tmem + a * 32 + ks * 8, bd, idesc, (a | ks) ? 1u : 0u);
+            }
+          }
+          tc::tc_commit(&bars[HB_B3_FREE + buf]);
+          tc::tc_commit(&bars[HB_D_FULL + buf]);
+        }
+        __syncwarp();
+      }
+    };
+    HmPre A, B;
+    int idA[4], idB[4];
+    load_ids(0, idA);
+    load_ids(1, idB);
+    issue(0, idA, A);
+    load_ids(2, idA);
+#pragma unroll 1
+    for (int m = 0; m < nitems; m += 2) {   // nitems is even
+      issue(m + 1, idB, B);
+      load_ids(m + 3, idB);
+      cnt = hm_mma_item<M, true>(A, acc);
+      if (NG == 1) finish(m);
+      issue(m + 2, idA, A);
+      load_ids(m + 4, idA);
+      if (NG == 1) {
+        cnt = hm_mma_item<M, true>(B, acc);
+      } else {
+        cnt += hm_mma_item<M, false>(B, acc);
+      }
+      finish(m + 1);
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------ weight image in TMEM layout
+// wt[img][lane][col]: lane 32q + 16h + i <-> row (h, o = 16q + i) of [Wh;Wl] of output block ob, column = K pair of
+// aggregation unit u; K order: atom a < 8 holds weights m = 2(a>>1), +1 and the channel units of parity a&1
+// (slot s of the atom: m = 2(a>>1) + (s>>2), unit = 2(s&3) + (a&1)), atom 8 holds m = 8.
+__global__ void __launch_bounds__(1024)
+prep_wt_kernel(const float* __restrict__ W0, uint32_t* __restrict__ wt, float* __restrict__ wunscale, int M, int Cout,
+               int Cw, int CB, int nunits) {
+  __shared__ float red[32];
+  const int total = M * Cout * Cw;
+  float mx = 0.f;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) mx = fmaxf(mx, fabsf(W0[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  int E = (__float_as_int(mx) >> 23) & 0xFF;
+  E = min(max(E, 16), 240);
+  const float sc = __int_as_float((253 - E) << 23);
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) wunscale[0] = __int_as_float((E + 1) << 23);
+  const int ob = blockIdx.y / nunits, u = blockIdx.y % nunits;
+  const int wcols = M * 32;
+  uint32_t* dst = wt + static_cast<size_t>(blockIdx.y) * 128 * wcols;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 128 * wcols; e += gridDim.x * blockDim.x) {
+    const int ln = e / wcols, col = e % wcols;
+    const int q = ln >> 5, h = (ln >> 4) & 1, o = 16 * q + (ln & 15);
+    uint32_t word = 0;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int kpos = 2 * col + kk, a = kpos >> 6, s = (kpos & 63) >> 3, pos = kpos & 7;
+      int m, c;
+      if (a < 8) m = 2 * (a >> 1) + (s >> 2), c = (2 * (s & 3) + (a & 1)) * 8 + pos;
+      else m = 8, c = kpos & 63;
+      float v = 0.f;
+      if (o < CB && ob * CB + o < Cout && u * 64 + c < Cw && m < M)
+        v = W0[(static_cast<size_t>(m) * Cout + ob * CB + o) * Cw + u * 64 + c] * sc;
+      const __half hv = __float2half_rn(v);
+      const __half out = h ? __float2half_rn((v - __half2float(hv)) * 2048.f) : hv;
+      word |= static_cast<uint32_t>(__half_as_ushort(out)) << (16 * kk);
+    }
+    dst[e] = word;
+  }
+}
+
+// ------------------------------------------------------------------ fp16 hi|lo image of x, all units of a layer
+// img[r][u] = [fp16(x_r[64u..] * s) (64 halves) | fp16 residuals (64 halves)], s = 2^(126-E), E = exponent of max|x|;
+// channels beyond Cw read as zero.
+__global__ void __launch_bounds__(256)
+hm_absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(x) + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+__global__ void __launch_bounds__(256)
+hm_prep_img_kernel(const float* __restrict__ x, int ldx, int Cw, int nunits, int64_t rows,
+                   const unsigned* __restrict__ maxbits, uint4* __restrict__ img, float* __restrict__ xunscale) {
+  int E = static_cast<int>((__ldg(maxbits) >> 23) & 0xFF);
+  E = min(max(E, 16), 240);
+  const float sc = __int_as_float((253 - E) << 23);
+  if (blockIdx.x == 0 && threadIdx.x == 0) xunscale[0] = __int_as_float((E + 1) << 23);
+  const int per_row = nunits * 8;   // one thread per 8 channels
+  const int64_t total = rows * per_row;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / per_row;
+    const int j = static_cast<int>(i % per_row), u = j >> 3, jj = j & 7;
+    const int c0 = u * 64 + jj * 8;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (c0 < Cw) a = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c0));
+    if (c0 + 4 < Cw) b = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c0 + 4));
+    const float v[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, b.x * sc, b.y * sc, b.z * sc, b.w * sc};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_rn(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+    uint4* dst = img + (r * nunits + u) * 16 + jj;
+    dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+struct HmWs {
+  uint4* img;
+  unsigned* scal;     // [0] max|x| bits, [1] 2^ex un-scale
+  uint32_t* wt;
+  float* wunscale;
+};
+size_t hm_img_bytes(int64_t rows_img, int nunits) { return static_cast<size_t>(rows_img) * nunits * 256; }
+size_t hm_wt_bytes(int M, int nimg) { return static_cast<size_t>(nimg) * 128 * M * 32 * 4; }
+HmWs hm_views(void* ws_ptr, size_t ws_bytes, int64_t rows_img, int nunits, int M, int nimg, bool* ok) {
+  Workspace ws(ws_ptr, ws_bytes);
+  HmWs v;
+  v.img = reinterpret_cast<uint4*>(ws.take<char>(hm_img_bytes(rows_img, nunits)));
+  v.scal = ws.take<unsigned>(16);
+  v.wt = reinterpret_cast<uint32_t*>(ws.take<char>(hm_wt_bytes(M, nimg)));
+  v.wunscale = ws.take<float>(16);
+  *ok = ws.ok();
+  return v;
+}
+
+}  // namespace
+
+bool conv_hm_supported(int Cin, int Cw, int Cout, int M, int K) {
+  return (M == 8 || M == 9) && K >= 1 && K <= 32 && Cin % 4 == 0 && Cw % 4 == 0 && (Cw == 32 || Cw == 64 || Cw == 128) &&
+         (Cout == 32 || Cout == 64 || Cout == 128);
+}
+
+size_t conv_hm_workspace(int64_t rows_img, int Cw, int Cout, int M) {
+  const int nunits = (Cw + 63) / 64, CB = Cout < 64 ? Cout : 64, nob = Cout / CB;
+  return ws_bytes(hm_img_bytes(rows_img + 1, nunits), 1) + ws_bytes(16, 4) + ws_bytes(hm_wt_bytes(M, nunits * nob), 1) +
+         ws_bytes(16, 4);
+}
+
+// p.x: rows >> upshift rows of Cin floats (the first Cw are aggregated); p.uvx: their logits, with room for one more
+// row (zeroed here).
+// ypool (optional): [rows / 4][Cout] max over groups of 4 rows of y; ymax (optional): atomicMax target for max|y| bits;
+// xmax (optional): device word that already holds the bits of an upper bound of max|x| (else computed here).
+int launch_conv_hm(const ConvFwdParams& p, const float* W0, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                   int upshift, float* ypool, unsigned* ymax, const unsigned* xmax) {
+  const int nunits = (p.Cw + 63) / 64, CB = p.Cout < 64 ? p.Cout : 64, nob = p.Cout / CB;
+  const int64_t rows_img = p.rows >> upshift;
+  bool ok = false;
+  const HmWs v = hm_views(workspace, workspace_bytes, rows_img + 1, nunits, p.M, nunits * nob, &ok);
+  FGC_REQUIRE(ok, "conv_hm: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              conv_hm_workspace(rows_img, p.Cw, p.Cout, p.M));
+  FGC_REQUIRE(ypool == nullptr || (p.N % 4 == 0), "conv_hm: pooled output needs N %% 4 == 0");
+  const int blocks = num_sms() * 8;
+  if (xmax == nullptr) {
+    FGC_CUDA(cudaMemsetAsync(v.scal, 0, 16 * sizeof(unsigned), st));
+    hm_absmax_kernel<<<blocks, 256, 0, st>>>(p.x, rows_img * (p.Cin / 4), v.scal);
+    FGC_LAUNCHED("absmax_kernel");
+    xmax = v.scal;
+  }
+  hm_prep_img_kernel<<<blocks, 256, 0, st>>>(p.x, p.Cin, p.Cw, nunits, rows_img, xmax, v.img,
+                                             reinterpret_cast<float*>(v.scal + 1));
+  FGC_LAUNCHED("prep_x_image_kernel");
+  // row `rows_img` of the image and of the logits is all zero: what padding and out-of-range slots read
+  FGC_CUDA(cudaMemsetAsync(v.img + rows_img * nunits * 16, 0, static_cast<size_t>(nunits) * 256, st));
+  FGC_CUDA(cudaMemsetAsync(const_cast<float*>(p.uvx) + rows_img * 2 * p.M, 0, static_cast<size_t>(2 * p.M) * 4, st));
+  prep_wt_kernel<<<dim3(4, nunits * nob), 1024, 0, st>>>(W0, v.wt, v.wunscale, p.M, p.Cout, p.Cw, CB, nunits);
+  FGC_LAUNCHED("prep_w_image_kernel");
+  HmParams hp{};
+  hp.img_ld = nunits * 16, hp.xunscale = reinterpret_cast<const float*>(v.scal + 1), hp.uvx = p.uvx, hp.adj = p.adj;
+  hp.wunscale = v.wunscale, hp.ldy = p.Cout, hp.ldp = p.Cout, hp.rows = p.rows, hp.ntiles = (p.rows + kHT - 1) / kHT;
+  hp.N = p.N, hp.K = p.K, hp.upshift = upshift, hp.bias_mask = p.bias_mask, hp.act = p.act, hp.alpha = p.alpha;
+  hp.cout = CB, hp.single = p.rows == p.N, hp.zrow = static_cast<int>(rows_img);
+  auto kern = p.M == 9 ? (p.K <= 16 ? conv_hm_kernel<9, 1> : conv_hm_kernel<9, 2>)
+                       : (p.K <= 16 ? conv_hm_kernel<8, 1> : conv_hm_kernel<8, 2>);
+  const int smem = p.M == 9 ? HmCfg<9>::SMEM_BYTES : HmCfg<8>::SMEM_BYTES;
+  FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int64_t grid = num_sms();
+  if (grid > hp.ntiles) grid = hp.ntiles;
+  if (grid < 1) grid = 1;
+  for (int ob = 0; ob < nob; ++ob)
+    for (int u = 0; u < nunits; ++u) {
+      const bool last = u == nunits - 1;
+      hp.img = v.img + u * 16;
+      hp.wt = v.wt + static_cast<size_t>(ob * nunits + u) * 128 * p.M * 32;
+      hp.b = p.b + ob * CB, hp.y = p.y + ob * CB;
+      hp.ypool = (last && ypool != nullptr) ? ypool + ob * CB : nullptr;
+      hp.ymax = last ? ymax : nullptr;
+      hp.add_bias = u == 0, hp.accumulate = u > 0, hp.apply_act = last;
+      kern<<<static_cast<unsigned>(grid), kHThreads, smem, st>>>(hp);
+      FGC_LAUNCHED("conv_hm_kernel");
+    }
+  return FGC_OK;
+}
+
+}  // namespace fgc

@@ -108,6 +108,11 @@ int build_reverse_adj(const int32_t* adj, int B, int N, int K, int32_t* rev_ptr,
                       int64_t* nnz_out, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_reduce_partials(const float* part, float* out, int64_t n, int P, int64_t stride,
                            cudaStream_t st);
+// HMMA-aggregation + tcgen05-contraction forward (conv_hm.cu): any adjacency, no tile plan
+bool conv_hm_supported(int Cin, int Cw, int Cout, int M, int K);
+size_t conv_hm_workspace(int64_t rows_img, int Cw, int Cout, int M);
+int launch_conv_hm(const ConvFwdParams& p, const float* W0, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                   int upshift = 0, float* ypool = nullptr, unsigned* ymax = nullptr, const unsigned* xmax = nullptr);
 // fused regression head on tcgen05 (lin_tc.cu)
 bool mlp_head_tc_supported(int64_t rows, int Cin, int H, int Cout);
 size_t mlp_head_tc_workspace();

@@ -203,9 +203,9 @@ def test_fused_upsampling_is_bit_identical_to_the_repeated_input(B, N, Cin, Cout
     assert torch.equal(y_up, y_mat)
     ref = cf.conv_fwd(cf.upsample(xc[:1].astype(np.float64), 2), adj[:1], W0, b, u, v, c)
     assert np.abs(y_up[:1].cpu().numpy() - ref).max() < 1e-5
-    # shapes without the path say so instead of computing something else
-    a8 = [T(a) for a in (W0[:8], b, u[:8], v[:8], c[:8])]
-    assert ops.conv_fwd_up(T(xc), T(adj), *a8, upshift=2) is None
+    # shapes without the path say so instead of computing something else (M = 5 has no tensor-core forward)
+    a5 = [T(a) for a in (W0[:5], b, u[:5], v[:5], c[:5])]
+    assert ops.conv_fwd_up(T(xc), T(adj), *a5, upshift=2) is None
 
 
 def test_network_with_fused_upsampling_matches_unfused_at_size():
