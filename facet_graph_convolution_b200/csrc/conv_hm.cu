@@ -2,7 +2,7 @@
 // :870-932 with M = 9; also the M = 8 benchmark layer): per-facet aggregation on the warp-level tensor path
 // (mma.sync m16n8k16), contraction with W on tcgen05.  No tile plan, no per-tile row dedup: works on any adjacency.
 //
-//   stage 1 (8 aggregator warps, one facet at a time per warp, registers only)
+//   stage 1 (16 aggregator warps, one facet at a time per warp, registers only)
 //       S_n[m, c] = sum_k q[n,k,m] x_{j_k}[c]            A = q  (16 x 16: rows m, columns = neighbour slots)
 //                                                         B = the 16 gathered rows of the fp16 hi|lo image of x
 //       q is computed in the A-fragment layout (lane (g,t) owns row m = g and slots 2t,2t+1,2t+8,2t+9; the
@@ -23,6 +23,8 @@
 // One launch covers 64 aggregation channels x up to 64 outputs; wider layers are sums of launches over channel
 // blocks (bias in the first, activation / pooling in the last), as in conv_fwd_tc.cu.
 #include "conv_launch.cuh"
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace fgc {
@@ -30,9 +32,9 @@ namespace fgc {
 namespace {
 
 constexpr int kHT = 32;                              // facets per tile
-constexpr int kHAgg = 8;                             // aggregator warps
+constexpr int kHAgg = 16;                            // aggregator warps
 constexpr int kHFpw = kHT / kHAgg;                   // facets per warp and tile
-constexpr int kHThreads = (4 + kHAgg) * 32;          // 4 epilogue warps + aggregators (3 warps per sub-partition)
+constexpr int kHThreads = (4 + kHAgg) * 32;          // 4 epilogue warps + aggregators (5 warps per sub-partition)
 
 template <int M>
 struct HmCfg {
@@ -239,6 +241,8 @@ conv_hm_kernel(const HmParams p) {
   float* rowinv = reinterpret_cast<float*>(smem + Cfg::OFF_ROW);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nepi = p.cout >> 4;   // epilogue warps with outputs
+  // tiles blockIdx.x, + gridDim.x, ...  (a contiguous range per CTA was measured slower: 0.67 vs 0.63 ms per 562 k rows)
+  const int my_tiles = static_cast<int>((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -361,10 +365,9 @@ conv_hm_kernel(const HmParams p) {
     }
   } else {
     // =========================================================== aggregators (+ stage-2 issue by the last to arrive)
-    // Facet n of this warp: tile counter n >> 2, facet n & 3 of the warp's four; item m = n * NG + slot group.
+    // Facet n of this warp: tile counter n / kHFpw, facet n % kHFpw of the warp's own; item m = n * NG + slot group.
     const int aw = warp - 4;
     const int g = lane >> 2, t = lane & 3;
-    const int my_tiles = static_cast<int>((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const int nitems = my_tiles * kHFpw * NG;
     const int rows32 = static_cast<int>(p.rows);
     constexpr uint32_t idesc = (1u << 4) | ((static_cast<uint32_t>(Cfg::ND) >> 3) << 17) | ((128u >> 4) << 24);
@@ -374,7 +377,7 @@ conv_hm_kernel(const HmParams p) {
     const uint4* img_g = p.img + g;
     auto row_of = [&](int m) -> int {   // global row of item m, -1 when there is none
       const int n = m / NG;
-      const int r = (static_cast<int>(blockIdx.x) + (n >> 2) * static_cast<int>(gridDim.x)) * kHT + aw * kHFpw + (n & 3);
+      const int r = (static_cast<int>(blockIdx.x) + (n / kHFpw) * static_cast<int>(gridDim.x)) * kHT + aw * kHFpw + (n % kHFpw);
       return (m < nitems && r < rows32) ? r : -1;
     };
     auto load_ids = [&](int m, int (&id)[4]) {
@@ -415,7 +418,7 @@ conv_hm_kernel(const HmParams p) {
     float acc[8][4];
     int cnt = 0;
     auto finish = [&](int m) {   // the facet of item m is aggregated: drain, and after the warp's last facet hand over
-      const int n = m / NG, it = n >> 2, fi = n & 3, buf = it & 1, f = aw * kHFpw + fi;
+      const int n = m / NG, it = n / kHFpw, fi = n % kHFpw, buf = it & 1, f = aw * kHFpw + fi;
       if (fi == 0) tc::mbar_wait(&bars[HB_B3_FREE + buf], ((it >> 1) & 1) ^ 1);
       hm_drain<M>(smem + buf * Cfg::B3_BUF, f, g, t, acc);
       if (lane == 0) rowinv[(it & 3) * kHT + f] = invtab[cnt];
@@ -450,26 +453,25 @@ conv_hm_kernel(const HmParams p) {
         __syncwarp();
       }
     };
-    HmPre A, B;
-    int idA[4], idB[4];
-    load_ids(0, idA);
-    load_ids(1, idB);
-    issue(0, idA, A);
-    load_ids(2, idA);
+    // the adjacency ids of the next item are in flight while the current one is gathered and aggregated;
+    // memory latency is otherwise covered by the other four aggregator warps of the sub-partition
+    HmPre P;
+    int idc[4], idn[4];
+    load_ids(0, idc);
 #pragma unroll 1
-    for (int m = 0; m < nitems; m += 2) {   // nitems is even
-      issue(m + 1, idB, B);
-      load_ids(m + 3, idB);
-      cnt = hm_mma_item<M, true>(A, acc);
-      if (NG == 1) finish(m);
-      issue(m + 2, idA, A);
-      load_ids(m + 4, idA);
-      if (NG == 1) {
-        cnt = hm_mma_item<M, true>(B, acc);
+    for (int m = 0; m < nitems; m += NG) {
+      load_ids(m + 1, idn);
+      issue(m, idc, P);
+      cnt = hm_mma_item<M, true>(P, acc);
+      if (NG == 2) {
+        load_ids(m + 2, idc);
+        issue(m + 1, idn, P);
+        cnt += hm_mma_item<M, false>(P, acc);
       } else {
-        cnt += hm_mma_item<M, false>(B, acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) idc[i] = idn[i];
       }
-      finish(m + 1);
+      finish(m + NG - 1);
     }
   }
   tc::tc_fence_before_sync();
