@@ -77,6 +77,11 @@ SIGNATURES = {
     "fgc_lin_bwd_workspace": (sz, [i64, i32, i32]),
     "fgc_mlp_head_workspace": (sz, [i64, i32, i32, i32]),
     "fgc_mlp_head_fwd": (i32, [p, p, p, p, p, p, i64, i32, i32, i32, f32, p, sz, p]),
+    "fgc_net_param_count": (i32, []),
+    "fgc_net_prepared_bytes": (sz, []),
+    "fgc_net_prepare": (i32, [p, i32, p, sz, p]),
+    "fgc_net_fwd_workspace": (sz, [i32, i32, i32]),
+    "fgc_net_fwd": (i32, [i32, i32, i32, p, p, p, p, p, i32, p, p, p, sz, p]),
     "fgc_normalize_workspace": (sz, [i64]),
     "fgc_normalize_rows": (i32, [p, p, i64, p, sz, p]),
     "fgc_normalize_rows_bwd": (i32, [p, p, p, i64, p, sz, p]),

@@ -99,7 +99,7 @@ static bool use_hm(const fgc_conv_shape* s) {
 
 static size_t conv_fwd_workspace(const fgc_conv_shape* s) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
-  return (use_hm(s) ? conv_hm_workspace(rows, s->Cw, s->Cout, s->M) + 256 : 0) + ws_bytes((rows + 1) * 2 * s->M, 4) + ws_bytes(static_cast<size_t>(s->M) * s->Cout * s->Cw, 4) +
+  return (use_hm(s) ? conv_hm_workspace(rows, s->Cw, s->Cout, s->M, s->B) + 256 : 0) + ws_bytes((rows + 1) * 2 * s->M, 4) + ws_bytes(static_cast<size_t>(s->M) * s->Cout * s->Cw, 4) +
          ws_bytes(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw), 1) + (use_mma(s) ? conv_mma_workspace(rows) + 256 : 0) + 512;
 }
 
@@ -117,7 +117,7 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
     Workspace wsu(workspace, workspace_bytes);
     float* uvx_c = wsu.take<float>((rows + 1) * 2 * s->M);
     if (use_hm(s)) {
-      const size_t hb = conv_hm_workspace(rows >> upshift, s->Cw, s->Cout, s->M);
+      const size_t hb = conv_hm_workspace(rows >> upshift, s->Cw, s->Cout, s->M, s->B);
       char* hws = wsu.take<char>(hb);
       FGC_REQUIRE(wsu.ok(), "conv_fwd_up: workspace too small");
       fgc_conv_shape sc = *s;
@@ -165,7 +165,7 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
   rc = launch_assign_logits(s, x, u, v, c, uvx, st);
   if (rc) return rc;
   if (use_hm(s)) {
-    const size_t hb = conv_hm_workspace(rows, s->Cw, s->Cout, s->M);
+    const size_t hb = conv_hm_workspace(rows, s->Cw, s->Cout, s->M, s->B);
     char* hws = ws.take<char>(hb);
     FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the HMMA-aggregation path");
     return launch_conv_hm(p, W0, hws, hb, st);

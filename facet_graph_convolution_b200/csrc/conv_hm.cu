@@ -56,7 +56,7 @@ enum { HB_B3_FREE = 0, HB_D_FULL = 2, HB_D_FREE = 4, HB_NUM = 6 };
 struct HmParams {
   const uint4* img;        // fp16 image of this launch's 64-channel unit: row r at img + r * img_ld, [0..8) hi, [8..16) lo
   int img_ld;
-  const float* xunscale;
+  const float* xunscale;   // [B]: 2^ex of the image rows of every batch element
   const float* uvx;        // [rows >> upshift][2M]
   const int32_t* adj;
   const uint32_t* wt;      // [128 TMEM lanes][W_COLS]
@@ -66,7 +66,7 @@ struct HmParams {
   int ldy;
   float* ypool;            // optional: max over groups of 4 consecutive rows of the final output
   int ldp;
-  unsigned* ymax;          // optional: atomicMax of the bits of |final output|
+  unsigned* ymax;          // optional, [B]: atomicMax of the bits of |final output| per batch element (needs N % 16 == 0)
   int64_t rows, ntiles;
   int N, K, upshift;
   int bias_mask, act;
@@ -287,10 +287,11 @@ conv_hm_kernel(const HmParams p) {
       // After one shuffle round lane (h, i) owns facets 16h .. 16h+15 of channel o.
       const int hh = lane >> 4, o = q * 16 + (lane & 15);
       const float bo = p.add_bias ? __ldg(p.b + o) : 0.f;
-      const float sc0 = __ldg(p.xunscale) * __ldg(p.wunscale);
+      const float wun = __ldg(p.wunscale);
       const bool unmasked = !p.bias_mask;
+      const bool aligned = (p.N & 15) == 0;   // a lane's 16 rows lie in one batch element
       int it = 0;
-      float amax = 0.f;
+
       for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const int64_t r0 = tile * kHT + 16 * hh;
@@ -328,12 +329,23 @@ conv_hm_kernel(const HmParams p) {
         for (int j = 0; j < 16; ++j) send[j] = __shfl_xor_sync(0xffffffffu, send[j], 16);
         float yv[16];
         float* yp = p.y + r0 * p.ldy + o;
+        float yold[16];
+        if (p.accumulate) {   // all sixteen loads in flight at once (one after the other they cost a DRAM latency each)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) yold[j] = (j < nv) ? __ldcg(yp + j * p.ldy) : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) yold[j] = 0.f;
+        }
+        const int be0 = nv > 0 ? static_cast<int>(r0 / p.N) : 0;
+        float sc0 = __ldg(p.xunscale + be0) * wun;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float accv = hh ? (send[j] + keep[j]) : (keep[j] + send[j]);   // (Wh.Sh + Wh.Sl) + Wl.Sh / 2048
           const float fl = (inv[j] > 0.f || unmasked) ? bo : 0.f;
+          if (!aligned && j > 0 && j < nv) sc0 = __ldg(p.xunscale + (r0 + j) / p.N) * wun;
           float v = fmaf(inv[j] * sc0, accv, fl);
-          if (p.accumulate && j < nv) v += yp[j * p.ldy];
+          v += yold[j];
           if (p.apply_act && p.act == FGC_ACT_LRELU) v = lrelu_f(v, p.alpha);
           yv[j] = v;
         }
@@ -352,15 +364,17 @@ conv_hm_kernel(const HmParams p) {
             if (4 * a < nv) pp[a * p.ldp] = fmaxf(fmaxf(yv[4 * a], yv[4 * a + 1]), fmaxf(yv[4 * a + 2], yv[4 * a + 3]));
         }
         if (p.ymax != nullptr) {
+          // max|y| per batch element: reduced over the 16 lanes that share the element, one atomic per half warp and
+          // tile (max is order-independent: the atomics keep the result deterministic; thousands of same-address
+          // atomics per launch serialise in L2 -- measured +180 us per 140 k rows when every lane issued its own)
+          float m = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (j < nv) amax = fmaxf(amax, fabsf(yv[j]));
-        }
-      }
-      if (p.ymax != nullptr) {   // max is order-independent: the atomic keeps the result deterministic
+            if (j < nv) m = fmaxf(m, fabsf(yv[j]));
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
-        if (lane == 0) atomicMax(p.ymax, __float_as_uint(amax));
+          for (int s = 8; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+          if ((lane & 15) == 0 && nv > 0) atomicMax(p.ymax + be0, __float_as_uint(m));
+        }
       }
     }
   } else {
@@ -528,8 +542,10 @@ prep_wt_kernel(const float* __restrict__ W0, uint32_t* __restrict__ wt, float* _
 // img[r][u] = [fp16(x_r[64u..] * s) (64 halves) | fp16 residuals (64 halves)], s = 2^(126-E), E = exponent of max|x|;
 // channels beyond Cw read as zero.
 __global__ void __launch_bounds__(256)
-hm_absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__ out) {
+hm_absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__ out) {   // blockIdx.y: batch element
   float m = 0.f;
+  x += static_cast<int64_t>(blockIdx.y) * n4 * 4;
+  out += blockIdx.y;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(x) + i);
@@ -541,12 +557,8 @@ hm_absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__
 }
 
 __global__ void __launch_bounds__(256)
-hm_prep_img_kernel(const float* __restrict__ x, int ldx, int Cw, int nunits, int64_t rows,
+hm_prep_img_kernel(const float* __restrict__ x, int ldx, int Cw, int nunits, int64_t rows, int Nimg,
                    const unsigned* __restrict__ maxbits, uint4* __restrict__ img, float* __restrict__ xunscale) {
-  int E = static_cast<int>((__ldg(maxbits) >> 23) & 0xFF);
-  E = min(max(E, 16), 240);
-  const float sc = __int_as_float((253 - E) << 23);
-  if (blockIdx.x == 0 && threadIdx.x == 0) xunscale[0] = __int_as_float((E + 1) << 23);
   const int per_row = nunits * 8;   // one thread per 8 channels
   const int64_t total = rows * per_row;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -554,6 +566,10 @@ hm_prep_img_kernel(const float* __restrict__ x, int ldx, int Cw, int nunits, int
     const int64_t r = i / per_row;
     const int j = static_cast<int>(i % per_row), u = j >> 3, jj = j & 7;
     const int c0 = u * 64 + jj * 8;
+    const int be = static_cast<int>(r / Nimg);            // the scale is per batch element
+    const int E = min(max(static_cast<int>((__ldg(maxbits + be) >> 23) & 0xFF), 16), 240);
+    const float sc = __int_as_float((253 - E) << 23);
+    if (j == 0 && r == static_cast<int64_t>(be) * Nimg) xunscale[be] = __int_as_float((E + 1) << 23);
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (c0 < Cw) a = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c0));
     if (c0 + 4 < Cw) b = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c0 + 4));
@@ -567,24 +583,8 @@ hm_prep_img_kernel(const float* __restrict__ x, int ldx, int Cw, int nunits, int
   }
 }
 
-struct HmWs {
-  uint4* img;
-  unsigned* scal;     // [0] max|x| bits, [1] 2^ex un-scale
-  uint32_t* wt;
-  float* wunscale;
-};
 size_t hm_img_bytes(int64_t rows_img, int nunits) { return static_cast<size_t>(rows_img) * nunits * 256; }
 size_t hm_wt_bytes(int M, int nimg) { return static_cast<size_t>(nimg) * 128 * M * 32 * 4; }
-HmWs hm_views(void* ws_ptr, size_t ws_bytes, int64_t rows_img, int nunits, int M, int nimg, bool* ok) {
-  Workspace ws(ws_ptr, ws_bytes);
-  HmWs v;
-  v.img = reinterpret_cast<uint4*>(ws.take<char>(hm_img_bytes(rows_img, nunits)));
-  v.scal = ws.take<unsigned>(16);
-  v.wt = reinterpret_cast<uint32_t*>(ws.take<char>(hm_wt_bytes(M, nimg)));
-  v.wunscale = ws.take<float>(16);
-  *ok = ws.ok();
-  return v;
-}
 
 }  // namespace
 
@@ -593,48 +593,45 @@ bool conv_hm_supported(int Cin, int Cw, int Cout, int M, int K) {
          (Cout == 32 || Cout == 64 || Cout == 128);
 }
 
-size_t conv_hm_workspace(int64_t rows_img, int Cw, int Cout, int M) {
-  const int nunits = (Cw + 63) / 64, CB = Cout < 64 ? Cout : 64, nob = Cout / CB;
-  return ws_bytes(hm_img_bytes(rows_img + 1, nunits), 1) + ws_bytes(16, 4) + ws_bytes(hm_wt_bytes(M, nunits * nob), 1) +
-         ws_bytes(16, 4);
+size_t conv_hm_weights_bytes(int Cw, int Cout, int M);
+size_t conv_hm_workspace(int64_t rows_img, int Cw, int Cout, int M, int B) {
+  const int nunits = (Cw + 63) / 64;
+  return ws_bytes(hm_img_bytes(rows_img + 1, nunits), 1) + ws_bytes(2 * static_cast<size_t>(B) + 16, 4) +
+         ws_bytes(conv_hm_weights_bytes(Cw, Cout, M), 1);
 }
 
-// p.x: rows >> upshift rows of Cin floats (the first Cw are aggregated); p.uvx: their logits, with room for one more
-// row (zeroed here).
-// ypool (optional): [rows / 4][Cout] max over groups of 4 rows of y; ymax (optional): atomicMax target for max|y| bits;
-// xmax (optional): device word that already holds the bits of an upper bound of max|x| (else computed here).
-int launch_conv_hm(const ConvFwdParams& p, const float* W0, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                   int upshift, float* ypool, unsigned* ymax, const unsigned* xmax) {
-  const int nunits = (p.Cw + 63) / 64, CB = p.Cout < 64 ? p.Cout : 64, nob = p.Cout / CB;
-  const int64_t rows_img = p.rows >> upshift;
-  bool ok = false;
-  const HmWs v = hm_views(workspace, workspace_bytes, rows_img + 1, nunits, p.M, nunits * nob, &ok);
-  FGC_REQUIRE(ok, "conv_hm: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
-              conv_hm_workspace(rows_img, p.Cw, p.Cout, p.M));
-  FGC_REQUIRE(ypool == nullptr || (p.N % 4 == 0), "conv_hm: pooled output needs N %% 4 == 0");
-  const int blocks = num_sms() * 8;
-  if (xmax == nullptr) {
-    FGC_CUDA(cudaMemsetAsync(v.scal, 0, 16 * sizeof(unsigned), st));
-    hm_absmax_kernel<<<blocks, 256, 0, st>>>(p.x, rows_img * (p.Cin / 4), v.scal);
-    FGC_LAUNCHED("absmax_kernel");
-    xmax = v.scal;
-  }
-  hm_prep_img_kernel<<<blocks, 256, 0, st>>>(p.x, p.Cin, p.Cw, nunits, rows_img, xmax, v.img,
-                                             reinterpret_cast<float*>(v.scal + 1));
-  FGC_LAUNCHED("prep_x_image_kernel");
-  // row `rows_img` of the image and of the logits is all zero: what padding and out-of-range slots read
-  FGC_CUDA(cudaMemsetAsync(v.img + rows_img * nunits * 16, 0, static_cast<size_t>(nunits) * 256, st));
-  FGC_CUDA(cudaMemsetAsync(const_cast<float*>(p.uvx) + rows_img * 2 * p.M, 0, static_cast<size_t>(2 * p.M) * 4, st));
-  prep_wt_kernel<<<dim3(4, nunits * nob), 1024, 0, st>>>(W0, v.wt, v.wunscale, p.M, p.Cout, p.Cw, CB, nunits);
+size_t conv_hm_weights_bytes(int Cw, int Cout, int M) {
+  const int nunits = (Cw + 63) / 64, CB = Cout < 64 ? Cout : 64, nob = Cout / CB;
+  return align_up(hm_wt_bytes(M, nunits * nob), 256) + 256;
+}
+
+// Weight images of one layer (all output blocks x aggregation units) + the un-scale word behind them:
+// constant across calls, so inference prepares them once (fgc_net_prepare).
+int launch_conv_hm_weights(const float* W0, int M, int Cout, int Cw, void* wbuf, cudaStream_t st) {
+  const int nunits = (Cw + 63) / 64, CB = Cout < 64 ? Cout : 64, nob = Cout / CB;
+  float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wbuf) + align_up(hm_wt_bytes(M, nunits * nob), 256));
+  prep_wt_kernel<<<dim3(4, nunits * nob), 1024, 0, st>>>(W0, static_cast<uint32_t*>(wbuf), wunscale, M, Cout, Cw, CB, nunits);
   FGC_LAUNCHED("prep_w_image_kernel");
+  return FGC_OK;
+}
+
+// The convolution proper on prepared operands: img[rows_img + 1][nunits][16] / uvx[rows_img + 1][2M] (last row zero),
+// xunscale[B] = 2^ex of the image rows of every batch element, wbuf from launch_conv_hm_weights; ymax: [B] or null.
+int launch_conv_hm_core(const void* img, const float* xunscale, const float* uvx, const int32_t* adj, const void* wbuf,
+                        const float* b, float* y, float* ypool, unsigned* ymax, int64_t rows, int N, int K, int M, int Cw,
+                        int Cout, int upshift, int bias_mask, int act, float alpha, cudaStream_t st) {
+  const int nunits = (Cw + 63) / 64, CB = Cout < 64 ? Cout : 64, nob = Cout / CB;
+  const int64_t rows_img = rows >> upshift;
+  FGC_REQUIRE(ypool == nullptr || (N % 4 == 0), "conv_hm: pooled output needs N %% 4 == 0");
   HmParams hp{};
-  hp.img_ld = nunits * 16, hp.xunscale = reinterpret_cast<const float*>(v.scal + 1), hp.uvx = p.uvx, hp.adj = p.adj;
-  hp.wunscale = v.wunscale, hp.ldy = p.Cout, hp.ldp = p.Cout, hp.rows = p.rows, hp.ntiles = (p.rows + kHT - 1) / kHT;
-  hp.N = p.N, hp.K = p.K, hp.upshift = upshift, hp.bias_mask = p.bias_mask, hp.act = p.act, hp.alpha = p.alpha;
-  hp.cout = CB, hp.single = p.rows == p.N, hp.zrow = static_cast<int>(rows_img);
-  auto kern = p.M == 9 ? (p.K <= 16 ? conv_hm_kernel<9, 1> : conv_hm_kernel<9, 2>)
-                       : (p.K <= 16 ? conv_hm_kernel<8, 1> : conv_hm_kernel<8, 2>);
-  const int smem = p.M == 9 ? HmCfg<9>::SMEM_BYTES : HmCfg<8>::SMEM_BYTES;
+  hp.img_ld = nunits * 16, hp.xunscale = xunscale, hp.uvx = uvx, hp.adj = adj;
+  hp.wunscale = reinterpret_cast<const float*>(static_cast<const char*>(wbuf) + align_up(hm_wt_bytes(M, nunits * nob), 256));
+  hp.ldy = Cout, hp.ldp = Cout, hp.rows = rows, hp.ntiles = (rows + kHT - 1) / kHT;
+  hp.N = N, hp.K = K, hp.upshift = upshift, hp.bias_mask = bias_mask, hp.act = act, hp.alpha = alpha;
+  hp.cout = CB, hp.single = rows == N, hp.zrow = static_cast<int>(rows_img);
+  auto kern = M == 9 ? (K <= 16 ? conv_hm_kernel<9, 1> : conv_hm_kernel<9, 2>)
+                     : (K <= 16 ? conv_hm_kernel<8, 1> : conv_hm_kernel<8, 2>);
+  const int smem = M == 9 ? HmCfg<9>::SMEM_BYTES : HmCfg<8>::SMEM_BYTES;
   FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int64_t grid = num_sms();
   if (grid > hp.ntiles) grid = hp.ntiles;
@@ -642,15 +639,59 @@ int launch_conv_hm(const ConvFwdParams& p, const float* W0, void* workspace, siz
   for (int ob = 0; ob < nob; ++ob)
     for (int u = 0; u < nunits; ++u) {
       const bool last = u == nunits - 1;
-      hp.img = v.img + u * 16;
-      hp.wt = v.wt + static_cast<size_t>(ob * nunits + u) * 128 * p.M * 32;
-      hp.b = p.b + ob * CB, hp.y = p.y + ob * CB;
+      hp.img = static_cast<const uint4*>(img) + u * 16;
+      hp.wt = static_cast<const uint32_t*>(wbuf) + static_cast<size_t>(ob * nunits + u) * 128 * M * 32;
+      hp.b = b + ob * CB, hp.y = y + ob * CB;
       hp.ypool = (last && ypool != nullptr) ? ypool + ob * CB : nullptr;
       hp.ymax = last ? ymax : nullptr;
       hp.add_bias = u == 0, hp.accumulate = u > 0, hp.apply_act = last;
       kern<<<static_cast<unsigned>(grid), kHThreads, smem, st>>>(hp);
       FGC_LAUNCHED("conv_hm_kernel");
     }
+  return FGC_OK;
+}
+
+// Generic entry (any caller of conv_fwd): p.x: rows >> upshift rows of Cin floats (the first Cw are aggregated);
+// p.uvx: their logits, with room for one more row (zeroed here).
+// ypool (optional): [rows / 4][Cout] max over groups of 4 rows of y; ymax (optional): atomicMax target for max|y| bits;
+// xmax (optional): device word that already holds the bits of an upper bound of max|x| (else computed here).
+int launch_conv_hm(const ConvFwdParams& p, const float* W0, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                   int upshift, float* ypool, unsigned* ymax, const unsigned* xmax) {
+  const int nunits = (p.Cw + 63) / 64;
+  const int64_t rows_img = p.rows >> upshift;
+  Workspace ws(workspace, workspace_bytes);
+  const int B = static_cast<int>(p.rows / p.N), Nimg = p.N >> upshift;
+  uint4* img = reinterpret_cast<uint4*>(ws.take<char>(hm_img_bytes(rows_img + 1, nunits)));
+  unsigned* scal = ws.take<unsigned>(2 * static_cast<size_t>(B) + 16);   // [B] max|x| bits, then [B] 2^ex un-scales
+  float* xunscale = reinterpret_cast<float*>(scal + B);
+  char* wbuf = ws.take<char>(conv_hm_weights_bytes(p.Cw, p.Cout, p.M));
+  FGC_REQUIRE(ws.ok(), "conv_hm: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              conv_hm_workspace(rows_img, p.Cw, p.Cout, p.M, B));
+  const int blocks = num_sms() * 8;
+  if (xmax == nullptr) {
+    FGC_CUDA(cudaMemsetAsync(scal, 0, static_cast<size_t>(B) * sizeof(unsigned), st));
+    int rca = launch_absmax_bits(p.x, static_cast<int64_t>(Nimg) * (p.Cin / 4), B, scal, st);
+    if (rca) return rca;
+    xmax = scal;
+  }
+  hm_prep_img_kernel<<<blocks, 256, 0, st>>>(p.x, p.Cin, p.Cw, nunits, rows_img, Nimg, xmax, img, xunscale);
+  FGC_LAUNCHED("prep_x_image_kernel");
+  // row `rows_img` of the image and of the logits is all zero: what padding and out-of-range slots read
+  FGC_CUDA(cudaMemsetAsync(img + rows_img * nunits * 16, 0, static_cast<size_t>(nunits) * 256, st));
+  FGC_CUDA(cudaMemsetAsync(const_cast<float*>(p.uvx) + rows_img * 2 * p.M, 0, static_cast<size_t>(2 * p.M) * 4, st));
+  int rc = launch_conv_hm_weights(W0, p.M, p.Cout, p.Cw, wbuf, st);
+  if (rc) return rc;
+  return launch_conv_hm_core(img, xunscale, p.uvx, p.adj, wbuf, p.b, p.y, ypool, ymax, p.rows,
+                             p.N, p.K, p.M, p.Cw, p.Cout, upshift, p.bias_mask, p.act, p.alpha, st);
+}
+
+// max|x| of every batch element (n4_per_elem float4 each) -> atomicMax on out[b] (bits); out must have been zeroed
+int launch_absmax_bits(const float* x, int64_t n4_per_elem, int B, unsigned* out, cudaStream_t st) {
+  int bx = (num_sms() * 8 + B - 1) / B;
+  if (static_cast<int64_t>(bx) * 256 > n4_per_elem) bx = static_cast<int>((n4_per_elem + 255) / 256);
+  if (bx < 1) bx = 1;
+  hm_absmax_kernel<<<dim3(bx, B), 256, 0, st>>>(x, n4_per_elem, out);
+  FGC_LAUNCHED("absmax_kernel");
   return FGC_OK;
 }
 

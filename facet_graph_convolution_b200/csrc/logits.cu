@@ -6,6 +6,8 @@
 // 16-byte load per lane), the [u;v] coefficients of the lane's channels live in registers, and the
 // per-row reduction over channels is a transpose-reduce over the LPR lanes.  The generic
 // thread-per-row kernels in conv_fwd.cu / conv_bwd.cu remain for every other shape.
+#include <cuda_fp16.h>
+
 #include "conv_common.cuh"
 #include "conv_launch.cuh"
 
@@ -242,6 +244,123 @@ logits_bwd_p_warp_kernel(const LgParams p) {
   }
 }
 
+// ------------------------------------------------------------------ fused pre-pass of the HMMA-aggregation forward
+// One pass over the rows of a layer input (optionally the channel concatenation [xa | xb] of two tensors, reference
+// Code/model.py:909,929, never materialised): assignment logits uvx[r] = [u;v] . x_r + [c;0] and the fp16 hi|lo image
+// img[r][unit] = [fp16(x s) (64) | fp16(x s - hi) (64)] with s = 2^(126-E), E = exponent of max(max|xa|, max|xb|)
+// per batch element (upper bounds the producing kernels leave behind; per element, so that a batch of patches gives
+// every patch exactly the result of running it alone).  Row `rows` of both outputs is zeroed (what padding slots read).
+struct PrepRowsParams {
+  const float* xa;
+  const float* xb;
+  const float* u;
+  const float* v;
+  const float* c;
+  const unsigned* maxa;
+  const unsigned* maxb;
+  uint4* img;
+  float* uvx;
+  float* xunscale;
+  int64_t rows;
+  int lda, Ca, ldb, Cb, M, nunits;
+  int Nimg;   // rows per batch element: maxa / maxb / xunscale are per element
+};
+
+template <int OP, int LPR>
+__global__ void __launch_bounds__(256, (OP <= 16) ? 2 : 1)
+prep_rows_warp_kernel(const PrepRowsParams p) {
+  constexpr int RPW = 32 / LPR, OPL = OP / LPR;
+  const int lane = threadIdx.x & 31, gl = lane % LPR, sub = lane / LPR;
+  const int O = 2 * p.M, Cin = p.Ca + p.Cb;
+  const int c4 = 4 * gl;
+  const bool act = c4 < Cin;                 // lane holds real channels
+  const bool inimg = c4 < p.nunits * 64;     // lane holds image channels (zeros beyond Cin)
+  float w[OP][4];
+#pragma unroll
+  for (int o = 0; o < OP; ++o)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = 0.f;
+      if (o < O && c4 + j < Cin) t = (o < p.M) ? __ldg(p.u + o * Cin + c4 + j) : __ldg(p.v + (o - p.M) * Cin + c4 + j);
+      w[o][j] = t;
+    }
+  float cb[OPL];
+#pragma unroll
+  for (int i = 0; i < OPL; ++i) {
+    const int o = gl * OPL + i;
+    cb[i] = (o < p.M) ? __ldg(p.c + o) : 0.f;
+  }
+  auto scale_exp = [&](int be) {   // exponent of the element's max |x| (clamped so that both scales stay normal)
+    unsigned mb = __ldg(p.maxa + be);
+    if (p.maxb != nullptr) mb = max(mb, __ldg(p.maxb + be));
+    return min(max(static_cast<int>((mb >> 23) & 0xFF), 16), 240);
+  };
+  {
+    const int nelem = static_cast<int>(p.rows / p.Nimg);
+    for (int be = blockIdx.x * blockDim.x + threadIdx.x; be < nelem; be += gridDim.x * blockDim.x)
+      p.xunscale[be] = __int_as_float((scale_exp(be) + 1) << 23);
+  }
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < p.nunits * 16) p.img[p.rows * p.nunits * 16 + threadIdx.x] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < O) p.uvx[p.rows * O + threadIdx.x] = 0.f;
+  }
+  const bool from_a = c4 < p.Ca;
+  const float* src = from_a ? p.xa + c4 : p.xb + (c4 - p.Ca);
+  const int ld = from_a ? p.lda : p.ldb;
+  uint8_t* const imgb = reinterpret_cast<uint8_t*>(p.img) + (c4 >> 6) * 256 + (c4 & 63) * 2;
+  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  constexpr int U = 4;   // row groups per iteration: all loads are in flight before the first is consumed
+  for (int64_t r0 = wid * RPW; r0 < p.rows; r0 += U * nw * RPW) {
+    int64_t rr[U];
+    float4 xs[U];
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      rr[t] = r0 + t * nw * RPW + sub;
+      xs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rr[t] < p.rows && act) xs[t] = __ldg(reinterpret_cast<const float4*>(src + rr[t] * ld));
+    }
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const float4 xv = xs[t];
+      const int64_t r = rr[t];
+      if (r < p.rows && inimg) {
+        const float sc = __int_as_float((253 - scale_exp(static_cast<int>(r / p.Nimg))) << 23);
+        const __half2 h0 = __floats2half2_rn(xv.x * sc, xv.y * sc), h1 = __floats2half2_rn(xv.z * sc, xv.w * sc);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(xv.x * sc - f0.x, xv.y * sc - f0.y);
+        const __half2 l1 = __floats2half2_rn(xv.z * sc - f1.x, xv.w * sc - f1.y);
+        uint8_t* d = imgb + r * (p.nunits * 256);
+        *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(d + 128) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
+      float a[OP];
+#pragma unroll
+      for (int o = 0; o < OP; ++o) a[o] = fmaf(xv.x, w[o][0], fmaf(xv.y, w[o][1], fmaf(xv.z, w[o][2], xv.w * w[o][3])));
+      transpose_reduce<OP, LPR>(a, gl);
+      if (r < p.rows) {
+#pragma unroll
+        for (int i = 0; i < OPL; ++i) {
+          const int o = gl * OPL + i;
+          if (o < O) p.uvx[r * O + o] = a[i] + cb[i];
+        }
+      }
+    }
+  }
+}
+
+template <int OP, int LPR>
+int run_prep_rows(const PrepRowsParams& p, cudaStream_t st) {
+  const int64_t rows_per_block = 8 * (32 / LPR);
+  int64_t blocks = (p.rows + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  prep_rows_warp_kernel<OP, LPR><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
+  FGC_LAUNCHED("prep_rows_kernel");
+  return FGC_OK;
+}
+
 template <int OP, int LPR>
 int run_assign(const LgParams& p, cudaStream_t st) {
   const int64_t rows_per_block = 8 * (32 / LPR);
@@ -285,6 +404,22 @@ int fast_lpr(int Cin, int Ca0, int Ca, int M) {
 }
 
 }  // namespace
+
+// rows of [xa (Ca channels, row stride lda) | xb (Cb, ldb; may be null)] -> uvx[rows + 1][2M], img[rows + 1][nunits][16]
+int launch_prep_rows(const float* xa, int lda, int Ca, const float* xb, int ldb, int Cb, const float* u, const float* v,
+                     const float* c, int M, int64_t rows, int Nimg, const unsigned* maxa, const unsigned* maxb, void* img,
+                     float* uvx, float* xunscale, cudaStream_t st) {
+  const int Cin = Ca + Cb, nunits = (Cin + 63) / 64;
+  FGC_REQUIRE(Ca % 4 == 0 && Cb % 4 == 0 && Cin <= 128 && 2 * M <= 32 && lda % 4 == 0 && (xb == nullptr || ldb % 4 == 0),
+              "prep_rows: unsupported shape (Ca=%d Cb=%d M=%d)", Ca, Cb, M);
+  FGC_REQUIRE(Nimg > 0 && rows % Nimg == 0, "prep_rows: rows must be a multiple of the rows per batch element");
+  PrepRowsParams p{xa, xb, u, v, c, maxa, maxb, static_cast<uint4*>(img), uvx, xunscale, rows, lda, Ca, ldb, Cb, M, nunits, Nimg};
+  if (Cin <= 64) {
+    if (2 * M <= 16) return run_prep_rows<16, 16>(p, st);
+    return run_prep_rows<32, 16>(p, st);
+  }
+  return run_prep_rows<32, 32>(p, st);
+}
 
 #define FGC_LG_DISPATCH(FN, ...)                                              \
   do {                                                                        \

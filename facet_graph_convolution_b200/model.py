@@ -234,6 +234,39 @@ def _up_conv(h, adj, out_channels, M, steps, fused_ok):
     return custom_conv2d(custom_upsampling(h, steps=steps), adj, out_channels, M)[0]
 
 
+def _net_variables(in_channels, multiScale=False):
+    """The network's variables in the reference's creation order (model.py:853-941), created (or fetched from the
+    active store) without running any layer."""
+    M = 9
+    out = []
+
+    def conv(cin, cout):
+        out.extend([weight_variable([M, cout, cin]), bias_variable([cout]), assignment_variable([M, cin]),
+                    assignment_variable([M]), assignment_variable([M, cin])])
+
+    def head(cin):
+        out.extend([weight_variable([cin, 1024]), bias_variable([1024]), weight_variable([1024, 3]), bias_variable([3])])
+
+    conv(in_channels, 32), conv(32, 64), conv(64, 128), conv(128, 128)
+    if multiScale:
+        head(128)
+    conv(128, 64), conv(128, 64)
+    if multiScale:
+        head(64)
+    conv(64, 32), conv(64, 32)
+    head(32)
+    return out
+
+
+def _fused_forward_ok(x, adjs, multiScale):
+    if multiScale or not x.is_cuda or x.dim() != 3 or x.shape[2] != 6 or len(adjs) != 3:
+        return False
+    B, N0, _ = x.shape
+    K = adjs[0].shape[2]
+    return (N0 % 16 == 0 and N0 >= 16 and K <= 32 and tuple(adjs[1].shape) == (B, N0 // 4, K)
+            and tuple(adjs[2].shape) == (B, N0 // 16, K) and B * N0 >= 64)
+
+
 def get_model_reg_multi_scale(x, adjs, keep_prob=1.0, coarsening_steps=2, multiScale=False, fuse=True):
     """Drop-in for reference Code/model.py:837-946: the 3-level U-Net of facet-graph convolutions.
 
@@ -248,6 +281,16 @@ def get_model_reg_multi_scale(x, adjs, keep_prob=1.0, coarsening_steps=2, multiS
     M = 9
     infer = fuse and not torch.is_grad_enabled()
     A = ops.ACT_LRELU
+    if infer and _fused_forward_ok(x, adjs, multiScale):
+        # the whole forward as one C-ABI call (fgc_net_fwd): pooling / up-sampling / concatenation fused into the
+        # convolutions, weight images prepared once per set of parameters and kept on the variable store
+        store = _store_for(x)
+        params = _net_variables(6)
+        prep = getattr(store, "_net_prepared", None)
+        if prep is None or not prep.matches(params):
+            prep = ops.NetPrepared(params)
+            store._net_prepared = prep
+        return ops.net_forward(x, adjs, prep)
 
     def conv_act(h, adj, cout):
         if infer:

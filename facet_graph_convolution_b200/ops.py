@@ -510,6 +510,49 @@ def vertex_update_ms(x, normals, faces, v_faces, scale, steps=2, iters=20):
     return out
 
 
+# ----------------------------------------------------------------------------- whole-network inference forward
+class NetPrepared:
+    """Caller-owned tensor-core weight images of the reference network (fgc_net_prepare): depend only on the 44
+    parameter tensors, so inference builds them once per checkpoint and reuses them for every patch batch."""
+
+    def __init__(self, params):
+        L = _lib.lib()
+        if len(params) != int(L.fgc_net_param_count()):
+            raise _lib.FacetConvError("NetPrepared: %d parameter tensors expected in creation order, got %d"
+                                      % (int(L.fgc_net_param_count()), len(params)))
+        self.params = [_f32(t, "param") for t in params]
+        self.key = tuple((t.data_ptr(), t._version) for t in params)
+        dev = self.params[0].device
+        self.ptrs = (C.c_void_p * len(self.params))(*[t.data_ptr() for t in self.params])
+        self.buf = torch.empty(int(L.fgc_net_prepared_bytes()), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(L.fgc_net_prepare(self.ptrs, len(self.params), _p(self.buf), self.buf.numel(), _stream(self.buf)),
+                  "fgc_net_prepare")
+
+    def matches(self, params) -> bool:
+        return self.key == tuple((t.data_ptr(), t._version) for t in params)
+
+
+def net_forward(x, adjs, prepared: NetPrepared, workspace: Optional[torch.Tensor] = None):
+    """get_model_reg_multi_scale(x, adjs, multiScale=False) (reference Code/model.py:837-946) as one C-ABI call:
+    x[B,N0,6], adjs = [adj0[B,N0,K], adj1[B,N0/4,K], adj2[B,N0/16,K]] -> y[B,N0,3] (before normalizeTensor)."""
+    L = _lib.lib()
+    x = _f32(x, "x")
+    a0, a1, a2 = (_i32(a, "adj") for a in adjs)
+    B, N0, Cin = x.shape
+    K = a0.shape[2]
+    if Cin != 6 or tuple(a0.shape) != (B, N0, K) or tuple(a1.shape) != (B, N0 // 4, K) or tuple(a2.shape) != (B, N0 // 16, K):
+        raise _lib.FacetConvError("net_forward: x[B,N0,6], adj0[B,N0,K], adj1[B,N0/4,K], adj2[B,N0/16,K] expected, got %s %s %s %s"
+                                  % (tuple(x.shape), tuple(a0.shape), tuple(a1.shape), tuple(a2.shape)))
+    y = torch.empty((B, N0, 3), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        nws = int(L.fgc_net_fwd_workspace(B, N0, K))
+        ws = workspace if (workspace is not None and workspace.numel() >= nws) else _ws(nws, x)
+        check(L.fgc_net_fwd(B, N0, K, _p(x), _p(a0), _p(a1), _p(a2), prepared.ptrs, len(prepared.params), _p(prepared.buf),
+                            _p(y), _p(ws), ws.numel(), _stream(x)), "fgc_net_fwd")
+    return y
+
+
 def launch_count() -> int:
     return int(_lib.lib().fgc_launch_count())
 

@@ -218,6 +218,24 @@ FGC_API int fgc_mlp_head_fwd(const float* x, const float* W1, const float* b1, c
                      const float* b2, float* y, int64_t rows, int Cin, int H, int Cout, float alpha,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- the network's inference forward
+ * reference Code/model.py:837-946, get_model_reg_multi_scale(x, adjs, keep_prob, multiScale=False): the
+ * 3-level U-Net as one call.  x[B,N0,6], adj0[B,N0,K], adj1[B,N0/4,K], adj2[B,N0/16,K] (reference layout:
+ * 1-indexed, 0 = padding, ids local to the batch element), N0 a multiple of 16; params = the
+ * fgc_net_param_count() = 44 parameter tensors in the reference's variable-creation order
+ * (W0[9,Cout,Cin], b, u, c, v for conv1 conv2 conv3 dconv3 upconv2 dconv2 upconv1 dconv1, then W[32,1024], b,
+ * W[1024,3], b of the head: model.py:853-941); y[B,N0,3] = the network output BEFORE normalizeTensor.
+ * fgc_net_prepare builds the tensor-core weight images once per set of parameters into a caller-owned
+ * buffer of fgc_net_prepared_bytes() bytes.  Pooling, up-sampling and concatenation are fused into the
+ * convolutions; batch elements are independent patches. */
+FGC_API int fgc_net_param_count(void);
+FGC_API size_t fgc_net_prepared_bytes(void);
+FGC_API int fgc_net_prepare(const float* const* params, int nparams, void* prepared, size_t prepared_bytes, void* stream);
+FGC_API size_t fgc_net_fwd_workspace(int B, int N0, int K);
+FGC_API int fgc_net_fwd(int B, int N0, int K, const float* x, const int32_t* adj0, const int32_t* adj1, const int32_t* adj2,
+                const float* const* params, int nparams, const void* prepared, float* y, void* workspace,
+                size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- output normalisation & loss
  * reference Code/utils.py:1700-1715 (normalizeTensor) over x[rows,3] of ONE patch: global
  * mean-abs rescale, then row L2 normalisation with the three 1e-5 epsilons. */

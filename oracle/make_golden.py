@@ -253,6 +253,75 @@ def net_and_vertex_cases(ref):
     print("wrote net_ms_icosphere2", x.shape, faces_p.shape, v_faces.shape, vpos.shape)
 
 
+def _pack_adj(a):
+    a = np.asarray(a)
+    return a.astype(np.uint16) if a.max() < 65536 else a.astype(np.int32)
+
+
+def c1_cases(ref):
+    """BASELINE config C1 exactly as SURVEY section 8(d) defines it: icosphere-5 (20 480 faces, 10 242 vertices), noise
+    sigma = 0.3 x mean edge length (RandomState(0)), K = 16, reference preprocessing with np.random.seed(0), weights
+    RandomState(1234) in creation order; once as a single patch (MAX_PATCH_SIZE 25 000) and once with the default
+    20 000 (two patches: the overlap-sum + float64 two-pass normalise of Code/train.py:117-136), each followed by the
+    60 sweeps of update_position2.  Inputs are stored (adjacency as uint16) so the GPU test needs no host pyramid."""
+    V, F = mesh.icosphere(5)
+    Vn = mesh.add_vertex_noise(V, F, 0.3, 0)
+    K = 16
+    for tag, max_patch in (("c1_icosphere5_1patch", 25000), ("c1_icosphere5_2patch", 20000)):
+        im = preprocess(ref, Vn, F, K, seed=0, max_patch=max_patch)
+        npatch = len(im.in_list)
+        d = dict(V=Vn.astype(np.float32), F=F.astype(np.int32), npatch=np.int32(npatch), K=np.int32(K))
+        num_faces = 0
+        if npatch > 1:
+            for pi in range(npatch):
+                num_faces = max(num_faces, int(np.max(im.patch_indices[pi])) + 1)
+        predicted = np.zeros([num_faces, 3]) if npatch > 1 else None
+        vs = None
+        for pi in range(npatch):
+            x = im.in_list[pi].astype(np.float32)
+            adjs = [a.astype(np.int32) for a in im.adj_list[pi]]
+            perm = np.asarray(im.permutations[pi]).astype(np.int32)
+            nreal = int(im.num_faces[pi])
+            y, vs = rr.run(ref.model.get_model_reg_multi_scale, T(x), [T(a) for a in adjs], 1.0,
+                           provider=rr.rng_provider(1234))
+            yn = ref.utils.normalizeTensor(y)
+            outN = rr.to_np(yn)[0][perm][:nreal]          # train.py:117-121
+            if npatch == 1:
+                predicted = outN
+            else:
+                pidx = np.asarray(im.patch_indices[pi])
+                predicted[pidx] = predicted[pidx] + outN    # train.py:126
+                d["pidx%d" % pi] = pidx.astype(np.int32)
+            d["x%d" % pi] = x
+            for l in range(3):
+                d["adj%d_%d" % (pi, l)] = _pack_adj(adjs[l])
+            d["perm%d" % pi] = perm
+            d["nreal%d" % pi] = np.int32(nreal)
+            d["y_norm%d" % pi] = rr.to_np(yn)[0].astype(np.float32)
+            print(tag, "patch", pi, x.shape, [a.shape for a in adjs], "real", nreal)
+        pred = ref.utils.normalize(predicted)               # train.py:136 (float64 two-pass normalise)
+        e_map = im.edge_map.astype(np.int32)
+        v_e_map = im.v_e_map.astype(np.int32)
+        verts = Vn[None].astype(np.float32)
+        xo = ref.train.update_position2(T(verts), T(pred[None].astype(np.float32)), T(e_map), T(v_e_map),
+                                        iter_num=60, max_edges=20)
+        # the 474 199 weights are not stored: RandomState(1234).normal(0, std, shape) in creation order reproduces
+        # them (shapes / std-devs / a checksum are)
+        shp = np.zeros((len(vs), 3), np.int32)
+        for i, v in enumerate(vs):
+            shp[i, :v.ndim] = v.shape
+        std = np.array([0.01 if (v.ndim == 1 and i % 5 == 1 and i < 40) or (i >= 40 and v.ndim == 1) else 0.05
+                        for i, v in enumerate(vs)], np.float64)
+        chk = np.random.RandomState(1234)
+        for i, v in enumerate(vs):
+            assert np.array_equal(chk.normal(0.0, std[i], size=v.shape).astype(np.float32), v), i
+        d.update(pred_normals=pred.astype(np.float64), verts_out=rr.to_np(xo)[0].astype(np.float32),
+                 nparams=np.int32(len(vs)), pshape=shp, pstd=std,
+                 psum=np.float64(sum(float(np.asarray(v, np.float64).sum()) for v in vs)))
+        np.savez_compressed(os.path.join(OUT, tag + ".npz"), **d)
+        print("wrote", tag, os.path.getsize(os.path.join(OUT, tag + ".npz")) // 1024, "KiB")
+
+
 def index_cases(ref):
     """Index layouts of the reference's host builders on small meshes (bit-exact targets)."""
     d = {}
@@ -435,6 +504,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rr.load()
     torch.manual_seed(0)
+    if len(sys.argv) > 1:          # python -m oracle.make_golden c1_cases [...]: only the named generators
+        for nm in sys.argv[1:]:
+            globals()[nm](ref)
+        return
     conv_case(ref, "conv_6_32_M9_K23_B2", 2, 300, 6, 32, 9, 23, seed=1)
     conv_case(ref, "conv_64_32_M9_K23", 1, 200, 64, 32, 9, 23, seed=2)
     conv_case(ref, "conv_64_64_M8_K16_B2", 2, 256, 64, 64, 8, 16, seed=3)
@@ -449,6 +522,7 @@ def main():
     coarsen_cases(ref)
     patch_cases(ref)
     patch_vertex_cases(ref)
+    c1_cases(ref)
 
 
 if __name__ == "__main__":

@@ -127,3 +127,16 @@ def test_ref_order_port(name):
     for got, key in zip(out, ("y", "gx", "gW0", "gb", "gu", "gv", "gc")):
         ref = g[key]
         assert np.abs(got.numpy() - ref).max() / max(1.0, np.abs(ref).max()) < 1e-5, key
+
+
+def test_closed_form_network_matches_reference_on_c1_patch():
+    """The oracle's network port against the reference run on the second patch of the two-patch C1 case
+    (2 480 nodes of the noisy icosphere-5; the full-size patches are compared on the GPU)."""
+    g = golden("c1_icosphere5_2patch")
+    rs = np.random.RandomState(1234)
+    params = [rs.normal(0.0, float(std), size=tuple(int(v) for v in shp if v > 0)).astype(np.float32)
+              for shp, std in zip(g["pshape"], g["pstd"])]
+    adjs = [g["adj1_%d" % l].astype(np.int32) for l in range(3)]
+    y = cf.net_forward(g["x1"], adjs, cf.split_net_params(params))
+    yn = cf.normalize_tensor(y)
+    assert np.abs(yn[0] - g["y_norm1"]).max() < 2e-5
