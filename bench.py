@@ -1,15 +1,17 @@
 #!/usr/bin/env python
-"""Headline benchmark: facets/s through one facet-graph convolution layer, forward + backward
-(BASELINE.json configs[1], "C2": N = 1 000 000 facets, K = 16, M = 8, Cin = Cout = 64, fp32).
+"""Headline benchmark: facets/s of denoise inference -- BASELINE.json `metric`, quoted on configs[2] ("C3"): the full
+multi-scale denoising network (reference Code/model.py:837-946 driven as Code/train.py:100-126 drives it, patch by
+patch) on a synthetic 2 000 000-facet mesh cut into 100 halo patches, patches dealt to the ranks, NO collective.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--adjacency mesh|dedup|random] [--facets N]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c3|c2]
 
-One "step" = one forward + one backward pass of the layer over one batch of synthetic input
-(mesh-like adjacency of a 1000x500-quad torus in the reference's getFacesLargeAdj layout).
-Under torchrun every rank runs the same-sized shard (weak scaling); the only exchange is the
-data-parallel all-reduce of the layer's parameter gradients (NCCL), as in training.
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte model.
+One "step" = one pass of the network forward + normalizeTensor over ALL patches of the mesh (every rank runs its
+share; strong scaling); `value` = real (core) facets x steps / max-over-ranks CUDA-event time with the patch tensors
+resident in HBM; `e2e` = the same pass from pinned HOST patch tensors to pinned host normals (copies inside the timed
+region).  `layers` / `roofline` give every layer's algorithmic GB/s (SURVEY section 8(d) byte model) against the
+measured HBM peak.  `--config c2` (also summarised under `layer` of the default line) is BASELINE configs[1]: one
+facet-graph convolution layer, N = 1 M facets, K = 16, M = 8, Cin = Cout = 64, forward + backward, weak scaling with
+one NCCL all-reduce of the parameter gradients.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
@@ -137,7 +139,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def result(self):
         self.stop_flag = True
@@ -182,20 +184,10 @@ def cpu_net_reference(x, adjs, params, repeat=1):
     return (time.perf_counter() - t0) / repeat
 
 
-# ----------------------------------------------------------------------------- main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--adjacency", default="mesh", choices=["mesh", "dedup", "random"])
-    ap.add_argument("--facets", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample", type=int, default=20_000)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-
+# ----------------------------------------------------------------------------- C2: one layer, forward + backward
+def run_c2(args, as_record=False):
+    """BASELINE configs[1].  Returns the JSON line as a dict (rank 0; None elsewhere).  as_record: the short run whose
+    summary the default (C3) line carries under `layer` -- no e2e, no CPU leg, no process group of its own."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -208,7 +200,7 @@ def main():
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
-            return
+            return None
         steps = max(1, min(args.steps, 5))
         warm = max(1, min(args.warmup, 1))
         val, ms, n, cores = cpu_reference_run(steps, warm, args.cpu_sample, args.adjacency)
@@ -221,8 +213,7 @@ def main():
                                            "1M facets would need >100 GB); TensorFlow unavailable" % n},
                 "e2e": {"value": val, "unit": "facets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
-        return
+        return line
 
     # ------------------------------------------------------------------ B200 arm
     import torch
@@ -230,9 +221,12 @@ def main():
     _lib.require_device()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if as_record:
+        world = 1
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
     n = args.facets
@@ -392,15 +386,337 @@ def main():
                         "sample": "oracle/ref_order.py (reference evaluation order on torch-CPU, autograd backward), "
                                   "3 fwd+bwd steps on %d facets, %.0f ms/step" % (ns, ms)}
 
-    if rank == 0:
+    line = None
+    if rank == 0 or as_record:
         line = {"metric": "facets/sec", "value": value, "unit": "facets/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "kernels": kernels, "layer": layer}
-        print(json.dumps(line))
+    return line
+
+
+# ----------------------------------------------------------------------------- C3: the network on a patched mesh
+NET_K, NET_M = 16, 9
+# (name, Cin, Cout, level of the rows, pooled second output) in execution order -- Code/model.py:853-932
+NET_LAYERS = [("conv1", 6, 32, 0, True), ("conv2", 32, 64, 1, True), ("conv3", 64, 128, 2, False),
+              ("dconv3", 128, 128, 2, False), ("upconv2", 128, 64, 1, False), ("dconv2", 128, 64, 1, False),
+              ("upconv1", 64, 32, 0, False), ("dconv1", 64, 32, 0, False)]
+
+
+def net_params(seed=1234):
+    """Random-init parameters in the reference's creation order (Code/model.py:31-44 std-devs)."""
+    rs = np.random.RandomState(seed)
+    shapes = []
+    for _, ci, co, _, _ in NET_LAYERS:
+        shapes += [((NET_M, co, ci), 0.05), ((co,), 0.01), ((NET_M, ci), 0.05), ((NET_M,), 0.05), ((NET_M, ci), 0.05)]
+    shapes += [((32, 1024), 0.05), ((1024,), 0.01), ((1024, 3), 0.05), ((3,), 0.01)]
+    return [rs.normal(0, sd, sh).astype(np.float32) for sh, sd in shapes]
+
+
+def layer_bytes(name, rows0, K=NET_K, M=NET_M):
+    """Algorithmic bytes of one layer call over rows0 level-0 rows: x read once, adj read once,
+    y written once (+ the pooled copy when the pooling is fused), parameters once; head: 4 N (32 + 3); normalise 2 4 N 3."""
+    if name == "head":
+        return 4 * rows0 * (32 + 3) + 4 * (32 * 1024 + 1024 + 1024 * 3 + 3)
+    if name == "normalize":
+        return 2 * 4 * rows0 * 3
+    for nm, ci, co, lvl, pooled in NET_LAYERS:
+        if nm == name:
+            n = rows0 >> (2 * lvl)
+            b = 4 * n * (ci + K + co) + 4 * (M * ci * co + 2 * M * ci + M + co)
+            return b + (4 * (n // 4) * co if pooled else 0)
+    return None
+
+
+# library profiler names -> layer (net_fwd.cu tags every launch of the fused forward with its layer)
+def _layer_of(kernel_name):
+    for nm, *_ in NET_LAYERS:
+        if kernel_name in (nm, "prep_" + nm):
+            return nm
+    return {"conv_fwd_small_kernel": "conv1", "pool_max_kernel": "conv1", "absmax_kernel": "conv1",
+            "mlp_head_tc_kernel": "head", "mlp_head_kernel": "head", "prep_head_w_kernel": "head",
+            "seg_abs_sum_kernel": "normalize", "seg_normalize_kernel": "normalize", "abs_sum_kernel": "normalize",
+            "normalize_rows_kernel": "normalize"}.get(kernel_name)
+
+
+def make_c3_patches(grid, block, only):
+    from facet_graph_convolution_b200 import patches
+    return patches.grid_patches(grid, grid, block=block, halo=3, K=NET_K, only=only)
+
+
+def cpu_net_run(steps, warmup, grid, block):
+    """Reference arm / cpu_baseline leg: the oracle's closed form of the reference network (oracle/closed_form.py,
+    fp32 NumPy with all BLAS threads) + normalizeTensor on ONE patch of the C3 mesh per step."""
+    from oracle import closed_form as cf
+    mine, _ = make_c3_patches(grid, block, [0])
+    p = mine[0]
+    pd = cf.split_net_params(net_params())
+    x, adjs = p.x[None].astype(np.float32), [a[None] for a in p.adjs]
+    run = lambda: cf.normalize_tensor(cf.net_forward(x, adjs, pd, dtype=np.float32), dtype=np.float32)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return int(p.core.sum()) / dt, dt * 1e3, p.x.shape[0], int(p.core.sum()), os.cpu_count() or 1
+
+
+def run_c3(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    grid, block, PB = args.grid, args.block, max(1, args.patch_batch)
+    npatch = ((grid + block - 1) // block) ** 2
+    workload = ("C3 denoise inference: multi-scale network (8 facet-graph convs, M=%d, K=%d, 474199 params) + normalizeTensor "
+                "on a %dx%d-quad height field = %d facets in %d patches of %dx%d quads + 3-quad halo, patches dealt to "
+                "%d GPU(s), no collective, %d patches per launch" % (NET_M, NET_K, grid, grid, 2 * grid * grid, npatch,
+                                                                   block, block, world, PB))
+    config = {"workload": workload, "facets": 2 * grid * grid, "patches": npatch, "K": NET_K, "M": NET_M,
+              "parallelism": "patch-sharded x%d (no data-path collective)" % world,
+              "l2": "patch tensors of one pass (x + 3 adjacency levels, ~240 MB per 2 M facets) exceed the 126 MB L2; "
+                    "every pass re-reads them, no flush"}
+    if args.impl == "reference":
+        if rank != 0:
+            return None
+        steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 1))
+        val, ms, nodes, core, cores = cpu_net_run(steps, warm, grid, block)
+        return {"impl": "reference", "metric": "facets/sec (denoise inference, fp32)", "value": val, "unit": "facets/s",
+                "n_gpus": 0, "steps": steps,
+                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "facets/s", "cores": cores, "kind": "port",
+                                 "sample": "oracle/closed_form.py net_forward + normalize_tensor (fp32 NumPy restatement of "
+                                           "Code/model.py:837-946; TensorFlow is not installable and the Python reference "
+                                           "cannot travel to the GPU box), one of the %d patches per step (%d nodes, %d core "
+                                           "facets), whole mesh = per-patch time x %d" % (npatch, nodes, core, npatch)},
+                "e2e": {"value": val, "unit": "facets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+    import torch
+    from facet_graph_convolution_b200 import _lib, ops, patches
+    from facet_graph_convolution_b200 import model as fm
+    _lib.require_device()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    plan = patches.partition([1] * npatch, world)          # equal-sized blocks: every rank derives the same deal
+    t0 = time.perf_counter()
+    mine, num_faces = make_c3_patches(grid, block, plan[rank])
+    t_gen = time.perf_counter() - t0
+    store = fm.VariableStore(dev, params=net_params())
+    groups = [list(range(i, min(i + PB, len(mine)))) for i in range(0, len(mine), PB)]
+    host = []
+    for g in groups:
+        xb, ab = patches.batch_patches(mine, g)
+        host.append((torch.from_numpy(xb).pin_memory(), [torch.from_numpy(a).pin_memory() for a in ab],
+                     torch.tensor([mine[i].x.shape[0] for i in g], dtype=torch.int32).pin_memory()))
+    resident = [(x.to(dev), [a.to(dev) for a in adjs], ns.to(dev)) for x, adjs, ns in host]
+    core = sum(int(p.core.sum()) for p in mine)
+    rows0 = sum(int(x.shape[0] * x.shape[1]) for x, _, _ in host)     # level-0 rows launched per pass (halo + padding incl.)
+
+    def fwd(x, adjs, cnt):
+        """the public API: the reference's network function + normalizeTensor per patch (utils.py:1700-1715)"""
+        with torch.no_grad(), fm.variable_store(store):
+            y = fm.get_model_reg_multi_scale(x, adjs, 1.0)
+            return ops.normalize_rows_segmented(y, cnt)
+
+    def one_pass():
+        for x, adjs, cnt in resident:
+            fwd(x, adjs, cnt)
+
+    for _ in range(max(args.warmup, 3)):
+        one_pass()
+    barrier()
+    # per-layer CUDA-event times of one pass (library profiler; outside the timed region)
+    stream = torch.cuda.current_stream()
+    L.fgc_profile_begin(C.c_void_p(stream.cuda_stream))
+    one_pass()
+    buf = C.create_string_buffer(1 << 16)
+    L.fgc_profile_end(buf, len(buf))
+    prof = {ln.split()[0]: (float(ln.split()[1]), int(ln.split()[2])) for ln in buf.value.decode().strip().splitlines()}
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = L.fgc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_pass()
+    e1.record()
+    barrier()
+    launches = (L.fgc_launch_count() - n0)
+    clocks = sampler.result()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    total_core, total_rows0 = core, rows0
+    if world > 1:
+        t = torch.tensor([core, rows0, launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        total_core, total_rows0, launches = (int(v) for v in t.tolist())
+    ms_per_step = ms_total / args.steps
+    value = total_core * args.steps / (ms_total * 1e-3)
+
+    # ---- per-layer roofline (this rank's pass): algorithmic bytes / (layer's kernels incl. its pre-pass)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    layers, other_ms = {}, 0.0
+    for kn, (ms_k, cnt) in prof.items():
+        ln = _layer_of(kn)
+        if ln is None:
+            other_ms += ms_k
+            continue
+        d = layers.setdefault(ln, {"ms_per_pass": 0.0, "launches_per_pass": 0, "kernels": {}})
+        d["ms_per_pass"] += ms_k
+        d["launches_per_pass"] += cnt
+        d["kernels"][kn] = round(ms_k, 4)
+    for ln, d in layers.items():
+        kb = layer_bytes(ln, rows0)
+        d["algorithmic_bytes_per_pass"] = kb
+        d["algorithmic_GBps"] = kb / (d["ms_per_pass"] * 1e-3) / 1e9
+        d["frac_of_hbm_peak"] = d["algorithmic_GBps"] / peak_gbs
+    net_bytes = sum(d["algorithmic_bytes_per_pass"] for d in layers.values())
+    prof_ms = sum(d["ms_per_pass"] for d in layers.values()) + other_ms
+    dom = max(layers, key=lambda k: layers[k]["ms_per_pass"]) if layers else None
+    roofline = None
+    if dom:
+        d = layers[dom]
+        main_k = max(d["kernels"], key=lambda k: d["kernels"][k])
+        roofline = {"bound": "hbm", "kernel": main_k, "layer": dom, "achieved": d["algorithmic_GBps"], "peak": peak_gbs,
+                    "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": measured_traffic(main_k), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_pass"] / max(1, len(groups)),
+                    "ms_per_launch": d["ms_per_pass"] / max(1, len(groups)),
+                    "note": "dominant LAYER of the pass (its convolution launches + its pre-pass); one 'launch' = the layer over "
+                            "one batch of %d patches; bytes per SURVEY 8(d): 4 B N (Cin + K + Cout) + parameters" % PB,
+                    "network": {"algorithmic_bytes_per_pass": net_bytes, "algorithmic_GBps": net_bytes / (prof_ms * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": net_bytes / (prof_ms * 1e-3) / 1e9 / peak_gbs,
+                                "bytes_per_level0_row": net_bytes / max(1, rows0)}}
+
+    # ---- end to end: pinned HOST patch tensors in, pinned host normals out, uploads of batch i+1 under batch i
+    e2e = None
+    if not args.no_e2e:
+        outs = [torch.empty(x.shape[0], x.shape[1], 3).pin_memory() for x, _, _ in host]
+        copy_s = torch.cuda.Stream()
+        h2d = sum(x.numel() * 4 + sum(a.numel() * 4 for a in adjs) + ns.numel() * 4 for x, adjs, ns in host)
+        d2h = sum(o.numel() * 4 for o in outs)
+
+        def e2e_pass():
+            cur = torch.cuda.current_stream()
+            staged = None
+
+            def upload(i):
+                with torch.cuda.stream(copy_s):
+                    x, adjs, ns = host[i]
+                    t = (x.to(dev, non_blocking=True), [a.to(dev, non_blocking=True) for a in adjs], ns.to(dev, non_blocking=True))
+                    ev = torch.cuda.Event()
+                    ev.record(copy_s)
+                return t, ev
+
+            staged = upload(0)
+            for i in range(len(host)):
+                (xd, ad, nd), ev = staged
+                if i + 1 < len(host):
+                    staged = upload(i + 1)
+                cur.wait_event(ev)
+                yn = fwd(xd, ad, nd)
+                for t in (xd, nd, *ad):
+                    t.record_stream(cur)
+                outs[i].copy_(yn, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_pass()
+        barrier()
+        ksteps = max(2, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_pass()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if world > 1:
+            t = torch.tensor([h2d, d2h], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            h2d, d2h = (int(v) for v in t.tolist())
+        e2e = {"value": total_core * ksteps / dt, "unit": "facets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": ksteps, "ms_per_step": dt / ksteps * 1e3,
+               "api": "model.get_model_reg_multi_scale + normalizeTensor per patch batch (fgc_net_fwd / "
+                      "fgc_normalize_rows_segmented through the C ABI) from pinned host patch tensors (features + 3-level "
+                      "adjacency pyramid) to pinned host normals; uploads of the next batch overlap the current forward"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, ms, nodes, pc, cores = cpu_net_run(2, 1, grid, block)
+        cpu_baseline = {"value": val, "unit": "facets/s", "cores": cores, "kind": "port",
+                        "sample": "oracle/closed_form.py net_forward + normalize_tensor (fp32 NumPy), 2 passes over 1 of the %d "
+                                  "patches (%d nodes, %d core facets), %.0f ms per patch" % (npatch, nodes, pc, ms)}
+    layer_rec = None
+    if rank == 0 and world == 1 and not args.no_layer:
+        sub = argparse.Namespace(**vars(args))
+        sub.steps, sub.warmup, sub.no_e2e, sub.no_cpu_baseline, sub.impl = 5, 3, True, True, "b200"
+        r = run_c2(sub, as_record=True)
+        layer_rec = {"workload": r["config"]["workload"], "facets_per_s": r["value"], "ms_per_step": r["ms_per_step"],
+                     "roofline": r["roofline"], "layer": r["layer"],
+                     "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in r["kernels"].items()}}
+    line = None
+    if rank == 0:
+        line = {"metric": "facets/sec (denoise inference, fp32)", "value": value, "unit": "facets/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "layers": layers,
+                "cpu_baseline": cpu_baseline, "layer": layer_rec,
+                "rows": {"core_facets": total_core, "level0_rows_per_pass": total_rows0,
+                         "host_patch_generation_s": t_gen, "patches_this_rank": len(mine)}}
+    if world > 1:
+        dist.barrier()
+    return line
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c2"])
+    ap.add_argument("--grid", type=int, default=1000, help="c3: quads per side (1000 -> 2 M facets)")
+    ap.add_argument("--block", type=int, default=100, help="c3: quads per side of a patch core")
+    ap.add_argument("--patch-batch", type=int, default=25, help="c3: patches per launch (1 = the reference's B = 1)")
+    ap.add_argument("--adjacency", default="mesh", choices=["mesh", "dedup", "random"], help="c2")
+    ap.add_argument("--facets", type=int, default=1_000_000, help="c2")
+    ap.add_argument("--cpu-sample", type=int, default=20_000, help="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-layer", action="store_true", help="c3: skip the C2 layer record")
+    args = ap.parse_args()
+    line = run_c2(args) if args.config == "c2" else run_c3(args)
+    if line is not None:
+        print(json.dumps(line))
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

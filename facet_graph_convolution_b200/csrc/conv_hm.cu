@@ -619,7 +619,7 @@ int launch_conv_hm_weights(const float* W0, int M, int Cout, int Cw, void* wbuf,
 // xunscale[B] = 2^ex of the image rows of every batch element, wbuf from launch_conv_hm_weights; ymax: [B] or null.
 int launch_conv_hm_core(const void* img, const float* xunscale, const float* uvx, const int32_t* adj, const void* wbuf,
                         const float* b, float* y, float* ypool, unsigned* ymax, int64_t rows, int N, int K, int M, int Cw,
-                        int Cout, int upshift, int bias_mask, int act, float alpha, cudaStream_t st) {
+                        int Cout, int upshift, int bias_mask, int act, float alpha, cudaStream_t st, const char* tag) {
   const int nunits = (Cw + 63) / 64, CB = Cout < 64 ? Cout : 64, nob = Cout / CB;
   const int64_t rows_img = rows >> upshift;
   FGC_REQUIRE(ypool == nullptr || (N % 4 == 0), "conv_hm: pooled output needs N %% 4 == 0");
@@ -646,7 +646,7 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* uvx
       hp.ymax = last ? ymax : nullptr;
       hp.add_bias = u == 0, hp.accumulate = u > 0, hp.apply_act = last;
       kern<<<static_cast<unsigned>(grid), kHThreads, smem, st>>>(hp);
-      FGC_LAUNCHED("conv_hm_kernel");
+      FGC_LAUNCHED(tag != nullptr ? tag : "conv_hm_kernel");
     }
   return FGC_OK;
 }

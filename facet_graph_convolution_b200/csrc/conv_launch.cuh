@@ -117,12 +117,13 @@ size_t conv_hm_weights_bytes(int Cw, int Cout, int M);
 int launch_conv_hm_weights(const float* W0, int M, int Cout, int Cw, void* wbuf, cudaStream_t st);
 int launch_conv_hm_core(const void* img, const float* xunscale, const float* uvx, const int32_t* adj, const void* wbuf,
                         const float* b, float* y, float* ypool, unsigned* ymax, int64_t rows, int N, int K, int M, int Cw,
-                        int Cout, int upshift, int bias_mask, int act, float alpha, cudaStream_t st);
+                        int Cout, int upshift, int bias_mask, int act, float alpha, cudaStream_t st,
+                        const char* tag = nullptr);   // tag: name the launches carry in the library profiler
 int launch_absmax_bits(const float* x, int64_t n4_per_elem, int B, unsigned* out, cudaStream_t st);
 // fused pre-pass (logits.cu): logits + fp16 image of [xa | xb] in one pass
 int launch_prep_rows(const float* xa, int lda, int Ca, const float* xb, int ldb, int Cb, const float* u, const float* v,
                      const float* c, int M, int64_t rows, int Nimg, const unsigned* maxa, const unsigned* maxb, void* img,
-                     float* uvx, float* xunscale, cudaStream_t st);
+                     float* uvx, float* xunscale, cudaStream_t st, const char* tag = nullptr);
 // fused regression head on tcgen05 (lin_tc.cu)
 bool mlp_head_tc_supported(int64_t rows, int Cin, int H, int Cout);
 size_t mlp_head_tc_workspace();

@@ -350,14 +350,14 @@ prep_rows_warp_kernel(const PrepRowsParams p) {
 }
 
 template <int OP, int LPR>
-int run_prep_rows(const PrepRowsParams& p, cudaStream_t st) {
+int run_prep_rows(const PrepRowsParams& p, cudaStream_t st, const char* tag) {
   const int64_t rows_per_block = 8 * (32 / LPR);
   int64_t blocks = (p.rows + rows_per_block - 1) / rows_per_block;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   prep_rows_warp_kernel<OP, LPR><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
-  FGC_LAUNCHED("prep_rows_kernel");
+  FGC_LAUNCHED(tag != nullptr ? tag : "prep_rows_kernel");
   return FGC_OK;
 }
 
@@ -408,17 +408,17 @@ int fast_lpr(int Cin, int Ca0, int Ca, int M) {
 // rows of [xa (Ca channels, row stride lda) | xb (Cb, ldb; may be null)] -> uvx[rows + 1][2M], img[rows + 1][nunits][16]
 int launch_prep_rows(const float* xa, int lda, int Ca, const float* xb, int ldb, int Cb, const float* u, const float* v,
                      const float* c, int M, int64_t rows, int Nimg, const unsigned* maxa, const unsigned* maxb, void* img,
-                     float* uvx, float* xunscale, cudaStream_t st) {
+                     float* uvx, float* xunscale, cudaStream_t st, const char* tag) {
   const int Cin = Ca + Cb, nunits = (Cin + 63) / 64;
   FGC_REQUIRE(Ca % 4 == 0 && Cb % 4 == 0 && Cin <= 128 && 2 * M <= 32 && lda % 4 == 0 && (xb == nullptr || ldb % 4 == 0),
               "prep_rows: unsupported shape (Ca=%d Cb=%d M=%d)", Ca, Cb, M);
   FGC_REQUIRE(Nimg > 0 && rows % Nimg == 0, "prep_rows: rows must be a multiple of the rows per batch element");
   PrepRowsParams p{xa, xb, u, v, c, maxa, maxb, static_cast<uint4*>(img), uvx, xunscale, rows, lda, Ca, ldb, Cb, M, nunits, Nimg};
   if (Cin <= 64) {
-    if (2 * M <= 16) return run_prep_rows<16, 16>(p, st);
-    return run_prep_rows<32, 16>(p, st);
+    if (2 * M <= 16) return run_prep_rows<16, 16>(p, st, tag);
+    return run_prep_rows<32, 16>(p, st, tag);
   }
-  return run_prep_rows<32, 32>(p, st);
+  return run_prep_rows<32, 32>(p, st, tag);
 }
 
 #define FGC_LG_DISPATCH(FN, ...)                                              \

@@ -20,6 +20,10 @@ constexpr int kNetConvs = 8;
 constexpr int kCin[kNetConvs] = {6, 32, 64, 128, 128, 128, 64, 64};
 constexpr int kCout[kNetConvs] = {32, 64, 128, 128, 64, 64, 32, 32};
 constexpr int kNetParams = kNetConvs * 5 + 4;
+// names the launches of a layer carry in the library profiler (fgc_profile_begin/_end): bench.py's per-layer table
+const char* const kLayerTag[kNetConvs] = {"conv1", "conv2", "conv3", "dconv3", "upconv2", "dconv2", "upconv1", "dconv1"};
+const char* const kPrepTag[kNetConvs] = {"prep_conv1", "prep_conv2", "prep_conv3", "prep_dconv3", "prep_upconv2",
+                                         "prep_dconv2", "prep_upconv1", "prep_dconv1"};
 
 struct PreparedLayout {
   size_t off[kNetConvs];
@@ -141,10 +145,11 @@ int fgc_net_fwd(int B, int N0, int K, const float* x, const int32_t* adj0, const
                    int64_t rows_in, int Nin, const int32_t* adj, int64_t rows, int N, int upshift, int act, float* out,
                    float* pooled, unsigned* omax) -> int {
     const ConvP p = conv_params(params, l);
-    int r = launch_prep_rows(xa, Ca, Ca, xb, Cb, Cb, p.u, p.v, p.c, kNetM, rows_in, Nin, ma, mb, w.img, w.uvx, w.xunscale, st);
+    int r = launch_prep_rows(xa, Ca, Ca, xb, Cb, Cb, p.u, p.v, p.c, kNetM, rows_in, Nin, ma, mb, w.img, w.uvx, w.xunscale, st,
+                             kPrepTag[l]);
     if (r) return r;
     return launch_conv_hm_core(w.img, w.xunscale, w.uvx, adj, prep + L.off[l], p.b, out, pooled, omax, rows, N, K, kNetM,
-                               Ca + Cb, kCout[l], upshift, 1, act, alpha, st);
+                               Ca + Cb, kCout[l], upshift, 1, act, alpha, st, kLayerTag[l]);
   };
   // ---- Level 1: conv2 on pool(h1); its epilogue also writes pool(h2)
   rc = layer(1, w.p1, 32, mx[0], nullptr, 0, nullptr, R1, N1, adj1, R1, N1, 0, FGC_ACT_LRELU, w.h2, w.p2, mx[1]);
