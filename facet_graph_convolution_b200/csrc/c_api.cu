@@ -94,7 +94,9 @@ static bool use_mma(const fgc_conv_shape* s) {
 // HMMA-aggregation forward (conv_hm.cu): the dense layers without a tile plan, fused upsampling included
 static bool use_hm(const fgc_conv_shape* s) {
   static const bool disabled = getenv("FGC_DISABLE_HM") != nullptr || getenv("FGC_DISABLE_TC") != nullptr;
-  return !disabled && conv_hm_supported(s->Cin, s->Cw, s->Cout, s->M, s->K) && static_cast<int64_t>(s->B) * s->N >= 64;
+  // plain feature assignment over the whole row (the network's layers; the position / window variants keep their kernels)
+  return !disabled && conv_hm_supported(s->Cin, s->Cw, s->Cout, s->M, s->K) && s->Cw == s->Cin && s->Ca0 == 0 &&
+         s->Ca == s->Cin && prep_rows_supported(s->Cin, 0, s->M) && static_cast<int64_t>(s->B) * s->N >= 64;
 }
 
 static size_t conv_fwd_workspace(const fgc_conv_shape* s) {
@@ -120,12 +122,8 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
       const size_t hb = conv_hm_workspace(rows >> upshift, s->Cw, s->Cout, s->M, s->B);
       char* hws = wsu.take<char>(hb);
       FGC_REQUIRE(wsu.ok(), "conv_fwd_up: workspace too small");
-      fgc_conv_shape sc = *s;
-      sc.B = 1, sc.N = static_cast<int>(rows >> upshift);
-      int rch = launch_assign_logits(&sc, x, u, v, c, uvx_c, st);
-      if (rch) return rch;
-      ConvFwdParams ph{x, adj, uvx_c, nullptr, b, y, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M, bias_mask, act, alpha};
-      return launch_conv_hm(ph, W0, hws, hb, st, upshift);
+      ConvFwdParams ph{x, adj, nullptr, nullptr, b, y, rows, s->N, s->K, s->Cin, s->Cw, s->Cout, s->M, bias_mask, act, alpha};
+      return launch_conv_hm(ph, W0, u, v, c, hws, hb, st, upshift);
     }
     wsu.take<float>(static_cast<size_t>(s->M) * s->Cout * s->Cw);
     char* wimg_u = wsu.take<char>(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw));
@@ -162,14 +160,14 @@ static int conv_fwd(const fgc_conv_shape* s, const float* x, const int32_t* adj,
     if (rc) return rc;
     return launch_conv_mma(p, W0, plan, img, wimg, st, fused);
   }
-  rc = launch_assign_logits(s, x, u, v, c, uvx, st);
-  if (rc) return rc;
   if (use_hm(s)) {
     const size_t hb = conv_hm_workspace(rows, s->Cw, s->Cout, s->M, s->B);
     char* hws = ws.take<char>(hb);
     FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the HMMA-aggregation path");
-    return launch_conv_hm(p, W0, hws, hb, st);
+    return launch_conv_hm(p, W0, u, v, c, hws, hb, st);
   }
+  rc = launch_assign_logits(s, x, u, v, c, uvx, st);
+  if (rc) return rc;
   if (use_tc(s)) {
     char* wimg = ws.take<char>(conv_fwd_tc_workspace(s->Cout, s->M, s->Cw));
     FGC_REQUIRE(ws.ok(), "conv_fwd: workspace too small for the tensor-core path");

@@ -57,7 +57,8 @@ struct HmParams {
   const uint4* img;        // fp16 image of this launch's 64-channel unit: row r at img + r * img_ld, [0..8) hi, [8..16) lo
   int img_ld;
   const float* xunscale;   // [B]: 2^ex of the image rows of every batch element
-  const float* uvx;        // [rows >> upshift][2M]
+  const float* lg;         // [2][rows_img + 1][16]: pairs {vl'[m], vl'[8]} of every row, then pairs {uo'[m], uo'[8]} (prep_rows)
+  const unsigned* flag;    // != 0: some row's logits spread over > 60 binary orders -> re-centre the softmax here
   const int32_t* adj;
   const uint32_t* wt;      // [128 TMEM lanes][W_COLS]
   const float* wunscale;
@@ -115,8 +116,8 @@ __device__ __forceinline__ uint32_t w4(const uint4& v, int i) { return i == 0 ? 
 // The inputs of item n+1 (and the adjacency ids of item n+2) are in flight while item n is computed.
 struct HmPre {            // prefetched inputs of one item
   uint4 xh[4], xl[4];     // 16-byte unit g of the hi / lo plane of the rows of this lane's four slots
-  float vg[4], v8[4];     // neighbour logits of weight g / weight 8 of those slots
-  float uo_g, uo_8;       // own logits
+  float2 vl[4];           // neighbour logits of weights g and 8 of those slots (max-shifted, in log2 units)
+  float2 uo;              // own logits of weights g and 8
   int okm;                // bit i: slot i holds a valid neighbour
   int nz;                 // non-zero ids among this lane's four slots
 };
@@ -135,23 +136,27 @@ __device__ __forceinline__ void hm_mma(float (&d)[4], uint32_t a0, uint32_t a1, 
 
 // acc (+)= contribution of the item's 16 slots; returns the number of non-zero ids among them
 template <int M, bool FIRST>
-__device__ __forceinline__ int hm_mma_item(const HmPre& in, float (&acc)[8][4]) {
+__device__ __forceinline__ int hm_mma_item(const HmPre& in, float (&acc)[8][4], bool recentre) {
   int c = in.nz;
   c += __shfl_xor_sync(0xffffffffu, c, 1);
   c += __shfl_xor_sync(0xffffffffu, c, 2);
-  constexpr float L2E = 1.4426950408889634f;
   float qg[4], q8[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float ag = in.uo_g + in.vg[i];
-    const float a8 = (M == 9) ? in.uo_8 + in.v8[i] : 0.f;
-    float mx = (M == 9) ? fmaxf(ag, a8) : ag;
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-    const float ms = -mx * L2E;
-    const float eg = ex2_approx(fmaf(ag, L2E, ms));
-    const float e8 = (M == 9) ? ex2_approx(fmaf(a8, L2E, ms)) : 0.f;
+    // logits arrive max-shifted per row and in log2 units: uo' + vl' <= 0, and the largest of the M sums is
+    // >= -(smaller of the two rows' spreads), so exp2 cannot underflow for all M at once unless the pre-pass
+    // raised its flag -- then (warp-uniform) the exact maximum over m is subtracted as the reference's softmax does
+    float ag = in.uo.x + in.vl[i].x;
+    float a8 = (M == 9) ? in.uo.y + in.vl[i].y : 0.f;
+    if (recentre) {
+      float mx = (M == 9) ? fmaxf(ag, a8) : ag;
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+      ag -= mx, a8 -= mx;
+    }
+    const float eg = ex2_approx(ag);
+    const float e8 = (M == 9) ? ex2_approx(a8) : 0.f;
     float z = eg;
     z += __shfl_xor_sync(0xffffffffu, z, 4);
     z += __shfl_xor_sync(0xffffffffu, z, 8);
@@ -338,12 +343,20 @@ conv_hm_kernel(const HmParams p) {
           for (int j = 0; j < 16; ++j) yold[j] = 0.f;
         }
         const int be0 = nv > 0 ? static_cast<int>(r0 / p.N) : 0;
-        float sc0 = __ldg(p.xunscale + be0) * wun;
+        const float sca = __ldg(p.xunscale + be0) * wun;
+        // rows of the next batch element start at j = cross (N >= 16: at most one boundary inside a lane's 16 rows)
+        int cross = 16;
+        float scb = sca;
+        if (!aligned && nv > 0) {
+          cross = static_cast<int>(static_cast<int64_t>(be0 + 1) * p.N - r0);
+          if (cross < nv) scb = __ldg(p.xunscale + be0 + 1) * wun;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float accv = hh ? (send[j] + keep[j]) : (keep[j] + send[j]);   // (Wh.Sh + Wh.Sl) + Wl.Sh / 2048
           const float fl = (inv[j] > 0.f || unmasked) ? bo : 0.f;
-          if (!aligned && j > 0 && j < nv) sc0 = __ldg(p.xunscale + (r0 + j) / p.N) * wun;
+          float sc0 = j < cross ? sca : scb;
+          if (p.N < 16 && j > 0 && j < nv) sc0 = __ldg(p.xunscale + (r0 + j) / p.N) * wun;   // tiny elements: several boundaries
           float v = fmaf(inv[j] * sc0, accv, fl);
           v += yold[j];
           if (p.apply_act && p.act == FGC_ACT_LRELU) v = lrelu_f(v, p.alpha);
@@ -386,9 +399,10 @@ conv_hm_kernel(const HmParams p) {
     const int rows32 = static_cast<int>(p.rows);
     constexpr uint32_t idesc = (1u << 4) | ((static_cast<uint32_t>(Cfg::ND) >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t sb = tc::smem_u32(smem);
-    const float* uvx_g = p.uvx + g;
-    const float* uvx_vg = p.uvx + M + g;
+    const float2* lg_v = reinterpret_cast<const float2*>(p.lg) + g;                             // neighbour pair of row j: lg_v[8 j]
+    const float2* lg_u = lg_v + static_cast<int64_t>(p.zrow + 1) * 8;                           // own pair of row r: lg_u[8 r]
     const uint4* img_g = p.img + g;
+    const bool recentre = __ldg(p.flag) != 0;
     auto row_of = [&](int m) -> int {   // global row of item m, -1 when there is none
       const int n = m / NG;
       const int r = (static_cast<int>(blockIdx.x) + (n / kHFpw) * static_cast<int>(gridDim.x)) * kHT + aw * kHFpw + (n % kHFpw);
@@ -411,9 +425,7 @@ conv_hm_kernel(const HmParams p) {
         while (r >= base_next) base_cur = base_next, base_next += p.N;
         base = base_cur;
       }
-      const int64_t ro = static_cast<int64_t>((r < 0 ? 0 : r) >> p.upshift) * (2 * M);
-      o.uo_g = __ldg(uvx_g + ro);
-      o.uo_8 = (M == 9) ? __ldg(p.uvx + ro + 8) : 0.f;
+      o.uo = __ldg(lg_u + static_cast<int64_t>((r < 0 ? 0 : r) >> p.upshift) * 8);
       o.okm = 0, o.nz = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -421,9 +433,7 @@ conv_hm_kernel(const HmParams p) {
         const int row = ok ? ((base + id[i] - 1) >> p.upshift) : p.zrow;   // zrow: all-zero image / logit row
         o.okm |= ok ? (1 << i) : 0;
         o.nz += (id[i] != 0);
-        const int64_t lo = static_cast<int64_t>(row) * (2 * M);
-        o.vg[i] = __ldg(uvx_vg + lo);
-        o.v8[i] = (M == 9) ? __ldg(p.uvx + lo + (M + 8)) : 0.f;
+        o.vl[i] = __ldg(lg_v + static_cast<int64_t>(row) * 8);
         const uint4* src = img_g + static_cast<int64_t>(row) * p.img_ld;
         o.xh[i] = __ldg(src);
         o.xl[i] = __ldg(src + 8);
@@ -467,8 +477,10 @@ conv_hm_kernel(const HmParams p) {
         __syncwarp();
       }
     };
-    // the adjacency ids of the next item are in flight while the current one is gathered and aggregated;
-    // memory latency is otherwise covered by the other four aggregator warps of the sub-partition
+    // The adjacency ids of the next item are in flight while the current one is gathered and aggregated; memory
+    // latency is otherwise covered by the other four aggregator warps of the sub-partition.  (Issuing the row loads
+    // of item m+1 right after the MMAs of item m, to fly under its drain, was measured SLOWER: 0.82 vs 0.63 ms per
+    // 562 k rows -- the proxy fence at the end of a warp's facets then waits for those loads.)
     HmPre P;
     int idc[4], idn[4];
     load_ids(0, idc);
@@ -476,11 +488,11 @@ conv_hm_kernel(const HmParams p) {
     for (int m = 0; m < nitems; m += NG) {
       load_ids(m + 1, idn);
       issue(m, idc, P);
-      cnt = hm_mma_item<M, true>(P, acc);
+      cnt = hm_mma_item<M, true>(P, acc, recentre);
       if (NG == 2) {
         load_ids(m + 2, idc);
         issue(m + 1, idn, P);
-        cnt += hm_mma_item<M, false>(P, acc);
+        cnt += hm_mma_item<M, false>(P, acc, recentre);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) idc[i] = idn[i];
@@ -538,9 +550,7 @@ prep_wt_kernel(const float* __restrict__ W0, uint32_t* __restrict__ wt, float* _
   }
 }
 
-// ------------------------------------------------------------------ fp16 hi|lo image of x, all units of a layer
-// img[r][u] = [fp16(x_r[64u..] * s) (64 halves) | fp16 residuals (64 halves)], s = 2^(126-E), E = exponent of max|x|;
-// channels beyond Cw read as zero.
+// ------------------------------------------------------------------ max|x| per batch element (image scale)
 __global__ void __launch_bounds__(256)
 hm_absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__ out) {   // blockIdx.y: batch element
   float m = 0.f;
@@ -556,33 +566,6 @@ hm_absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
-__global__ void __launch_bounds__(256)
-hm_prep_img_kernel(const float* __restrict__ x, int ldx, int Cw, int nunits, int64_t rows, int Nimg,
-                   const unsigned* __restrict__ maxbits, uint4* __restrict__ img, float* __restrict__ xunscale) {
-  const int per_row = nunits * 8;   // one thread per 8 channels
-  const int64_t total = rows * per_row;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / per_row;
-    const int j = static_cast<int>(i % per_row), u = j >> 3, jj = j & 7;
-    const int c0 = u * 64 + jj * 8;
-    const int be = static_cast<int>(r / Nimg);            // the scale is per batch element
-    const int E = min(max(static_cast<int>((__ldg(maxbits + be) >> 23) & 0xFF), 16), 240);
-    const float sc = __int_as_float((253 - E) << 23);
-    if (j == 0 && r == static_cast<int64_t>(be) * Nimg) xunscale[be] = __int_as_float((E + 1) << 23);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (c0 < Cw) a = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c0));
-    if (c0 + 4 < Cw) b = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c0 + 4));
-    const float v[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, b.x * sc, b.y * sc, b.z * sc, b.w * sc};
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) split_rn(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
-    uint4* dst = img + (r * nunits + u) * 16 + jj;
-    dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    dst[8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  }
-}
-
 size_t hm_img_bytes(int64_t rows_img, int nunits) { return static_cast<size_t>(rows_img) * nunits * 256; }
 size_t hm_wt_bytes(int M, int nimg) { return static_cast<size_t>(nimg) * 128 * M * 32 * 4; }
 
@@ -596,8 +579,8 @@ bool conv_hm_supported(int Cin, int Cw, int Cout, int M, int K) {
 size_t conv_hm_weights_bytes(int Cw, int Cout, int M);
 size_t conv_hm_workspace(int64_t rows_img, int Cw, int Cout, int M, int B) {
   const int nunits = (Cw + 63) / 64;
-  return ws_bytes(hm_img_bytes(rows_img + 1, nunits), 1) + ws_bytes(2 * static_cast<size_t>(B) + 16, 4) +
-         ws_bytes(conv_hm_weights_bytes(Cw, Cout, M), 1);
+  return ws_bytes(hm_img_bytes(rows_img + 1, nunits), 1) + ws_bytes(static_cast<size_t>(rows_img + 1) * 32, 4) +
+         ws_bytes(2 * static_cast<size_t>(B) + 16, 4) + ws_bytes(conv_hm_weights_bytes(Cw, Cout, M), 1);
 }
 
 size_t conv_hm_weights_bytes(int Cw, int Cout, int M) {
@@ -615,16 +598,18 @@ int launch_conv_hm_weights(const float* W0, int M, int Cout, int Cw, void* wbuf,
   return FGC_OK;
 }
 
-// The convolution proper on prepared operands: img[rows_img + 1][nunits][16] / uvx[rows_img + 1][2M] (last row zero),
+// The convolution proper on prepared operands (launch_prep_rows): img[rows_img + 1][nunits][16] / lg[2][rows_img + 1][16]
+// (last row of each zero), flag = the pre-pass's spread flag,
 // xunscale[B] = 2^ex of the image rows of every batch element, wbuf from launch_conv_hm_weights; ymax: [B] or null.
-int launch_conv_hm_core(const void* img, const float* xunscale, const float* uvx, const int32_t* adj, const void* wbuf,
+int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg, const unsigned* flag, const int32_t* adj,
+                        const void* wbuf,
                         const float* b, float* y, float* ypool, unsigned* ymax, int64_t rows, int N, int K, int M, int Cw,
                         int Cout, int upshift, int bias_mask, int act, float alpha, cudaStream_t st, const char* tag) {
   const int nunits = (Cw + 63) / 64, CB = Cout < 64 ? Cout : 64, nob = Cout / CB;
   const int64_t rows_img = rows >> upshift;
   FGC_REQUIRE(ypool == nullptr || (N % 4 == 0), "conv_hm: pooled output needs N %% 4 == 0");
   HmParams hp{};
-  hp.img_ld = nunits * 16, hp.xunscale = xunscale, hp.uvx = uvx, hp.adj = adj;
+  hp.img_ld = nunits * 16, hp.xunscale = xunscale, hp.lg = lg, hp.flag = flag, hp.adj = adj;
   hp.wunscale = reinterpret_cast<const float*>(static_cast<const char*>(wbuf) + align_up(hm_wt_bytes(M, nunits * nob), 256));
   hp.ldy = Cout, hp.ldp = Cout, hp.rows = rows, hp.ntiles = (rows + kHT - 1) / kHT;
   hp.N = N, hp.K = K, hp.upshift = upshift, hp.bias_mask = bias_mask, hp.act = act, hp.alpha = alpha;
@@ -651,38 +636,31 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* uvx
   return FGC_OK;
 }
 
-// Generic entry (any caller of conv_fwd): p.x: rows >> upshift rows of Cin floats (the first Cw are aggregated);
-// p.uvx: their logits, with room for one more row (zeroed here).
-// ypool (optional): [rows / 4][Cout] max over groups of 4 rows of y; ymax (optional): atomicMax target for max|y| bits;
-// xmax (optional): device word that already holds the bits of an upper bound of max|x| (else computed here).
-int launch_conv_hm(const ConvFwdParams& p, const float* W0, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                   int upshift, float* ypool, unsigned* ymax, const unsigned* xmax) {
+// Generic entry (any caller of conv_fwd with plain feature assignment, Cw = Cin): p.x: rows >> upshift rows of Cin floats.
+// ypool (optional): [rows / 4][Cout] max over groups of 4 rows of y; ymax (optional): [B] atomicMax targets for max|y| bits.
+int launch_conv_hm(const ConvFwdParams& p, const float* W0, const float* u, const float* v, const float* c, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st, int upshift, float* ypool, unsigned* ymax) {
   const int nunits = (p.Cw + 63) / 64;
   const int64_t rows_img = p.rows >> upshift;
   Workspace ws(workspace, workspace_bytes);
   const int B = static_cast<int>(p.rows / p.N), Nimg = p.N >> upshift;
   uint4* img = reinterpret_cast<uint4*>(ws.take<char>(hm_img_bytes(rows_img + 1, nunits)));
-  unsigned* scal = ws.take<unsigned>(2 * static_cast<size_t>(B) + 16);   // [B] max|x| bits, then [B] 2^ex un-scales
+  float* lg = ws.take<float>((rows_img + 1) * 32);
+  unsigned* scal = ws.take<unsigned>(2 * static_cast<size_t>(B) + 16);   // [B] max|x| bits, [B] 2^ex un-scales, flag
   float* xunscale = reinterpret_cast<float*>(scal + B);
+  unsigned* flag = scal + 2 * B;
   char* wbuf = ws.take<char>(conv_hm_weights_bytes(p.Cw, p.Cout, p.M));
   FGC_REQUIRE(ws.ok(), "conv_hm: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
               conv_hm_workspace(rows_img, p.Cw, p.Cout, p.M, B));
-  const int blocks = num_sms() * 8;
-  if (xmax == nullptr) {
-    FGC_CUDA(cudaMemsetAsync(scal, 0, static_cast<size_t>(B) * sizeof(unsigned), st));
-    int rca = launch_absmax_bits(p.x, static_cast<int64_t>(Nimg) * (p.Cin / 4), B, scal, st);
-    if (rca) return rca;
-    xmax = scal;
-  }
-  hm_prep_img_kernel<<<blocks, 256, 0, st>>>(p.x, p.Cin, p.Cw, nunits, rows_img, Nimg, xmax, img, xunscale);
-  FGC_LAUNCHED("prep_x_image_kernel");
-  // row `rows_img` of the image and of the logits is all zero: what padding and out-of-range slots read
-  FGC_CUDA(cudaMemsetAsync(img + rows_img * nunits * 16, 0, static_cast<size_t>(nunits) * 256, st));
-  FGC_CUDA(cudaMemsetAsync(const_cast<float*>(p.uvx) + rows_img * 2 * p.M, 0, static_cast<size_t>(2 * p.M) * 4, st));
-  int rc = launch_conv_hm_weights(W0, p.M, p.Cout, p.Cw, wbuf, st);
+  FGC_CUDA(cudaMemsetAsync(scal, 0, (2 * static_cast<size_t>(B) + 16) * sizeof(unsigned), st));
+  int rc = launch_absmax_bits(p.x, static_cast<int64_t>(Nimg) * (p.Cin / 4), B, scal, st);
   if (rc) return rc;
-  return launch_conv_hm_core(img, xunscale, p.uvx, p.adj, wbuf, p.b, p.y, ypool, ymax, p.rows,
-                             p.N, p.K, p.M, p.Cw, p.Cout, upshift, p.bias_mask, p.act, p.alpha, st);
+  rc = launch_prep_rows(p.x, p.Cin, p.Cin, nullptr, 0, 0, u, v, c, p.M, rows_img, Nimg, scal, nullptr, img, lg, xunscale, flag, st);
+  if (rc) return rc;
+  rc = launch_conv_hm_weights(W0, p.M, p.Cout, p.Cw, wbuf, st);
+  if (rc) return rc;
+  return launch_conv_hm_core(img, xunscale, lg, flag, p.adj, wbuf, p.b, p.y, ypool, ymax, p.rows, p.N, p.K, p.M, p.Cw, p.Cout,
+                             upshift, p.bias_mask, p.act, p.alpha, st);
 }
 
 // max|x| of every batch element (n4_per_elem float4 each) -> atomicMax on out[b] (bits); out must have been zeroed

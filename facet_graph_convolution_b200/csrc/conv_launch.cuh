@@ -111,11 +111,12 @@ int launch_reduce_partials(const float* part, float* out, int64_t n, int P, int6
 // HMMA-aggregation + tcgen05-contraction forward (conv_hm.cu): any adjacency, no tile plan
 bool conv_hm_supported(int Cin, int Cw, int Cout, int M, int K);
 size_t conv_hm_workspace(int64_t rows_img, int Cw, int Cout, int M, int B);
-int launch_conv_hm(const ConvFwdParams& p, const float* W0, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                   int upshift = 0, float* ypool = nullptr, unsigned* ymax = nullptr, const unsigned* xmax = nullptr);
+int launch_conv_hm(const ConvFwdParams& p, const float* W0, const float* u, const float* v, const float* c, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st, int upshift = 0, float* ypool = nullptr, unsigned* ymax = nullptr);
 size_t conv_hm_weights_bytes(int Cw, int Cout, int M);
 int launch_conv_hm_weights(const float* W0, int M, int Cout, int Cw, void* wbuf, cudaStream_t st);
-int launch_conv_hm_core(const void* img, const float* xunscale, const float* uvx, const int32_t* adj, const void* wbuf,
+int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg, const unsigned* flag, const int32_t* adj,
+                        const void* wbuf,
                         const float* b, float* y, float* ypool, unsigned* ymax, int64_t rows, int N, int K, int M, int Cw,
                         int Cout, int upshift, int bias_mask, int act, float alpha, cudaStream_t st,
                         const char* tag = nullptr);   // tag: name the launches carry in the library profiler
@@ -123,7 +124,8 @@ int launch_absmax_bits(const float* x, int64_t n4_per_elem, int B, unsigned* out
 // fused pre-pass (logits.cu): logits + fp16 image of [xa | xb] in one pass
 int launch_prep_rows(const float* xa, int lda, int Ca, const float* xb, int ldb, int Cb, const float* u, const float* v,
                      const float* c, int M, int64_t rows, int Nimg, const unsigned* maxa, const unsigned* maxb, void* img,
-                     float* uvx, float* xunscale, cudaStream_t st, const char* tag = nullptr);
+                     float* lg, float* xunscale, unsigned* flag, cudaStream_t st, const char* tag = nullptr);
+bool prep_rows_supported(int Ca, int Cb, int M);
 // fused regression head on tcgen05 (lin_tc.cu)
 bool mlp_head_tc_supported(int64_t rows, int Cin, int H, int Cout);
 size_t mlp_head_tc_workspace();

@@ -246,10 +246,19 @@ logits_bwd_p_warp_kernel(const LgParams p) {
 
 // ------------------------------------------------------------------ fused pre-pass of the HMMA-aggregation forward
 // One pass over the rows of a layer input (optionally the channel concatenation [xa | xb] of two tensors, reference
-// Code/model.py:909,929, never materialised): assignment logits uvx[r] = [u;v] . x_r + [c;0] and the fp16 hi|lo image
-// img[r][unit] = [fp16(x s) (64) | fp16(x s - hi) (64)] with s = 2^(126-E), E = exponent of max(max|xa|, max|xb|)
-// per batch element (upper bounds the producing kernels leave behind; per element, so that a batch of patches gives
-// every patch exactly the result of running it alone).  Row `rows` of both outputs is zeroed (what padding slots read).
+// Code/model.py:909,929, never materialised).  Per row it writes
+//   * the fp16 hi|lo image  img[r][unit] = [fp16(x s) (64) | fp16(x s - hi) (64)],  s = 2^(126-E), E = exponent of
+//     max(max|xa|, max|xb|) of the row's batch element (upper bounds the producing kernels leave behind; per element,
+//     so that a batch of patches gives every patch exactly the result of running it alone);
+//   * the assignment logits (reference Code/model.py:74-95: u.x + c and v.x) in the form conv_hm.cu consumes:
+//     lg[r][0..15] = pairs {vl'[m], vl'[8]}, m = 0..7 (the table the consumer GATHERS: 64 bytes per row, kept
+//     apart from the own-row table so that gathered rows cost half an L1 line), lg[rows + 1 + r][0..15] = pairs
+//     {uo'[m], uo'[8]} (read once per facet, streaming), with
+//     uo' = (u.x + c - max_m) log2(e), vl' = (v.x - max_m) log2(e): exp2(uo' + vl') needs no further max.
+//     *flag is set when a row's logits spread over more than 60 binary orders (the consumer then re-centres).
+// The 2M dot products per row run on the warp-level tensor path: 16 rows x Cin as A fragments (the hi/lo split the
+// image needs anyway), [u;v] as fp16 hi|lo B fragments in shared memory, x_hi.w_hi + x_lo.w_hi + x_hi.w_lo in fp32.
+// Row `rows` of both outputs is zeroed (what padding slots read).
 struct PrepRowsParams {
   const float* xa;
   const float* xb;
@@ -259,36 +268,77 @@ struct PrepRowsParams {
   const unsigned* maxa;
   const unsigned* maxb;
   uint4* img;
-  float* uvx;
+  float* lg;
   float* xunscale;
+  unsigned* flag;
   int64_t rows;
   int lda, Ca, ldb, Cb, M, nunits;
   int Nimg;   // rows per batch element: maxa / maxb / xunscale are per element
 };
 
-template <int OP, int LPR>
-__global__ void __launch_bounds__(256, (OP <= 16) ? 2 : 1)
-prep_rows_warp_kernel(const PrepRowsParams p) {
-  constexpr int RPW = 32 / LPR, OPL = OP / LPR;
-  const int lane = threadIdx.x & 31, gl = lane % LPR, sub = lane / LPR;
-  const int O = 2 * p.M, Cin = p.Ca + p.Cb;
-  const int c4 = 4 * gl;
-  const bool act = c4 < Cin;                 // lane holds real channels
-  const bool inimg = c4 < p.nunits * 64;     // lane holds image channels (zeros beyond Cin)
-  float w[OP][4];
+__device__ __forceinline__ void prep_split(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void prep_hmma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int kPrepWarps = 8;
+
+// Output columns of the logit GEMM: 0..7 = uo[0..7], 8..15 = vl[0..7], 16 = uo[8], 17 = vl[8] (M = 9), rest zero.
+// k order inside a 16-channel step: k = 2t, 2t+1 <-> channels 4t, 4t+1; k = 2t+8, 2t+9 <-> channels 4t+2, 4t+3
+// (lane (g,t) then loads one float4 per row and step).
+__global__ void __launch_bounds__(kPrepWarps * 32)
+prep_rows_mma_kernel(const PrepRowsParams p) {
+  extern __shared__ uint4 wfrag[];             // [Cin/16][3][32]: {b0 hi, b1 hi, b0 lo, b1 lo} of (step, n-block, lane)
+  __shared__ float red[kPrepWarps];
+  __shared__ float wsc_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int Cin = p.Ca + p.Cb, nsteps = Cin >> 4, M = p.M;
+  // ---- weight fragments (every block builds its own: 2M x Cin values, L2-resident)
+  {
+    float mx = 0.f;
+    for (int e = threadIdx.x; e < M * Cin; e += blockDim.x) mx = fmaxf(mx, fmaxf(fabsf(__ldg(p.u + e)), fabsf(__ldg(p.v + e))));
 #pragma unroll
-  for (int o = 0; o < OP; ++o)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float t = 0.f;
-      if (o < O && c4 + j < Cin) t = (o < p.M) ? __ldg(p.u + o * Cin + c4 + j) : __ldg(p.v + (o - p.M) * Cin + c4 + j);
-      w[o][j] = t;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m2 = 0.f;
+      for (int i = 0; i < kPrepWarps; ++i) m2 = fmaxf(m2, red[i]);
+      int E = (__float_as_int(m2) >> 23) & 0xFF;
+      E = min(max(E, 16), 240);
+      wsc_s = __int_as_float((253 - E) << 23);   // |w| * wsc in [0.5, 1)
     }
-  float cb[OPL];
+    __syncthreads();
+    const float wsc = wsc_s;
+    for (int e = threadIdx.x; e < nsteps * 3 * 32; e += blockDim.x) {
+      const int ln = e & 31, nb = (e >> 5) % 3, ks = e / 96;
+      const int gg = ln >> 2, tt = ln & 3;
+      const int col = nb * 8 + gg;             // output column this lane's B fragment feeds
+      const float* src = nullptr;
+      if (col < 8) src = p.u + col * Cin;
+      else if (col < 16) src = p.v + (col - 8) * Cin;
+      else if (col == 16 && M == 9) src = p.u + 8 * Cin;
+      else if (col == 17 && M == 9) src = p.v + 8 * Cin;
+      float w4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (src != nullptr && (col & 7) < M) {
 #pragma unroll
-  for (int i = 0; i < OPL; ++i) {
-    const int o = gl * OPL + i;
-    cb[i] = (o < p.M) ? __ldg(p.c + o) : 0.f;
+        for (int j = 0; j < 4; ++j) w4[j] = __ldg(src + ks * 16 + 4 * tt + j) * wsc;
+      }
+      uint4 f;
+      prep_split(w4[0], w4[1], f.x, f.z);
+      prep_split(w4[2], w4[3], f.y, f.w);
+      wfrag[e] = f;
+    }
+    __syncthreads();
   }
   auto scale_exp = [&](int be) {   // exponent of the element's max |x| (clamped so that both scales stay normal)
     unsigned mb = __ldg(p.maxa + be);
@@ -302,63 +352,95 @@ prep_rows_warp_kernel(const PrepRowsParams p) {
   }
   if (blockIdx.x == 0) {
     if (threadIdx.x < p.nunits * 16) p.img[p.rows * p.nunits * 16 + threadIdx.x] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x < O) p.uvx[p.rows * O + threadIdx.x] = 0.f;
+    if (threadIdx.x < 16) p.lg[p.rows * 16 + threadIdx.x] = 0.f, p.lg[(2 * p.rows + 1) * 16 + threadIdx.x] = 0.f;
   }
-  const bool from_a = c4 < p.Ca;
-  const float* src = from_a ? p.xa + c4 : p.xb + (c4 - p.Ca);
-  const int ld = from_a ? p.lda : p.ldb;
-  uint8_t* const imgb = reinterpret_cast<uint8_t*>(p.img) + (c4 >> 6) * 256 + (c4 & 63) * 2;
-  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  constexpr int U = 4;   // row groups per iteration: all loads are in flight before the first is consumed
-  for (int64_t r0 = wid * RPW; r0 < p.rows; r0 += U * nw * RPW) {
-    int64_t rr[U];
-    float4 xs[U];
+  const float wun = 1.f / wsc_s;
+  const float cu0 = (2 * t < M) ? __ldg(p.c + 2 * t) : 0.f, cu1 = (2 * t + 1 < M) ? __ldg(p.c + 2 * t + 1) : 0.f;
+  const float c8 = (M == 9) ? __ldg(p.c + 8) : 0.f;
+  constexpr float L2E = 1.4426950408889634f;
+  bool spread = false;
+  const int64_t nblk = (p.rows + 15) >> 4;
+  for (int64_t blk = static_cast<int64_t>(blockIdx.x) * kPrepWarps + warp; blk < nblk;
+       blk += static_cast<int64_t>(gridDim.x) * kPrepWarps) {
+    const int64_t r0 = blk * 16 + g, r1 = r0 + 8;
+    const bool ok0 = r0 < p.rows, ok1 = r1 < p.rows;
+    const int e0 = ok0 ? scale_exp(static_cast<int>(r0 / p.Nimg)) : 127, e1 = ok1 ? scale_exp(static_cast<int>(r1 / p.Nimg)) : 127;
+    const float sc0 = __int_as_float((253 - e0) << 23), sc1 = __int_as_float((253 - e1) << 23);
+    float acc[3][4];
 #pragma unroll
-    for (int t = 0; t < U; ++t) {
-      rr[t] = r0 + t * nw * RPW + sub;
-      xs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rr[t] < p.rows && act) xs[t] = __ldg(reinterpret_cast<const float4*>(src + rr[t] * ld));
-    }
+    for (int nb = 0; nb < 3; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+    for (int u0 = 0; u0 < nsteps; u0 += 4) {          // one 64-channel unit (4 steps) at a time
+      float4 xa0[4], xa1[4];
 #pragma unroll
-    for (int t = 0; t < U; ++t) {
-      const float4 xv = xs[t];
-      const int64_t r = rr[t];
-      if (r < p.rows && inimg) {
-        const float sc = __int_as_float((253 - scale_exp(static_cast<int>(r / p.Nimg))) << 23);
-        const __half2 h0 = __floats2half2_rn(xv.x * sc, xv.y * sc), h1 = __floats2half2_rn(xv.z * sc, xv.w * sc);
-        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-        const __half2 l0 = __floats2half2_rn(xv.x * sc - f0.x, xv.y * sc - f0.y);
-        const __half2 l1 = __floats2half2_rn(xv.z * sc - f1.x, xv.w * sc - f1.y);
-        uint8_t* d = imgb + r * (p.nunits * 256);
-        *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-        *reinterpret_cast<uint2*>(d + 128) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      for (int j = 0; j < 4; ++j) {
+        const int ch = (u0 + j) * 16 + 4 * t;
+        xa0[j] = make_float4(0.f, 0.f, 0.f, 0.f), xa1[j] = xa0[j];
+        if (u0 + j < nsteps) {
+          const float* s0 = ch < p.Ca ? p.xa + r0 * p.lda + ch : p.xb + r0 * p.ldb + (ch - p.Ca);
+          const float* s1 = ch < p.Ca ? p.xa + r1 * p.lda + ch : p.xb + r1 * p.ldb + (ch - p.Ca);
+          if (ok0) xa0[j] = __ldg(reinterpret_cast<const float4*>(s0));
+          if (ok1) xa1[j] = __ldg(reinterpret_cast<const float4*>(s1));
+        }
       }
-      float a[OP];
+      const int unit = u0 >> 2;
 #pragma unroll
-      for (int o = 0; o < OP; ++o) a[o] = fmaf(xv.x, w[o][0], fmaf(xv.y, w[o][1], fmaf(xv.z, w[o][2], xv.w * w[o][3])));
-      transpose_reduce<OP, LPR>(a, gl);
-      if (r < p.rows) {
+      for (int j = 0; j < 4; ++j) {
+        // a0 = row g (k 2t,2t+1), a1 = row g+8, a2 = row g (k 2t+8, 2t+9), a3 = row g+8
+        uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
+        prep_split(xa0[j].x * sc0, xa0[j].y * sc0, h0, l0);
+        prep_split(xa1[j].x * sc1, xa1[j].y * sc1, h1, l1);
+        prep_split(xa0[j].z * sc0, xa0[j].w * sc0, h2, l2);
+        prep_split(xa1[j].z * sc1, xa1[j].w * sc1, h3, l3);
+        // image: channels (u0+j)*16 + 4t .. +3 of this unit: 8 bytes per plane (written for padded channels too)
+        const int cc = (j * 16 + 4 * t) * 2;   // byte offset inside the 128-byte plane
+        if (ok0) {
+          uint8_t* d = reinterpret_cast<uint8_t*>(p.img) + (r0 * p.nunits + unit) * 256 + cc;
+          *reinterpret_cast<uint2*>(d) = make_uint2(h0, h2);
+          *reinterpret_cast<uint2*>(d + 128) = make_uint2(l0, l2);
+        }
+        if (ok1) {
+          uint8_t* d = reinterpret_cast<uint8_t*>(p.img) + (r1 * p.nunits + unit) * 256 + cc;
+          *reinterpret_cast<uint2*>(d) = make_uint2(h1, h3);
+          *reinterpret_cast<uint2*>(d + 128) = make_uint2(l1, l3);
+        }
+        if (u0 + j < nsteps) {
 #pragma unroll
-        for (int i = 0; i < OPL; ++i) {
-          const int o = gl * OPL + i;
-          if (o < O) p.uvx[r * O + o] = a[i] + cb[i];
+          for (int nb = 0; nb < 3; ++nb) {
+            const uint4 f = wfrag[((u0 + j) * 3 + nb) * 32 + lane];
+            prep_hmma(acc[nb], h0, h1, h2, h3, f.x, f.y);
+            prep_hmma(acc[nb], l0, l1, l2, l3, f.x, f.y);
+            prep_hmma(acc[nb], h0, h1, h2, h3, f.z, f.w);
+          }
         }
       }
     }
+    // ---- logits of rows r0 (c0,c1) and r1 (c2,c3): nb 0 = uo[2t,2t+1], nb 1 = vl[2t,2t+1], nb 2 (t = 0) = uo[8], vl[8]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t r = h ? r1 : r0;
+      const bool ok = h ? ok1 : ok0;
+      const float un = __int_as_float(((h ? e1 : e0) + 1) << 23) * wun;
+      float u_a = fmaf(acc[0][2 * h], un, cu0), u_b = fmaf(acc[0][2 * h + 1], un, cu1);
+      float v_a = acc[1][2 * h] * un, v_b = acc[1][2 * h + 1] * un;
+      float u8 = fmaf(__shfl_sync(0xffffffffu, acc[2][2 * h], lane & ~3), un, c8);
+      float v8 = __shfl_sync(0xffffffffu, acc[2][2 * h + 1], lane & ~3) * un;
+      float mu = (2 * t + 1 < M) ? fmaxf(u_a, u_b) : ((2 * t < M) ? u_a : -INFINITY);
+      float mv = (2 * t + 1 < M) ? fmaxf(v_a, v_b) : ((2 * t < M) ? v_a : -INFINITY);
+      mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 1)), mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 2));
+      mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, 1)), mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, 2));
+      if (M == 9) mu = fmaxf(mu, u8), mv = fmaxf(mv, v8);
+      u_a = (u_a - mu) * L2E, u_b = (u_b - mu) * L2E, u8 = (M == 9) ? (u8 - mu) * L2E : 0.f;
+      v_a = (v_a - mv) * L2E, v_b = (v_b - mv) * L2E, v8 = (M == 9) ? (v8 - mv) * L2E : 0.f;
+      if (2 * t >= M) u_a = 0.f, v_a = 0.f;
+      if (2 * t + 1 >= M) u_b = 0.f, v_b = 0.f;
+      if (ok) {
+        spread |= (fminf(fminf(u_a, u_b), u8) < -60.f) || (fminf(fminf(v_a, v_b), v8) < -60.f);
+        reinterpret_cast<float4*>(p.lg + r * 16)[t] = make_float4(v_a, v8, v_b, v8);   // pairs {vl'[2t], vl'[8]}, {vl'[2t+1], vl'[8]}
+        reinterpret_cast<float4*>(p.lg + (p.rows + 1 + r) * 16)[t] = make_float4(u_a, u8, u_b, u8);
+      }
+    }
   }
-}
-
-template <int OP, int LPR>
-int run_prep_rows(const PrepRowsParams& p, cudaStream_t st, const char* tag) {
-  const int64_t rows_per_block = 8 * (32 / LPR);
-  int64_t blocks = (p.rows + rows_per_block - 1) / rows_per_block;
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  prep_rows_warp_kernel<OP, LPR><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
-  FGC_LAUNCHED(tag != nullptr ? tag : "prep_rows_kernel");
-  return FGC_OK;
+  if (__any_sync(0xffffffffu, spread) && lane == 0) atomicOr(p.flag, 1u);
 }
 
 template <int OP, int LPR>
@@ -405,20 +487,29 @@ int fast_lpr(int Cin, int Ca0, int Ca, int M) {
 
 }  // namespace
 
-// rows of [xa (Ca channels, row stride lda) | xb (Cb, ldb; may be null)] -> uvx[rows + 1][2M], img[rows + 1][nunits][16]
+// rows of [xa (Ca channels, row stride lda) | xb (Cb, ldb; may be null)] -> lg[2][rows + 1][16], img[rows + 1][nunits][16];
+// *flag (zeroed by the caller) receives 1 when the consumer must re-centre its softmax
+bool prep_rows_supported(int Ca, int Cb, int M) {
+  const int Cin = Ca + Cb;
+  return (M == 8 || M == 9) && Ca % 16 == 0 && Cb % 16 == 0 && Cin >= 16 && Cin <= 128 && (Cin == 32 || Cin % 64 == 0);
+}
 int launch_prep_rows(const float* xa, int lda, int Ca, const float* xb, int ldb, int Cb, const float* u, const float* v,
                      const float* c, int M, int64_t rows, int Nimg, const unsigned* maxa, const unsigned* maxb, void* img,
-                     float* uvx, float* xunscale, cudaStream_t st, const char* tag) {
+                     float* lg, float* xunscale, unsigned* flag, cudaStream_t st, const char* tag) {
   const int Cin = Ca + Cb, nunits = (Cin + 63) / 64;
-  FGC_REQUIRE(Ca % 4 == 0 && Cb % 4 == 0 && Cin <= 128 && 2 * M <= 32 && lda % 4 == 0 && (xb == nullptr || ldb % 4 == 0),
+  FGC_REQUIRE(prep_rows_supported(Ca, Cb, M) && lda % 4 == 0 && (xb == nullptr || ldb % 4 == 0),
               "prep_rows: unsupported shape (Ca=%d Cb=%d M=%d)", Ca, Cb, M);
   FGC_REQUIRE(Nimg > 0 && rows % Nimg == 0, "prep_rows: rows must be a multiple of the rows per batch element");
-  PrepRowsParams p{xa, xb, u, v, c, maxa, maxb, static_cast<uint4*>(img), uvx, xunscale, rows, lda, Ca, ldb, Cb, M, nunits, Nimg};
-  if (Cin <= 64) {
-    if (2 * M <= 16) return run_prep_rows<16, 16>(p, st, tag);
-    return run_prep_rows<32, 16>(p, st, tag);
-  }
-  return run_prep_rows<32, 32>(p, st, tag);
+  PrepRowsParams p{xa, xb, u, v, c, maxa, maxb, static_cast<uint4*>(img), lg, xunscale, flag, rows, lda, Ca, ldb, Cb, M, nunits, Nimg};
+  const int64_t nblk = (rows + 15) / 16;
+  int64_t blocks = (nblk + kPrepWarps - 1) / kPrepWarps;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = static_cast<size_t>(Cin / 16) * 3 * 32 * 16;
+  prep_rows_mma_kernel<<<static_cast<unsigned>(blocks), kPrepWarps * 32, smem, st>>>(p);
+  FGC_LAUNCHED(tag != nullptr ? tag : "prep_rows_kernel");
+  return FGC_OK;
 }
 
 #define FGC_LG_DISPATCH(FN, ...)                                              \

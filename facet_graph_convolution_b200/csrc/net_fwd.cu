@@ -47,7 +47,7 @@ ConvP conv_params(const float* const* params, int l) {
 }
 
 struct NetWs {
-  float *h1, *p1, *h2, *p2, *h3, *d3, *u2, *d2, *u1, *d1, *uvx, *xunscale;
+  float *h1, *p1, *h2, *p2, *h3, *d3, *u2, *d2, *u1, *d1, *lg, *xunscale;
   char *img, *head;
   unsigned* mx;   // [8][B] max|.| bits: 0 h1, 1 h2, 2 h3, 3 d3, 4 u2, 5 d2, 6 u1
   bool ok;
@@ -61,10 +61,10 @@ NetWs carve(void* p, size_t n, int B, int64_t R0) {
   w.p2 = ws.take<float>(R2 * 64), w.h3 = ws.take<float>(R2 * 128), w.d3 = ws.take<float>(R2 * 128);
   w.u2 = ws.take<float>(R1 * 64), w.d2 = ws.take<float>(R1 * 64), w.u1 = ws.take<float>(R0 * 32);
   w.d1 = ws.take<float>(R0 * 32);
-  w.uvx = ws.take<float>((R0 + 1) * 2 * kNetM);
+  w.lg = ws.take<float>((R0 + 1) * 32);
   w.img = ws.take<char>(static_cast<size_t>(R0 + 1) * 256);       // largest image: dconv1, R0 rows x 1 unit (= R1 x 2 x 2)
   w.xunscale = ws.take<float>(B);
-  w.mx = ws.take<unsigned>(8 * static_cast<size_t>(B));
+  w.mx = ws.take<unsigned>(8 * static_cast<size_t>(B) + 16);   // + the pre-pass's spread flag
   w.head = ws.take<char>(head_ws_bytes(R0));
   w.ok = ws.ok();
   return w;
@@ -101,9 +101,9 @@ size_t fgc_net_fwd_workspace(int B, int N0, int K) {
   const int64_t R1 = R0 / 4, R2 = R0 / 16;
   size_t n = 0;
   for (int64_t c : {R0 * 32, R1 * 32, R1 * 64, R2 * 64, R2 * 128, R2 * 128, R1 * 64, R1 * 64, R0 * 32, R0 * 32,
-                    (R0 + 1) * 2 * kNetM})
+                    (R0 + 1) * 32})
     n += ws_bytes(static_cast<size_t>(c), 4);
-  n += ws_bytes(static_cast<size_t>(R0 + 1) * 256, 1) + ws_bytes(B, 4) + ws_bytes(8 * static_cast<size_t>(B), 4) +
+  n += ws_bytes(static_cast<size_t>(R0 + 1) * 256, 1) + ws_bytes(B, 4) + ws_bytes(8 * static_cast<size_t>(B) + 16, 4) +
        ws_bytes(head_ws_bytes(R0), 1);
   return n + 1024;
 }
@@ -125,7 +125,8 @@ int fgc_net_fwd(int B, int N0, int K, const float* x, const int32_t* adj0, const
   const PreparedLayout L;
   const char* prep = static_cast<const char*>(prepared);
   const float alpha = 0.1f;   // model.py:841
-  FGC_CUDA(cudaMemsetAsync(w.mx, 0, 8 * static_cast<size_t>(B) * sizeof(unsigned), st));
+  FGC_CUDA(cudaMemsetAsync(w.mx, 0, (8 * static_cast<size_t>(B) + 16) * sizeof(unsigned), st));
+  unsigned* flag = w.mx + 8 * static_cast<size_t>(B);
   unsigned* mx[8];
   for (int i = 0; i < 8; ++i) mx[i] = w.mx + static_cast<size_t>(i) * B;
   int rc;
@@ -145,10 +146,10 @@ int fgc_net_fwd(int B, int N0, int K, const float* x, const int32_t* adj0, const
                    int64_t rows_in, int Nin, const int32_t* adj, int64_t rows, int N, int upshift, int act, float* out,
                    float* pooled, unsigned* omax) -> int {
     const ConvP p = conv_params(params, l);
-    int r = launch_prep_rows(xa, Ca, Ca, xb, Cb, Cb, p.u, p.v, p.c, kNetM, rows_in, Nin, ma, mb, w.img, w.uvx, w.xunscale, st,
-                             kPrepTag[l]);
+    int r = launch_prep_rows(xa, Ca, Ca, xb, Cb, Cb, p.u, p.v, p.c, kNetM, rows_in, Nin, ma, mb, w.img, w.lg, w.xunscale, flag,
+                             st, kPrepTag[l]);
     if (r) return r;
-    return launch_conv_hm_core(w.img, w.xunscale, w.uvx, adj, prep + L.off[l], p.b, out, pooled, omax, rows, N, K, kNetM,
+    return launch_conv_hm_core(w.img, w.xunscale, w.lg, flag, adj, prep + L.off[l], p.b, out, pooled, omax, rows, N, K, kNetM,
                                Ca + Cb, kCout[l], upshift, 1, act, alpha, st, kLayerTag[l]);
   };
   // ---- Level 1: conv2 on pool(h1); its epilogue also writes pool(h2)

@@ -98,6 +98,24 @@ def test_fused_upsampling_at_size(Cin, Cout):
     assert np.abs(y.cpu().numpy() - ref).max() < TOL_Y
 
 
+def test_extreme_logit_spread_recentres_the_softmax():
+    """logits spread over hundreds of units (the pre-pass's row-wise shifts alone would let exp2 underflow for every
+    weight at once): the kernel re-centres per (facet, neighbour) exactly like the reference's softmax."""
+    from facet_graph_convolution_b200 import ops
+    rs = np.random.RandomState(3)
+    adj = _mesh_adj(40, 28, 16, dedup=True)
+    N = adj.shape[1]
+    W0, b, u, v, c = _params(rs, 9, 64, 32)
+    u, v = (u * 60).astype(np.float32), (v * 60).astype(np.float32)
+    x = rs.randn(1, N, 64).astype(np.float32)
+    lg = np.einsum("nc,mc->nm", x[0].astype(np.float64), u.astype(np.float64))
+    assert (lg.max(1) - lg.min(1)).max() > 100          # the case really is extreme
+    y = ops.conv_fwd(T(x), T(adj), T(W0), T(b), T(u), T(v), T(c)).cpu().numpy()
+    ref = cf.conv_fwd(x, adj, W0, b, u, v, c)
+    assert np.isfinite(y).all()
+    assert np.abs(y - ref).max() < 2e-5                 # logits of magnitude ~100 carry ~1e-5 of fp32 rounding themselves
+
+
 def test_large_logit_spread_and_scale():
     """softmax with logits spread over +-60 and activations of magnitude 1e3 / 1e-3 (exact power-of-two scaling)."""
     from facet_graph_convolution_b200 import ops
