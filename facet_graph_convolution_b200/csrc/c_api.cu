@@ -240,13 +240,32 @@ static int host_reserve(int device, size_t bytes) {
   return FGC_OK;
 }
 
+// Every exit of a host-buffer entry point (error exits included) leaves no copy from / to the caller's buffers in
+// flight on the cached streams, and the caller's current device as it was.
+struct HostCallGuard {
+  int prev = -1;
+  HostCallGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      prev = -1;
+      cudaGetLastError();
+    }
+  }
+  ~HostCallGuard() {
+    if (g_hc.s_in) cudaStreamSynchronize(g_hc.s_in);
+    if (g_hc.stream) cudaStreamSynchronize(g_hc.stream);
+    if (g_hc.s_out) cudaStreamSynchronize(g_hc.s_out);
+    g_gx_ready_event = nullptr;
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 }  // namespace fgc
 
 using namespace fgc;
 
 extern "C" {
 
-int fgc_version(void) { return 100; }
+int fgc_version(void) { return 101; }
 const char* fgc_last_error(void) { return g_err; }
 uint64_t fgc_launch_count(void) { return g_launches.load(); }
 
@@ -449,6 +468,7 @@ int fgc_conv_fwd_host(const fgc_conv_shape* s, const float* x, const int32_t* ad
   const size_t ox = place(nx * 4), oadj = place(nadj * 4), oy = place(ny * 4), oW = place(nW * 4),
                ob = place(s->Cout * 4), ou = place(nu * 4), ov = place(nu * 4), oc = place(s->M * 4),
                ows = place(wsb);
+  HostCallGuard guard;
   rc = host_reserve(device, total);
   if (rc) return rc;
   char* d = g_hc.dev;
@@ -497,6 +517,7 @@ int fgc_conv_fwd_bwd_host(const fgc_conv_shape* s, const float* x, const int32_t
                orp = place((rows + 1) * 4), ore = place(nadj * 4), orw = place(wsr), owf = place(wsf),
                owb = place(wsb), opf = place(pbf), opr = place(pbr), ora = place(mma ? rows * kKrMax * 4 : 0),
                odg = place(256);
+  HostCallGuard guard;
   rc = host_reserve(device, total);
   if (rc) return rc;
   // Three streams: copies in, kernels, copies out.  The adjacency goes first (the reverse adjacency

@@ -404,29 +404,23 @@ class FacetConv(torch.nn.Module):
 
 class DenoisingNet(torch.nn.Module):
     """The reference network (model.py:837-946) as a module whose parameters are kept in the
-    reference's variable-creation order (so a TF checkpoint could be mapped onto it)."""
+    reference's variable-creation order (so a TF checkpoint could be mapped onto it).  The parameters
+    exist as soon as the module does (their shapes depend only on in_channels / multi_scale / M = 9), so
+    an optimizer, a GradBucket or load_state_dict set up before the first forward sees all of them."""
 
     def __init__(self, in_channels=6, multi_scale=False, device="cuda", params=None, seed=None):
         super().__init__()
         self.multi_scale = multi_scale
+        self.in_channels = int(in_channels)
         store = VariableStore(device=device, params=params, seed=seed)
-        # dry-run shapes on the creation order without touching the GPU kernels
+        with variable_store(store):
+            _net_variables(self.in_channels, multi_scale)      # creation order W0,b,u,c,v per conv; W,b per linear
+        self.plist = torch.nn.ParameterList([torch.nn.Parameter(t) for t in store.params])
+        store.params = list(self.plist)
         self._store = store
-        self._in_channels = in_channels
-        self._built = False
-        self.plist = torch.nn.ParameterList()
-
-    def _ensure_built(self, x, adjs):
-        if self._built:
-            return
-        with torch.no_grad(), variable_store(self._store):
-            get_model_reg_multi_scale(x, adjs, 1.0, multiScale=self.multi_scale)
-        for t in self._store.params:
-            self.plist.append(torch.nn.Parameter(t))
-        self._store.params = list(self.plist)
-        self._built = True
 
     def forward(self, x, adjs):
-        self._ensure_built(x, adjs)
+        if x.shape[-1] != self.in_channels:
+            raise ValueError("DenoisingNet built for %d input channels, got %d" % (self.in_channels, x.shape[-1]))
         with variable_store(self._store):
             return get_model_reg_multi_scale(x, adjs, 1.0, multiScale=self.multi_scale)

@@ -52,9 +52,11 @@ class GradBucket:
 
     def __init__(self, params: Sequence[torch.Tensor]):
         self.params = list(params)
+        if not self.params:
+            raise ValueError("GradBucket: empty parameter list (a step over it would update nothing)")
         self.sizes = [int(p.numel()) for p in self.params]
         self.total = sum(self.sizes)
-        dev = self.params[0].device if self.params else "cpu"
+        dev = self.params[0].device
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.views: List[torch.Tensor] = []
         o = 0
@@ -141,6 +143,38 @@ def loss_on_patch(forward, x, adjs, gt, rng: np.random.RandomState, samples: int
     return fm.faceNormalsLoss(n[:, idx, :].contiguous(), gt[:, idx, :].contiguous())
 
 
+@torch.no_grad()
+def sync_replicas(bucket: GradBucket, opt: Optional[Adam] = None, group=None, src: int = 0, check_only: bool = False):
+    """Data-parallel replicas must start identical: train_step only averages GRADIENTS, so replicas whose initial
+    parameters (unseeded random init per rank) or Adam state (a rank that resumed from a checkpoint) differ would
+    drift apart silently while every step reports a finite loss.  Broadcasts parameters, both Adam moments and the
+    step count from rank `src` (one flat buffer each); with check_only=True nothing is overwritten and a mismatch
+    raises instead.  No-op without an initialised process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([p.detach().reshape(-1) for p in bucket.params])
+    bufs = [flat] + ([opt.m, opt.v, torch.tensor([float(opt.t)], device=flat.device)] if opt is not None else [])
+    if check_only:
+        for b in bufs:
+            ref = b.clone()
+            dist.broadcast(ref, src, group=group)
+            bad = torch.tensor([0.0 if torch.equal(ref, b) else 1.0], device=flat.device)
+            dist.all_reduce(bad, group=group)
+            if float(bad.item()) > 0:
+                raise RuntimeError("data-parallel replicas differ (parameters or optimizer state): call "
+                                   "sync_replicas(bucket, opt) before the first train_step")
+        return
+    for b in bufs:
+        dist.broadcast(b, src, group=group)
+    o = 0
+    for p, n in zip(bucket.params, bucket.sizes):
+        p.copy_(flat[o:o + n].view_as(p))
+        o += n
+    if opt is not None:
+        opt.t = int(bufs[3].item())
+
+
 _STACK_CACHE = {}
 _STACK_CACHE_MAX = 16
 
@@ -194,7 +228,9 @@ def train_step(net, batch, bucket: GradBucket, opt: Adam, rng: np.random.RandomS
                samples: int = COST_SAMPLES, augment: bool = True, stack: bool = True) -> float:
     """forward + backward over this rank's `batch` of (x[1,N0,Cin], adjs, gt[1,N0,3]) patches,
     one all-reduce of the flat gradient bucket, Adam.  Returns the rank-local mean loss.
-    Equal-sized patches are stacked into one forward/backward (`stack`); ragged ones run one by one."""
+    Equal-sized patches are stacked into one forward/backward (`stack`); ragged ones run one by one.
+    Requires identical replicas (parameters and Adam state): call sync_replicas(bucket, opt) once after
+    construction / resume."""
     for p in bucket.params:
         p.grad = None
     total = 0.0

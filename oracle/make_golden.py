@@ -322,6 +322,50 @@ def c1_cases(ref):
         print("wrote", tag, os.path.getsize(os.path.join(OUT, tag + ".npz")) // 1024, "KiB")
 
 
+def c4_grad_case(ref):
+    """BASELINE config C4's unit of work at its real size: ONE 8 192-node patch (2 048 / 512 nodes at the coarser
+    levels, K = 16, Wang-et-al-shaped: a noisy height-field patch with its binary-tree pyramid), loss =
+    faceNormalsLoss(normalizeTensor(net(x)), gt) as Code/train.py:493-517 builds it, gradient of every one of the
+    474 199 parameters by torch autograd THROUGH THE REFERENCE SOURCE (Code/model.py / utils.py / train.py over the
+    stand-in).  Weights RandomState(99) in creation order (not stored)."""
+    from facet_graph_convolution_b200 import patches
+    K = 16
+    pl, _ = patches.grid_patches(64, 64, block=64, halo=0, K=K, seed=5)     # 64 x 64 quads = 8 192 facets, one patch
+    p = pl[0]
+    assert p.x.shape[0] == 8192
+    x = p.x[None].astype(np.float32)
+    adjs = [a[None].astype(np.int32) for a in p.adjs]
+    rs = np.random.RandomState(17)
+    gt = x[:, :, :3] + 0.2 * rs.randn(1, 8192, 3).astype(np.float32)          # "clean" normals near the noisy ones
+    gt /= np.linalg.norm(gt, axis=-1, keepdims=True)
+    gt[0, 100:110] = 0                                                        # rows the loss must ignore (fake nodes)
+    holder = []
+    prov = rr.rng_provider(99)
+
+    def provider(shape, stddev, nm):
+        t = T(prov(shape, stddev, nm)).requires_grad_(True)
+        holder.append(t)
+        return t
+
+    ref.tf.variables.reset(provider)
+    with contextlib.redirect_stdout(io.StringIO()):
+        yt = ref.model.get_model_reg_multi_scale(T(x), [T(a) for a in adjs], 1.0)
+    loss = ref.train.faceNormalsLoss(ref.utils.normalizeTensor(yt), T(gt))
+    loss.backward()
+    d = dict(x=x, gt=gt, loss=np.float32(loss.item()), y=yt.detach().numpy(), nparams=np.int32(len(holder)),
+             pshape=np.array([list(t.shape) + [0] * (3 - t.dim()) for t in holder], np.int32),
+             pstd=np.array([0.01 if (t.dim() == 1 and i % 5 == 1 and i < 40) or (i >= 40 and t.dim() == 1) else 0.05
+                            for i, t in enumerate(holder)], np.float64))
+    chk = np.random.RandomState(99)
+    for i, t in enumerate(holder):
+        assert np.array_equal(chk.normal(0.0, d["pstd"][i], size=tuple(t.shape)).astype(np.float32), t.detach().numpy()), i
+        d["g%02d" % i] = t.grad.numpy()
+    for l in range(3):
+        d["adj%d" % l] = _pack_adj(adjs[l])
+    np.savez_compressed(os.path.join(OUT, "c4_grad_8192.npz"), **d)
+    print("wrote c4_grad_8192 loss", loss.item(), os.path.getsize(os.path.join(OUT, "c4_grad_8192.npz")) // 1024, "KiB")
+
+
 def index_cases(ref):
     """Index layouts of the reference's host builders on small meshes (bit-exact targets)."""
     d = {}
@@ -523,6 +567,7 @@ def main():
     patch_cases(ref)
     patch_vertex_cases(ref)
     c1_cases(ref)
+    c4_grad_case(ref)
 
 
 if __name__ == "__main__":

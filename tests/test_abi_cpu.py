@@ -61,16 +61,20 @@ def test_product_package_never_imports_oracle():
 
 
 def test_reference_arm_of_bench_runs_on_cpu():
-    """`bench.py --impl reference` (the CPU arm the driver times beside the B200 arm) needs no GPU: one bounded
-    step of the reference-order port, one JSON line with the contract's keys."""
+    """`bench.py --impl reference` (the CPU arm the driver times beside the B200 arm) needs no GPU: bounded steps
+    of the oracle port of the reference network on one patch of the C3 mesh (default), or of the reference-order
+    layer port (--config c2); one JSON line with the contract's keys."""
     import json
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "1", "--cpu-sample", "2000"], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-2000:]
-    line = json.loads(r.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["metric"] == "facets/sec" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
-    assert line["e2e"] == {"value": line["value"], "unit": "facets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["gpu_launches"] == 0
+    for extra, metric in ((["--grid", "200", "--block", "40"], "facets/sec (denoise inference, fp32)"),
+                          (["--config", "c2", "--cpu-sample", "2000"], "facets/sec")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                            "--warmup", "1"] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["metric"] == metric and line["value"] > 0
+        assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+        assert line["e2e"] == {"value": line["value"], "unit": "facets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert line["gpu_launches"] == 0
+        assert "workload" in line["config"]

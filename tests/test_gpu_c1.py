@@ -71,3 +71,30 @@ def test_c1_inference_matches_reference(name):
     xo = fm.update_position2(T(g["V"][None].astype(np.float32)), T(pred[None].astype(np.float32)), e_map_d[None],
                              v_e_d[None], iter_num=60, max_edges=20)
     assert np.abs(xo.cpu().numpy()[0] - g["verts_out"]).max() < 1e-4
+
+
+def test_c4_training_gradient_matches_reference_at_patch_size():
+    """BASELINE config C4's unit of work at its real size (one 8 192-node patch, K = 16): d loss / d parameter for
+    all 474 199 parameters against torch autograd THROUGH THE REFERENCE SOURCE (c4_grad_8192.npz, written by
+    oracle/make_golden.py::c4_grad_case).  Tolerance: 1e-4 of each tensor's largest gradient entry."""
+    from facet_graph_convolution_b200 import model as fm
+    g = golden("c4_grad_8192")
+    rs = np.random.RandomState(99)
+    params = [rs.normal(0.0, float(std), size=tuple(int(v) for v in shp if v > 0)).astype(np.float32)
+              for shp, std in zip(g["pshape"], g["pstd"])]
+    store = fm.VariableStore("cuda:0", params=params, requires_grad=True)
+    adjs = [T(g["adj%d" % l].astype(np.int32)) for l in range(3)]
+    with fm.variable_store(store):
+        y = fm.get_model_reg_multi_scale(T(g["x"]), adjs, 1.0)
+    assert np.abs(y.detach().cpu().numpy() - g["y"]).max() < 1e-5
+    loss = fm.faceNormalsLoss(fm.normalizeTensor(y), T(g["gt"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-3          # degrees
+    loss.backward()
+    worst = 0.0
+    for i, t in enumerate(store.params):
+        ref = g["g%02d" % i]
+        scale = max(float(np.abs(ref).max()), 1e-6)
+        assert t.grad is not None, i
+        err = float(np.abs(t.grad.cpu().numpy() - ref).max()) / scale
+        worst = max(worst, err)
+        assert err < 1e-4, (i, store.names[i], err)

@@ -271,4 +271,5 @@ def test_multi_scale_pipeline_from_raw_mesh():
                                     T(d["v_faces"][None].astype(np.int32)), 2,
                                     iter_num_list=[int(i) for i in g["iters"]])
     assert len(dxl) == 3
-    assert np.abs(xo.cpu().numpy() - g["verts_out"]).max() < 5e-4
+    err = np.abs(xo.cpu().numpy() - g["verts_out"]).max()
+    assert err < 1e-4, err      # north_star: vertex positions max-abs <= 1e-4

@@ -11,6 +11,15 @@ from oracle import closed_form as cf
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _keep_every_tile_plan(monkeypatch):
+    """These tests exercise the planned kernels on adjacencies (random ids) whose plans production code would
+    drop; the threshold is lifted for the duration of ONE test and restored afterwards (monkeypatch), so the
+    setting cannot leak into other test modules of the session."""
+    from facet_graph_convolution_b200 import ops
+    monkeypatch.setattr(ops.ConvPlan, "MAX_MEAN_ROWS", 1e9)
+
+
 def dev():
     return torch.device("cuda:0")
 
@@ -82,7 +91,6 @@ def _cases():
 
 def test_tile_plan_is_bit_exact():
     from facet_graph_convolution_b200 import ops
-    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
     for name, x, adj in _cases():
         B, N, K = adj.shape
         plan = ops.ConvPlan(T(adj), 8)
@@ -118,7 +126,6 @@ def test_tile_plan_is_bit_exact():
 @pytest.mark.parametrize("bias_mask,act", [(True, 0), (False, 0), (True, 1)])
 def test_planned_forward_matches_oracle(bias_mask, act):
     from facet_graph_convolution_b200 import ops
-    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
     rs = np.random.RandomState(1)
     for name, x, adj in _cases():
         W0, b, u, v, c = _params(rs)
@@ -132,7 +139,6 @@ def test_planned_forward_matches_oracle(bias_mask, act):
 
 def test_planned_backward_matches_oracle_and_is_reproducible():
     from facet_graph_convolution_b200 import ops
-    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
     rs = np.random.RandomState(2)
     for name, x, adj in _cases():
         W0, b, u, v, c = _params(rs)
@@ -154,7 +160,6 @@ def test_planned_backward_matches_oracle_and_is_reproducible():
 def test_backward_with_saved_forward_products_is_bit_identical():
     """conv_bwd(saved=...) reuses the forward's logits and fp16 image of x: same bits as recomputing."""
     from facet_graph_convolution_b200 import ops
-    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
     rs = np.random.RandomState(3)
     for name, x, adj in _cases():
         W0, b, u, v, c = _params(rs)
@@ -277,7 +282,6 @@ np.savez(%r, **res)
     env = dict(os.environ, FGC_DISABLE_TMA="1")
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
     ref = np.load(out)
-    ops.ConvPlan.MAX_MEAN_ROWS = 1e9
     rs = np.random.RandomState(9)
     for name, x, adj in _cases():
         W0, b, u, v, c = _params(rs)

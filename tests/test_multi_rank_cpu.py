@@ -211,3 +211,61 @@ def test_world2_inference_on_patches_cut_by_the_reference_patch_loop():
         assert pr.exitcode == 0
     for _, pred in res:
         assert np.abs(pred - single).max() < 1e-6
+
+
+def _sync_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                     # unseeded-init stand-in: every rank draws its own weights
+        params = [torch.randn(5, 3), torch.randn(4)]
+        b = T.GradBucket(params)
+        opt = T.Adam(b)
+        opt.m.fill_(float(rank)), opt.v.fill_(float(rank) + 1)
+        opt.t = 7 * rank
+        caught = False
+        try:
+            T.sync_replicas(b, opt, check_only=True)      # replicas differ: must raise on every rank
+        except RuntimeError:
+            caught = True
+        T.sync_replicas(b, opt)                           # broadcast from rank 0
+        T.sync_replicas(b, opt, check_only=True)          # now identical: must not raise
+        q.put((rank, caught, [p.clone().numpy() for p in params], opt.m.clone().numpy(), opt.v.clone().numpy(), opt.t))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_replicas_are_synchronised_before_training():
+    """train_step only averages gradients; differing initial parameters / Adam state must be caught
+    (check_only) and repaired (broadcast from rank 0)."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    assert res[0][1] and res[1][1]
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a, b)
+    torch.manual_seed(100)
+    assert np.array_equal(res[1][2][0], torch.randn(5, 3).numpy())      # rank 0's draw won
+    assert np.array_equal(res[0][3], res[1][3]) and np.array_equal(res[0][4], res[1][4])
+    assert res[0][5] == res[1][5] == 0
+
+
+def test_grad_bucket_rejects_an_empty_parameter_list_and_the_network_has_its_parameters_at_construction():
+    with pytest.raises(ValueError):
+        T.GradBucket([])
+    from facet_graph_convolution_b200 import model as fm
+    net = fm.DenoisingNet(device="cpu", seed=0)           # no forward has run
+    ps = list(net.parameters())
+    assert len(ps) == 44 and sum(p.numel() for p in ps) == 474199
+    assert tuple(ps[0].shape) == (9, 32, 6) and tuple(ps[-2].shape) == (1024, 3)
+    ms = fm.DenoisingNet(device="cpu", seed=0, multi_scale=True)
+    assert sum(p.numel() for p in ms.parameters()) == 679005
+    T.GradBucket(ps)                                      # an optimizer can be set up before the first forward
