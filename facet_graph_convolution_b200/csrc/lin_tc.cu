@@ -2,16 +2,20 @@
 // (reference Code/model.py:936-941 through custom_lin :763-769; 72 KFLOP per facet, the largest single FLOP
 // item of the network).  The 1024-wide hidden activation never leaves the SM.
 //
-// One persistent CTA per SM, tiles of 128 rows, 9 warps:
-//   warps 4-7  producers: thread = row.  The row is scaled by its own power of two (the scale is a per-lane
+// One persistent CTA per SM, tiles of 128 rows, 13 warps:
+//   warps 8-11 producers: thread = row.  The row is scaled by its own power of two (the scale is a per-lane
 //              factor of the accumulator, undone in the epilogue) and split into fp16 hi + fp16 residual,
 //              written as the K-major 128B-swizzled A operand (K = 32: the first 64 bytes of every row).
-//   warp  8    MMA issuer: per tile and chunk of 256 hidden units  D[128 x 256] = Ah.Bh + Al.Bh + Ah.Bl
+//   warp  12   MMA issuer: per tile and chunk of 256 hidden units  D[128 x 256] = Ah.Bh + Al.Bh + Ah.Bl
 //              (tcgen05.mma kind::f16, M = 128, N = 256, two k-steps each; fp32 accumulation in TMEM).
 //              B = the resident fp16 hi/lo image of W1^T (512 hidden units per launch: 128 KB of shared memory).
-//   warps 0-3  epilogue: tcgen05.ld of the chunk, h = lrelu(scale * d + b1), three FMAs per hidden unit
-//              into the row's outputs; the two chunk accumulators ping-pong, so the MMAs of the next tile run
-//              under the epilogue of this one.
+//   warps 0-7  epilogue: two warps per TMEM lane quadrant, each takes half of a chunk's columns: tcgen05.ld,
+//              h = lrelu(scale * d + b1) and the three output FMAs on PAIRS of hidden units (packed fp32x2
+//              FMAs; parameters staged as pair records, two 16-byte shared loads per pair); the partner warp's
+//              partial sums cross through shared memory, always added in the same order.  The two chunk
+//              accumulators ping-pong, so the MMAs of the next tile run under the epilogue of this one.
+//              (With four thread-per-row epilogue warps and scalar FMAs the epilogue was the whole kernel:
+//              ~8 instructions per hidden unit and row, 1.24 ms per 2.25 M rows against a 0.19 ms MMA floor.)
 // The 1024 hidden units are two launches of 512 (the weight image of all 1024 does not fit shared memory):
 // the first writes y = b2 + partial, the second adds its partial.
 #include "conv_common.cuh"
@@ -27,16 +31,20 @@ constexpr int kHH = 1024;        // hidden units
 constexpr int kHPass = 512;      // hidden units per launch
 constexpr int kHChunk = 256;     // hidden units per MMA (N)
 constexpr int kHTile = 128;      // rows per tile
-constexpr int kHThreads = 9 * 32;
+constexpr int kHThreads = 13 * 32;
+constexpr int kHEpi = 8;         // epilogue warps
+constexpr int kHProd0 = 8;       // first producer warp
+constexpr int kHIssuer = 12;
 
 struct HeadCfg {
   static constexpr int B_PLANE = kHPass * 128;             // [512 rows = hidden units][64 K halves], 32 used
   static constexpr int A_PLANE = kHTile * 128;
   static constexpr int OFF_B = 0;                          // hi | lo
   static constexpr int OFF_A = OFF_B + 2 * B_PLANE;        // 2 buffers x (hi | lo)
-  static constexpr int OFF_PRM = OFF_A + 4 * A_PLANE;      // [512] float4 (b1, W2[.,0], W2[.,1], W2[.,2])
+  static constexpr int OFF_PRM = OFF_A + 4 * A_PLANE;      // [256 pairs] {b1 i, b1 i+1, W2[i,0], W2[i+1,0]} {W2[.,1] pair, W2[.,2] pair}
   static constexpr int OFF_RS = OFF_PRM + kHPass * 16;     // [4][128] row un-scales
-  static constexpr int OFF_BAR = OFF_RS + 4 * kHTile * 4;
+  static constexpr int OFF_EX = OFF_RS + 4 * kHTile * 4;   // [2][128] float4: partial sums of the second warp of a quadrant
+  static constexpr int OFF_BAR = OFF_EX + 2 * kHTile * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 256;
 };
 static_assert(HeadCfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
@@ -69,19 +77,22 @@ mlp_head_tc_kernel(const HeadParams p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&bars[H_A_FULL + i], 4), tc::mbar_init(&bars[H_A_FREE + i], 1);
-      tc::mbar_init(&bars[H_D_FULL + i], 1), tc::mbar_init(&bars[H_D_FREE + i], 4);
+      tc::mbar_init(&bars[H_D_FULL + i], 1), tc::mbar_init(&bars[H_D_FREE + i], kHEpi);
     }
     tc::mbar_fence_init();
   }
-  if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == kHIssuer) tc::tmem_alloc(tmem_slot, 512);
   {
     uint4* dst = reinterpret_cast<uint4*>(smem + Cfg::OFF_B);
     for (int i = threadIdx.x; i < 2 * Cfg::B_PLANE / 16; i += kHThreads) dst[i] = __ldg(p.wimg + i);
     // rows of A beyond K = 32 are never read; zero them once so that no NaN pattern sits in the operand
     uint4* az = reinterpret_cast<uint4*>(smem + Cfg::OFF_A);
     for (int i = threadIdx.x; i < 4 * Cfg::A_PLANE / 16; i += kHThreads) az[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < kHPass; i += kHThreads)
-      prm[i] = make_float4(__ldg(p.b1 + i), __ldg(p.W2 + 3 * i), __ldg(p.W2 + 3 * i + 1), __ldg(p.W2 + 3 * i + 2));
+    for (int i = threadIdx.x; i < kHPass / 2; i += kHThreads) {   // pair records of hidden units 2i, 2i+1
+      const int h0 = 2 * i, h1 = 2 * i + 1;
+      prm[2 * i] = make_float4(__ldg(p.b1 + h0), __ldg(p.b1 + h1), __ldg(p.W2 + 3 * h0), __ldg(p.W2 + 3 * h1));
+      prm[2 * i + 1] = make_float4(__ldg(p.W2 + 3 * h0 + 1), __ldg(p.W2 + 3 * h1 + 1), __ldg(p.W2 + 3 * h0 + 2), __ldg(p.W2 + 3 * h1 + 2));
+    }
     tc::fence_proxy_async_smem();
   }
   tc::tc_fence_before_sync();
@@ -89,50 +100,75 @@ mlp_head_tc_kernel(const HeadParams p) {
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kHEpi) {
     // =========================================================== epilogue
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    const int row = warp * 32 + lane;
+    const int q = warp & 3, half = warp >> 2;            // TMEM lane quadrant, column half of every chunk
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int row = q * 32 + lane;
     const float wun = __ldg(p.wunscale);
     const float b20 = __ldg(p.b2), b21 = __ldg(p.b2 + 1), b22 = __ldg(p.b2 + 2);
+    const float2 al2 = make_float2(p.alpha, p.alpha);
+    const bool fast_act = p.alpha >= 0.f && p.alpha <= 1.f;   // lrelu(h) = max(h, alpha h)
+    float4* ex = reinterpret_cast<float4*>(smem + Cfg::OFF_EX);
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-      float sc = 0.f;
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+      float2 sc2 = a0;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         tc::mbar_wait(&bars[H_D_FULL + c], t & 1);
         tc::tc_fence_after_sync();
-        if (c == 0) sc = rs[(t & 3) * kHTile + row] * wun;
+        if (c == 0) {
+          const float sc = rs[(t & 3) * kHTile + row] * wun;
+          sc2 = make_float2(sc, sc);
+        }
 #pragma unroll 1
-        for (int j = 0; j < kHChunk / 32; ++j) {
+        for (int j = 0; j < kHChunk / 64; ++j) {
+          const int col0 = half * (kHChunk / 2) + j * 32;          // first hidden unit of this load inside the chunk
           uint32_t d[32];
-          tc::tmem_ld32(tmem + lane_base + c * kHChunk + j * 32, d);
+          tc::tmem_ld32(tmem + lane_base + c * kHChunk + col0, d);
           tc::tc_wait_ld();
-          if (j == kHChunk / 32 - 1) {
+          if (j == kHChunk / 64 - 1) {
             tc::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bars[H_D_FREE + c]);
           }
-          const float4* pp = prm + c * kHChunk + j * 32;
+          const float4* pp = prm + (c * kHChunk + col0);           // two float4 per pair of hidden units
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float4 q = pp[i];
-            const float h = lrelu_f(fmaf(__uint_as_float(d[i]), sc, q.x), p.alpha);
-            a0 = fmaf(h, q.y, a0), a1 = fmaf(h, q.z, a1), a2 = fmaf(h, q.w, a2);
+          for (int i = 0; i < 16; ++i) {
+            const float4 r0 = pp[2 * i], r1 = pp[2 * i + 1];
+            float2 h = make_float2(r0.x, r0.y);                     // b1 pair
+            tc::ffma2(h, make_float2(__uint_as_float(d[2 * i]), __uint_as_float(d[2 * i + 1])), sc2);
+            if (fast_act) {
+              float2 ah = make_float2(0.f, 0.f);
+              tc::ffma2(ah, h, al2);
+              h.x = fmaxf(h.x, ah.x), h.y = fmaxf(h.y, ah.y);
+            } else {
+              h.x = lrelu_f(h.x, p.alpha), h.y = lrelu_f(h.y, p.alpha);
+            }
+            tc::ffma2(a0, h, make_float2(r0.z, r0.w));
+            tc::ffma2(a1, h, make_float2(r1.x, r1.y));
+            tc::ffma2(a2, h, make_float2(r1.z, r1.w));
           }
         }
       }
-      const int64_t r = tile * kHTile + row;
-      if (r < p.rows) {
-        float* yr = p.y + 3 * r;
-        if (p.accumulate) yr[0] += a0, yr[1] += a1, yr[2] += a2;
-        else yr[0] = a0 + b20, yr[1] = a1 + b21, yr[2] = a2 + b22;
+      const float s0 = a0.x + a0.y, s1 = a1.x + a1.y, s2 = a2.x + a2.y;
+      // the second warp of the quadrant hands its partial sums to the first (fixed order of addition)
+      if (half == 1) ex[(t & 1) * kHTile + row] = make_float4(s0, s1, s2, 0.f);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      if (half == 0) {
+        const float4 o = ex[(t & 1) * kHTile + row];
+        const int64_t r = tile * kHTile + row;
+        if (r < p.rows) {
+          float* yr = p.y + 3 * r;
+          if (p.accumulate) yr[0] += s0 + o.x, yr[1] += s1 + o.y, yr[2] += s2 + o.z;
+          else yr[0] = (s0 + o.x) + b20, yr[1] = (s1 + o.y) + b21, yr[2] = (s2 + o.z) + b22;
+        }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < kHIssuer) {
     // =========================================================== producers: thread = row
-    const int row = (warp - 4) * 32 + lane;
+    const int row = (warp - kHProd0) * 32 + lane;
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
       const int b = t & 1;
@@ -206,7 +242,7 @@ mlp_head_tc_kernel(const HeadParams p) {
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+  if (warp == kHIssuer) tc::tmem_dealloc(tmem, 512);
 }
 
 // image of W1^T for both passes: pass p, plane (hi, lo): [512 hidden units][128 B], K-major, 128B swizzle;
