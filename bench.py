@@ -471,8 +471,8 @@ def run_c3(args):
     npatch = ((grid + block - 1) // block) ** 2
     workload = ("C3 denoise inference: multi-scale network (8 facet-graph convs, M=%d, K=%d, 474199 params) + normalizeTensor "
                 "on a %dx%d-quad height field = %d facets in %d patches of %dx%d quads + 3-quad halo, patches dealt to "
-                "%d GPU(s), no collective, %d patches per launch" % (NET_M, NET_K, grid, grid, 2 * grid * grid, npatch,
-                                                                   block, block, world, PB))
+                "%d GPU(s), no collective, <= %d patches per launch" % (NET_M, NET_K, grid, grid, 2 * grid * grid, npatch,
+                                                                      block, block, world, PB))
     config = {"workload": workload, "facets": 2 * grid * grid, "patches": npatch, "K": NET_K, "M": NET_M,
               "parallelism": "patch-sharded x%d (no data-path collective)" % world,
               "l2": "patch tensors of one pass (x + 3 adjacency levels, ~240 MB per 2 M facets) exceed the 126 MB L2; "
@@ -521,12 +521,24 @@ def run_c3(args):
     mine, num_faces = make_c3_patches(grid, block, plan[rank])
     t_gen = time.perf_counter() - t0
     store = fm.VariableStore(dev, params=net_params())
+    def stack(groups):
+        out = []
+        for g in groups:
+            xb, ab = patches.batch_patches(mine, g)
+            out.append((torch.from_numpy(xb).pin_memory(), [torch.from_numpy(a).pin_memory() for a in ab],
+                        torch.tensor([mine[i].x.shape[0] for i in g], dtype=torch.int32).pin_memory()))
+        return out
+
+    # launch groups of <= PB patches
     groups = [list(range(i, min(i + PB, len(mine)))) for i in range(0, len(mine), PB)]
-    host = []
-    for g in groups:
-        xb, ab = patches.batch_patches(mine, g)
-        host.append((torch.from_numpy(xb).pin_memory(), [torch.from_numpy(a).pin_memory() for a in ab],
-                     torch.tensor([mine[i].x.shape[0] for i in g], dtype=torch.int32).pin_memory()))
+    host = stack(groups)
+    # the end-to-end pass wants at least two groups per rank, so that group i+1 uploads under the forward of group i
+    # (8 ranks: 12-13 patches each -> 7 + 6); the device-resident pass keeps the larger, more efficient launches
+    if len(groups) >= 2 or len(mine) < 2:
+        host_e2e = host
+    else:
+        per = (len(mine) + 1) // 2
+        host_e2e = stack([list(range(i, min(i + per, len(mine)))) for i in range(0, len(mine), per)])
     resident = [(x.to(dev), [a.to(dev) for a in adjs], ns.to(dev)) for x, adjs, ns in host]
     core = sum(int(p.core.sum()) for p in mine)
     rows0 = sum(int(x.shape[0] * x.shape[1]) for x, _, _ in host)     # level-0 rows launched per pass (halo + padding incl.)
@@ -616,9 +628,9 @@ def run_c3(args):
     # ---- end to end: pinned HOST patch tensors in, pinned host normals out, uploads of batch i+1 under batch i
     e2e = None
     if not args.no_e2e:
-        outs = [torch.empty(x.shape[0], x.shape[1], 3).pin_memory() for x, _, _ in host]
+        outs = [torch.empty(x.shape[0], x.shape[1], 3).pin_memory() for x, _, _ in host_e2e]
         copy_s = torch.cuda.Stream()
-        h2d = sum(x.numel() * 4 + sum(a.numel() * 4 for a in adjs) + ns.numel() * 4 for x, adjs, ns in host)
+        h2d = sum(x.numel() * 4 + sum(a.numel() * 4 for a in adjs) + ns.numel() * 4 for x, adjs, ns in host_e2e)
         d2h = sum(o.numel() * 4 for o in outs)
 
         def e2e_pass():
@@ -627,16 +639,16 @@ def run_c3(args):
 
             def upload(i):
                 with torch.cuda.stream(copy_s):
-                    x, adjs, ns = host[i]
+                    x, adjs, ns = host_e2e[i]
                     t = (x.to(dev, non_blocking=True), [a.to(dev, non_blocking=True) for a in adjs], ns.to(dev, non_blocking=True))
                     ev = torch.cuda.Event()
                     ev.record(copy_s)
                 return t, ev
 
             staged = upload(0)
-            for i in range(len(host)):
+            for i in range(len(host_e2e)):
                 (xd, ad, nd), ev = staged
-                if i + 1 < len(host):
+                if i + 1 < len(host_e2e):
                     staged = upload(i + 1)
                 cur.wait_event(ev)
                 yn = fwd(xd, ad, nd)

@@ -264,18 +264,21 @@ conv_hm_kernel(const HmParams p) {
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
-    // weight operand -> TMEM: lane 32 warp + l of the image is TMEM lane 32 warp + l, column = K pair
-    const uint32_t* src = p.wt + static_cast<size_t>(warp * 32 + lane) * Cfg::W_COLS;
+  {
+    // weight operand -> TMEM: lane 32 q + l of the image is TMEM lane 32 q + l, column = K pair.  A warp reaches the
+    // TMEM lanes of quadrant warp % 4 only; the five warps of a quadrant share its 32-column chunks (a launch over a
+    // few patches is short enough for this prologue -- 147 KB per CTA -- to show when four warps do it alone)
+    const int q = warp & 3;
+    const uint32_t* src = p.wt + static_cast<size_t>(q * 32 + lane) * Cfg::W_COLS;
 #pragma unroll 1
-    for (int c0 = 0; c0 < Cfg::W_COLS; c0 += 32) {
+    for (int c0 = (warp >> 2) * 32; c0 < Cfg::W_COLS; c0 += (kHThreads / 128) * 32) {
       uint32_t r[32];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const uint4 tq = __ldg(reinterpret_cast<const uint4*>(src + c0) + u);
         r[4 * u] = tq.x, r[4 * u + 1] = tq.y, r[4 * u + 2] = tq.z, r[4 * u + 3] = tq.w;
       }
-      tc::tmem_st32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+      tc::tmem_st32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
     }
     tc::tc_wait_st();
     tc::tc_fence_before_sync();
