@@ -26,6 +26,7 @@
 #include <stdlib.h>
 
 #include "tc_common.cuh"
+#include <type_traits>
 
 namespace fgc {
 
@@ -234,6 +235,120 @@ __device__ __forceinline__ void hm_drain(uint8_t* b3, int f, int g, int t, const
   }
 }
 
+// epilogue warp `warp` (TMEM lane quadrant `warp`): Y (TMEM) -> global, every tile of this CTA
+struct HmNoHook {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+// `before_tile(it)` runs ahead of the epilogue of the CTA's tile number it (the second-generation kernel issues stage 2 there)
+template <class Cfg, int BAR_FULL, int BAR_FREE, class Hook = HmNoHook>
+__device__ __forceinline__ void hm_epilogue(const HmParams& p, uint64_t* bars, const float* rowinv, uint32_t tmem, int warp,
+                                            int lane, Hook before_tile = Hook()) {
+  const int q = warp;
+  const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+  // lane 16h + i of quadrant q: h = 0 holds Wh.(Sh|Sl) of channel o = 16q + i, h = 1 holds Wl.Sh.
+  // After one shuffle round lane (h, i) owns facets 16h .. 16h+15 of channel o.
+  const int hh = lane >> 4, o = q * 16 + (lane & 15);
+  const float bo = p.add_bias ? __ldg(p.b + o) : 0.f;
+  const float wun = __ldg(p.wunscale);
+  const bool unmasked = !p.bias_mask;
+  const bool aligned = (p.N & 15) == 0;   // a lane's 16 rows lie in one batch element
+  int it = 0;
+
+  for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    before_tile(it);
+    const int buf = it & 1;
+    const int64_t r0 = tile * kHT + 16 * hh;
+    int64_t left = p.rows - r0;
+    const int nv = left >= 16 ? 16 : (left < 0 ? 0 : static_cast<int>(left));
+    tc::mbar_wait_relaxed(&bars[BAR_FULL + buf], (it >> 1) & 1);
+    tc::tc_fence_after_sync();
+    uint32_t d0[32], d1[32];
+    tc::tmem_ld32(tmem + lane_base + Cfg::D_COL + buf * Cfg::ND, d0);        // . Sh of facets 0..31
+    tc::tmem_ld32(tmem + lane_base + Cfg::D_COL + buf * Cfg::ND + 32, d1);   // . Sl
+    float inv[16];
+    {
+      const float4* ri = reinterpret_cast<const float4*>(rowinv + (it & 3) * kHT + 16 * hh);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = ri[j];
+        inv[4 * j] = v.x, inv[4 * j + 1] = v.y, inv[4 * j + 2] = v.z, inv[4 * j + 3] = v.w;
+      }
+    }
+    tc::tc_wait_ld();
+    tc::tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&bars[BAR_FREE + buf]);
+    float keep[16], send[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a_lo = __uint_as_float(d0[j]) + __uint_as_float(d1[j]);             // facets 0..15  (hi lanes)
+      const float a_up = __uint_as_float(d0[16 + j]) + __uint_as_float(d1[16 + j]);   // facets 16..31 (hi lanes)
+      const float l_lo = __uint_as_float(d0[j]) * (1.f / 2048.f);                     // facets 0..15  (lo lanes)
+      const float l_up = __uint_as_float(d0[16 + j]) * (1.f / 2048.f);                // facets 16..31 (lo lanes)
+      keep[j] = hh ? l_up : a_lo;
+      send[j] = hh ? l_lo : a_up;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) send[j] = __shfl_xor_sync(0xffffffffu, send[j], 16);
+    float yv[16];
+    float* yp = p.y + r0 * p.ldy + o;
+    float yold[16];
+    if (p.accumulate) {   // all sixteen loads in flight at once (one after the other they cost a DRAM latency each)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) yold[j] = (j < nv) ? __ldcg(yp + j * p.ldy) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) yold[j] = 0.f;
+    }
+    const int be0 = nv > 0 ? static_cast<int>(r0 / p.N) : 0;
+    const float sca = __ldg(p.xunscale + be0) * wun;
+    // rows of the next batch element start at j = cross (N >= 16: at most one boundary inside a lane's 16 rows)
+    int cross = 16;
+    float scb = sca;
+    if (!aligned && nv > 0) {
+      cross = static_cast<int>(static_cast<int64_t>(be0 + 1) * p.N - r0);
+      if (cross < nv) scb = __ldg(p.xunscale + be0 + 1) * wun;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float accv = hh ? (send[j] + keep[j]) : (keep[j] + send[j]);   // (Wh.Sh + Wh.Sl) + Wl.Sh / 2048
+      const float fl = (inv[j] > 0.f || unmasked) ? bo : 0.f;
+      float sc0 = j < cross ? sca : scb;
+      if (p.N < 16 && j > 0 && j < nv) sc0 = __ldg(p.xunscale + (r0 + j) / p.N) * wun;   // tiny elements: several boundaries
+      float v = fmaf(inv[j] * sc0, accv, fl);
+      v += yold[j];
+      if (p.apply_act && p.act == FGC_ACT_LRELU) v = lrelu_f(v, p.alpha);
+      yv[j] = v;
+    }
+    if (nv == 16) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) yp[j * p.ldy] = yv[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nv) yp[j * p.ldy] = yv[j];
+    }
+    if (p.ypool != nullptr) {
+      float* pp = p.ypool + (r0 >> 2) * p.ldp + o;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (4 * a < nv) pp[a * p.ldp] = fmaxf(fmaxf(yv[4 * a], yv[4 * a + 1]), fmaxf(yv[4 * a + 2], yv[4 * a + 3]));
+    }
+    if (p.ymax != nullptr) {
+      // max|y| per batch element: reduced over the 16 lanes that share the element, one atomic per half warp and
+      // tile (max is order-independent: the atomics keep the result deterministic; thousands of same-address
+      // atomics per launch serialise in L2 -- measured +180 us per 140 k rows when every lane issued its own)
+      float m = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nv) m = fmaxf(m, fabsf(yv[j]));
+#pragma unroll
+      for (int s = 8; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+      if ((lane & 15) == 0 && nv > 0) atomicMax(p.ymax + be0, __float_as_uint(m));
+    }
+  }
+}
+
 template <int M, int NG>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_hm_kernel(const HmParams p) {
@@ -288,111 +403,7 @@ conv_hm_kernel(const HmParams p) {
 
   if (warp < 4) {
     // =========================================================== epilogue: Y (TMEM) -> global
-    if (warp < nepi) {
-      const int q = warp;
-      const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-      // lane 16h + i of quadrant q: h = 0 holds Wh.(Sh|Sl) of channel o = 16q + i, h = 1 holds Wl.Sh.
-      // After one shuffle round lane (h, i) owns facets 16h .. 16h+15 of channel o.
-      const int hh = lane >> 4, o = q * 16 + (lane & 15);
-      const float bo = p.add_bias ? __ldg(p.b + o) : 0.f;
-      const float wun = __ldg(p.wunscale);
-      const bool unmasked = !p.bias_mask;
-      const bool aligned = (p.N & 15) == 0;   // a lane's 16 rows lie in one batch element
-      int it = 0;
-
-      for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int64_t r0 = tile * kHT + 16 * hh;
-        int64_t left = p.rows - r0;
-        const int nv = left >= 16 ? 16 : (left < 0 ? 0 : static_cast<int>(left));
-        tc::mbar_wait_relaxed(&bars[HB_D_FULL + buf], (it >> 1) & 1);
-        tc::tc_fence_after_sync();
-        uint32_t d0[32], d1[32];
-        tc::tmem_ld32(tmem + lane_base + Cfg::D_COL + buf * Cfg::ND, d0);        // . Sh of facets 0..31
-        tc::tmem_ld32(tmem + lane_base + Cfg::D_COL + buf * Cfg::ND + 32, d1);   // . Sl
-        float inv[16];
-        {
-          const float4* ri = reinterpret_cast<const float4*>(rowinv + (it & 3) * kHT + 16 * hh);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 v = ri[j];
-            inv[4 * j] = v.x, inv[4 * j + 1] = v.y, inv[4 * j + 2] = v.z, inv[4 * j + 3] = v.w;
-          }
-        }
-        tc::tc_wait_ld();
-        tc::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&bars[HB_D_FREE + buf]);
-        float keep[16], send[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a_lo = __uint_as_float(d0[j]) + __uint_as_float(d1[j]);             // facets 0..15  (hi lanes)
-          const float a_up = __uint_as_float(d0[16 + j]) + __uint_as_float(d1[16 + j]);   // facets 16..31 (hi lanes)
-          const float l_lo = __uint_as_float(d0[j]) * (1.f / 2048.f);                     // facets 0..15  (lo lanes)
-          const float l_up = __uint_as_float(d0[16 + j]) * (1.f / 2048.f);                // facets 16..31 (lo lanes)
-          keep[j] = hh ? l_up : a_lo;
-          send[j] = hh ? l_lo : a_up;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) send[j] = __shfl_xor_sync(0xffffffffu, send[j], 16);
-        float yv[16];
-        float* yp = p.y + r0 * p.ldy + o;
-        float yold[16];
-        if (p.accumulate) {   // all sixteen loads in flight at once (one after the other they cost a DRAM latency each)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) yold[j] = (j < nv) ? __ldcg(yp + j * p.ldy) : 0.f;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) yold[j] = 0.f;
-        }
-        const int be0 = nv > 0 ? static_cast<int>(r0 / p.N) : 0;
-        const float sca = __ldg(p.xunscale + be0) * wun;
-        // rows of the next batch element start at j = cross (N >= 16: at most one boundary inside a lane's 16 rows)
-        int cross = 16;
-        float scb = sca;
-        if (!aligned && nv > 0) {
-          cross = static_cast<int>(static_cast<int64_t>(be0 + 1) * p.N - r0);
-          if (cross < nv) scb = __ldg(p.xunscale + be0 + 1) * wun;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float accv = hh ? (send[j] + keep[j]) : (keep[j] + send[j]);   // (Wh.Sh + Wh.Sl) + Wl.Sh / 2048
-          const float fl = (inv[j] > 0.f || unmasked) ? bo : 0.f;
-          float sc0 = j < cross ? sca : scb;
-          if (p.N < 16 && j > 0 && j < nv) sc0 = __ldg(p.xunscale + (r0 + j) / p.N) * wun;   // tiny elements: several boundaries
-          float v = fmaf(inv[j] * sc0, accv, fl);
-          v += yold[j];
-          if (p.apply_act && p.act == FGC_ACT_LRELU) v = lrelu_f(v, p.alpha);
-          yv[j] = v;
-        }
-        if (nv == 16) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) yp[j * p.ldy] = yv[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nv) yp[j * p.ldy] = yv[j];
-        }
-        if (p.ypool != nullptr) {
-          float* pp = p.ypool + (r0 >> 2) * p.ldp + o;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-            if (4 * a < nv) pp[a * p.ldp] = fmaxf(fmaxf(yv[4 * a], yv[4 * a + 1]), fmaxf(yv[4 * a + 2], yv[4 * a + 3]));
-        }
-        if (p.ymax != nullptr) {
-          // max|y| per batch element: reduced over the 16 lanes that share the element, one atomic per half warp and
-          // tile (max is order-independent: the atomics keep the result deterministic; thousands of same-address
-          // atomics per launch serialise in L2 -- measured +180 us per 140 k rows when every lane issued its own)
-          float m = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nv) m = fmaxf(m, fabsf(yv[j]));
-#pragma unroll
-          for (int s = 8; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-          if ((lane & 15) == 0 && nv > 0) atomicMax(p.ymax + be0, __float_as_uint(m));
-        }
-      }
-    }
+    if (warp < nepi) hm_epilogue<Cfg, HB_D_FULL, HB_D_FREE>(p, bars, rowinv, tmem, warp, lane);
   } else {
     // =========================================================== aggregators (+ stage-2 issue by the last to arrive)
     // Facet n of this warp: tile counter n / kHFpw, facet n % kHFpw of the warp's own; item m = n * NG + slot group.
@@ -508,13 +519,368 @@ conv_hm_kernel(const HmParams p) {
   if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
+// =====================================================================================================================
+// Second generation of the same kernel (default; FGC_HM_V1=1 selects the one above for comparisons).
+// What changes, and why (ncu of the kernel above, profiles/r2_summary.md: 583 warp instructions and ~190 L1 data-pipe
+// wavefronts per facet at an IPC of 0.45 per sub-partition; every aggregator warp ran load -> wait -> compute -> fence):
+//   * the 16 gathered rows of a facet go global -> shared with cp.async (16-byte units, eight consecutive lanes copy one
+//     128-byte line: 4 wavefronts per instruction instead of 16) into a 4 KB per-warp stage, 128B-swizzled, and come
+//     back as B fragments with ldmatrix.x4.trans (natural channel order: no byte permutes, no register staging);
+//   * the copies of facet n+1 are issued as soon as the fragments of facet n are in registers and land under its MMAs,
+//     its drain and the softmax of facet n+1;
+//   * aggregator warps never fence: they hand a tile over with one mbarrier arrive per warp (release), a dedicated
+//     issuer warp waits (acquire), executes the generic->async proxy fence and issues stage 2 -- so copies in flight
+//     never stall a hand-over (MEMBAR waits for every outstanding memory operation of its thread);
+//   * ids are loaded once per facet (lane k < 16: slot k), row indices are computed once and spread by shuffles,
+//     the neighbour count is one ballot.
+constexpr int kH2Threads = (4 + kHAgg) * 32;         // 4 epilogue warps (warp 0 also issues stage 2) + aggregators:
+                                                     // five warps per sub-partition, 96 registers each
+constexpr int kH2StageBytes = 4096;                  // [hi: slots 0-7 | slots 8-15][lo: same], rows of 128 B
+
+template <int M>
+struct Hm2Cfg : HmCfg<M> {
+  static constexpr int OFF_STAGE = 2 * HmCfg<M>::B3_BUF;
+  static constexpr int OFF_ROW2 = OFF_STAGE + kHAgg * kH2StageBytes;
+  static constexpr int OFF_BAR2 = OFF_ROW2 + 4 * kHT * 4;
+  static constexpr int SMEM_BYTES2 = OFF_BAR2 + 512;
+};
+
+enum { H2_B3_FREE = 0, H2_D_FULL = 2, H2_D_FREE = 4, H2_B3_FULL = 6, H2_NUM = 8 };
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+}
+
+struct Hm2Pre {           // per-item inputs of the softmax
+  float2 vl[4];           // neighbour logits of weights g and 8 of this lane's four slots (2t, 2t+1, 2t+8, 2t+9)
+  float2 uo;              // own logits of weights g and 8
+  int okm;                // bit i: slot i of this lane holds a valid neighbour
+  int cnt;                // non-zero ids among the item's 16 slots
+};
+
+// soft assignments of the item in the A-fragment layout: a[0..3] = hi of rows g (a0,a2) / rows 8+ (a1,a3), a[4..7] = lo
+template <int M>
+__device__ __forceinline__ void hm2_softmax(const Hm2Pre& in, bool recentre, uint32_t (&a)[8]) {
+  float qg[4], q8[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float ag = in.uo.x + in.vl[i].x;
+    float a8 = (M == 9) ? in.uo.y + in.vl[i].y : 0.f;
+    if (recentre) {
+      float mx = (M == 9) ? fmaxf(ag, a8) : ag;
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+      ag -= mx, a8 -= mx;
+    }
+    const float eg = ex2_approx(ag);
+    const float e8 = (M == 9) ? ex2_approx(a8) : 0.f;
+    float z = eg;
+    z += __shfl_xor_sync(0xffffffffu, z, 4);
+    z += __shfl_xor_sync(0xffffffffu, z, 8);
+    z += __shfl_xor_sync(0xffffffffu, z, 16);
+    z += e8;
+    const float rs = ((in.okm >> i) & 1) ? rcp_approx(z) : 0.f;
+    qg[i] = eg * rs;
+    q8[i] = e8 * rs;
+  }
+  split_rn(qg[0], qg[1], a[0], a[4]);
+  split_rn(qg[2], qg[3], a[2], a[6]);
+  if (M == 9) {
+    split_rn(q8[0], q8[1], a[1], a[5]);
+    split_rn(q8[2], q8[3], a[3], a[7]);
+  } else {
+    a[1] = a[4], a[3] = a[6];     // rows 8..15 carry q_lo
+    a[5] = 0u, a[7] = 0u;
+  }
+}
+
+// S of facet f (C fragments, natural channel order: acc[u][j] = row g, channel 8u + 2t + j; acc[u][2 + j] = row 8+) ->
+// fp16 hi/lo rows of the stage-2 B operand.  K order of stage 2 (prep_wt_kernel writes the weights in the same order):
+// atom a = 2 (m >> 1) + h, chunk 4 (m & 1) + t, element 2 (u & 3) + j  <->  weight m, channel 8 (4 h + (u & 3)) + 2 t + j;
+// atom 8 = weight 8 in natural channel order.  The eight lanes of a quarter warp store to eight different chunks.
+template <int M>
+__device__ __forceinline__ void hm2_drain(uint8_t* b3, int f, int g, int t, const float (&acc)[8][4]) {
+  using Cfg = HmCfg<M>;
+  const int sw = f & 7;
+  uint8_t* rh = b3 + (f >> 3) * 1024 + sw * 128;              // hi row f of an atom
+  uint8_t* rl = rh + (kHT >> 3) * 1024;                       // lo row 32 + f
+  const int chunk = (((g & 1) * 4 + t) ^ sw) << 4;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v0 = acc[4 * h + j][0], v1 = acc[4 * h + j][1];
+      if (M == 8) v0 += acc[4 * h + j][2], v1 += acc[4 * h + j][3];
+      split_trunc(v0, v1, hi[j], lo[j]);
+    }
+    const int aoff = (2 * (g >> 1) + h) * Cfg::ATOM_BYTES + chunk;
+    *reinterpret_cast<uint4*>(rh + aoff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(rl + aoff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (M == 9) {
+    // row m = 8 (every lane holds a copy of its 16 channels): lane (g,t) converts channels 8g + 2t, +1
+    float e0 = acc[0][2], e1 = acc[0][3];
+#pragma unroll
+    for (int i = 1; i < 8; ++i)
+      if (g == i) e0 = acc[i][2], e1 = acc[i][3];
+    uint32_t hi, lo;
+    split_trunc(e0, e1, hi, lo);
+    const int off = 8 * Cfg::ATOM_BYTES + ((g ^ sw) << 4) + t * 4;
+    *reinterpret_cast<uint32_t*>(rh + off) = hi;
+    *reinterpret_cast<uint32_t*>(rl + off) = lo;
+  }
+}
+
+template <int M, int NG>
+__global__ void __launch_bounds__(kH2Threads, 1)
+conv_hm2_kernel(const HmParams p) {
+  using Cfg = Hm2Cfg<M>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + H2_NUM);
+  float* invtab = reinterpret_cast<float*>(tmem_slot + 2);          // [33] 1 / cnt (0 for cnt = 0)
+  float* rowinv = reinterpret_cast<float*>(smem + Cfg::OFF_ROW2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nepi = p.cout >> 4;   // epilogue warps with outputs
+  const int my_tiles = static_cast<int>((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bars[H2_B3_FREE + i], 1);
+      tc::mbar_init(&bars[H2_D_FULL + i], 1), tc::mbar_init(&bars[H2_D_FREE + i], nepi);
+      tc::mbar_init(&bars[H2_B3_FULL + i], kHAgg);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 5) invtab[lane + 1] = 1.f / static_cast<float>(lane + 1), invtab[0] = 0.f;
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  {
+    // weight operand -> TMEM: lane 32 q + l of the image is TMEM lane 32 q + l, column = K pair.  A warp reaches the
+    // TMEM lanes of quadrant warp % 4 only; five warps per quadrant share its 32-column chunks.
+    const int q = warp & 3;
+    const uint32_t* src = p.wt + static_cast<size_t>(q * 32 + lane) * Cfg::W_COLS;
+#pragma unroll 1
+    for (int c0 = (warp >> 2) * 32; c0 < Cfg::W_COLS; c0 += 5 * 32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint4 tq = __ldg(reinterpret_cast<const uint4*>(src + c0) + u);
+        r[4 * u] = tq.x, r[4 * u + 1] = tq.y, r[4 * u + 2] = tq.z, r[4 * u + 3] = tq.w;
+      }
+      tc::tmem_st32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+    }
+    tc::tc_wait_st();
+    tc::tc_fence_before_sync();
+  }
+  __syncthreads();
+  tc::tc_fence_after_sync();
+
+  if (warp < 4) {
+    // =========================================================== epilogue: Y (TMEM) -> global; warp 0 also issues stage 2
+    if (warp == 0) {
+      constexpr uint32_t idesc = (1u << 4) | ((static_cast<uint32_t>(Cfg::ND) >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t sb = tc::smem_u32(smem);
+      auto issue_stage2 = [&](int it) {
+        const int buf = it & 1;
+        const uint32_t par = (it >> 1) & 1;
+        tc::mbar_wait_relaxed(&bars[H2_B3_FULL + buf], par);   // all 16 aggregator warps have stored their rows of S
+        tc::fence_proxy_async_smem();                          // ... and the tensor core may read them
+        tc::mbar_wait(&bars[H2_D_FREE + buf], par ^ 1);
+        tc::tc_fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t b3 = sb + buf * Cfg::B3_BUF;
+#pragma unroll 1
+          for (int a = 0; a < Cfg::NATOM; ++a) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bd = tc::smem_desc_k_sw128(b3 + a * Cfg::ATOM_BYTES + ks * 32);
+              tc::mma_f16_ts(tmem + Cfg::D_COL + buf * Cfg::ND, tmem + a * 32 + ks * 8, bd, idesc, (a | ks) ? 1u : 0u);
+            }
+          }
+          tc::tc_commit(&bars[H2_B3_FREE + buf]);
+          tc::tc_commit(&bars[H2_D_FULL + buf]);
+        }
+        __syncwarp();
+      };
+      hm_epilogue<Cfg, H2_D_FULL, H2_D_FREE>(p, bars, rowinv, tmem, warp, lane, issue_stage2);
+    } else if (warp < nepi) {
+      hm_epilogue<Cfg, H2_D_FULL, H2_D_FREE>(p, bars, rowinv, tmem, warp, lane);
+    }
+  } else {
+    // =========================================================== aggregators
+    // Facet n of this warp: tile counter n / kHFpw, facet n % kHFpw of the warp's own; item m = n * NG + slot group.
+    const int aw = warp - 4;
+    const int g = lane >> 2, t = lane & 3;
+    const int nitems = my_tiles * kHFpw * NG;
+    const int rows32 = static_cast<int>(p.rows);
+    const float2* lg_v = reinterpret_cast<const float2*>(p.lg) + g;                             // neighbour pair of row j: lg_v[8 j]
+    const float2* lg_u = lg_v + static_cast<int64_t>(p.zrow + 1) * 8;                           // own pair of row r: lg_u[8 r]
+    const bool recentre = __ldg(p.flag) != 0;
+    const uint32_t stage = tc::smem_u32(smem + Cfg::OFF_STAGE + aw * kH2StageBytes);
+    // copies: this lane moves 16-byte unit cc of the rows of slots cq, cq + 4, cq + 8, cq + 12 (hi plane, then lo plane)
+    const int cq = lane >> 3, cc = lane & 7;
+    const uint32_t cdst0 = stage + cq * 128 + ((cc ^ cq) << 4);
+    const uint32_t cdst1 = stage + (cq + 4) * 128 + ((cc ^ (cq + 4)) << 4);
+    const uint4* img_c = p.img + cc;
+    // fragments: lane supplies row (lane & 7) of matrix lane >> 3 = (slots 0-7 | slots 8-15) x (unit 2 up | unit 2 up + 1)
+    const uint32_t laddr = (stage + ((lane >> 3) & 1) * 1024 + (lane & 7) * 128) | ((((lane >> 4) ^ lane) & 7) << 4);
+    auto row_of = [&](int m) -> int {   // global row of item m, -1 when there is none
+      const int n = m / NG;
+      const int r = (static_cast<int>(blockIdx.x) + (n / kHFpw) * static_cast<int>(gridDim.x)) * kHT + aw * kHFpw + (n % kHFpw);
+      return (m < nitems && r < rows32) ? r : -1;
+    };
+    auto load_id = [&](int m, int r) -> int {   // id of slot (lane & 15) of item m (row r), 0 when there is none
+      const int k = (m % NG) * 16 + (lane & 15);
+      return (r >= 0 && k < p.K) ? __ldg(p.adj + static_cast<int64_t>(r) * p.K + k) : 0;
+    };
+    int base_cur = 0, base_next = p.N;     // batch element of the rows the issue stage walks (monotone)
+    // row index of this lane's slot, validity / count bits, and the copies of the hi plane of the item's 16 rows
+    auto issue_hi = [&](int r, int id, Hm2Pre& o) -> int {
+      int base = 0;
+      if (!p.single && r >= 0) {
+        while (r >= base_next) base_cur = base_next, base_next += p.N;
+        base = base_cur;
+      }
+      const bool ok = static_cast<unsigned>(id - 1) < static_cast<unsigned>(p.N);
+      const int row = ok ? ((base + id - 1) >> p.upshift) : p.zrow;   // zrow: all-zero image / logit row
+      const unsigned okb = __ballot_sync(0xffffffffu, ok);
+      const unsigned nzb = __ballot_sync(0xffffffffu, id != 0) & 0xFFFFu;
+      o.okm = static_cast<int>(((okb >> (2 * t)) & 3u) | (((okb >> (2 * t + 8)) & 3u) << 2));
+      o.cnt = __popc(nzb);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = __shfl_sync(0xffffffffu, row, cq + 4 * i);
+        cp_async16(((i & 1) ? cdst1 : cdst0) + (i >> 1) * 1024, img_c + static_cast<int64_t>(rr) * p.img_ld);
+      }
+      cp_async_commit();
+      return row;
+    };
+    auto issue_lo = [&](int row) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = __shfl_sync(0xffffffffu, row, cq + 4 * i);
+        cp_async16(((i & 1) ? cdst1 : cdst0) + (i >> 1) * 1024 + 2048, img_c + static_cast<int64_t>(rr) * p.img_ld + 8);
+      }
+      cp_async_commit();
+    };
+    auto issue_logits = [&](int r, int row, Hm2Pre& o) {
+      o.uo = __ldg(lg_u + static_cast<int64_t>((r < 0 ? 0 : r) >> p.upshift) * 8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = __shfl_sync(0xffffffffu, row, 2 * t + (i & 1) + 8 * (i >> 1));
+        o.vl[i] = __ldg(lg_v + static_cast<int64_t>(rr) * 8);
+      }
+    };
+    float acc[8][4];
+    int cnt = 0;
+    Hm2Pre P;
+    int r1 = row_of(0);
+    int idn = load_id(0, r1);
+    {
+      const int row = issue_hi(r1, idn, P);
+      issue_lo(row);
+      issue_logits(r1, row, P);
+    }
+    r1 = row_of(1);
+    idn = load_id(1, r1);
+    // One item.  In flight while it is computed: the copies of the next item's rows (hi plane from the moment this item's
+    // hi fragments are in registers, lo plane likewise), the next item's logits (from after the MMAs) and the ids of the
+    // item after that.
+    auto step = [&](int m, auto first_c, auto last_c) {
+      constexpr bool FIRST = decltype(first_c)::value, LAST = decltype(last_c)::value;
+      uint32_t a[8];
+      hm2_softmax<M>(P, recentre, a);
+      cnt = FIRST ? P.cnt : cnt + P.cnt;
+      const bool more = m + 1 < nitems;
+      uint32_t bf[4][4];
+      asm volatile("cp.async.wait_group 1;" ::: "memory");     // hi plane of this item
+      __syncwarp();
+#pragma unroll
+      for (int up = 0; up < 4; ++up) ldsm_x4_t(laddr ^ (up << 5), bf[up]);
+      __syncwarp();
+      int row = 0;
+      if (more) row = issue_hi(r1, idn, P);       // overwrites okm / cnt of P: both consumed above
+#pragma unroll
+      for (int up = 0; up < 4; ++up) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int u = 2 * up + j;
+          if (M == 9) {
+            hm_mma<FIRST>(acc[u], a[0], a[1], a[2], a[3], bf[up][2 * j], bf[up][2 * j + 1]);
+            hm_mma<false>(acc[u], a[4], a[5], a[6], a[7], bf[up][2 * j], bf[up][2 * j + 1]);
+          } else {
+            hm_mma<FIRST>(acc[u], a[0], a[1], a[2], a[3], bf[up][2 * j], bf[up][2 * j + 1]);   // rows g: q_hi.x_hi, rows g+8: q_lo.x_hi
+          }
+        }
+      }
+      if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");   // lo plane of this item (the next hi plane may be pending)
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int up = 0; up < 4; ++up) ldsm_x4_t((laddr ^ (up << 5)) + 2048, bf[up]);
+      __syncwarp();
+      if (more) issue_lo(row);
+      const int r2 = row_of(m + 2);
+      idn = load_id(m + 2, r2);
+#pragma unroll
+      for (int up = 0; up < 4; ++up) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int u = 2 * up + j;
+          if (M == 9) hm_mma<false>(acc[u], a[0], a[1], a[2], a[3], bf[up][2 * j], bf[up][2 * j + 1]);
+          else hm_mma<false>(acc[u], a[0], 0u, a[2], 0u, bf[up][2 * j], bf[up][2 * j + 1]);
+        }
+      }
+      if (more) issue_logits(r1, row, P);
+      r1 = r2;
+      if (LAST) {
+        const int n = m / NG, it = n / kHFpw, fi = n % kHFpw, buf = it & 1, f = aw * kHFpw + fi;
+        if (fi == 0) tc::mbar_wait(&bars[H2_B3_FREE + buf], ((it >> 1) & 1) ^ 1);
+        hm2_drain<M>(smem + buf * Cfg::B3_BUF, f, g, t, acc);
+        if (lane == 0) rowinv[(it & 3) * kHT + f] = invtab[cnt];
+        if (fi == kHFpw - 1) {
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bars[H2_B3_FULL + buf]);
+        }
+      }
+    };
+#pragma unroll 1
+    for (int m = 0; m < nitems; m += NG) {
+      if (NG == 1) {
+        step(m, std::true_type{}, std::true_type{});
+      } else {
+        step(m, std::true_type{}, std::false_type{});
+        step(m + 1, std::false_type{}, std::true_type{});
+      }
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, 512);
+}
+
 // ------------------------------------------------------------------ weight image in TMEM layout
 // wt[img][lane][col]: lane 32q + 16h + i <-> row (h, o = 16q + i) of [Wh;Wl] of output block ob, column = K pair of
 // aggregation unit u; K order: atom a < 8 holds weights m = 2(a>>1), +1 and the channel units of parity a&1
 // (slot s of the atom: m = 2(a>>1) + (s>>2), unit = 2(s&3) + (a&1)), atom 8 holds m = 8.
 __global__ void __launch_bounds__(1024)
 prep_wt_kernel(const float* __restrict__ W0, uint32_t* __restrict__ wt, float* __restrict__ wunscale, int M, int Cout,
-               int Cw, int CB, int nunits) {
+               int Cw, int CB, int nunits, int v1_order) {
   __shared__ float red[32];
   const int total = M * Cout * Cw;
   float mx = 0.f;
@@ -540,8 +906,14 @@ prep_wt_kernel(const float* __restrict__ W0, uint32_t* __restrict__ wt, float* _
     for (int kk = 0; kk < 2; ++kk) {
       const int kpos = 2 * col + kk, a = kpos >> 6, s = (kpos & 63) >> 3, pos = kpos & 7;
       int m, c;
-      if (a < 8) m = 2 * (a >> 1) + (s >> 2), c = (2 * (s & 3) + (a & 1)) * 8 + pos;
-      else m = 8, c = kpos & 63;
+      if (a < 8) {
+        m = 2 * (a >> 1) + (s >> 2);
+        // second-generation kernel (hm2_drain): chunk s = 4 (m & 1) + t, element pos = 2 (u & 3) + j of atom 2 (m >> 1) + h
+        // holds channel 8 (4 h + (u & 3)) + 2 t + j; first generation: unit 2 (s & 3) + (a & 1), element pos
+        c = v1_order ? (2 * (s & 3) + (a & 1)) * 8 + pos : 8 * (4 * (a & 1) + (pos >> 1)) + 2 * (s & 3) + (pos & 1);
+      } else {
+        m = 8, c = kpos & 63;
+      }
       float v = 0.f;
       if (o < CB && ob * CB + o < Cout && u * 64 + c < Cw && m < M)
         v = W0[(static_cast<size_t>(m) * Cout + ob * CB + o) * Cw + u * 64 + c] * sc;
@@ -567,6 +939,15 @@ hm_absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// FGC_HM_V1=1: the first-generation kernel (register-staged gathers) instead of the cp.async / ldmatrix one
+bool hm_use_v1() {
+  static const bool v = [] {
+    const char* e = getenv("FGC_HM_V1");
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
 }
 
 size_t hm_img_bytes(int64_t rows_img, int nunits) { return static_cast<size_t>(rows_img) * nunits * 256; }
@@ -596,7 +977,8 @@ size_t conv_hm_weights_bytes(int Cw, int Cout, int M) {
 int launch_conv_hm_weights(const float* W0, int M, int Cout, int Cw, void* wbuf, cudaStream_t st) {
   const int nunits = (Cw + 63) / 64, CB = Cout < 64 ? Cout : 64, nob = Cout / CB;
   float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wbuf) + align_up(hm_wt_bytes(M, nunits * nob), 256));
-  prep_wt_kernel<<<dim3(4, nunits * nob), 1024, 0, st>>>(W0, static_cast<uint32_t*>(wbuf), wunscale, M, Cout, Cw, CB, nunits);
+  prep_wt_kernel<<<dim3(4, nunits * nob), 1024, 0, st>>>(W0, static_cast<uint32_t*>(wbuf), wunscale, M, Cout, Cw, CB, nunits,
+                                                                hm_use_v1() ? 1 : 0);
   FGC_LAUNCHED("prep_w_image_kernel");
   return FGC_OK;
 }
@@ -617,9 +999,14 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg,
   hp.ldy = Cout, hp.ldp = Cout, hp.rows = rows, hp.ntiles = (rows + kHT - 1) / kHT;
   hp.N = N, hp.K = K, hp.upshift = upshift, hp.bias_mask = bias_mask, hp.act = act, hp.alpha = alpha;
   hp.cout = CB, hp.single = rows == N, hp.zrow = static_cast<int>(rows_img);
-  auto kern = M == 9 ? (K <= 16 ? conv_hm_kernel<9, 1> : conv_hm_kernel<9, 2>)
-                     : (K <= 16 ? conv_hm_kernel<8, 1> : conv_hm_kernel<8, 2>);
-  const int smem = M == 9 ? HmCfg<9>::SMEM_BYTES : HmCfg<8>::SMEM_BYTES;
+  const bool v1 = hm_use_v1();
+  auto kern = v1 ? (M == 9 ? (K <= 16 ? conv_hm_kernel<9, 1> : conv_hm_kernel<9, 2>)
+                           : (K <= 16 ? conv_hm_kernel<8, 1> : conv_hm_kernel<8, 2>))
+                 : (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1> : conv_hm2_kernel<9, 2>)
+                           : (K <= 16 ? conv_hm2_kernel<8, 1> : conv_hm2_kernel<8, 2>));
+  const int smem = v1 ? (M == 9 ? HmCfg<9>::SMEM_BYTES : HmCfg<8>::SMEM_BYTES)
+                      : (M == 9 ? Hm2Cfg<9>::SMEM_BYTES2 : Hm2Cfg<8>::SMEM_BYTES2);
+  const int threads = v1 ? kHThreads : kH2Threads;
   FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int64_t grid = num_sms();
   if (grid > hp.ntiles) grid = hp.ntiles;
@@ -633,7 +1020,7 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg,
       hp.ypool = (last && ypool != nullptr) ? ypool + ob * CB : nullptr;
       hp.ymax = last ? ymax : nullptr;
       hp.add_bias = u == 0, hp.accumulate = u > 0, hp.apply_act = last;
-      kern<<<static_cast<unsigned>(grid), kHThreads, smem, st>>>(hp);
+      kern<<<static_cast<unsigned>(grid), threads, smem, st>>>(hp);
       FGC_LAUNCHED(tag != nullptr ? tag : "conv_hm_kernel");
     }
   return FGC_OK;
