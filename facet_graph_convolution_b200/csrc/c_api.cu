@@ -359,7 +359,10 @@ int fgc_conv_fwd_up(const fgc_conv_shape* s, const float* x_coarse, const int32_
                   as_stream(stream), nullptr, upshift);
 }
 
-int fgc_debug_trace(int64_t* out, int n) { return debug_mma_trace(out, n); }
+int fgc_debug_trace(int64_t* out, int n) {
+  if (getenv("FGC_HM_TRACE") != nullptr) return debug_hm_trace(out, n);   // conv_hm.cu's pipeline stamps
+  return debug_mma_trace(out, n);
+}
 
 size_t fgc_conv_plan_bytes(int B, int N, int K, int M) {
   if (B <= 0 || N <= 0 || K <= 0 || K > FGC_MAX_K || M != 8) return 0;

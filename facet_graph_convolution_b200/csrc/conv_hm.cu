@@ -76,6 +76,7 @@ struct HmParams {
   int add_bias, accumulate, apply_act;
   int cout;                // outputs of this launch (16 .. 64, multiple of 16)
   int single;              // B == 1: neighbour ids index the rows directly
+  int trace;               // FGC_HM_TRACE: clock64 stamps of CTA 0 (tests/micro/hm_trace.py)
   int zrow;                // index of an all-zero row of the image and of uvx (padding / out-of-range slots read it)
 };
 
@@ -236,6 +237,13 @@ __device__ __forceinline__ void hm_drain(uint8_t* b3, int f, int g, int t, const
 }
 
 // epilogue warp `warp` (TMEM lane quadrant `warp`): Y (TMEM) -> global, every tile of this CTA
+// optional pipeline trace (FGC_HM_TRACE=1): clock64 stamps of CTA 0, first 64 tiles, 16 events per tile
+__device__ long long g_hm_trace[64 * 16];
+#define HM_TR(t, ev)                                                                  \
+  do {                                                                                \
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) < 64) g_hm_trace[(t) * 16 + (ev)] = clock64(); \
+  } while (0)
+
 struct HmNoHook {
   __device__ __forceinline__ void operator()(int) const {}
 };
@@ -252,6 +260,7 @@ __device__ __forceinline__ void hm_epilogue(const HmParams& p, uint64_t* bars, c
   const float wun = __ldg(p.wunscale);
   const bool unmasked = !p.bias_mask;
   const bool aligned = (p.N & 15) == 0;   // a lane's 16 rows lie in one batch element
+  const bool do_act = p.apply_act && p.act == FGC_ACT_LRELU;
   int it = 0;
 
   for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -260,7 +269,28 @@ __device__ __forceinline__ void hm_epilogue(const HmParams& p, uint64_t* bars, c
     const int64_t r0 = tile * kHT + 16 * hh;
     int64_t left = p.rows - r0;
     const int nv = left >= 16 ? 16 : (left < 0 ? 0 : static_cast<int>(left));
-    tc::mbar_wait_relaxed(&bars[BAR_FULL + buf], (it >> 1) & 1);
+    // everything that does not depend on the accumulator is fetched before the wait: the scale(s) of the rows' batch
+    // element(s) and, for accumulating launches, the sixteen partial sums (all loads in flight at once)
+    float* yp = p.y + r0 * p.ldy + o;
+    float yold[16];
+    if (p.accumulate) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) yold[j] = (j < nv) ? __ldcg(yp + j * p.ldy) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) yold[j] = 0.f;
+    }
+    const int be0 = nv > 0 ? static_cast<int>(static_cast<int>(r0) / p.N) : 0;
+    const float sca = __ldg(p.xunscale + be0) * wun;
+    // rows of the next batch element start at j = cross (N >= 16: at most one boundary inside a lane's 16 rows)
+    int cross = 16;
+    float scb = sca;
+    if (!aligned && nv > 0) {
+      cross = static_cast<int>(static_cast<int64_t>(be0 + 1) * p.N - r0);
+      if (cross < nv) scb = __ldg(p.xunscale + be0 + 1) * wun;
+    }
+    tc::mbar_wait_lazy(&bars[BAR_FULL + buf], (it >> 1) & 1);
+    if (warp < 2) HM_TR(it, 4 + 2 * warp);
     tc::tc_fence_after_sync();
     uint32_t d0[32], d1[32];
     tc::tmem_ld32(tmem + lane_base + Cfg::D_COL + buf * Cfg::ND, d0);        // . Sh of facets 0..31
@@ -291,42 +321,33 @@ __device__ __forceinline__ void hm_epilogue(const HmParams& p, uint64_t* bars, c
 #pragma unroll
     for (int j = 0; j < 16; ++j) send[j] = __shfl_xor_sync(0xffffffffu, send[j], 16);
     float yv[16];
-    float* yp = p.y + r0 * p.ldy + o;
-    float yold[16];
-    if (p.accumulate) {   // all sixteen loads in flight at once (one after the other they cost a DRAM latency each)
+    if (nv == 16 && cross >= 16 && p.N >= 16) {
+      // the common case -- sixteen rows of one batch element -- without per-row branches (the branchy general loop
+      // below was the larger part of an epilogue of ~6 000 cycles per tile, a third of it instruction-cache misses)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) yold[j] = (j < nv) ? __ldcg(yp + j * p.ldy) : 0.f;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) yold[j] = 0.f;
-    }
-    const int be0 = nv > 0 ? static_cast<int>(r0 / p.N) : 0;
-    const float sca = __ldg(p.xunscale + be0) * wun;
-    // rows of the next batch element start at j = cross (N >= 16: at most one boundary inside a lane's 16 rows)
-    int cross = 16;
-    float scb = sca;
-    if (!aligned && nv > 0) {
-      cross = static_cast<int>(static_cast<int64_t>(be0 + 1) * p.N - r0);
-      if (cross < nv) scb = __ldg(p.xunscale + be0 + 1) * wun;
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float accv = hh ? (send[j] + keep[j]) : (keep[j] + send[j]);   // (Wh.Sh + Wh.Sl) + Wl.Sh / 2048
-      const float fl = (inv[j] > 0.f || unmasked) ? bo : 0.f;
-      float sc0 = j < cross ? sca : scb;
-      if (p.N < 16 && j > 0 && j < nv) sc0 = __ldg(p.xunscale + (r0 + j) / p.N) * wun;   // tiny elements: several boundaries
-      float v = fmaf(inv[j] * sc0, accv, fl);
-      v += yold[j];
-      if (p.apply_act && p.act == FGC_ACT_LRELU) v = lrelu_f(v, p.alpha);
-      yv[j] = v;
-    }
-    if (nv == 16) {
+      for (int j = 0; j < 16; ++j) {
+        const float accv = hh ? (send[j] + keep[j]) : (keep[j] + send[j]);   // (Wh.Sh + Wh.Sl) + Wl.Sh / 2048
+        const float fl = (inv[j] > 0.f || unmasked) ? bo : 0.f;
+        float v = fmaf(inv[j] * sca, accv, fl);
+        v += yold[j];
+        if (do_act) v = lrelu_f(v, p.alpha);
+        yv[j] = v;
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) yp[j * p.ldy] = yv[j];
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < nv) yp[j * p.ldy] = yv[j];
+      for (int j = 0; j < 16; ++j) {
+        const float accv = hh ? (send[j] + keep[j]) : (keep[j] + send[j]);
+        const float fl = (inv[j] > 0.f || unmasked) ? bo : 0.f;
+        float sc0 = j < cross ? sca : scb;
+        if (p.N < 16 && j > 0 && j < nv) sc0 = __ldg(p.xunscale + (r0 + j) / p.N) * wun;   // tiny elements: several boundaries
+        float v = fmaf(inv[j] * sc0, accv, fl);
+        v += yold[j];
+        if (do_act) v = lrelu_f(v, p.alpha);
+        yv[j] = v;
+        if (j < nv) yp[j * p.ldy] = v;
+      }
     }
     if (p.ypool != nullptr) {
       float* pp = p.ypool + (r0 >> 2) * p.ldp + o;
@@ -346,6 +367,7 @@ __device__ __forceinline__ void hm_epilogue(const HmParams& p, uint64_t* bars, c
       for (int s = 8; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
       if ((lane & 15) == 0 && nv > 0) atomicMax(p.ymax + be0, __float_as_uint(m));
     }
+    if (warp < 2) HM_TR(it, 5 + 2 * warp);
   }
 }
 
@@ -569,28 +591,44 @@ struct Hm2Pre {           // per-item inputs of the softmax
 // soft assignments of the item in the A-fragment layout: a[0..3] = hi of rows g (a0,a2) / rows 8+ (a1,a3), a[4..7] = lo
 template <int M>
 __device__ __forceinline__ void hm2_softmax(const Hm2Pre& in, bool recentre, uint32_t (&a)[8]) {
+  // the four slots of the lane side by side: every shuffle round is four independent shuffles (one slot after the other
+  // is a chain of ~12 dependent shuffle / MUFU latencies per slot, which five warps per sub-partition do not cover)
+  float ag[4], a8[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ag[i] = in.uo.x + in.vl[i].x;
+    a8[i] = (M == 9) ? in.uo.y + in.vl[i].y : 0.f;
+  }
+  if (recentre) {   // warp-uniform: the pre-pass saw logits spread over > 60 binary orders
+    float mx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mx[i] = (M == 9) ? fmaxf(ag[i], a8[i]) : ag[i];
+#pragma unroll
+    for (int sh = 4; sh <= 16; sh <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], sh));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ag[i] -= mx[i], a8[i] -= mx[i];
+  }
+  float eg[4], e8[4], z[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    eg[i] = ex2_approx(ag[i]);
+    e8[i] = (M == 9) ? ex2_approx(a8[i]) : 0.f;
+    z[i] = eg[i];
+  }
+#pragma unroll
+  for (int sh = 4; sh <= 16; sh <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] += __shfl_xor_sync(0xffffffffu, z[i], sh);
+  }
   float qg[4], q8[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float ag = in.uo.x + in.vl[i].x;
-    float a8 = (M == 9) ? in.uo.y + in.vl[i].y : 0.f;
-    if (recentre) {
-      float mx = (M == 9) ? fmaxf(ag, a8) : ag;
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-      ag -= mx, a8 -= mx;
-    }
-    const float eg = ex2_approx(ag);
-    const float e8 = (M == 9) ? ex2_approx(a8) : 0.f;
-    float z = eg;
-    z += __shfl_xor_sync(0xffffffffu, z, 4);
-    z += __shfl_xor_sync(0xffffffffu, z, 8);
-    z += __shfl_xor_sync(0xffffffffu, z, 16);
-    z += e8;
-    const float rs = ((in.okm >> i) & 1) ? rcp_approx(z) : 0.f;
-    qg[i] = eg * rs;
-    q8[i] = e8 * rs;
+    const float rs = ((in.okm >> i) & 1) ? rcp_approx(z[i] + e8[i]) : 0.f;
+    qg[i] = eg[i] * rs;
+    q8[i] = e8[i] * rs;
   }
   split_rn(qg[0], qg[1], a[0], a[4]);
   split_rn(qg[2], qg[3], a[2], a[6]);
@@ -698,9 +736,11 @@ conv_hm2_kernel(const HmParams p) {
       auto issue_stage2 = [&](int it) {
         const int buf = it & 1;
         const uint32_t par = (it >> 1) & 1;
-        tc::mbar_wait_relaxed(&bars[H2_B3_FULL + buf], par);   // all 16 aggregator warps have stored their rows of S
+        tc::mbar_wait_lazy(&bars[H2_B3_FULL + buf], par);   // all 16 aggregator warps have stored their rows of S
+        HM_TR(it, 2);
         tc::fence_proxy_async_smem();                          // ... and the tensor core may read them
         tc::mbar_wait(&bars[H2_D_FREE + buf], par ^ 1);
+        HM_TR(it, 3);
         tc::tc_fence_after_sync();
         if (tc::elect_one()) {
           const uint32_t b3 = sb + buf * Cfg::B3_BUF;
@@ -717,7 +757,13 @@ conv_hm2_kernel(const HmParams p) {
         }
         __syncwarp();
       };
-      hm_epilogue<Cfg, H2_D_FULL, H2_D_FREE>(p, bars, rowinv, tmem, warp, lane, issue_stage2);
+      // stage 2 of tile it + 1 is issued BEFORE the epilogue of tile it: its MMAs then run under this warp's epilogue
+      // (issue -> epilogue -> issue in program order made the tile period T_mma + T_epilogue, which bound the kernel)
+      auto before_tile = [&](int it) {
+        if (it == 0) issue_stage2(0);
+        if (it + 1 < my_tiles) issue_stage2(it + 1);
+      };
+      hm_epilogue<Cfg, H2_D_FULL, H2_D_FREE>(p, bars, rowinv, tmem, warp, lane, before_tile);
     } else if (warp < nepi) {
       hm_epilogue<Cfg, H2_D_FULL, H2_D_FREE>(p, bars, rowinv, tmem, warp, lane);
     }
@@ -815,18 +861,14 @@ conv_hm2_kernel(const HmParams p) {
       __syncwarp();
       int row = 0;
       if (more) row = issue_hi(r1, idn, P);       // overwrites okm / cnt of P: both consumed above
+      // eight independent accumulators per round (back-to-back MMAs into one accumulator wait for each other)
 #pragma unroll
-      for (int up = 0; up < 4; ++up) {
+      for (int u = 0; u < 8; ++u)   // M = 8: rows g: q_hi.x_hi, rows g+8: q_lo.x_hi
+        hm_mma<FIRST>(acc[u], a[0], a[1], a[2], a[3], bf[u >> 1][2 * (u & 1)], bf[u >> 1][2 * (u & 1) + 1]);
+      if (M == 9) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int u = 2 * up + j;
-          if (M == 9) {
-            hm_mma<FIRST>(acc[u], a[0], a[1], a[2], a[3], bf[up][2 * j], bf[up][2 * j + 1]);
-            hm_mma<false>(acc[u], a[4], a[5], a[6], a[7], bf[up][2 * j], bf[up][2 * j + 1]);
-          } else {
-            hm_mma<FIRST>(acc[u], a[0], a[1], a[2], a[3], bf[up][2 * j], bf[up][2 * j + 1]);   // rows g: q_hi.x_hi, rows g+8: q_lo.x_hi
-          }
-        }
+        for (int u = 0; u < 8; ++u)
+          hm_mma<false>(acc[u], a[4], a[5], a[6], a[7], bf[u >> 1][2 * (u & 1)], bf[u >> 1][2 * (u & 1) + 1]);
       }
       if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");   // lo plane of this item (the next hi plane may be pending)
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -850,11 +892,17 @@ conv_hm2_kernel(const HmParams p) {
       r1 = r2;
       if (LAST) {
         const int n = m / NG, it = n / kHFpw, fi = n % kHFpw, buf = it & 1, f = aw * kHFpw + fi;
-        if (fi == 0) tc::mbar_wait(&bars[H2_B3_FREE + buf], ((it >> 1) & 1) ^ 1);
+        if (fi == 0) {
+          if (aw == 0) HM_TR(it, 9);
+          tc::mbar_wait(&bars[H2_B3_FREE + buf], ((it >> 1) & 1) ^ 1);
+          if (aw == 0) HM_TR(it, 10);
+        }
         hm2_drain<M>(smem + buf * Cfg::B3_BUF, f, g, t, acc);
         if (lane == 0) rowinv[(it & 3) * kHT + f] = invtab[cnt];
         if (fi == kHFpw - 1) {
           __syncwarp();
+          if (aw == 0) HM_TR(it, 1);
+          if (aw == kHAgg - 1) HM_TR(it, 8);
           if (lane == 0) tc::mbar_arrive(&bars[H2_B3_FULL + buf]);
         }
       }
@@ -955,6 +1003,13 @@ size_t hm_wt_bytes(int M, int nimg) { return static_cast<size_t>(nimg) * 128 * M
 
 }  // namespace
 
+int debug_hm_trace(int64_t* out, int n) {
+  long long host[64 * 16];
+  FGC_CUDA(cudaMemcpyFromSymbol(host, g_hm_trace, sizeof(host)));
+  for (int i = 0; i < n && i < 64 * 16; ++i) out[i] = host[i];
+  return FGC_OK;
+}
+
 bool conv_hm_supported(int Cin, int Cw, int Cout, int M, int K) {
   return (M == 8 || M == 9) && K >= 1 && K <= 32 && Cin % 4 == 0 && Cw % 4 == 0 && (Cw == 32 || Cw == 64 || Cw == 128) &&
          (Cout == 32 || Cout == 64 || Cout == 128);
@@ -999,6 +1054,10 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg,
   hp.ldy = Cout, hp.ldp = Cout, hp.rows = rows, hp.ntiles = (rows + kHT - 1) / kHT;
   hp.N = N, hp.K = K, hp.upshift = upshift, hp.bias_mask = bias_mask, hp.act = act, hp.alpha = alpha;
   hp.cout = CB, hp.single = rows == N, hp.zrow = static_cast<int>(rows_img);
+  {
+    static const bool trace = getenv("FGC_HM_TRACE") != nullptr;
+    hp.trace = trace ? 1 : 0;
+  }
   const bool v1 = hm_use_v1();
   auto kern = v1 ? (M == 9 ? (K <= 16 ? conv_hm_kernel<9, 1> : conv_hm_kernel<9, 2>)
                            : (K <= 16 ? conv_hm_kernel<8, 1> : conv_hm_kernel<8, 2>))

@@ -49,6 +49,15 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     if (++polls > 4) __nanosleep(64);
   }
 }
+// for waits of several microseconds (a whole tile of the aggregators' work): the sleep doubles up to ~0.5 us, so the
+// waiting warp issues a handful of instructions per tile instead of one poll every ~130 cycles
+__device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity) {
+  uint32_t ns = 32;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (ns < 512) ns <<= 1;
+  }
+}
 
 // One lane of the (converged) warp, chosen by hardware.  Unlike `lane == 0`, ptxas knows the branch
 // is taken by exactly one thread, so uniform-datapath instructions (tcgen05.mma / commit) inside it
