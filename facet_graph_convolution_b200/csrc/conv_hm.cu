@@ -55,6 +55,8 @@ struct HmCfg {
 enum { HB_B3_FREE = 0, HB_D_FULL = 2, HB_D_FREE = 4, HB_NUM = 6 };
 
 struct HmParams {
+  alignas(64) unsigned char tmap[128];   // CUtensorMap of the whole image (second-generation kernel, TMA row gather)
+  int unit_col;            // first column (in halves) of this launch's 64-channel unit inside an image row
   const uint4* img;        // fp16 image of this launch's 64-channel unit: row r at img + r * img_ld, [0..8) hi, [8..16) lo
   int img_ld;
   const float* xunscale;   // [B]: 2^ex of the image rows of every batch element
@@ -567,7 +569,7 @@ struct Hm2Cfg : HmCfg<M> {
   static constexpr int SMEM_BYTES2 = OFF_BAR2 + 512;
 };
 
-enum { H2_B3_FREE = 0, H2_D_FULL = 2, H2_D_FREE = 4, H2_B3_FULL = 6, H2_NUM = 8 };
+enum { H2_B3_FREE = 0, H2_D_FULL = 2, H2_D_FREE = 4, H2_B3_FULL = 6, H2_ROWS_HI = 8, H2_ROWS_LO = 8 + kHAgg, H2_NUM = 8 + 2 * kHAgg };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -679,9 +681,9 @@ __device__ __forceinline__ void hm2_drain(uint8_t* b3, int f, int g, int t, cons
   }
 }
 
-template <int M, int NG>
+template <int M, int NG, bool TMA>
 __global__ void __launch_bounds__(kH2Threads, 1)
-conv_hm2_kernel(const HmParams p) {
+conv_hm2_kernel(const __grid_constant__ HmParams p) {
   using Cfg = Hm2Cfg<M>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR2);
@@ -698,6 +700,7 @@ conv_hm2_kernel(const HmParams p) {
       tc::mbar_init(&bars[H2_D_FULL + i], 1), tc::mbar_init(&bars[H2_D_FREE + i], nepi);
       tc::mbar_init(&bars[H2_B3_FULL + i], kHAgg);
     }
+    for (int i = 0; i < 2 * kHAgg; ++i) tc::mbar_init(&bars[H2_ROWS_HI + i], 1);   // TMA: one plane of one warp's stage
     tc::mbar_fence_init();
   }
   if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
@@ -795,8 +798,8 @@ conv_hm2_kernel(const HmParams p) {
       return (r >= 0 && k < p.K) ? __ldg(p.adj + static_cast<int64_t>(r) * p.K + k) : 0;
     };
     int base_cur = 0, base_next = p.N;     // batch element of the rows the issue stage walks (monotone)
-    // row index of this lane's slot, validity / count bits, and the copies of the hi plane of the item's 16 rows
-    auto issue_hi = [&](int r, int id, Hm2Pre& o) -> int {
+    // row index of this lane's slot + the item's validity / count bits
+    auto prep_rows = [&](int r, int id, Hm2Pre& o) -> int {
       int base = 0;
       if (!p.single && r >= 0) {
         while (r >= base_next) base_cur = base_next, base_next += p.N;
@@ -808,21 +811,40 @@ conv_hm2_kernel(const HmParams p) {
       const unsigned nzb = __ballot_sync(0xffffffffu, id != 0) & 0xFFFFu;
       o.okm = static_cast<int>(((okb >> (2 * t)) & 3u) | (((okb >> (2 * t + 8)) & 3u) << 2));
       o.cnt = __popc(nzb);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = __shfl_sync(0xffffffffu, row, cq + 4 * i);
-        cp_async16(((i & 1) ? cdst1 : cdst0) + (i >> 1) * 1024, img_c + static_cast<int64_t>(rr) * p.img_ld);
-      }
-      cp_async_commit();
       return row;
     };
-    auto issue_lo = [&](int row) {
+    // one plane (0 hi, 1 lo) of the item's 16 rows -> this warp's stage.  TMA: four gathers of four rows (512 B each) by
+    // lanes 0..3, completion on the plane's mbarrier (phase = item parity); otherwise 16-byte cp.async, one commit group.
+    auto copy_plane = [&](int row, int plane) {
+      if constexpr (TMA) {
+        int rr[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = __shfl_sync(0xffffffffu, row, cq + 4 * i);
-        cp_async16(((i & 1) ? cdst1 : cdst0) + (i >> 1) * 1024 + 2048, img_c + static_cast<int64_t>(rr) * p.img_ld + 8);
+        for (int j = 0; j < 4; ++j) rr[j] = __shfl_sync(0xffffffffu, row, 4 * (lane & 3) + j);
+        uint64_t* bar = &bars[(plane ? H2_ROWS_LO : H2_ROWS_HI) + aw];
+        if (lane == 0) tc::mbar_arrive_expect_tx(bar, 2048);
+        __syncwarp();
+        if (lane < 4)
+          tc::tma_gather4_rows(stage + plane * 2048 + lane * 512, p.tmap, bar, p.unit_col + plane * 64, rr[0], rr[1], rr[2],
+                               rr[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = __shfl_sync(0xffffffffu, row, cq + 4 * i);
+          cp_async16(((i & 1) ? cdst1 : cdst0) + (i >> 1) * 1024 + plane * 2048,
+                     img_c + static_cast<int64_t>(rr) * p.img_ld + plane * 8);
+        }
+        cp_async_commit();
       }
-      cp_async_commit();
+    };
+    // the plane of item m has landed (cp.async: the groups complete in order hi(m), lo(m), hi(m+1), ...)
+    auto wait_plane = [&](int m, int plane, bool next_hi_pending) {
+      if constexpr (TMA) {
+        tc::mbar_wait(&bars[(plane ? H2_ROWS_LO : H2_ROWS_HI) + aw], m & 1);
+      } else {
+        if (plane == 0 || next_hi_pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
     };
     auto issue_logits = [&](int r, int row, Hm2Pre& o) {
       o.uo = __ldg(lg_u + static_cast<int64_t>((r < 0 ? 0 : r) >> p.upshift) * 8);
@@ -838,8 +860,9 @@ conv_hm2_kernel(const HmParams p) {
     int r1 = row_of(0);
     int idn = load_id(0, r1);
     {
-      const int row = issue_hi(r1, idn, P);
-      issue_lo(row);
+      const int row = prep_rows(r1, idn, P);
+      copy_plane(row, 0);
+      copy_plane(row, 1);
       issue_logits(r1, row, P);
     }
     r1 = row_of(1);
@@ -854,29 +877,30 @@ conv_hm2_kernel(const HmParams p) {
       cnt = FIRST ? P.cnt : cnt + P.cnt;
       const bool more = m + 1 < nitems;
       uint32_t bf[4][4];
-      asm volatile("cp.async.wait_group 1;" ::: "memory");     // hi plane of this item
-      __syncwarp();
+      wait_plane(m, 0, true);
 #pragma unroll
       for (int up = 0; up < 4; ++up) ldsm_x4_t(laddr ^ (up << 5), bf[up]);
       __syncwarp();
       int row = 0;
-      if (more) row = issue_hi(r1, idn, P);       // overwrites okm / cnt of P: both consumed above
+      if (more) row = prep_rows(r1, idn, P);       // overwrites okm / cnt of P: both consumed above
+      if (!TMA && more) copy_plane(row, 0);
       // eight independent accumulators per round (back-to-back MMAs into one accumulator wait for each other)
 #pragma unroll
       for (int u = 0; u < 8; ++u)   // M = 8: rows g: q_hi.x_hi, rows g+8: q_lo.x_hi
         hm_mma<FIRST>(acc[u], a[0], a[1], a[2], a[3], bf[u >> 1][2 * (u & 1)], bf[u >> 1][2 * (u & 1) + 1]);
+      // TMA writes through the async proxy: the gathers into the plane go out once every fragment register of the plane
+      // has been consumed by an MMA, i.e. its ldmatrix reads are complete
+      if (TMA && more) copy_plane(row, 0);
       if (M == 9) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           hm_mma<false>(acc[u], a[4], a[5], a[6], a[7], bf[u >> 1][2 * (u & 1)], bf[u >> 1][2 * (u & 1) + 1]);
       }
-      if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");   // lo plane of this item (the next hi plane may be pending)
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
+      wait_plane(m, 1, more);
 #pragma unroll
       for (int up = 0; up < 4; ++up) ldsm_x4_t((laddr ^ (up << 5)) + 2048, bf[up]);
       __syncwarp();
-      if (more) issue_lo(row);
+      if (!TMA && more) copy_plane(row, 1);
       const int r2 = row_of(m + 2);
       idn = load_id(m + 2, r2);
 #pragma unroll
@@ -888,6 +912,7 @@ conv_hm2_kernel(const HmParams p) {
           else hm_mma<false>(acc[u], a[0], 0u, a[2], 0u, bf[up][2 * j], bf[up][2 * j + 1]);
         }
       }
+      if (TMA && more) copy_plane(row, 1);
       if (more) issue_logits(r1, row, P);
       r1 = r2;
       if (LAST) {
@@ -1059,10 +1084,14 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg,
     hp.trace = trace ? 1 : 0;
   }
   const bool v1 = hm_use_v1();
+  // second generation: rows by TMA gather on request (FGC_TMA_MODES bit 4; slower than cp.async here, see make_hm_img_tmap)
+  const bool tma = !v1 && make_hm_img_tmap(hp.tmap, img, rows_img + 1, nunits);
   auto kern = v1 ? (M == 9 ? (K <= 16 ? conv_hm_kernel<9, 1> : conv_hm_kernel<9, 2>)
                            : (K <= 16 ? conv_hm_kernel<8, 1> : conv_hm_kernel<8, 2>))
-                 : (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1> : conv_hm2_kernel<9, 2>)
-                           : (K <= 16 ? conv_hm2_kernel<8, 1> : conv_hm2_kernel<8, 2>));
+                 : tma ? (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, true> : conv_hm2_kernel<9, 2, true>)
+                                 : (K <= 16 ? conv_hm2_kernel<8, 1, true> : conv_hm2_kernel<8, 2, true>))
+                       : (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, false> : conv_hm2_kernel<9, 2, false>)
+                                 : (K <= 16 ? conv_hm2_kernel<8, 1, false> : conv_hm2_kernel<8, 2, false>));
   const int smem = v1 ? (M == 9 ? HmCfg<9>::SMEM_BYTES : HmCfg<8>::SMEM_BYTES)
                       : (M == 9 ? Hm2Cfg<9>::SMEM_BYTES2 : Hm2Cfg<8>::SMEM_BYTES2);
   const int threads = v1 ? kHThreads : kH2Threads;
@@ -1074,6 +1103,7 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg,
     for (int u = 0; u < nunits; ++u) {
       const bool last = u == nunits - 1;
       hp.img = static_cast<const uint4*>(img) + u * 16;
+      hp.unit_col = u * 128;
       hp.wt = static_cast<const uint32_t*>(wbuf) + static_cast<size_t>(ob * nunits + u) * 128 * M * 32;
       hp.b = b + ob * CB, hp.y = y + ob * CB;
       hp.ypool = (last && ypool != nullptr) ? ypool + ob * CB : nullptr;

@@ -55,6 +55,8 @@ int build_conv_plan(const int32_t* adj, int B, int N, int K, int M, void* plan, 
 size_t conv_mma_workspace(int64_t rows);
 int debug_mma_trace(int64_t* out, int n);
 int debug_hm_trace(int64_t* out, int n);
+// 128-byte CUtensorMap of an fp16 hi|lo image with `nunits` 64-channel units per row (false: no encoder / disabled)
+bool make_hm_img_tmap(void* tm, const void* img, int64_t rows, int nunits);
 int prep_image_blocks();
 int launch_prep_image(const float* x, int ld, int64_t rows, void* img_ws, cudaStream_t st,
                       const float* pinv = nullptr, int bias_mask = 0, float* partB = nullptr, bool have_absmax = false);

@@ -59,6 +59,22 @@ __device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// one arrival + `bytes` expected transaction bytes (TMA copies complete them)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA gather of four rows of a 2-D tensor map (box = 64 elements x 1 row, 128-byte swizzle): rows r0..r3 at column `col`
+// land as four consecutive swizzled 128-byte rows at dst (shared, 512-byte aligned); 512 bytes complete on `bar`.
+__device__ __forceinline__ void tma_gather4_rows(uint32_t dst, const void* tmap, uint64_t* bar, int col, int r0, int r1, int r2,
+                                                 int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
 // One lane of the (converged) warp, chosen by hardware.  Unlike `lane == 0`, ptxas knows the branch
 // is taken by exactly one thread, so uniform-datapath instructions (tcgen05.mma / commit) inside it
 // are not wrapped in a per-active-thread election loop.

@@ -14,7 +14,8 @@ from facet_graph_convolution_b200 import mesh, ops
 Cin = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 Cout = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 dev = torch.device("cuda:0")
-_, F = mesh.grid_mesh(530, 530, torus=True, morton=True)
+nq = int(sys.argv[3]) if len(sys.argv) > 3 else 530
+_, F = mesh.grid_mesh(nq, nq, torus=True, morton=True)
 adj_d, _ = ops.build_faces_adj(torch.from_numpy(F.astype(np.int32)).to(dev), K=16)
 adj = adj_d[None].contiguous()
 N = adj.shape[1]
