@@ -475,6 +475,7 @@ def run_c3(args):
                                                                       block, block, world, PB))
     config = {"workload": workload, "facets": 2 * grid * grid, "patches": npatch, "K": NET_K, "M": NET_M,
               "parallelism": "patch-sharded x%d (no data-path collective)" % world,
+              "streams": "launch groups of a pass alternate over %d CUDA stream(s)" % max(1, args.streams),
               "l2": "patch tensors of one pass (x + 3 adjacency levels, ~240 MB per 2 M facets) exceed the 126 MB L2; "
                     "every pass re-reads them, no flush"}
     if args.impl == "reference":
@@ -532,13 +533,17 @@ def run_c3(args):
     # launch groups of <= PB patches
     groups = [list(range(i, min(i + PB, len(mine)))) for i in range(0, len(mine), PB)]
     host = stack(groups)
-    # the end-to-end pass wants at least two groups per rank, so that group i+1 uploads under the forward of group i
-    # (8 ranks: 12-13 patches each -> 7 + 6); the device-resident pass keeps the larger, more efficient launches
-    if len(groups) >= 2 or len(mine) < 2:
-        host_e2e = host
+    # the end-to-end pass starts computing as soon as a SMALL first group is on the device and uploads growing groups under
+    # the forward of the previous one (about 1/10, 3/10, 6/10 of the rank's patches): upload(first) + compute instead of
+    # upload(half) + compute
+    n = len(mine)
+    if n >= 6:
+        c1, c2 = max(1, n // 10), max(2, (4 * n) // 10)
+        host_e2e = stack([list(range(0, c1)), list(range(c1, c2)), list(range(c2, n))])
+    elif n >= 2:
+        host_e2e = stack([list(range(0, n // 2)), list(range(n // 2, n))])
     else:
-        per = (len(mine) + 1) // 2
-        host_e2e = stack([list(range(i, min(i + per, len(mine)))) for i in range(0, len(mine), per)])
+        host_e2e = host
     resident = [(x.to(dev), [a.to(dev) for a in adjs], ns.to(dev)) for x, adjs, ns in host]
     core = sum(int(p.core.sum()) for p in mine)
     rows0 = sum(int(x.shape[0] * x.shape[1]) for x, _, _ in host)     # level-0 rows launched per pass (halo + padding incl.)
@@ -549,9 +554,32 @@ def run_c3(args):
             y = fm.get_model_reg_multi_scale(x, adjs, 1.0)
             return ops.normalize_rows_segmented(y, cnt)
 
+    # launch groups are independent: alternating them over two streams lets the ramp-up of one group's kernel fill the
+    # tail of the other's (every kernel is one persistent CTA per SM)
+    nstreams = max(1, min(args.streams, len(resident)))
+    side = [torch.cuda.Stream() for _ in range(nstreams - 1)]
+
     def one_pass():
-        for x, adjs, cnt in resident:
-            fwd(x, adjs, cnt)
+        if not side:
+            for x, adjs, cnt in resident:
+                fwd(x, adjs, cnt)
+            return
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        for s_ in side:
+            s_.wait_event(start)
+        for i, (x, adjs, cnt) in enumerate(resident):
+            k = i % nstreams
+            if k == 0:
+                fwd(x, adjs, cnt)
+            else:
+                with torch.cuda.stream(side[k - 1]):
+                    fwd(x, adjs, cnt)
+        for s_ in side:
+            done = torch.cuda.Event()
+            done.record(s_)
+            main.wait_event(done)
 
     for _ in range(max(args.warmup, 3)):
         one_pass()
@@ -559,7 +587,8 @@ def run_c3(args):
     # per-layer CUDA-event times of one pass (library profiler; outside the timed region)
     stream = torch.cuda.current_stream()
     L.fgc_profile_begin(C.c_void_p(stream.cuda_stream))
-    one_pass()
+    for x, adjs, cnt in resident:      # single stream: the profiler brackets every launch with events on one stream
+        fwd(x, adjs, cnt)
     buf = C.create_string_buffer(1 << 16)
     L.fgc_profile_end(buf, len(buf))
     prof = {ln.split()[0]: (float(ln.split()[1]), int(ln.split()[2])) for ln in buf.value.decode().strip().splitlines()}
@@ -712,7 +741,8 @@ def main():
     ap.add_argument("--config", default="c3", choices=["c3", "c2"])
     ap.add_argument("--grid", type=int, default=1000, help="c3: quads per side (1000 -> 2 M facets)")
     ap.add_argument("--block", type=int, default=100, help="c3: quads per side of a patch core")
-    ap.add_argument("--patch-batch", type=int, default=25, help="c3: patches per launch (1 = the reference's B = 1)")
+    ap.add_argument("--patch-batch", type=int, default=50, help="c3: patches per launch (1 = the reference's B = 1)")
+    ap.add_argument("--streams", type=int, default=2, help="c3: launch groups of a pass alternate over this many CUDA streams")
     ap.add_argument("--adjacency", default="mesh", choices=["mesh", "dedup", "random"], help="c2")
     ap.add_argument("--facets", type=int, default=1_000_000, help="c2")
     ap.add_argument("--cpu-sample", type=int, default=20_000, help="c2")
