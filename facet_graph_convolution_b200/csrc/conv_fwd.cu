@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(128)
 conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ adj, const float* __restrict__ W0,
                       const float* __restrict__ b, const float* __restrict__ u, const float* __restrict__ v,
                       const float* __restrict__ c, float* __restrict__ y, int64_t rows, int N, int K, int bias_mask,
-                      int act, float alpha) {
+                      int act, float alpha, float* __restrict__ ypool, unsigned* __restrict__ ymax) {
   __shared__ __align__(16) float Wt[M * CIN * COUT];   // [(m, c)][o]
   __shared__ float us[M * CIN], vs[M * CIN], cs[M];
   for (int e = threadIdx.x; e < M * CIN * COUT; e += blockDim.x) {
@@ -259,8 +259,12 @@ conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ a
   for (int e = threadIdx.x; e < M * CIN; e += blockDim.x) us[e] = u[e], vs[e] = v[e];
   if (threadIdx.x < M) cs[threadIdx.x] = c[threadIdx.x];
   __syncthreads();
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows;
-       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  // warp-uniform trip count (the fused pooling / max|y| outputs shuffle across the warp): lanes past the end compute on
+  // row rows - 1 and store nothing
+  for (int64_t rw = static_cast<int64_t>(blockIdx.x) * blockDim.x + (threadIdx.x & ~31); rw < rows;
+       rw += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const bool valid = rw + (threadIdx.x & 31) < rows;
+    const int64_t r = valid ? rw + (threadIdx.x & 31) : rows - 1;
     const int64_t base = (r / N) * N;
     float xn[CIN], own[M], s[M][CIN];
 #pragma unroll
@@ -327,6 +331,7 @@ conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ a
     const float inv = cnt ? 1.f / static_cast<float>(cnt) : 0.f;
     const float fl = (cnt > 0 || !bias_mask) ? 1.f : 0.f;
     float4* yr = reinterpret_cast<float4*>(y + r * COUT);
+    float amax = 0.f;
 #pragma unroll
     for (int o4 = 0; o4 < COUT / 4; ++o4) {
       float o[4];
@@ -335,8 +340,33 @@ conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ a
         float yv = fmaf(inv, acc[4 * o4 + j], fl * __ldg(b + 4 * o4 + j));
         if (act == FGC_ACT_LRELU) yv = lrelu_f(yv, alpha);
         o[j] = yv;
+        amax = fmaxf(amax, fabsf(yv));
       }
-      yr[o4] = make_float4(o[0], o[1], o[2], o[3]);
+      if (valid) yr[o4] = make_float4(o[0], o[1], o[2], o[3]);
+      if (ypool != nullptr) {
+        // custom_binary_tree_pooling (model.py:863): max over the four consecutive rows of a group = four lanes
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = fmaxf(o[j], __shfl_xor_sync(0xffffffffu, o[j], 1));
+          o[j] = fmaxf(o[j], __shfl_xor_sync(0xffffffffu, o[j], 2));
+        }
+        if (valid && (threadIdx.x & 3) == 0)
+          reinterpret_cast<float4*>(ypool + (r >> 2) * COUT)[o4] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    if (ymax != nullptr) {
+      // max|y| per batch element (the image scale of the next layer): one atomic per warp when its rows share the element
+      const int be = static_cast<int>(r / N);
+      const int be0 = __shfl_sync(0xffffffffu, be, 0);
+      const bool same = __all_sync(0xffffffffu, be == be0);
+      if (!valid) amax = 0.f;
+      if (same) {
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, sft));
+        if ((threadIdx.x & 31) == 0) atomicMax(ymax + be0, __float_as_uint(amax));
+      } else if (valid) {
+        atomicMax(ymax + be, __float_as_uint(amax));
+      }
     }
   }
 }
@@ -348,14 +378,15 @@ bool conv_fwd_small_supported(const fgc_conv_shape* s) {
 
 int launch_conv_fwd_small(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0, const float* b,
                           const float* u, const float* v, const float* c, float* y, int bias_mask, int act,
-                          float alpha, cudaStream_t st) {
+                          float alpha, cudaStream_t st, float* ypool, unsigned* ymax) {
   const int64_t rows = static_cast<int64_t>(s->B) * s->N;
+  FGC_REQUIRE(ypool == nullptr || s->N % 4 == 0, "conv_fwd_small: pooled output needs N %% 4 == 0");
   int64_t blocks = (rows + 127) / 128;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   conv_fwd_small_kernel<9, 6, 32><<<static_cast<unsigned>(blocks), 128, 0, st>>>(x, adj, W0, b, u, v, c, y, rows, s->N,
-                                                                               s->K, bias_mask, act, alpha);
+                                                                               s->K, bias_mask, act, alpha, ypool, ymax);
   FGC_LAUNCHED("conv_fwd_small_kernel");
   return FGC_OK;
 }

@@ -40,7 +40,8 @@ size_t conv_fwd_tc_workspace(int Cout, int M, int Cw = 64);
 bool conv_fwd_small_supported(const fgc_conv_shape* s);
 int launch_conv_fwd_small(const fgc_conv_shape* s, const float* x, const int32_t* adj, const float* W0, const float* b,
                           const float* u, const float* v, const float* c, float* y, int bias_mask, int act,
-                          float alpha, cudaStream_t st);
+                          float alpha, cudaStream_t st, float* ypool = nullptr, unsigned* ymax = nullptr);
+// ypool (optional): [rows / 4][32] max over groups of 4 rows; ymax (optional): [B] atomicMax targets for max|y| bits
 int launch_conv_fwd_tc(const ConvFwdParams& p, const float* W0, void* wimg_ws, cudaStream_t st, int upshift = 0);
 bool bwd_tgt_tc_supported(int Cw, int Cout, int M);
 int launch_bwd_tgt_tc(const float* gy, const float* uvx, const float* W0, const float* da_edge,

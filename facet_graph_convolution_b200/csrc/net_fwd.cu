@@ -130,16 +130,12 @@ int fgc_net_fwd(int B, int N0, int K, const float* x, const int32_t* adj0, const
   unsigned* mx[8];
   for (int i = 0; i < 8; ++i) mx[i] = w.mx + static_cast<size_t>(i) * B;
   int rc;
-  // ---- Level 0: conv1 (6 -> 32, gather-bound: thread per facet, logits inline) + lrelu, pool, max|h1|
+  // ---- Level 0: conv1 (6 -> 32, gather-bound: thread per facet, logits inline) + lrelu; pool and max|h1| fused
   {
     const ConvP p = conv_params(params, 0);
     fgc_conv_shape s{B, N0, K, 6, 6, 0, 6, 32, kNetM};
-    rc = launch_conv_fwd_small(&s, x, adj0, p.W0, p.b, p.u, p.v, p.c, w.h1, 1, FGC_ACT_LRELU, alpha, st);
-    if (rc) return rc;
-    rc = fgc_pool_max(w.h1, w.p1, R1, 32, 4, stream);
-    if (rc) return rc;
-    rc = launch_absmax_bits(w.h1, static_cast<int64_t>(N0) * 8, B, mx[0], st);   // bounds max|p1| too
-    if (rc) return rc;
+    rc = launch_conv_fwd_small(&s, x, adj0, p.W0, p.b, p.u, p.v, p.c, w.h1, 1, FGC_ACT_LRELU, alpha, st, w.p1, mx[0]);
+    if (rc) return rc;   // pooled copy and max|h1| (bounds max|p1| too) come from the kernel's epilogue
   }
   // one dense layer: pre-pass over [xa | xb] (rows_in rows of Nin per element), then the convolution on `adj`
   auto layer = [&](int l, const float* xa, int Ca, const unsigned* ma, const float* xb, int Cb, const unsigned* mb,
