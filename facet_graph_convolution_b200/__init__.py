@@ -8,7 +8,7 @@ CUDA device and fails loudly otherwise.
 """
 from . import mesh  # noqa: F401  (NumPy only)
 
-__all__ = ["mesh", "mesh_io", "checkpoint", "ops", "model", "autograd", "build_library"]
+__all__ = ["mesh", "mesh_io", "checkpoint", "ops", "model", "autograd", "torch_ops", "build_library"]
 
 
 def build_library(force=False):
@@ -17,7 +17,7 @@ def build_library(force=False):
 
 
 def __getattr__(name):
-    if name in ("ops", "model", "autograd", "patches", "train", "checkpoint", "mesh_io", "coarsening"):
+    if name in ("ops", "model", "autograd", "patches", "train", "checkpoint", "mesh_io", "coarsening", "torch_ops"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)
