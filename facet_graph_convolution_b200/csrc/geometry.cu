@@ -172,8 +172,9 @@ __global__ void vertex_update_edges_kernel(const float* __restrict__ xin, float*
                                            const float* __restrict__ normals,
                                            const int32_t* __restrict__ edge_map,
                                            const int32_t* __restrict__ v_edges, int64_t V, int64_t F,
-                                           int64_t E, int max_edges, float lambda) {
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < V;
+                                           int64_t E, int max_edges, float lambda, int64_t v_begin = 0) {
+  // vertices v_begin .. V - 1 (a rank of the sharded update sweeps its own range and reads every vertex of x_in)
+  for (int64_t i = v_begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < V;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float x0 = xin[3 * i], x1 = xin[3 * i + 1], x2 = xin[3 * i + 2];
     float u0 = 0.f, u1 = 0.f, u2 = 0.f;
@@ -442,6 +443,24 @@ int fgc_vertex_update_edges(const float* x_in, float* x_out, const float* normal
     FGC_LAUNCHED("vertex_update_edges_kernel");
     src = dst;
   }
+  return FGC_OK;
+}
+
+// One Jacobi sweep of update_position2 over the vertices [v_begin, v_end): reads all of x_in, writes rows
+// v_begin .. v_end - 1 of x_out.  The building block of the sharded update (patches.vertex_update_edges_sharded:
+// every rank sweeps its range, one all-gather per sweep), bit-identical to the same sweep of fgc_vertex_update_edges.
+int fgc_vertex_update_edges_range(const float* x_in, float* x_out, const float* normals, const int32_t* edge_map,
+                                  const int32_t* v_edges, int64_t V, int64_t F, int64_t E, int max_edges,
+                                  int64_t v_begin, int64_t v_end, float lambda, void* stream) {
+  FGC_REQUIRE(x_in && x_out && normals && edge_map && v_edges && V > 0 && max_edges > 0, "vertex_update_edges_range: bad arguments");
+  FGC_REQUIRE(0 <= v_begin && v_begin <= v_end && v_end <= V, "vertex_update_edges_range: range [%lld, %lld) outside [0, %lld)",
+              static_cast<long long>(v_begin), static_cast<long long>(v_end), static_cast<long long>(V));
+  FGC_REQUIRE(x_in != x_out, "vertex_update_edges_range: a Jacobi sweep cannot run in place");
+  if (v_begin == v_end) return FGC_OK;
+  cudaStream_t st = as_stream(stream);
+  vertex_update_edges_kernel<<<vgrid(v_end - v_begin), 128, 0, st>>>(x_in, x_out, normals, edge_map, v_edges, v_end, F, E,
+                                                                      max_edges, lambda, v_begin);
+  FGC_LAUNCHED("vertex_update_edges_kernel");
   return FGC_OK;
 }
 

@@ -493,6 +493,25 @@ def vertex_update_edges(x, normals, edge_map, v_edges, iters=60, lam=1.0 / 18):
     return out
 
 
+def vertex_update_edges_range(x_in, x_out, normals, edge_map, v_edges, v_begin, v_end, lam=1.0 / 18):
+    """ONE sweep of update_position2 (reference Code/train.py:1467-1557) over vertices [v_begin, v_end): reads all of
+    x_in[V,3], writes rows v_begin..v_end-1 of x_out (in place on x_out; x_out may have padding rows past V)."""
+    L = _lib.lib()
+    x_in, normals = _f32(x_in, "x_in"), _f32(normals, "normals")
+    edge_map, v_edges = _i32(edge_map, "edge_map"), _i32(v_edges, "v_edges")
+    if x_out.dtype != torch.float32 or not x_out.is_contiguous() or x_out.device != x_in.device:
+        raise _lib.FacetConvError("vertex_update_edges_range: x_out must be a contiguous float32 tensor on x_in's device")
+    V = v_edges.shape[0]
+    if x_in.numel() < 3 * V or x_out.numel() < 3 * V:
+        raise _lib.FacetConvError("vertex_update_edges_range: x_in / x_out hold fewer than V = %d vertices" % V)
+    with torch.cuda.device(x_in.device):
+        check(L.fgc_vertex_update_edges_range(_p(x_in), _p(x_out), _p(normals), _p(edge_map), _p(v_edges), V,
+                                              normals.numel() // 3, edge_map.numel() // 4, v_edges.numel() // V,
+                                              int(v_begin), int(v_end), float(lam), _stream(x_in)),
+              "fgc_vertex_update_edges_range")
+    return x_out
+
+
 def vertex_update_ms(x, normals, faces, v_faces, scale, steps=2, iters=20):
     """One scale of reference Code/train.py:1668-1798 (update_position_MS)."""
     L = _lib.lib()

@@ -218,3 +218,46 @@ def grid_patches(nx: int, ny: int, block: int = 100, halo: int = 3, K: int = 16,
         out.append(Patch(x=featp, adjs=mesh.build_pyramid(adjp, 3, K), face_ids=fid, perm=None, core=core))
     del rs
     return out, 2 * nx * ny
+
+
+# ----------------------------------------------------------------------------- sharded vertex update (BASELINE config C5)
+def vertex_ranges(V: int, world: int):
+    """Equal contiguous vertex ranges, one per rank (the last ones may be short or empty): [(begin, end)] and the chunk."""
+    chunk = (V + world - 1) // world
+    return [(min(V, r * chunk), min(V, (r + 1) * chunk)) for r in range(world)], chunk
+
+
+def vertex_update_edges_sharded(x, normals, edge_map, v_edges, iters=60, lam=1.0 / 18, group=None, sweep=None):
+    """update_position2 (reference Code/train.py:1467-1557) with the vertices of ONE large mesh sharded over the ranks of
+    `group`: every rank holds the whole index tensors and all vertex positions, sweeps its own contiguous vertex range
+    (fgc_vertex_update_edges_range) and the ranges are exchanged with one all-gather per Jacobi sweep -- the only
+    exchange step of the path.  A Jacobi sweep reads nothing but the previous sweep's positions, so the result is
+    bit-identical to the single-device update.  `sweep(x_in, x_out, begin, end)` replaces the CUDA sweep in CPU tests.
+    x[V,3] -> x[V,3] on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    V = int(v_edges.shape[0])
+    if sweep is None:
+        from . import ops
+
+        def sweep(x_in, x_out, b, e):
+            ops.vertex_update_edges_range(x_in, x_out, normals, edge_map, v_edges, b, e, lam)
+    ranges, chunk = vertex_ranges(V, world)
+    b, e = ranges[rank]
+    cur = torch.zeros((world * chunk, 3), dtype=x.dtype, device=x.device)   # padded to equal shards for the all-gather
+    cur[:V] = x.reshape(V, 3)
+    nxt = torch.zeros_like(cur)
+    for _ in range(int(iters)):
+        sweep(cur, nxt, b, e)
+        if world > 1:
+            mine = nxt[rank * chunk:(rank + 1) * chunk]
+            if dist.get_backend(group) == "nccl":
+                dist.all_gather_into_tensor(nxt, mine, group=group)            # in place: shard r lands at rows r * chunk
+            else:
+                parts = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(parts, mine.clone(), group=group)
+                nxt.copy_(torch.cat(parts, 0))
+        cur, nxt = nxt, cur
+    return cur[:V].clone()

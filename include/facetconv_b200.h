@@ -265,6 +265,13 @@ FGC_API int fgc_vertex_update_edges(const float* x_in, float* x_out, const float
                             const int32_t* edge_map, const int32_t* v_edges, int64_t V, int64_t F,
                             int64_t E, int max_edges, int iters, float lambda, void* workspace,
                             size_t workspace_bytes, void* stream);
+/* ONE sweep of the same update over the vertex range [v_begin, v_end): reads every row of x_in, writes rows
+ * v_begin .. v_end-1 of x_out (x_out != x_in).  Lets N ranks shard the vertices of a large scan (BASELINE config C5,
+ * reference Code/train.py:1467-1557 run on one device there): each sweeps its range, one all-gather per sweep. */
+FGC_API int fgc_vertex_update_edges_range(const float* x_in, float* x_out, const float* normals,
+                                  const int32_t* edge_map, const int32_t* v_edges, int64_t V, int64_t F,
+                                  int64_t E, int max_edges, int64_t v_begin, int64_t v_end, float lambda,
+                                  void* stream);
 /* reference Code/train.py:1668-1798 (update_position_MS + updateFacesCenter) for ONE scale:
  * `iters` sweeps of  x_v += (1/#faces_v) sum_{f in v_faces[v]} n_F (n_F.(c_F - x_v)),
  * F = f >> (2*scale) (floor, -1 stays padding), c = face centres pooled `scale` times with

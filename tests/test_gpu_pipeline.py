@@ -187,3 +187,31 @@ def test_from_raw_mesh_to_denoised_vertices_equals_the_reference_pipeline(tmp_pa
     mesh_io.write_mesh(xo[0].cpu().numpy(), g["F"], str(tmp_path / "out.obj"))
     V2, _, _, F2, _ = mesh_io.load_mesh(str(tmp_path), "out.obj")
     assert np.array_equal(F2, g["F"]) and np.abs(V2 - g["verts_out"][0]).max() < 1e-4
+
+
+def test_range_sweeps_reproduce_the_one_call_vertex_update_bit_for_bit():
+    """fgc_vertex_update_edges_range (the building block of the sharded C5 update, patches.vertex_update_edges_sharded):
+    three vertex ranges per sweep, ping-pong buffers, 9 sweeps == fgc_vertex_update_edges with iters = 9, and the
+    sharded driver itself (world size 1 here; world 2 runs under gloo in tests/test_multi_rank_cpu.py)."""
+    from facet_graph_convolution_b200 import mesh, ops, patches
+    V, F = mesh.grid_mesh(40, 30)
+    rs = np.random.RandomState(7)
+    V = (V + rs.randn(*V.shape) * 0.01).astype(np.float32)
+    n = rs.randn(F.shape[0], 3).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    em, ve = mesh.edge_maps(F, 20)
+    dev = torch.device("cuda:0")
+    tx, tn = torch.from_numpy(V).to(dev), torch.from_numpy(n).to(dev)
+    tem, tve = torch.from_numpy(em.astype(np.int32)).to(dev), torch.from_numpy(ve.astype(np.int32)).to(dev)
+    ref = ops.vertex_update_edges(tx, tn, tem, tve, iters=9)
+    nv = V.shape[0]
+    cuts = [0, nv // 3 + 1, (2 * nv) // 3, nv]
+    cur, nxt = tx.clone(), torch.empty_like(tx)
+    for _ in range(9):
+        for b, e in zip(cuts, cuts[1:]):
+            ops.vertex_update_edges_range(cur, nxt, tn, tem, tve, b, e)
+        cur, nxt = nxt, cur
+    assert torch.equal(cur, ref)
+    assert torch.equal(patches.vertex_update_edges_sharded(tx, tn, tem, tve, iters=9), ref)
+    with pytest.raises(RuntimeError):
+        ops.vertex_update_edges_range(cur, nxt, tn, tem, tve, 5, nv + 1)

@@ -269,3 +269,61 @@ def test_grad_bucket_rejects_an_empty_parameter_list_and_the_network_has_its_par
     ms = fm.DenoisingNet(device="cpu", seed=0, multi_scale=True)
     assert sum(p.numel() for p in ms.parameters()) == 679005
     T.GradBucket(ps)                                      # an optimizer can be set up before the first forward
+
+
+# ----------------------------------------------------------------------------- sharded vertex update (config C5)
+def _vertex_case():
+    from facet_graph_convolution_b200 import mesh
+    V, F = mesh.grid_mesh(9, 7)
+    rs = np.random.RandomState(4)
+    V = (V + rs.randn(*V.shape) * 0.02).astype(np.float32)
+    n = rs.randn(F.shape[0], 3).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    em, ve = mesh.edge_maps(F, 20)
+    return V, n, em.astype(np.int32), ve.astype(np.int32)
+
+
+def _oracle_sweep(normals, edge_map, v_edges):
+    """one Jacobi sweep of update_position2 over a vertex range, from the oracle's closed form (fp64)"""
+    from oracle import closed_form as cf
+
+    def sweep(x_in, x_out, b, e):
+        V = v_edges.shape[0]
+        full = cf.update_position2(x_in[:V].numpy(), normals, edge_map, v_edges, iter_num=1)
+        x_out[b:e] = torch.from_numpy(full[b:e])
+    return sweep
+
+
+def _vertex_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from facet_graph_convolution_b200 import patches
+        V, n, em, ve = _vertex_case()
+        out = patches.vertex_update_edges_sharded(torch.from_numpy(V.astype(np.float64)), n, em, ve, iters=7,
+                                                  sweep=_oracle_sweep(n, em, ve))
+        q.put((rank, out.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_sharded_vertex_update_equals_the_single_process_update():
+    from oracle import closed_form as cf
+    from facet_graph_convolution_b200 import patches
+    V, n, em, ve = _vertex_case()
+    ref = cf.update_position2(V.astype(np.float64), n, em, ve, iter_num=7)
+    ranges, chunk = patches.vertex_ranges(V.shape[0], 3)
+    assert ranges[0][0] == 0 and ranges[-1][1] == V.shape[0] and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert chunk * 3 >= V.shape[0]
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_vertex_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(2):                      # every rank ends with the whole mesh, equal to the unsharded update
+        assert np.array_equal(got[r], ref), np.abs(got[r] - ref).max()
