@@ -1,5 +1,6 @@
 """BASELINE config C5, vertex part: update_position2 (reference Code/train.py:1467-1557, 60 Jacobi sweeps) over ONE large
-mesh, single device against the vertex-sharded update (every rank sweeps its vertex range, one NCCL all-gather per sweep).
+mesh, single device against the vertex-sharded update (every rank sweeps its vertex range; per sweep one NCCL all-to-all
+of the halo vertices, or one all-gather of all positions).
 
     python benchmarks/vertex_update_bench.py [--grid 3162] [--iters 60]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
@@ -68,8 +69,12 @@ def main():
         return out, ms
 
     single, ms_single = timed(lambda it: ops.vertex_update_edges(Vd, n, e_map, v_e, iters=it))
-    sharded, ms_sharded = timed(lambda it: patches.vertex_update_edges_sharded(Vd, n, e_map, v_e, iters=it))
-    same = bool(torch.equal(single.reshape(-1, 3), sharded.reshape(-1, 3)))
+    sharded, ms_sharded = timed(lambda it: patches.vertex_update_edges_sharded(Vd, n, e_map, v_e, iters=it, exchange="halo"))
+    gathered, ms_gather = timed(lambda it: patches.vertex_update_edges_sharded(Vd, n, e_map, v_e, iters=it,
+                                                                                exchange="allgather"))
+    same = bool(torch.equal(single.reshape(-1, 3), sharded.reshape(-1, 3)) and
+                torch.equal(single.reshape(-1, 3), gathered.reshape(-1, 3)))
+    halo_rows = int(patches.VertexHalo(e_map, v_e).need.numel()) if world > 1 else 0
     if world > 1:
         t = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -78,12 +83,13 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": "update_position2 sweeps/s over one mesh", "n_gpus": world, "vertices": nv, "faces": nf, "edges": ne,
-            "iters": args.iters, "ms_single_device": ms_single, "ms_sharded": ms_sharded,
-            "speedup": ms_single / ms_sharded, "bit_identical": same,
-            "allgather_bytes_per_sweep": 12 * nv, "algorithmic_GBps_single": args.iters * sweep_bytes / (ms_single * 1e-3) / 1e9,
+            "iters": args.iters, "ms_single_device": ms_single, "ms_sharded": ms_sharded, "ms_sharded_allgather": ms_gather,
+            "speedup": ms_single / ms_sharded, "bit_identical": same, "halo_rows_rank0": halo_rows,
+            "halo_bytes_per_sweep_rank0": 12 * halo_rows, "allgather_bytes_per_sweep": 12 * nv, "algorithmic_GBps_single": args.iters * sweep_bytes / (ms_single * 1e-3) / 1e9,
             "algorithmic_GBps_sharded": args.iters * sweep_bytes / (ms_sharded * 1e-3) / 1e9, "setup_s": t_setup,
             "config": {"workload": "C5 vertex update: %dx%d-quad height field, %d sweeps; sharded = contiguous vertex ranges over "
-                                   "%d rank(s), one NCCL all-gather of the positions per sweep" % (args.grid, args.grid,
+                                   "%d rank(s), one NCCL all-to-all of the halo positions per sweep (ms_sharded; setup of the "
+                                   "halo lists included) or one all-gather of all positions per sweep (ms_sharded_allgather)" % (args.grid, args.grid,
                                                                                                    args.iters, world)}}))
     if world > 1:
         dist.destroy_process_group()

@@ -2,20 +2,22 @@
 // :870-932 with M = 9; also the M = 8 benchmark layer): per-facet aggregation on the warp-level tensor path
 // (mma.sync m16n8k16), contraction with W on tcgen05.  No tile plan, no per-tile row dedup: works on any adjacency.
 //
-//   stage 1 (16 aggregator warps, one facet at a time per warp, registers only)
+//   stage 1 (16 aggregator warps, one facet at a time per warp)
 //       S_n[m, c] = sum_k q[n,k,m] x_{j_k}[c]            A = q  (16 x 16: rows m, columns = neighbour slots)
 //                                                         B = the 16 gathered rows of the fp16 hi|lo image of x
 //       q is computed in the A-fragment layout (lane (g,t) owns row m = g and slots 2t,2t+1,2t+8,2t+9; the
-//       softmax normaliser is a 3-step shuffle sum over the 8 g-lanes), the gathered rows are loaded straight
-//       from global / L1 as 16-byte units (lane (g,t): channels 8g..8g+7 of the rows of its four slots) and
-//       turned into B fragments with byte permutes: n-block nb of the MMA holds channels {8g'+nb}.
-//       q_hi.x_hi + q_lo.x_hi + q_hi.x_lo in fp32 accumulators = fp32-class precision.
-//       M = 9: rows 8..15 of A all carry q[.,8] (every lane then owns a copy of S[8,.] and converts 2 of its 64
-//       values); M = 8: rows 8..15 carry q_lo, so two MMAs per n-block instead of three.
+//       softmax normaliser is a 3-step shuffle sum over the 8 g-lanes, the four slots side by side).  The gathered
+//       rows go global -> shared with 16-byte cp.async (eight lanes per 128-byte line) into a per-warp 4 KB stage,
+//       128B-swizzled, and come back as B fragments with ldmatrix.x4.trans; the copies of facet n+1 fly under the
+//       MMAs, the drain and the next softmax.  q_hi.x_hi + q_lo.x_hi + q_hi.x_lo in fp32 accumulators = fp32-class
+//       precision.  M = 9: rows 8..15 of A all carry q[.,8] (every lane then owns a copy of S[8,.] and converts 2 of
+//       its 64 values); M = 8: rows 8..15 carry q_lo, so two MMAs per n-block instead of three.
 //   drain   S -> fp16 hi (11 bits, exact) + fp16 residual -> shared memory, directly in the K-major 128B-swizzled
 //       layout of the B operand of stage 2 ([hi rows of the tile's 32 facets | lo rows], one 64-element atom per
-//       (weight pair, unit parity) so that the 16-byte stores of a quarter warp hit 8 different bank groups).
-//   stage 2 (one elected thread)   Y^T[(h,o), f] = sum_{m,c} [Wh;Wl][(h,o),(m,c)] [Sh|Sl][(m,c), f]
+//       (weight pair, channel half) so that the 16-byte stores of a quarter warp hit 8 different bank groups).
+//       Hand-over: one mbarrier arrive per warp and tile, no fence in the aggregators.
+//   stage 2 (epilogue warp 0, one elected thread, after the generic->async proxy fence)
+//       Y^T[(h,o), f] = sum_{m,c} [Wh;Wl][(h,o),(m,c)] [Sh|Sl][(m,c), f]
 //       tcgen05.mma M = 128, N = 64, K = 64 M, A = the weight image resident in TMEM for the CTA's lifetime.
 //   epilogue (4 warps on the TMEM lane quadrants)  y = act(inv_cnt * scale * (Wh.Sh + Wh.Sl + 2^-11 Wl.Sh) + flag * b),
 //       optional max over groups of 4 rows (custom_binary_tree_pooling, model.py:863,875) and max|y| for the
@@ -35,7 +37,6 @@ namespace {
 constexpr int kHT = 32;                              // facets per tile
 constexpr int kHAgg = 16;                            // aggregator warps
 constexpr int kHFpw = kHT / kHAgg;                   // facets per warp and tile
-constexpr int kHThreads = (4 + kHAgg) * 32;          // 4 epilogue warps + aggregators (5 warps per sub-partition)
 
 template <int M>
 struct HmCfg {
@@ -52,7 +53,6 @@ struct HmCfg {
   static_assert(W_COLS <= D_COL && D_COL + 2 * ND <= 512, "TMEM overflow");
 };
 
-enum { HB_B3_FREE = 0, HB_D_FULL = 2, HB_D_FREE = 4, HB_NUM = 6 };
 
 struct HmParams {
   alignas(64) unsigned char tmap[128];   // CUtensorMap of the whole image (second-generation kernel, TMA row gather)
@@ -116,16 +116,6 @@ __device__ __forceinline__ void split_trunc(float a, float b, uint32_t& hi, uint
 }
 __device__ __forceinline__ uint32_t w4(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
-// ---- aggregator building blocks.  Work item = (facet, group of 16 neighbour slots); K <= 16: one item per facet.
-// The inputs of item n+1 (and the adjacency ids of item n+2) are in flight while item n is computed.
-struct HmPre {            // prefetched inputs of one item
-  uint4 xh[4], xl[4];     // 16-byte unit g of the hi / lo plane of the rows of this lane's four slots
-  float2 vl[4];           // neighbour logits of weights g and 8 of those slots (max-shifted, in log2 units)
-  float2 uo;              // own logits of weights g and 8
-  int okm;                // bit i: slot i holds a valid neighbour
-  int nz;                 // non-zero ids among this lane's four slots
-};
-
 template <bool ZERO_C>
 __device__ __forceinline__ void hm_mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                        uint32_t b1) {
@@ -135,106 +125,6 @@ __device__ __forceinline__ void hm_mma(float (&d)[4], uint32_t a0, uint32_t a1, 
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
   } else {
     hmma16816(d, a0, a1, a2, a3, b0, b1);
-  }
-}
-
-// acc (+)= contribution of the item's 16 slots; returns the number of non-zero ids among them
-template <int M, bool FIRST>
-__device__ __forceinline__ int hm_mma_item(const HmPre& in, float (&acc)[8][4], bool recentre) {
-  int c = in.nz;
-  c += __shfl_xor_sync(0xffffffffu, c, 1);
-  c += __shfl_xor_sync(0xffffffffu, c, 2);
-  float qg[4], q8[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    // logits arrive max-shifted per row and in log2 units: uo' + vl' <= 0, and the largest of the M sums is
-    // >= -(smaller of the two rows' spreads), so exp2 cannot underflow for all M at once unless the pre-pass
-    // raised its flag -- then (warp-uniform) the exact maximum over m is subtracted as the reference's softmax does
-    float ag = in.uo.x + in.vl[i].x;
-    float a8 = (M == 9) ? in.uo.y + in.vl[i].y : 0.f;
-    if (recentre) {
-      float mx = (M == 9) ? fmaxf(ag, a8) : ag;
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-      ag -= mx, a8 -= mx;
-    }
-    const float eg = ex2_approx(ag);
-    const float e8 = (M == 9) ? ex2_approx(a8) : 0.f;
-    float z = eg;
-    z += __shfl_xor_sync(0xffffffffu, z, 4);
-    z += __shfl_xor_sync(0xffffffffu, z, 8);
-    z += __shfl_xor_sync(0xffffffffu, z, 16);
-    z += e8;
-    const float rs = ((in.okm >> i) & 1) ? rcp_approx(z) : 0.f;
-    qg[i] = eg * rs;
-    q8[i] = e8 * rs;
-  }
-  uint32_t gh0, gl0, gh1, gl1, eh0 = 0, el0 = 0, eh1 = 0, el1 = 0;
-  split_rn(qg[0], qg[1], gh0, gl0);
-  split_rn(qg[2], qg[3], gh1, gl1);
-  if (M == 9) {
-    split_rn(q8[0], q8[1], eh0, el0);
-    split_rn(q8[2], q8[3], eh1, el1);
-  }
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    const uint32_t sel = (nb & 1) ? 0x7632u : 0x5410u;
-    const uint32_t b0 = __byte_perm(w4(in.xh[0], nb >> 1), w4(in.xh[1], nb >> 1), sel);
-    const uint32_t b1 = __byte_perm(w4(in.xh[2], nb >> 1), w4(in.xh[3], nb >> 1), sel);
-    if (M == 9) {
-      hm_mma<FIRST>(acc[nb], gh0, eh0, gh1, eh1, b0, b1);
-      hm_mma<false>(acc[nb], gl0, el0, gl1, el1, b0, b1);
-    } else {
-      hm_mma<FIRST>(acc[nb], gh0, gl0, gh1, gl1, b0, b1);   // rows g: q_hi.x_hi, rows g+8: q_lo.x_hi
-    }
-  }
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    const uint32_t sel = (nb & 1) ? 0x7632u : 0x5410u;
-    const uint32_t b0 = __byte_perm(w4(in.xl[0], nb >> 1), w4(in.xl[1], nb >> 1), sel);
-    const uint32_t b1 = __byte_perm(w4(in.xl[2], nb >> 1), w4(in.xl[3], nb >> 1), sel);
-    if (M == 9) hm_mma<false>(acc[nb], gh0, eh0, gh1, eh1, b0, b1);
-    else hm_mma<false>(acc[nb], gh0, 0u, gh1, 0u, b0, b1);
-  }
-  return c;
-}
-
-// S of facet f (C fragments) -> fp16 hi/lo rows of the stage-2 B operand.
-// rows m = g of units 2t (c0) and 2t+1 (c1) -> atoms 2(g>>1) + {0,1}, slot 4(g&1) + t
-template <int M>
-__device__ __forceinline__ void hm_drain(uint8_t* b3, int f, int g, int t, const float (&acc)[8][4]) {
-  using Cfg = HmCfg<M>;
-  const int sw = f & 7;
-  uint8_t* rh = b3 + (f >> 3) * 1024 + sw * 128;              // hi row f of an atom
-  uint8_t* rl = rh + (kHT >> 3) * 1024;                       // lo row 32 + f
-  const int slot = (((g & 1) * 4 + t) ^ sw) << 4;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float v0 = acc[2 * j][h], v1 = acc[2 * j + 1][h];
-      if (M == 8) v0 += acc[2 * j][2 + h], v1 += acc[2 * j + 1][2 + h];
-      split_trunc(v0, v1, hi[j], lo[j]);
-    }
-    const int aoff = (2 * (g >> 1) + h) * Cfg::ATOM_BYTES + slot;
-    *reinterpret_cast<uint4*>(rh + aoff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(rl + aoff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  }
-  if (M == 9) {
-    // row m = 8 (every lane holds a copy): lane (g,t) converts channels 16t + 8(g>>2) + 2(g&3), +1
-    const int gq = g & 3;
-    const bool up = g >= 4;
-    const float e0 = gq == 0 ? acc[0][2] : (gq == 1 ? acc[2][2] : (gq == 2 ? acc[4][2] : acc[6][2]));
-    const float e1 = gq == 0 ? acc[1][2] : (gq == 1 ? acc[3][2] : (gq == 2 ? acc[5][2] : acc[7][2]));
-    const float o0 = gq == 0 ? acc[0][3] : (gq == 1 ? acc[2][3] : (gq == 2 ? acc[4][3] : acc[6][3]));
-    const float o1 = gq == 0 ? acc[1][3] : (gq == 1 ? acc[3][3] : (gq == 2 ? acc[5][3] : acc[7][3]));
-    uint32_t hi, lo;
-    split_trunc(up ? o0 : e0, up ? o1 : e1, hi, lo);
-    const int off = 8 * Cfg::ATOM_BYTES + (((2 * t + (g >> 2)) ^ sw) << 4) + gq * 4;
-    *reinterpret_cast<uint32_t*>(rh + off) = hi;
-    *reinterpret_cast<uint32_t*>(rl + off) = lo;
   }
 }
 
@@ -373,180 +263,10 @@ __device__ __forceinline__ void hm_epilogue(const HmParams& p, uint64_t* bars, c
   }
 }
 
-template <int M, int NG>
-__global__ void __launch_bounds__(kHThreads, 1)
-conv_hm_kernel(const HmParams p) {
-  using Cfg = HmCfg<M>;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + HB_NUM);
-  unsigned* arrived = reinterpret_cast<unsigned*>(tmem_slot + 2);   // [2] aggregator warps done with B3 buffer b
-  float* invtab = reinterpret_cast<float*>(arrived + 2);            // [33] 1 / cnt (0 for cnt = 0)
-  float* rowinv = reinterpret_cast<float*>(smem + Cfg::OFF_ROW);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nepi = p.cout >> 4;   // epilogue warps with outputs
-  // tiles blockIdx.x, + gridDim.x, ...  (a contiguous range per CTA was measured slower: 0.67 vs 0.63 ms per 562 k rows)
-  const int my_tiles = static_cast<int>((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&bars[HB_B3_FREE + i], 1);
-      tc::mbar_init(&bars[HB_D_FULL + i], 1), tc::mbar_init(&bars[HB_D_FREE + i], nepi);
-      arrived[i] = 0;
-    }
-    tc::mbar_fence_init();
-  }
-  if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
-  if (warp == 5 && lane <= 32 - 1) invtab[lane + 1] = 1.f / static_cast<float>(lane + 1), invtab[0] = 0.f;
-  tc::tc_fence_before_sync();
-  __syncthreads();
-  tc::tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-
-  {
-    // weight operand -> TMEM: lane 32 q + l of the image is TMEM lane 32 q + l, column = K pair.  A warp reaches the
-    // TMEM lanes of quadrant warp % 4 only; the five warps of a quadrant share its 32-column chunks (a launch over a
-    // few patches is short enough for this prologue -- 147 KB per CTA -- to show when four warps do it alone)
-    const int q = warp & 3;
-    const uint32_t* src = p.wt + static_cast<size_t>(q * 32 + lane) * Cfg::W_COLS;
-#pragma unroll 1
-    for (int c0 = (warp >> 2) * 32; c0 < Cfg::W_COLS; c0 += (kHThreads / 128) * 32) {
-      uint32_t r[32];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint4 tq = __ldg(reinterpret_cast<const uint4*>(src + c0) + u);
-        r[4 * u] = tq.x, r[4 * u + 1] = tq.y, r[4 * u + 2] = tq.z, r[4 * u + 3] = tq.w;
-      }
-      tc::tmem_st32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
-    }
-    tc::tc_wait_st();
-    tc::tc_fence_before_sync();
-  }
-  __syncthreads();
-  tc::tc_fence_after_sync();
-
-  if (warp < 4) {
-    // =========================================================== epilogue: Y (TMEM) -> global
-    if (warp < nepi) hm_epilogue<Cfg, HB_D_FULL, HB_D_FREE>(p, bars, rowinv, tmem, warp, lane);
-  } else {
-    // =========================================================== aggregators (+ stage-2 issue by the last to arrive)
-    // Facet n of this warp: tile counter n / kHFpw, facet n % kHFpw of the warp's own; item m = n * NG + slot group.
-    const int aw = warp - 4;
-    const int g = lane >> 2, t = lane & 3;
-    const int nitems = my_tiles * kHFpw * NG;
-    const int rows32 = static_cast<int>(p.rows);
-    constexpr uint32_t idesc = (1u << 4) | ((static_cast<uint32_t>(Cfg::ND) >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t sb = tc::smem_u32(smem);
-    const float2* lg_v = reinterpret_cast<const float2*>(p.lg) + g;                             // neighbour pair of row j: lg_v[8 j]
-    const float2* lg_u = lg_v + static_cast<int64_t>(p.zrow + 1) * 8;                           // own pair of row r: lg_u[8 r]
-    const uint4* img_g = p.img + g;
-    const bool recentre = __ldg(p.flag) != 0;
-    auto row_of = [&](int m) -> int {   // global row of item m, -1 when there is none
-      const int n = m / NG;
-      const int r = (static_cast<int>(blockIdx.x) + (n / kHFpw) * static_cast<int>(gridDim.x)) * kHT + aw * kHFpw + (n % kHFpw);
-      return (m < nitems && r < rows32) ? r : -1;
-    };
-    auto load_ids = [&](int m, int (&id)[4]) {
-      const int r = row_of(m);
-      const int32_t* arow = p.adj + static_cast<int64_t>(r < 0 ? 0 : r) * p.K + (m % NG) * 16 + 2 * t;
-      const int kmax = (r < 0) ? 0 : p.K - (m % NG) * 16 - 2 * t;   // slots of this lane: offsets 0, 1, 8, 9
-      id[0] = (0 < kmax) ? __ldg(arow) : 0;
-      id[1] = (1 < kmax) ? __ldg(arow + 1) : 0;
-      id[2] = (8 < kmax) ? __ldg(arow + 8) : 0;
-      id[3] = (9 < kmax) ? __ldg(arow + 9) : 0;
-    };
-    int base_cur = 0, base_next = p.N;     // batch element of the rows the issue stage walks (monotone)
-    auto issue = [&](int m, const int (&id)[4], HmPre& o) {
-      const int r = row_of(m);
-      int base = 0;
-      if (!p.single && r >= 0) {
-        while (r >= base_next) base_cur = base_next, base_next += p.N;
-        base = base_cur;
-      }
-      o.uo = __ldg(lg_u + static_cast<int64_t>((r < 0 ? 0 : r) >> p.upshift) * 8);
-      o.okm = 0, o.nz = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool ok = static_cast<unsigned>(id[i] - 1) < static_cast<unsigned>(p.N);
-        const int row = ok ? ((base + id[i] - 1) >> p.upshift) : p.zrow;   // zrow: all-zero image / logit row
-        o.okm |= ok ? (1 << i) : 0;
-        o.nz += (id[i] != 0);
-        o.vl[i] = __ldg(lg_v + static_cast<int64_t>(row) * 8);
-        const uint4* src = img_g + static_cast<int64_t>(row) * p.img_ld;
-        o.xh[i] = __ldg(src);
-        o.xl[i] = __ldg(src + 8);
-      }
-    };
-    float acc[8][4];
-    int cnt = 0;
-    auto finish = [&](int m) {   // the facet of item m is aggregated: drain, and after the warp's last facet hand over
-      const int n = m / NG, it = n / kHFpw, fi = n % kHFpw, buf = it & 1, f = aw * kHFpw + fi;
-      if (fi == 0) tc::mbar_wait(&bars[HB_B3_FREE + buf], ((it >> 1) & 1) ^ 1);
-      hm_drain<M>(smem + buf * Cfg::B3_BUF, f, g, t, acc);
-      if (lane == 0) rowinv[(it & 3) * kHT + f] = invtab[cnt];
-      if (fi != kHFpw - 1) return;
-      // this warp's rows of the tile are in place: the last of the 8 warps to get here issues stage 2
-      tc::fence_proxy_async_smem();
-      __syncwarp();
-      int last = 0;
-      if (lane == 0) {
-        __threadfence_block();
-        last = (atomicAdd(&arrived[buf], 1u) & (kHAgg - 1)) == kHAgg - 1;
-      }
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
-        __threadfence_block();
-        tc::fence_proxy_async_smem();
-        tc::mbar_wait(&bars[HB_D_FREE + buf], ((it >> 1) & 1) ^ 1);
-        tc::tc_fence_after_sync();
-        if (tc::elect_one()) {
-          const uint32_t b3 = sb + buf * Cfg::B3_BUF;
-#pragma unroll 1
-          for (int a = 0; a < Cfg::NATOM; ++a) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t bd = tc::smem_desc_k_sw128(b3 + a * Cfg::ATOM_BYTES + ks * 32);
-              tc::mma_f16_ts(tmem + Cfg::D_COL + buf * Cfg::ND, tmem + a * 32 + ks * 8, bd, idesc, (a | ks) ? 1u : 0u);
-            }
-          }
-          tc::tc_commit(&bars[HB_B3_FREE + buf]);
-          tc::tc_commit(&bars[HB_D_FULL + buf]);
-        }
-        __syncwarp();
-      }
-    };
-    // The adjacency ids of the next item are in flight while the current one is gathered and aggregated; memory
-    // latency is otherwise covered by the other four aggregator warps of the sub-partition.  (Issuing the row loads
-    // of item m+1 right after the MMAs of item m, to fly under its drain, was measured SLOWER: 0.82 vs 0.63 ms per
-    // 562 k rows -- the proxy fence at the end of a warp's facets then waits for those loads.)
-    HmPre P;
-    int idc[4], idn[4];
-    load_ids(0, idc);
-#pragma unroll 1
-    for (int m = 0; m < nitems; m += NG) {
-      load_ids(m + 1, idn);
-      issue(m, idc, P);
-      cnt = hm_mma_item<M, true>(P, acc, recentre);
-      if (NG == 2) {
-        load_ids(m + 2, idc);
-        issue(m + 1, idn, P);
-        cnt += hm_mma_item<M, false>(P, acc, recentre);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) idc[i] = idn[i];
-      }
-      finish(m + NG - 1);
-    }
-  }
-  tc::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem, 512);
-}
-
 // =====================================================================================================================
-// Second generation of the same kernel (default; FGC_HM_V1=1 selects the one above for comparisons).
-// What changes, and why (ncu of the kernel above, profiles/r2_summary.md: 583 warp instructions and ~190 L1 data-pipe
-// wavefronts per facet at an IPC of 0.45 per sub-partition; every aggregator warp ran load -> wait -> compute -> fence):
+// The kernel.  Second generation: the first (git history; profiles/r2_summary.md: register-staged 16-byte gathers with
+// byte permutes, a proxy fence per warp and tile, 583 warp instructions and ~190 L1 data-pipe wavefronts per facet at an
+// IPC of 0.45 per sub-partition, every aggregator warp running load -> wait -> compute -> fence) differed in this:
 //   * the 16 gathered rows of a facet go global -> shared with cp.async (16-byte units, eight consecutive lanes copy one
 //     128-byte line: 4 wavefronts per instruction instead of 16) into a 4 KB per-warp stage, 128B-swizzled, and come
 //     back as B fragments with ldmatrix.x4.trans (natural channel order: no byte permutes, no register staging);
@@ -953,7 +673,7 @@ conv_hm2_kernel(const __grid_constant__ HmParams p) {
 // (slot s of the atom: m = 2(a>>1) + (s>>2), unit = 2(s&3) + (a&1)), atom 8 holds m = 8.
 __global__ void __launch_bounds__(1024)
 prep_wt_kernel(const float* __restrict__ W0, uint32_t* __restrict__ wt, float* __restrict__ wunscale, int M, int Cout,
-               int Cw, int CB, int nunits, int v1_order) {
+               int Cw, int CB, int nunits) {
   __shared__ float red[32];
   const int total = M * Cout * Cw;
   float mx = 0.f;
@@ -981,9 +701,9 @@ prep_wt_kernel(const float* __restrict__ W0, uint32_t* __restrict__ wt, float* _
       int m, c;
       if (a < 8) {
         m = 2 * (a >> 1) + (s >> 2);
-        // second-generation kernel (hm2_drain): chunk s = 4 (m & 1) + t, element pos = 2 (u & 3) + j of atom 2 (m >> 1) + h
-        // holds channel 8 (4 h + (u & 3)) + 2 t + j; first generation: unit 2 (s & 3) + (a & 1), element pos
-        c = v1_order ? (2 * (s & 3) + (a & 1)) * 8 + pos : 8 * (4 * (a & 1) + (pos >> 1)) + 2 * (s & 3) + (pos & 1);
+        // hm2_drain's order: chunk s = 4 (m & 1) + t, element pos = 2 (u & 3) + j of atom 2 (m >> 1) + h holds channel
+        // 8 (4 h + (u & 3)) + 2 t + j
+        c = 8 * (4 * (a & 1) + (pos >> 1)) + 2 * (s & 3) + (pos & 1);
       } else {
         m = 8, c = kpos & 63;
       }
@@ -1012,15 +732,6 @@ hm_absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
-}
-
-// FGC_HM_V1=1: the first-generation kernel (register-staged gathers) instead of the cp.async / ldmatrix one
-bool hm_use_v1() {
-  static const bool v = [] {
-    const char* e = getenv("FGC_HM_V1");
-    return e != nullptr && e[0] == '1';
-  }();
-  return v;
 }
 
 size_t hm_img_bytes(int64_t rows_img, int nunits) { return static_cast<size_t>(rows_img) * nunits * 256; }
@@ -1057,8 +768,7 @@ size_t conv_hm_weights_bytes(int Cw, int Cout, int M) {
 int launch_conv_hm_weights(const float* W0, int M, int Cout, int Cw, void* wbuf, cudaStream_t st) {
   const int nunits = (Cw + 63) / 64, CB = Cout < 64 ? Cout : 64, nob = Cout / CB;
   float* wunscale = reinterpret_cast<float*>(static_cast<char*>(wbuf) + align_up(hm_wt_bytes(M, nunits * nob), 256));
-  prep_wt_kernel<<<dim3(4, nunits * nob), 1024, 0, st>>>(W0, static_cast<uint32_t*>(wbuf), wunscale, M, Cout, Cw, CB, nunits,
-                                                                hm_use_v1() ? 1 : 0);
+  prep_wt_kernel<<<dim3(4, nunits * nob), 1024, 0, st>>>(W0, static_cast<uint32_t*>(wbuf), wunscale, M, Cout, Cw, CB, nunits);
   FGC_LAUNCHED("prep_w_image_kernel");
   return FGC_OK;
 }
@@ -1083,18 +793,14 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg,
     static const bool trace = getenv("FGC_HM_TRACE") != nullptr;
     hp.trace = trace ? 1 : 0;
   }
-  const bool v1 = hm_use_v1();
-  // second generation: rows by TMA gather on request (FGC_TMA_MODES bit 4; slower than cp.async here, see make_hm_img_tmap)
-  const bool tma = !v1 && make_hm_img_tmap(hp.tmap, img, rows_img + 1, nunits);
-  auto kern = v1 ? (M == 9 ? (K <= 16 ? conv_hm_kernel<9, 1> : conv_hm_kernel<9, 2>)
-                           : (K <= 16 ? conv_hm_kernel<8, 1> : conv_hm_kernel<8, 2>))
-                 : tma ? (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, true> : conv_hm2_kernel<9, 2, true>)
-                                 : (K <= 16 ? conv_hm2_kernel<8, 1, true> : conv_hm2_kernel<8, 2, true>))
-                       : (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, false> : conv_hm2_kernel<9, 2, false>)
-                                 : (K <= 16 ? conv_hm2_kernel<8, 1, false> : conv_hm2_kernel<8, 2, false>));
-  const int smem = v1 ? (M == 9 ? HmCfg<9>::SMEM_BYTES : HmCfg<8>::SMEM_BYTES)
-                      : (M == 9 ? Hm2Cfg<9>::SMEM_BYTES2 : Hm2Cfg<8>::SMEM_BYTES2);
-  const int threads = v1 ? kHThreads : kH2Threads;
+  // rows by TMA gather on request (FGC_TMA_MODES bit 4; slower than cp.async here, see make_hm_img_tmap)
+  const bool tma = make_hm_img_tmap(hp.tmap, img, rows_img + 1, nunits);
+  auto kern = tma ? (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, true> : conv_hm2_kernel<9, 2, true>)
+                            : (K <= 16 ? conv_hm2_kernel<8, 1, true> : conv_hm2_kernel<8, 2, true>))
+                  : (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, false> : conv_hm2_kernel<9, 2, false>)
+                            : (K <= 16 ? conv_hm2_kernel<8, 1, false> : conv_hm2_kernel<8, 2, false>));
+  const int smem = M == 9 ? Hm2Cfg<9>::SMEM_BYTES2 : Hm2Cfg<8>::SMEM_BYTES2;
+  const int threads = kH2Threads;
   FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int64_t grid = num_sms();
   if (grid > hp.ntiles) grid = hp.ntiles;

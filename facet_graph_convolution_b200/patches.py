@@ -227,12 +227,73 @@ def vertex_ranges(V: int, world: int):
     return [(min(V, r * chunk), min(V, (r + 1) * chunk)) for r in range(world)], chunk
 
 
-def vertex_update_edges_sharded(x, normals, edge_map, v_edges, iters=60, lam=1.0 / 18, group=None, sweep=None):
+class VertexHalo:
+    """Which vertex positions a rank of the sharded update must receive from / send to its peers every sweep: the
+    vertices its own range reads through update_position2's index tensors (the two ends of every edge around an owned
+    vertex) that another rank owns.  Built once per mesh from v_edges / edge_map (one exchange of id lists)."""
+
+    def __init__(self, edge_map, v_edges, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        V = int(v_edges.shape[0])
+        ranges, chunk = vertex_ranges(V, self.world)
+        self.begin, self.end = ranges[self.rank]
+        dev = v_edges.device
+        ve = v_edges[self.begin:self.end].reshape(-1).long()
+        ve = ve[(ve >= 0) & (ve < edge_map.shape[0])]
+        ends = edge_map[:, :2].long()[torch.unique(ve)].reshape(-1)
+        need = torch.unique(ends[(ends < self.begin) | (ends >= self.end)])          # sorted => grouped by owner
+        recv_counts = torch.bincount(need // chunk, minlength=self.world).to(torch.int64)
+        send_counts = torch.empty_like(recv_counts)
+        _all_to_all(send_counts, recv_counts, [1] * self.world, [1] * self.world, group)
+        self.recv_splits = [int(c) for c in recv_counts.tolist()]
+        self.send_splits = [int(c) for c in send_counts.tolist()]
+        self.need = need
+        self.send_ids = torch.empty(sum(self.send_splits), dtype=torch.int64, device=dev)
+        _all_to_all(self.send_ids, need, self.send_splits, self.recv_splits, group)     # peers tell me what they need
+        if self.send_ids.numel() and (int(self.send_ids.min()) < self.begin or int(self.send_ids.max()) >= self.end):
+            raise RuntimeError("VertexHalo: a peer asked for a vertex this rank does not own")
+
+    def exchange(self, x):
+        """x[*,3]: owned rows are current; fills the halo rows from their owners (one all-to-all)."""
+        import torch
+        send = x[self.send_ids]
+        recv = torch.empty((self.need.numel(), 3), dtype=x.dtype, device=x.device)
+        _all_to_all(recv, send, [3 * c for c in self.recv_splits], [3 * c for c in self.send_splits], self.group, cols=3)
+        x[self.need] = recv
+
+
+def _all_to_all(out, inp, out_splits, in_splits, group, cols=1):
+    """all_to_all_single with uneven splits (NCCL); gloo (CPU tests) goes through all_gather of the whole send buffers."""
+    import torch
+    import torch.distributed as dist
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(out.reshape(-1), inp.reshape(-1).contiguous(), out_splits, in_splits, group=group)
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, (in_splits, inp.reshape(-1).cpu()), group=group)
+    parts = []
+    for src in range(world):
+        spl, buf = sizes[src]
+        off = sum(spl[:rank])
+        parts.append(buf[off:off + spl[rank]])
+    flat = torch.cat(parts) if parts else inp.reshape(-1)[:0]
+    out.reshape(-1).copy_(flat.to(out.device))
+
+
+def vertex_update_edges_sharded(x, normals, edge_map, v_edges, iters=60, lam=1.0 / 18, group=None, sweep=None,
+                                exchange="halo"):
     """update_position2 (reference Code/train.py:1467-1557) with the vertices of ONE large mesh sharded over the ranks of
-    `group`: every rank holds the whole index tensors and all vertex positions, sweeps its own contiguous vertex range
-    (fgc_vertex_update_edges_range) and the ranges are exchanged with one all-gather per Jacobi sweep -- the only
-    exchange step of the path.  A Jacobi sweep reads nothing but the previous sweep's positions, so the result is
-    bit-identical to the single-device update.  `sweep(x_in, x_out, begin, end)` replaces the CUDA sweep in CPU tests.
+    `group`: every rank holds the whole index tensors, sweeps its own contiguous vertex range
+    (fgc_vertex_update_edges_range) and after every Jacobi sweep receives the positions its next sweep reads from other
+    ranks -- the only exchange step of the path.  exchange = "halo": one all-to-all of exactly those vertices (the ends of
+    the edges around owned vertices; VertexHalo), and one all-gather of the ranges at the end; "allgather": all positions
+    after every sweep.  A Jacobi sweep reads nothing but the previous sweep's positions, so both are bit-identical to the
+    single-device update.  `sweep(x_in, x_out, begin, end)` replaces the CUDA sweep in CPU tests.
     x[V,3] -> x[V,3] on every rank."""
     import torch
     import torch.distributed as dist
@@ -248,16 +309,25 @@ def vertex_update_edges_sharded(x, normals, edge_map, v_edges, iters=60, lam=1.0
     b, e = ranges[rank]
     cur = torch.zeros((world * chunk, 3), dtype=x.dtype, device=x.device)   # padded to equal shards for the all-gather
     cur[:V] = x.reshape(V, 3)
-    nxt = torch.zeros_like(cur)
+    nxt = cur.clone()
+
+    def gather_all(buf):
+        mine = buf[rank * chunk:(rank + 1) * chunk]
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(buf, mine, group=group)            # in place: shard r lands at rows r * chunk
+        else:
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine.clone(), group=group)
+            buf.copy_(torch.cat(parts, 0))
+
+    halo = VertexHalo(edge_map, v_edges, group) if (world > 1 and exchange == "halo") else None
     for _ in range(int(iters)):
         sweep(cur, nxt, b, e)
-        if world > 1:
-            mine = nxt[rank * chunk:(rank + 1) * chunk]
-            if dist.get_backend(group) == "nccl":
-                dist.all_gather_into_tensor(nxt, mine, group=group)            # in place: shard r lands at rows r * chunk
-            else:
-                parts = [torch.empty_like(mine) for _ in range(world)]
-                dist.all_gather(parts, mine.clone(), group=group)
-                nxt.copy_(torch.cat(parts, 0))
+        if halo is not None:
+            halo.exchange(nxt)
+        elif world > 1:
+            gather_all(nxt)
         cur, nxt = nxt, cur
+    if halo is not None:
+        gather_all(cur)
     return cur[:V].clone()

@@ -300,9 +300,14 @@ def _vertex_worker(rank, world, port, q):
     try:
         from facet_graph_convolution_b200 import patches
         V, n, em, ve = _vertex_case()
-        out = patches.vertex_update_edges_sharded(torch.from_numpy(V.astype(np.float64)), n, em, ve, iters=7,
-                                                  sweep=_oracle_sweep(n, em, ve))
-        q.put((rank, out.numpy()))
+        outs = []
+        for mode in ("halo", "allgather"):
+            out = patches.vertex_update_edges_sharded(torch.from_numpy(V.astype(np.float64)), torch.from_numpy(n),
+                                                      torch.from_numpy(em), torch.from_numpy(ve), iters=7,
+                                                      sweep=_oracle_sweep(n, em, ve), exchange=mode)
+            outs.append(out.numpy())
+        halo = patches.VertexHalo(torch.from_numpy(em), torch.from_numpy(ve))
+        q.put((rank, outs, int(halo.need.numel()), sum(halo.send_splits)))
     finally:
         dist.destroy_process_group()
 
@@ -321,9 +326,16 @@ def test_world2_sharded_vertex_update_equals_the_single_process_update():
     procs = [ctx.Process(target=_vertex_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(2))
+    got = {}
+    for _ in range(2):
+        r, outs, nneed, nsend = q.get(timeout=120)
+        got[r] = (outs, nneed, nsend)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     for r in range(2):                      # every rank ends with the whole mesh, equal to the unsharded update
-        assert np.array_equal(got[r], ref), np.abs(got[r] - ref).max()
+        for out in got[r][0]:
+            assert np.array_equal(out, ref), np.abs(out - ref).max()
+    # the halo is a thin band, not the mesh: what one rank needs the other sends, and it is far fewer rows than V
+    assert got[0][1] == got[1][2] and got[1][1] == got[0][2]
+    assert 0 < got[0][1] < V.shape[0] // 3
