@@ -242,10 +242,12 @@ class VertexHalo:
         ranges, chunk = vertex_ranges(V, self.world)
         self.begin, self.end = ranges[self.rank]
         dev = v_edges.device
-        ve = v_edges[self.begin:self.end].reshape(-1).long()
-        ve = ve[(ve >= 0) & (ve < edge_map.shape[0])]
-        ends = edge_map[:, :2].long()[torch.unique(ve)].reshape(-1)
-        need = torch.unique(ends[(ends < self.begin) | (ends >= self.end)])          # sorted => grouped by owner
+        # getEdgeMap (reference Code/utils.py:91-183) lists under a vertex the edges incident to it, so what an owned vertex
+        # reads is the other end of each of its edges: one pass over the edge list finds the edges with exactly one owned
+        # end (a scan of the range's v_edges rows would sort 20 ids per vertex to find the same thin band)
+        a, bb = edge_map[:, 0].long(), edge_map[:, 1].long()
+        own_a, own_b = (a >= self.begin) & (a < self.end), (bb >= self.begin) & (bb < self.end)
+        need = torch.unique(torch.cat([bb[own_a & ~own_b], a[own_b & ~own_a]]))       # sorted => grouped by owner
         recv_counts = torch.bincount(need // chunk, minlength=self.world).to(torch.int64)
         send_counts = torch.empty_like(recv_counts)
         _all_to_all(send_counts, recv_counts, [1] * self.world, [1] * self.world, group)
