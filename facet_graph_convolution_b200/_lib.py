@@ -65,6 +65,7 @@ SIGNATURES = {
     "fgc_concat2": (i32, [p, p, p, i64, i32, i32, p]),
     "fgc_split2": (i32, [p, p, p, i64, i32, i32, p]),
     "fgc_gather_perm": (i32, [p, p, p, i64, i32, p]),
+    "fgc_push_rows": (i32, [p, p, p, i64, i32, p]),
     "fgc_greedy_pairing": (i32, [p, p, p, i64, p, i64, p, i32, i32, p, p, p]),
     "fgc_grow_patch": (i32, [p, i64, i32, i64, i64, p, i64, p, i64, p, p, p]),
     "fgc_face_features": (i32, [p, p, i64, i64, i32, p, p, sz, p]),

@@ -143,6 +143,17 @@ __global__ void gather_perm_kernel(const float* __restrict__ x, const int32_t* _
 
 using namespace fgc;
 
+namespace fgc {
+__global__ void push_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, const int64_t* __restrict__ ids,
+                                 int64_t n, int C) {
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t off = ids[e / C] * C + e % C;
+    dst[off] = src[off];
+  }
+}
+}  // namespace fgc
+
 extern "C" {
 
 int fgc_pool_max(const float* x, float* y, int64_t rows_out, int C, int group, void* stream) {
@@ -228,6 +239,18 @@ int fgc_split2(const float* gy, float* ga, float* gb, int64_t rows, int Ca, int 
   if (n == 0) return FGC_OK;
   split2_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(gy, ga, gb, n, Ca, Cb);
   FGC_LAUNCHED("split2_kernel");
+  return FGC_OK;
+}
+
+// Rows ids[0..n) of src are stored at the same row indices of dst: dst is normally ANOTHER GPU's copy of the tensor
+// (a peer-mapped pointer of a symmetric allocation), so these are plain stores over NVLink -- the exchange step of the
+// vertex-sharded update (patches.vertex_update_edges_sharded, exchange = "p2p"): what a rank's peers read of its range
+// after a sweep is pushed into their buffers, no collective call, no staging copy.
+int fgc_push_rows(const float* src, float* dst, const int64_t* ids, int64_t n, int C, void* stream) {
+  FGC_REQUIRE(src && dst && (ids || n == 0) && C > 0 && n >= 0, "push_rows: bad arguments");
+  if (n == 0) return FGC_OK;
+  push_rows_kernel<<<grid_for(n * C), 256, 0, as_stream(stream)>>>(src, dst, ids, n * C, C);
+  FGC_LAUNCHED("push_rows_kernel");
   return FGC_OK;
 }
 

@@ -512,6 +512,18 @@ def vertex_update_edges_range(x_in, x_out, normals, edge_map, v_edges, v_begin, 
     return x_out
 
 
+def push_rows(src, dst_ptr: int, ids):
+    """dst[ids[i]] = src[ids[i]] (rows of src.shape[-1] floats) where dst is given as a raw device pointer: another GPU's
+    mapping of the same tensor (symmetric memory).  fgc_push_rows; runs on the current stream of src's device."""
+    L = _lib.lib()
+    src = _f32(src, "src")
+    if ids.dtype != torch.int64 or not ids.is_contiguous() or ids.device != src.device:
+        raise _lib.FacetConvError("push_rows: ids must be a contiguous int64 tensor on src's device")
+    with torch.cuda.device(src.device):
+        check(L.fgc_push_rows(_p(src), C.c_void_p(int(dst_ptr)), _p(ids), ids.numel(), int(src.shape[-1]), _stream(src)),
+              "fgc_push_rows")
+
+
 def vertex_update_ms(x, normals, faces, v_faces, scale, steps=2, iters=20):
     """One scale of reference Code/train.py:1668-1798 (update_position_MS)."""
     L = _lib.lib()

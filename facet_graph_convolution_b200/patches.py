@@ -294,7 +294,9 @@ def vertex_update_edges_sharded(x, normals, edge_map, v_edges, iters=60, lam=1.0
     (fgc_vertex_update_edges_range) and after every Jacobi sweep receives the positions its next sweep reads from other
     ranks -- the only exchange step of the path.  exchange = "halo": one all-to-all of exactly those vertices (the ends of
     the edges around owned vertices; VertexHalo), and one all-gather of the ranges at the end; "allgather": all positions
-    after every sweep.  A Jacobi sweep reads nothing but the previous sweep's positions, so both are bit-identical to the
+    after every sweep; "p2p" (NCCL groups on one node): the ping-pong position buffers live in symmetric memory, after its
+    sweep every rank stores the rows its peers read straight into THEIR buffers over NVLink (fgc_push_rows) and a
+    device-side barrier closes the sweep -- no collective call, no host synchronisation inside the loop.  A Jacobi sweep reads nothing but the previous sweep's positions, so both are bit-identical to the
     single-device update.  `sweep(x_in, x_out, begin, end)` replaces the CUDA sweep in CPU tests.
     x[V,3] -> x[V,3] on every rank."""
     import torch
@@ -322,6 +324,8 @@ def vertex_update_edges_sharded(x, normals, edge_map, v_edges, iters=60, lam=1.0
             dist.all_gather(parts, mine.clone(), group=group)
             buf.copy_(torch.cat(parts, 0))
 
+    if world > 1 and exchange == "p2p":
+        return _vertex_update_p2p(x, V, b, e, chunk, edge_map, v_edges, int(iters), group, sweep, gather_all)
     halo = VertexHalo(edge_map, v_edges, group) if (world > 1 and exchange == "halo") else None
     for _ in range(int(iters)):
         sweep(cur, nxt, b, e)
@@ -333,3 +337,49 @@ def vertex_update_edges_sharded(x, normals, edge_map, v_edges, iters=60, lam=1.0
     if halo is not None:
         gather_all(cur)
     return cur[:V].clone()
+
+
+_P2P_BUFFERS = {}
+
+
+def _vertex_update_p2p(x, V, b, e, chunk, edge_map, v_edges, iters, group, sweep, gather_all):
+    """exchange = "p2p" of vertex_update_edges_sharded: symmetric-memory ping-pong buffers, direct peer stores of the halo
+    rows, one device-side barrier per sweep.  Hazards: sweep s reads buffer A and writes own rows of B; the pushes of
+    sweep s write halo rows of the peers' B; the barrier orders them before sweep s+1 reads B and before the pushes of
+    sweep s+1 touch A, whose last readers (sweep s) are then done on every rank."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    from . import ops
+    grp = group if group is not None else dist.group.WORLD
+    world, rank = dist.get_world_size(grp), dist.get_rank(grp)
+    halo = VertexHalo(edge_map, v_edges, group)
+    rows = world * chunk
+    # the symmetric allocation and its rendezvous (an exchange of IPC handles, ~100 ms) are kept per (group, size): a
+    # pipeline that updates scan after scan pays them once
+    key = (id(grp), rows, str(x.device))
+    if key not in _P2P_BUFFERS:
+        buf = symm_mem.empty((2, rows, 3), dtype=torch.float32, device=x.device)
+        _P2P_BUFFERS.clear()
+        _P2P_BUFFERS[key] = (buf, symm_mem.rendezvous(buf, grp))
+    buf, hdl = _P2P_BUFFERS[key]
+    hdl.barrier()              # the previous call's readers are done on every rank
+    buf.zero_()
+    buf[0, :V] = x.reshape(V, 3)
+    buf[1].copy_(buf[0])
+    peers, off = [], 0
+    for p_, n_ in enumerate(halo.send_splits):
+        if n_:
+            peers.append((p_, halo.send_ids[off:off + n_].contiguous()))
+        off += n_
+    plane = rows * 3 * 4
+    hdl.barrier()
+    for it in range(iters):
+        ci = it & 1
+        sweep(buf[ci], buf[1 - ci], b, e)
+        for p_, ids in peers:
+            ops.push_rows(buf[1 - ci], int(hdl.buffer_ptrs[p_]) + (1 - ci) * plane, ids)
+        hdl.barrier()
+    out = buf[iters & 1].clone()
+    gather_all(out)
+    return out[:V].clone()

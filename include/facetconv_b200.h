@@ -200,6 +200,10 @@ FGC_API int fgc_split2(const float* gy, float* ga, float* gb, int64_t rows, int 
  * train.py:117-121) */
 FGC_API int fgc_gather_perm(const float* x, const int32_t* idx, float* y, int64_t rows_out, int C,
                     void* stream);
+/* dst[ids[i]][0..C) = src[ids[i]][0..C) for i < n: rows pushed into another buffer at the same indices.  dst may be a
+ * peer GPU's mapping of the same tensor (symmetric memory): the per-sweep exchange of the vertex-sharded
+ * update_position2 (reference Code/train.py:1467-1557 runs it on one device) as direct NVLink stores. */
+FGC_API int fgc_push_rows(const float* src, float* dst, const int64_t* ids, int64_t n, int C, void* stream);
 
 /* ---------------------------------------------------------------- per-facet linear layers
  * reference Code/model.py:763-769 (custom_lin): y = x @ W + b, W[Cin,Cout] */
