@@ -741,7 +741,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=["c3", "c2"])
     ap.add_argument("--grid", type=int, default=1000, help="c3: quads per side (1000 -> 2 M facets)")
     ap.add_argument("--block", type=int, default=100, help="c3: quads per side of a patch core")
-    ap.add_argument("--patch-batch", type=int, default=50, help="c3: patches per launch (1 = the reference's B = 1)")
+    ap.add_argument("--patch-batch", type=int, default=100, help="c3: patches per launch (1 = the reference's B = 1)")
     ap.add_argument("--streams", type=int, default=2, help="c3: launch groups of a pass alternate over this many CUDA streams")
     ap.add_argument("--adjacency", default="mesh", choices=["mesh", "dedup", "random"], help="c2")
     ap.add_argument("--facets", type=int, default=1_000_000, help="c2")
