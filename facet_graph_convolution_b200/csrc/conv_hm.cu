@@ -638,16 +638,22 @@ conv_hm2_kernel(const __grid_constant__ HmParams p) {
       if (LAST) {
         const int n = m / NG, it = n / kHFpw, fi = n % kHFpw, buf = it & 1, f = aw * kHFpw + fi;
         if (fi == 0) {
+#ifdef FGC_HM_TRACE_AGG   // aggregator stamps cost ~15 instructions per facet: only in builds with this flag
           if (aw == 0) HM_TR(it, 9);
+#endif
           tc::mbar_wait(&bars[H2_B3_FREE + buf], ((it >> 1) & 1) ^ 1);
+#ifdef FGC_HM_TRACE_AGG
           if (aw == 0) HM_TR(it, 10);
+#endif
         }
         hm2_drain<M>(smem + buf * Cfg::B3_BUF, f, g, t, acc);
         if (lane == 0) rowinv[(it & 3) * kHT + f] = invtab[cnt];
         if (fi == kHFpw - 1) {
           __syncwarp();
+#ifdef FGC_HM_TRACE_AGG
           if (aw == 0) HM_TR(it, 1);
           if (aw == kHAgg - 1) HM_TR(it, 8);
+#endif
           if (lane == 0) tc::mbar_arrive(&bars[H2_B3_FULL + buf]);
         }
       }

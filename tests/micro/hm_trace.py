@@ -39,4 +39,5 @@ for t in range(4, 24):
     r = tr[t]
     f = lambda i: "%7d" % (r[i] - t0) if r[i] > 0 else "     -1"
     print("t%2d  %s %s | %s %s | %s %s | %s %s | %s %s" % (t, f(1), f(8), f(2), f(3), f(4), f(5), f(6), f(7), f(9), f(10)))
-print("tile period (agg0 arrive): %.0f cycles" % np.diff(tr[4:40, 1]).mean())
+print("tile period (stage 2 issue): %.0f cycles" % np.diff(tr[4:40, 3]).mean())
+print("(aggregator stamps -- columns 1, 2, 9, 10 -- need a build with -DFGC_HM_TRACE_AGG)")
