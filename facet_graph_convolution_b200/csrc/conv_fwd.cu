@@ -244,8 +244,11 @@ int launch_conv_fwd(const ConvFwdParams& p, cudaStream_t st) {
 // neighbour logits inline (no uvx pre-pass), softmax, s[M][CIN] in registers, contraction against a
 // transposed weight image in shared memory read by broadcast -- same arithmetic order per facet for every
 // launch geometry.
+#ifndef FGC_SMALL_BLOCKS
+#define FGC_SMALL_BLOCKS 4
+#endif
 template <int M, int CIN, int COUT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, FGC_SMALL_BLOCKS)
 conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ adj, const float* __restrict__ W0,
                       const float* __restrict__ b, const float* __restrict__ u, const float* __restrict__ v,
                       const float* __restrict__ c, float* __restrict__ y, int64_t rows, int N, int K, int bias_mask,
