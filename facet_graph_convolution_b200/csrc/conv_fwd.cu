@@ -14,6 +14,7 @@
 
 #include "conv_common.cuh"
 #include "conv_launch.cuh"
+#include "tc_common.cuh"
 
 namespace fgc {
 
@@ -254,7 +255,7 @@ conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ a
                       const float* __restrict__ c, float* __restrict__ y, int64_t rows, int N, int K, int bias_mask,
                       int act, float alpha, float* __restrict__ ypool, unsigned* __restrict__ ymax) {
   __shared__ __align__(16) float Wt[M * CIN * COUT];   // [(m, c)][o]
-  __shared__ float us[M * CIN], vs[M * CIN], cs[M];
+  __shared__ __align__(8) float us[M * CIN], vs[M * CIN], cs[M];
   for (int e = threadIdx.x; e < M * CIN * COUT; e += blockDim.x) {
     const int o = e % COUT, mc = e / COUT;
     Wt[e] = W0[(static_cast<size_t>(mc / CIN) * COUT + o) * CIN + mc % CIN];
@@ -269,7 +270,9 @@ conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ a
     const bool valid = rw + (threadIdx.x & 31) < rows;
     const int64_t r = valid ? rw + (threadIdx.x & 31) : rows - 1;
     const int64_t base = (r / N) * N;
-    float xn[CIN], own[M], s[M][CIN];
+    static_assert(CIN % 2 == 0, "channel pairs");
+    float xn[CIN], own[M];
+    float2 s2[M][CIN / 2];          // s[m][i] in channel pairs: the aggregation runs on packed fp32x2 FMAs
 #pragma unroll
     for (int i = 0; i < CIN; ++i) xn[i] = __ldg(x + r * CIN + i);
 #pragma unroll
@@ -279,7 +282,7 @@ conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ a
       for (int i = 0; i < CIN; ++i) a = fmaf(us[m * CIN + i], xn[i], a);
       own[m] = a;
 #pragma unroll
-      for (int i = 0; i < CIN; ++i) s[m][i] = 0.f;
+      for (int i = 0; i < CIN / 2; ++i) s2[m][i] = make_float2(0.f, 0.f);
     }
     int cnt = 0;
     for (int k = 0; k < K; ++k) {
@@ -291,11 +294,14 @@ conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ a
       float xj[CIN];
 #pragma unroll
       for (int i = 0; i < CIN; ++i) xj[i] = __ldg(xr + i);
+      float2 xj2[CIN / 2];
+#pragma unroll
+      for (int i = 0; i < CIN / 2; ++i) xj2[i] = make_float2(xj[2 * i], xj[2 * i + 1]);
       float q[M];
       float mx = -3.4e38f;
 #pragma unroll
       for (int m = 0; m < M; ++m) {
-        float a = own[m];
+        float a = own[m];     // (the dot products on packed FMAs, two partial sums per weight, measured slower)
 #pragma unroll
         for (int i = 0; i < CIN; ++i) a = fmaf(vs[m * CIN + i], xj[i], a);
         q[m] = a;
@@ -311,26 +317,32 @@ conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ a
 #pragma unroll
       for (int m = 0; m < M; ++m) {
         const float qq = q[m] * rs;
+        const float2 qq2 = make_float2(qq, qq);
 #pragma unroll
-        for (int i = 0; i < CIN; ++i) s[m][i] = fmaf(qq, xj[i], s[m][i]);
+        for (int i = 0; i < CIN / 2; ++i) tc::ffma2(s2[m][i], qq2, xj2[i]);
       }
     }
-    float acc[COUT];
+    // contraction on packed fp32x2 FMAs (two outputs per instruction; each output still one IEEE fma chain in (m, i) order)
+    float2 acc2[COUT / 2];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    for (int o = 0; o < COUT / 2; ++o) acc2[o] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int m = 0; m < M; ++m)
 #pragma unroll
       for (int i = 0; i < CIN; ++i) {
-        const float sv = s[m][i];
+        const float sv1 = (i & 1) ? s2[m][i >> 1].y : s2[m][i >> 1].x;
+        const float2 sv = make_float2(sv1, sv1);
         const float4* wr = reinterpret_cast<const float4*>(Wt + (m * CIN + i) * COUT);
 #pragma unroll
         for (int o4 = 0; o4 < COUT / 4; ++o4) {
           const float4 w = wr[o4];
-          acc[4 * o4] = fmaf(sv, w.x, acc[4 * o4]), acc[4 * o4 + 1] = fmaf(sv, w.y, acc[4 * o4 + 1]);
-          acc[4 * o4 + 2] = fmaf(sv, w.z, acc[4 * o4 + 2]), acc[4 * o4 + 3] = fmaf(sv, w.w, acc[4 * o4 + 3]);
+          tc::ffma2(acc2[2 * o4], sv, make_float2(w.x, w.y));
+          tc::ffma2(acc2[2 * o4 + 1], sv, make_float2(w.z, w.w));
         }
       }
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT / 2; ++o) acc[2 * o] = acc2[o].x, acc[2 * o + 1] = acc2[o].y;
     const float inv = cnt ? 1.f / static_cast<float>(cnt) : 0.f;
     const float fl = (cnt > 0 || !bias_mask) ? 1.f : 0.f;
     float4* yr = reinterpret_cast<float4*>(y + r * COUT);
