@@ -64,6 +64,9 @@ struct HeadParams {
   float alpha;
 };
 
+// FAST_ACT: 0 <= alpha <= 1, lrelu(h) = max(h, alpha h) (a runtime flag made the compiler issue BOTH activation forms
+// predicated -- nine issue slots per pair of hidden units where three do)
+template <bool FAST_ACT>
 __global__ void __launch_bounds__(kHThreads, 1)
 mlp_head_tc_kernel(const HeadParams p) {
   using Cfg = HeadCfg;
@@ -108,49 +111,64 @@ mlp_head_tc_kernel(const HeadParams p) {
     const float wun = __ldg(p.wunscale);
     const float b20 = __ldg(p.b2), b21 = __ldg(p.b2 + 1), b22 = __ldg(p.b2 + 2);
     const float2 al2 = make_float2(p.alpha, p.alpha);
-    const bool fast_act = p.alpha >= 0.f && p.alpha <= 1.f;   // lrelu(h) = max(h, alpha h)
     float4* ex = reinterpret_cast<float4*>(smem + Cfg::OFF_EX);
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
       float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
       float2 sc2 = a0;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        tc::mbar_wait(&bars[H_D_FULL + c], t & 1);
-        tc::tc_fence_after_sync();
-        if (c == 0) {
-          const float sc = rs[(t & 3) * kHTile + row] * wun;
-          sc2 = make_float2(sc, sc);
-        }
-#pragma unroll 1
-        for (int j = 0; j < kHChunk / 64; ++j) {
-          const int col0 = half * (kHChunk / 2) + j * 32;          // first hidden unit of this load inside the chunk
-          uint32_t d[32];
-          tc::tmem_ld32(tmem + lane_base + c * kHChunk + col0, d);
-          tc::tc_wait_ld();
-          if (j == kHChunk / 64 - 1) {
-            tc::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&bars[H_D_FREE + c]);
-          }
-          const float4* pp = prm + (c * kHChunk + col0);           // two float4 per pair of hidden units
+      // The 2 chunks x 4 column blocks of this warp, with the TMEM load of block k+1 in flight while block k is
+      // computed (load -> wait -> compute, as first written, exposed the TMEM latency eight times per tile).
+      constexpr int kBlk = kHChunk / 64;                                // blocks per chunk
+      auto block_addr = [&](int k) -> uint32_t {
+        return tmem + lane_base + (k / kBlk) * kHChunk + half * (kHChunk / 2) + (k % kBlk) * 32;
+      };
+      auto compute = [&](const uint32_t (&d)[32], int k) {
+        const float4* pp = prm + ((k / kBlk) * kHChunk + half * (kHChunk / 2) + (k % kBlk) * 32);   // two float4 per pair
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 r0 = pp[2 * i], r1 = pp[2 * i + 1];
-            float2 h = make_float2(r0.x, r0.y);                     // b1 pair
-            tc::ffma2(h, make_float2(__uint_as_float(d[2 * i]), __uint_as_float(d[2 * i + 1])), sc2);
-            if (fast_act) {
-              float2 ah = make_float2(0.f, 0.f);
-              tc::ffma2(ah, h, al2);
-              h.x = fmaxf(h.x, ah.x), h.y = fmaxf(h.y, ah.y);
-            } else {
-              h.x = lrelu_f(h.x, p.alpha), h.y = lrelu_f(h.y, p.alpha);
-            }
-            tc::ffma2(a0, h, make_float2(r0.z, r0.w));
-            tc::ffma2(a1, h, make_float2(r1.x, r1.y));
-            tc::ffma2(a2, h, make_float2(r1.z, r1.w));
+        for (int i = 0; i < 16; ++i) {
+          const float4 r0 = pp[2 * i], r1 = pp[2 * i + 1];
+          float2 h = make_float2(r0.x, r0.y);                     // b1 pair
+          tc::ffma2(h, make_float2(__uint_as_float(d[2 * i]), __uint_as_float(d[2 * i + 1])), sc2);
+          if (FAST_ACT) {
+            float2 ah = make_float2(0.f, 0.f);
+            tc::ffma2(ah, h, al2);
+            h.x = fmaxf(h.x, ah.x), h.y = fmaxf(h.y, ah.y);
+          } else {
+            h.x = lrelu_f(h.x, p.alpha), h.y = lrelu_f(h.y, p.alpha);
           }
+          tc::ffma2(a0, h, make_float2(r0.z, r0.w));
+          tc::ffma2(a1, h, make_float2(r1.x, r1.y));
+          tc::ffma2(a2, h, make_float2(r1.z, r1.w));
         }
+      };
+      // after the loads of a chunk's last block have landed the accumulator may be overwritten
+      auto release_chunk = [&](int c) {
+        tc::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[H_D_FREE + c]);
+      };
+      uint32_t dA[32], dB[32];
+      tc::mbar_wait(&bars[H_D_FULL + 0], t & 1);
+      tc::tc_fence_after_sync();
+      {
+        const float sc = rs[(t & 3) * kHTile + row] * wun;
+        sc2 = make_float2(sc, sc);
+      }
+      tc::tmem_ld32(block_addr(0), dA);
+#pragma unroll 1
+      for (int k = 0; k < 2 * kBlk; k += 2) {
+        tc::tc_wait_ld();                                   // block k is in dA
+        tc::tmem_ld32(block_addr(k + 1), dB);               // same chunk (kBlk is even)
+        compute(dA, k);
+        tc::tc_wait_ld();                                   // block k + 1 is in dB
+        if (k + 2 == kBlk) {                                // chunk 0 fully read: free it, then wait for chunk 1
+          release_chunk(0);
+          tc::mbar_wait(&bars[H_D_FULL + 1], t & 1);
+          tc::tc_fence_after_sync();
+        }
+        if (k + 2 < 2 * kBlk) tc::tmem_ld32(block_addr(k + 2), dA);
+        else release_chunk(1);
+        compute(dB, k + 1);
       }
       const float s0 = a0.x + a0.y, s1 = a1.x + a1.y, s2 = a2.x + a2.y;
       // the second warp of the quadrant hands its partial sums to the first (fixed order of addition)
@@ -294,7 +312,8 @@ int launch_mlp_head_tc(const float* x, const float* W1, const float* b1, const f
               mlp_head_tc_workspace());
   prep_head_w_kernel<<<16, 1024, 0, st>>>(W1, reinterpret_cast<uint16_t*>(img), wunscale);
   FGC_LAUNCHED("prep_head_w_kernel");
-  FGC_CUDA(cudaFuncSetAttribute(mlp_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg::SMEM_BYTES));
+  auto kern = (alpha >= 0.f && alpha <= 1.f) ? mlp_head_tc_kernel<true> : mlp_head_tc_kernel<false>;
+  FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg::SMEM_BYTES));
   HeadParams p{};
   p.x = x, p.wunscale = wunscale, p.b2 = b2, p.y = y, p.rows = rows, p.alpha = alpha;
   p.ntiles = (rows + kHTile - 1) / kHTile;
@@ -303,7 +322,7 @@ int launch_mlp_head_tc(const float* x, const float* W1, const float* b1, const f
   for (int pass = 0; pass < kHH / kHPass; ++pass) {
     p.wimg = reinterpret_cast<const uint4*>(img + static_cast<size_t>(pass) * 2 * HeadCfg::B_PLANE);
     p.b1 = b1 + pass * kHPass, p.W2 = W2 + static_cast<size_t>(pass) * kHPass * 3, p.accumulate = pass > 0;
-    mlp_head_tc_kernel<<<static_cast<unsigned>(grid), kHThreads, HeadCfg::SMEM_BYTES, st>>>(p);
+    kern<<<static_cast<unsigned>(grid), kHThreads, HeadCfg::SMEM_BYTES, st>>>(p);
     FGC_LAUNCHED("mlp_head_tc_kernel");
   }
   return FGC_OK;
