@@ -263,6 +263,222 @@ mlp_head_tc_kernel(const HeadParams p) {
   if (warp == kHIssuer) tc::tmem_dealloc(tmem, 512);
 }
 
+// Two-tile variant (default): the epilogue is bound by its parameter loads -- warp-broadcast LDS.128 still cost four LSU
+// wavefronts each, 8 192 wavefront-cycles per 128-row tile and launch -- so the CTA keeps TWO tiles in flight (the two A
+// buffers), the hidden units go through TMEM in chunks of 128 columns per tile, and every parameter load serves a row of
+// each tile.  Same roles, barriers and arithmetic (per row: the same fma chain in the same order) as the kernel above.
+template <bool FAST_ACT>
+__global__ void __launch_bounds__(kHThreads, 1)
+mlp_head_tc2_kernel(const HeadParams p) {
+  using Cfg = HeadCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + H_NUM);
+  float4* prm = reinterpret_cast<float4*>(smem + Cfg::OFF_PRM);
+  float* rs = reinterpret_cast<float*>(smem + Cfg::OFF_RS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bars[H_A_FULL + i], 4), tc::mbar_init(&bars[H_A_FREE + i], 1);
+      tc::mbar_init(&bars[H_D_FULL + i], 1), tc::mbar_init(&bars[H_D_FREE + i], kHEpi);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == kHIssuer) tc::tmem_alloc(tmem_slot, 512);
+  {
+    uint4* dst = reinterpret_cast<uint4*>(smem + Cfg::OFF_B);
+    for (int i = threadIdx.x; i < 2 * Cfg::B_PLANE / 16; i += kHThreads) dst[i] = __ldg(p.wimg + i);
+    // rows of A beyond K = 32 are never read; zero them once so that no NaN pattern sits in the operand
+    uint4* az = reinterpret_cast<uint4*>(smem + Cfg::OFF_A);
+    for (int i = threadIdx.x; i < 4 * Cfg::A_PLANE / 16; i += kHThreads) az[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < kHPass / 2; i += kHThreads) {   // pair records of hidden units 2i, 2i+1
+      const int h0 = 2 * i, h1 = 2 * i + 1;
+      prm[2 * i] = make_float4(__ldg(p.b1 + h0), __ldg(p.b1 + h1), __ldg(p.W2 + 3 * h0), __ldg(p.W2 + 3 * h1));
+      prm[2 * i + 1] = make_float4(__ldg(p.W2 + 3 * h0 + 1), __ldg(p.W2 + 3 * h1 + 1), __ldg(p.W2 + 3 * h0 + 2), __ldg(p.W2 + 3 * h1 + 2));
+    }
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < kHEpi) {
+    // =========================================================== epilogue
+    const int q = warp & 3, half = warp >> 2;            // TMEM lane quadrant, column half of every chunk
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int row = q * 32 + lane;
+    const float wun = __ldg(p.wunscale);
+    const float b20 = __ldg(p.b2), b21 = __ldg(p.b2 + 1), b22 = __ldg(p.b2 + 2);
+    const float2 al2 = make_float2(p.alpha, p.alpha);
+    float4* ex = reinterpret_cast<float4*>(smem + Cfg::OFF_EX);
+    const int my_tiles = static_cast<int>((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    constexpr int kC2 = 128;                                  // hidden units per chunk and tile
+#pragma unroll 1
+    for (int P = 0; 2 * P < my_tiles; ++P) {
+      const int tA = 2 * P, tB = 2 * P + 1;
+      const bool has_b = tB < my_tiles;
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1v = a0, b2v = a0;
+      float2 scA2 = make_float2(0.f, 0.f), scB2 = scA2;
+#pragma unroll 1
+      for (int c4 = 0; c4 < kHPass / kC2; ++c4) {
+        const int s = c4 & 1, n = 2 * P + (c4 >> 1);
+        tc::mbar_wait(&bars[H_D_FULL + s], n & 1);
+        tc::tc_fence_after_sync();
+        if (c4 == 0) {     // the scales were written before the producers' arrive that the MMAs of this pair waited for
+          const float sa = rs[(tA & 3) * kHTile + row] * wun, sb_ = rs[(tB & 3) * kHTile + row] * wun;
+          scA2 = make_float2(sa, sa), scB2 = make_float2(sb_, sb_);
+        }
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          const int col0 = half * (kC2 / 2) + j * 32;             // first hidden unit of this block inside the chunk
+          uint32_t dA[32], dB[32];
+          tc::tmem_ld32(tmem + lane_base + s * 2 * kC2 + col0, dA);
+          tc::tmem_ld32(tmem + lane_base + s * 2 * kC2 + kC2 + col0, dB);
+          tc::tc_wait_ld();
+          if (j == 1) {
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bars[H_D_FREE + s]);
+          }
+          const float4* pp = prm + (c4 * kC2 + col0);             // two float4 per pair of hidden units
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 r0 = pp[2 * i], r1 = pp[2 * i + 1];
+            float2 hA = make_float2(r0.x, r0.y), hB = hA;           // b1 pair
+            tc::ffma2(hA, make_float2(__uint_as_float(dA[2 * i]), __uint_as_float(dA[2 * i + 1])), scA2);
+            tc::ffma2(hB, make_float2(__uint_as_float(dB[2 * i]), __uint_as_float(dB[2 * i + 1])), scB2);
+            if (FAST_ACT) {
+              float2 tA2 = make_float2(0.f, 0.f), tB2 = tA2;
+              tc::ffma2(tA2, hA, al2);
+              tc::ffma2(tB2, hB, al2);
+              hA.x = fmaxf(hA.x, tA2.x), hA.y = fmaxf(hA.y, tA2.y);
+              hB.x = fmaxf(hB.x, tB2.x), hB.y = fmaxf(hB.y, tB2.y);
+            } else {
+              hA.x = lrelu_f(hA.x, p.alpha), hA.y = lrelu_f(hA.y, p.alpha);
+              hB.x = lrelu_f(hB.x, p.alpha), hB.y = lrelu_f(hB.y, p.alpha);
+            }
+            const float2 w0 = make_float2(r0.z, r0.w), w1 = make_float2(r1.x, r1.y), w2 = make_float2(r1.z, r1.w);
+            tc::ffma2(a0, hA, w0), tc::ffma2(a1, hA, w1), tc::ffma2(a2, hA, w2);
+            tc::ffma2(b0, hB, w0), tc::ffma2(b1v, hB, w1), tc::ffma2(b2v, hB, w2);
+          }
+        }
+      }
+      // the second warp of the quadrant hands its partial sums to the first (fixed order of addition)
+      const float sA0 = a0.x + a0.y, sA1 = a1.x + a1.y, sA2 = a2.x + a2.y;
+      const float sB0 = b0.x + b0.y, sB1 = b1v.x + b1v.y, sB2 = b2v.x + b2v.y;
+      if (half == 1) {
+        ex[row] = make_float4(sA0, sA1, sA2, 0.f);
+        ex[kHTile + row] = make_float4(sB0, sB1, sB2, 0.f);
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      if (half == 0) {
+        const float4 oA = ex[row], oB = ex[kHTile + row];
+        const int64_t tileA = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(tA) * gridDim.x;
+        const int64_t rA = tileA * kHTile + row, rB = (tileA + gridDim.x) * kHTile + row;
+        if (rA < p.rows) {
+          float* yr = p.y + 3 * rA;
+          if (p.accumulate) yr[0] += sA0 + oA.x, yr[1] += sA1 + oA.y, yr[2] += sA2 + oA.z;
+          else yr[0] = (sA0 + oA.x) + b20, yr[1] = (sA1 + oA.y) + b21, yr[2] = (sA2 + oA.z) + b22;
+        }
+        if (has_b && rB < p.rows) {
+          float* yr = p.y + 3 * rB;
+          if (p.accumulate) yr[0] += sB0 + oB.x, yr[1] += sB1 + oB.y, yr[2] += sB2 + oB.z;
+          else yr[0] = (sB0 + oB.x) + b20, yr[1] = (sB1 + oB.y) + b21, yr[2] = (sB2 + oB.z) + b22;
+        }
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // ex[] is reused by the next pair
+    }
+  } else if (warp < kHIssuer) {
+    // =========================================================== producers: thread = row
+    const int row = (warp - kHProd0) * 32 + lane;
+    int t = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+      const int b = t & 1;
+      const int64_t r = tile * kHTile + row;
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = (r < p.rows) ? __ldg(reinterpret_cast<const float4*>(p.x + r * kHK) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+      int E = (__float_as_int(mx) >> 23) & 0xFF;
+      E = min(max(E, 16), 240);
+      const float sc = __int_as_float((267 - E) << 23);   // 2^(140-E): |x| sc in [2^13, 2^14)
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float f[4] = {v[i].x * sc, v[i].y * sc, v[i].z * sc, v[i].w * sc};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const __half2 hh = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(f[2 * k] - hf.x, f[2 * k + 1] - hf.y);
+          hi[2 * i + k] = *reinterpret_cast<const uint32_t*>(&hh);
+          lo[2 * i + k] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+      }
+      tc::mbar_wait(&bars[H_A_FREE + b], ((t >> 1) & 1) ^ 1);
+      uint8_t* ah = smem + Cfg::OFF_A + b * 2 * Cfg::A_PLANE + (row >> 3) * 1024 + (row & 7) * 128;
+      uint8_t* al = ah + Cfg::A_PLANE;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        *reinterpret_cast<uint4*>(ah + ((u ^ (row & 7)) << 4)) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+        *reinterpret_cast<uint4*>(al + ((u ^ (row & 7)) << 4)) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+      }
+      rs[(t & 3) * kHTile + row] = __int_as_float((E - 13) << 23);   // 2^(E-140)
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[H_A_FULL + b]);
+    }
+  } else {
+    // =========================================================== MMA issuer
+    constexpr int kC2 = 128;
+    constexpr uint32_t idesc = tc::idesc_f16(128, kC2);
+    const uint32_t sb = tc::smem_u32(smem);
+    const int my_tiles = static_cast<int>((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+#pragma unroll 1
+    for (int P = 0; 2 * P < my_tiles; ++P) {
+      const bool has_b = 2 * P + 1 < my_tiles;
+      tc::mbar_wait(&bars[H_A_FULL + 0], P & 1);
+      if (has_b) tc::mbar_wait(&bars[H_A_FULL + 1], P & 1);
+#pragma unroll 1
+      for (int c4 = 0; c4 < kHPass / kC2; ++c4) {
+        const int s = c4 & 1, n = 2 * P + (c4 >> 1);
+        tc::mbar_wait(&bars[H_D_FREE + s], (n & 1) ^ 1);
+        tc::tc_fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t bh = sb + Cfg::OFF_B + c4 * kC2 * 128, bl = bh + Cfg::B_PLANE;
+#pragma unroll 1
+          for (int tb = 0; tb < (has_b ? 2 : 1); ++tb) {
+            const uint32_t ah = sb + Cfg::OFF_A + tb * 2 * Cfg::A_PLANE, al = ah + Cfg::A_PLANE;
+            const uint32_t d = tmem + s * 2 * kC2 + tb * kC2;
+#pragma unroll
+            for (int ks = 0; ks < kHK / 16; ++ks) {
+              const uint64_t dah = tc::smem_desc_k_sw128(ah + ks * 32), dal = tc::smem_desc_k_sw128(al + ks * 32);
+              const uint64_t dbh = tc::smem_desc_k_sw128(bh + ks * 32), dbl = tc::smem_desc_k_sw128(bl + ks * 32);
+              tc::mma_f16_ss(d, dah, dbh, idesc, ks ? 1u : 0u);
+              tc::mma_f16_ss(d, dal, dbh, idesc, 1u);
+              tc::mma_f16_ss(d, dah, dbl, idesc, 1u);
+            }
+          }
+          tc::tc_commit(&bars[H_D_FULL + s]);
+          if (c4 == kHPass / kC2 - 1) {
+            tc::tc_commit(&bars[H_A_FREE + 0]);
+            if (has_b) tc::tc_commit(&bars[H_A_FREE + 1]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kHIssuer) tc::tmem_dealloc(tmem, 512);
+}
+
 // image of W1^T for both passes: pass p, plane (hi, lo): [512 hidden units][128 B], K-major, 128B swizzle;
 // values W1[k][512 p + n] * 2^(140 - E) with E the exponent of max|W1| (hi < 2^14, residual in the normal range)
 __global__ void __launch_bounds__(1024)
@@ -312,7 +528,10 @@ int launch_mlp_head_tc(const float* x, const float* W1, const float* b1, const f
               mlp_head_tc_workspace());
   prep_head_w_kernel<<<16, 1024, 0, st>>>(W1, reinterpret_cast<uint16_t*>(img), wunscale);
   FGC_LAUNCHED("prep_head_w_kernel");
-  auto kern = (alpha >= 0.f && alpha <= 1.f) ? mlp_head_tc_kernel<true> : mlp_head_tc_kernel<false>;
+  static const bool one_tile = getenv("FGC_HEAD_V1") != nullptr;   // the one-tile-per-CTA kernel, for comparisons
+  const bool fast = alpha >= 0.f && alpha <= 1.f;
+  auto kern = one_tile ? (fast ? mlp_head_tc_kernel<true> : mlp_head_tc_kernel<false>)
+                       : (fast ? mlp_head_tc2_kernel<true> : mlp_head_tc2_kernel<false>);
   FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg::SMEM_BYTES));
   HeadParams p{};
   p.x = x, p.wunscale = wunscale, p.b2 = b2, p.y = y, p.rows = rows, p.alpha = alpha;
