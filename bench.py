@@ -659,6 +659,7 @@ def run_c3(args):
     if not args.no_e2e:
         outs = [torch.empty(x.shape[0], x.shape[1], 3).pin_memory() for x, _, _ in host_e2e]
         copy_s = torch.cuda.Stream()
+        down_s = torch.cuda.Stream()
         h2d = sum(x.numel() * 4 + sum(a.numel() * 4 for a in adjs) + ns.numel() * 4 for x, adjs, ns in host_e2e)
         d2h = sum(o.numel() * 4 for o in outs)
 
@@ -683,7 +684,13 @@ def run_c3(args):
                 yn = fwd(xd, ad, nd)
                 for t in (xd, nd, *ad):
                     t.record_stream(cur)
-                outs[i].copy_(yn, non_blocking=True)
+                # the normals of this group leave on their own stream, under the forward of the next group
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(down_s):
+                    down_s.wait_event(done)
+                    outs[i].copy_(yn, non_blocking=True)
+                yn.record_stream(down_s)
             torch.cuda.synchronize()
 
         e2e_pass()
@@ -701,7 +708,7 @@ def run_c3(args):
                "steps": ksteps, "ms_per_step": dt / ksteps * 1e3,
                "api": "model.get_model_reg_multi_scale + normalizeTensor per patch batch (fgc_net_fwd / "
                       "fgc_normalize_rows_segmented through the C ABI) from pinned host patch tensors (features + 3-level "
-                      "adjacency pyramid) to pinned host normals; uploads of the next batch overlap the current forward"}
+                      "adjacency pyramid) to pinned host normals; uploads of the next group and the download of the previous group's normals overlap the current forward"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
