@@ -430,26 +430,29 @@ conv_hm2_kernel(const __grid_constant__ HmParams p) {
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  {
-    // weight operand -> TMEM: lane 32 q + l of the image is TMEM lane 32 q + l, column = K pair.  A warp reaches the
-    // TMEM lanes of quadrant warp % 4 only; five warps per quadrant share its 32-column chunks.
-    const int q = warp & 3;
-    const uint32_t* src = p.wt + static_cast<size_t>(q * 32 + lane) * Cfg::W_COLS;
+  if (warp < 4) {
+    // weight operand -> TMEM: lane 32 q + l of the image is TMEM lane 32 q + l, column = K pair; a warp reaches the TMEM
+    // lanes of quadrant warp % 4 only.  The epilogue warps with outputs load their own quadrant while the aggregators are
+    // already at work on the first tile (stage 2 is the first reader; quadrants without outputs -- lanes of D that nobody
+    // reads -- are left as they are): the prologue, 147 KB per CTA from L2, is off the critical path of short launches.
+    if (warp < nepi) {
+      const uint32_t* src = p.wt + static_cast<size_t>(warp * 32 + lane) * Cfg::W_COLS;
 #pragma unroll 1
-    for (int c0 = (warp >> 2) * 32; c0 < Cfg::W_COLS; c0 += 5 * 32) {
-      uint32_t r[32];
+      for (int c0 = 0; c0 < Cfg::W_COLS; c0 += 32) {
+        uint32_t r[32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint4 tq = __ldg(reinterpret_cast<const uint4*>(src + c0) + u);
-        r[4 * u] = tq.x, r[4 * u + 1] = tq.y, r[4 * u + 2] = tq.z, r[4 * u + 3] = tq.w;
+        for (int u = 0; u < 8; ++u) {
+          const uint4 tq = __ldg(reinterpret_cast<const uint4*>(src + c0) + u);
+          r[4 * u] = tq.x, r[4 * u + 1] = tq.y, r[4 * u + 2] = tq.z, r[4 * u + 3] = tq.w;
+        }
+        tc::tmem_st32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
       }
-      tc::tmem_st32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+      tc::tc_wait_st();
+      tc::tc_fence_before_sync();
+      asm volatile("bar.sync 1, %0;" ::"r"(nepi * 32) : "memory");
+      tc::tc_fence_after_sync();
     }
-    tc::tc_wait_st();
-    tc::tc_fence_before_sync();
   }
-  __syncthreads();
-  tc::tc_fence_after_sync();
 
   if (warp < 4) {
     // =========================================================== epilogue: Y (TMEM) -> global; warp 0 also issues stage 2
