@@ -9,23 +9,41 @@ import torch
 
 from . import ops
 
-_REV_CACHE = {}
+import collections
+
+# LRU, bounded by entries AND by the bytes the cached index tensors pin on the GPU (a training set cycles through far more
+# patches than fit: callers that iterate over many adjacencies should own their ReverseAdjacency / ConvPlan instead)
+_REV_CACHE = collections.OrderedDict()
 _REV_CACHE_MAX = 64
+_CACHE_MAX_BYTES = 2 << 30
+
+
+def _entry_bytes(obj) -> int:
+    n = 0
+    for v in vars(obj).values():
+        if isinstance(v, torch.Tensor):
+            n += v.numel() * v.element_size()
+    return n
+
+
+def _evict(cache):
+    while len(cache) > _REV_CACHE_MAX or (len(cache) > 1 and sum(e[2] for e in cache.values()) > _CACHE_MAX_BYTES):
+        cache.popitem(last=False)
 
 
 def reverse_adjacency(adj: torch.Tensor) -> ops.ReverseAdjacency:
     key = (adj.data_ptr(), tuple(adj.shape), adj._version, str(adj.device), adj.dtype)
     hit = _REV_CACHE.get(key)
     if hit is not None:
+        _REV_CACHE.move_to_end(key)
         return hit[0]
     rev = ops.ReverseAdjacency(adj)
-    if len(_REV_CACHE) >= _REV_CACHE_MAX:
-        _REV_CACHE.pop(next(iter(_REV_CACHE)))
-    _REV_CACHE[key] = (rev, adj)  # keep adj alive so the pointer cannot be recycled
+    _REV_CACHE[key] = (rev, adj, _entry_bytes(rev))  # keep adj alive so the pointer cannot be recycled
+    _evict(_REV_CACHE)
     return rev
 
 
-_PLAN_CACHE = {}
+_PLAN_CACHE = collections.OrderedDict()
 
 
 def conv_plan(adj: torch.Tensor, M: int):
@@ -36,11 +54,11 @@ def conv_plan(adj: torch.Tensor, M: int):
     key = (adj.data_ptr(), tuple(adj.shape), adj._version, str(adj.device), adj.dtype, int(M))
     hit = _PLAN_CACHE.get(key)
     if hit is not None:
+        _PLAN_CACHE.move_to_end(key)
         return hit[0]
     plan = ops.ConvPlan(adj, M)
-    if len(_PLAN_CACHE) >= _REV_CACHE_MAX:
-        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-    _PLAN_CACHE[key] = (plan, adj)
+    _PLAN_CACHE[key] = (plan, adj, _entry_bytes(plan))
+    _evict(_PLAN_CACHE)
     return plan
 
 
