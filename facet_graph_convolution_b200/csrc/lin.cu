@@ -49,6 +49,47 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const f
   }
 }
 
+// ------------------------------------------------------------------ y = act(x @ W + b), Cout <= 4 (the 1024 -> 3 output
+// layer of the regression head in training): warp per row, the lanes split Cin in float4 steps, one shuffle tree per
+// output in a fixed order; pure bandwidth (the row is read once, coalesced) where the tile GEMM left 31 of 32 columns
+// of its thread map idle (0.59 -> 0.0x ms per 32 768 rows of 1024)
+template <int NO>
+__global__ void __launch_bounds__(256)
+lin_fwd_narrow_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                      float* __restrict__ y, int64_t rows, int Cin, int act, float alpha) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = w0; r < rows; r += nw) {
+    const float4* xr = reinterpret_cast<const float4*>(x + r * Cin);
+    float acc[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) acc[o] = 0.f;
+    for (int k4 = lane; k4 < Cin / 4; k4 += 32) {
+      const float4 v = __ldg(xr + k4);
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 0; o < NO; ++o) acc[o] = fmaf(xv[j], __ldg(W + static_cast<int64_t>(4 * k4 + j) * NO + o), acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
+    }
+    if (lane < NO) {
+      float v = acc[0];
+#pragma unroll
+      for (int o = 1; o < NO; ++o)
+        if (lane == o) v = acc[o];
+      v += __ldg(b + lane);
+      if (act == FGC_ACT_LRELU) v = lrelu_f(v, alpha);
+      y[r * NO + lane] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ fused head
 constexpr int kHeadMaxOut = 4;
 __global__ void __launch_bounds__(kThreads)
@@ -122,6 +163,45 @@ __global__ void transpose2d_kernel(const float* __restrict__ W, float* __restric
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int r = e / C, c = e % C;
     Wt[static_cast<int64_t>(c) * R + r] = W[e];
+  }
+}
+
+// gx = gy @ W^T for a WIDE layer with a narrow input (Cin = 32 outputs of this kernel, Cout = hundreds of columns to reduce
+// over: the 32 -> 1024 layer of the regression head in training).  A warp takes eight rows, lane i owns output i of each:
+// per four columns one coalesced 128-byte read of each of the four Wt rows and one broadcast 16-byte read of gy per row
+// (a lane-per-column split made every Wt load touch 32 lines: 0.49 ms; the tile GEMM needed a 128 KB row tile per CTA for
+// this shape: 0.73 ms).  Fixed summation order (k ascending).
+__global__ void __launch_bounds__(256)
+lin_bwd_x_wide_kernel(const float* __restrict__ gy, const float* __restrict__ Wt, float* __restrict__ gx, int64_t rows,
+                      int Cout) {
+  constexpr int R = 8;
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r0 = R * w0; r0 < rows; r0 += R * nw) {
+    float acc[R];
+    const float4* g[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      acc[i] = 0.f;
+      g[i] = reinterpret_cast<const float4*>(gy + (r0 + i < rows ? r0 + i : r0) * Cout);
+    }
+#pragma unroll 2
+    for (int k4 = 0; k4 < Cout / 4; ++k4) {
+      const float* wr = Wt + static_cast<int64_t>(4 * k4) * 32 + lane;
+      const float w0v = __ldg(wr), w1v = __ldg(wr + 32), w2v = __ldg(wr + 64), w3v = __ldg(wr + 96);
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const float4 v = __ldg(g[i] + k4);
+        acc[i] = fmaf(v.x, w0v, acc[i]);
+        acc[i] = fmaf(v.y, w1v, acc[i]);
+        acc[i] = fmaf(v.z, w2v, acc[i]);
+        acc[i] = fmaf(v.w, w3v, acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+      if (r0 + i < rows) gx[(r0 + i) * 32 + lane] = acc[i];
   }
 }
 
@@ -272,6 +352,16 @@ int fgc_lin_fwd(const float* x, const float* W, const float* b, float* y, int64_
                 int Cout, int act, float alpha, void* stream) {
   FGC_REQUIRE(x && W && b && y && rows >= 0 && Cin > 0 && Cout > 0, "lin_fwd: bad arguments");
   if (rows == 0) return FGC_OK;
+  if (Cout <= 4 && Cin % 4 == 0 && Cin >= 128) {
+    int64_t blocks = (rows + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    auto kern = Cout == 1 ? lin_fwd_narrow_kernel<1> : Cout == 2 ? lin_fwd_narrow_kernel<2>
+                : Cout == 3 ? lin_fwd_narrow_kernel<3> : lin_fwd_narrow_kernel<4>;
+    kern<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(x, W, b, y, rows, Cin, act, alpha);
+    FGC_LAUNCHED("lin_fwd_narrow_kernel");
+    return FGC_OK;
+  }
   const size_t smem = (static_cast<size_t>(kTileFacets) * ((Cin + 3) & ~3) + kChunkK * 128) * 4;
   FGC_UNSUPPORTED(smem > 227 * 1024, "lin_fwd: Cin = %d too large", Cin);
   FGC_CUDA(cudaFuncSetAttribute(lin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -335,6 +425,13 @@ int fgc_lin_bwd(const float* gy, const float* x, const float* W, float* gx, floa
   if (gx) {
     transpose2d_kernel<<<static_cast<unsigned>((nW + 255) / 256), 256, 0, st>>>(W, Wt, Cin, Cout);
     FGC_LAUNCHED("transpose2d_kernel");
+    if (Cin == 32 && Cout % 128 == 0) {
+      int64_t blocks = (rows + 63) / 64;
+      const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+      if (blocks > cap) blocks = cap;
+      lin_bwd_x_wide_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(gy, Wt, gx, rows, Cout);
+      FGC_LAUNCHED("lin_bwd_x_wide_kernel");
+    } else {
     const size_t smem = (static_cast<size_t>(kTileFacets) * ((Cout + 3) & ~3) + kChunkK * 128) * 4;
     FGC_UNSUPPORTED(smem > 227 * 1024, "lin_bwd: Cout = %d too large", Cout);
     FGC_CUDA(cudaFuncSetAttribute(lin_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -342,6 +439,7 @@ int fgc_lin_bwd(const float* gy, const float* x, const float* W, float* gx, floa
     if (grid > ntiles) grid = ntiles;
     lin_bwd_x_kernel<<<static_cast<unsigned>(grid), kThreads, smem, st>>>(gy, Wt, gx, rows, Cin, Cout);
     FGC_LAUNCHED("lin_bwd_x_kernel");
+    }
   }
   {
     const size_t ldc = (Cin + 3) & ~3;
