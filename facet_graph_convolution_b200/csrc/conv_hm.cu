@@ -423,6 +423,9 @@ conv_hm2_kernel(const __grid_constant__ HmParams p) {
     for (int i = 0; i < 2 * kHAgg; ++i) tc::mbar_init(&bars[H2_ROWS_HI + i], 1);   // TMA: one plane of one warp's stage
     tc::mbar_fence_init();
   }
+  // programmatic dependent launch: the next launch of the layer (or any kernel launched with the attribute) may start its
+  // prologue on an SM as soon as this CTA has left it; it waits (griddepcontrol.wait) before it touches data
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
   if (warp == 5) invtab[lane + 1] = 1.f / static_cast<float>(lane + 1), invtab[0] = 0.f;
   tc::tc_fence_before_sync();
@@ -453,6 +456,9 @@ conv_hm2_kernel(const __grid_constant__ HmParams p) {
       tc::tc_fence_after_sync();
     }
   }
+  // everything below reads what earlier kernels of the stream wrote (image, logit tables, scales, partial y): the weight
+  // image above is the only input that is older (fgc_net_prepare / launch_conv_hm_weights of an earlier launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < 4) {
     // =========================================================== epilogue: Y (TMEM) -> global; warp 0 also issues stage 2
@@ -743,6 +749,13 @@ hm_absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
+// FGC_DISABLE_PDL: launch the convolution kernels fully stream-ordered (no overlap of a launch's prologue with the tail of
+// the previous kernel)
+bool hm_pdl_enabled() {
+  static const bool v = getenv("FGC_DISABLE_PDL") == nullptr;
+  return v;
+}
+
 size_t hm_img_bytes(int64_t rows_img, int nunits) { return static_cast<size_t>(rows_img) * nunits * 256; }
 size_t hm_wt_bytes(int M, int nimg) { return static_cast<size_t>(nimg) * 128 * M * 32 * 4; }
 
@@ -824,7 +837,15 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg,
       hp.ypool = (last && ypool != nullptr) ? ypool + ob * CB : nullptr;
       hp.ymax = last ? ymax : nullptr;
       hp.add_bias = u == 0, hp.accumulate = u > 0, hp.apply_act = last;
-      kern<<<static_cast<unsigned>(grid), threads, smem, st>>>(hp);
+      {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(static_cast<unsigned>(grid)), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = hm_pdl_enabled() ? 1 : 0;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        FGC_CUDA(cudaLaunchKernelEx(&cfg, kern, hp));
+      }
       FGC_LAUNCHED(tag != nullptr ? tag : "conv_hm_kernel");
     }
   return FGC_OK;

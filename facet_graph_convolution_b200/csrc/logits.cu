@@ -297,6 +297,7 @@ constexpr int kPrepWarps = 8;
 // (lane (g,t) then loads one float4 per row and step).
 __global__ void __launch_bounds__(kPrepWarps * 32)
 prep_rows_mma_kernel(const PrepRowsParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the convolution launched next may start its prologue early
   extern __shared__ uint4 wfrag[];             // [Cin/16][3][32]: {b0 hi, b1 hi, b0 lo, b1 lo} of (step, n-block, lane)
   __shared__ float red[kPrepWarps];
   __shared__ float wsc_s;
