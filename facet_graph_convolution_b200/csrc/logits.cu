@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 
 #include "conv_common.cuh"
+#include <stdlib.h>
 #include "conv_launch.cuh"
 
 namespace fgc {
@@ -341,6 +342,8 @@ prep_rows_mma_kernel(const PrepRowsParams p) {
     }
     __syncthreads();
   }
+  // the parameters above are older than the stream's previous kernel; the rows and their max|x| are what it wrote
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   auto scale_exp = [&](int be) {   // exponent of the element's max |x| (clamped so that both scales stay normal)
     unsigned mb = __ldg(p.maxa + be);
     if (p.maxb != nullptr) mb = max(mb, __ldg(p.maxb + be));
@@ -508,7 +511,18 @@ int launch_prep_rows(const float* xa, int lda, int Ca, const float* xb, int ldb,
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const size_t smem = static_cast<size_t>(Cin / 16) * 3 * 32 * 16;
-  prep_rows_mma_kernel<<<static_cast<unsigned>(blocks), kPrepWarps * 32, smem, st>>>(p);
+  {
+    // programmatic stream serialization: the weight-fragment prologue above runs under the previous kernel's tail when that
+    // kernel releases its dependents early (conv_hm2_kernel does); griddepcontrol.wait guards the first dependent read
+    static const bool pdl = getenv("FGC_DISABLE_PDL") == nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(blocks)), cfg.blockDim = dim3(kPrepWarps * 32), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    FGC_CUDA(cudaLaunchKernelEx(&cfg, prep_rows_mma_kernel, p));
+  }
   FGC_LAUNCHED(tag != nullptr ? tag : "prep_rows_kernel");
   return FGC_OK;
 }
