@@ -134,6 +134,8 @@ bool prep_rows_supported(int Ca, int Cb, int M);
 bool mlp_head_tc_supported(int64_t rows, int Cin, int H, int Cout);
 size_t mlp_head_tc_workspace();
 int launch_mlp_head_tc(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* y,
-                       int64_t rows, float alpha, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                       int64_t rows, float alpha, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                       const void* prepared = nullptr);   // prepared: from launch_mlp_head_tc_prepare, or null
+int launch_mlp_head_tc_prepare(const float* W1, void* prepared, size_t prepared_bytes, cudaStream_t st);
 
 }  // namespace fgc

@@ -77,6 +77,7 @@ mlp_head_tc_kernel(const HeadParams p) {
   float* rs = reinterpret_cast<float*>(smem + Cfg::OFF_RS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&bars[H_A_FULL + i], 4), tc::mbar_init(&bars[H_A_FREE + i], 1);
@@ -102,6 +103,9 @@ mlp_head_tc_kernel(const HeadParams p) {
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  // launched with programmatic stream serialization: everything above (weight image, parameter records: older than the
+  // stream's previous kernel) may run under that kernel's tail; the rows and the partial y are read below
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < kHEpi) {
     // =========================================================== epilogue
@@ -278,6 +282,7 @@ mlp_head_tc2_kernel(const HeadParams p) {
   float* rs = reinterpret_cast<float*>(smem + Cfg::OFF_RS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&bars[H_A_FULL + i], 4), tc::mbar_init(&bars[H_A_FREE + i], 1);
@@ -303,6 +308,9 @@ mlp_head_tc2_kernel(const HeadParams p) {
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  // launched with programmatic stream serialization: everything above (weight image, parameter records: older than the
+  // stream's previous kernel) may run under that kernel's tail; the rows and the partial y are read below
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < kHEpi) {
     // =========================================================== epilogue
@@ -519,15 +527,31 @@ bool mlp_head_tc_supported(int64_t rows, int Cin, int H, int Cout) {
 
 size_t mlp_head_tc_workspace() { return 2 * 2 * static_cast<size_t>(HeadCfg::B_PLANE) + 1024; }
 
+// The fp16 image of W1 depends only on the parameters: inference prepares it once (fgc_net_prepare) into a buffer of
+// mlp_head_tc_workspace() bytes and passes it as `prepared` to launch_mlp_head_tc.
+int launch_mlp_head_tc_prepare(const float* W1, void* prepared, size_t prepared_bytes, cudaStream_t st) {
+  Workspace ws(prepared, prepared_bytes);
+  char* img = ws.take<char>(2 * 2 * static_cast<size_t>(HeadCfg::B_PLANE));
+  float* wunscale = ws.take<float>(4);
+  FGC_REQUIRE(ws.ok(), "mlp_head: prepared buffer too small (%zu bytes given, %zu needed)", prepared_bytes, mlp_head_tc_workspace());
+  prep_head_w_kernel<<<16, 1024, 0, st>>>(W1, reinterpret_cast<uint16_t*>(img), wunscale);
+  FGC_LAUNCHED("prep_head_w_kernel");
+  return FGC_OK;
+}
+
 int launch_mlp_head_tc(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* y,
-                       int64_t rows, float alpha, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  Workspace ws(workspace, workspace_bytes);
+                       int64_t rows, float alpha, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                       const void* prepared) {
+  const bool have = prepared != nullptr;
+  Workspace ws(have ? const_cast<void*>(prepared) : workspace, have ? mlp_head_tc_workspace() : workspace_bytes);
   char* img = ws.take<char>(2 * 2 * static_cast<size_t>(HeadCfg::B_PLANE));
   float* wunscale = ws.take<float>(4);
   FGC_REQUIRE(ws.ok(), "mlp_head: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
               mlp_head_tc_workspace());
-  prep_head_w_kernel<<<16, 1024, 0, st>>>(W1, reinterpret_cast<uint16_t*>(img), wunscale);
-  FGC_LAUNCHED("prep_head_w_kernel");
+  if (!have) {
+    prep_head_w_kernel<<<16, 1024, 0, st>>>(W1, reinterpret_cast<uint16_t*>(img), wunscale);
+    FGC_LAUNCHED("prep_head_w_kernel");
+  }
   static const bool one_tile = getenv("FGC_HEAD_V1") != nullptr;   // the one-tile-per-CTA kernel, for comparisons
   const bool fast = alpha >= 0.f && alpha <= 1.f;
   auto kern = one_tile ? (fast ? mlp_head_tc_kernel<true> : mlp_head_tc_kernel<false>)
@@ -541,7 +565,17 @@ int launch_mlp_head_tc(const float* x, const float* W1, const float* b1, const f
   for (int pass = 0; pass < kHH / kHPass; ++pass) {
     p.wimg = reinterpret_cast<const uint4*>(img + static_cast<size_t>(pass) * 2 * HeadCfg::B_PLANE);
     p.b1 = b1 + pass * kHPass, p.W2 = W2 + static_cast<size_t>(pass) * kHPass * 3, p.accumulate = pass > 0;
-    kern<<<static_cast<unsigned>(grid), kHThreads, HeadCfg::SMEM_BYTES, st>>>(p);
+    {
+      static const bool pdl = getenv("FGC_DISABLE_PDL") == nullptr;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(static_cast<unsigned>(grid)), cfg.blockDim = dim3(kHThreads), cfg.dynamicSmemBytes = HeadCfg::SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+      cfg.attrs = attr, cfg.numAttrs = 1;
+      FGC_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    }
     FGC_LAUNCHED("mlp_head_tc_kernel");
   }
   return FGC_OK;

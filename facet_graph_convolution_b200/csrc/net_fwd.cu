@@ -27,6 +27,7 @@ const char* const kPrepTag[kNetConvs] = {"prep_conv1", "prep_conv2", "prep_conv3
 
 struct PreparedLayout {
   size_t off[kNetConvs];
+  size_t head;    // fp16 image of the head's W1 (mlp_head_tc_workspace() bytes)
   size_t total;
   PreparedLayout() {
     size_t o = 256;
@@ -35,6 +36,8 @@ struct PreparedLayout {
       off[l] = o;
       o += align_up(conv_hm_weights_bytes(kCin[l], kCout[l], kNetM), 256);
     }
+    head = o;
+    o += align_up(mlp_head_tc_workspace(), 256);
     total = o;
   }
 };
@@ -92,7 +95,7 @@ int fgc_net_prepare(const float* const* params, int nparams, void* prepared, siz
     int rc = launch_conv_hm_weights(params[5 * l], kNetM, kCout[l], kCin[l], static_cast<char*>(prepared) + L.off[l], st);
     if (rc) return rc;
   }
-  return FGC_OK;
+  return launch_mlp_head_tc_prepare(params[40], static_cast<char*>(prepared) + L.head, mlp_head_tc_workspace(), st);
 }
 
 size_t fgc_net_fwd_workspace(int B, int N0, int K) {
@@ -167,6 +170,9 @@ int fgc_net_fwd(int B, int N0, int K, const float* x, const int32_t* adj0, const
   rc = layer(7, w.u1, 32, mx[6], w.h1, 32, mx[0], R0, N0, adj0, R0, N0, 0, FGC_ACT_LRELU, w.d1, nullptr, nullptr);
   if (rc) return rc;
   // ---- regression head 32 -> 1024 -> 3 (model.py:936-941), hidden activation never materialised
+  if (mlp_head_tc_supported(R0, 32, 1024, 3))   // W1's image comes prepared
+    return launch_mlp_head_tc(w.d1, params[40], params[41], params[42], params[43], y, R0, alpha, w.head, head_ws_bytes(R0), st,
+                              prep + L.head);
   return fgc_mlp_head_fwd(w.d1, params[40], params[41], params[42], params[43], y, R0, 32, 1024, 3, alpha, w.head,
                           head_ws_bytes(R0), stream);
 }
