@@ -367,7 +367,7 @@ __device__ __forceinline__ void hm2_softmax(const Hm2Pre& in, bool recentre, uin
 // fp16 hi/lo rows of the stage-2 B operand.  K order of stage 2 (prep_wt_kernel writes the weights in the same order):
 // atom a = 2 (m >> 1) + h, chunk 4 (m & 1) + t, element 2 (u & 3) + j  <->  weight m, channel 8 (4 h + (u & 3)) + 2 t + j;
 // atom 8 = weight 8 in natural channel order.  The eight lanes of a quarter warp store to eight different chunks.
-template <int M>
+template <int M, bool HALF = false>
 __device__ __forceinline__ void hm2_drain(uint8_t* b3, int f, int g, int t, const float (&acc)[8][4]) {
   using Cfg = HmCfg<M>;
   const int sw = f & 7;
@@ -375,7 +375,7 @@ __device__ __forceinline__ void hm2_drain(uint8_t* b3, int f, int g, int t, cons
   uint8_t* rl = rh + (kHT >> 3) * 1024;                       // lo row 32 + f
   const int chunk = (((g & 1) * 4 + t) ^ sw) << 4;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < (HALF ? 1 : 2); ++h) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -391,19 +391,25 @@ __device__ __forceinline__ void hm2_drain(uint8_t* b3, int f, int g, int t, cons
     // row m = 8 (every lane holds a copy of its 16 channels): lane (g,t) converts channels 8g + 2t, +1
     float e0 = acc[0][2], e1 = acc[0][3];
 #pragma unroll
-    for (int i = 1; i < 8; ++i)
+    for (int i = 1; i < (HALF ? 4 : 8); ++i)
       if (g == i) e0 = acc[i][2], e1 = acc[i][3];
     uint32_t hi, lo;
     split_trunc(e0, e1, hi, lo);
     const int off = 8 * Cfg::ATOM_BYTES + ((g ^ sw) << 4) + t * 4;
-    *reinterpret_cast<uint32_t*>(rh + off) = hi;
-    *reinterpret_cast<uint32_t*>(rl + off) = lo;
+    if (!HALF || g < 4) {
+      *reinterpret_cast<uint32_t*>(rh + off) = hi;
+      *reinterpret_cast<uint32_t*>(rl + off) = lo;
+    }
   }
 }
 
-template <int M, int NG, bool TMA>
+// HALF: the layer aggregates 32 channels (conv2 of the network): the upper half of the 64-channel unit is zeros, so its
+// copies, fragments, MMAs, drain stores and stage-2 K atoms are skipped.
+template <int M, int NG, bool TMA, bool HALF = false>
 __global__ void __launch_bounds__(kH2Threads, 1)
 conv_hm2_kernel(const __grid_constant__ HmParams p) {
+  static_assert(!(HALF && TMA), "the half-unit instantiation uses the cp.async path");
+  constexpr int NUP = HALF ? 2 : 4;   // pairs of 8-channel blocks with data
   using Cfg = Hm2Cfg<M>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR2);
@@ -478,8 +484,10 @@ conv_hm2_kernel(const __grid_constant__ HmParams p) {
           const uint32_t b3 = sb + buf * Cfg::B3_BUF;
 #pragma unroll 1
           for (int a = 0; a < Cfg::NATOM; ++a) {
+            if (HALF && a < 8 && (a & 1)) continue;       // atoms of the upper channel half: all zero
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
+              if (HALF && a == 8 && ks >= 2) continue;    // weight 8, channels 32..63
               const uint64_t bd = tc::smem_desc_k_sw128(b3 + a * Cfg::ATOM_BYTES + ks * 32);
               tc::mma_f16_ts(tmem + Cfg::D_COL + buf * Cfg::ND, tmem + a * 32 + ks * 8, bd, idesc, (a | ks) ? 1u : 0u);
             }
@@ -559,8 +567,9 @@ conv_hm2_kernel(const __grid_constant__ HmParams p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int rr = __shfl_sync(0xffffffffu, row, cq + 4 * i);
-          cp_async16(((i & 1) ? cdst1 : cdst0) + (i >> 1) * 1024 + plane * 2048,
-                     img_c + static_cast<int64_t>(rr) * p.img_ld + plane * 8);
+          if (!HALF || cc < 4)
+            cp_async16(((i & 1) ? cdst1 : cdst0) + (i >> 1) * 1024 + plane * 2048,
+                       img_c + static_cast<int64_t>(rr) * p.img_ld + plane * 8);
         }
         cp_async_commit();
       }
@@ -608,32 +617,32 @@ conv_hm2_kernel(const __grid_constant__ HmParams p) {
       uint32_t bf[4][4];
       wait_plane(m, 0, true);
 #pragma unroll
-      for (int up = 0; up < 4; ++up) ldsm_x4_t(laddr ^ (up << 5), bf[up]);
+      for (int up = 0; up < NUP; ++up) ldsm_x4_t(laddr ^ (up << 5), bf[up]);
       __syncwarp();
       int row = 0;
       if (more) row = prep_rows(r1, idn, P);       // overwrites okm / cnt of P: both consumed above
       if (!TMA && more) copy_plane(row, 0);
       // eight independent accumulators per round (back-to-back MMAs into one accumulator wait for each other)
 #pragma unroll
-      for (int u = 0; u < 8; ++u)   // M = 8: rows g: q_hi.x_hi, rows g+8: q_lo.x_hi
+      for (int u = 0; u < 2 * NUP; ++u)   // M = 8: rows g: q_hi.x_hi, rows g+8: q_lo.x_hi
         hm_mma<FIRST>(acc[u], a[0], a[1], a[2], a[3], bf[u >> 1][2 * (u & 1)], bf[u >> 1][2 * (u & 1) + 1]);
       // TMA writes through the async proxy: the gathers into the plane go out once every fragment register of the plane
       // has been consumed by an MMA, i.e. its ldmatrix reads are complete
       if (TMA && more) copy_plane(row, 0);
       if (M == 9) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 2 * NUP; ++u)
           hm_mma<false>(acc[u], a[4], a[5], a[6], a[7], bf[u >> 1][2 * (u & 1)], bf[u >> 1][2 * (u & 1) + 1]);
       }
       wait_plane(m, 1, more);
 #pragma unroll
-      for (int up = 0; up < 4; ++up) ldsm_x4_t((laddr ^ (up << 5)) + 2048, bf[up]);
+      for (int up = 0; up < NUP; ++up) ldsm_x4_t((laddr ^ (up << 5)) + 2048, bf[up]);
       __syncwarp();
       if (!TMA && more) copy_plane(row, 1);
       const int r2 = row_of(m + 2);
       idn = load_id(m + 2, r2);
 #pragma unroll
-      for (int up = 0; up < 4; ++up) {
+      for (int up = 0; up < NUP; ++up) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int u = 2 * up + j;
@@ -655,7 +664,7 @@ conv_hm2_kernel(const __grid_constant__ HmParams p) {
           if (aw == 0) HM_TR(it, 10);
 #endif
         }
-        hm2_drain<M>(smem + buf * Cfg::B3_BUF, f, g, t, acc);
+        hm2_drain<M, HALF>(smem + buf * Cfg::B3_BUF, f, g, t, acc);
         if (lane == 0) rowinv[(it & 3) * kHT + f] = invtab[cnt];
         if (fi == kHFpw - 1) {
           __syncwarp();
@@ -817,10 +826,12 @@ int launch_conv_hm_core(const void* img, const float* xunscale, const float* lg,
   }
   // rows by TMA gather on request (FGC_TMA_MODES bit 4; slower than cp.async here, see make_hm_img_tmap)
   const bool tma = make_hm_img_tmap(hp.tmap, img, rows_img + 1, nunits);
-  auto kern = tma ? (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, true> : conv_hm2_kernel<9, 2, true>)
-                            : (K <= 16 ? conv_hm2_kernel<8, 1, true> : conv_hm2_kernel<8, 2, true>))
-                  : (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, false> : conv_hm2_kernel<9, 2, false>)
-                            : (K <= 16 ? conv_hm2_kernel<8, 1, false> : conv_hm2_kernel<8, 2, false>));
+  const bool half = Cw == 32 && M == 9 && !tma && getenv("FGC_HM_NO_HALF") == nullptr;
+  auto kern = half ? (K <= 16 ? conv_hm2_kernel<9, 1, false, true> : conv_hm2_kernel<9, 2, false, true>)
+              : tma ? (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, true> : conv_hm2_kernel<9, 2, true>)
+                              : (K <= 16 ? conv_hm2_kernel<8, 1, true> : conv_hm2_kernel<8, 2, true>))
+                    : (M == 9 ? (K <= 16 ? conv_hm2_kernel<9, 1, false> : conv_hm2_kernel<9, 2, false>)
+                              : (K <= 16 ? conv_hm2_kernel<8, 1, false> : conv_hm2_kernel<8, 2, false>));
   const int smem = M == 9 ? Hm2Cfg<9>::SMEM_BYTES2 : Hm2Cfg<8>::SMEM_BYTES2;
   const int threads = kH2Threads;
   FGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
