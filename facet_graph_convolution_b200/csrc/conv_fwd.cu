@@ -291,12 +291,15 @@ conv_fwd_small_kernel(const float* __restrict__ x, const int32_t* __restrict__ a
       ++cnt;
       if (id < 0 || id > N) continue; // id outside the patch: a counted neighbour that contributes zero
       const float* xr = x + (base + id - 1) * CIN;
+      // rows of CIN = 6 floats are 8-byte aligned: three 8-byte loads per neighbour (every load of a thread-per-facet
+      // gather touches 32 different lines, so the load count is what the LSU pays for)
       float xj[CIN];
-#pragma unroll
-      for (int i = 0; i < CIN; ++i) xj[i] = __ldg(xr + i);
       float2 xj2[CIN / 2];
 #pragma unroll
-      for (int i = 0; i < CIN / 2; ++i) xj2[i] = make_float2(xj[2 * i], xj[2 * i + 1]);
+      for (int i = 0; i < CIN / 2; ++i) {
+        xj2[i] = __ldg(reinterpret_cast<const float2*>(xr) + i);
+        xj[2 * i] = xj2[i].x, xj[2 * i + 1] = xj2[i].y;
+      }
       float q[M];
       float mx = -3.4e38f;
 #pragma unroll
