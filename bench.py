@@ -92,12 +92,18 @@ def kernel_bytes(name, n):
     return table.get(name.replace("_tc_kernel", "_kernel"))
 
 
-def measured_traffic(name):
+def measured_traffic(name, rows_per_launch=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-    capture of this workload (profiles/traffic.json, written by profiles/summarize.py), or None."""
+    capture of this workload (profiles/traffic.json, written by profiles/summarize.py), or None.
+    An entry that records the rows of the captured launch is scaled to `rows_per_launch` of this run (the traffic of
+    these kernels is proportional to the rows they process)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t["kernels"].get(name, {}).get("dram_bytes_per_launch")
+        e = t["kernels"].get(name, {})
+        v = e.get("dram_bytes_per_launch")
+        if v is not None and rows_per_launch and e.get("rows_per_launch"):
+            v = int(round(v * rows_per_launch / e["rows_per_launch"]))
+        return v
     except Exception:
         return None
 
@@ -645,7 +651,7 @@ def run_c3(args):
         d = layers[dom]
         main_k = max(d["kernels"], key=lambda k: d["kernels"][k])
         roofline = {"bound": "hbm", "kernel": main_k, "layer": dom, "achieved": d["algorithmic_GBps"], "peak": peak_gbs,
-                    "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": measured_traffic(main_k), "peak_source": peak_src,
+                    "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": measured_traffic(main_k, rows0 / max(1, len(groups))), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_pass"] / max(1, len(groups)),
                     "ms_per_launch": d["ms_per_pass"] / max(1, len(groups)),
                     "note": "dominant LAYER of the pass (its convolution launches + its pre-pass); one 'launch' = the layer over "
