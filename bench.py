@@ -730,18 +730,130 @@ def run_c3(args):
         layer_rec = {"workload": r["config"]["workload"], "facets_per_s": r["value"], "ms_per_step": r["ms_per_step"],
                      "roofline": r["roofline"], "layer": r["layer"],
                      "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in r["kernels"].items()}}
+    # C4 (every rank: the step holds the all-reduce) and C1 (rank 0) beside the headline; a failure here must not
+    # take the headline line with it
+    train_rec, c1_rec = None, None
+    if not args.no_extra:
+        try:
+            train_rec = train_record(rank, world, dev)
+        except Exception as e:  # noqa: BLE001
+            train_rec = {"error": repr(e)[:300]}
+        if rank == 0:
+            try:
+                c1_rec = c1_record(dev)
+            except Exception as e:  # noqa: BLE001
+                c1_rec = {"error": repr(e)[:300]}
     line = None
     if rank == 0:
         line = {"metric": "facets/sec (denoise inference, fp32)", "value": value, "unit": "facets/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "layers": layers,
-                "cpu_baseline": cpu_baseline, "layer": layer_rec,
+                "cpu_baseline": cpu_baseline, "layer": layer_rec, "train": train_rec, "single_mesh": c1_rec,
                 "rows": {"core_facets": total_core, "level0_rows_per_pass": total_rows0,
                          "host_patch_generation_s": t_gen, "patches_this_rank": len(mine)}}
     if world > 1:
         dist.barrier()
     return line
+
+
+
+# ----------------------------------------------------------------------------- sub-records: C4 training step, C1 latency
+def train_record(rank, world, dev, steps=10, warmup=3, batch_size=4):
+    """C4 (BASELINE.json configs[3]): data-parallel training step of the multi-scale network on 8 192-facet patches
+    (`Code/train.py:493-520, 619`): random rotation, forward, faceNormalsLoss on sampled facets, deterministic backward,
+    ONE all-reduce of the flat gradient bucket over NCCL, Adam.  Weak scaling: `batch_size` patches per rank.  Every rank
+    calls this (the all-reduce is a collective); CUDA-event time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from facet_graph_convolution_b200 import _lib, mesh, patches
+    from facet_graph_convolution_b200 import model as fm
+    from facet_graph_convolution_b200 import train as ftrain
+    L = _lib.lib()
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    nq = 64   # 64 x 64 quads = 8 192 triangles per patch
+    batch = []
+    for bi in range(batch_size):
+        P, _ = patches.grid_patches(nq, nq, block=nq, halo=0, K=NET_K, seed=rank * 100 + bi)
+        p = P[0]
+        gt = np.zeros((p.x.shape[0], 3), np.float32)
+        gt[: p.num_real] = p.x[: p.num_real, :3]
+        batch.append((T(p.x[None]), [T(a[None]) for a in p.adjs], T(gt[None])))
+    net = fm.DenoisingNet(6, device=dev, params=net_params())
+    bucket = ftrain.GradBucket(list(net.parameters()))
+    opt = ftrain.Adam(bucket)
+    rng = np.random.RandomState(rank)
+    group = dist.group.WORLD if world > 1 else None
+    for _ in range(warmup):
+        ftrain.train_step(net, batch, bucket, opt, rng, group)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = L.fgc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ftrain.train_step(net, batch, bucket, opt, rng, group)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    facets = batch_size * 2 * nq * nq * world
+    return {"workload": "C4 training step: %d patches/GPU x 8192 level-0 facets, K=%d, M=%d, random rotation, faceNormalsLoss on "
+                        "sampled facets, fwd + deterministic bwd, one NCCL all-reduce of the flat gradient bucket (%d floats = "
+                        "%.2f MB), Adam" % (batch_size, NET_K, NET_M, bucket.flat.numel(), bucket.flat.numel() * 4 / 1e6),
+            "facets_per_s": facets / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "warmup": warmup, "scaling": "weak",
+            "parallelism": "dp%d" % world, "gpu_launches_per_step": (L.fgc_launch_count() - n0) / steps}
+
+
+def c1_record(dev, steps=20, warmup=5):
+    """C1 (BASELINE.json configs[0]): one ~20k-facet mesh (icosphere-5, 20 480 facets, one patch, B = 1) through the
+    network + normalizeTensor and the 60-sweep vertex update (`Code/train.py:100-136, 1467-1557`): latency per mesh."""
+    import torch
+    from facet_graph_convolution_b200 import mesh
+    from facet_graph_convolution_b200 import model as fm
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    V, F = mesh.icosphere(5)
+    Vn = mesh.add_vertex_noise(V, F, 0.3, 0).astype(np.float32)
+    feat = mesh.face_features(Vn, F).astype(np.float32)
+    feat, adj0 = mesh.pad_to_multiple(feat, mesh.dedup_adj(mesh.faces_large_adj(F, NET_K)), 16)
+    adjs = mesh.build_pyramid(adj0, 3, NET_K)
+    e_map, v_e = mesh.edge_maps(F, 20)
+    nreal = F.shape[0]
+    x_d, adjs_d = T(feat[None]), [T(a[None]) for a in adjs]
+    v_d, em_d, ve_d = T(Vn[None]), T(e_map[None]), T(v_e[None])
+    store = fm.VariableStore(dev, params=net_params())
+
+    def fwd_only():
+        with torch.no_grad(), fm.variable_store(store):
+            return fm.normalizeTensor(fm.get_model_reg_multi_scale(x_d, adjs_d, 1.0))
+
+    def vertex(n):
+        with torch.no_grad():
+            return fm.update_position2(v_d, n[:, :nreal].contiguous(), em_d, ve_d, iter_num=60, max_edges=20)
+
+    for _ in range(warmup):
+        vertex(fwd_only())
+    torch.cuda.synchronize()
+    tf, tv = [], []
+    for _ in range(steps):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        n = fwd_only()
+        e1.record()
+        vertex(n)
+        e2.record()
+        torch.cuda.synchronize()
+        tf.append(e0.elapsed_time(e1))
+        tv.append(e1.elapsed_time(e2))
+    ms_f, ms_v = float(np.median(tf)), float(np.median(tv))
+    return {"workload": "C1 single-mesh denoise: icosphere-5 (%d facets, one patch, B=1), network + normalizeTensor, then 60 "
+                        "sweeps of update_position2" % nreal,
+            "facets_per_s_forward": nreal / (ms_f * 1e-3), "ms_forward": ms_f, "ms_vertex_update_60_sweeps": ms_v,
+            "steps": steps, "warmup": warmup}
 
 
 # ----------------------------------------------------------------------------- main
@@ -762,6 +874,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-layer", action="store_true", help="c3: skip the C2 layer record")
+    ap.add_argument("--no-extra", action="store_true", help="c3: skip the C4 training-step and C1 single-mesh records")
     args = ap.parse_args()
     line = run_c2(args) if args.config == "c2" else run_c3(args)
     if line is not None:

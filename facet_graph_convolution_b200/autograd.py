@@ -178,3 +178,19 @@ class FaceNormalsLossFn(torch.autograd.Function):
     def backward(ctx, g):
         (gfn,) = ctx.saved_tensors
         return gfn * g, None
+
+
+
+class PointSetLossFn(torch.autograd.Function):
+    """accuracyLoss / fullLoss (reference Code/train.py:1332-1424): gradient with respect to the predicted points."""
+
+    @staticmethod
+    def forward(ctx, p0, p1, ind0, ind1, mode):
+        loss, gp0 = ops.point_set_loss(p0, p1, ind0, ind1, mode, need_grad=True)
+        ctx.save_for_backward(gp0)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (gp0,) = ctx.saved_tensors
+        return gp0 * g, None, None, None, None

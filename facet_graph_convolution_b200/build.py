@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libfacetconv_b200.so")
-SOURCES = ["c_api.cu", "conv_fwd.cu", "conv_fwd_tc.cu", "conv_mma.cu", "conv_hm.cu", "net_fwd.cu", "logits.cu", "conv_bwd.cu", "conv_bwd_tc.cu", "pointwise.cu", "lin.cu", "lin_tc.cu", "geometry.cu", "mesh_index.cu", "host_graph.cu"]
+SOURCES = ["c_api.cu", "conv_fwd.cu", "conv_fwd_tc.cu", "conv_mma.cu", "conv_hm.cu", "net_fwd.cu", "logits.cu", "conv_bwd.cu", "conv_bwd_tc.cu", "pointwise.cu", "lin.cu", "lin_tc.cu", "geometry.cu", "pointset.cu", "mesh_index.cu", "host_graph.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

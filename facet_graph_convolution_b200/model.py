@@ -216,6 +216,27 @@ def faceNormalsLoss(fn, gt_fn):
     return ops.face_normals_loss(fn, gt_fn)[0].reshape(())
 
 
+def _point_set(P0, P1, ind0, ind1, mode):
+    if _needs_grad(P0):
+        return ag.PointSetLossFn.apply(P0, P1, ind0, ind1, mode)
+    return ops.point_set_loss(P0, P1, ind0, ind1, mode)[0].reshape(())
+
+
+def accuracyLoss(P0, P1, sample_ind):
+    """Drop-in for reference Code/train.py:1332-1370: P0[batch, n0, 3] predicted, P1[batch, n1, 3] ground truth."""
+    return _point_set(P0, P1, sample_ind, None, 0)
+
+
+def fullLoss(P0, P1, sample_ind0, sample_ind1):
+    """Drop-in for reference Code/train.py:1373-1424 (the loss of trainAccuracyNet / trainDoubleLossNet, :781, :1100)."""
+    return _point_set(P0, P1, sample_ind0, sample_ind1, 1)
+
+
+def sampledAccuracyLoss(P0, P1):
+    """Drop-in for reference Code/train.py:1428-1464: both sets flattened over the batch (the reshape at :1441-1442)."""
+    return _point_set(P0.reshape(1, -1, 3), P1.reshape(1, -1, 3), None, None, 0)
+
+
 # ----------------------------------------------------------------------------- network
 def _up_conv(h, adj, out_channels, M, steps, fused_ok):
     """custom_conv2d(custom_upsampling(h, steps), adj, out_channels, M)[0] (reference model.py:902-905, 923-926);

@@ -474,6 +474,29 @@ def face_normals_loss(fn, gt, need_grad=False, gscale=1.0):
     return loss, gfn
 
 
+def point_set_loss(p0, p1, ind0=None, ind1=None, mode=1, need_grad=False):
+    """reference Code/train.py:1332-1370 (accuracyLoss, mode 0) / :1373-1424 (fullLoss, mode 1).
+    p0[batch, n0, 3], p1[batch, n1, 3]; ind0 / ind1 int32 sample rows or None.  Returns (loss[1], d loss / d p0 or None)."""
+    L = _lib.lib()
+    p0, p1 = _f32(p0, "p0"), _f32(p1, "p1")
+    if p0.dim() != 3 or p1.dim() != 3 or p0.shape[2] != 3 or p1.shape[2] != 3 or p0.shape[0] != p1.shape[0]:
+        raise ValueError("point_set_loss: p0[batch, n0, 3] and p1[batch, n1, 3] expected")
+    batch, n0, n1 = p0.shape[0], p0.shape[1], p1.shape[1]
+    ind0 = None if ind0 is None else _i32(ind0, "ind0")
+    ind1 = None if ind1 is None else _i32(ind1, "ind1")
+    for ind, n, nm in ((ind0, n0, "ind0"), (ind1, n1, "ind1")):
+        if ind is not None and ind.numel() and (int(ind.min()) < 0 or int(ind.max()) >= n):
+            raise IndexError("point_set_loss: %s outside [0, %d)" % (nm, n))     # tf.gather raises on the CPU too
+    loss = torch.empty(1, dtype=torch.float32, device=p0.device)
+    gp0 = torch.empty_like(p0) if need_grad else None
+    with torch.cuda.device(p0.device):
+        ws = _ws(L.fgc_point_set_loss_workspace(batch, n0, n1), p0)
+        check(L.fgc_point_set_loss(_p(p0), _p(p1), batch, n0, n1, _p(ind0), 0 if ind0 is None else ind0.numel(), _p(ind1),
+                                   0 if ind1 is None else ind1.numel(), int(mode), _p(loss), _p(gp0), _p(ws), ws.numel(),
+                                   _stream(p0)), "fgc_point_set_loss")
+    return loss, gp0
+
+
 # ----------------------------------------------------------------------------- vertex updates
 def vertex_update_edges(x, normals, edge_map, v_edges, iters=60, lam=1.0 / 18):
     """reference Code/train.py:1467-1557 (update_position2).  x[V,3] -> x[V,3]."""

@@ -259,6 +259,20 @@ FGC_API int fgc_face_normals_loss(const float* fn, const float* gt, float* loss,
                           int64_t rows, float gscale, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* reference Code/train.py:1332-1370 (accuracyLoss, mode 0) and :1373-1424 (fullLoss, mode 1); sampledAccuracyLoss
+ * (:1428-1464) is mode 0 over the batch flattened into one point set with ind0 = NULL.
+ *   p0[batch][n0][3] predicted points, p1[batch][n1][3] ground truth; ind0[ns0] / ind1[ns1] int32 sample rows (device;
+ *   NULL = every row; ind1 is read by mode 1 only).
+ *   loss[0] = 1000 * (mean over (batch, sample) of the thresholded nearest-point distance P0 -> P1
+ *                     + mean of the nearest-point distance P1 -> P0), thresholds 5 / none (mode 0), 5000 / 5000 (mode 1);
+ *   gp0[batch][n0][3] (nullable) = d loss / d p0, accumulated in a fixed order (bit-reproducible).
+ * Nothing of size n0 x n1 is materialised. */
+FGC_API size_t fgc_point_set_loss_workspace(int batch, int64_t n0, int64_t n1);
+FGC_API int fgc_point_set_loss(const float* p0, const float* p1, int batch, int64_t n0, int64_t n1,
+                       const int32_t* ind0 /*nullable*/, int ns0, const int32_t* ind1 /*nullable*/, int ns1,
+                       int mode, float* loss, float* gp0 /*nullable*/, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* ---------------------------------------------------------------- vertex position updates
  * reference Code/train.py:1467-1557 (update_position2): `iters` Jacobi sweeps,
  *   x_i += (1/18) sum_{e in v_edges[i]} sum_{w in (v1,v2)(e)} sum_{f in (f1,f2)(e)} n_f (n_f.(x_w - x_i))

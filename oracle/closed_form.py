@@ -418,3 +418,54 @@ def update_position_ms(x, face_normals_list, faces, v_faces, steps=2, iter_num_l
             x = x + lmbd * (w[..., None] * vfn).sum(axis=1)
         dx_list.append(x - x_init)
     return x, dx_list
+
+
+# ----------------------------------------------------------------------------- point-set losses
+def _nearest(a, c):
+    """min_j |a_i - c_j| and its argmin per batch element -- the two reduce_min of Code/train.py:1355-1357 / :1408-1410
+    without the [batch, n, m] tensor kept.  a[B,n,3], c[B,m,3] -> (dist[B,n], arg[B,n])."""
+    B, n, _ = a.shape
+    dist = np.empty((B, n), a.dtype)
+    arg = np.empty((B, n), np.int64)
+    for b in range(B):
+        for i0 in range(0, n, 512):
+            df = a[b, i0:i0 + 512, None, :] - c[b][None, :, :]
+            d = np.sqrt((df * df).sum(-1))
+            arg[b, i0:i0 + 512] = d.argmin(1)
+            dist[b, i0:i0 + 512] = d.min(1)
+    return dist, arg
+
+
+def point_set_loss(P0, P1, ind0=None, ind1=None, mode="full", dtype=np.float64):
+    """accuracyLoss (Code/train.py:1332-1370, mode "accuracy"), fullLoss (:1373-1424, mode "full") and, with both sets
+    flattened over the batch and no sample, sampledAccuracyLoss (:1428-1464).  Returns (loss, d loss / d P0); the gradient
+    of a minimum goes to its argmin, |x| differentiates to x / |x| (TensorFlow's reduce_min / norm gradients)."""
+    P0, P1 = np.asarray(P0, dtype), np.asarray(P1, dtype)
+    B, n0, _ = P0.shape
+    i0 = np.arange(n0) if ind0 is None else np.asarray(ind0, np.int64)
+    i1 = np.arange(P1.shape[1]) if ind1 is None else np.asarray(ind1, np.int64)
+    g = np.zeros_like(P0)
+    sP0 = P0[:, i0]
+    # precision: the sampled predicted points against every ground-truth point
+    thr_p = 5.0 if mode == "accuracy" else 5000.0
+    dp, jp = _nearest(sP0, P1)
+    keep = dp <= thr_p
+    prec = np.where(keep, dp, 0.0)
+    wp = 1000.0 / prec.size
+    for b in range(B):
+        diff = sP0[b] - P1[b][jp[b]]
+        np.add.at(g[b], i0, (wp * keep[b] / np.where(dp[b] > 0, dp[b], 1.0))[:, None] * diff)
+    if mode == "accuracy":      # every ground-truth point against the SAMPLED predicted points, no threshold
+        dc, jc = _nearest(P1, sP0)
+        comp, keepc, rows = dc, np.ones_like(dc, bool), i0[jc]
+        q = P1
+    else:                       # the sampled ground-truth points against every predicted point
+        q = P1[:, i1]
+        dc, jc = _nearest(q, P0)
+        keepc = dc <= 5000.0
+        comp, rows = np.where(keepc, dc, 0.0), jc
+    wc = 1000.0 / comp.size
+    for b in range(B):
+        diff = P0[b][rows[b]] - q[b]
+        np.add.at(g[b], rows[b], (wc * keepc[b] / np.where(dc[b] > 0, dc[b], 1.0))[:, None] * diff)
+    return 1000.0 * (prec.mean() + comp.mean()), g

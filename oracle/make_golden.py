@@ -544,6 +544,32 @@ def patch_vertex_cases(ref):
     print("wrote patch_vertex_cases", len(im.in_list))
 
 
+def point_loss_cases(ref):
+    """accuracyLoss / fullLoss / sampledAccuracyLoss (Code/train.py:1332-1464) and their gradients with respect to the
+    predicted points, from the reference functions (autograd through the stand-in)."""
+    rs = np.random.RandomState(17)
+    d = {}
+    for tag, batch, n0, n1, ns, spread in (("a", 1, 700, 650, 120, 8.0), ("b", 2, 300, 340, 64, 3.0), ("c", 1, 1500, 1400, 500, 6000.0),
+                                           ("d", 2, 420, 400, 100, 60000.0)):
+        p0 = (rs.rand(batch, n0, 3) * spread).astype(np.float32)
+        p1 = (rs.rand(batch, n1, 3) * spread).astype(np.float32)
+        p1[:, : min(n0, n1) // 2] = p0[:, : min(n0, n1) // 2] + rs.randn(batch, min(n0, n1) // 2, 3).astype(np.float32) * 0.01 * spread
+        i0 = rs.randint(0, n0, ns).astype(np.int32)          # with repetitions, as np.random.randint draws them
+        i1 = rs.randint(0, n1, ns).astype(np.int32)
+        d[tag + "_p0"], d[tag + "_p1"], d[tag + "_i0"], d[tag + "_i1"] = p0, p1, i0, i1
+        for nm, fn in (("acc", lambda x: ref.train.accuracyLoss(x, T(p1), torch.from_numpy(i0.astype(np.int64)))),
+                       ("full", lambda x: ref.train.fullLoss(x, T(p1), torch.from_numpy(i0.astype(np.int64)),
+                                                               torch.from_numpy(i1.astype(np.int64)))),
+                       ("samp", lambda x: ref.train.sampledAccuracyLoss(x, T(p1)))):
+            x = T(p0).requires_grad_(True)
+            loss = fn(x)
+            loss.backward()
+            d["%s_%s_loss" % (tag, nm)] = np.float32(rr.to_np(loss))
+            d["%s_%s_grad" % (tag, nm)] = x.grad.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "point_losses.npz"), **d)
+    print("wrote point_losses")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rr.load()
@@ -568,6 +594,7 @@ def main():
     patch_vertex_cases(ref)
     c1_cases(ref)
     c4_grad_case(ref)
+    point_loss_cases(ref)
 
 
 if __name__ == "__main__":

@@ -140,3 +140,17 @@ def test_closed_form_network_matches_reference_on_c1_patch():
     y = cf.net_forward(g["x1"], adjs, cf.split_net_params(params))
     yn = cf.normalize_tensor(y)
     assert np.abs(yn[0] - g["y_norm1"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_point_set_losses(tag):
+    """oracle restatement of accuracyLoss / fullLoss / sampledAccuracyLoss against the reference's own outputs and
+    autograd gradients (tests/golden/point_losses.npz, oracle/make_golden.py point_loss_cases)."""
+    g = golden("point_losses")
+    p0, p1, i0, i1 = (g[tag + "_" + k] for k in ("p0", "p1", "i0", "i1"))
+    for nm, args in (("acc", (p0, p1, i0, None, "accuracy")), ("full", (p0, p1, i0, i1, "full")),
+                     ("samp", (p0.reshape(1, -1, 3), p1.reshape(1, -1, 3), None, None, "accuracy"))):
+        loss, grad = cf.point_set_loss(*args)
+        ref_l, ref_g = float(g["%s_%s_loss" % (tag, nm)]), g["%s_%s_grad" % (tag, nm)]
+        assert abs(loss - ref_l) <= 2e-6 * abs(ref_l), (tag, nm, loss, ref_l)
+        assert np.abs(grad.reshape(ref_g.shape) - ref_g).max() <= 2e-5 * np.abs(ref_g).max(), (tag, nm)
