@@ -39,12 +39,12 @@ def test_small_ops():
     n = fm.normalizeTensor(T(g["norm_in"])).cpu().numpy()
     assert np.abs(n - g["norm_out"]).max() < 2e-6
     loss = fm.faceNormalsLoss(T(g["loss_fn"]), T(g["loss_gt"])).item()
-    assert abs(loss - float(g["loss"])) < 1e-3
+    assert abs(loss - float(g["loss"])) < 1e-4            # degrees; measured 2e-6 (tests/micro/tolerance_probe.py)
     # gradient of loss(normalizeTensor(n)) through both backward kernels
     nt = T(g["norm_in"]).requires_grad_(True)
     fm.faceNormalsLoss(fm.normalizeTensor(nt), T(g["loss_gt"])).backward()
     ref = g["loss_norm_grad"]
-    assert np.abs(nt.grad.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-3
+    assert np.abs(nt.grad.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-5     # measured 2e-7
     # concat / split / permutation gather are exact copies
     a, b = torch.randn(2, 10, 5, device=dev()), torch.randn(2, 10, 3, device=dev())
     cat = ops.concat2(a, b)
@@ -165,13 +165,13 @@ def test_network_training_gradients():
         y = fm.get_model_reg_multi_scale(T(g["x"]), adjs, 1.0)
     assert np.abs(y.detach().cpu().numpy() - g["y"]).max() < 1e-5
     loss = fm.faceNormalsLoss(fm.normalizeTensor(y), T(g["gt"]))
-    assert abs(loss.item() - float(g["loss"])) < 1e-2
+    assert abs(loss.item() - float(g["loss"])) < 1e-4       # degrees; measured 8e-6 (tests/micro/tolerance_probe.py)
     loss.backward()
     for i, t in enumerate(store.params):
         ref = g["g%02d" % i]
         scale = max(float(np.abs(ref).max()), 1e-3)
         assert t.grad is not None, i
-        assert np.abs(t.grad.cpu().numpy() - ref).max() / scale < 5e-3, (i, store.names[i])
+        assert np.abs(t.grad.cpu().numpy() - ref).max() / scale < 1e-4, (i, store.names[i])   # measured 3e-6
 
 
 def _rand_adj(rs, B, N, K):

@@ -95,7 +95,7 @@ def test_training_step_reduces_loss_and_matches_oracle_loss():
                                     pc.x[None, :, :3].astype(np.float64))
     with torch.no_grad():
         l0 = float(fm.faceNormalsLoss(fm.normalizeTensor(y0), gt))
-    assert abs(l0 - float(ref_loss)) < 1e-2
+    assert abs(l0 - float(ref_loss)) < 1e-3      # degrees, against the fp64 closed form
     plist = list(net.parameters())
     assert sum(t.numel() for t in plist) == 474199           # one 1.9 MB bucket
     bucket = T.GradBucket(plist)
