@@ -95,6 +95,8 @@ SIGNATURES = {
     "fgc_vertex_update_edges_range": (i32, [p, p, p, p, p, i64, i64, i64, i32, i64, i64, f32, p]),
     "fgc_vertex_update_ms_workspace": (sz, [i64, i64]),
     "fgc_vertex_update_ms": (i32, [p, p, p, p, p, i64, i64, i32, i32, i32, i32, p, sz, p]),
+    "fgc_vertex_update_ms_bwd_workspace": (sz, [i64, i64, i32, i32]),
+    "fgc_vertex_update_ms_bwd": (i32, [p, p, p, p, i64, i64, i32, i32, i32, i32, p, p, p, p, p, p, p, p, sz, p]),
     "fgc_conv_fwd_host": (i32, [PS, p, p, p, p, p, p, p, p, i32, i32, f32, i32]),
     "fgc_conv_fwd_bwd_host": (i32, [PS, p, p, p, p, p, p, p, p, p, p, p, p, p, p, p, i32, i32]),
     "fgc_host_release": (None, []),

@@ -194,3 +194,21 @@ class PointSetLossFn(torch.autograd.Function):
     def backward(ctx, g):
         (gp0,) = ctx.saved_tensors
         return gp0 * g, None, None, None, None
+
+
+class VertexUpdateMSFn(torch.autograd.Function):
+    """One scale of update_position_MS (reference Code/train.py:1668-1765) with the gradient TensorFlow derives for it:
+    with respect to the incoming vertices and to this scale's face normals."""
+
+    @staticmethod
+    def forward(ctx, x, normals, faces, v_faces, scale, steps, iters, lists):
+        ctx.save_for_backward(x, normals, faces, v_faces)
+        ctx.cfg = (int(scale), int(steps), int(iters), lists)
+        return ops.vertex_update_ms(x, normals, faces, v_faces, scale, steps, iters)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, normals, faces, v_faces = ctx.saved_tensors
+        scale, steps, iters, lists = ctx.cfg
+        g_in, g_n = ops.vertex_update_ms_bwd(g.contiguous(), x, normals, faces, v_faces, scale, steps, iters, lists)
+        return g_in, g_n.view_as(normals), None, None, None, None, None, None

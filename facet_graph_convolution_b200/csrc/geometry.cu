@@ -280,6 +280,136 @@ __global__ void vertex_update_ms_kernel(const float* __restrict__ xin, float* __
   }
 }
 
+// ------------------------------------------------------------------ vertex update (multi-scale), backward
+// One sweep is  x'_v = x_v + lam_v sum_k (n_k . e_k) n_k,  e_k = c_k - x_v  (k: the faces around v at this scale).
+// With g = dL/dx', h = lam g, a_k = n_k . h, w_k = n_k . e_k:
+//   dL/dx_v = g - sum_k a_k n_k        dL/dn_k += a_k e_k + w_k h        dL/dc_k += a_k n_k
+// The per-slot terms are written out and summed per coarse face / per vertex over index lists in a
+// fixed order (no float atomics): the gradient is bit-reproducible.
+__global__ void ms_bwd_slots_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                    const float* __restrict__ normals, const float* __restrict__ centres,
+                                    const int32_t* __restrict__ v_faces, int64_t V, int64_t Fs, int max_faces,
+                                    int shift, float* __restrict__ gx, float* __restrict__ slot_gn,
+                                    float* __restrict__ slot_gc) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < V;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float x0 = x[3 * i], x1 = x[3 * i + 1], x2 = x[3 * i + 2];
+    const float g0 = g[3 * i], g1 = g[3 * i + 1], g2 = g[3 * i + 2];
+    const int32_t* vf = v_faces + i * max_faces;
+    int numf = 0;
+    for (int s = 0; s < max_faces; ++s) numf += (vf[s] != -1);
+    const float lam = 1.f / static_cast<float>(numf);
+    const float h0 = lam * g0, h1 = lam * g1, h2 = lam * g2;
+    float d0 = g0, d1 = g1, d2 = g2;
+    for (int s = 0; s < max_faces; ++s) {
+      const int f = vf[s];
+      const int64_t Fc = f >> shift;
+      if (f < 0 || Fc >= Fs) continue;       // slots outside the index list: never read
+      const float n0 = normals[3 * Fc], n1 = normals[3 * Fc + 1], n2 = normals[3 * Fc + 2];
+      const float e0 = centres[3 * Fc] - x0, e1 = centres[3 * Fc + 1] - x1, e2 = centres[3 * Fc + 2] - x2;
+      const float w = n0 * e0 + n1 * e1 + n2 * e2;
+      const float a = n0 * h0 + n1 * h1 + n2 * h2;
+      d0 -= a * n0, d1 -= a * n1, d2 -= a * n2;
+      float* sn = slot_gn + (i * max_faces + s) * 3;
+      float* sc = slot_gc + (i * max_faces + s) * 3;
+      sn[0] = a * e0 + w * h0, sn[1] = a * e1 + w * h1, sn[2] = a * e2 + w * h2;
+      sc[0] = a * n0, sc[1] = a * n1, sc[2] = a * n2;
+    }
+    gx[3 * i] = d0, gx[3 * i + 1] = d1, gx[3 * i + 2] = d2;
+  }
+}
+
+// per coarse face: gn += its slots' normal terms; the centre gradient goes down the avg_ignore_zeros tree
+// (the tf.where masks of Code/model.py:799-809 route it) to the fine faces' centres: gfine[f] = dL/d(centre of f)
+__global__ void ms_bwd_faces_kernel(const float* __restrict__ x, const int32_t* __restrict__ faces,
+                                    const int32_t* __restrict__ slot_ptr, const int32_t* __restrict__ slot_id,
+                                    const float* __restrict__ slot_gn, const float* __restrict__ slot_gc,
+                                    float* __restrict__ gn, float* __restrict__ gfine, int64_t Fs, int levels) {
+  const int group = 1 << levels;
+  for (int64_t F = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; F < Fs;
+       F += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    for (int32_t q = slot_ptr[F]; q < slot_ptr[F + 1]; ++q) {
+      const int64_t sl = slot_id[q];
+      a0 += slot_gn[3 * sl], a1 += slot_gn[3 * sl + 1], a2 += slot_gn[3 * sl + 2];
+      c0 += slot_gc[3 * sl], c1 += slot_gc[3 * sl + 1], c2 += slot_gc[3 * sl + 2];
+    }
+    gn[3 * F] += a0, gn[3 * F + 1] += a1, gn[3 * F + 2] += a2;
+    // forward tree (as face_centres_kernel), every level kept: node (level s, index p) at tree[off_s + p]
+    float v[31][3];
+    unsigned zmask = 0;   // bit (off + p): node is all-zero
+    for (int gI = 0; gI < group; ++gI) {
+      const int64_t f = F * group + gI;
+      float c[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int vid = faces[3 * f + t];
+        if (vid >= 0) {
+          c[0] += x[3 * static_cast<int64_t>(vid)];
+          c[1] += x[3 * static_cast<int64_t>(vid) + 1];
+          c[2] += x[3 * static_cast<int64_t>(vid) + 2];
+        }
+      }
+      v[gI][0] = c[0] / 3.f, v[gI][1] = c[1] / 3.f, v[gI][2] = c[2] / 3.f;
+    }
+    int off = 0, n = group;
+    for (int s = 0; s < levels; ++s) {
+      const int nn = n >> 1;
+      for (int p = 0; p < nn; ++p) {
+        const float* u0 = v[off + 2 * p];
+        const float* u1 = v[off + 2 * p + 1];
+        const bool z0 = u0[0] == 0.f && u0[1] == 0.f && u0[2] == 0.f;
+        const bool z1 = u1[0] == 0.f && u1[1] == 0.f && u1[2] == 0.f;
+        if (z0) zmask |= 1u << (off + 2 * p);
+        if (z1) zmask |= 1u << (off + 2 * p + 1);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float a = z0 ? u1[j] : u0[j];
+          const float b = z1 ? u0[j] : u1[j];
+          v[off + n + p][j] = (a + b) / 2.f;
+        }
+      }
+      off += n;
+      n = nn;
+    }
+    // backward: gradients overwrite the node values, root first
+    v[off][0] = c0, v[off][1] = c1, v[off][2] = c2;
+    for (int s = levels - 1; s >= 0; --s) {
+      const int nn = n;       // nodes of level s + 1
+      n <<= 1;                // nodes of level s
+      off -= n;
+      for (int p = 0; p < nn; ++p) {
+        const bool z0 = (zmask >> (off + 2 * p)) & 1u, z1 = (zmask >> (off + 2 * p + 1)) & 1u;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float gh = v[off + n + p][j] / 2.f;   // d mean / d cline0 = d mean / d cline1
+          // cline0 = z0 ? line1 : line0, cline1 = z1 ? line0 : line1
+          v[off + 2 * p][j] = (z0 ? 0.f : gh) + (z1 ? gh : 0.f);
+          v[off + 2 * p + 1][j] = (z0 ? gh : 0.f) + (z1 ? 0.f : gh);
+        }
+      }
+    }
+    for (int gI = 0; gI < group; ++gI) {
+      const int64_t f = F * group + gI;
+      gfine[3 * f] = v[gI][0], gfine[3 * f + 1] = v[gI][1], gfine[3 * f + 2] = v[gI][2];
+    }
+  }
+}
+
+// per vertex: the centres of the faces it is a corner of (index list over `faces`, ascending corner id)
+__global__ void ms_bwd_verts_kernel(const int32_t* __restrict__ vert_ptr, const int32_t* __restrict__ vert_corner,
+                                    const float* __restrict__ gfine, float* __restrict__ gx, int64_t V) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < V;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int32_t q = vert_ptr[i]; q < vert_ptr[i + 1]; ++q) {
+      const int64_t f = vert_corner[q] / 3;
+      a0 += gfine[3 * f] / 3.f, a1 += gfine[3 * f + 1] / 3.f, a2 += gfine[3 * f + 2] / 3.f;
+    }
+    gx[3 * i] += a0, gx[3 * i + 1] += a1, gx[3 * i + 2] += a2;
+  }
+}
+
 static inline unsigned vgrid(int64_t n) {
   int64_t b = (n + 127) / 128;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
@@ -496,6 +626,67 @@ int fgc_vertex_update_ms(const float* x_in, float* x_out, const float* normals, 
                                                       max_faces, levels);
     FGC_LAUNCHED("vertex_update_ms_kernel");
     src = dst;
+  }
+  return FGC_OK;
+}
+
+size_t fgc_vertex_update_ms_bwd_workspace(int64_t V, int64_t N0, int max_faces, int iters) {
+  const size_t v3 = static_cast<size_t>(V) * 3;
+  return ws_bytes(v3 * static_cast<size_t>(iters > 0 ? iters : 1), 4) + 2 * ws_bytes(v3, 4) +
+         2 * ws_bytes(v3 * static_cast<size_t>(max_faces), 4) + 2 * ws_bytes(static_cast<size_t>(N0) * 3, 4) + 1024;
+}
+
+int fgc_vertex_update_ms_bwd(const float* x_in, const float* normals, const int32_t* faces, const int32_t* v_faces,
+                             int64_t V, int64_t N0, int max_faces, int scale, int steps, int iters,
+                             const int32_t* slot_ptr, const int32_t* slot_id, const int32_t* vert_ptr,
+                             const int32_t* vert_corner, const float* g_out, float* g_in, float* g_normals,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  FGC_REQUIRE(x_in && normals && faces && v_faces && slot_ptr && slot_id && vert_ptr && vert_corner && g_out && g_in &&
+                  g_normals && V > 0 && N0 > 0 && iters >= 0 && scale >= 0 && steps > 0 && max_faces > 0,
+              "vertex_update_ms_bwd: bad arguments");
+  const int levels = scale * steps;
+  FGC_UNSUPPORTED(levels > 4, "vertex_update_ms_bwd: at most 16 fine faces per coarse face");
+  FGC_REQUIRE(N0 % (1ll << levels) == 0, "vertex_update_ms_bwd: N0 not divisible by 2^(scale*steps)");
+  cudaStream_t st = as_stream(stream);
+  const int64_t Fs = N0 >> levels;
+  const size_t v3 = static_cast<size_t>(V) * 3;
+  Workspace ws(workspace, workspace_bytes);
+  float* traj = ws.take<float>(v3 * static_cast<size_t>(iters > 0 ? iters : 1));   // x before sweep t
+  float* ga = ws.take<float>(v3);
+  float* gb = ws.take<float>(v3);
+  float* slot_gn = ws.take<float>(v3 * max_faces);
+  float* slot_gc = ws.take<float>(v3 * max_faces);
+  float* centres = ws.take<float>(static_cast<size_t>(N0) * 3);
+  float* gfine = ws.take<float>(static_cast<size_t>(N0) * 3);
+  FGC_REQUIRE(ws.ok(), "vertex_update_ms_bwd: workspace too small");
+  FGC_CUDA(cudaMemsetAsync(g_normals, 0, static_cast<size_t>(Fs) * 12, st));
+  if (iters == 0) {
+    FGC_CUDA(cudaMemcpyAsync(g_in, g_out, v3 * 4, cudaMemcpyDeviceToDevice, st));
+    return FGC_OK;
+  }
+  // the forward trajectory again (the same two kernels as fgc_vertex_update_ms: the same bits)
+  FGC_CUDA(cudaMemcpyAsync(traj, x_in, v3 * 4, cudaMemcpyDeviceToDevice, st));
+  for (int it = 0; it + 1 < iters; ++it) {
+    face_centres_kernel<<<vgrid(Fs), 128, 0, st>>>(traj + it * v3, faces, centres, Fs, levels);
+    FGC_LAUNCHED("face_centres_kernel");
+    vertex_update_ms_kernel<<<vgrid(V), 128, 0, st>>>(traj + it * v3, traj + (it + 1) * v3, normals, centres, v_faces, V, Fs,
+                                                      max_faces, levels);
+    FGC_LAUNCHED("vertex_update_ms_kernel");
+  }
+  const float* g = g_out;
+  for (int it = iters - 1; it >= 0; --it) {
+    float* gnext = (it == 0) ? g_in : ((g == ga) ? gb : ga);
+    const float* x = traj + it * v3;
+    face_centres_kernel<<<vgrid(Fs), 128, 0, st>>>(x, faces, centres, Fs, levels);
+    FGC_LAUNCHED("face_centres_kernel");
+    ms_bwd_slots_kernel<<<vgrid(V), 128, 0, st>>>(x, g, normals, centres, v_faces, V, Fs, max_faces, levels, gnext, slot_gn,
+                                                  slot_gc);
+    FGC_LAUNCHED("ms_bwd_slots_kernel");
+    ms_bwd_faces_kernel<<<vgrid(Fs), 128, 0, st>>>(x, faces, slot_ptr, slot_id, slot_gn, slot_gc, g_normals, gfine, Fs, levels);
+    FGC_LAUNCHED("ms_bwd_faces_kernel");
+    ms_bwd_verts_kernel<<<vgrid(V), 128, 0, st>>>(vert_ptr, vert_corner, gfine, gnext, V);
+    FGC_LAUNCHED("ms_bwd_verts_kernel");
+    g = gnext;
   }
   return FGC_OK;
 }

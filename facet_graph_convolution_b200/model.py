@@ -362,19 +362,27 @@ def update_position2(x, face_normals, edge_map, v_edges, iter_num=20, max_edges=
     return out.reshape(shape)
 
 
-def update_position_MS(x, face_normals_list, faces, v_faces0, coarsening_steps, iter_num_list=(80, 20, 20)):
+def update_position_MS(x, face_normals_list, faces, v_faces0, coarsening_steps, iter_num_list=(80, 20, 20),
+                       index_lists=None):
     """Drop-in for reference Code/train.py:1668-1765.  Scales are visited coarsest first and
     iter_num_list is indexed by the loop counter (the coarsest scale gets iter_num_list[0]).
-    Returns (x[1,V,3], [dx per visited scale])."""
+    Returns (x[1,V,3], [dx per visited scale]).  Differentiable with respect to x and the normals (the vertex-space
+    trainers, train.py:771-781); `index_lists[scale]` = ops.vertex_update_ms_lists(...) lets a trainer build the
+    backward's index lists once per mesh."""
     x = x.reshape(-1, 3)
     scale_num = len(face_normals_list)
     dx_list = []
     for s in range(scale_num):
         cur_scale = scale_num - 1 - s
         x_init = x
-        x = ops.vertex_update_ms(x, face_normals_list[cur_scale].reshape(-1, 3), faces.reshape(-1, 3),
-                                 v_faces0.reshape(x.shape[0], -1), cur_scale, coarsening_steps,
-                                 iter_num_list[s])
+        nrm = face_normals_list[cur_scale].reshape(-1, 3)
+        if _needs_grad(x) or _needs_grad(nrm):
+            lists = None if index_lists is None else index_lists[cur_scale]
+            x = ag.VertexUpdateMSFn.apply(x, nrm, faces.reshape(-1, 3), v_faces0.reshape(x.shape[0], -1), cur_scale,
+                                          coarsening_steps, iter_num_list[s], lists)
+        else:
+            x = ops.vertex_update_ms(x, nrm, faces.reshape(-1, 3), v_faces0.reshape(x.shape[0], -1), cur_scale,
+                                     coarsening_steps, iter_num_list[s])
         dx_list.append(x - x_init)
     return x.unsqueeze(0), dx_list
 

@@ -564,6 +564,47 @@ def vertex_update_ms(x, normals, faces, v_faces, scale, steps=2, iters=20):
     return out
 
 
+def _group_index(keys, valid, nbins):
+    """CSR of the positions where `valid`, grouped by `keys` (ascending position inside a group): (ptr[nbins+1], ids)."""
+    pos = torch.nonzero(valid.reshape(-1)).reshape(-1)
+    k = keys.reshape(-1)[pos].to(torch.int64)
+    order = torch.sort(k, stable=True).indices
+    ptr = torch.zeros(nbins + 1, dtype=torch.int64, device=keys.device)
+    ptr[1:] = torch.cumsum(torch.bincount(k, minlength=nbins), 0)
+    return ptr.to(torch.int32), pos[order].to(torch.int32).contiguous()
+
+
+def vertex_update_ms_lists(faces, v_faces, V, scale, steps=2):
+    """Index lists of fgc_vertex_update_ms_bwd for one scale (depend on the mesh only: build once, reuse every step)."""
+    faces, v_faces = _i32(faces, "faces").reshape(-1, 3), _i32(v_faces, "v_faces").reshape(V, -1)
+    levels = int(scale) * int(steps)
+    Fs = faces.shape[0] >> levels
+    fc = torch.where(v_faces >= 0, v_faces >> levels, torch.full_like(v_faces, -1))
+    slot_ptr, slot_id = _group_index(fc, (fc >= 0) & (fc < Fs), Fs)
+    vert_ptr, vert_corner = _group_index(faces, faces >= 0, V)
+    return slot_ptr, slot_id, vert_ptr, vert_corner
+
+
+def vertex_update_ms_bwd(g_out, x, normals, faces, v_faces, scale, steps=2, iters=20, lists=None):
+    """Backward of vertex_update_ms: (dL/dx_in[V,3], dL/dnormals[Fs,3])."""
+    L = _lib.lib()
+    x, normals, g_out = _f32(x, "x"), _f32(normals, "normals"), _f32(g_out, "g_out")
+    faces, v_faces = _i32(faces, "faces"), _i32(v_faces, "v_faces")
+    V = x.numel() // 3
+    N0 = faces.numel() // 3
+    max_faces = v_faces.numel() // V
+    if lists is None:
+        lists = vertex_update_ms_lists(faces, v_faces, V, scale, steps)
+    slot_ptr, slot_id, vert_ptr, vert_corner = lists
+    g_in, g_n = torch.empty_like(x), torch.empty_like(normals)
+    with torch.cuda.device(x.device):
+        ws = _ws(L.fgc_vertex_update_ms_bwd_workspace(V, N0, max_faces, int(iters)), x)
+        check(L.fgc_vertex_update_ms_bwd(_p(x), _p(normals), _p(faces), _p(v_faces), V, N0, max_faces, int(scale), int(steps),
+                                         int(iters), _p(slot_ptr), _p(slot_id), _p(vert_ptr), _p(vert_corner), _p(g_out),
+                                         _p(g_in), _p(g_n), _p(ws), ws.numel(), _stream(x)), "fgc_vertex_update_ms_bwd")
+    return g_in, g_n
+
+
 # ----------------------------------------------------------------------------- whole-network inference forward
 class NetPrepared:
     """Caller-owned tensor-core weight images of the reference network (fgc_net_prepare): depend only on the 44

@@ -247,3 +247,74 @@ def train_step(net, batch, bucket: GradBucket, opt: Adam, rng: np.random.RandomS
     bucket.all_reduce_mean(group)
     opt.step()
     return total
+
+# ----------------------------------------------------------------------------- vertex-space trainers
+SAMP_NUM = 500               # reference Code/train.py:653, :935
+MS_ITERS = (80, 20, 20)      # reference Code/train.py:771, :1089
+
+
+class VertexPatch:
+    """What one step of the vertex-space trainers feeds (Code/train.py:824-842): face features and adjacency pyramid,
+    noisy and ground-truth vertices, the patch's faces and per-vertex face lists, optionally ground-truth face normals.
+    The index lists of the vertex update's backward depend on the mesh only and are built on first use."""
+
+    def __init__(self, x, adjs, verts, gt_verts, faces, v_faces, gt_normals=None, steps: int = 2):
+        self.x, self.adjs, self.verts, self.gt_verts = x, adjs, verts, gt_verts
+        self.faces, self.v_faces, self.gt_normals, self.steps = faces, v_faces, gt_normals, steps
+        self._lists = None
+
+    def index_lists(self):
+        from . import ops
+        if self._lists is None:
+            V = self.verts.reshape(-1, 3).shape[0]
+            self._lists = [ops.vertex_update_ms_lists(self.faces, self.v_faces, V, sc, self.steps) for sc in range(3)]
+        return self._lists
+
+
+def vertex_loss_on_patch(forward_ms, patch: VertexPatch, rng: np.random.RandomState, samples: int = SAMP_NUM,
+                         augment: bool = True, double_loss: bool = False, iters=MS_ITERS, sample_ids=None):
+    """The objective of trainAccuracyNet (Code/train.py:741-781) and, with `double_loss`, of trainDoubleLossNet
+    (:1060-1102) for one patch: random rotation of the features and of both vertex sets, multi-scale network
+    (`forward_ms(x, adjs)` returns the three heads), normalizeTensor of the FINE head only (:767), update_position_MS
+    over the three heads, fullLoss between the refined and the ground-truth vertices (+ faceNormalsLoss of the fine head).
+    Sample ids are drawn per step with replacement (:833-834) unless given."""
+    from . import model as fm
+    x, verts, gtv, gtn = patch.x, patch.verts, patch.gt_verts, patch.gt_normals
+    if augment:
+        R = torch.from_numpy(rand_rotation_matrix(rng).astype(np.float32)).to(x.device)
+        x, verts, gtv = rotate_features(x, R), rotate_features(verts, R), rotate_features(gtv, R)
+        if gtn is not None:
+            gtn = rotate_features(gtn, R)
+    if sample_ids is None:
+        nv, ng = verts.reshape(-1, 3).shape[0], gtv.reshape(-1, 3).shape[0]
+        sample_ids = (torch.from_numpy(rng.randint(nv, size=samples).astype(np.int32)).to(x.device),
+                      torch.from_numpy(rng.randint(ng, size=samples).astype(np.int32)).to(x.device))
+    n0, n1, n2 = forward_ms(x, patch.adjs)
+    n0 = fm.normalizeTensor(n0)
+    refined, _ = fm.update_position_MS(verts, [n0, n1, n2], patch.faces, patch.v_faces, patch.steps, iter_num_list=iters,
+                                       index_lists=patch.index_lists())
+    loss = fm.fullLoss(refined, gtv.reshape(1, -1, 3), sample_ids[0], sample_ids[1])
+    if double_loss:
+        if gtn is None:
+            raise ValueError("double_loss needs ground-truth face normals")
+        loss = loss + fm.faceNormalsLoss(n0, gtn)
+    return loss
+
+
+def train_step_vertices(net, batch: Sequence[VertexPatch], bucket: GradBucket, opt: Adam, rng: np.random.RandomState,
+                        group=None, samples: int = SAMP_NUM, augment: bool = True, double_loss: bool = False,
+                        iters=MS_ITERS) -> float:
+    """One optimisation step of trainAccuracyNet / trainDoubleLossNet over this rank's patches (the reference steps on
+    one patch at a time, :842; a batch averages the patch losses), then the same single all-reduce + Adam as train_step.
+    `net` is a multi-scale DenoisingNet (three heads)."""
+    for p in bucket.params:
+        p.grad = None
+    total = 0.0
+    for patch in batch:
+        loss = vertex_loss_on_patch(net, patch, rng, samples, augment, double_loss, iters) / len(batch)
+        loss.backward()
+        total += float(loss.detach())
+    bucket.pack()
+    bucket.all_reduce_mean(group)
+    opt.step()
+    return total

@@ -300,6 +300,19 @@ FGC_API int fgc_vertex_update_ms(const float* x_in, float* x_out, const float* n
                          int max_faces, int scale, int steps, int iters, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Backward of fgc_vertex_update_ms (what TensorFlow's autodiff derives for the sweeps of Code/train.py:1724-1758 inside
+ * trainAccuracyNet / trainDoubleLossNet, :771-781, :1089-1102): g_out = dL/dx_out -> g_in[V,3] = dL/dx_in and
+ * g_normals[N0 >> levels, 3] = dL/dnormals (overwritten).  The forward trajectory is recomputed into the workspace
+ * (iters * V * 12 bytes).  Index lists, built once per mesh by the caller, make every sum a fixed-order gather:
+ *   slot_ptr[Fs+1] / slot_id[]       the v_faces slots (v * max_faces + k) that map to coarse face F, ascending;
+ *   vert_ptr[V+1]  / vert_corner[]   the corners (f * 3 + t) of `faces` that are vertex v, ascending. */
+FGC_API size_t fgc_vertex_update_ms_bwd_workspace(int64_t V, int64_t N0, int max_faces, int iters);
+FGC_API int fgc_vertex_update_ms_bwd(const float* x_in, const float* normals, const int32_t* faces, const int32_t* v_faces,
+                             int64_t V, int64_t N0, int max_faces, int scale, int steps, int iters,
+                             const int32_t* slot_ptr, const int32_t* slot_id, const int32_t* vert_ptr,
+                             const int32_t* vert_corner, const float* g_out, float* g_in, float* g_normals,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- index builders
  * GPU versions of the host loops that produce the index tensors above; pure integer work, outputs
  * bit-identical to the reference's (pinned by tests/golden/index_layouts.npz, which the reference

@@ -570,6 +570,72 @@ def point_loss_cases(ref):
     print("wrote point_losses")
 
 
+def ms_train_case(ref):
+    """The objective of the vertex-space trainers on icosphere-2 (Code/train.py:760-781 trainAccuracyNet, :1080-1102
+    trainDoubleLossNet): multi-scale network -> normalizeTensor of the fine head only -> update_position_MS [80,20,20]
+    -> fullLoss (+ faceNormalsLoss), gradients of every parameter by autograd through the reference code; and the
+    gradient of the vertex update alone with respect to its inputs."""
+    from facet_graph_convolution_b200 import mesh
+    K = 16
+    V, F = mesh.icosphere(2)
+    Vn = mesh.add_vertex_noise(V, F, 0.3, 1)
+    im = preprocess(ref, Vn, F, K, multi=True, seed=1)
+    x = im.in_list[0].astype(np.float32)
+    adjs = [a.astype(np.int32) for a in im.adj_list[0]]
+    faces_p = np.asarray(im.faces_list[0]).astype(np.int32)
+    v_faces = np.asarray(im.v_faces_list[0]).astype(np.int32)
+    vpos = np.asarray(im.v_list[0]).astype(np.float32)
+    rs = np.random.RandomState(33)
+    gtv = (vpos * 0.97 + 0.01 * rs.randn(*vpos.shape)).astype(np.float32)
+    gtn = x[:, :, :3] + 0.1 * rs.randn(*x[:, :, :3].shape).astype(np.float32)
+    nrm = np.linalg.norm(gtn, axis=-1, keepdims=True)
+    gtn = np.where(np.abs(x[:, :, :3]).sum(-1, keepdims=True) > 0, gtn / np.maximum(nrm, 1e-9), 0.0).astype(np.float32)
+    nv = vpos.reshape(-1, 3).shape[0]
+    i0 = rs.randint(0, nv, 60).astype(np.int32)
+    i1 = rs.randint(0, nv, 60).astype(np.int32)
+    iters = [80, 20, 20]
+    prov = rr.rng_provider(4321)
+    holder = []
+
+    def provider(shape, stddev, nm):
+        t = T(prov(shape, stddev, nm)).requires_grad_(True)
+        holder.append(t)
+        return t
+
+    ref.tf.variables.reset(provider)
+    vp = T(vpos).requires_grad_(True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ys = ref.model.get_model_reg_multi_scale(T(x), [T(a) for a in adjs], 1.0, multiScale=True)
+    n0 = ref.utils.normalizeTensor(ys[0])
+    heads = [n0, ys[1], ys[2]]
+    for t in heads:
+        t.retain_grad()
+    xo, _ = ref.train.update_position_MS(vp, heads, T(faces_p), T(v_faces), 2, iter_num_list=iters)
+    L64 = lambda a: torch.from_numpy(a.astype(np.int64))
+    points = ref.train.fullLoss(xo, T(gtv), L64(i0), L64(i1))
+    normals = ref.train.faceNormalsLoss(n0, T(gtn))
+    d = dict(x=x, adj0=adjs[0], adj1=adjs[1], adj2=adjs[2], faces=faces_p, v_faces=v_faces, verts_in=vpos, gt_verts=gtv,
+             gt_normals=gtn, ind0=i0, ind1=i1, iters=np.array(iters, np.int32), nparams=np.int32(len(holder)),
+             verts_out=rr.to_np(xo), points_loss=np.float32(points.item()), normals_loss=np.float32(normals.item()),
+             h0=rr.to_np(heads[0]), h1=rr.to_np(heads[1]), h2=rr.to_np(heads[2]))
+    points.backward(retain_graph=True)
+    d["gv_points"] = vp.grad.numpy().copy()
+    for i, t in enumerate(heads):
+        d["gh%d_points" % i] = t.grad.numpy().copy()
+    # the parameters are the draws of rng_provider(4321) in creation order: tests/golden/net_ms_icosphere2.npz holds them
+    chk = np.load(os.path.join(OUT, "net_ms_icosphere2.npz"))
+    for i, t in enumerate(holder):
+        assert np.array_equal(chk["p%02d" % i], t.detach().numpy()), i
+        d["gp%02d" % i] = t.grad.numpy().copy()
+        t.grad = None
+    (points + normals).backward()
+    for i, t in enumerate(holder):          # the double loss: the first layer and the heads (the rest is the sum rule)
+        if i < 5 or i >= len(holder) - 12:
+            d["gd%02d" % i] = t.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "ms_train_icosphere2.npz"), **d)
+    print("wrote ms_train_icosphere2: points", points.item(), "normals", normals.item(), "params", len(holder))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rr.load()
@@ -595,6 +661,7 @@ def main():
     c1_cases(ref)
     c4_grad_case(ref)
     point_loss_cases(ref)
+    ms_train_case(ref)
 
 
 if __name__ == "__main__":
