@@ -31,7 +31,7 @@ def _run(nm, p0, p1, i0, i1):
     else:
         loss = fm.sampledAccuracyLoss(x, T(p1))
     loss.backward()
-    return float(loss), x.grad.cpu().numpy()
+    return float(loss.detach()), x.grad.cpu().numpy()
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
