@@ -126,10 +126,14 @@ bwd_src_kernel(const BwdSrcParams p) {
   const int ldg = (p.Cout + 3) & ~3;
   float* DS = sm;                                   // [32][lda]
   float* GZ = DS + kTileFacets * lda;               // [32][ldg]
+  // the weight chunk of the GEMM phase and the per-warp assignment tables of the per-facet phase share one region:
+  // block barriers separate the phases in both directions (after the GEMM, at the end of the tile loop), and the
+  // 16 KB it saves let two CTAs of the 64-channel layers share an SM (119.8 -> 103.4 KB)
   float* Bs = GZ + kTileFacets * ldg;               // [32][128]
-  float* qs_all = Bs + kChunkK * 128;               // [8][32][QS]
+  float* qs_all = Bs;                               // [8][32][QS]
   float* dq_all = qs_all + kWarps * 32 * QS;        // [8][32][QS]
-  int* nbr_all = reinterpret_cast<int*>(dq_all + kWarps * 32 * QS);  // [8][32]
+  constexpr int kShared = (kChunkK * 128 > 2 * kWarps * 32 * QS) ? kChunkK * 128 : 2 * kWarps * 32 * QS;
+  int* nbr_all = reinterpret_cast<int*>(Bs + kShared);  // [8][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* qs = qs_all + warp * 32 * QS;
@@ -760,7 +764,8 @@ int build_reverse_adj(const int32_t* adj, int B, int N, int K, int32_t* rev_ptr,
 static size_t smem_src(int MP, int M, int Cw, int Cout) {
   const int QS = (MP + 3) / 4 * 4;
   const size_t lda = (M * Cw + 3) & ~3, ldg = (Cout + 3) & ~3;
-  return (kTileFacets * lda + kTileFacets * ldg + kChunkK * 128 + 2 * kWarps * 32 * QS + kWarps * 32) * 4;
+  const size_t shared = std::max<size_t>(kChunkK * 128, 2 * kWarps * 32 * QS);   // weight chunk | assignment tables
+  return (kTileFacets * lda + kTileFacets * ldg + shared + kWarps * 32) * 4;
 }
 static size_t smem_tgt(int MP, int M, int Cout) {
   const int QS = (MP + 3) / 4 * 4;
