@@ -384,6 +384,27 @@ def run_c2(args, as_record=False):
                       "plans are rebuilt from adj inside every call)"}
         L.fgc_host_release()
 
+    # ---- one-shot forward (inference sees an adjacency once: the tile plan is part of the cost) beside the amortised one
+    one_shot = None
+    try:
+        def ev_ms(fn, reps=5):
+            ts = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return float(np.median(ts))
+        one_shot = {"plan_build_ms": ev_ms(lambda: ops.ConvPlan(adj, M_W)),
+                    "forward_planned_ms": ev_ms(lambda: ops.conv_fwd(x, adj, W0, b, u, v, c, plan=plan)),
+                    "forward_plan_free_ms": ev_ms(lambda: ops.conv_fwd(x, adj, W0, b, u, v, c)),
+                    "note": "amortised (training: the plan is built once per adjacency) = forward_planned_ms; one-shot planned "
+                            "= plan_build_ms + forward_planned_ms; the plan-free kernel needs no plan"}
+    except Exception as e:  # noqa: BLE001
+        one_shot = {"error": repr(e)[:200]}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -398,7 +419,7 @@ def run_c2(args, as_record=False):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "kernels": kernels, "layer": layer}
+                "cpu_baseline": cpu_baseline, "kernels": kernels, "layer": layer, "one_shot": one_shot}
     return line
 
 
@@ -728,7 +749,7 @@ def run_c3(args):
         sub.steps, sub.warmup, sub.no_e2e, sub.no_cpu_baseline, sub.impl = 5, 3, True, True, "b200"
         r = run_c2(sub, as_record=True)
         layer_rec = {"workload": r["config"]["workload"], "facets_per_s": r["value"], "ms_per_step": r["ms_per_step"],
-                     "roofline": r["roofline"], "layer": r["layer"],
+                     "roofline": r["roofline"], "layer": r["layer"], "one_shot": r.get("one_shot"),
                      "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in r["kernels"].items()}}
     # C4 (every rank: the step holds the all-reduce) and C1 (rank 0) beside the headline; a failure here must not
     # take the headline line with it

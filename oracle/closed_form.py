@@ -420,6 +420,69 @@ def update_position_ms(x, face_normals_list, faces, v_faces, steps=2, iter_num_l
     return x, dx_list
 
 
+def _pool_avg_ignore_zeros_bwd(x, g, steps=2):
+    """Gradient of pool_avg_ignore_zeros with respect to x[1,N,3] given g[1,N/2**steps,3]: the tf.where masks of
+    Code/model.py:799-809 route it (a zero row's gradient goes to its sibling, which then counts twice)."""
+    levels = [np.asarray(x)]
+    for _ in range(steps):
+        levels.append(pool_avg_ignore_zeros(levels[-1], 1))
+    for lvl in range(steps - 1, -1, -1):
+        px = levels[lvl].reshape(1, -1, 2, 3)
+        z0 = np.all(px[:, :, 0, :] == 0, axis=-1, keepdims=True)
+        z1 = np.all(px[:, :, 1, :] == 0, axis=-1, keepdims=True)
+        gh = g / 2
+        g0 = np.where(z0, 0.0, gh) + np.where(z1, gh, 0.0)
+        g1 = np.where(z0, gh, 0.0) + np.where(z1, 0.0, gh)
+        g = np.stack([g0, g1], axis=2).reshape(1, -1, 3)
+    return g
+
+
+def update_position_ms_bwd(g_out, x, face_normals_list, faces, v_faces, steps=2, iter_num_list=(80, 20, 20),
+                           dtype=np.float64):
+    """Reverse-mode derivative of update_position_ms (what TensorFlow derives for Code/train.py:1724-1758 inside the
+    vertex-space trainers, :771-781): given g_out = dL/dx_out returns (dL/dx_in[V,3], [dL/dnormals per scale, in the order
+    of face_normals_list]).  One sweep is x'_v = x_v + lam_v sum_k (n_k.e_k) n_k with e_k = c_k(x) - x_v."""
+    x = np.asarray(x, dtype).reshape(-1, 3).copy()
+    V = x.shape[0]
+    vf0 = np.asarray(v_faces).reshape(V, -1).astype(np.int64)
+    numf = (vf0 != -1).sum(axis=-1).astype(dtype)
+    with np.errstate(divide="ignore"):
+        lmbd = (1.0 / numf)[:, None]
+    f1 = np.asarray(faces).reshape(-1, 3).astype(np.int64) + 1
+    nscale = len(face_normals_list)
+    tape = []          # (scale, vf, vfn, x before the sweep)
+    for s in range(nscale):
+        cur = nscale - 1 - s
+        fn = np.concatenate([np.zeros((1, 3), dtype), np.asarray(face_normals_list[cur], dtype).reshape(-1, 3)], 0)
+        vf = np.floor_divide(vf0, (2 ** steps) ** cur) + 1
+        vfn = fn[vf]
+        for _ in range(iter_num_list[s]):
+            tape.append((cur, vf, vfn, x))
+            cpos = np.concatenate([np.zeros((1, 3), dtype), update_faces_center(x, faces, steps, dtype)[cur].reshape(-1, 3)], 0)
+            e = cpos[vf] - x[:, None, :]
+            x = x + lmbd * ((vfn * e).sum(-1)[..., None] * vfn).sum(axis=1)
+    g = np.asarray(g_out, dtype).reshape(-1, 3).copy()
+    gn = [np.zeros((np.asarray(t).reshape(-1, 3).shape[0] + 1, 3), dtype) for t in face_normals_list]
+    for cur, vf, vfn, xt in reversed(tape):
+        cents = update_faces_center(xt, faces, steps, dtype)
+        cpos = np.concatenate([np.zeros((1, 3), dtype), cents[cur].reshape(-1, 3)], 0)
+        e = cpos[vf] - xt[:, None, :]
+        h = lmbd * g
+        a = (vfn * h[:, None, :]).sum(-1)                 # n_k . h
+        w = (vfn * e).sum(-1)                             # n_k . e_k
+        np.add.at(gn[cur], vf, a[..., None] * e + w[..., None] * h[:, None, :])
+        gc = np.zeros_like(cpos)
+        np.add.at(gc, vf, a[..., None] * vfn)
+        gx = g - (a[..., None] * vfn).sum(axis=1)
+        g0 = gc[1:][None]
+        for lvl in range(cur, 0, -1):                     # down the pooling pyramid to the fine face centres
+            g0 = _pool_avg_ignore_zeros_bwd(cents[lvl - 1], g0, steps)
+        gv = np.zeros((V + 1, 3), dtype)
+        np.add.at(gv, f1, np.repeat(g0.reshape(-1, 1, 3) / 3.0, 3, axis=1))
+        g = gx + gv[1:]
+    return g, [t[1:] for t in gn]
+
+
 # ----------------------------------------------------------------------------- point-set losses
 def _nearest(a, c):
     """min_j |a_i - c_j| and its argmin per batch element -- the two reduce_min of Code/train.py:1355-1357 / :1408-1410

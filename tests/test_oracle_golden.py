@@ -154,3 +154,21 @@ def test_point_set_losses(tag):
         ref_l, ref_g = float(g["%s_%s_loss" % (tag, nm)]), g["%s_%s_grad" % (tag, nm)]
         assert abs(loss - ref_l) <= 2e-6 * abs(ref_l), (tag, nm, loss, ref_l)
         assert np.abs(grad.reshape(ref_g.shape) - ref_g).max() <= 2e-5 * np.abs(ref_g).max(), (tag, nm)
+
+
+def test_update_position_ms_backward():
+    """oracle reverse-mode of update_position_MS against autograd through the reference (ms_train_icosphere2.npz:
+    gradients of fullLoss(update_position_MS(...)) with respect to the vertices and the three heads)."""
+    g = golden("ms_train_icosphere2")
+    heads = [g["h0"], g["h1"], g["h2"]]
+    iters = [int(i) for i in g["iters"]]
+    xo, _ = cf.update_position_ms(g["verts_in"], heads, g["faces"], g["v_faces"], 2, iters)
+    assert np.abs(xo - g["verts_out"].reshape(-1, 3)).max() < 1e-5
+    loss, gx = cf.point_set_loss(xo[None], g["gt_verts"].astype(np.float64), g["ind0"], g["ind1"], "full")
+    assert abs(loss - float(g["points_loss"])) < 2e-6 * abs(loss)
+    gv, gn = cf.update_position_ms_bwd(gx[0], g["verts_in"], heads, g["faces"], g["v_faces"], 2, iters)
+    # the golden is fp32 autograd through 120 sweeps (measured difference to this fp64 restatement: 2.2e-5 relative)
+    assert np.abs(gv - g["gv_points"].reshape(-1, 3)).max() <= 1e-4 * np.abs(g["gv_points"]).max()
+    for i in range(3):
+        ref = g["gh%d_points" % i].reshape(-1, 3)
+        assert np.abs(gn[i] - ref).max() <= 1e-4 * np.abs(ref).max(), i
