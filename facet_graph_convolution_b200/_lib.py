@@ -88,7 +88,7 @@ SIGNATURES = {
     "fgc_normalize_rows_bwd": (i32, [p, p, p, i64, p, sz, p]),
     "fgc_normalize_rows_segmented": (i32, [p, p, i32, i64, p, p, sz, p]),
     "fgc_face_normals_loss": (i32, [p, p, p, p, i64, f32, p, sz, p]),
-    "fgc_point_set_loss_workspace": (sz, [i32, i64, i64]),
+    "fgc_point_set_loss_workspace": (sz, [i32, i64, i64, i32, i32]),
     "fgc_point_set_loss": (i32, [p, p, i32, i64, i64, p, i32, p, i32, i32, p, p, p, sz, p]),
     "fgc_vertex_update_workspace": (sz, [i64]),
     "fgc_vertex_update_edges": (i32, [p, p, p, p, p, i64, i64, i64, i32, i32, f32, p, sz, p]),

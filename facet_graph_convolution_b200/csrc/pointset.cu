@@ -135,9 +135,11 @@ using namespace fgc;
 
 extern "C" {
 
-size_t fgc_point_set_loss_workspace(int batch, int64_t n0, int64_t n1) {
-  // both terms have at most max(n0, n1) queries per batch element
-  const size_t ev = static_cast<size_t>(batch) * static_cast<size_t>(n0 + n1);
+size_t fgc_point_set_loss_workspace(int batch, int64_t n0, int64_t n1, int ns0, int ns1) {
+  // events: the precision term has ns0 queries per batch element (n0 without a sample), the completeness term n1
+  // (accuracyLoss) or ns1 (fullLoss): sized for the larger
+  const size_t q0 = static_cast<size_t>(ns0 > 0 ? ns0 : n0), q1 = static_cast<size_t>(ns1 > n1 ? ns1 : n1);
+  const size_t ev = static_cast<size_t>(batch) * (q0 + q1);
   return ws_bytes(ev, 8) + ws_bytes(ev, 4) * 2 + ws_bytes(ev * 3, 4) + 1024;
 }
 

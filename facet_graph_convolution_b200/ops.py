@@ -490,9 +490,10 @@ def point_set_loss(p0, p1, ind0=None, ind1=None, mode=1, need_grad=False):
     loss = torch.empty(1, dtype=torch.float32, device=p0.device)
     gp0 = torch.empty_like(p0) if need_grad else None
     with torch.cuda.device(p0.device):
-        ws = _ws(L.fgc_point_set_loss_workspace(batch, n0, n1), p0)
-        check(L.fgc_point_set_loss(_p(p0), _p(p1), batch, n0, n1, _p(ind0), 0 if ind0 is None else ind0.numel(), _p(ind1),
-                                   0 if ind1 is None else ind1.numel(), int(mode), _p(loss), _p(gp0), _p(ws), ws.numel(),
+        ns0, ns1 = (0 if ind0 is None else ind0.numel()), (0 if ind1 is None else ind1.numel())
+        ws = _ws(L.fgc_point_set_loss_workspace(batch, n0, n1, ns0, ns1), p0)
+        check(L.fgc_point_set_loss(_p(p0), _p(p1), batch, n0, n1, _p(ind0), ns0, _p(ind1), ns1, int(mode), _p(loss), _p(gp0),
+                                   _p(ws), ws.numel(),
                                    _stream(p0)), "fgc_point_set_loss")
     return loss, gp0
 

@@ -267,7 +267,7 @@ FGC_API int fgc_face_normals_loss(const float* fn, const float* gt, float* loss,
  *                     + mean of the nearest-point distance P1 -> P0), thresholds 5 / none (mode 0), 5000 / 5000 (mode 1);
  *   gp0[batch][n0][3] (nullable) = d loss / d p0, accumulated in a fixed order (bit-reproducible).
  * Nothing of size n0 x n1 is materialised. */
-FGC_API size_t fgc_point_set_loss_workspace(int batch, int64_t n0, int64_t n1);
+FGC_API size_t fgc_point_set_loss_workspace(int batch, int64_t n0, int64_t n1, int ns0, int ns1);
 FGC_API int fgc_point_set_loss(const float* p0, const float* p1, int batch, int64_t n0, int64_t n1,
                        const int32_t* ind0 /*nullable*/, int ns0, const int32_t* ind1 /*nullable*/, int ns1,
                        int mode, float* loss, float* gp0 /*nullable*/, void* workspace, size_t workspace_bytes,

@@ -90,3 +90,17 @@ def test_bad_sample_index_raises():
     p = T(np.zeros((1, 10, 3), np.float32))
     with pytest.raises(IndexError):
         fm.accuracyLoss(p, p, T(np.array([3, 10], np.int32)))
+
+
+def test_more_samples_than_points():
+    """4 000 sample ids (drawn with replacement, Code/train.py:561 style) over 900 points: the event lists are sized
+    by the sample, not by the point count."""
+    rs = np.random.RandomState(8)
+    p0 = rs.rand(1, 900, 3).astype(np.float32) * 10
+    p1 = rs.rand(1, 800, 3).astype(np.float32) * 10
+    i0, i1 = rs.randint(0, 900, 4000).astype(np.int32), rs.randint(0, 800, 4000).astype(np.int32)
+    for nm, mode in (("full", "full"), ("acc", "accuracy")):
+        loss, grad = _run(nm, p0, p1, i0, i1)
+        ol, og = cf.point_set_loss(p0, p1, i0, i1 if nm == "full" else None, mode)
+        assert abs(loss - ol) <= LOSS_RTOL * abs(ol)
+        assert np.abs(grad - og).max() <= GRAD_RTOL * np.abs(og).max()
