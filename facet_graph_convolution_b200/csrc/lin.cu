@@ -318,6 +318,63 @@ lin_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ gy, floa
 }
 
 
+// Weight gradient of a NARROW layer (Cout <= 4, e.g. the 1024 -> 3 projection of the head): the input rows are the
+// big operand (rows x Cin floats, read once), so thread t owns four input channels, streams its 16 bytes of every
+// row of the chunk and keeps the 4 x Cout sums in registers; the chunk's gy rows sit in shared memory.  Same
+// partial layout and fixed summation order per chunk as lin_bwd_w_kernel.
+constexpr int kNarrowRows = 128;
+__global__ void __launch_bounds__(256)
+lin_bwd_w_narrow_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partW,
+                        float* __restrict__ partB, int64_t rows, int Cin, int Cout, int64_t rows_per_chunk) {
+  __shared__ float G[kNarrowRows * 4];
+  const int chunk = blockIdx.x;
+  const int64_t r_begin = chunk * rows_per_chunk, r_end = min(rows, r_begin + rows_per_chunk);
+  float gb_acc = 0.f;
+  float* pw = partW + static_cast<int64_t>(chunk) * Cin * Cout;
+  for (int cb = 0; cb < Cin; cb += 4 * 256) {
+    // every thread runs every row block (barriers inside); threads past Cin only help staging
+    const int c0 = cb + 4 * static_cast<int>(threadIdx.x);
+    const bool own = c0 < Cin;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[i][o] = 0.f;
+    for (int64_t rb = r_begin; rb < r_end; rb += kNarrowRows) {
+      const int nr = (r_end - rb < kNarrowRows) ? static_cast<int>(r_end - rb) : kNarrowRows;
+      __syncthreads();
+      for (int e = threadIdx.x; e < nr * 4; e += 256) {
+        const int f = e >> 2, o = e & 3;
+        G[e] = (o < Cout) ? __ldg(gy + (rb + f) * Cout + o) : 0.f;
+      }
+      __syncthreads();
+      if (own) {
+#pragma unroll 4
+        for (int f = 0; f < nr; ++f) {
+          const float4 h = __ldg(reinterpret_cast<const float4*>(x + (rb + f) * Cin + c0));
+          const float4 g = *reinterpret_cast<const float4*>(G + 4 * f);
+          const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][0] = fmaf(hv[i], g.x, acc[i][0]);
+            acc[i][1] = fmaf(hv[i], g.y, acc[i][1]);
+            acc[i][2] = fmaf(hv[i], g.z, acc[i][2]);
+            acc[i][3] = fmaf(hv[i], g.w, acc[i][3]);
+          }
+        }
+      }
+      if (cb == 0 && static_cast<int>(threadIdx.x) < Cout)
+        for (int f = 0; f < nr; ++f) gb_acc += G[4 * f + threadIdx.x];
+    }
+    if (own) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        for (int o = 0; o < Cout; ++o) pw[static_cast<int64_t>(c0 + i) * Cout + o] = acc[i][o];
+    }
+  }
+  if (static_cast<int>(threadIdx.x) < Cout) partB[static_cast<int64_t>(chunk) * Cout + threadIdx.x] = gb_acc;
+}
+
 struct LinPlan {
   int os, nslices, chunks;
   int64_t tiles_per_chunk;
@@ -441,7 +498,11 @@ int fgc_lin_bwd(const float* gy, const float* x, const float* W, float* gx, floa
     FGC_LAUNCHED("lin_bwd_x_kernel");
     }
   }
-  {
+  if (Cout <= 4 && Cin % 4 == 0 && Cin >= 256) {
+    const int64_t rows_per_chunk = pl.tiles_per_chunk * kTileFacets;
+    lin_bwd_w_narrow_kernel<<<pl.chunks, 256, 0, st>>>(x, gy, partW, partB, rows, Cin, Cout, rows_per_chunk);
+    FGC_LAUNCHED("lin_bwd_w_narrow_kernel");
+  } else {
     const size_t ldc = (Cin + 3) & ~3;
     const size_t smem = (ldc * pl.os + kTileFacets * ldc + kTileFacets * pl.os) * 4;
     FGC_UNSUPPORTED(smem > 227 * 1024, "lin_bwd: Cin = %d too large", Cin);
