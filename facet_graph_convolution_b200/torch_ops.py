@@ -9,6 +9,8 @@ autograd.  Importing this module registers the ops; `facet_graph_convolution_b20
     gx, gW0, gb, gu, gv, gc = torch.ops.fgc.conv_bwd(gy, x, adj, W0, u, v, c, True)
     p = torch.ops.fgc.pool_max(x, 4);  r = torch.ops.fgc.upsample(x, 4);  n = torch.ops.fgc.normalize_rows(y)
     y = torch.ops.fgc.mlp_head(x, W1, b1, W2, b2, 0.1)
+    loss, _ = torch.ops.fgc.point_set_loss(p0, p1, ind0, ind1, 1)            # fullLoss (train.py:1373-1424), differentiable
+    x1 = torch.ops.fgc.vertex_update_ms(x0, normals, faces, v_faces, scale, 2, 20)   # one scale of update_position_MS
 """
 from __future__ import annotations
 
@@ -164,6 +166,57 @@ def register() -> None:
     def _(x, adj):
         return x.new_empty((adj.shape[0], adj.shape[1], adj.shape[2], x.shape[2]))
 
+    # ---- vertex-space training (reference Code/train.py:1332-1424 losses, :1668-1765 vertex update)
+    @torch.library.custom_op("fgc::point_set_loss", mutates_args=())
+    def point_set_loss(p0: torch.Tensor, p1: torch.Tensor, ind0: torch.Tensor, ind1: torch.Tensor,
+                       mode: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        # empty index tensors = "every row"; returns (loss[1], d loss / d p0)
+        loss, g = ops.point_set_loss(p0, p1, ind0 if ind0.numel() else None, ind1 if ind1.numel() else None, mode,
+                                     need_grad=True)
+        return loss, g
+
+    @point_set_loss.register_fake
+    def _(p0, p1, ind0, ind1, mode):
+        return p0.new_empty((1,)), torch.empty_like(p0)
+
+    def _psl_setup(ctx, inputs, output):
+        ctx.save_for_backward(output[1])
+
+    def _psl_backward(ctx, g_loss, g_grad):
+        return ctx.saved_tensors[0] * g_loss, None, None, None, None
+
+    point_set_loss.register_autograd(_psl_backward, setup_context=_psl_setup)
+
+    @torch.library.custom_op("fgc::vertex_update_ms", mutates_args=())
+    def vertex_update_ms(x: torch.Tensor, normals: torch.Tensor, faces: torch.Tensor, v_faces: torch.Tensor, scale: int,
+                         steps: int, iters: int) -> torch.Tensor:
+        return ops.vertex_update_ms(x, normals, faces, v_faces, scale, steps, iters)
+
+    @vertex_update_ms.register_fake
+    def _(x, normals, faces, v_faces, scale, steps, iters):
+        return torch.empty_like(x)
+
+    @torch.library.custom_op("fgc::vertex_update_ms_bwd", mutates_args=())
+    def vertex_update_ms_bwd(g: torch.Tensor, x: torch.Tensor, normals: torch.Tensor, faces: torch.Tensor,
+                             v_faces: torch.Tensor, scale: int, steps: int, iters: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        return ops.vertex_update_ms_bwd(g.contiguous(), x, normals, faces, v_faces, scale, steps, iters)
+
+    @vertex_update_ms_bwd.register_fake
+    def _(g, x, normals, faces, v_faces, scale, steps, iters):
+        return torch.empty_like(x), torch.empty_like(normals)
+
+    def _vu_setup(ctx, inputs, output):
+        x, normals, faces, v_faces, scale, steps, iters = inputs
+        ctx.save_for_backward(x, normals, faces, v_faces)
+        ctx.cfg = (scale, steps, iters)
+
+    def _vu_backward(ctx, g):
+        x, normals, faces, v_faces = ctx.saved_tensors
+        gx, gn = torch.ops.fgc.vertex_update_ms_bwd(g, x, normals, faces, v_faces, *ctx.cfg)
+        return gx, gn, None, None, None, None, None
+
+    vertex_update_ms.register_autograd(_vu_backward, setup_context=_vu_setup)
+
 
 OP_NAMES = ("conv_fwd", "conv_bwd", "conv_fwd_up", "pool_max", "pool_max_bwd", "upsample", "upsample_bwd", "normalize_rows",
-            "normalize_rows_bwd", "mlp_head", "gather_rows")
+            "normalize_rows_bwd", "mlp_head", "gather_rows", "point_set_loss", "vertex_update_ms", "vertex_update_ms_bwd")

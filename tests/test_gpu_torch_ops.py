@@ -83,3 +83,29 @@ def test_torch_compile_traces_through_the_ops():
     except Exception as e:   # pragma: no cover - dynamo unavailable in this build
         pytest.skip("torch.compile unavailable: %r" % (e,))
     assert torch.equal(y, ops.pool_max(ops.conv_fwd(x, adj, W0, b, u, v, c, True, ops.ACT_LRELU, 0.1), 4) * 2.0)
+
+
+def test_vertex_space_ops_match_the_python_front_end():
+    """fgc::point_set_loss / fgc::vertex_update_ms through the dispatcher (autograd included) == model.fullLoss /
+    model.update_position_MS, bit for bit."""
+    from conftest import golden
+    from facet_graph_convolution_b200 import model as fm
+    g = golden("ms_train_icosphere2")
+    dv = torch.device("cuda:0")
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dv)
+    faces, vf = T(g["faces"]).reshape(-1, 3), T(g["v_faces"]).reshape(-1, g["v_faces"].shape[-1])
+    outs = []
+    for use_op in (False, True):
+        x0 = T(g["verts_in"]).reshape(-1, 3).requires_grad_(True)
+        n1 = T(g["h1"]).reshape(-1, 3).requires_grad_(True)
+        if use_op:
+            x1 = torch.ops.fgc.vertex_update_ms(x0, n1, faces, vf, 1, 2, 20)
+            loss, _ = torch.ops.fgc.point_set_loss(x1.unsqueeze(0), T(g["gt_verts"]), T(g["ind0"]), T(g["ind1"]), 1)
+            loss = loss.reshape(())
+        else:
+            x1, _ = fm.update_position_MS(x0, [torch.zeros(faces.shape[0], 3, device=dv), n1], faces, vf, 2, iter_num_list=[20, 0])
+            loss = fm.fullLoss(x1, T(g["gt_verts"]), T(g["ind0"]), T(g["ind1"]))
+        loss.backward()
+        outs.append((loss.detach().clone(), x0.grad.clone(), n1.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

@@ -37,6 +37,15 @@ def test_shape_inference_on_fake_tensors():
                                    torch.empty(3), 0.1)
         assert tuple(h.shape) == (B, N, 3)
         assert tuple(torch.ops.fgc.gather_rows(x, adj).shape) == (B, N, K, Cin)
+        p0, p1 = torch.empty(1, 50, 3), torch.empty(1, 40, 3)
+        i0 = torch.empty(10, dtype=torch.int32)
+        loss, gp0 = torch.ops.fgc.point_set_loss(p0, p1, i0, i0, 1)
+        assert tuple(loss.shape) == (1,) and tuple(gp0.shape) == (1, 50, 3)
+        xv, nr = torch.empty(30, 3), torch.empty(16, 3)
+        fc, vf = torch.empty(64, 3, dtype=torch.int32), torch.empty(30, 25, dtype=torch.int32)
+        assert tuple(torch.ops.fgc.vertex_update_ms(xv, nr, fc, vf, 1, 2, 20).shape) == (30, 3)
+        gx, gn = torch.ops.fgc.vertex_update_ms_bwd(xv, xv, nr, fc, vf, 1, 2, 20)
+        assert tuple(gx.shape) == (30, 3) and tuple(gn.shape) == (16, 3)
 
 
 def test_cpu_tensors_fail_loudly():
