@@ -565,8 +565,9 @@ def run_c3(args):
     # upload(half) + compute
     n = len(mine)
     if n >= 6:
-        c1, c2 = max(1, n // 10), max(2, (4 * n) // 10)
-        host_e2e = stack([list(range(0, c1)), list(range(c1, c2)), list(range(c2, n))])
+        cuts = sorted({min(n - 1, max(1, (int(pc) * n) // 100)) for pc in args.e2e_split.split(",") if pc})
+        bounds = [0] + cuts + [n]
+        host_e2e = stack([list(range(a, b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a])
     elif n >= 2:
         host_e2e = stack([list(range(0, n // 2)), list(range(n // 2, n))])
     else:
@@ -894,6 +895,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=20_000, help="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-split", default="10,40", help="c3: cumulative percentages at which the end-to-end pass cuts a "
+                    "rank's patches into upload groups (10,40 -> groups of about 1/10, 3/10 and 6/10)")
     ap.add_argument("--no-layer", action="store_true", help="c3: skip the C2 layer record")
     ap.add_argument("--no-extra", action="store_true", help="c3: skip the C4 training-step and C1 single-mesh records")
     args = ap.parse_args()
