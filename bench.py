@@ -725,8 +725,9 @@ def run_c3(args):
             torch.cuda.synchronize()
 
         e2e_pass()
+        e2e_pass()
         barrier()
-        ksteps = max(2, min(args.steps, 10))
+        ksteps = max(2, min(args.steps, 20))
         t0 = time.perf_counter()
         for _ in range(ksteps):
             e2e_pass()
