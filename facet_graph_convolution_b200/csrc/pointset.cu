@@ -19,6 +19,11 @@ namespace {
 constexpr int kQ = 256;        // queries per block (one per thread)
 constexpr int kTile = 1024;    // candidates staged per shared-memory tile
 
+// sample ids outside [0, n) never read out of bounds through the bare C ABI (the Python front end raises before the call)
+__device__ __forceinline__ int64_t clamp_row(int32_t id, int64_t n) {
+  return id < 0 ? 0 : (id >= n ? n - 1 : static_cast<int64_t>(id));
+}
+
 // queries a[b][ia ? ia[i] : i], candidates c[b][ic ? ic[j] : j]; block (x: query group, y: candidate share, z: batch)
 __global__ void __launch_bounds__(kQ)
 nearest_kernel(const float* __restrict__ a, const int32_t* __restrict__ ia, int nq, int64_t stride_a,
@@ -31,7 +36,7 @@ nearest_kernel(const float* __restrict__ a, const int32_t* __restrict__ ia, int 
   const float* cb = c + static_cast<int64_t>(b) * stride_c * 3;
   float ax = 0.f, ay = 0.f, az = 0.f;
   if (q < nq) {
-    const int64_t r = ia ? ia[q] : q;
+    const int64_t r = ia ? clamp_row(ia[q], stride_a) : q;
     ax = ab[r * 3]; ay = ab[r * 3 + 1]; az = ab[r * 3 + 2];
   }
   const int j0 = blockIdx.y * share, j1 = min(nc, j0 + share);
@@ -41,7 +46,7 @@ nearest_kernel(const float* __restrict__ a, const int32_t* __restrict__ ia, int 
     const int n = min(kTile, j1 - t0);
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += kQ) {
-      const int64_t r = ic ? ic[t0 + t] : (t0 + t);
+      const int64_t r = ic ? clamp_row(ic[t0 + t], stride_c) : (t0 + t);
       tile[t] = make_float4(cb[r * 3], cb[r * 3 + 1], cb[r * 3 + 2], 0.f);
     }
     __syncthreads();
@@ -76,7 +81,7 @@ __global__ void events_kernel(const unsigned long long* __restrict__ packed, int
   const int j = static_cast<int>(key & 0xffffffffu);
   const bool kept = thr < 0.f || d <= thr;
   val[e] = kept ? d : 0.f;
-  const int64_t ra = ia ? ia[q] : q, rc = ic ? ic[j] : j;
+  const int64_t ra = ia ? clamp_row(ia[q], stride_a) : q, rc = ic ? clamp_row(ic[j], stride_c) : j;
   const float* pa = a + (static_cast<int64_t>(b) * stride_a + ra) * 3;
   const float* pc = c + (static_cast<int64_t>(b) * stride_c + rc) * 3;
   // d|x - y|/dx = (x - y)/|x - y|; at distance 0 the reference's quotient is 0/0, here the event carries no gradient

@@ -485,7 +485,7 @@ def point_set_loss(p0, p1, ind0=None, ind1=None, mode=1, need_grad=False):
     ind0 = None if ind0 is None else _i32(ind0, "ind0")
     ind1 = None if ind1 is None else _i32(ind1, "ind1")
     for ind, n, nm in ((ind0, n0, "ind0"), (ind1, n1, "ind1")):
-        if ind is not None and ind.numel() and (int(ind.min()) < 0 or int(ind.max()) >= n):
+        if ind is not None and ind.numel() and bool(((ind < 0) | (ind >= n)).any()):      # one host sync per index set
             raise IndexError("point_set_loss: %s outside [0, %d)" % (nm, n))     # tf.gather raises on the CPU too
     loss = torch.empty(1, dtype=torch.float32, device=p0.device)
     gp0 = torch.empty_like(p0) if need_grad else None
