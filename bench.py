@@ -566,8 +566,8 @@ def run_c3(args):
     n = len(mine)
     if n >= 6:
         # measured on one GPU (100 patches): 10,40 -> 10.93 ms, 5,25,60 -> 10.70, 8,30,65 -> 10.68, 5,30 -> 11.44; few
-        # patches per rank (multi-GPU) keep three groups
-        split = args.e2e_split if args.e2e_split != "auto" else ("8,30,65" if n >= 40 else "10,40")
+        # patches per rank (multi-GPU) keep three groups (2 GPUs, 50 patches each: 5.72 ms with three, 5.93 with four)
+        split = args.e2e_split if args.e2e_split != "auto" else ("8,30,65" if n >= 80 else "10,40")
         cuts = sorted({min(n - 1, max(1, (int(pc) * n) // 100)) for pc in split.split(",") if pc})
         bounds = [0] + cuts + [n]
         host_e2e = stack([list(range(a, b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a])
@@ -900,7 +900,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-split", default="auto", help="c3: cumulative percentages at which the end-to-end pass cuts a "
-                    "rank's patches into upload groups (10,40 -> groups of about 1/10, 3/10 and 6/10; auto: 8,30,65 from 40 "
+                    "rank's patches into upload groups (10,40 -> groups of about 1/10, 3/10 and 6/10; auto: 8,30,65 from 80 "
                     "patches per rank, else 10,40)")
     ap.add_argument("--no-layer", action="store_true", help="c3: skip the C2 layer record")
     ap.add_argument("--no-extra", action="store_true", help="c3: skip the C4 training-step and C1 single-mesh records")
