@@ -56,3 +56,20 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises(RuntimeError):
         torch.ops.fgc.conv_fwd(x, adj, torch.zeros(9, 32, 32), torch.zeros(32), torch.zeros(9, 32), torch.zeros(9, 32),
                                torch.zeros(9), True, 0, 0.1)
+
+
+def test_group_index_is_a_stable_csr():
+    """ops._group_index (the index lists of fgc_vertex_update_ms_bwd): positions grouped by key, ascending inside a
+    group, invalid positions dropped -- against a plain Python grouping."""
+    import numpy as np
+    from facet_graph_convolution_b200 import ops
+    rs = np.random.RandomState(2)
+    keys = rs.randint(-1, 7, size=(40, 5)).astype(np.int32)
+    valid = (keys >= 0) & (keys < 6)
+    ptr, ids = ops._group_index(torch.from_numpy(keys), torch.from_numpy(valid), 6)
+    ptr, ids = ptr.numpy(), ids.numpy()
+    flat = keys.reshape(-1)
+    assert ptr[0] == 0 and ptr[-1] == valid.sum() and ptr.dtype == np.int32 and ids.dtype == np.int32
+    for k in range(6):
+        want = [i for i in range(flat.size) if flat[i] == k]
+        assert ids[ptr[k]:ptr[k + 1]].tolist() == want
