@@ -766,7 +766,7 @@ def run_c3(args):
             train_rec = {"error": repr(e)[:300]}
         if rank == 0:
             try:
-                c1_rec = c1_record(dev)
+                c1_rec = c1_record(dev, graph=(world == 1))   # no capture while other ranks wait in a collective
             except Exception as e:  # noqa: BLE001
                 c1_rec = {"error": repr(e)[:300]}
     line = None
@@ -835,7 +835,7 @@ def train_record(rank, world, dev, steps=10, warmup=3, batch_size=4):
             "parallelism": "dp%d" % world, "gpu_launches_per_step": (L.fgc_launch_count() - n0) / steps}
 
 
-def c1_record(dev, steps=20, warmup=5):
+def c1_record(dev, steps=20, warmup=5, graph=True):
     """C1 (BASELINE.json configs[0]): one ~20k-facet mesh (icosphere-5, 20 480 facets, one patch, B = 1) through the
     network + normalizeTensor and the 60-sweep vertex update (`Code/train.py:100-136, 1467-1557`): latency per mesh."""
     import torch
@@ -876,7 +876,36 @@ def c1_record(dev, steps=20, warmup=5):
         tf.append(e0.elapsed_time(e1))
         tv.append(e1.elapsed_time(e2))
     ms_f, ms_v = float(np.median(tf)), float(np.median(tv))
-    return {"workload": "C1 single-mesh denoise: icosphere-5 (%d facets, one patch, B=1), network + normalizeTensor, then 60 "
+    # the same step (about 150 launches: network, normalise, 60 sweeps) captured once and replayed from a CUDA graph
+    graph_ms = None
+    try:
+        if not graph:
+            raise RuntimeError("skipped")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            vertex(fwd_only())
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            x_g = vertex(fwd_only())
+        x_e = vertex(fwd_only())
+        g.replay()
+        torch.cuda.synchronize()
+        if torch.equal(x_g, x_e):
+            tg = []
+            for _ in range(steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                tg.append(e0.elapsed_time(e1))
+            graph_ms = float(np.median(tg))
+    except Exception:  # noqa: BLE001
+        graph_ms = None
+    rec_extra = {"ms_step_eager": ms_f + ms_v, "ms_step_cuda_graph": graph_ms}
+    return {**rec_extra, "workload": "C1 single-mesh denoise: icosphere-5 (%d facets, one patch, B=1), network + normalizeTensor, then 60 "
                         "sweeps of update_position2" % nreal,
             "facets_per_s_forward": nreal / (ms_f * 1e-3), "ms_forward": ms_f, "ms_vertex_update_60_sweeps": ms_v,
             "steps": steps, "warmup": warmup}
