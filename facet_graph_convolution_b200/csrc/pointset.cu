@@ -179,9 +179,11 @@ int fgc_point_set_loss(const float* p0, const float* p1, int batch, int64_t n0, 
   for (int t = 0; t < 2; ++t) {
     const Term& T = terms[t];
     const int qb = (T.nq + kQ - 1) / kQ;
-    // enough candidate shares to fill the machine twice, none shorter than one tile
-    int shares = max(1, min((T.nc + kTile - 1) / kTile, (2 * sms + qb * batch - 1) / (qb * batch)));
-    int share = ((T.nc + shares - 1) / shares + kTile - 1) / kTile * kTile;
+    // enough candidate shares to fill the machine twice, none shorter than 128 candidates (a 500-sample query set over
+    // the ~10 k vertices of a mesh was 22 CTAs with whole-tile shares: ncu, profiles/r6_pointset_summary.md)
+    constexpr int kMinShare = 128;
+    int shares = max(1, min((T.nc + kMinShare - 1) / kMinShare, (2 * sms + qb * batch - 1) / (qb * batch)));
+    int share = ((T.nc + shares - 1) / shares + kMinShare - 1) / kMinShare * kMinShare;
     shares = (T.nc + share - 1) / share;
     nearest_kernel<<<dim3(qb, shares, batch), kQ, 0, st>>>(T.a, T.ia, T.nq, T.stride_a, T.c, T.ic, T.nc, T.stride_c, share,
                                                           packed + off);
