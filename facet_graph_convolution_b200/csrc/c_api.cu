@@ -265,7 +265,7 @@ using namespace fgc;
 
 extern "C" {
 
-int fgc_version(void) { return 101; }
+int fgc_version(void) { return 102; }   // 102: point-set loss, backward of the multi-scale vertex update
 const char* fgc_last_error(void) { return g_err; }
 uint64_t fgc_launch_count(void) { return g_launches.load(); }
 
