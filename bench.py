@@ -792,7 +792,7 @@ def train_record(rank, world, dev, steps=10, warmup=3, batch_size=4):
     calls this (the all-reduce is a collective); CUDA-event time, max over ranks."""
     import torch
     import torch.distributed as dist
-    from facet_graph_convolution_b200 import _lib, mesh, patches
+    from facet_graph_convolution_b200 import _lib, patches
     from facet_graph_convolution_b200 import model as fm
     from facet_graph_convolution_b200 import train as ftrain
     L = _lib.lib()
